@@ -1,0 +1,95 @@
+// b200_internal.cuh -- shared internals of the sm_100a kernels behind include/ggml_b200.h
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "ggml_b200.h"
+
+struct b200_ctx {
+    int          device;
+    cudaStream_t stream;
+    bool         owns_stream;
+    int          sm_count;
+    int          cc_major, cc_minor;
+    // scratch for quantized activations (qs plane, d plane, per-block sums) -- grown on demand
+    void        *ws;
+    size_t       ws_size;
+    // staging for repack at set_tensor / un-repack at get_tensor
+    void        *stage;
+    size_t       stage_size;
+    // options
+    int          opt_pdl;
+    int          opt_gemm;
+    int          opt_gemv_max_n;
+    int64_t      launches;
+    char         err[512];
+};
+
+void b200_set_error(b200_ctx *ctx, const char *fmt, ...);
+
+#define B200_CUDA_TRY(ctx, call)                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            b200_set_error((ctx), "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                           cudaGetErrorString(e__));                                               \
+            (void)cudaGetLastError();                                                              \
+            return B200_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+#define B200_REQUIRE(ctx, cond, code)                                                              \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            b200_set_error((ctx), "%s:%d: requirement failed: %s", __FILE__, __LINE__, #cond);     \
+            return (code);                                                                         \
+        }                                                                                          \
+    } while (0)
+
+int b200_ws_reserve(b200_ctx *ctx, size_t bytes);     // ctx->ws >= bytes
+int b200_stage_reserve(b200_ctx *ctx, size_t bytes);  // ctx->stage >= bytes
+
+__host__ __device__ static inline size_t b200_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- storage geometry of a repacked quantized tensor -----------------------------------------
+static inline int b200_qs_bytes(int type) { return type == B200_TYPE_Q4_0 ? 16 : 32; }
+static inline int b200_wire_bytes(int type) { return type == B200_TYPE_Q4_0 ? B200_Q4_0_BYTES : B200_Q8_0_BYTES; }
+
+// ---- launchers implemented in the .cu files --------------------------------------------------
+int b200_launch_repack(b200_ctx *ctx, int type, void *tensor_dev, int64_t nblocks_total, const void *wire_dev,
+                       int64_t block_off, int64_t nblocks);
+int b200_launch_unrepack(b200_ctx *ctx, int type, const void *tensor_dev, int64_t nblocks_total, void *wire_dev,
+                         int64_t block_off, int64_t nblocks);
+
+struct b200_gemv_params {
+    int            type;
+    const uint8_t *qs;         // qs plane of src0 (already offset to its first block)
+    const __half  *d;          // d plane of src0 (already offset)
+    int64_t        k, m, ne02, ne03;
+    const float   *x;          // src1
+    int64_t        n, ne12, ne13;
+    size_t         nb11, nb12, nb13;
+    float         *dst;        // dense [ne13][ne12][dst_n][m], already offset to this launch's first column
+    int64_t        dst_n;      // columns of the whole dst (>= n when the caller chunks columns)
+    int32_t       *dots;       // non-null: dump per-block int32 partials [n][m][k/32] instead of dst
+};
+int b200_launch_gemv(b200_ctx *ctx, const b200_gemv_params &p);
+
+struct b200_gemm_params {
+    int            type;
+    const uint8_t *qs;
+    const __half  *d;
+    int64_t        k, m;       // one 2-D weight matrix
+    const int8_t  *aq;         // quantized activations, planar [n][k]
+    const __half  *ad;         // [n][k/32]
+    int64_t        n;
+    float         *dst;        // [n][m]
+    int32_t       *dots;       // non-null: dump per-block int32 partials
+};
+int b200_launch_gemm(b200_ctx *ctx, const b200_gemm_params &p);
+bool b200_gemm_available(void);

@@ -1,0 +1,172 @@
+// b200_mul_mat.cu -- the mul_mat entry points of include/ggml_b200.h: argument checks that mirror the
+// reference's asserts (src/ggml.c:11832-11849, src/ggml-quants.c:3473) and dispatch between the decode
+// GEMV (b200_gemv.cu) and the prefill tensor-core GEMM (b200_gemm_tc.cu).  No CPU path exists here.
+#include "b200_internal.cuh"
+
+static bool quant_type_ok(int type) { return type == B200_TYPE_Q4_0 || type == B200_TYPE_Q8_0; }
+
+// n > gemv_max_n goes to the tcgen05 GEMM when it can take the shape, else column chunks through the GEMV.
+static bool use_gemm(const b200_ctx *ctx, const b200_mul_mat_args *a) {
+    if (a->flags & B200_MM_FORCE_GEMV) return false;
+    if (!b200_gemm_available()) return false;
+    if (a->flags & B200_MM_FORCE_GEMM) return true;
+    if (!ctx->opt_gemm) return false;
+    return a->ne11 > ctx->opt_gemv_max_n;
+}
+
+static int run_gemv_chunks(b200_ctx *ctx, const b200_mul_mat_args *a, const uint8_t *qs, const __half *d) {
+    // column chunks of <= 8; each chunk re-streams the weights (only used when the GEMM cannot serve the shape)
+    for (int64_t c0 = 0; c0 < a->ne11; c0 += 8) {
+        b200_gemv_params p;
+        memset(&p, 0, sizeof(p));
+        p.type = a->type;
+        p.qs = qs;
+        p.d = d;
+        p.k = a->ne00;
+        p.m = a->ne01;
+        p.ne02 = a->ne02;
+        p.ne03 = a->ne03;
+        p.x = reinterpret_cast<const float *>(reinterpret_cast<const char *>(a->src1_dev) + c0 * a->nb11);
+        p.n = (a->ne11 - c0) < 8 ? (a->ne11 - c0) : 8;
+        p.ne12 = a->ne12;
+        p.ne13 = a->ne13;
+        p.nb11 = a->nb11;
+        p.nb12 = a->nb12;
+        p.nb13 = a->nb13;
+        p.dst = a->dst_dev + c0 * a->ne01;
+        // dst batch stride must stay ne11*m: tell the kernel the full n for addressing via a second field
+        // (the kernel addresses dst as ((i13*ne12+i12)*n_total + c)*m + row; n_total is carried in dst_n)
+        p.dst_n = a->ne11;
+        int rc = b200_launch_gemv(ctx, p);
+        if (rc != B200_OK) return rc;
+    }
+    return B200_OK;
+}
+
+static int run_gemm(b200_ctx *ctx, const b200_mul_mat_args *a, const uint8_t *qs, const __half *d) {
+    const int64_t k = a->ne00, m = a->ne01, n = a->ne11, nb = k / 32;
+    // scratch: int8 plane [n][k] + fp16 scales [n][nb], per (i12,i13) slice reused
+    const size_t q_bytes = b200_align_up((size_t)n * k, 256);
+    const size_t d_bytes = b200_align_up((size_t)n * nb * 2, 256);
+    int rc = b200_ws_reserve(ctx, q_bytes + d_bytes);
+    if (rc != B200_OK) return rc;
+    int8_t *aq = (int8_t *)ctx->ws;
+    uint16_t *ad = (uint16_t *)((uint8_t *)ctx->ws + q_bytes);
+    const int64_t r2 = a->ne12 / a->ne02, r3 = a->ne13 / a->ne03;
+    const int qsb = b200_qs_bytes(a->type);
+    for (int64_t i13 = 0; i13 < a->ne13; i13++)
+        for (int64_t i12 = 0; i12 < a->ne12; i12++) {
+            const float *x = reinterpret_cast<const float *>(reinterpret_cast<const char *>(a->src1_dev) + i13 * a->nb13 + i12 * a->nb12);
+            rc = b200_quantize_q8_0(ctx, x, k, n, a->nb11, aq, ad);
+            if (rc != B200_OK) return rc;
+            const int64_t wrow0 = ((i13 / r3) * a->ne02 + (i12 / r2)) * m;
+            b200_gemm_params g;
+            memset(&g, 0, sizeof(g));
+            g.type = a->type;
+            g.qs = qs + wrow0 * nb * qsb;
+            g.d = d + wrow0 * nb;
+            g.k = k;
+            g.m = m;
+            g.aq = aq;
+            g.ad = reinterpret_cast<const __half *>(ad);
+            g.n = n;
+            g.dst = a->dst_dev + (i13 * a->ne12 + i12) * n * m;
+            rc = b200_launch_gemm(ctx, g);
+            if (rc != B200_OK) return rc;
+        }
+    return B200_OK;
+}
+
+extern "C" {
+
+int b200_mul_mat(b200_ctx *ctx, const b200_mul_mat_args *a) {
+    B200_REQUIRE(ctx, ctx && a, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, quant_type_ok(a->type), B200_ERR_UNSUPPORTED);
+    B200_REQUIRE(ctx, a->ne00 > 0 && a->ne00 % B200_QK == 0, B200_ERR_INVALID);   // assert(n % qk == 0)
+    B200_REQUIRE(ctx, a->ne01 > 0 && a->ne02 > 0 && a->ne03 > 0, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, a->ne11 > 0 && a->ne12 > 0 && a->ne13 > 0, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, a->ne12 % a->ne02 == 0 && a->ne13 % a->ne03 == 0, B200_ERR_INVALID);  // ggml_can_mul_mat
+    B200_REQUIRE(ctx, a->src0_dev && a->src1_dev && a->dst_dev, B200_ERR_INVALID);
+    const int64_t nb = a->ne00 / B200_QK;
+    const int64_t nblk = nb * a->ne01 * a->ne02 * a->ne03;
+    B200_REQUIRE(ctx, a->src0_block_off >= 0 && a->src0_block_off + nblk <= a->src0_nblocks_total, B200_ERR_INVALID);
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int qsb = b200_qs_bytes(a->type);
+    const uint8_t *qs = (const uint8_t *)a->src0_dev + a->src0_block_off * qsb;
+    const __half *d = (const __half *)((const uint8_t *)a->src0_dev + a->src0_nblocks_total * qsb) + a->src0_block_off;
+    if (use_gemm(ctx, a)) return run_gemm(ctx, a, qs, d);
+    return run_gemv_chunks(ctx, a, qs, d);
+}
+
+int b200_block_dots(b200_ctx *ctx, int type, const void *src0_dev, int64_t k, int64_t m, const float *src1_dev, int64_t n,
+                    int32_t *out_dev, int path) {
+    B200_REQUIRE(ctx, ctx && quant_type_ok(type), B200_ERR_INVALID);
+    B200_REQUIRE(ctx, k > 0 && k % B200_QK == 0 && m > 0 && n > 0, B200_ERR_INVALID);
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int64_t nb = k / 32;
+    const int qsb = b200_qs_bytes(type);
+    const uint8_t *qs = (const uint8_t *)src0_dev;
+    const __half *d = (const __half *)((const uint8_t *)src0_dev + m * nb * qsb);
+    if (path == 0) {
+        for (int64_t c0 = 0; c0 < n; c0 += 8) {
+            b200_gemv_params p;
+            memset(&p, 0, sizeof(p));
+            p.type = type; p.qs = qs; p.d = d; p.k = k; p.m = m; p.ne02 = 1; p.ne03 = 1;
+            p.x = src1_dev + c0 * k;
+            p.n = (n - c0) < 8 ? (n - c0) : 8;
+            p.ne12 = 1; p.ne13 = 1;
+            p.nb11 = (size_t)k * 4; p.nb12 = p.nb11 * n; p.nb13 = p.nb12;
+            p.dst = NULL;
+            p.dst_n = n;
+            p.dots = out_dev + c0 * m * nb;
+            int rc = b200_launch_gemv(ctx, p);
+            if (rc != B200_OK) return rc;
+        }
+        return B200_OK;
+    }
+    B200_REQUIRE(ctx, b200_gemm_available(), B200_ERR_UNSUPPORTED);
+    const size_t q_bytes = b200_align_up((size_t)n * k, 256);
+    const size_t d_bytes = b200_align_up((size_t)n * nb * 2, 256);
+    int rc = b200_ws_reserve(ctx, q_bytes + d_bytes);
+    if (rc != B200_OK) return rc;
+    int8_t *aq = (int8_t *)ctx->ws;
+    uint16_t *ad = (uint16_t *)((uint8_t *)ctx->ws + q_bytes);
+    rc = b200_quantize_q8_0(ctx, src1_dev, k, n, (size_t)k * 4, aq, ad);
+    if (rc != B200_OK) return rc;
+    b200_gemm_params g;
+    memset(&g, 0, sizeof(g));
+    g.type = type; g.qs = qs; g.d = d; g.k = k; g.m = m; g.aq = aq; g.ad = reinterpret_cast<const __half *>(ad); g.n = n;
+    g.dst = NULL;
+    g.dots = out_dev;
+    return b200_launch_gemm(ctx, g);
+}
+
+int b200_mul_mat_host(b200_ctx *ctx, int type, const void *src0_dev, int64_t k, int64_t m, const float *src1_host, int64_t n,
+                      float *dst_host) {
+    B200_REQUIRE(ctx, ctx && quant_type_ok(type), B200_ERR_INVALID);
+    B200_REQUIRE(ctx, k > 0 && k % B200_QK == 0 && m > 0 && n > 0, B200_ERR_INVALID);
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    // host-visible io scratch lives behind the activation scratch (the GEMM path grows ws itself, so use stage)
+    const size_t x_bytes = b200_align_up((size_t)n * k * 4, 256), y_bytes = b200_align_up((size_t)n * m * 4, 256);
+    int rc = b200_stage_reserve(ctx, x_bytes + y_bytes);
+    if (rc != B200_OK) return rc;
+    float *x_dev = (float *)ctx->stage;
+    float *y_dev = (float *)((uint8_t *)ctx->stage + x_bytes);
+    rc = b200_upload_async(ctx, x_dev, src1_host, (size_t)n * k * 4);
+    if (rc != B200_OK) return rc;
+    b200_mul_mat_args a;
+    memset(&a, 0, sizeof(a));
+    a.type = type;
+    a.src0_dev = src0_dev;
+    a.src0_nblocks_total = m * (k / 32);
+    a.ne00 = k; a.ne01 = m; a.ne02 = 1; a.ne03 = 1;
+    a.src1_dev = x_dev;
+    a.ne11 = n; a.ne12 = 1; a.ne13 = 1;
+    a.nb11 = (size_t)k * 4; a.nb12 = a.nb11 * n; a.nb13 = a.nb12;
+    a.dst_dev = y_dev;
+    rc = b200_mul_mat(ctx, &a);
+    if (rc != B200_OK) return rc;
+    return b200_download(ctx, dst_host, y_dev, (size_t)n * m * 4);
+}
+
+}  // extern "C"

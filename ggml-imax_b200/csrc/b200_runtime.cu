@@ -1,0 +1,307 @@
+// b200_runtime.cu -- contexts, device buffers and transfers behind include/ggml_b200.h.
+// Stands in for the buffer/stream plumbing of a ggml backend (src/ggml-backend-impl.h:18-117);
+// no kernels of the hot path live here.
+#include "b200_internal.cuh"
+
+#include <stdarg.h>
+#include <stdlib.h>
+
+static char g_last_error[512] = "";
+
+void b200_set_error(b200_ctx *ctx, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    snprintf(g_last_error, sizeof(g_last_error), "%s", buf);
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s", buf);
+    if (getenv("B200_VERBOSE")) fprintf(stderr, "[ggml_b200] %s\n", buf);
+}
+
+extern "C" {
+
+const char *b200_last_error(const b200_ctx *ctx) { return ctx ? ctx->err : g_last_error; }
+
+int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int b200_device_info(int device, char *name, size_t name_len, size_t *free_bytes, size_t *total_bytes,
+                     int *sm_count, int *cc_major, int *cc_minor) {
+    cudaDeviceProp prop;
+    B200_CUDA_TRY(NULL, cudaGetDeviceProperties(&prop, device));
+    if (name && name_len) snprintf(name, name_len, "%s", prop.name);
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (free_bytes || total_bytes) {
+        int cur = 0;
+        B200_CUDA_TRY(NULL, cudaGetDevice(&cur));
+        B200_CUDA_TRY(NULL, cudaSetDevice(device));
+        size_t f = 0, t = 0;
+        B200_CUDA_TRY(NULL, cudaMemGetInfo(&f, &t));
+        if (free_bytes) *free_bytes = f;
+        if (total_bytes) *total_bytes = t;
+        B200_CUDA_TRY(NULL, cudaSetDevice(cur));
+    }
+    return B200_OK;
+}
+
+static int ctx_create_common(int device, void *stream, bool own, b200_ctx **out) {
+    if (!out) return B200_ERR_INVALID;
+    *out = NULL;
+    int n = b200_device_count();
+    if (n <= 0) {
+        b200_set_error(NULL, "no CUDA device visible: the B200 backend has no CPU fallback");
+        return B200_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) {
+        b200_set_error(NULL, "device %d out of range (0..%d)", device, n - 1);
+        return B200_ERR_INVALID;
+    }
+    cudaDeviceProp prop;
+    B200_CUDA_TRY(NULL, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        b200_set_error(NULL, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major,
+                       prop.minor);
+        return B200_ERR_UNSUPPORTED;
+    }
+    b200_ctx *ctx = (b200_ctx *)calloc(1, sizeof(b200_ctx));
+    if (!ctx) return B200_ERR_ALLOC;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    ctx->opt_pdl = getenv("B200_NO_PDL") ? 0 : 1;
+    ctx->opt_gemm = getenv("B200_NO_GEMM") ? 0 : 1;
+    ctx->opt_gemv_max_n = 8;
+    B200_CUDA_TRY(ctx, cudaSetDevice(device));
+    if (own) {
+        cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            b200_set_error(NULL, "cudaStreamCreate: %s", cudaGetErrorString(e));
+            free(ctx);
+            return B200_ERR_CUDA;
+        }
+        ctx->owns_stream = true;
+    } else {
+        ctx->stream = (cudaStream_t)stream;
+        ctx->owns_stream = false;
+    }
+    *out = ctx;
+    return B200_OK;
+}
+
+int b200_ctx_create(int device, b200_ctx **out) { return ctx_create_common(device, NULL, true, out); }
+int b200_ctx_create_on_stream(int device, void *cuda_stream, b200_ctx **out) {
+    return ctx_create_common(device, cuda_stream, false, out);
+}
+
+void b200_ctx_destroy(b200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    free(ctx);
+}
+
+void *b200_ctx_stream(const b200_ctx *ctx) { return ctx ? (void *)ctx->stream : NULL; }
+int b200_ctx_device(const b200_ctx *ctx) { return ctx ? ctx->device : -1; }
+int64_t b200_ctx_launch_count(const b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int b200_ctx_set_option(b200_ctx *ctx, const char *key, int64_t value) {
+    if (!ctx || !key) return B200_ERR_INVALID;
+    if (!strcmp(key, "pdl")) { ctx->opt_pdl = value != 0; return B200_OK; }
+    if (!strcmp(key, "gemm")) { ctx->opt_gemm = value != 0; return B200_OK; }
+    if (!strcmp(key, "gemv_max_n")) {
+        if (value < 1 || value > 8) return B200_ERR_INVALID;
+        ctx->opt_gemv_max_n = (int)value;
+        return B200_OK;
+    }
+    b200_set_error(ctx, "unknown option '%s'", key);
+    return B200_ERR_INVALID;
+}
+
+int b200_malloc(b200_ctx *ctx, void **dptr, size_t size) {
+    B200_REQUIRE(ctx, ctx && dptr, B200_ERR_INVALID);
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(dptr, size ? size : 1);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        b200_set_error(ctx, "cudaMalloc(%zu) failed: %s", size, cudaGetErrorString(e));
+        *dptr = NULL;
+        return B200_ERR_ALLOC;
+    }
+    return B200_OK;
+}
+
+int b200_free(b200_ctx *ctx, void *dptr) {
+    B200_REQUIRE(ctx, ctx != NULL, B200_ERR_INVALID);
+    if (!dptr) return B200_OK;
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    B200_CUDA_TRY(ctx, cudaFree(dptr));
+    return B200_OK;
+}
+
+int b200_memset(b200_ctx *ctx, void *dptr, int value, size_t size) {
+    B200_REQUIRE(ctx, ctx != NULL, B200_ERR_INVALID);
+    if (!size) return B200_OK;
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, cudaMemsetAsync(dptr, value, size, ctx->stream));
+    B200_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+int b200_upload_async(b200_ctx *ctx, void *dst_dev, const void *src_host, size_t size) {
+    B200_REQUIRE(ctx, ctx != NULL, B200_ERR_INVALID);
+    if (!size) return B200_OK;
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, cudaMemcpyAsync(dst_dev, src_host, size, cudaMemcpyHostToDevice, ctx->stream));
+    return B200_OK;
+}
+
+int b200_download_async(b200_ctx *ctx, void *dst_host, const void *src_dev, size_t size) {
+    B200_REQUIRE(ctx, ctx != NULL, B200_ERR_INVALID);
+    if (!size) return B200_OK;
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, cudaMemcpyAsync(dst_host, src_dev, size, cudaMemcpyDeviceToHost, ctx->stream));
+    return B200_OK;
+}
+
+int b200_upload(b200_ctx *ctx, void *dst_dev, const void *src_host, size_t size) {
+    int rc = b200_upload_async(ctx, dst_dev, src_host, size);
+    if (rc != B200_OK) return rc;
+    B200_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+int b200_download(b200_ctx *ctx, void *dst_host, const void *src_dev, size_t size) {
+    int rc = b200_download_async(ctx, dst_host, src_dev, size);
+    if (rc != B200_OK) return rc;
+    B200_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+int b200_copy_d2d(b200_ctx *ctx, void *dst_dev, const void *src_dev, size_t size) {
+    B200_REQUIRE(ctx, ctx != NULL, B200_ERR_INVALID);
+    if (!size) return B200_OK;
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, cudaMemcpyAsync(dst_dev, src_dev, size, cudaMemcpyDeviceToDevice, ctx->stream));
+    return B200_OK;
+}
+
+int b200_synchronize(b200_ctx *ctx) {
+    B200_REQUIRE(ctx, ctx != NULL, B200_ERR_INVALID);
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+struct b200_graph {
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    int device;
+};
+
+int b200_graph_begin(b200_ctx *ctx) {
+    B200_REQUIRE(ctx, ctx != NULL, B200_ERR_INVALID);
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    return B200_OK;
+}
+
+int b200_graph_end(b200_ctx *ctx, b200_graph **out) {
+    B200_REQUIRE(ctx, ctx && out, B200_ERR_INVALID);
+    *out = NULL;
+    cudaGraph_t g = NULL;
+    B200_CUDA_TRY(ctx, cudaStreamEndCapture(ctx->stream, &g));
+    cudaGraphExec_t exec = NULL;
+    cudaError_t e = cudaGraphInstantiate(&exec, g, 0);
+    if (e != cudaSuccess) {
+        b200_set_error(ctx, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        cudaGraphDestroy(g);
+        return B200_ERR_CUDA;
+    }
+    b200_graph *h = (b200_graph *)calloc(1, sizeof(b200_graph));
+    if (!h) return B200_ERR_ALLOC;
+    h->graph = g;
+    h->exec = exec;
+    h->device = ctx->device;
+    *out = h;
+    return B200_OK;
+}
+
+int b200_graph_launch(b200_ctx *ctx, b200_graph *graph) {
+    B200_REQUIRE(ctx, ctx && graph, B200_ERR_INVALID);
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, cudaGraphLaunch(graph->exec, ctx->stream));
+    return B200_OK;
+}
+
+void b200_graph_destroy(b200_graph *graph) {
+    if (!graph) return;
+    cudaSetDevice(graph->device);
+    if (graph->exec) cudaGraphExecDestroy(graph->exec);
+    if (graph->graph) cudaGraphDestroy(graph->graph);
+    free(graph);
+}
+
+int b200_reserve_workspace(b200_ctx *ctx, int64_t k, int64_t n) {
+    B200_REQUIRE(ctx, ctx && k > 0 && n > 0 && k % 32 == 0, B200_ERR_INVALID);
+    const size_t q_bytes = b200_align_up((size_t)n * k, 256);
+    const size_t d_bytes = b200_align_up((size_t)n * (k / 32) * 2, 256);
+    return b200_ws_reserve(ctx, q_bytes + d_bytes);
+}
+
+int b200_host_malloc(void **hptr, size_t size) {
+    if (!hptr) return B200_ERR_INVALID;
+    cudaError_t e = cudaMallocHost(hptr, size ? size : 1);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        b200_set_error(NULL, "cudaMallocHost(%zu) failed: %s", size, cudaGetErrorString(e));
+        *hptr = NULL;
+        return B200_ERR_ALLOC;
+    }
+    return B200_OK;
+}
+
+int b200_host_free(void *hptr) {
+    if (!hptr) return B200_OK;
+    B200_CUDA_TRY(NULL, cudaFreeHost(hptr));
+    return B200_OK;
+}
+
+}  // extern "C"
+
+static int reserve(b200_ctx *ctx, void **p, size_t *cur, size_t bytes) {
+    if (*cur >= bytes) return B200_OK;
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (*p) {
+        B200_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        B200_CUDA_TRY(ctx, cudaFree(*p));
+        *p = NULL;
+        *cur = 0;
+    }
+    size_t want = b200_align_up(bytes + bytes / 4, 1 << 20);
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        b200_set_error(ctx, "workspace cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        return B200_ERR_ALLOC;
+    }
+    *cur = want;
+    return B200_OK;
+}
+
+int b200_ws_reserve(b200_ctx *ctx, size_t bytes) { return reserve(ctx, &ctx->ws, &ctx->ws_size, bytes); }
+int b200_stage_reserve(b200_ctx *ctx, size_t bytes) { return reserve(ctx, &ctx->stage, &ctx->stage_size, bytes); }

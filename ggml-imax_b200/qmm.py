@@ -1,0 +1,367 @@
+"""ctypes binding of include/ggml_b200.h -- the host-side mirror used by tests/, bench.py and smoke().
+
+Names and argument meaning follow the reference path they replace:
+  quantize_row_q8_0      src/ggml-quants.c:465           -> Context.quantize_row_q8_0
+  ggml_backend_tensor_set/get on a Q4_0/Q8_0 tensor (src/ggml-backend.c:221-247) -> QTensor.set / QTensor.get
+  ggml_compute_forward_mul_mat (src/ggml.c:11808)        -> Context.mul_mat
+
+Python is plumbing only: every byte of arithmetic happens in the CUDA kernels behind the C ABI.  If the
+shared library is missing or no sm_100 device is usable this module raises -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "lib" / "libggml_b200.so"
+BACKEND_LIB_PATH = PKG_DIR / "lib" / "libggml-b200-backend.so"
+
+TYPE_F32, TYPE_Q4_0, TYPE_Q8_0 = 0, 2, 8
+QK = 32
+WIRE_BYTES = {TYPE_Q4_0: 18, TYPE_Q8_0: 34}
+TYPE_NAMES = {TYPE_Q4_0: "q4_0", TYPE_Q8_0: "q8_0"}
+MM_FORCE_GEMV, MM_FORCE_GEMM = 1, 2
+
+OK, ERR_CUDA, ERR_INVALID, ERR_UNSUPPORTED, ERR_ALLOC = 0, -1, -2, -3, -4
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"ggml_b200 error {code}: {msg}")
+        self.code = code
+
+
+class MulMatArgs(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32), ("flags", C.c_int32),
+        ("src0_dev", C.c_void_p), ("src0_nblocks_total", C.c_int64), ("src0_block_off", C.c_int64),
+        ("ne00", C.c_int64), ("ne01", C.c_int64), ("ne02", C.c_int64), ("ne03", C.c_int64),
+        ("src1_dev", C.c_void_p),
+        ("ne11", C.c_int64), ("ne12", C.c_int64), ("ne13", C.c_int64),
+        ("nb11", C.c_size_t), ("nb12", C.c_size_t), ("nb13", C.c_size_t),
+        ("dst_dev", C.c_void_p),
+    ]
+
+
+# every symbol include/ggml_b200.h declares (tests check the list against the header and the .so)
+_SIGNATURES = {
+    "b200_device_count": (C.c_int, []),
+    "b200_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                   C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b200_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "b200_ctx_create_on_stream": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200_ctx_destroy": (None, [C.c_void_p]),
+    "b200_last_error": (C.c_char_p, [C.c_void_p]),
+    "b200_ctx_stream": (C.c_void_p, [C.c_void_p]),
+    "b200_ctx_device": (C.c_int, [C.c_void_p]),
+    "b200_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "b200_ctx_launch_count": (C.c_int64, [C.c_void_p]),
+    "b200_malloc": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t]),
+    "b200_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200_memset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
+    "b200_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "b200_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "b200_upload_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "b200_download_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "b200_copy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "b200_synchronize": (C.c_int, [C.c_void_p]),
+    "b200_host_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "b200_host_free": (C.c_int, [C.c_void_p]),
+    "b200_graph_begin": (C.c_int, [C.c_void_p]),
+    "b200_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200_graph_destroy": (None, [C.c_void_p]),
+    "b200_reserve_workspace": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
+    "b200_set_quantized": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]),
+    "b200_get_quantized": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]),
+    "b200_repack_from_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]),
+    "b200_unrepack_to_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]),
+    "b200_quantize_q8_0": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "b200_quantize_q8_0_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_size_t, C.c_void_p]),
+    "b200_mul_mat": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs)]),
+    "b200_block_dots": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    "b200_mul_mat_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+}
+
+_lib = None
+
+
+def declared_symbols() -> list[str]:
+    return sorted(_SIGNATURES)
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree C-ABI library; loud failure if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} not built: run `make -C {PKG_DIR}` (or __graft_entry__.build()); "
+                           "the B200 path has no CPU fallback")
+    lib = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def device_count() -> int:
+    return load_library().b200_device_count()
+
+
+def _ptr(a) -> C.c_void_p:
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if isinstance(a, DeviceBuffer):
+        return C.c_void_p(a.ptr)
+    return C.c_void_p(int(a))
+
+
+class DeviceBuffer:
+    """Device allocation owned by a Context (b200_malloc / b200_free)."""
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.ctx, self.nbytes = ctx, int(nbytes)
+        p = C.c_void_p()
+        ctx._check(ctx.lib.b200_malloc(ctx.h, C.byref(p), self.nbytes))
+        self.ptr = p.value
+
+    def free(self):
+        if self.ptr:
+            self.ctx._check(self.ctx.lib.b200_free(self.ctx.h, C.c_void_p(self.ptr)))
+            self.ptr = 0
+
+    def upload(self, arr: np.ndarray, offset: int = 0):
+        arr = np.ascontiguousarray(arr)
+        assert offset + arr.nbytes <= self.nbytes
+        self.ctx._check(self.ctx.lib.b200_upload(self.ctx.h, C.c_void_p(self.ptr + offset), _ptr(arr), arr.nbytes))
+
+    def download(self, dtype, count: int, offset: int = 0) -> np.ndarray:
+        out = np.empty(count, dtype=dtype)
+        assert offset + out.nbytes <= self.nbytes
+        self.ctx._check(self.ctx.lib.b200_download(self.ctx.h, _ptr(out), C.c_void_p(self.ptr + offset), out.nbytes))
+        return out
+
+
+class QTensor:
+    """A Q4_0/Q8_0 tensor [k, m, ne02, ne03] resident on the device in the repacked plane layout.
+
+    set()/get() are ggml_backend_tensor_set/get for a quantized tensor: wire-format blocks in, wire-format out."""
+
+    def __init__(self, ctx: "Context", qtype: int, k: int, m: int, ne02: int = 1, ne03: int = 1, buf: DeviceBuffer | None = None,
+                 ptr: int | None = None):
+        assert qtype in WIRE_BYTES and k % QK == 0
+        self.ctx, self.type, self.k, self.m, self.ne02, self.ne03 = ctx, qtype, k, m, ne02, ne03
+        self.nblocks = (k // QK) * m * ne02 * ne03
+        self.nbytes = self.nblocks * WIRE_BYTES[qtype]
+        self.buf = None
+        if ptr is not None:
+            self.ptr = int(ptr)
+        else:
+            self.buf = buf or DeviceBuffer(ctx, self.nbytes)
+            self.ptr = self.buf.ptr
+
+    def set(self, wire: np.ndarray, block_off: int = 0):
+        wire = np.ascontiguousarray(wire).view(np.uint8).reshape(-1)
+        nb = wire.nbytes // WIRE_BYTES[self.type]
+        assert nb * WIRE_BYTES[self.type] == wire.nbytes
+        self.ctx._check(self.ctx.lib.b200_set_quantized(self.ctx.h, self.type, C.c_void_p(self.ptr), self.nblocks, _ptr(wire),
+                                                        block_off, nb))
+
+    def get(self, block_off: int = 0, nblocks: int | None = None) -> np.ndarray:
+        nb = self.nblocks - block_off if nblocks is None else nblocks
+        out = np.empty(nb * WIRE_BYTES[self.type], dtype=np.uint8)
+        self.ctx._check(self.ctx.lib.b200_get_quantized(self.ctx.h, self.type, C.c_void_p(self.ptr), self.nblocks, _ptr(out),
+                                                        block_off, nb))
+        return out
+
+    def free(self):
+        if self.buf is not None:
+            self.buf.free()
+
+
+class Context:
+    """One (device, stream): b200_ctx.  `stream` = a raw cudaStream_t (int) to borrow, e.g. torch's current stream."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        if stream is None:
+            rc = self.lib.b200_ctx_create(device, C.byref(h))
+        else:
+            rc = self.lib.b200_ctx_create_on_stream(device, C.c_void_p(stream), C.byref(h))
+        if rc != OK:
+            raise B200Error(rc, (self.lib.b200_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.lib.b200_ctx_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != OK:
+            raise B200Error(rc, (self.lib.b200_last_error(self.h) or b"").decode())
+
+    # -- plumbing
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.b200_ctx_set_option(self.h, key.encode(), int(value)))
+
+    def launch_count(self) -> int:
+        return int(self.lib.b200_ctx_launch_count(self.h))
+
+    def stream(self) -> int:
+        return int(self.lib.b200_ctx_stream(self.h) or 0)
+
+    def synchronize(self):
+        self._check(self.lib.b200_synchronize(self.h))
+
+    def alloc(self, nbytes: int) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, arr: np.ndarray) -> DeviceBuffer:
+        arr = np.ascontiguousarray(arr)
+        b = DeviceBuffer(self, max(arr.nbytes, 1))
+        if arr.nbytes:
+            b.upload(arr)
+        return b
+
+    def graph_begin(self):
+        self._check(self.lib.b200_graph_begin(self.h))
+
+    def graph_end(self) -> int:
+        g = C.c_void_p()
+        self._check(self.lib.b200_graph_end(self.h, C.byref(g)))
+        return g.value
+
+    def graph_launch(self, g: int):
+        self._check(self.lib.b200_graph_launch(self.h, C.c_void_p(g)))
+
+    def graph_destroy(self, g: int):
+        self.lib.b200_graph_destroy(C.c_void_p(g))
+
+    def reserve_workspace(self, k: int, n: int):
+        self._check(self.lib.b200_reserve_workspace(self.h, k, n))
+
+    # -- the path
+    def quantize_row_q8_0(self, x: np.ndarray) -> np.ndarray:
+        """x: [nrows, k] float32 (host).  Returns nrows*(k/32) block_q8_0 records (uint8 [nrows, k/32*34]) made on the GPU."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim == 1:
+            x = x[None, :]
+        nrows, k = x.shape
+        xd = self.to_device(x)
+        out = self.alloc(max(nrows * (k // QK) * 34, 1))
+        try:
+            self._check(self.lib.b200_quantize_q8_0_blocks(self.h, C.c_void_p(xd.ptr), k, nrows, k * 4, C.c_void_p(out.ptr)))
+            return out.download(np.uint8, nrows * (k // QK) * 34).reshape(nrows, -1)
+        finally:
+            xd.free()
+            out.free()
+
+    def quantize_q8_0_planar(self, x: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        nrows, k = x.shape
+        xd = self.to_device(x)
+        qs = self.alloc(nrows * k)
+        d = self.alloc(nrows * (k // QK) * 2)
+        try:
+            self._check(self.lib.b200_quantize_q8_0(self.h, C.c_void_p(xd.ptr), k, nrows, k * 4, C.c_void_p(qs.ptr), C.c_void_p(d.ptr)))
+            return qs.download(np.int8, nrows * k).reshape(nrows, k), d.download(np.uint16, nrows * (k // QK)).reshape(nrows, -1)
+        finally:
+            xd.free(); qs.free(); d.free()
+
+    def mul_mat_device(self, w: QTensor, x_ptr: int, n: int, dst_ptr: int, ne12: int = 1, ne13: int = 1,
+                       nb11: int | None = None, nb12: int | None = None, nb13: int | None = None, flags: int = 0,
+                       block_off: int = 0, m: int | None = None, nblocks_total: int | None = None):
+        """Asynchronous mul_mat on device pointers (what graph_compute does for one MUL_MAT node)."""
+        a = MulMatArgs()
+        a.type, a.flags = w.type, flags
+        a.src0_dev = w.ptr
+        a.src0_nblocks_total = w.nblocks if nblocks_total is None else nblocks_total
+        a.src0_block_off = block_off
+        a.ne00, a.ne01, a.ne02, a.ne03 = w.k, (w.m if m is None else m), w.ne02, w.ne03
+        a.src1_dev = x_ptr
+        a.ne11, a.ne12, a.ne13 = n, ne12, ne13
+        a.nb11 = w.k * 4 if nb11 is None else nb11
+        a.nb12 = a.nb11 * n if nb12 is None else nb12
+        a.nb13 = a.nb12 * ne12 if nb13 is None else nb13
+        a.dst_dev = dst_ptr
+        self._check(self.lib.b200_mul_mat(self.h, C.byref(a)))
+
+    def mul_mat(self, w: QTensor, x: np.ndarray, flags: int = 0) -> np.ndarray:
+        """x: [ne13, ne12, n, k] (or [n, k]) float32 host.  Returns dst [ne13, ne12, n, m] float32 (ggml dst[m,n,ne12,ne13])."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        shape = x.shape
+        if x.ndim == 2:
+            x = x[None, None]
+        ne13, ne12, n, k = x.shape
+        assert k == w.k
+        xd = self.to_device(x)
+        out = self.alloc(ne13 * ne12 * n * w.m * 4)
+        try:
+            self.mul_mat_device(w, xd.ptr, n, out.ptr, ne12, ne13, flags=flags)
+            self.synchronize()
+            y = out.download(np.float32, ne13 * ne12 * n * w.m).reshape(ne13, ne12, n, w.m)
+            return y[0, 0] if len(shape) == 2 else y
+        finally:
+            xd.free(); out.free()
+
+    def mul_mat_host(self, w: QTensor, x: np.ndarray) -> np.ndarray:
+        """End-to-end convenience call with HOST buffers (upload + mul_mat + download inside the C ABI)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n, k = x.shape
+        y = np.empty((n, w.m), dtype=np.float32)
+        self._check(self.lib.b200_mul_mat_host(self.h, w.type, C.c_void_p(w.ptr), k, w.m, _ptr(x), n, _ptr(y)))
+        return y
+
+    def block_dots(self, w: QTensor, x: np.ndarray, path: int = 0) -> np.ndarray:
+        """Per-block int32 partial sums [n, m, k/32] exactly as the kernels form them (parity instrumentation)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n, k = x.shape
+        nb = k // QK
+        xd = self.to_device(x)
+        out = self.alloc(n * w.m * nb * 4)
+        try:
+            self._check(self.lib.b200_memset(self.h, C.c_void_p(out.ptr), 0x7f, n * w.m * nb * 4))
+            self._check(self.lib.b200_block_dots(self.h, w.type, C.c_void_p(w.ptr), k, w.m, C.c_void_p(xd.ptr), n, C.c_void_p(out.ptr), path))
+            self.synchronize()
+            return out.download(np.int32, n * w.m * nb).reshape(n, w.m, nb)
+        finally:
+            xd.free(); out.free()
+
+
+# ---- synthetic weights made directly in the wire format (no CPU quantizer involved) ---------------------
+
+def random_wire_weights(qtype: int, k: int, m: int, seed: int = 1234, scale: float | None = None) -> np.ndarray:
+    """Random-init Q4_0/Q8_0 rows in wire format: uniform quants, fp16 block scales around `scale`
+    (default: weights ~ unit-variance rows / sqrt(k), so chains of mul_mats stay O(1))."""
+    rng = np.random.default_rng(seed)
+    nb = k // QK
+    wb = WIRE_BYTES[qtype]
+    out = np.empty((m * nb, wb), dtype=np.uint8)
+    qstd = 4.32 if qtype == TYPE_Q4_0 else 73.3
+    base = (1.0 / (qstd * np.sqrt(k))) if scale is None else scale
+    d = (base * rng.uniform(0.8, 1.2, size=m * nb)).astype(np.float16)
+    out[:, 0:2] = d.view(np.uint8).reshape(-1, 2)
+    if qtype == TYPE_Q4_0:
+        # nibbles 1..15 -> quants -7..7: zero-mean, so a chain of mul_mats keeps O(1) activations
+        out[:, 2:] = rng.integers(1, 16, size=(m * nb, 16), dtype=np.uint8) | (rng.integers(1, 16, size=(m * nb, 16), dtype=np.uint8) << 4)
+    else:
+        out[:, 2:] = rng.integers(-127, 128, size=(m * nb, 32), dtype=np.int8).view(np.uint8)
+    return out.reshape(m, nb * wb)

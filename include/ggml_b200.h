@@ -1,0 +1,171 @@
+/*
+ * ggml_b200.h -- thin C ABI of the B200 (sm_100a) quantized mul_mat path.
+ *
+ * This is the drop-in boundary between host code written in C (the ggml backend in
+ * ggml-imax_b200/host/ggml-b200.c, or any FFI: ctypes, cgo, JNI ...) and the CUDA kernels in
+ * ggml-imax_b200/csrc/.  Plain pointers and sizes only; no C++/torch types.  Every entry point
+ * names the reference interface it stands in for (paths relative to the reference checkout).
+ *
+ * There is NO CPU fallback behind any of these calls: without a usable sm_100 device they return
+ * B200_ERR_CUDA / B200_ERR_UNSUPPORTED and leave the reason in b200_last_error().
+ *
+ * All *_dev pointers are device pointers obtained from b200_malloc() (or any CUDA allocation on
+ * the context's device).  Unless stated otherwise calls are asynchronous on the context's stream;
+ * b200_upload/b200_download/b200_set_quantized/b200_get_quantized are synchronous like the
+ * reference's buffer set_tensor/get_tensor (src/ggml-backend.c:221-247).
+ */
+#ifndef GGML_B200_H
+#define GGML_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#  define B200_API __attribute__((visibility("default")))
+#else
+#  define B200_API
+#endif
+
+/* status codes */
+#define B200_OK               0
+#define B200_ERR_CUDA        (-1)   /* a CUDA runtime/driver call failed (see b200_last_error) */
+#define B200_ERR_INVALID     (-2)   /* bad argument / shape the reference would GGML_ASSERT on  */
+#define B200_ERR_UNSUPPORTED (-3)   /* valid ggml, but outside this path (supports_op == false)   */
+#define B200_ERR_ALLOC       (-4)   /* device allocation failed (GGML_STATUS_ALLOC_FAILED)        */
+
+/* tensor types: numeric values of enum ggml_type (include/ggml/ggml.h:347-355) */
+#define B200_TYPE_F32   0
+#define B200_TYPE_Q4_0  2
+#define B200_TYPE_Q8_0  8
+
+/* wire formats (src/ggml-common.h:144-149, :186-191) */
+#define B200_QK            32
+#define B200_Q4_0_BYTES    18
+#define B200_Q8_0_BYTES    34
+
+typedef struct b200_ctx b200_ctx;   /* one per (device, stream); not thread-safe, like a ggml_backend */
+
+/* ---- devices / contexts ------------------------------------------------------------------
+ * replaces ggml_backend_cuda_get_device_count / _get_device_description / _get_device_memory
+ * (src/ggml-cuda.h:33-36) and the per-backend context of ggml_backend_cuda_init (src/ggml-cuda.h:19) */
+B200_API int  b200_device_count(void);
+B200_API int  b200_device_info(int device, char *name, size_t name_len, size_t *free_bytes, size_t *total_bytes,
+                               int *sm_count, int *cc_major, int *cc_minor);
+B200_API int  b200_ctx_create(int device, b200_ctx **out);
+/* same, but launches on a stream owned by the caller (e.g. torch's current stream, for plumbing) */
+B200_API int  b200_ctx_create_on_stream(int device, void *cuda_stream, b200_ctx **out);
+B200_API void b200_ctx_destroy(b200_ctx *ctx);
+B200_API const char *b200_last_error(const b200_ctx *ctx);   /* ctx may be NULL: last global error */
+B200_API void *b200_ctx_stream(const b200_ctx *ctx);         /* the cudaStream_t launches go to     */
+B200_API int  b200_ctx_device(const b200_ctx *ctx);
+/* knobs: "pdl" (0/1 programmatic dependent launch on the decode GEMV), "gemm" (0 = never use the
+ * tcgen05 GEMM, 1 = auto), "gemv_max_n" (largest n served by the GEMV). returns B200_ERR_INVALID if unknown */
+B200_API int  b200_ctx_set_option(b200_ctx *ctx, const char *key, int64_t value);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+B200_API int64_t b200_ctx_launch_count(const b200_ctx *ctx);
+
+/* ---- device buffers -----------------------------------------------------------------------
+ * replaces ggml_backend_buffer_type_i.alloc_buffer and ggml_backend_buffer_i.{free_buffer,clear,
+ * set_tensor,get_tensor,cpy_tensor} for non-quantized data (src/ggml-backend-impl.h:18-48) */
+B200_API int b200_malloc(b200_ctx *ctx, void **dptr, size_t size);
+B200_API int b200_free(b200_ctx *ctx, void *dptr);
+B200_API int b200_memset(b200_ctx *ctx, void *dptr, int value, size_t size);            /* sync */
+B200_API int b200_upload(b200_ctx *ctx, void *dst_dev, const void *src_host, size_t size);   /* sync */
+B200_API int b200_download(b200_ctx *ctx, void *dst_host, const void *src_dev, size_t size); /* sync */
+B200_API int b200_upload_async(b200_ctx *ctx, void *dst_dev, const void *src_host, size_t size);
+B200_API int b200_download_async(b200_ctx *ctx, void *dst_host, const void *src_dev, size_t size);
+B200_API int b200_copy_d2d(b200_ctx *ctx, void *dst_dev, const void *src_dev, size_t size);  /* async */
+B200_API int b200_synchronize(b200_ctx *ctx);          /* ggml_backend_i.synchronize */
+/* pinned host staging (ggml_backend_cuda_host_buffer_type, src/ggml-cuda.h:31) */
+B200_API int b200_host_malloc(void **hptr, size_t size);
+B200_API int b200_host_free(void *hptr);
+
+/* ---- launch graphs --------------------------------------------------------------------------
+ * Decode runs hundreds of microsecond-sized mul_mats per token, so the launch path matters as much as
+ * the kernels.  b200_graph_begin/end bracket any sequence of the asynchronous calls of this header
+ * (b200_mul_mat, b200_quantize_q8_0, b200_*_async on pinned memory ...) on the context's stream and
+ * turn it into one replayable CUDA graph; b200_graph_launch replays it.  This is what the backend's
+ * graph_compute uses for a repeated ggml_cgraph (cf. the reference's opt-in GGML_CUDA_USE_GRAPHS,
+ * src/ggml-cuda.cu:2461-2709).  No allocation may happen between begin and end: call
+ * b200_reserve_workspace first when the sequence contains prefill-sized mul_mats. */
+typedef struct b200_graph b200_graph;
+B200_API int  b200_graph_begin(b200_ctx *ctx);
+B200_API int  b200_graph_end(b200_ctx *ctx, b200_graph **out);
+B200_API int  b200_graph_launch(b200_ctx *ctx, b200_graph *graph);
+B200_API void b200_graph_destroy(b200_graph *graph);
+/* make sure the activation scratch can hold n columns of k (no-op if already large enough) */
+B200_API int  b200_reserve_workspace(b200_ctx *ctx, int64_t k, int64_t n);
+
+/* ---- quantized tensor storage ("repack once at set_tensor") --------------------------------
+ * A Q4_0/Q8_0 tensor of nblocks_total blocks occupies exactly its ggml_nbytes() on the device but
+ * laid out as planes:   [ qs plane: nblocks_total * 16 B (Q4_0, packed nibbles, original nibble order)
+ *                                 or nblocks_total * 32 B (Q8_0, int8) ]
+ *                       [ d plane : nblocks_total * 2 B  (fp16 block scales) ]
+ * set = ggml_backend_buffer_i.set_tensor for a quantized tensor: src_host holds `nblocks` blocks in
+ * wire format destined for blocks [block_off, block_off+nblocks).  get is the exact inverse, so
+ * get(set(x)) == x byte for byte (needed by ggml_backend_graph_copy, src/ggml-backend.c:1974-2060). */
+B200_API int b200_set_quantized(b200_ctx *ctx, int type, void *tensor_dev, int64_t nblocks_total,
+                                const void *src_host, int64_t block_off, int64_t nblocks);
+B200_API int b200_get_quantized(b200_ctx *ctx, int type, const void *tensor_dev, int64_t nblocks_total,
+                                void *dst_host, int64_t block_off, int64_t nblocks);
+/* same repack but from wire-format blocks already on the device (tensor copy between layouts) */
+B200_API int b200_repack_from_device(b200_ctx *ctx, int type, void *tensor_dev, int64_t nblocks_total,
+                                     const void *src_wire_dev, int64_t block_off, int64_t nblocks);
+B200_API int b200_unrepack_to_device(b200_ctx *ctx, int type, const void *tensor_dev, int64_t nblocks_total,
+                                     void *dst_wire_dev, int64_t block_off, int64_t nblocks);
+
+/* ---- activation quantization ---------------------------------------------------------------
+ * replaces quantize_row_q8_0 (src/ggml-quants.c:465, AVX2 body :535-618), bit-exact.
+ * x_dev: nrows rows of k floats, rows row_stride_bytes apart.
+ * planar form (what the kernels consume): qs_dev [nrows][k] int8, d_dev [nrows][k/32] fp16.
+ * blocks form: nrows * (k/32) block_q8_0 in wire format (34 B), what the reference writes to wdata
+ * (src/ggml.c:11956-11971). */
+B200_API int b200_quantize_q8_0(b200_ctx *ctx, const float *x_dev, int64_t k, int64_t nrows, size_t row_stride_bytes,
+                                int8_t *qs_dev, uint16_t *d_dev);
+B200_API int b200_quantize_q8_0_blocks(b200_ctx *ctx, const float *x_dev, int64_t k, int64_t nrows,
+                                       size_t row_stride_bytes, void *blocks_dev);
+
+/* ---- mul_mat -------------------------------------------------------------------------------
+ * replaces ggml_compute_forward_mul_mat (src/ggml.c:11808-12097) for src0 in {Q4_0,Q8_0} (repacked
+ * storage above), src1 F32, dst F32.  Same argument meaning as the ggml tensors:
+ *   src0 [ne00=k, ne01=m, ne02, ne03] contiguous;   src1 [k, ne11=n, ne12, ne13] with byte strides
+ *   nb11/nb12/nb13 (nb10 == 4);   dst [m, n, ne12, ne13] dense;   ne12 % ne02 == 0, ne13 % ne03 == 0.
+ * src0_nblocks_total / src0_block_off locate src0 inside its repacked tensor (0 / total for a
+ * whole tensor; a row-range view uses the parent's total and its own first block). */
+typedef struct b200_mul_mat_args {
+    int32_t      type;                 /* B200_TYPE_Q4_0 or B200_TYPE_Q8_0 */
+    int32_t      flags;                /* B200_MM_* */
+    const void  *src0_dev;             /* base of the repacked tensor that holds src0 */
+    int64_t      src0_nblocks_total;
+    int64_t      src0_block_off;
+    int64_t      ne00, ne01, ne02, ne03;
+    const float *src1_dev;
+    int64_t      ne11, ne12, ne13;
+    size_t       nb11, nb12, nb13;
+    float       *dst_dev;
+} b200_mul_mat_args;
+
+#define B200_MM_FORCE_GEMV  1   /* use the dp4a GEMV for any n (column chunks of <= 8) */
+#define B200_MM_FORCE_GEMM  2   /* use the tcgen05 GEMM for any n */
+
+B200_API int b200_mul_mat(b200_ctx *ctx, const b200_mul_mat_args *args);
+
+/* parity instrumentation: per-block int32 partial sums exactly as the kernels form them.
+ * out_dev [n][m][k/32] int32.  path 0 = GEMV inner loop (dp4a), path 1 = GEMM (tcgen05 accumulators).
+ * Compared bit-for-bit with the integer loop of src/ggml-quants.c:3858-3869 / :5010-5015. */
+B200_API int b200_block_dots(b200_ctx *ctx, int type, const void *src0_dev, int64_t k, int64_t m,
+                             const float *src1_dev, int64_t n, int32_t *out_dev, int path);
+
+/* host-buffer convenience used by end-to-end timing and smoke: upload src1 (n*k floats, dense),
+ * mul_mat against a resident repacked src0 [k, m], download dst (n*m floats).  Synchronous. */
+B200_API int b200_mul_mat_host(b200_ctx *ctx, int type, const void *src0_dev, int64_t k, int64_t m,
+                               const float *src1_host, int64_t n, float *dst_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGML_B200_H */
