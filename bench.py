@@ -258,7 +258,7 @@ def run_b200(args):
                 "note": "per rank; at N>1 the step time includes the NCCL all-gathers"}
 
     extra = {}
-    if world == 1:
+    if world == 1 and not args.no_extras:
         extra = run_extras(torch, qmm, ctx, stream, P, args)
         tr = ROOT / "profiles" / "traffic.json"
         if tr.exists():
@@ -517,6 +517,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a captured CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C1/C2 sub-benchmarks (A/B runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -304,6 +304,10 @@ int b200_launch_gemv(b200_ctx *ctx, const b200_gemv_params &p) {
     B200_REQUIRE(ctx, p.ne12 * p.ne13 <= 65535, B200_ERR_UNSUPPORTED);
     B200_REQUIRE(ctx, ((uintptr_t)p.x & 15) == 0 && (p.nb11 & 15) == 0 && (p.nb12 & 15) == 0 && (p.nb13 & 15) == 0, B200_ERR_UNSUPPORTED);
     const bool dots = p.dots != NULL;
+    if (ctx->opt_gemv_stream) {  // the streaming kernel (b200_gemv_stream.cu) takes the 2-D, k % 256 == 0 shapes
+        int rc = B200_OK;
+        if (b200_try_launch_gemv_stream(ctx, p, &rc)) return rc;
+    }
     if (p.type == B200_TYPE_Q4_0) return launch_cols<B200_TYPE_Q4_0>(ctx, p, dots);
     if (p.type == B200_TYPE_Q8_0) return launch_cols<B200_TYPE_Q8_0>(ctx, p, dots);
     return B200_ERR_UNSUPPORTED;

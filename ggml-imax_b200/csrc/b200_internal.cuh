@@ -26,6 +26,7 @@ struct b200_ctx {
     int          opt_pdl;
     int          opt_gemm;
     int          opt_gemv_max_n;
+    int          opt_gemv_stream;
     int64_t      launches;
     char         err[512];
 };
@@ -79,6 +80,7 @@ struct b200_gemv_params {
     int32_t       *dots;       // non-null: dump per-block int32 partials [n][m][k/32] instead of dst
 };
 int b200_launch_gemv(b200_ctx *ctx, const b200_gemv_params &p);
+bool b200_try_launch_gemv_stream(b200_ctx *ctx, const b200_gemv_params &p, int *rc);
 
 struct b200_gemm_params {
     int            type;

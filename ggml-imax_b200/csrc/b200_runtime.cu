@@ -81,6 +81,7 @@ static int ctx_create_common(int device, void *stream, bool own, b200_ctx **out)
     ctx->opt_pdl = getenv("B200_NO_PDL") ? 0 : 1;
     ctx->opt_gemm = getenv("B200_NO_GEMM") ? 0 : 1;
     ctx->opt_gemv_max_n = 8;
+    ctx->opt_gemv_stream = getenv("B200_NO_STREAM_GEMV") ? 0 : 1;
     B200_CUDA_TRY(ctx, cudaSetDevice(device));
     if (own) {
         cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -121,6 +122,7 @@ int b200_ctx_set_option(b200_ctx *ctx, const char *key, int64_t value) {
     if (!ctx || !key) return B200_ERR_INVALID;
     if (!strcmp(key, "pdl")) { ctx->opt_pdl = value != 0; return B200_OK; }
     if (!strcmp(key, "gemm")) { ctx->opt_gemm = value != 0; return B200_OK; }
+    if (!strcmp(key, "gemv_stream")) { ctx->opt_gemv_stream = value != 0; return B200_OK; }
     if (!strcmp(key, "gemv_max_n")) {
         if (value < 1 || value > 8) return B200_ERR_INVALID;
         ctx->opt_gemv_max_n = (int)value;

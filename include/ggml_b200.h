@@ -63,7 +63,7 @@ B200_API const char *b200_last_error(const b200_ctx *ctx);   /* ctx may be NULL:
 B200_API void *b200_ctx_stream(const b200_ctx *ctx);         /* the cudaStream_t launches go to     */
 B200_API int  b200_ctx_device(const b200_ctx *ctx);
 /* knobs: "pdl" (0/1 programmatic dependent launch on the decode GEMV), "gemm" (0 = never use the
- * tcgen05 GEMM, 1 = auto), "gemv_max_n" (largest n served by the GEMV). returns B200_ERR_INVALID if unknown */
+ * tcgen05 GEMM, 1 = auto), "gemv_max_n" (largest n served by the GEMV), "gemv_stream" (0 = generic GEMV only). returns B200_ERR_INVALID if unknown */
 B200_API int  b200_ctx_set_option(b200_ctx *ctx, const char *key, int64_t value);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 B200_API int64_t b200_ctx_launch_count(const b200_ctx *ctx);

@@ -93,14 +93,19 @@ def test_repacked_layout_is_planes(gpu_ctx, qmm):
 # ---- per-block int32 dots ---------------------------------------------------------------------------
 
 @pytest.mark.parametrize("qtype", [Q4_0, Q8_0])
-@pytest.mark.parametrize("m,k,n", [(16, 256, 1), (33, 96, 5), (64, 4096, 3), (5, 32, 8), (40, 1024, 11)])
+@pytest.mark.parametrize("m,k,n", [(16, 256, 1), (33, 96, 5), (64, 4096, 3), (5, 32, 8), (40, 1024, 11), (300, 768, 1),
+                                   (9, 16384, 1), (20, 8192, 2), (7, 12288, 1)])
 def test_block_dots_gemv_bit_exact(gpu_ctx, qmm, oracle, qtype, m, k, n):
     t, wire = make_w(oracle, qmm, gpu_ctx, qtype, m, k, seed=m + k + n)
     rng = np.random.default_rng(n)
     x = rng.uniform(-1, 1, (n, k)).astype(np.float32)
-    got = gpu_ctx.block_dots(t, x, path=0)
     ref = oracle.block_dots(qtype, wire, oracle.quantize_row_q8_0(x), k)
-    assert np.array_equal(got, ref)
+    try:
+        for stream in (1, 0):
+            gpu_ctx.set_option("gemv_stream", stream)
+            assert np.array_equal(gpu_ctx.block_dots(t, x, path=0), ref), stream
+    finally:
+        gpu_ctx.set_option("gemv_stream", 1)
     t.free()
 
 
@@ -124,16 +129,22 @@ def test_mul_mat_golden_cases(gpu_ctx, qmm, golden):
 
 @pytest.mark.parametrize("qtype", [Q4_0, Q8_0])
 @pytest.mark.parametrize("m,k,n", [(1, 32, 1), (16, 256, 1), (16, 256, 16), (50257 // 64, 768, 1), (4096, 4096, 1),
-                                   (1000, 3072, 2), (333, 768, 7), (129, 64, 8), (64, 16384, 1), (2304, 768, 9)])
+                                   (1000, 3072, 2), (333, 768, 7), (129, 64, 8), (64, 16384, 1), (2304, 768, 9), (4096, 16384, 1),
+                                   (100, 8192, 3), (50, 12288, 1), (700, 28672 // 7 * 8, 1), (148, 256, 1), (147, 512, 8)])
 def test_mul_mat_vs_oracle(gpu_ctx, qmm, oracle, qtype, m, k, n):
     t, wire = make_w(oracle, qmm, gpu_ctx, qtype, m, k, seed=m * 7 + k + n)
     rng = np.random.default_rng(m + n)
     x = rng.uniform(-1, 1, (n, k)).astype(np.float32)
     ref = oracle.mul_mat(qtype, wire, k, m, 1, 1, x[None, None])[0, 0]
-    for flags in (0, qmm.MM_FORCE_GEMV):
-        got = gpu_ctx.mul_mat(t, x, flags=flags)
-        err = nmse(got, ref)
-        assert err <= MUL_MAT_NMSE_TOL and err <= 1e-9, (flags, err)
+    try:
+        for stream in (1, 0):                       # streaming GEMV (b200_gemv_stream.cu) and generic GEMV (b200_gemv.cu)
+            gpu_ctx.set_option("gemv_stream", stream)
+            for flags in (0, qmm.MM_FORCE_GEMV):
+                got = gpu_ctx.mul_mat(t, x, flags=flags)
+                err = nmse(got, ref)
+                assert err <= MUL_MAT_NMSE_TOL and err <= 1e-9, (stream, flags, err)
+    finally:
+        gpu_ctx.set_option("gemv_stream", 1)
     assert nmse(gpu_ctx.mul_mat_host(t, x), ref) <= 1e-9
     t.free()
 
