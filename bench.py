@@ -359,7 +359,7 @@ def run_extras(torch, qmm, ctx, stream, P, args):
             bufs.append(b); ts.append(t)
             ys.append(torch.empty(n * m, dtype=torch.float32, device=dev))
         x = torch.rand(n * k, dtype=torch.float32, device=dev) * 2 - 1
-        ctx.reserve_workspace(k, n)
+        ctx.reserve_workspace(qtype, k, m, n)
         try:
             def c2():
                 for t, y in zip(ts, ys):

@@ -1,7 +1,363 @@
-// placeholder until the tcgen05 GEMM lands
+// b200_gemm_tc.cu -- prefill path: dst[n][m] = W[m,k] (int8, per-32 fp16 scales) x Xq[n,k] (Q8_0 activations),
+// a dense contraction on the 5th-generation tensor cores (tcgen05.mma kind::i8, int32 accumulators in TMEM).
+//
+// Stands in for the COMPUTE phase of ggml_compute_forward_mul_mat (src/ggml.c:12056-12096) at n >= 9:
+//   dst[n][m] = sum_kb  d_w[m][kb] * d_x[n][kb] * ( sum_{j<32} w[m][32 kb + j] * q[n][32 kb + j] )
+// The inner integer sum is exactly the per-block partial of ggml_vec_dot_q4_0_q8_0 / _q8_0_q8_0
+// (src/ggml-quants.c:3858-3869, :5010-5015).  One tcgen05.mma has K = 32 for 8-bit operands == one quant block,
+// so every MMA produces the exact int32 block partials of a 128 x 128 tile; they are read back from TMEM,
+// converted, multiplied by the product of the two fp16 scales and accumulated in fp32 registers.
+//
+// CTA = one 128(m) x 128(n) output tile, 12 warps:
+//   warp 0      TMA producer: A tile (128 rows x 128 B) and B tile (128 x 128 B) per stage, SWIZZLE_128B, 4 k-blocks
+//   warp 1      MMA issuer: 4 x tcgen05.mma (K=32 each) per stage, each into its own 128-column TMEM buffer
+//               (4 buffers = all 512 columns), tcgen05.commit -> mbarriers (TMEM full, smem stage empty)
+//   warp 2      TMEM allocator / deallocator
+//   warps 4-11  epilogue: warp w reads TMEM lanes 32*(w%4).. (its hardware quadrant), columns 64*((w-4)/4)..;
+//               thread = one weight row: d_w is a per-thread scalar, d_x a warp-uniform (broadcast) load;
+//               64 fp32 accumulators per thread; final store is coalesced along m.
+// Q4_0 weights are expanded to int8 (nib - 8) by expand_q4_0_kernel into scratch first (v1; fusing the expansion
+// behind the TMA load is the next step).
 #include "b200_internal.cuh"
-bool b200_gemm_available(void) { return false; }
-int b200_launch_gemm(b200_ctx *ctx, const b200_gemm_params &) {
-    b200_set_error(ctx, "tcgen05 GEMM not built");
-    return B200_ERR_UNSUPPORTED;
+
+#include <cudaTypedefs.h>
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 128;  // BK bytes of int8 = one 128-byte swizzle atom = 4 quant blocks
+constexpr int kStages = 4;
+constexpr int kTmemBufs = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 128 + kEpiWarps * 32;
+constexpr int kStageBytes = BM * BK + BN * BK;  // 32 KB
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, int8 x int8 -> int32, M = 128, N = 128, K = 32
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B (8-row x 128-byte atoms, 1024 B apart), sm_100 version bit
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address       bits [0,14)
+    d |= (uint64_t)0 << 16;                         // leading byte offset bits [16,30) (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset  bits [32,46): 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                         // descriptor version  bits [46,48) = 1 on sm_100
+    d |= (uint64_t)2 << 61;                         // layout type         bits [61,64) = SWIZZLE_128B
+    return d;
+}
+
+// instruction descriptor: dense, no saturate, D = S32, A = B = signed 8-bit, both K-major, N = 128, M = 128
+constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct GemmArgs {
+    const __half *dw;   // weight scales [m][nb]
+    const float *dxT;   // activation scales, transposed fp32 [nb][ldn]
+    int64_t ldn;
+    float *dst;         // [n][m]
+    int32_t *dots;      // parity dump [n][m][nb] or null
+    int m, n, k;
+};
+
+template <bool DOTS>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+    uint64_t *full_bar = bars;                       // [kStages]   TMA -> MMA
+    uint64_t *empty_bar = bars + kStages;            // [kStages]   MMA -> TMA
+    uint64_t *tfull_bar = bars + 2 * kStages;        // [kTmemBufs] MMA -> epilogue
+    uint64_t *tempty_bar = tfull_bar + kTmemBufs;    // [kTmemBufs] epilogue -> MMA
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + kTmemBufs);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int nb = g.k >> 5;
+    const int kiters = (g.k + BK - 1) / BK;          // TMA zero-fills a ragged last stage
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < kTmemBufs; b++) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int it = 0; it < kiters; it++) {
+                const int s = it % kStages;
+                const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                unsigned char *sa = smem + s * kStageBytes;
+                unsigned char *sb = sa + BM * BK;
+                mbar_expect_tx(&full_bar[s], kStageBytes);
+                tma_load_2d(sa, &map_a, it * BK, m0, &full_bar[s]);
+                tma_load_2d(sb, &map_b, it * BK, n0, &full_bar[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            for (int it = 0; it < kiters; it++) {
+                const int s = it % kStages;
+                const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * kStageBytes);
+                const uint32_t sb = sa + BM * BK;
+                const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sb);
+#pragma unroll
+                for (int j = 0; j < BK / 32; j++) {
+                    const int kb = it * (BK / 32) + j;
+                    if (kb < nb) {
+                        const int buf = kb % kTmemBufs;
+                        const uint32_t tph = (uint32_t)(kb / kTmemBufs) & 1u;
+                        mbar_wait(&tempty_bar[buf], tph ^ 1u);   // epilogue has drained this TMEM buffer
+                        tc_fence_after();
+                        // K advance inside the 128-byte swizzle atom: +32 bytes = +2 in the (>>4) start-address field
+                        tc_mma_i8(tmem_base + (uint32_t)(buf * BN), da + (uint64_t)(j * 2), db + (uint64_t)(j * 2), kIdescI8, 0u);
+                        tc_commit(&tfull_bar[buf]);              // arrives when this MMA has written TMEM
+                    }
+                }
+                tc_commit(&empty_bar[s]);                        // smem stage reusable once its MMAs have read it
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const int ew = warp - 4;
+        const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int half = ew >> 2;                  // which 64 of the 128 columns
+        const int row = m0 + quad * 32 + lane;     // weight row owned by this thread
+        const int row_c = row < g.m ? row : g.m - 1;
+        const __half *dwp = g.dw + (int64_t)row_c * nb;
+        const float *dxp = g.dxT + n0 + half * 64;
+        float acc[64];
+#pragma unroll
+        for (int j = 0; j < 64; j++) acc[j] = 0.0f;
+
+        for (int kb = 0; kb < nb; kb++) {
+            const int buf = kb % kTmemBufs;
+            const uint32_t tph = (uint32_t)(kb / kTmemBufs) & 1u;
+            const float dw = __half2float(dwp[kb]);
+            mbar_wait(&tfull_bar[buf], tph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + half * 64);
+            uint32_t p0[32], p1[32];
+            tc_ld32(taddr, p0);
+            tc_ld32(taddr + 32, p1);
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);   // TMEM buffer may be overwritten by MMA kb + 4
+            if (DOTS) {
+                if (row < g.m) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const int c0 = n0 + half * 64 + j, c1 = c0 + 32;
+                        if (c0 < g.n) g.dots[((int64_t)c0 * g.m + row) * nb + kb] = (int32_t)p0[j];
+                        if (c1 < g.n) g.dots[((int64_t)c1 * g.m + row) * nb + kb] = (int32_t)p1[j];
+                    }
+                }
+            } else {
+                const float4 *dx4 = reinterpret_cast<const float4 *>(dxp + (int64_t)kb * g.ldn);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; j4++) {
+                    const float4 d0 = __ldg(dx4 + j4), d1 = __ldg(dx4 + 8 + j4);
+                    acc[j4 * 4 + 0] = fmaf((float)(int32_t)p0[j4 * 4 + 0], dw * d0.x, acc[j4 * 4 + 0]);
+                    acc[j4 * 4 + 1] = fmaf((float)(int32_t)p0[j4 * 4 + 1], dw * d0.y, acc[j4 * 4 + 1]);
+                    acc[j4 * 4 + 2] = fmaf((float)(int32_t)p0[j4 * 4 + 2], dw * d0.z, acc[j4 * 4 + 2]);
+                    acc[j4 * 4 + 3] = fmaf((float)(int32_t)p0[j4 * 4 + 3], dw * d0.w, acc[j4 * 4 + 3]);
+                    acc[32 + j4 * 4 + 0] = fmaf((float)(int32_t)p1[j4 * 4 + 0], dw * d1.x, acc[32 + j4 * 4 + 0]);
+                    acc[32 + j4 * 4 + 1] = fmaf((float)(int32_t)p1[j4 * 4 + 1], dw * d1.y, acc[32 + j4 * 4 + 1]);
+                    acc[32 + j4 * 4 + 2] = fmaf((float)(int32_t)p1[j4 * 4 + 2], dw * d1.z, acc[32 + j4 * 4 + 2]);
+                    acc[32 + j4 * 4 + 3] = fmaf((float)(int32_t)p1[j4 * 4 + 3], dw * d1.w, acc[32 + j4 * 4 + 3]);
+                }
+            }
+        }
+        if (!DOTS && row < g.m) {
+#pragma unroll
+            for (int j = 0; j < 64; j++) {
+                const int c = n0 + half * 64 + j;
+                if (c < g.n) g.dst[(int64_t)c * g.m + row] = acc[j];   // 32 lanes -> 128 contiguous bytes
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+// Q4_0 qs plane (packed nibbles) -> int8 (nib - 8) rows [m][k]; one thread per block
+__global__ void __launch_bounds__(256) expand_q4_0_kernel(const uint4 *__restrict__ qs, uint4 *__restrict__ out, int64_t nblocks) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const uint4 v = qs[b];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        // per byte: (nib | 0x80) - 8, then ^ 0x80  ==  nib - 8 in two's complement, no borrow across bytes
+        lo[i] = (((w[i] & 0x0F0F0F0Fu) | 0x80808080u) - 0x08080808u) ^ 0x80808080u;
+        hi[i] = ((((w[i] >> 4) & 0x0F0F0F0Fu) | 0x80808080u) - 0x08080808u) ^ 0x80808080u;
+    }
+    out[2 * b] = make_uint4(lo[0], lo[1], lo[2], lo[3]);       // elements 0..15
+    out[2 * b + 1] = make_uint4(hi[0], hi[1], hi[2], hi[3]);   // elements 16..31
+}
+
+// fp16 activation scales [n][nb] -> fp32 transposed [nb][ldn] (zero padded) for warp-uniform loads in the epilogue
+__global__ void __launch_bounds__(256) transpose_scales_kernel(const __half *__restrict__ d, float *__restrict__ dT, int n, int nb, int64_t ldn) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)nb * ldn) return;
+    const int kb = (int)(t / ldn), c = (int)(t - (int64_t)kb * ldn);
+    dT[t] = c < n ? __half2float(d[(int64_t)c * nb + kb]) : 0.0f;
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// rows x k bytes of int8, row pitch k; box = 128 rows x 128 bytes, 128-byte swizzle, out-of-bounds -> zeros
+bool make_map(CUtensorMap *map, const void *base, int64_t rows, int64_t k) {
+    auto fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)k};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool b200_gemm_available(void) { return get_encode_fn() != nullptr; }
+
+// extra scratch the GEMM needs beyond the quantized activations: transposed scales (+ expanded Q4_0 weights)
+size_t b200_gemm_scratch_bytes(int type, int64_t k, int64_t m, int64_t n) {
+    const int64_t nb = k / 32, ldn = (n + BN - 1) / BN * BN;
+    size_t b = b200_align_up((size_t)nb * ldn * 4, 256);
+    if (type == B200_TYPE_Q4_0) b += b200_align_up((size_t)m * k, 256);
+    return b;
+}
+
+int b200_launch_gemm(b200_ctx *ctx, const b200_gemm_params &p) {
+    B200_REQUIRE(ctx, p.k % 32 == 0 && p.k >= 32 && p.m >= 1 && p.n >= 1, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, p.scratch != NULL, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, p.m < (1 << 30) && p.n < (1 << 30) && p.k < (1 << 30), B200_ERR_UNSUPPORTED);
+    const int64_t nb = p.k / 32, ldn = (p.n + BN - 1) / BN * BN;
+    float *dxT = (float *)p.scratch;
+    const int8_t *a8 = (const int8_t *)p.qs;
+    {
+        const int64_t total = nb * ldn;
+        transpose_scales_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(p.ad, dxT, (int)p.n, (int)nb, ldn);
+        ctx->launches++;
+    }
+    if (p.type == B200_TYPE_Q4_0) {
+        int8_t *w8 = (int8_t *)((uint8_t *)p.scratch + b200_align_up((size_t)nb * ldn * 4, 256));
+        const int64_t nblocks = p.m * nb;
+        expand_q4_0_kernel<<<(unsigned)((nblocks + 255) / 256), 256, 0, ctx->stream>>>((const uint4 *)p.qs, (uint4 *)w8, nblocks);
+        ctx->launches++;
+        a8 = w8;
+    }
+    B200_CUDA_TRY(ctx, cudaGetLastError());
+    CUtensorMap map_a, map_b;
+    if (!make_map(&map_a, a8, p.m, p.k) || !make_map(&map_b, p.aq, p.n, p.k)) {
+        b200_set_error(ctx, "cuTensorMapEncodeTiled failed (m=%lld n=%lld k=%lld)", (long long)p.m, (long long)p.n, (long long)p.k);
+        return B200_ERR_CUDA;
+    }
+    GemmArgs g;
+    g.dw = p.d;
+    g.dxT = dxT;
+    g.ldn = ldn;
+    g.dst = p.dst;
+    g.dots = p.dots;
+    g.m = (int)p.m;
+    g.n = (int)p.n;
+    g.k = (int)p.k;
+    dim3 grid((unsigned)((p.m + BM - 1) / BM), (unsigned)((p.n + BN - 1) / BN), 1);
+    if (p.dots) {
+        B200_CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        gemm_i8_kernel<true><<<grid, kGemmThreads, kSmemBytes, ctx->stream>>>(map_a, map_b, g);
+    } else {
+        B200_CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        gemm_i8_kernel<false><<<grid, kGemmThreads, kSmemBytes, ctx->stream>>>(map_a, map_b, g);
+    }
+    ctx->launches++;
+    B200_CUDA_TRY(ctx, cudaGetLastError());
+    return B200_OK;
 }

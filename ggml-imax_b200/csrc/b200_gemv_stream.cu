@@ -61,6 +61,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 struct StreamGeom {
     int rs;           // rows per stage
+    int pr;           // rows whose k-split partials are parked before one combine
     int stages;       // ring depth
     int g;            // warps per row (k-segments)
     int stage_qs;     // bytes of qs per full stage
@@ -156,35 +157,48 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
     pdl_wait();  // activations (and dst, for write-after-read) belong to the previous grid until here
 
     // ---- quantize the activation columns into shared memory: quantize_row_q8_0, bit-exact ----
+    // 8 lanes per block, one float4 per lane.  Loads are issued in batches of kQB per thread BEFORE any use, so a
+    // column costs ceil(k / (4*256*kQB)) L2 round trips instead of one per 1024 elements.  tasks-per-column is a
+    // multiple of 64 (k % 256 == 0), so every warp is uniformly live or dead and the shuffles see all 32 lanes.
     {
-        const char *xbase = reinterpret_cast<const char *>(p.x);
-        const int tasks = NCOLS * nb * 8;
-        for (int t = threadIdx.x; t < ((tasks + 31) & ~31); t += kConsumerThreads) {
-            const bool live = t < tasks;
-            const int tt = live ? t : tasks - 1;
-            const int c = tt / (nb * 8);
-            const int r = tt - c * (nb * 8);
-            const int b = r >> 3, sub = r & 7;
-            const float4 v = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(xbase + (size_t)c * p.nb11) + b * 32 + sub * 4);
-            float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-            const float id = amax != 0.0f ? __fdiv_rn(127.f, amax) : 0.0f;
-            const int q0 = __float2int_rn(__fmul_rn(v.x, id)), q1 = __float2int_rn(__fmul_rn(v.y, id));
-            const int q2 = __float2int_rn(__fmul_rn(v.z, id)), q3 = __float2int_rn(__fmul_rn(v.w, id));
-            int s = q0 + q1 + q2 + q3;
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            if (live) {
-                const uint32_t packed = (uint32_t)(q0 & 0xff) | ((uint32_t)(q1 & 0xff) << 8) | ((uint32_t)(q2 & 0xff) << 16) | ((uint32_t)(q3 & 0xff) << 24);
-                unsigned char *col = act + (size_t)c * g.act_col;
-                // two planes (elements 0..15 / 16..31 of every block) -> 16-byte reads at stride 16 per lane
-                *reinterpret_cast<uint32_t *>(col + (size_t)(sub >> 2) * (k >> 1) + b * 16 + (sub & 3) * 4) = packed;
-                if (sub == 0) {
-                    reinterpret_cast<float *>(col + k)[b] = __half2float(__float2half_rn(__fdiv_rn(amax, 127.f)));
-                    if (TYPE == B200_TYPE_Q4_0) reinterpret_cast<int *>(col + k + (size_t)nb * 4)[b] = 8 * s;
+        constexpr int kQB = 8;
+        const int tpc = nb * 8;
+#pragma unroll 1
+        for (int c = 0; c < NCOLS; c++) {
+            const float *xcol = reinterpret_cast<const float *>(reinterpret_cast<const char *>(p.x) + (size_t)c * p.nb11);
+            unsigned char *col = act + (size_t)c * g.act_col;
+#pragma unroll 1
+            for (int base = 0; base < tpc; base += kConsumerThreads * kQB) {
+                float4 v[kQB];
+#pragma unroll
+                for (int u = 0; u < kQB; u++) {
+                    const int t = base + u * kConsumerThreads + (int)threadIdx.x;
+                    if (t < tpc) v[u] = *reinterpret_cast<const float4 *>(xcol + (size_t)t * 4);
+                }
+#pragma unroll
+                for (int u = 0; u < kQB; u++) {
+                    const int t = base + u * kConsumerThreads + (int)threadIdx.x;
+                    if (t < tpc) {
+                        const int b = t >> 3, sub = t & 7;
+                        float amax = fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
+                        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+                        const float id = amax != 0.0f ? __fdiv_rn(127.f, amax) : 0.0f;
+                        const int q0 = __float2int_rn(__fmul_rn(v[u].x, id)), q1 = __float2int_rn(__fmul_rn(v[u].y, id));
+                        const int q2 = __float2int_rn(__fmul_rn(v[u].z, id)), q3 = __float2int_rn(__fmul_rn(v[u].w, id));
+                        int sq = q0 + q1 + q2 + q3;
+                        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+                        const uint32_t packed = (uint32_t)(q0 & 0xff) | ((uint32_t)(q1 & 0xff) << 8) | ((uint32_t)(q2 & 0xff) << 16) | ((uint32_t)(q3 & 0xff) << 24);
+                        // two planes (elements 0..15 / 16..31 of every block) -> 16-byte reads at stride 16 per lane
+                        *reinterpret_cast<uint32_t *>(col + (size_t)(sub >> 2) * (k >> 1) + b * 16 + (sub & 3) * 4) = packed;
+                        if (sub == 0) {
+                            reinterpret_cast<float *>(col + k)[b] = __half2float(__float2half_rn(__fdiv_rn(amax, 127.f)));
+                            if (TYPE == B200_TYPE_Q4_0) reinterpret_cast<int *>(col + k + (size_t)nb * 4)[b] = 8 * sq;
+                        }
+                    }
                 }
             }
         }
@@ -213,6 +227,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
         }
     }
 
+    int rows_in_chunk = 0, chunk_row0 = 0, cpar = 0;
     for (int it = 0; it < nstage_iters; it++) {
         const int s = it % g.stages;
         const uint32_t ph = (uint32_t)(it / g.stages) & 1u;
@@ -291,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
 #pragma unroll
                     for (int c = 0; c < NCOLS; c++)
                         if (c == lane) v = acc[c];
-                    if (row_live) part[(((it & 1) * g.rs + rr) * kConsumerWarps + seg) * NCOLS + lane] = v;
+                    if (row_live) part[((cpar * g.pr + rows_in_chunk + rr) * kConsumerWarps + seg) * NCOLS + lane] = v;
                 }
             }
         }
@@ -299,12 +314,20 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
         if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp is done reading stage s
 
         if (!DOTS && G > 1) {
-            consumer_bar_sync();
-            for (int t = threadIdx.x; t < rows * NCOLS; t += kConsumerThreads) {
-                const int r = t / NCOLS, c = t - r * NCOLS;
-                float v = 0.0f;
-                for (int sg = 0; sg < G; sg++) v += part[(((it & 1) * g.rs + r) * kConsumerWarps + sg) * NCOLS + c];
-                p.dst[(int64_t)c * p.m + r_begin + (int64_t)it * g.rs + r] = v;
+            // k-split: partials of up to g.pr rows are parked in shared memory (double-buffered by chunk parity) and
+            // combined in segment order after ONE barrier per chunk -- for decode shapes that is once per kernel
+            rows_in_chunk += rows;
+            if (it == nstage_iters - 1 || rows_in_chunk + g.rs > g.pr) {
+                consumer_bar_sync();
+                for (int t = threadIdx.x; t < rows_in_chunk * NCOLS; t += kConsumerThreads) {
+                    const int r = t / NCOLS, c = t - r * NCOLS;
+                    float v = 0.0f;
+                    for (int sg = 0; sg < G; sg++) v += part[((cpar * g.pr + r) * kConsumerWarps + sg) * NCOLS + c];
+                    p.dst[(int64_t)c * p.m + r_begin + chunk_row0 + r] = v;
+                }
+                chunk_row0 += rows_in_chunk;
+                rows_in_chunk = 0;
+                cpar ^= 1;
             }
         }
     }
@@ -330,7 +353,10 @@ bool stream_geometry(const b200_gemv_params &p, StreamGeom *g) {
     g->stage_bytes = (int)b200_align_up((size_t)g->stage_qs + g->stage_sc, 128);
     g->act_col = (int)stream_act_col_bytes(p.type, k);
     const int act_bytes = (int)b200_align_up((size_t)g->act_col * p.n, 128);
-    const int part_bytes = (int)b200_align_up((size_t)2 * rs * kConsumerWarps * p.n * 4, 128);
+    int pr = 64 / (int)p.n;
+    if (pr < rs) pr = rs;
+    g->pr = pr;
+    const int part_bytes = G > 1 ? (int)b200_align_up((size_t)2 * pr * kConsumerWarps * p.n * 4, 128) : 128;
     const int bar_bytes = 2 * kMaxStages * 8;
     // two of these kernels must be co-resident per SM (current + programmatic dependent): <= ~110 KB each
     const int budget = 110 * 1024 - act_bytes - part_bytes - bar_bytes - 256;

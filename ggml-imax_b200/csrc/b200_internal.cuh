@@ -92,6 +92,10 @@ struct b200_gemm_params {
     int64_t        n;
     float         *dst;        // [n][m]
     int32_t       *dots;       // non-null: dump per-block int32 partials
+    void          *scratch;    // b200_gemm_scratch_bytes(type, k, m, n) bytes
 };
 int b200_launch_gemm(b200_ctx *ctx, const b200_gemm_params &p);
 bool b200_gemm_available(void);
+size_t b200_gemm_scratch_bytes(int type, int64_t k, int64_t m, int64_t n);
+// activation scratch layout inside ctx->ws for one prefill mul_mat: [int8 plane n*k][fp16 scales n*k/32][gemm scratch]
+size_t b200_prefill_ws_bytes(int type, int64_t k, int64_t m, int64_t n);

@@ -43,15 +43,20 @@ static int run_gemv_chunks(b200_ctx *ctx, const b200_mul_mat_args *a, const uint
     return B200_OK;
 }
 
+size_t b200_prefill_ws_bytes(int type, int64_t k, int64_t m, int64_t n) {
+    return b200_align_up((size_t)n * k, 256) + b200_align_up((size_t)n * (k / 32) * 2, 256) + b200_gemm_scratch_bytes(type, k, m, n);
+}
+
 static int run_gemm(b200_ctx *ctx, const b200_mul_mat_args *a, const uint8_t *qs, const __half *d) {
     const int64_t k = a->ne00, m = a->ne01, n = a->ne11, nb = k / 32;
-    // scratch: int8 plane [n][k] + fp16 scales [n][nb], per (i12,i13) slice reused
+    // scratch: int8 plane [n][k] + fp16 scales [n][nb] + GEMM scratch, reused per (i12,i13) slice
     const size_t q_bytes = b200_align_up((size_t)n * k, 256);
     const size_t d_bytes = b200_align_up((size_t)n * nb * 2, 256);
-    int rc = b200_ws_reserve(ctx, q_bytes + d_bytes);
+    int rc = b200_ws_reserve(ctx, b200_prefill_ws_bytes(a->type, k, m, n));
     if (rc != B200_OK) return rc;
     int8_t *aq = (int8_t *)ctx->ws;
     uint16_t *ad = (uint16_t *)((uint8_t *)ctx->ws + q_bytes);
+    void *scratch = (uint8_t *)ctx->ws + q_bytes + d_bytes;
     const int64_t r2 = a->ne12 / a->ne02, r3 = a->ne13 / a->ne03;
     const int qsb = b200_qs_bytes(a->type);
     for (int64_t i13 = 0; i13 < a->ne13; i13++)
@@ -71,6 +76,7 @@ static int run_gemm(b200_ctx *ctx, const b200_mul_mat_args *a, const uint8_t *qs
             g.ad = reinterpret_cast<const __half *>(ad);
             g.n = n;
             g.dst = a->dst_dev + (i13 * a->ne12 + i12) * n * m;
+            g.scratch = scratch;
             rc = b200_launch_gemm(ctx, g);
             if (rc != B200_OK) return rc;
         }
@@ -127,7 +133,7 @@ int b200_block_dots(b200_ctx *ctx, int type, const void *src0_dev, int64_t k, in
     B200_REQUIRE(ctx, b200_gemm_available(), B200_ERR_UNSUPPORTED);
     const size_t q_bytes = b200_align_up((size_t)n * k, 256);
     const size_t d_bytes = b200_align_up((size_t)n * nb * 2, 256);
-    int rc = b200_ws_reserve(ctx, q_bytes + d_bytes);
+    int rc = b200_ws_reserve(ctx, b200_prefill_ws_bytes(type, k, m, n));
     if (rc != B200_OK) return rc;
     int8_t *aq = (int8_t *)ctx->ws;
     uint16_t *ad = (uint16_t *)((uint8_t *)ctx->ws + q_bytes);
@@ -138,6 +144,7 @@ int b200_block_dots(b200_ctx *ctx, int type, const void *src0_dev, int64_t k, in
     g.type = type; g.qs = qs; g.d = d; g.k = k; g.m = m; g.aq = aq; g.ad = reinterpret_cast<const __half *>(ad); g.n = n;
     g.dst = NULL;
     g.dots = out_dev;
+    g.scratch = (uint8_t *)ctx->ws + q_bytes + d_bytes;
     return b200_launch_gemm(ctx, g);
 }
 

@@ -258,11 +258,9 @@ void b200_graph_destroy(b200_graph *graph) {
     free(graph);
 }
 
-int b200_reserve_workspace(b200_ctx *ctx, int64_t k, int64_t n) {
-    B200_REQUIRE(ctx, ctx && k > 0 && n > 0 && k % 32 == 0, B200_ERR_INVALID);
-    const size_t q_bytes = b200_align_up((size_t)n * k, 256);
-    const size_t d_bytes = b200_align_up((size_t)n * (k / 32) * 2, 256);
-    return b200_ws_reserve(ctx, q_bytes + d_bytes);
+int b200_reserve_workspace(b200_ctx *ctx, int type, int64_t k, int64_t m, int64_t n) {
+    B200_REQUIRE(ctx, ctx && k > 0 && n > 0 && m > 0 && k % 32 == 0, B200_ERR_INVALID);
+    return b200_ws_reserve(ctx, b200_prefill_ws_bytes(type, k, m, n));
 }
 
 int b200_host_malloc(void **hptr, size_t size) {

@@ -75,7 +75,7 @@ _SIGNATURES = {
     "b200_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "b200_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_graph_destroy": (None, [C.c_void_p]),
-    "b200_reserve_workspace": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
+    "b200_reserve_workspace": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64]),
     "b200_set_quantized": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]),
     "b200_get_quantized": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]),
     "b200_repack_from_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]),
@@ -255,8 +255,8 @@ class Context:
     def graph_destroy(self, g: int):
         self.lib.b200_graph_destroy(C.c_void_p(g))
 
-    def reserve_workspace(self, k: int, n: int):
-        self._check(self.lib.b200_reserve_workspace(self.h, k, n))
+    def reserve_workspace(self, qtype: int, k: int, m: int, n: int):
+        self._check(self.lib.b200_reserve_workspace(self.h, qtype, k, m, n))
 
     # -- the path
     def quantize_row_q8_0(self, x: np.ndarray) -> np.ndarray:

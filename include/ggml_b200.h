@@ -97,8 +97,8 @@ B200_API int  b200_graph_begin(b200_ctx *ctx);
 B200_API int  b200_graph_end(b200_ctx *ctx, b200_graph **out);
 B200_API int  b200_graph_launch(b200_ctx *ctx, b200_graph *graph);
 B200_API void b200_graph_destroy(b200_graph *graph);
-/* make sure the activation scratch can hold n columns of k (no-op if already large enough) */
-B200_API int  b200_reserve_workspace(b200_ctx *ctx, int64_t k, int64_t n);
+/* make sure the scratch of a prefill mul_mat (type, k, m, n) exists (no-op if already large enough) */
+B200_API int  b200_reserve_workspace(b200_ctx *ctx, int type, int64_t k, int64_t m, int64_t n);
 
 /* ---- quantized tensor storage ("repack once at set_tensor") --------------------------------
  * A Q4_0/Q8_0 tensor of nblocks_total blocks occupies exactly its ggml_nbytes() on the device but

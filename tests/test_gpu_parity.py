@@ -109,6 +109,34 @@ def test_block_dots_gemv_bit_exact(gpu_ctx, qmm, oracle, qtype, m, k, n):
     t.free()
 
 
+@pytest.mark.parametrize("qtype", [Q4_0, Q8_0])
+@pytest.mark.parametrize("m,k,n", [(128, 128, 128), (16, 256, 16), (130, 96, 70), (300, 4096, 33), (257, 32, 129), (64, 1024, 200)])
+def test_block_dots_gemm_bit_exact(gpu_ctx, qmm, oracle, qtype, m, k, n):
+    """The int32 accumulators the tcgen05 MMAs leave in TMEM, one K=32 MMA per quant block, read back unscaled."""
+    t, wire = make_w(oracle, qmm, gpu_ctx, qtype, m, k, seed=m + k + n + 1)
+    rng = np.random.default_rng(n + 5)
+    x = rng.uniform(-1, 1, (n, k)).astype(np.float32)
+    ref = oracle.block_dots(qtype, wire, oracle.quantize_row_q8_0(x), k)
+    got = gpu_ctx.block_dots(t, x, path=1)
+    assert np.array_equal(got, ref)
+    t.free()
+
+
+@pytest.mark.parametrize("qtype", [Q4_0, Q8_0])
+@pytest.mark.parametrize("m,k,n", [(128, 128, 128), (1, 32, 9), (16, 256, 16), (300, 4096, 33), (11008 // 8, 4096, 512), (4096, 1024, 64),
+                                   (257, 736, 129), (50257 // 16, 768, 128)])
+def test_mul_mat_gemm_vs_oracle(gpu_ctx, qmm, oracle, qtype, m, k, n):
+    """Prefill shapes through the tensor-core GEMM (forced, so small n is covered too)."""
+    t, wire = make_w(oracle, qmm, gpu_ctx, qtype, m, k, seed=m * 3 + k + n)
+    rng = np.random.default_rng(m + n + 2)
+    x = rng.uniform(-1, 1, (n, k)).astype(np.float32)
+    ref = oracle.mul_mat(qtype, wire, k, m, 1, 1, x[None, None])[0, 0]
+    got = gpu_ctx.mul_mat(t, x, flags=qmm.MM_FORCE_GEMM)
+    err = nmse(got, ref)
+    assert np.all(np.isfinite(got)) and err <= MUL_MAT_NMSE_TOL and err <= 1e-9, err
+    t.free()
+
+
 # ---- mul_mat ----------------------------------------------------------------------------------------
 
 def test_mul_mat_golden_cases(gpu_ctx, qmm, golden):
