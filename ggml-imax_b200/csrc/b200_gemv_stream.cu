@@ -7,7 +7,7 @@
 //
 //  * one persistent CTA per SM; CTA c owns a contiguous run of weight rows, i.e. one contiguous byte range of
 //    the qs plane and one of the fp16 scale plane (the repacked layout makes both 16-byte aligned);
-//  * a producer thread streams that range into a shared-memory ring with 1-D bulk async copies
+//  * one elected thread streams that range into a shared-memory ring with 1-D bulk async copies
 //    (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) -- no registers are tied up by loads in flight,
 //    ~100 KB per SM can be in flight;
 //  * programmatic dependent launch: the kernel is co-resident with its predecessor (2 x ~100 KB of shared memory
@@ -25,7 +25,7 @@ namespace {
 
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kThreads = kConsumerThreads + 32;  // + producer warp
+constexpr int kThreads = kConsumerThreads;       // lane 0 of warp 0 doubles as the bulk-copy producer (8 warps -> 128 regs at 2 CTAs/SM)
 constexpr int kMaxStages = 8;
 constexpr int kSegBlocks = 128;                  // blocks of k handled by one warp (4 per lane)
 
@@ -58,6 +58,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void stamp(unsigned long long *trace, int slot) {
+    if (trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        trace[(size_t)blockIdx.x * B200_TRACE_STAMPS + slot] = t;
+    }
+}
 
 struct StreamGeom {
     int rs;           // rows per stage
@@ -77,22 +84,69 @@ __host__ __device__ inline size_t stream_act_col_bytes(int type, int k) {
     return (raw + 15) & ~(size_t)15;
 }
 
-// block dot of one 16/32-byte weight block against the activation block held as two uint4 (elements 0..15, 16..31)
+// shared-memory accessors on 32-bit shared-window addresses (keeps all ring/row arithmetic in 32-bit registers)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_h2f(uint32_t addr) {
+    unsigned short h;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
+    return __half2float(__ushort_as_half(h));
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar_addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+
+// unsigned-byte x signed-byte 4-way dot with int32 accumulate (SASS IDP.4A.U8.S8)
+__device__ __forceinline__ int dp4a_u8s8(uint32_t a, int b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// exact int32 dot of one weight block against one activation block held as two uint4 (elements 0..15, 16..31).
+//   Q4_0: low nibbles are masked in place; HIGH nibbles stay in place too (w & 0xF0F0F0F0 == 16 * nib as an unsigned
+//   byte) and go through the unsigned x signed dp4a, so their partial is exactly 16 * sum and is shifted back.
+//   (nib - 8) . q == nib . q - 8 * sum(q): s8 = 8 * sum(q) comes precomputed with the activations.
 template <int TYPE>
 __device__ __forceinline__ int block_dot(const uint4 &w0, const uint4 &w1, const uint4 &alo, const uint4 &ahi, int s8) {
-    int sumi;
     if (TYPE == B200_TYPE_Q4_0) {
-        sumi = -s8;  // (nib - 8) . q == nib . q - 8 * sum(q)
-        sumi = __dp4a((int)(w0.x & 0x0F0F0F0Fu), (int)alo.x, sumi);
-        sumi = __dp4a((int)(w0.y & 0x0F0F0F0Fu), (int)alo.y, sumi);
-        sumi = __dp4a((int)(w0.z & 0x0F0F0F0Fu), (int)alo.z, sumi);
-        sumi = __dp4a((int)(w0.w & 0x0F0F0F0Fu), (int)alo.w, sumi);
-        sumi = __dp4a((int)((w0.x >> 4) & 0x0F0F0F0Fu), (int)ahi.x, sumi);
-        sumi = __dp4a((int)((w0.y >> 4) & 0x0F0F0F0Fu), (int)ahi.y, sumi);
-        sumi = __dp4a((int)((w0.z >> 4) & 0x0F0F0F0Fu), (int)ahi.z, sumi);
-        sumi = __dp4a((int)((w0.w >> 4) & 0x0F0F0F0Fu), (int)ahi.w, sumi);
+        int lo = -s8;
+        lo = __dp4a((int)(w0.x & 0x0F0F0F0Fu), (int)alo.x, lo);
+        lo = __dp4a((int)(w0.y & 0x0F0F0F0Fu), (int)alo.y, lo);
+        lo = __dp4a((int)(w0.z & 0x0F0F0F0Fu), (int)alo.z, lo);
+        lo = __dp4a((int)(w0.w & 0x0F0F0F0Fu), (int)alo.w, lo);
+        int hi = 0;
+        hi = dp4a_u8s8(w0.x & 0xF0F0F0F0u, (int)ahi.x, hi);
+        hi = dp4a_u8s8(w0.y & 0xF0F0F0F0u, (int)ahi.y, hi);
+        hi = dp4a_u8s8(w0.z & 0xF0F0F0F0u, (int)ahi.z, hi);
+        hi = dp4a_u8s8(w0.w & 0xF0F0F0F0u, (int)ahi.w, hi);
+        return lo + (hi >> 4);                             // hi is an exact multiple of 16
     } else {
-        sumi = __dp4a((int)w0.x, (int)alo.x, 0);
+        int sumi = __dp4a((int)w0.x, (int)alo.x, 0);
         sumi = __dp4a((int)w0.y, (int)alo.y, sumi);
         sumi = __dp4a((int)w0.z, (int)alo.z, sumi);
         sumi = __dp4a((int)w0.w, (int)alo.w, sumi);
@@ -100,8 +154,8 @@ __device__ __forceinline__ int block_dot(const uint4 &w0, const uint4 &w1, const
         sumi = __dp4a((int)w1.y, (int)ahi.y, sumi);
         sumi = __dp4a((int)w1.z, (int)ahi.z, sumi);
         sumi = __dp4a((int)w1.w, (int)ahi.w, sumi);
+        return sumi;
     }
-    return sumi;
 }
 
 template <int TYPE, int NCOLS, bool DOTS>
@@ -133,68 +187,93 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
     }
     __syncthreads();
     pdl_launch_dependents();
+    if (threadIdx.x == 0) stamp(p.trace, 0);
 
-    if (warp == kConsumerWarps) {
-        // ===== producer: stream this CTA's byte ranges into the ring (does not wait for the previous grid) =====
-        if (lane == 0) {
-            const uint8_t *gq = p.qs + r_begin * row_qs;
-            const uint8_t *gs = reinterpret_cast<const uint8_t *>(p.d) + r_begin * row_sc;
-            for (int it = 0; it < nstage_iters; it++) {
-                const int s = it % g.stages;
-                const uint32_t ph = (uint32_t)(it / g.stages) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                const int rows = min(g.rs, nrows - it * g.rs);
-                unsigned char *dst = ring + (size_t)s * g.stage_bytes;
-                mbar_expect_tx(&full_bar[s], (uint32_t)(rows * (row_qs + row_sc)));
-                bulk_g2s(dst, gq + (size_t)it * g.rs * row_qs, (uint32_t)(rows * row_qs), &full_bar[s]);
-                bulk_g2s(dst + g.stage_qs, gs + (size_t)it * g.rs * row_sc, (uint32_t)(rows * row_sc), &full_bar[s]);
-            }
+    // ===== producer duty (lane 0 of warp 0): stream this CTA's byte ranges into the ring =====
+    // Stage use f may be issued once every warp has released use f - stages (empty barrier) -- and this warp itself
+    // has, which holds while f < it + stages (it = the next stage this warp will consume).  The first `stages` uses
+    // need nothing and are issued right here, BEFORE waiting for the previous grid.
+    const uint8_t *gq = p.qs + r_begin * row_qs;
+    const uint8_t *gs = reinterpret_cast<const uint8_t *>(p.d) + r_begin * row_sc;
+    int issued = 0, ist = 0;
+    uint32_t iph = 0;
+    auto produce = [&](int upto) {
+        while (issued < upto) {
+            mbar_wait(&empty_bar[ist], iph ^ 1u);
+            const int rows = min(g.rs, nrows - issued * g.rs);
+            unsigned char *dst = ring + (size_t)ist * g.stage_bytes;
+            mbar_expect_tx(&full_bar[ist], (uint32_t)(rows * (row_qs + row_sc)));
+            bulk_g2s(dst, gq, (uint32_t)(rows * row_qs), &full_bar[ist]);
+            bulk_g2s(dst + g.stage_qs, gs, (uint32_t)(rows * row_sc), &full_bar[ist]);
+            gq += (size_t)g.rs * row_qs;
+            gs += (size_t)g.rs * row_sc;
+            issued++;
+            if (++ist == g.stages) { ist = 0; iph ^= 1u; }
         }
-        return;
+    };
+    if (threadIdx.x == 0) {
+        produce(min(nstage_iters, g.stages));
+        stamp(p.trace, 1);
     }
+    __syncwarp();   // reconverge BEFORE griddepcontrol.wait: a warp parked in the wait takes its diverged lane 0 with it
 
     // ===== consumers =====
     pdl_wait();  // activations (and dst, for write-after-read) belong to the previous grid until here
+    if (threadIdx.x == 0) stamp(p.trace, 2);
+    if (p.trace && threadIdx.x == 32) {   // tracing only: when did the first / last primed stage actually land?
+        mbar_wait(&full_bar[0], 0);
+        stamp(p.trace, 6);
+        mbar_wait(&full_bar[min(nstage_iters, g.stages) - 1], 0);
+        stamp(p.trace, 7);
+    }
 
     // ---- quantize the activation columns into shared memory: quantize_row_q8_0, bit-exact ----
-    // 8 lanes per block, one float4 per lane.  Loads are issued in batches of kQB per thread BEFORE any use, so a
-    // column costs ceil(k / (4*256*kQB)) L2 round trips instead of one per 1024 elements.  tasks-per-column is a
-    // multiple of 64 (k % 256 == 0), so every warp is uniformly live or dead and the shuffles see all 32 lanes.
+    // Two lanes per block, 16 consecutive floats (4 x 128-bit loads) per lane: one amax shuffle, ONE 127/amax
+    // division per 16 elements, and the lane's 16 int8 are exactly one 16-byte store into the lo/hi plane.
+    // All loads of a batch are issued before any use (one L2 round trip per 8192 elements per CTA).
     {
-        constexpr int kQB = 8;
-        const int tpc = nb * 8;
+        constexpr int kQB = 2;
+        const int tpc = nb * 2;   // lane-tasks per column; even, and a lane's partner (lane ^ 1) shares its block
 #pragma unroll 1
         for (int c = 0; c < NCOLS; c++) {
             const float *xcol = reinterpret_cast<const float *>(reinterpret_cast<const char *>(p.x) + (size_t)c * p.nb11);
             unsigned char *col = act + (size_t)c * g.act_col;
 #pragma unroll 1
             for (int base = 0; base < tpc; base += kConsumerThreads * kQB) {
-                float4 v[kQB];
+                float4 v[kQB][4];
 #pragma unroll
                 for (int u = 0; u < kQB; u++) {
-                    const int t = base + u * kConsumerThreads + (int)threadIdx.x;
-                    if (t < tpc) v[u] = *reinterpret_cast<const float4 *>(xcol + (size_t)t * 4);
+                    const int t = min(base + u * kConsumerThreads + (int)threadIdx.x, tpc - 1);
+                    const float4 *src = reinterpret_cast<const float4 *>(xcol + (size_t)t * 16);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[u][j] = src[j];
                 }
 #pragma unroll
                 for (int u = 0; u < kQB; u++) {
-                    const int t = base + u * kConsumerThreads + (int)threadIdx.x;
-                    if (t < tpc) {
-                        const int b = t >> 3, sub = t & 7;
-                        float amax = fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
-                        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-                        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-                        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-                        const float id = amax != 0.0f ? __fdiv_rn(127.f, amax) : 0.0f;
-                        const int q0 = __float2int_rn(__fmul_rn(v[u].x, id)), q1 = __float2int_rn(__fmul_rn(v[u].y, id));
-                        const int q2 = __float2int_rn(__fmul_rn(v[u].z, id)), q3 = __float2int_rn(__fmul_rn(v[u].w, id));
-                        int sq = q0 + q1 + q2 + q3;
-                        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-                        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-                        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-                        const uint32_t packed = (uint32_t)(q0 & 0xff) | ((uint32_t)(q1 & 0xff) << 8) | ((uint32_t)(q2 & 0xff) << 16) | ((uint32_t)(q3 & 0xff) << 24);
-                        // two planes (elements 0..15 / 16..31 of every block) -> 16-byte reads at stride 16 per lane
-                        *reinterpret_cast<uint32_t *>(col + (size_t)(sub >> 2) * (k >> 1) + b * 16 + (sub & 3) * 4) = packed;
-                        if (sub == 0) {
+                    const int tt = base + u * kConsumerThreads + (int)threadIdx.x;
+                    const bool live = tt < tpc;
+                    const int t = live ? tt : tpc - 1;
+                    const int b = t >> 1, h = t & 1;
+                    float amax = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[u][j].x), fabsf(v[u][j].y)), fmaxf(fabsf(v[u][j].z), fabsf(v[u][j].w))));
+                    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                    const float id = amax != 0.0f ? __fdiv_rn(127.f, amax) : 0.0f;
+                    uint32_t pk[4];
+                    int sq = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int q0 = __float2int_rn(__fmul_rn(v[u][j].x, id)), q1 = __float2int_rn(__fmul_rn(v[u][j].y, id));
+                        const int q2 = __float2int_rn(__fmul_rn(v[u][j].z, id)), q3 = __float2int_rn(__fmul_rn(v[u][j].w, id));
+                        sq += q0 + q1 + q2 + q3;
+                        pk[j] = (uint32_t)(q0 & 0xff) | ((uint32_t)(q1 & 0xff) << 8) | ((uint32_t)(q2 & 0xff) << 16) | ((uint32_t)(q3 & 0xff) << 24);
+                    }
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                    if (live) {
+                        // plane h holds elements 16h..16h+15 of every block -> conflict-free 16-byte reads later
+                        *reinterpret_cast<uint4 *>(col + (size_t)h * (k >> 1) + (size_t)b * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        if (h == 0) {
                             reinterpret_cast<float *>(col + k)[b] = __half2float(__float2half_rn(__fdiv_rn(amax, 127.f)));
                             if (TYPE == B200_TYPE_Q4_0) reinterpret_cast<int *>(col + k + (size_t)nb * 4)[b] = 8 * sq;
                         }
@@ -204,6 +283,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
         }
     }
     consumer_bar_sync();
+    if (threadIdx.x == 0) stamp(p.trace, 3);
 
     // ---- which (row-in-pass, k-segment) this warp serves ----
     const int G = g.g;
@@ -212,6 +292,18 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
     const int rows_per_pass = kConsumerWarps / G;
     const int b0 = seg * kSegBlocks;  // first block of the segment
 
+    const uint32_t ring_a = smem_u32(ring), act_a = smem_u32(act);
+    const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+
+    // per-lane loop invariants: the lane's 4 blocks are b0 + lane + 32 i, i.e. fixed byte offsets inside a row plus
+    // compile-time multiples of 32 blocks.  Lanes past the end of a short row ("dead", k < 4096 * segments) read
+    // whatever follows in shared memory (the allocation is padded) and are predicated off at the accumulate.
+    const uint32_t woff0 = (uint32_t)((b0 + lane) * QSB);
+    const uint32_t soff0 = (uint32_t)(g.stage_qs + (b0 + lane) * 2);
+    bool blive[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) blive[i] = b0 + lane + 32 * i < nb;
+
     // n == 1: the lane's activation blocks live in registers for the whole kernel
     uint4 alo[4], ahi[4];
     float da[4];
@@ -219,105 +311,139 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
     if (NCOLS == 1) {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const int b = min(b0 + lane + 32 * i, nb - 1);
-            alo[i] = *reinterpret_cast<const uint4 *>(act + (size_t)b * 16);
-            ahi[i] = *reinterpret_cast<const uint4 *>(act + (size_t)(k >> 1) + (size_t)b * 16);
-            da[i] = reinterpret_cast<const float *>(act + k)[b];
-            s8[i] = TYPE == B200_TYPE_Q4_0 ? reinterpret_cast<const int *>(act + k + (size_t)nb * 4)[b] : 0;
+            const uint32_t b = (uint32_t)min(b0 + lane + 32 * i, nb - 1);
+            alo[i] = lds128(act_a + b * 16);
+            ahi[i] = lds128(act_a + (uint32_t)(k >> 1) + b * 16);
+            da[i] = lds_f32(act_a + (uint32_t)k + b * 4);
+            s8[i] = TYPE == B200_TYPE_Q4_0 ? lds_s32(act_a + (uint32_t)k + (uint32_t)nb * 4 + b * 4) : 0;
         }
     }
 
-    int rows_in_chunk = 0, chunk_row0 = 0, cpar = 0;
-    for (int it = 0; it < nstage_iters; it++) {
-        const int s = it % g.stages;
-        const uint32_t ph = (uint32_t)(it / g.stages) & 1u;
-        const int rows = min(g.rs, nrows - it * g.rs);
-        const unsigned char *sq = ring + (size_t)s * g.stage_bytes;
-        const unsigned char *ssc = sq + g.stage_qs;
-        mbar_wait(&full_bar[s], ph);
-
-        for (int r0 = 0; r0 < rows; r0 += rows_per_pass) {
-            const int r = r0 + row_in_pass;
-            const bool row_live = r < rows;
-            const int rr = row_live ? r : rows - 1;
-            const unsigned char *wrow = sq + (size_t)rr * row_qs;
-            const __half *srow = reinterpret_cast<const __half *>(ssc + (size_t)rr * row_sc);
-            const int64_t grow = r_begin + (int64_t)it * g.rs + rr;
-            float acc[NCOLS];
+    // The warp's rows form a sequence of "slots" (stage, pass).  kU slots are processed as ONE straight-line block:
+    // wait for the stages they live in, kU independent row dots, one joint shuffle reduction, release the stages.
+    // All stage/pass bookkeeping is incremental (no divisions) and all shared addresses are 32-bit.
+    constexpr int kU = NCOLS == 1 ? 4 : (NCOLS <= 2 ? 2 : 1);
+    const int ppst = g.rs / rows_per_pass;            // passes per stage
+    const int total_slots = nstage_iters * ppst;
+    const int gsz = min(kU, g.stages * ppst);         // a group holds its stages until released: stay inside the ring
+    int rows_in_chunk = 0, chunk_row0 = 0, cpar = 0;  // k-split bookkeeping (G > 1, where ppst == 1)
+    int it = 0, ps = 0, st = 0;                       // stage iteration / pass / ring slot of the next slot
+    uint32_t par = 0;                                 // parity of the full barrier for `it`
+    for (int j0 = 0; j0 < total_slots; j0 += gsz) {
+        const int nslot = min(gsz, total_slots - j0);
+        if (threadIdx.x == 0) produce(min(nstage_iters, it + g.stages));
+        __syncwarp();
+        float acc[kU][NCOLS];
+        int grow[kU];          // row index relative to r_begin
+        int prow[kU];          // row index relative to the k-split chunk
+        bool rlive[kU];
+        uint32_t wbase[kU], sbase[kU];
+        uint32_t rel_mask = 0;  // bit u: slot u is the last pass of its stage; bits 8.. : its ring slot (4 bits each)
+        int chunk_rows_added = 0;
+        // ---- phase 1: wait for the stages, resolve row addresses ----
 #pragma unroll
-            for (int c = 0; c < NCOLS; c++) acc[c] = 0.0f;
-
+        for (int u = 0; u < kU; u++) {
+            const bool valid = u < nslot;
+            if (valid && (ps == 0 || u == 0)) {
+                mbar_wait_a(full_a + 8u * (uint32_t)st, par);
+                if (j0 == 0 && u == 0 && threadIdx.x == 0) stamp(p.trace, 4);
+            }
+            const int rows = valid ? min(g.rs, nrows - it * g.rs) : 1;   // slots past the group alias row 0 of the ring
+            const int r = ps * rows_per_pass + row_in_pass;
+            rlive[u] = valid && r < rows;
+            const int rr = valid ? min(r, rows - 1) : 0;
+            const uint32_t stage_a = ring_a + (valid ? (uint32_t)(st * g.stage_bytes) : 0u);
+            wbase[u] = stage_a + (uint32_t)(rr * row_qs);
+            sbase[u] = stage_a + (uint32_t)(rr * row_sc);   // + soff[i] (which already includes stage_qs)
+            grow[u] = it * g.rs + rr;
+            prow[u] = rows_in_chunk + chunk_rows_added + rr;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int bb = b0 + lane + 32 * i;
-                const bool live = bb < nb && bb < b0 + kSegBlocks;
-                const int b = live ? bb : nb - 1;
-                const uint4 w0 = *reinterpret_cast<const uint4 *>(wrow + (size_t)b * QSB);
+            for (int c = 0; c < NCOLS; c++) acc[u][c] = 0.0f;
+            if (valid) {
+                if (ps + 1 == ppst) {      // leaving the stage after this slot
+                    rel_mask |= (1u << u) | ((uint32_t)st << (8 + 4 * u));
+                    if (G > 1) chunk_rows_added += rows;
+                    ps = 0;
+                    it++;
+                    if (++st == g.stages) { st = 0; par ^= 1u; }
+                } else {
+                    ps++;
+                }
+            }
+        }
+        // ---- phase 2: the dots (straight-line) ----
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const uint4 w0 = lds128(wbase[u] + woff0 + (uint32_t)(i * 32 * QSB));
                 uint4 w1 = make_uint4(0, 0, 0, 0);
-                if (TYPE == B200_TYPE_Q8_0) w1 = *reinterpret_cast<const uint4 *>(wrow + (size_t)b * QSB + 16);
-                const float dw = __half2float(srow[b]);
+                if (TYPE == B200_TYPE_Q8_0) w1 = lds128(wbase[u] + woff0 + (uint32_t)(i * 32 * QSB + 16));
+                const float dw = lds_h2f(sbase[u] + soff0 + (uint32_t)(i * 64));
                 if (NCOLS == 1) {
                     const int sumi = block_dot<TYPE>(w0, w1, alo[i], ahi[i], s8[i]);
                     if (DOTS) {
-                        if (live && row_live) p.dots[grow * nb + b] = sumi;
-                    } else if (live) {
-                        acc[0] = fmaf((float)sumi, dw * da[i], acc[0]);
+                        if (blive[i] && rlive[u]) p.dots[(r_begin + grow[u]) * nb + b0 + lane + 32 * i] = sumi;
+                    } else if (blive[i]) {
+                        acc[u][0] = fmaf((float)sumi, dw * da[i], acc[u][0]);
                     }
                 } else {
+                    const uint32_t b = (uint32_t)min(b0 + lane + 32 * i, nb - 1);
 #pragma unroll
                     for (int c = 0; c < NCOLS; c++) {
-                        const unsigned char *col = act + (size_t)c * g.act_col;
-                        const uint4 xlo = *reinterpret_cast<const uint4 *>(col + (size_t)b * 16);
-                        const uint4 xhi = *reinterpret_cast<const uint4 *>(col + (size_t)(k >> 1) + (size_t)b * 16);
-                        const float dx = reinterpret_cast<const float *>(col + k)[b];
-                        const int sx = TYPE == B200_TYPE_Q4_0 ? reinterpret_cast<const int *>(col + k + (size_t)nb * 4)[b] : 0;
+                        const uint32_t col = act_a + (uint32_t)(c * g.act_col);
+                        const uint4 xlo = lds128(col + b * 16);
+                        const uint4 xhi = lds128(col + (uint32_t)(k >> 1) + b * 16);
+                        const float dx = lds_f32(col + (uint32_t)k + b * 4);
+                        const int sx = TYPE == B200_TYPE_Q4_0 ? lds_s32(col + (uint32_t)k + (uint32_t)nb * 4 + b * 4) : 0;
                         const int sumi = block_dot<TYPE>(w0, w1, xlo, xhi, sx);
                         if (DOTS) {
-                            if (live && row_live) p.dots[((int64_t)c * p.m + grow) * nb + b] = sumi;
-                        } else if (live) {
-                            acc[c] = fmaf((float)sumi, dw * dx, acc[c]);
+                            if (blive[i] && rlive[u]) p.dots[((int64_t)c * p.m + r_begin + grow[u]) * nb + b] = sumi;
+                        } else if (blive[i]) {
+                            acc[u][c] = fmaf((float)sumi, dw * dx, acc[u][c]);
                         }
                     }
                 }
             }
+        }
+        // ---- phase 3: release every stage whose last pass was in this group ----
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < kU; u++)
+                if (rel_mask & (1u << u)) mbar_arrive_a(empty_a + 8u * ((rel_mask >> (8 + 4 * u)) & 15u));
+        }
+        rows_in_chunk += chunk_rows_added;
 
-            if (!DOTS) {
+        if (!DOTS) {
 #pragma unroll
-                for (int c = 0; c < NCOLS; c++) {
-                    float v = acc[c];
-                    v += __shfl_xor_sync(0xffffffffu, v, 16);
-                    v += __shfl_xor_sync(0xffffffffu, v, 8);
-                    v += __shfl_xor_sync(0xffffffffu, v, 4);
-                    v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    v += __shfl_xor_sync(0xffffffffu, v, 1);
-                    acc[c] = v;
-                }
-                if (G == 1) {
-                    if (row_live && lane < NCOLS) {
-                        float v = 0.0f;
+            for (int off = 16; off >= 1; off >>= 1)
 #pragma unroll
-                        for (int c = 0; c < NCOLS; c++)
-                            if (c == lane) v = acc[c];
-                        p.dst[(int64_t)lane * p.m + grow] = v;
-                    }
-                } else if (lane < NCOLS) {
-                    // k-split: park this segment's partial; combined below in segment order (deterministic)
-                    float v = 0.0f;
+                for (int u = 0; u < kU; u++)
+#pragma unroll
+                    for (int c = 0; c < NCOLS; c++) acc[u][c] += __shfl_xor_sync(0xffffffffu, acc[u][c], off);
+            // lane (u * NCOLS + c) publishes value (u, c)
+            if (lane < kU * NCOLS) {
+                float v = 0.0f;
+                int gr = 0, pr = 0;
+                bool lv = false;
+#pragma unroll
+                for (int u = 0; u < kU; u++)
 #pragma unroll
                     for (int c = 0; c < NCOLS; c++)
-                        if (c == lane) v = acc[c];
-                    if (row_live) part[((cpar * g.pr + rows_in_chunk + rr) * kConsumerWarps + seg) * NCOLS + lane] = v;
+                        if (lane == u * NCOLS + c) { v = acc[u][c]; gr = grow[u]; pr = prow[u]; lv = rlive[u]; }
+                const int c = lane % NCOLS;
+                if (lv) {
+                    if (G == 1) p.dst[(int64_t)c * p.m + r_begin + gr] = v;
+                    else part[((cpar * g.pr + pr) * kConsumerWarps + seg) * NCOLS + c] = v;   // k-split: park the partial
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp is done reading stage s
 
         if (!DOTS && G > 1) {
             // k-split: partials of up to g.pr rows are parked in shared memory (double-buffered by chunk parity) and
-            // combined in segment order after ONE barrier per chunk -- for decode shapes that is once per kernel
-            rows_in_chunk += rows;
-            if (it == nstage_iters - 1 || rows_in_chunk + g.rs > g.pr) {
+            // combined in segment order after ONE barrier per chunk -- for decode shapes that is once per kernel.
+            if (j0 + gsz >= total_slots || rows_in_chunk + kU * g.rs > g.pr) {
                 consumer_bar_sync();
                 for (int t = threadIdx.x; t < rows_in_chunk * NCOLS; t += kConsumerThreads) {
                     const int r = t / NCOLS, c = t - r * NCOLS;
@@ -331,6 +457,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
             }
         }
     }
+    if (threadIdx.x == 0) stamp(p.trace, 5);
 }
 
 bool stream_geometry(const b200_gemv_params &p, StreamGeom *g) {
@@ -354,12 +481,12 @@ bool stream_geometry(const b200_gemv_params &p, StreamGeom *g) {
     g->act_col = (int)stream_act_col_bytes(p.type, k);
     const int act_bytes = (int)b200_align_up((size_t)g->act_col * p.n, 128);
     int pr = 64 / (int)p.n;
-    if (pr < rs) pr = rs;
+    if (pr < 4 * rs) pr = 4 * rs;   // at least one group of kU (<= 4) stages
     g->pr = pr;
     const int part_bytes = G > 1 ? (int)b200_align_up((size_t)2 * pr * kConsumerWarps * p.n * 4, 128) : 128;
     const int bar_bytes = 2 * kMaxStages * 8;
     // two of these kernels must be co-resident per SM (current + programmatic dependent): <= ~110 KB each
-    const int budget = 110 * 1024 - act_bytes - part_bytes - bar_bytes - 256;
+    const int budget = 110 * 1024 - act_bytes - part_bytes - bar_bytes - 8192 - 256;
     int stages = budget / g->stage_bytes;
     if (stages < 2) return false;
     if (stages > kMaxStages) stages = kMaxStages;
@@ -368,7 +495,7 @@ bool stream_geometry(const b200_gemv_params &p, StreamGeom *g) {
     g->act_off = stages * g->stage_bytes;
     g->part_off = g->act_off + act_bytes;
     g->bar_off = g->part_off + part_bytes;
-    g->total = g->bar_off + bar_bytes;
+    g->total = g->bar_off + bar_bytes + 8192;   // slack for the unclamped reads of dead lanes
     return true;
 }
 
@@ -389,7 +516,11 @@ int launch_stream_typed(b200_ctx *ctx, const b200_gemv_params &p, const StreamGe
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = ctx->opt_pdl ? 1 : 0;
-    B200_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kern, p, g));
+    b200_gemv_params pp = p;
+    pp.trace = NULL;
+    if (ctx->trace && ctx->trace_next < ctx->trace_capacity)
+        pp.trace = ctx->trace + (size_t)(ctx->trace_next++) * B200_TRACE_MAX_CTAS * B200_TRACE_STAMPS;
+    B200_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kern, pp, g));
     ctx->launches++;
     return B200_OK;
 }

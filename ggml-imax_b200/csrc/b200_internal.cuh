@@ -27,11 +27,18 @@ struct b200_ctx {
     int          opt_gemm;
     int          opt_gemv_max_n;
     int          opt_gemv_stream;
+    // optional device-side timeline: 8 x u64 %globaltimer stamps per (launch, CTA), see b200_ctx_set_trace
+    unsigned long long *trace;
+    int64_t      trace_capacity;   // in launches
+    int64_t      trace_next;       // next launch slot
     int64_t      launches;
     char         err[512];
 };
 
 void b200_set_error(b200_ctx *ctx, const char *fmt, ...);
+
+#define B200_TRACE_STAMPS 8
+#define B200_TRACE_MAX_CTAS 160
 
 #define B200_CUDA_TRY(ctx, call)                                                                   \
     do {                                                                                           \
@@ -78,6 +85,7 @@ struct b200_gemv_params {
     float         *dst;        // dense [ne13][ne12][dst_n][m], already offset to this launch's first column
     int64_t        dst_n;      // columns of the whole dst (>= n when the caller chunks columns)
     int32_t       *dots;       // non-null: dump per-block int32 partials [n][m][k/32] instead of dst
+    unsigned long long *trace; // non-null: this launch's [gridDim.x][8] timestamp slots
 };
 int b200_launch_gemv(b200_ctx *ctx, const b200_gemv_params &p);
 bool b200_try_launch_gemv_stream(b200_ctx *ctx, const b200_gemv_params &p, int *rc);

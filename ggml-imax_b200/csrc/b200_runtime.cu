@@ -132,6 +132,14 @@ int b200_ctx_set_option(b200_ctx *ctx, const char *key, int64_t value) {
     return B200_ERR_INVALID;
 }
 
+int b200_ctx_set_trace(b200_ctx *ctx, void *trace_dev, int64_t max_launches) {
+    B200_REQUIRE(ctx, ctx != NULL, B200_ERR_INVALID);
+    ctx->trace = (unsigned long long *)trace_dev;
+    ctx->trace_capacity = trace_dev ? max_launches : 0;
+    ctx->trace_next = 0;
+    return B200_OK;
+}
+
 int b200_malloc(b200_ctx *ctx, void **dptr, size_t size) {
     B200_REQUIRE(ctx, ctx && dptr, B200_ERR_INVALID);
     B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));

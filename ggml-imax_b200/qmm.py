@@ -60,6 +60,7 @@ _SIGNATURES = {
     "b200_ctx_device": (C.c_int, [C.c_void_p]),
     "b200_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "b200_ctx_launch_count": (C.c_int64, [C.c_void_p]),
+    "b200_ctx_set_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "b200_malloc": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t]),
     "b200_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_memset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
@@ -240,6 +241,9 @@ class Context:
         if arr.nbytes:
             b.upload(arr)
         return b
+
+    def set_trace(self, buf, max_launches: int):
+        self._check(self.lib.b200_ctx_set_trace(self.h, _ptr(buf), max_launches))
 
     def graph_begin(self):
         self._check(self.lib.b200_graph_begin(self.h))

@@ -68,6 +68,12 @@ B200_API int  b200_ctx_set_option(b200_ctx *ctx, const char *key, int64_t value)
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 B200_API int64_t b200_ctx_launch_count(const b200_ctx *ctx);
 
+/* device-side timeline for profiling the decode kernels (the reference has only host-side GGML_PERF counters,
+ * src/ggml.c:19198-19205): trace_dev = room for max_launches * 160 * 8 uint64 (%globaltimer ns stamps per CTA:
+ * 0 entry, 1 ring primed, 2 predecessor done (griddepcontrol.wait), 3 activations quantized, 4 first weights
+ * landed, 5 last row done).  NULL switches it off.  Launch i of the context after this call uses slot i. */
+B200_API int  b200_ctx_set_trace(b200_ctx *ctx, void *trace_dev, int64_t max_launches);
+
 /* ---- device buffers -----------------------------------------------------------------------
  * replaces ggml_backend_buffer_type_i.alloc_buffer and ggml_backend_buffer_i.{free_buffer,clear,
  * set_tensor,get_tensor,cpy_tensor} for non-quantized data (src/ggml-backend-impl.h:18-48) */
