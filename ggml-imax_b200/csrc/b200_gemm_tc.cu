@@ -8,14 +8,14 @@
 // so every MMA produces the exact int32 block partials of a 128 x 128 tile; they are read back from TMEM,
 // converted, multiplied by the product of the two fp16 scales and accumulated in fp32 registers.
 //
-// CTA = one 128(m) x 128(n) output tile, 12 warps:
+// CTA = one 128(m) x 128(n) output tile, 20 warps:
 //   warp 0      TMA producer: A tile (128 rows x 128 B) and B tile (128 x 128 B) per stage, SWIZZLE_128B, 4 k-blocks
 //   warp 1      MMA issuer: 4 x tcgen05.mma (K=32 each) per stage, each into its own 128-column TMEM buffer
 //               (4 buffers = all 512 columns), tcgen05.commit -> mbarriers (TMEM full, smem stage empty)
 //   warp 2      TMEM allocator / deallocator
-//   warps 4-11  epilogue: warp w reads TMEM lanes 32*(w%4).. (its hardware quadrant), columns 64*((w-4)/4)..;
+//   warps 4-19  epilogue: warp w reads TMEM lanes 32*(w%4).. (its hardware quadrant), columns 32*((w-4)/4)..;
 //               thread = one weight row: d_w is a per-thread scalar, d_x a warp-uniform (broadcast) load;
-//               64 fp32 accumulators per thread; final store is coalesced along m.
+//               32 fp32 accumulators per thread; final store is coalesced along m.
 // Q4_0 weights are expanded to int8 (nib - 8) by expand_q4_0_kernel into scratch first (v1; fusing the expansion
 // behind the TMA load is the next step).
 #include "b200_internal.cuh"
@@ -27,9 +27,10 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 128;  // BK bytes of int8 = one 128-byte swizzle atom = 4 quant blocks
 constexpr int kStages = 4;
 constexpr int kTmemBufs = 4;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;                // 4 per TMEM lane quadrant, BN / 4 = 32 columns each
 constexpr int kGemmThreads = 128 + kEpiWarps * 32;
-constexpr int kStageBytes = BM * BK + BN * BK;  // 32 KB
+constexpr int kScaleBytes = (BK / 32) * BN * 4;            // activation scales of the stage's 4 k-blocks: [4][128] fp32
+constexpr int kStageBytes = BM * BK + BN * BK + kScaleBytes;  // 34 KB (a multiple of 1024: operand tiles stay 1024-aligned)
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,6 +84,23 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+// packed fp32 pairs (sm_100 f32x2 arithmetic): one 64-bit register = {lo, hi}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B (8-row x 128-byte atoms, 1024 B apart), sm_100 version bit
@@ -110,7 +128,8 @@ struct GemmArgs {
 
 template <bool DOTS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_s, const GemmArgs g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
@@ -128,9 +147,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_s) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1 + kEpiWarps); }
         for (int b = 0; b < kTmemBufs; b++) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -155,6 +175,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_expect_tx(&full_bar[s], kStageBytes);
                 tma_load_2d(sa, &map_a, it * BK, m0, &full_bar[s]);
                 tma_load_2d(sb, &map_b, it * BK, n0, &full_bar[s]);
+                tma_load_2d(sb + BN * BK, &map_s, n0, it * (BK / 32), &full_bar[s]);   // d_x[4 k-blocks][128 columns]
             }
         }
     } else if (warp == 1) {
@@ -188,58 +209,89 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ===== epilogue =====
         const int ew = warp - 4;
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-        const int half = ew >> 2;                  // which 64 of the 128 columns
+        const int cgrp = ew >> 2;                  // which kCols-wide column group of the tile
         const int row = m0 + quad * 32 + lane;     // weight row owned by this thread
         const int row_c = row < g.m ? row : g.m - 1;
         const __half *dwp = g.dw + (int64_t)row_c * nb;
-        const float *dxp = g.dxT + n0 + half * 64;
-        float acc[64];
+        constexpr int kCols = BN / (kEpiWarps / 4);
+        static_assert(kCols == 32, "one tcgen05.ld.32x32b.x32 per k-block per warp");
+        float acc[kCols];
+        unsigned long long acc2[kCols / 2];   // packed pairs of fp32 accumulators
 #pragma unroll
-        for (int j = 0; j < 64; j++) acc[j] = 0.0f;
+        for (int j = 0; j < kCols / 2; j++) acc2[j] = 0ull;
 
-        for (int kb = 0; kb < nb; kb++) {
-            const int buf = kb % kTmemBufs;
-            const uint32_t tph = (uint32_t)(kb / kTmemBufs) & 1u;
-            const float dw = __half2float(dwp[kb]);
-            mbar_wait(&tfull_bar[buf], tph);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + half * 64);
-            uint32_t p0[32], p1[32];
-            tc_ld32(taddr, p0);
-            tc_ld32(taddr + 32, p1);
-            tc_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[buf]);   // TMEM buffer may be overwritten by MMA kb + 4
-            if (DOTS) {
-                if (row < g.m) {
+        // One iteration = one smem stage = 4 k-blocks = 4 TMEM buffers (kTmemBufs == BK/32), so buffer indices are
+        // compile-time, the mbarrier parity is one bit per iteration, and the 4 weight scales of the stage are one
+        // 8-byte load issued a full iteration ahead.  The scale math is packed f32x2 (FMUL2 / FFMA2 on sm_100).
+        static_assert(kTmemBufs == BK / 32, "one TMEM buffer per k-block of a stage");
+        const uint32_t smem_a = smem_u32(smem);
+        const bool dw_vec = (nb & 3) == 0;                 // rows of d_w are 8-byte aligned
+        uint2 dwq = make_uint2(0, 0);
+        auto load_dw = [&](int it) -> uint2 {
+            const int kb0 = it * 4;
+            if (dw_vec) return *reinterpret_cast<const uint2 *>(dwp + kb0);
+            uint16_t h[4];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int c0 = n0 + half * 64 + j, c1 = c0 + 32;
-                        if (c0 < g.n) g.dots[((int64_t)c0 * g.m + row) * nb + kb] = (int32_t)p0[j];
-                        if (c1 < g.n) g.dots[((int64_t)c1 * g.m + row) * nb + kb] = (int32_t)p1[j];
+            for (int j = 0; j < 4; j++) h[j] = kb0 + j < nb ? __half_as_ushort(dwp[kb0 + j]) : (uint16_t)0;
+            return make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+        };
+        dwq = load_dw(0);
+        int st = 0;
+        uint32_t tph = 0;
+        for (int it = 0; it < kiters; it++) {
+            const uint2 dwcur = dwq;
+            if (it + 1 < kiters) dwq = load_dw(it + 1);
+            const uint32_t sdx = smem_a + (uint32_t)(st * kStageBytes + BM * BK + BN * BK + cgrp * kCols * 4);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int kb = it * 4 + j;
+                if (kb < nb) {
+                    const uint32_t hbits = (j < 2 ? dwcur.x : dwcur.y) >> ((j & 1) * 16);
+                    const float dw = __half2float(__ushort_as_half((unsigned short)(hbits & 0xffffu)));
+                    mbar_wait(&tfull_bar[j], tph);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * BN + cgrp * kCols);
+                    uint32_t pv[32];
+                    tc_ld32(taddr, pv);
+                    tc_wait_ld();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[j]);   // TMEM buffer j may be overwritten by the next stage's MMA
+                    if (DOTS) {
+                        if (row < g.m) {
+#pragma unroll
+                            for (int c = 0; c < kCols; c++) {
+                                const int col = n0 + cgrp * kCols + c;
+                                if (col < g.n) g.dots[((int64_t)col * g.m + row) * nb + kb] = (int32_t)pv[c];
+                            }
+                        }
+                    } else {
+                        const unsigned long long dw2 = pack2(dw, dw);
+#pragma unroll
+                        for (int c4 = 0; c4 < kCols / 4; c4++) {
+                            unsigned long long d01, d23;   // d_x of 4 columns: warp-uniform shared-memory broadcast
+                            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(d01), "=l"(d23) : "r"(sdx + (uint32_t)(j * BN * 4 + c4 * 16)));
+                            const unsigned long long s01 = mul2(dw2, d01), s23 = mul2(dw2, d23);
+                            const unsigned long long v01 = pack2((float)(int32_t)pv[c4 * 4 + 0], (float)(int32_t)pv[c4 * 4 + 1]);
+                            const unsigned long long v23 = pack2((float)(int32_t)pv[c4 * 4 + 2], (float)(int32_t)pv[c4 * 4 + 3]);
+                            acc2[c4 * 2 + 0] = fma2(v01, s01, acc2[c4 * 2 + 0]);
+                            acc2[c4 * 2 + 1] = fma2(v23, s23, acc2[c4 * 2 + 1]);
+                        }
                     }
                 }
-            } else {
-                const float4 *dx4 = reinterpret_cast<const float4 *>(dxp + (int64_t)kb * g.ldn);
-#pragma unroll
-                for (int j4 = 0; j4 < 8; j4++) {
-                    const float4 d0 = __ldg(dx4 + j4), d1 = __ldg(dx4 + 8 + j4);
-                    acc[j4 * 4 + 0] = fmaf((float)(int32_t)p0[j4 * 4 + 0], dw * d0.x, acc[j4 * 4 + 0]);
-                    acc[j4 * 4 + 1] = fmaf((float)(int32_t)p0[j4 * 4 + 1], dw * d0.y, acc[j4 * 4 + 1]);
-                    acc[j4 * 4 + 2] = fmaf((float)(int32_t)p0[j4 * 4 + 2], dw * d0.z, acc[j4 * 4 + 2]);
-                    acc[j4 * 4 + 3] = fmaf((float)(int32_t)p0[j4 * 4 + 3], dw * d0.w, acc[j4 * 4 + 3]);
-                    acc[32 + j4 * 4 + 0] = fmaf((float)(int32_t)p1[j4 * 4 + 0], dw * d1.x, acc[32 + j4 * 4 + 0]);
-                    acc[32 + j4 * 4 + 1] = fmaf((float)(int32_t)p1[j4 * 4 + 1], dw * d1.y, acc[32 + j4 * 4 + 1]);
-                    acc[32 + j4 * 4 + 2] = fmaf((float)(int32_t)p1[j4 * 4 + 2], dw * d1.z, acc[32 + j4 * 4 + 2]);
-                    acc[32 + j4 * 4 + 3] = fmaf((float)(int32_t)p1[j4 * 4 + 3], dw * d1.w, acc[32 + j4 * 4 + 3]);
-                }
             }
+            // done with this stage's scales: let the producer refill it
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[st]);
+            tph ^= 1u;
+            if (++st == kStages) st = 0;
         }
+#pragma unroll
+        for (int c2 = 0; c2 < kCols / 2; c2++) unpack2(acc2[c2], acc[c2 * 2], acc[c2 * 2 + 1]);
         if (!DOTS && row < g.m) {
 #pragma unroll
-            for (int j = 0; j < 64; j++) {
-                const int c = n0 + half * 64 + j;
+            for (int j = 0; j < kCols; j++) {
+                const int c = n0 + cgrp * kCols + j;
                 if (c < g.n) g.dst[(int64_t)c * g.m + row] = acc[j];   // 32 lanes -> 128 contiguous bytes
             }
         }
@@ -303,6 +355,18 @@ bool make_map(CUtensorMap *map, const void *base, int64_t rows, int64_t k) {
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// transposed activation scales [nb][ldn] fp32; box = 4 k-blocks x 128 columns, rows past nb -> zeros
+bool make_scale_map(CUtensorMap *map, const void *base, int64_t nb, int64_t ldn) {
+    auto fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)ldn, (cuuint64_t)nb};
+    cuuint64_t strides[1] = {(cuuint64_t)ldn * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BN, (cuuint32_t)(BK / 32)};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 bool b200_gemm_available(void) { return get_encode_fn() != nullptr; }
@@ -335,8 +399,8 @@ int b200_launch_gemm(b200_ctx *ctx, const b200_gemm_params &p) {
         a8 = w8;
     }
     B200_CUDA_TRY(ctx, cudaGetLastError());
-    CUtensorMap map_a, map_b;
-    if (!make_map(&map_a, a8, p.m, p.k) || !make_map(&map_b, p.aq, p.n, p.k)) {
+    CUtensorMap map_a, map_b, map_s;
+    if (!make_map(&map_a, a8, p.m, p.k) || !make_map(&map_b, p.aq, p.n, p.k) || !make_scale_map(&map_s, dxT, nb, ldn)) {
         b200_set_error(ctx, "cuTensorMapEncodeTiled failed (m=%lld n=%lld k=%lld)", (long long)p.m, (long long)p.n, (long long)p.k);
         return B200_ERR_CUDA;
     }
@@ -352,10 +416,10 @@ int b200_launch_gemm(b200_ctx *ctx, const b200_gemm_params &p) {
     dim3 grid((unsigned)((p.m + BM - 1) / BM), (unsigned)((p.n + BN - 1) / BN), 1);
     if (p.dots) {
         B200_CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        gemm_i8_kernel<true><<<grid, kGemmThreads, kSmemBytes, ctx->stream>>>(map_a, map_b, g);
+        gemm_i8_kernel<true><<<grid, kGemmThreads, kSmemBytes, ctx->stream>>>(map_a, map_b, map_s, g);
     } else {
         B200_CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        gemm_i8_kernel<false><<<grid, kGemmThreads, kSmemBytes, ctx->stream>>>(map_a, map_b, g);
+        gemm_i8_kernel<false><<<grid, kGemmThreads, kSmemBytes, ctx->stream>>>(map_a, map_b, map_s, g);
     }
     ctx->launches++;
     B200_CUDA_TRY(ctx, cudaGetLastError());
