@@ -48,12 +48,20 @@ LAYER_MATS = [("q", N_EMBD, N_EMBD), ("k", N_EMBD, N_EMBD), ("v", N_EMBD, N_EMBD
 WORKLOAD = "gptj6b_q4_0_decode_mul_mat_chain(28x[4x4096^2,16384x4096,4096x16384]+50400x4096,n=1)"
 
 
-def load_qmm():
-    spec = importlib.util.spec_from_file_location("ggml_imax_b200_qmm", PKG / "qmm.py")
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
     mod = importlib.util.module_from_spec(spec)
-    sys.modules["ggml_imax_b200_qmm"] = mod
+    sys.modules[name] = mod
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_qmm():
+    return _load("ggml_imax_b200_qmm", PKG / "qmm.py")
+
+
+def load_rowsplit():
+    return _load("ggml_imax_b200_rowsplit", PKG / "rowsplit.py")
 
 
 def chain_mats():
@@ -139,6 +147,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     qmm = load_qmm()
+    rs = load_rowsplit()
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx = qmm.Context(local_rank, stream=stream.cuda_stream)   # our launches go to torch's stream: plumbing only
@@ -149,18 +158,17 @@ def run_b200(args):
     host_w = {}
     for name, m, k in set(mats):
         host_w[(m, k)] = qmm.random_wire_weights(Q4_0, k, m, seed=1234 + m + k)
-    weights = []       # (QTensor slice, m_slice, chunk c, m, k)
+    weights = []       # (QTensor row slice, RowSplit, k)
     keep = []
     for name, m, k in mats:
-        c = (m + world - 1) // world
-        r0, r1 = min(rank * c, m), min((rank + 1) * c, m)
-        nbytes = max(r1 - r0, 1) * (k // 32) * 18
+        split = rs.RowSplit(m, world, rank)
+        nbytes = max(split.rows, 1) * (k // 32) * 18
         buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         keep.append(buf)
-        t = qmm.QTensor(ctx, Q4_0, k, max(r1 - r0, 1), ptr=buf.data_ptr())
-        if r1 > r0:
-            t.set(host_w[(m, k)][r0:r1])
-        weights.append((t, r1 - r0, c, m, k))
+        t = qmm.QTensor(ctx, Q4_0, k, max(split.rows, 1), ptr=buf.data_ptr())
+        if split.rows > 0:
+            t.set(host_w[(m, k)][split.r0:split.r1])
+        weights.append((t, split, k))
     # activations: ping-pong full vectors sized for the largest padded m
     max_len = max(((m + world - 1) // world) * world for _, m, _ in mats)
     act = [torch.zeros(max_len, dtype=torch.float32, device=dev) for _ in range(2)]
@@ -173,16 +181,14 @@ def run_b200(args):
     def token_step():
         """one token: 169 mul_mats (each ONE fused quantize+GEMV launch) [+ all-gather of the dst slices]"""
         src = x_in
-        for i, (t, ms, c, m, k) in enumerate(weights):
+        for i, (t, split, k) in enumerate(weights):
             dst = act[i & 1]
-            if ms > 0:
-                ctx.mul_mat_device(t, src.data_ptr(), 1, dst.data_ptr() + rank * c * 4, m=ms)
-            if world > 1:
-                dist.all_gather_into_tensor(dst[: c * world], dst[rank * c:(rank + 1) * c])
+            rs.gathered_mul_mat(dist, split, 1, lambda out, ld, t=t, src=src, split=split:
+                                ctx.mul_mat_device(t, src.data_ptr(), 1, out.data_ptr(), m=split.rows), dst)
             src = dst
         return src
 
-    launches_per_step = sum(1 for w in weights if w[1] > 0)
+    launches_per_step = sum(1 for w in weights if w[1].rows > 0)
     # ---- capture the step once (our kernels + NCCL) into a CUDA graph: decode is launch-bound otherwise
     use_graph = not args.no_graph
     graph = None
@@ -249,7 +255,7 @@ def run_b200(args):
     logits_ok = bool(np.isfinite(logits_host.numpy()).all() and np.abs(logits_host.numpy()).max() > 0)
 
     bytes_step = sum(algorithmic_bytes(m, k, 1, 18) for _, m, k in mats)
-    bytes_rank = sum(algorithmic_bytes(ms, k, 1, 18) for (_, ms, _, _, k) in weights if ms > 0)
+    bytes_rank = sum(algorithmic_bytes(sp.rows, k, 1, 18) for (_, sp, k) in weights if sp.rows > 0)
     launch_us = ms_per_step * 1e3 / launches_per_step
     achieved = bytes_rank / launches_per_step / (launch_us * 1e-6) / 1e9
     roofline = {"bound": "hbm", "kernel": "gemv_kernel<Q4_0,1> (fused quantize_row_q8_0 + dp4a GEMV)", "achieved": round(achieved, 1),
@@ -286,11 +292,17 @@ def run_b200(args):
             line["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_tok_s(budget_s=20.0, steps=None)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if world > 1:
+        # tearing the process group down while a captured graph still holds NCCL kernels hangs in this torch/NCCL
+        # combination: drop the graph, rendezvous, and leave without the destructor dance
+        graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def run_extras(torch, qmm, ctx, stream, P, args):
