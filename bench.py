@@ -188,17 +188,83 @@ def run_b200(args):
             src = dst
         return src
 
+    # ---- fused path (N > 1): GEMV epilogue stores into every rank's activation vector over NVLink, flags instead of a collective
+    fused = None
+    out_ptr_fused = None
+    if world > 1 and args.gather == "fused":
+        try:
+            n_slots = len(weights) + 1
+            abuf = [ctx.alloc(max_len * 8), ctx.alloc(max_len * 8)]          # LL activation vectors: {fp32, tag} per element
+            state = ctx.alloc(n_slots * 2 * 4)
+            dense = ctx.alloc(N_VOCAB * 4)
+            for b in abuf + [state, dense]:
+                ctx._check(ctx.lib.b200_memset(ctx.h, b.ptr, 0, b.nbytes))
+            mine = [ctx.ipc_export(b.ptr) for b in abuf]
+            allh = [None] * world
+            dist.all_gather_object(allh, mine)
+            peers = [[abuf[0].ptr, abuf[1].ptr] if r == rank else [ctx.ipc_import(h) for h in allh[r]] for r in range(world)]
+            dist.barrier()
+            gathers = []
+            for i, (t, split, k) in enumerate(weights):
+                g = qmm.Gather()
+                g.world, g.rank, g.slot, g.wait_slot, g.row0 = world, rank, i, i - 1, split.r0
+                for r in range(world):
+                    g.peer_dst[r] = peers[r][i & 1]
+                g.state = state.ptr
+                gathers.append(g)
+            gw = qmm.Gather()
+            gw.world, gw.rank, gw.slot, gw.wait_slot, gw.row0 = world, rank, n_slots - 1, len(weights) - 1, 0
+            for r in range(world):
+                gw.peer_dst[r] = peers[r][0]
+            gw.state = state.ptr
+
+            def token_step_fused():
+                src = x_in.data_ptr()
+                for i, (t, split, k) in enumerate(weights):
+                    ctx.mul_mat_gather(t, src, gathers[i], m=split.rows)
+                    src = abuf[i & 1].ptr
+                ctx.gather_finish(gw, src, dense.ptr, N_VOCAB)      # logits complete on this rank, as plain fp32
+                return dense.ptr
+            fused = token_step_fused
+            out_ptr_fused = dense.ptr
+        except Exception as e:
+            print(f"[bench] fused all-gather unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+            fused = None
+
     launches_per_step = sum(1 for w in weights if w[1].rows > 0)
     # ---- capture the step once (our kernels + NCCL) into a CUDA graph: decode is launch-bound otherwise
     use_graph = not args.no_graph
     graph = None
     out_t = token_step()       # eager once: sets func attributes, warms NCCL
     torch.cuda.synchronize()
+    gather_check = None
+    step_fn = token_step
+    if fused is not None:
+        # same arithmetic, same row partition -> the fused path must reproduce the NCCL path bit for bit
+        ref_logits = out_t[:N_VOCAB].clone()
+        fused()
+        torch.cuda.synchronize()
+        got = np.empty(N_VOCAB, np.float32)
+        ctx._check(ctx.lib.b200_download(ctx.h, got.ctypes.data, out_ptr_fused, N_VOCAB * 4))
+        ok = bool(np.array_equal(got, ref_logits.cpu().numpy()))
+        okt = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        gather_check = bool(okt.item())
+        if gather_check:
+            step_fn = fused
+        else:
+            print("[bench] fused all-gather result differs from the NCCL path; using NCCL", file=sys.stderr)
+            fused = None
+    trace_buf = None
+    if args.trace:
+        trace_buf = ctx.alloc(launches_per_step * 160 * 8 * 8)
+        ctx._check(ctx.lib.b200_memset(ctx.h, trace_buf.ptr, 0, trace_buf.nbytes))
+        ctx.set_trace(trace_buf, launches_per_step)
     if use_graph:
         try:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=stream):
-                out_t = token_step()
+                out_t = step_fn()
         except Exception as e:  # capture not possible (e.g. PDL edge unsupported): say so, stay eager
             print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eager", file=sys.stderr)
             graph = None
@@ -208,7 +274,7 @@ def run_b200(args):
         if graph is not None:
             graph.replay()
         else:
-            token_step()
+            step_fn()
 
     def barrier():
         if world > 1:
@@ -245,13 +311,26 @@ def run_b200(args):
     def e2e_step():
         ctx._check(ctx.lib.b200_upload_async(ctx.h, x_in.data_ptr(), x_host.data_ptr(), N_EMBD * 4))
         step()
-        ctx._check(ctx.lib.b200_download_async(ctx.h, logits_host.data_ptr(), out_t.data_ptr(), N_VOCAB * 4))
+        ctx._check(ctx.lib.b200_download_async(ctx.h, logits_host.data_ptr(), out_ptr_fused if fused is not None else out_t.data_ptr(), N_VOCAB * 4))
         ctx.synchronize()
 
     for _ in range(3):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps) / args.steps
     clocks = sampler.stop() if rank == 0 else None
+    if trace_buf is not None:
+        tr = trace_buf.download(np.uint64, launches_per_step * 160 * 8).reshape(launches_per_step, 160, 8).astype(np.int64)
+        t0 = tr[0, :148, 0].min()
+        names = ["entry", "primed", "pred done", "quantized", "first w", "last row", "flags seen", "flags out"]
+        print(f"[trace r{rank}] launch " + " ".join(f"{n:>19s}" for n in names), file=sys.stderr)
+        for i in range(min(14, launches_per_step)):
+            ctas = min(148, weights[i][1].rows)
+            row = []
+            for sidx in range(8):
+                v = tr[i, :ctas, sidx]
+                v = v[v > 0] - t0
+                row.append(f"{v.min():8d}..{v.max():8d}" if v.size else " " * 18)
+            print(f"[trace r{rank}] {i:3d}    " + "  ".join(row), file=sys.stderr)
     logits_ok = bool(np.isfinite(logits_host.numpy()).all() and np.abs(logits_host.numpy()).max() > 0)
 
     bytes_step = sum(algorithmic_bytes(m, k, 1, 18) for _, m, k in mats)
@@ -261,7 +340,7 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": "gemv_kernel<Q4_0,1> (fused quantize_row_q8_0 + dp4a GEMV)", "achieved": round(achieved, 1),
                 "peak": P["hbm_gbs"], "unit": "GB/s", "frac": round(achieved / P["hbm_gbs"], 4), "traffic": None,
                 "peak_source": P["source"], "launch_us": round(launch_us, 3),
-                "note": "per rank; at N>1 the step time includes the NCCL all-gathers"}
+                "note": "per rank; at N>1 the step time includes the exchange of the dst slices"}
 
     extra = {}
     if world == 1 and not args.no_extras:
@@ -281,7 +360,8 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8 dots (dp4a) + fp32 accumulate; Q4_0 weights, Q8_0 activations",
             "data": "synthetic (random-init Q4_0 blocks, U(-1,1) activations, seed 1234)",
             "config": {"workload": WORKLOAD, "l2": "inputs larger than L2 (3.29 GB of weights per step)", "cuda_graph": graph is not None,
-                       "parallelism": f"row-split x{world} + NCCL all-gather" if world > 1 else "single GPU",
+                       "parallelism": (f"row-split x{world} + " + ("all-gather fused into the GEMV epilogue (NVLink peer stores + flags)" if fused is not None else "NCCL all-gather")) if world > 1 else "single GPU",
+                       "gather_check_vs_nccl": gather_check,
                        "weights_bytes_per_token": sum(m * (k // 32) * 18 for _, m, k in mats)},
             "e2e": {"value": round(1000.0 / ms_e2e, 2), "unit": "tokens/s", "h2d_bytes_per_step": N_EMBD * 4, "d2h_bytes_per_step": N_VOCAB * 4,
                     "ms_per_step": round(ms_e2e, 4), "logits_finite": logits_ok},
@@ -293,7 +373,7 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_tok_s(budget_s=20.0, steps=None)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # tearing the process group down while a captured graph still holds NCCL kernels hangs in this torch/NCCL
         # combination: drop the graph, rendezvous, and leave without the destructor dance
@@ -518,10 +598,25 @@ def run_reference(args):
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    # libraries (NCCL's version banner, for one) print to stdout; the contract is ONE JSON line there.  Park the real
+    # stdout, point fd 1 at stderr for the duration, and write the line to the parked descriptor at the end.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -530,6 +625,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a captured CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the C1/C2 sub-benchmarks (A/B runs)")
+    ap.add_argument("--trace", action="store_true", help="dump a device-side timeline of the first launches of a step to stderr")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N > 1: how dst slices are re-assembled")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -75,7 +75,7 @@ struct StreamGeom {
     int stage_sc;     // bytes of scales per full stage
     int stage_bytes;  // aligned total
     int act_col;      // bytes of activation scratch per column
-    int ring_off, act_off, part_off, bar_off, total;
+    int ring_off, act_off, part_off, bar_off, llstage_off, total;
 };
 
 __host__ __device__ inline size_t stream_act_col_bytes(int type, int k) {
@@ -158,8 +158,91 @@ __device__ __forceinline__ int block_dot(const uint4 &w0, const uint4 &w1, const
     }
 }
 
+// ---- fused all-gather ("LL" elements: {fp32 value, u32 tag} in one 8-byte word) --------------------------------
+// 16 consecutive LL elements (128 bytes) -> 16 floats, re-reading until every tag is the expected one.  Volatile loads go
+// to L2, which is where peer stores land; 8-byte stores are delivered atomically, so a matching tag implies the value.
+__device__ __forceinline__ void ll_load16(const void *src, uint32_t tag, float4 (&out)[4]) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(src);
+    unsigned backoff = 64;
+    for (;;) {
+        uint4 w[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[j].x), "=r"(w[j].y), "=r"(w[j].z), "=r"(w[j].w) : "l"(p + j));
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < 8; j++) ok = ok && w[j].y == tag && w[j].w == tag;
+        if (ok) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                out[j] = make_float4(__uint_as_float(w[2 * j].x), __uint_as_float(w[2 * j].z), __uint_as_float(w[2 * j + 1].x), __uint_as_float(w[2 * j + 1].z));
+            return;
+        }
+        __nanosleep(backoff);
+        if (backoff < 512) backoff += 64;
+    }
+}
+// Warp-cooperative form: the warp's 32 lane-tasks are one contiguous 4 KB run of LL elements.  It is read with fully
+// coalesced 128-bit volatile loads (lane stride 16 B; volatile loads bypass L1, so the per-lane form above costs 32 sector
+// requests per instruction), the tags are verified warp-wide, the values are parked in a 2 KB per-warp staging area and
+// each lane picks up its 16 consecutive floats.  nvalid = number of live lane-tasks of this warp (0..32).
+__device__ __forceinline__ void ll_load16_warp(const char *wbase, int nvalid, uint32_t tag, float *wstage, int lane, float4 (&out)[4]) {
+    uint4 w[8];
+    const int nv8 = nvalid * 8;
+    for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            // lanes past the end re-read the run's first chunk (always valid) so that no load is conditional
+            const int idx = j * 32 + lane < nv8 ? j * 32 + lane : 0;
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[j].x), "=r"(w[j].y), "=r"(w[j].z), "=r"(w[j].w) : "l"(wbase + (size_t)idx * 16));
+            ok = ok && w[j].y == tag && w[j].w == tag;
+        }
+        if (__all_sync(0xffffffffu, ok)) break;
+        __nanosleep(64);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (j * 32 + lane < nv8) *reinterpret_cast<float2 *>(wstage + 2 * (j * 32 + lane)) = make_float2(__uint_as_float(w[j].x), __uint_as_float(w[j].z));
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; j++) out[j] = *reinterpret_cast<const float4 *>(wstage + lane * 16 + j * 4);
+    __syncwarp();
+}
+// cheap readiness probe: spin on ONE element (a warp-uniform address -> one 32-byte sector per warp per poll) until it
+// carries the tag; the full loads that follow still verify every element, so this only has to be a good predictor
+__device__ __forceinline__ void ll_probe(const void *elem, uint32_t tag) {
+    uint32_t v, t;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v), "=r"(t) : "l"(elem));
+        if (t == tag) return;
+        __nanosleep(32);
+    }
+}
+__device__ __forceinline__ void ll_store(void *vec, int64_t idx, float v, uint32_t tag) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2 *>(vec) + idx), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+
+// one CTA: wait for an LL vector to be complete and write it out as plain fp32
+__global__ void __launch_bounds__(1024) gather_finish_kernel(const b200_gather gd, const uint2 *ll, float *out, int64_t count) {
+    __shared__ uint32_t s_epoch;
+    uint32_t *st = gd.state + 2 * (size_t)gd.slot;
+    if (threadIdx.x == 0) s_epoch = st[1];
+    __syncthreads();
+    const uint32_t tag = ((s_epoch + 1u) << 10) | (uint32_t)gd.wait_slot;   // what the producing slot stamped this time round
+    for (int64_t i = threadIdx.x; i < count; i += blockDim.x) {
+        uint32_t v, t;
+        do {
+            asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v), "=r"(t) : "l"(ll + i));
+        } while (t != tag);
+        out[i] = __uint_as_float(v);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) st[1] = s_epoch + 1u;
+}
+
 template <int TYPE, int NCOLS, bool DOTS>
-__global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gemv_params p, const StreamGeom g) {
+__global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gemv_params p, const StreamGeom g, const b200_gather gd) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int QSB = TYPE == B200_TYPE_Q4_0 ? 16 : 32;
     const int k = (int)p.k, nb = k >> 5;
@@ -211,21 +294,27 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
             if (++ist == g.stages) { ist = 0; iph ^= 1u; }
         }
     };
-    if (threadIdx.x == 0) {
-        produce(min(nstage_iters, g.stages));
-        stamp(p.trace, 1);
-    }
+    if (threadIdx.x == 0) produce(min(nstage_iters, g.stages));
     __syncwarp();   // reconverge BEFORE griddepcontrol.wait: a warp parked in the wait takes its diverged lane 0 with it
 
     // ===== consumers =====
-    pdl_wait();  // activations (and dst, for write-after-read) belong to the previous grid until here
+    // activations (and dst, for write-after-read) belong to the previous grid until here -- except in the fused
+    // all-gather chain, where src1 arrives as tagged LL elements: the tags ARE the dependency (a matching tag proves the
+    // producing CTA, local or remote, is past its own input reads), so the kernel does not wait for grid completion at all
+    if (!(gd.world > 1 && gd.wait_slot >= 0)) pdl_wait();
     if (threadIdx.x == 0) stamp(p.trace, 2);
-    if (p.trace && threadIdx.x == 32) {   // tracing only: when did the first / last primed stage actually land?
-        mbar_wait(&full_bar[0], 0);
-        stamp(p.trace, 6);
-        mbar_wait(&full_bar[min(nstage_iters, g.stages) - 1], 0);
-        stamp(p.trace, 7);
+    // fused all-gather: tags are (execution count + 1) << 10 | producing slot -- unique per (launch, replay), so a stale
+    // element of the ping-pong buffer (written by slot - 2 in the same replay) can never be mistaken for the new one.
+    // Every slot runs once per sequence, so this launch's own execution count is also its producer's.
+    uint32_t gd_tag = 0, gd_src_tag = 0;
+    if (gd.world > 1) {
+        uint32_t *s_tag = reinterpret_cast<uint32_t *>(empty_bar + kMaxStages);
+        if (threadIdx.x == 0) *s_tag = gd.state[2 * (size_t)gd.slot + 1] + 1u;
+        consumer_bar_sync();
+        gd_tag = (*s_tag << 10) | (uint32_t)gd.slot;
+        gd_src_tag = (*s_tag << 10) | (uint32_t)(gd.wait_slot & 1023);
     }
+    const bool ll_in = gd.world > 1 && gd.wait_slot >= 0;
 
     // ---- quantize the activation columns into shared memory: quantize_row_q8_0, bit-exact ----
     // Two lanes per block, 16 consecutive floats (4 x 128-bit loads) per lane: one amax shuffle, ONE 127/amax
@@ -241,13 +330,30 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
 #pragma unroll 1
             for (int base = 0; base < tpc; base += kConsumerThreads * kQB) {
                 float4 v[kQB][4];
+                if (ll_in) {
+                    // every CTA needs the whole vector, so what matters is its LAST element to land: probe the end of
+                    // this warp's span first (cheap, warp-uniform), then do the verified loads
+                    const int tlast = min(base + (kQB - 1) * kConsumerThreads + warp * 32 + 31, tpc - 1);
+                    ll_probe(reinterpret_cast<const char *>(p.x) + (size_t)tlast * 128 + 120, gd_src_tag);
+                    if (threadIdx.x == 0 && base == 0) stamp(p.trace, 1);
+                }
 #pragma unroll
                 for (int u = 0; u < kQB; u++) {
                     const int t = min(base + u * kConsumerThreads + (int)threadIdx.x, tpc - 1);
-                    const float4 *src = reinterpret_cast<const float4 *>(xcol + (size_t)t * 16);
+                    if (ll_in) {
+                        // src1 is the LL vector the previous launch scattered to every rank: 8 bytes per element
+                        const int tb = base + u * kConsumerThreads + warp * 32;   // first lane-task of this warp
+                        const int nvalid = max(0, min(32, tpc - tb));
+                        if (nvalid > 0)
+                            ll_load16_warp(reinterpret_cast<const char *>(p.x) + (size_t)tb * 128, nvalid, gd_src_tag,
+                                           reinterpret_cast<float *>(smem + g.llstage_off) + warp * 512, lane, v[u]);
+                    } else {
+                        const float4 *src = reinterpret_cast<const float4 *>(xcol + (size_t)t * 16);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) v[u][j] = src[j];
+                        for (int j = 0; j < 4; j++) v[u][j] = src[j];
+                    }
                 }
+                if (ll_in && threadIdx.x == 0 && base == 0) stamp(p.trace, 6);
 #pragma unroll
                 for (int u = 0; u < kQB; u++) {
                     const int tt = base + u * kConsumerThreads + (int)threadIdx.x;
@@ -434,7 +540,14 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
                         if (lane == u * NCOLS + c) { v = acc[u][c]; gr = grow[u]; pr = prow[u]; lv = rlive[u]; }
                 const int c = lane % NCOLS;
                 if (lv) {
-                    if (G == 1) p.dst[(int64_t)c * p.m + r_begin + gr] = v;
+                    if (G == 1) {
+                        if (gd.world > 1) {
+                            // fused all-gather, producer side: the element goes to every rank's full vector (NVLink stores)
+                            for (int r = 0; r < gd.world; r++) ll_store(gd.peer_dst[r], gd.row0 + r_begin + gr, v, gd_tag);
+                        } else {
+                            p.dst[(int64_t)c * p.m + r_begin + gr] = v;
+                        }
+                    }
                     else part[((cpar * g.pr + pr) * kConsumerWarps + seg) * NCOLS + c] = v;   // k-split: park the partial
                 }
             }
@@ -449,7 +562,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
                     const int r = t / NCOLS, c = t - r * NCOLS;
                     float v = 0.0f;
                     for (int sg = 0; sg < G; sg++) v += part[((cpar * g.pr + r) * kConsumerWarps + sg) * NCOLS + c];
-                    p.dst[(int64_t)c * p.m + r_begin + chunk_row0 + r] = v;
+                    if (gd.world > 1) {
+                        for (int pr = 0; pr < gd.world; pr++) ll_store(gd.peer_dst[pr], gd.row0 + r_begin + chunk_row0 + r, v, gd_tag);
+                    } else {
+                        p.dst[(int64_t)c * p.m + r_begin + chunk_row0 + r] = v;
+                    }
                 }
                 chunk_row0 += rows_in_chunk;
                 rows_in_chunk = 0;
@@ -458,6 +575,18 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
         }
     }
     if (threadIdx.x == 0) stamp(p.trace, 5);
+    if (gd.world > 1) {
+        // bookkeeping only (device-scope): the last CTA of the grid bumps the slot's execution count
+        consumer_bar_sync();
+        if (threadIdx.x == 0) {
+            uint32_t *st = gd.state + 2 * (size_t)gd.slot;
+            const uint32_t arrived = atomicAdd(st, 1u);
+            if (arrived == gridDim.x - 1) {
+                st[0] = 0;
+                st[1] = gd_tag >> 10;
+            }
+        }
+    }
 }
 
 bool stream_geometry(const b200_gemv_params &p, StreamGeom *g) {
@@ -484,9 +613,10 @@ bool stream_geometry(const b200_gemv_params &p, StreamGeom *g) {
     if (pr < 4 * rs) pr = 4 * rs;   // at least one group of kU (<= 4) stages
     g->pr = pr;
     const int part_bytes = G > 1 ? (int)b200_align_up((size_t)2 * pr * kConsumerWarps * p.n * 4, 128) : 128;
-    const int bar_bytes = 2 * kMaxStages * 8;
+    const int bar_bytes = 2 * kMaxStages * 8 + 16;   // + the broadcast slot of the gather tag
     // two of these kernels must be co-resident per SM (current + programmatic dependent): <= ~110 KB each
-    const int budget = 110 * 1024 - act_bytes - part_bytes - bar_bytes - 8192 - 256;
+    const int ll_bytes = p.gather ? kConsumerWarps * 2048 : 0;   // per-warp staging of the fused all-gather's LL loads
+    const int budget = 110 * 1024 - act_bytes - part_bytes - bar_bytes - ll_bytes - 8192 - 256;
     int stages = budget / g->stage_bytes;
     if (stages < 2) return false;
     if (stages > kMaxStages) stages = kMaxStages;
@@ -495,7 +625,8 @@ bool stream_geometry(const b200_gemv_params &p, StreamGeom *g) {
     g->act_off = stages * g->stage_bytes;
     g->part_off = g->act_off + act_bytes;
     g->bar_off = g->part_off + part_bytes;
-    g->total = g->bar_off + bar_bytes + 8192;   // slack for the unclamped reads of dead lanes
+    g->llstage_off = g->bar_off + bar_bytes;
+    g->total = g->llstage_off + ll_bytes + 8192;   // slack for the unclamped reads of dead lanes
     return true;
 }
 
@@ -520,7 +651,11 @@ int launch_stream_typed(b200_ctx *ctx, const b200_gemv_params &p, const StreamGe
     pp.trace = NULL;
     if (ctx->trace && ctx->trace_next < ctx->trace_capacity)
         pp.trace = ctx->trace + (size_t)(ctx->trace_next++) * B200_TRACE_MAX_CTAS * B200_TRACE_STAMPS;
-    B200_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kern, pp, g));
+    b200_gather gd;
+    memset(&gd, 0, sizeof(gd));
+    if (p.gather) gd = *p.gather;
+    pp.gather = NULL;
+    B200_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kern, pp, g, gd));
     ctx->launches++;
     return B200_OK;
 }
@@ -542,12 +677,20 @@ int launch_stream_cols(b200_ctx *ctx, const b200_gemv_params &p, const StreamGeo
 
 }  // namespace
 
+int b200_launch_gather_finish(b200_ctx *ctx, const b200_gather &gd, const void *ll_src, float *out, int64_t count) {
+    gather_finish_kernel<<<1, 1024, 0, ctx->stream>>>(gd, (const uint2 *)ll_src, out, count);
+    ctx->launches++;
+    B200_CUDA_TRY(ctx, cudaGetLastError());
+    return B200_OK;
+}
+
 // returns true when the streaming kernel takes this shape; *rc then holds the launch status
 bool b200_try_launch_gemv_stream(b200_ctx *ctx, const b200_gemv_params &p, int *rc) {
     if (p.ne12 != 1 || p.ne13 != 1 || p.ne02 != 1 || p.ne03 != 1) return false;
     if (p.k % 256 != 0 || p.k > 32768 || p.n < 1 || p.n > 8) return false;
     if (((uintptr_t)p.qs & 15) != 0 || ((uintptr_t)p.d & 15) != 0) return false;
     if (p.dots == NULL && p.dst_n != p.n) return false;  // column-chunked dst keeps the generic addressing
+    if (p.gather && (p.n != 1 || p.dots)) return false;
     StreamGeom g;
     if (!stream_geometry(p, &g)) return false;
     const bool dots = p.dots != NULL;

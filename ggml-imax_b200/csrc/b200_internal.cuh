@@ -86,9 +86,11 @@ struct b200_gemv_params {
     int64_t        dst_n;      // columns of the whole dst (>= n when the caller chunks columns)
     int32_t       *dots;       // non-null: dump per-block int32 partials [n][m][k/32] instead of dst
     unsigned long long *trace; // non-null: this launch's [gridDim.x][8] timestamp slots
+    const b200_gather *gather; // host pointer (launcher copies it into a kernel parameter); null: plain local dst
 };
 int b200_launch_gemv(b200_ctx *ctx, const b200_gemv_params &p);
 bool b200_try_launch_gemv_stream(b200_ctx *ctx, const b200_gemv_params &p, int *rc);
+int b200_launch_gather_finish(b200_ctx *ctx, const b200_gather &gd, const void *ll_src, float *out, int64_t count);
 
 struct b200_gemm_params {
     int            type;

@@ -104,6 +104,52 @@ int b200_mul_mat(b200_ctx *ctx, const b200_mul_mat_args *a) {
     return run_gemv_chunks(ctx, a, qs, d);
 }
 
+static bool gather_ok(const b200_gather *g) {
+    if (!g || g->world < 1 || g->world > B200_MAX_RANKS || g->rank < 0 || g->rank >= g->world || g->slot < 0 || g->slot >= 1024 ||
+        g->wait_slot >= 1024 || !g->state)
+        return false;
+    for (int r = 0; r < g->world; r++)
+        if (!g->peer_dst[r]) return false;
+    return true;
+}
+
+int b200_mul_mat_gather(b200_ctx *ctx, const b200_mul_mat_args *a, const b200_gather *g) {
+    B200_REQUIRE(ctx, ctx && a && gather_ok(g), B200_ERR_INVALID);
+    B200_REQUIRE(ctx, quant_type_ok(a->type), B200_ERR_UNSUPPORTED);
+    // decode only: one column, 2-D weights; shapes the streaming kernel takes (k % 256 == 0, k <= 32768)
+    B200_REQUIRE(ctx, a->ne11 == 1 && a->ne12 == 1 && a->ne13 == 1 && a->ne02 == 1 && a->ne03 == 1, B200_ERR_UNSUPPORTED);
+    B200_REQUIRE(ctx, a->ne00 > 0 && a->ne00 % 256 == 0 && a->ne00 <= 32768 && a->ne01 > 0, B200_ERR_UNSUPPORTED);
+    const int64_t nb = a->ne00 / B200_QK;
+    B200_REQUIRE(ctx, a->src0_block_off >= 0 && a->src0_block_off + nb * a->ne01 <= a->src0_nblocks_total, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, ((uintptr_t)a->src1_dev & 15) == 0, B200_ERR_UNSUPPORTED);
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int qsb = b200_qs_bytes(a->type);
+    b200_gemv_params p;
+    memset(&p, 0, sizeof(p));
+    p.type = a->type;
+    p.qs = (const uint8_t *)a->src0_dev + a->src0_block_off * qsb;
+    p.d = (const __half *)((const uint8_t *)a->src0_dev + a->src0_nblocks_total * qsb) + a->src0_block_off;
+    p.k = a->ne00; p.m = a->ne01; p.ne02 = 1; p.ne03 = 1;
+    p.x = a->src1_dev;
+    p.n = 1; p.ne12 = 1; p.ne13 = 1;
+    p.nb11 = (size_t)a->ne00 * 4; p.nb12 = p.nb11; p.nb13 = p.nb11;
+    p.dst = NULL;   // results go out as LL elements through gather->peer_dst
+    p.dst_n = 1;
+    p.gather = g;
+    int rc = B200_OK;
+    if (!b200_try_launch_gemv_stream(ctx, p, &rc)) {
+        b200_set_error(ctx, "b200_mul_mat_gather: shape not served by the streaming GEMV");
+        return B200_ERR_UNSUPPORTED;
+    }
+    return rc;
+}
+
+int b200_gather_finish(b200_ctx *ctx, const b200_gather *g, const void *ll_src_dev, float *dense_out_dev, int64_t count) {
+    B200_REQUIRE(ctx, ctx && gather_ok(g) && g->wait_slot >= 0 && ll_src_dev && dense_out_dev && count > 0, B200_ERR_INVALID);
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return b200_launch_gather_finish(ctx, *g, ll_src_dev, dense_out_dev, count);
+}
+
 int b200_block_dots(b200_ctx *ctx, int type, const void *src0_dev, int64_t k, int64_t m, const float *src1_dev, int64_t n,
                     int32_t *out_dev, int path) {
     B200_REQUIRE(ctx, ctx && quant_type_ok(type), B200_ERR_INVALID);

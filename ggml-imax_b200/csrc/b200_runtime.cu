@@ -271,6 +271,33 @@ int b200_reserve_workspace(b200_ctx *ctx, int type, int64_t k, int64_t m, int64_
     return b200_ws_reserve(ctx, b200_prefill_ws_bytes(type, k, m, n));
 }
 
+int b200_ipc_export(b200_ctx *ctx, void *dptr, void *handle64_out) {
+    B200_REQUIRE(ctx, ctx && dptr && handle64_out, B200_ERR_INVALID);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    B200_CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle64_out, &h, sizeof(h));
+    return B200_OK;
+}
+
+int b200_ipc_import(b200_ctx *ctx, const void *handle64, void **peer_ptr_out) {
+    B200_REQUIRE(ctx, ctx && handle64 && peer_ptr_out, B200_ERR_INVALID);
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    B200_CUDA_TRY(ctx, cudaIpcOpenMemHandle(peer_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200_OK;
+}
+
+int b200_ipc_close(b200_ctx *ctx, void *peer_ptr) {
+    B200_REQUIRE(ctx, ctx != NULL, B200_ERR_INVALID);
+    if (!peer_ptr) return B200_OK;
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, cudaIpcCloseMemHandle(peer_ptr));
+    return B200_OK;
+}
+
 int b200_host_malloc(void **hptr, size_t size) {
     if (!hptr) return B200_ERR_INVALID;
     cudaError_t e = cudaMallocHost(hptr, size ? size : 1);

@@ -47,6 +47,16 @@ class MulMatArgs(C.Structure):
     ]
 
 
+MAX_RANKS = 8
+
+
+class Gather(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32), ("rank", C.c_int32), ("slot", C.c_int32), ("wait_slot", C.c_int32), ("row0", C.c_int64),
+        ("peer_dst", C.c_void_p * MAX_RANKS), ("state", C.c_void_p),
+    ]
+
+
 # every symbol include/ggml_b200.h declares (tests check the list against the header and the .so)
 _SIGNATURES = {
     "b200_device_count": (C.c_int, []),
@@ -84,6 +94,11 @@ _SIGNATURES = {
     "b200_quantize_q8_0": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_size_t, C.c_void_p, C.c_void_p]),
     "b200_quantize_q8_0_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_size_t, C.c_void_p]),
     "b200_mul_mat": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs)]),
+    "b200_mul_mat_gather": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs), C.POINTER(Gather)]),
+    "b200_gather_finish": (C.c_int, [C.c_void_p, C.POINTER(Gather), C.c_void_p, C.c_void_p, C.c_int64]),
+    "b200_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_block_dots": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "b200_mul_mat_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
 }
@@ -307,6 +322,33 @@ class Context:
         a.nb13 = a.nb12 * ne12 if nb13 is None else nb13
         a.dst_dev = dst_ptr
         self._check(self.lib.b200_mul_mat(self.h, C.byref(a)))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        h = (C.c_ubyte * 64)()
+        self._check(self.lib.b200_ipc_export(self.h, C.c_void_p(ptr), h))
+        return bytes(h)
+
+    def ipc_import(self, handle: bytes) -> int:
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        self._check(self.lib.b200_ipc_import(self.h, h, C.byref(p)))
+        return p.value
+
+    def mul_mat_gather(self, w: QTensor, x_ptr: int, gather: "Gather", m: int | None = None):
+        """decode mul_mat of this rank's row slice with the all-gather fused into the epilogue (b200_mul_mat_gather)"""
+        a = MulMatArgs()
+        a.type = w.type
+        a.src0_dev = w.ptr
+        a.src0_nblocks_total = w.nblocks
+        a.ne00, a.ne01, a.ne02, a.ne03 = w.k, (w.m if m is None else m), 1, 1
+        a.src1_dev = x_ptr
+        a.ne11, a.ne12, a.ne13 = 1, 1, 1
+        a.nb11 = a.nb12 = a.nb13 = w.k * 4
+        a.dst_dev = gather.peer_dst[gather.rank]   # unused: results leave as LL elements
+        self._check(self.lib.b200_mul_mat_gather(self.h, C.byref(a), C.byref(gather)))
+
+    def gather_finish(self, gather: "Gather", ll_src_ptr: int, dense_out_ptr: int, count: int):
+        self._check(self.lib.b200_gather_finish(self.h, C.byref(gather), C.c_void_p(ll_src_ptr), C.c_void_p(dense_out_ptr), count))
 
     def mul_mat(self, w: QTensor, x: np.ndarray, flags: int = 0) -> np.ndarray:
         """x: [ne13, ne12, n, k] (or [n, k]) float32 host.  Returns dst [ne13, ne12, n, m] float32 (ggml dst[m,n,ne12,ne13])."""

@@ -160,6 +160,39 @@ typedef struct b200_mul_mat_args {
 
 B200_API int b200_mul_mat(b200_ctx *ctx, const b200_mul_mat_args *args);
 
+/* ---- row-split decode across GPUs: GEMV fused with its all-gather -----------------------------------
+ * Replaces the reference's multi-device mul_mat (split buffer + peer memcpys to a main GPU,
+ * src/ggml-cuda.cu:578-975, :1360-1647) for the decode case (n == 1), one process per GPU.
+ * Each rank holds a row slice of src0.  Instead of "kernel, then collective", the GEMV epilogue stores every
+ * finished dst element straight into the activation vector of EVERY rank over NVLink (peer-mapped pointers from
+ * b200_ipc_export / b200_ipc_import on b200_malloc'ed buffers).  No flags, no fences: an element travels as one
+ * 8-byte store {fp32 value, u32 tag} ("LL" layout, the tag is the execution count of the launch), which the fabric
+ * delivers atomically; the consuming kernel's activation loads simply re-read until the tag is the one it expects.
+ * Tags are monotonic and every launch slot keeps its execution count on the device, so a captured CUDA graph replays
+ * without resetting anything.
+ *   peer_dst[r] : rank r's LL activation vector for this launch's dst: uint64[>= row0 + ne01], zero-initialised,
+ *                 same layout on every rank; [rank] is the local one
+ *   state       : local uint32 [n_slots][2], zero-initialised ({arrived CTAs, executions})
+ *   slot        : index of this launch in the repeated sequence (unique per launch, including b200_gather_finish)
+ *   wait_slot   : >= 0: src1 of this launch is the LL vector produced by that slot (args->src1_dev points to it);
+ *                 -1: src1 is a plain local fp32 vector */
+#define B200_MAX_RANKS 8
+typedef struct b200_gather {
+    int32_t   world, rank;
+    int32_t   slot, wait_slot;
+    int64_t   row0;
+    void     *peer_dst[B200_MAX_RANKS];
+    uint32_t *state;
+} b200_gather;
+B200_API int b200_mul_mat_gather(b200_ctx *ctx, const b200_mul_mat_args *args, const b200_gather *gather);
+/* end of a sequence: wait for the LL vector ll_src_dev (count elements, produced by gather->wait_slot) to be complete
+ * and write it out as plain fp32 (dense_out_dev), e.g. the logits before they are read back */
+B200_API int b200_gather_finish(b200_ctx *ctx, const b200_gather *gather, const void *ll_src_dev, float *dense_out_dev, int64_t count);
+/* CUDA IPC plumbing for the peer pointers (handle = 64 bytes, exchange it with any host-side transport) */
+B200_API int b200_ipc_export(b200_ctx *ctx, void *dptr, void *handle64_out);
+B200_API int b200_ipc_import(b200_ctx *ctx, const void *handle64, void **peer_ptr_out);
+B200_API int b200_ipc_close(b200_ctx *ctx, void *peer_ptr);
+
 /* parity instrumentation: per-block int32 partial sums exactly as the kernels form them.
  * out_dev [n][m][k/32] int32.  path 0 = GEMV inner loop (dp4a), path 1 = GEMM (tcgen05 accumulators).
  * Compared bit-for-bit with the integer loop of src/ggml-quants.c:3858-3869 / :5010-5015. */
