@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; s++) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kConsumerWarps);
+            reinterpret_cast<int *>(empty_bar)[s] = 0;   // per-stage "warps that have left" counter
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -272,29 +272,24 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
     pdl_launch_dependents();
     if (threadIdx.x == 0) stamp(p.trace, 0);
 
-    // ===== producer duty (lane 0 of warp 0): stream this CTA's byte ranges into the ring =====
-    // Stage use f may be issued once every warp has released use f - stages (empty barrier) -- and this warp itself
-    // has, which holds while f < it + stages (it = the next stage this warp will consume).  The first `stages` uses
-    // need nothing and are issued right here, BEFORE waiting for the previous grid.
-    const uint8_t *gq = p.qs + r_begin * row_qs;
-    const uint8_t *gs = reinterpret_cast<const uint8_t *>(p.d) + r_begin * row_sc;
-    int issued = 0, ist = 0;
-    uint32_t iph = 0;
-    auto produce = [&](int upto) {
-        while (issued < upto) {
-            mbar_wait(&empty_bar[ist], iph ^ 1u);
-            const int rows = min(g.rs, nrows - issued * g.rs);
-            unsigned char *dst = ring + (size_t)ist * g.stage_bytes;
-            mbar_expect_tx(&full_bar[ist], (uint32_t)(rows * (row_qs + row_sc)));
-            bulk_g2s(dst, gq, (uint32_t)(rows * row_qs), &full_bar[ist]);
-            bulk_g2s(dst + g.stage_qs, gs, (uint32_t)(rows * row_sc), &full_bar[ist]);
-            gq += (size_t)g.rs * row_qs;
-            gs += (size_t)g.rs * row_sc;
-            issued++;
-            if (++ist == g.stages) { ist = 0; iph ^= 1u; }
-        }
+    // ===== streaming this CTA's byte ranges into the ring =====
+    // issue_stage(f, slot): bulk-copy stage use f (rows f*rs ..) into ring slot `slot`.  The first `stages` uses are issued
+    // by thread 0 right here, BEFORE waiting for the previous grid.  Afterwards the ring refills itself: every warp counts
+    // itself out of a stage (shared-memory counter), and the warp that leaves last re-issues that slot for use f + stages.
+    const uint8_t *gq0 = p.qs + r_begin * row_qs;
+    const uint8_t *gs0 = reinterpret_cast<const uint8_t *>(p.d) + r_begin * row_sc;
+    int *stage_cnt = reinterpret_cast<int *>(empty_bar);   // [kMaxStages] ints, reusing the (now unused) empty-barrier words
+    auto issue_stage = [&](int f, int slot) {
+        const int rows = min(g.rs, nrows - f * g.rs);
+        unsigned char *dst = ring + (size_t)slot * g.stage_bytes;
+        mbar_expect_tx(&full_bar[slot], (uint32_t)(rows * (row_qs + row_sc)));
+        bulk_g2s(dst, gq0 + (size_t)f * g.rs * row_qs, (uint32_t)(rows * row_qs), &full_bar[slot]);
+        bulk_g2s(dst + g.stage_qs, gs0 + (size_t)f * g.rs * row_sc, (uint32_t)(rows * row_sc), &full_bar[slot]);
     };
-    if (threadIdx.x == 0) produce(min(nstage_iters, g.stages));
+    if (threadIdx.x == 0) {
+        const int n0 = min(nstage_iters, g.stages);
+        for (int f = 0; f < n0; f++) issue_stage(f, f);
+    }
     __syncwarp();   // reconverge BEFORE griddepcontrol.wait: a warp parked in the wait takes its diverged lane 0 with it
 
     // ===== consumers =====
@@ -431,43 +426,85 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
     constexpr int kU = NCOLS == 1 ? 4 : (NCOLS <= 2 ? 2 : 1);
     const int ppst = g.rs / rows_per_pass;            // passes per stage
     const int total_slots = nstage_iters * ppst;
-    const int gsz = min(kU, g.stages * ppst);         // a group holds its stages until released: stay inside the ring
     int rows_in_chunk = 0, chunk_row0 = 0, cpar = 0;  // k-split bookkeeping (G > 1, where ppst == 1)
-    int it = 0, ps = 0, st = 0;                       // stage iteration / pass / ring slot of the next slot
+    int it = 0, ps = 0, st = 0;                       // stage use / pass / ring slot of the next slot
     uint32_t par = 0;                                 // parity of the full barrier for `it`
-    for (int j0 = 0; j0 < total_slots; j0 += gsz) {
-        const int nslot = min(gsz, total_slots - j0);
-        if (threadIdx.x == 0) produce(min(nstage_iters, it + g.stages));
-        __syncwarp();
+    for (int j0 = 0; j0 < total_slots; j0 += kU) {
+        const int nslot = min(kU, total_slots - j0);
         float acc[kU][NCOLS];
         int grow[kU];          // row index relative to r_begin
         int prow[kU];          // row index relative to the k-split chunk
         bool rlive[kU];
-        uint32_t wbase[kU], sbase[kU];
-        uint32_t rel_mask = 0;  // bit u: slot u is the last pass of its stage; bits 8.. : its ring slot (4 bits each)
         int chunk_rows_added = 0;
-        // ---- phase 1: wait for the stages, resolve row addresses ----
+        // Slots are processed one after the other -- wait for the slot's stage, 4 independent block dots per lane, count
+        // this warp out of the stage when it was its last pass -- so stages are released (and refilled) one at a time and
+        // the ring never drains behind a whole group.  Only the shuffle reduction is shared by the kU rows of the group.
 #pragma unroll
         for (int u = 0; u < kU; u++) {
             const bool valid = u < nslot;
-            if (valid && (ps == 0 || u == 0)) {
-                mbar_wait_a(full_a + 8u * (uint32_t)st, par);
-                if (j0 == 0 && u == 0 && threadIdx.x == 0) stamp(p.trace, 4);
-            }
-            const int rows = valid ? min(g.rs, nrows - it * g.rs) : 1;   // slots past the group alias row 0 of the ring
-            const int r = ps * rows_per_pass + row_in_pass;
-            rlive[u] = valid && r < rows;
-            const int rr = valid ? min(r, rows - 1) : 0;
-            const uint32_t stage_a = ring_a + (valid ? (uint32_t)(st * g.stage_bytes) : 0u);
-            wbase[u] = stage_a + (uint32_t)(rr * row_qs);
-            sbase[u] = stage_a + (uint32_t)(rr * row_sc);   // + soff[i] (which already includes stage_qs)
-            grow[u] = it * g.rs + rr;
-            prow[u] = rows_in_chunk + chunk_rows_added + rr;
 #pragma unroll
             for (int c = 0; c < NCOLS; c++) acc[u][c] = 0.0f;
+            rlive[u] = false;
+            grow[u] = 0;
+            prow[u] = 0;
             if (valid) {
-                if (ps + 1 == ppst) {      // leaving the stage after this slot
-                    rel_mask |= (1u << u) | ((uint32_t)st << (8 + 4 * u));
+                if (ps == 0) {
+                    mbar_wait_a(full_a + 8u * (uint32_t)st, par);
+                    if (j0 == 0 && u == 0 && threadIdx.x == 0) stamp(p.trace, 4);
+                }
+                const int rows = min(g.rs, nrows - it * g.rs);
+                const int r = ps * rows_per_pass + row_in_pass;
+                rlive[u] = r < rows;
+                const int rr = min(r, rows - 1);
+                const uint32_t stage_a = ring_a + (uint32_t)(st * g.stage_bytes);
+                const uint32_t wbase = stage_a + (uint32_t)(rr * row_qs) + woff0;
+                const uint32_t sbase = stage_a + (uint32_t)(rr * row_sc) + soff0;   // soff0 already includes stage_qs
+                grow[u] = it * g.rs + rr;
+                prow[u] = rows_in_chunk + chunk_rows_added + rr;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint4 w0 = lds128(wbase + (uint32_t)(i * 32 * QSB));
+                    uint4 w1 = make_uint4(0, 0, 0, 0);
+                    if (TYPE == B200_TYPE_Q8_0) w1 = lds128(wbase + (uint32_t)(i * 32 * QSB + 16));
+                    const float dw = lds_h2f(sbase + (uint32_t)(i * 64));
+                    if (NCOLS == 1) {
+                        const int sumi = block_dot<TYPE>(w0, w1, alo[i], ahi[i], s8[i]);
+                        if (DOTS) {
+                            if (blive[i] && rlive[u]) p.dots[(r_begin + grow[u]) * nb + b0 + lane + 32 * i] = sumi;
+                        } else if (blive[i]) {
+                            acc[u][0] = fmaf((float)sumi, dw * da[i], acc[u][0]);
+                        }
+                    } else {
+                        const uint32_t b = (uint32_t)min(b0 + lane + 32 * i, nb - 1);
+#pragma unroll
+                        for (int c = 0; c < NCOLS; c++) {
+                            const uint32_t col = act_a + (uint32_t)(c * g.act_col);
+                            const uint4 xlo = lds128(col + b * 16);
+                            const uint4 xhi = lds128(col + (uint32_t)(k >> 1) + b * 16);
+                            const float dx = lds_f32(col + (uint32_t)k + b * 4);
+                            const int sx = TYPE == B200_TYPE_Q4_0 ? lds_s32(col + (uint32_t)k + (uint32_t)nb * 4 + b * 4) : 0;
+                            const int sumi = block_dot<TYPE>(w0, w1, xlo, xhi, sx);
+                            if (DOTS) {
+                                if (blive[i] && rlive[u]) p.dots[((int64_t)c * p.m + r_begin + grow[u]) * nb + b] = sumi;
+                            } else if (blive[i]) {
+                                acc[u][c] = fmaf((float)sumi, dw * dx, acc[u][c]);
+                            }
+                        }
+                    }
+                }
+                if (ps + 1 == ppst) {
+                    // last pass over this stage: count the warp out; whoever is last re-arms the slot for use it + stages.
+                    // (shared-memory loads and the atomic go through the same in-order LSU path of the warp, so every
+                    //  lane's reads of the stage have been performed when the atomic is.)
+                    __syncwarp();
+                    if (lane == 0) {
+                        __threadfence_block();
+                        if (atomicAdd(&stage_cnt[st], 1) == kConsumerWarps - 1) {
+                            stage_cnt[st] = 0;
+                            __threadfence_block();
+                            if (it + g.stages < nstage_iters) issue_stage(it + g.stages, st);
+                        }
+                    }
                     if (G > 1) chunk_rows_added += rows;
                     ps = 0;
                     it++;
@@ -476,48 +513,6 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
                     ps++;
                 }
             }
-        }
-        // ---- phase 2: the dots (straight-line) ----
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-#pragma unroll
-            for (int u = 0; u < kU; u++) {
-                const uint4 w0 = lds128(wbase[u] + woff0 + (uint32_t)(i * 32 * QSB));
-                uint4 w1 = make_uint4(0, 0, 0, 0);
-                if (TYPE == B200_TYPE_Q8_0) w1 = lds128(wbase[u] + woff0 + (uint32_t)(i * 32 * QSB + 16));
-                const float dw = lds_h2f(sbase[u] + soff0 + (uint32_t)(i * 64));
-                if (NCOLS == 1) {
-                    const int sumi = block_dot<TYPE>(w0, w1, alo[i], ahi[i], s8[i]);
-                    if (DOTS) {
-                        if (blive[i] && rlive[u]) p.dots[(r_begin + grow[u]) * nb + b0 + lane + 32 * i] = sumi;
-                    } else if (blive[i]) {
-                        acc[u][0] = fmaf((float)sumi, dw * da[i], acc[u][0]);
-                    }
-                } else {
-                    const uint32_t b = (uint32_t)min(b0 + lane + 32 * i, nb - 1);
-#pragma unroll
-                    for (int c = 0; c < NCOLS; c++) {
-                        const uint32_t col = act_a + (uint32_t)(c * g.act_col);
-                        const uint4 xlo = lds128(col + b * 16);
-                        const uint4 xhi = lds128(col + (uint32_t)(k >> 1) + b * 16);
-                        const float dx = lds_f32(col + (uint32_t)k + b * 4);
-                        const int sx = TYPE == B200_TYPE_Q4_0 ? lds_s32(col + (uint32_t)k + (uint32_t)nb * 4 + b * 4) : 0;
-                        const int sumi = block_dot<TYPE>(w0, w1, xlo, xhi, sx);
-                        if (DOTS) {
-                            if (blive[i] && rlive[u]) p.dots[((int64_t)c * p.m + r_begin + grow[u]) * nb + b] = sumi;
-                        } else if (blive[i]) {
-                            acc[u][c] = fmaf((float)sumi, dw * dx, acc[u][c]);
-                        }
-                    }
-                }
-            }
-        }
-        // ---- phase 3: release every stage whose last pass was in this group ----
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-            for (int u = 0; u < kU; u++)
-                if (rel_mask & (1u << u)) mbar_arrive_a(empty_a + 8u * ((rel_mask >> (8 + 4 * u)) & 15u));
         }
         rows_in_chunk += chunk_rows_added;
 
@@ -556,7 +551,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
         if (!DOTS && G > 1) {
             // k-split: partials of up to g.pr rows are parked in shared memory (double-buffered by chunk parity) and
             // combined in segment order after ONE barrier per chunk -- for decode shapes that is once per kernel.
-            if (j0 + gsz >= total_slots || rows_in_chunk + kU * g.rs > g.pr) {
+            if (j0 + kU >= total_slots || rows_in_chunk + kU * g.rs > g.pr) {
                 consumer_bar_sync();
                 for (int t = threadIdx.x; t < rows_in_chunk * NCOLS; t += kConsumerThreads) {
                     const int r = t / NCOLS, c = t - r * NCOLS;
