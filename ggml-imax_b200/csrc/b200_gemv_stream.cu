@@ -76,6 +76,10 @@ struct StreamGeom {
     int stage_bytes;  // aligned total
     int act_col;      // bytes of activation scratch per column
     int ring_off, act_off, part_off, bar_off, llstage_off, total;
+    // division-free bookkeeping, precomputed on the host
+    int log2g;        // g == 1 << log2g
+    int ppst;         // passes per stage = rs / (8 / g)
+    int rows_q, rows_rem;   // CTA c owns rows [c*rows_q + min(c, rows_rem), +rows_q + (c < rows_rem))
 };
 
 __host__ __device__ inline size_t stream_act_col_bytes(int type, int k) {
@@ -256,10 +260,17 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
     uint64_t *empty_bar = full_bar + kMaxStages;
 
     // this CTA's contiguous run of rows
-    const int64_t r_begin = (int64_t)blockIdx.x * p.m / gridDim.x;
-    const int64_t r_end = (int64_t)(blockIdx.x + 1) * p.m / gridDim.x;
-    const int nrows = (int)(r_end - r_begin);
-    const int nstage_iters = (nrows + g.rs - 1) / g.rs;
+    const int bx = (int)blockIdx.x;
+    const int64_t r_begin = (int64_t)bx * g.rows_q + min(bx, g.rows_rem);
+    const int nrows = g.rows_q + (bx < g.rows_rem ? 1 : 0);
+    int nstage_iters = 0;
+    for (int r = 0; r < nrows; r += g.rs) nstage_iters++;   // ceil(nrows / rs) without a division (a handful of iterations)
+    // which (row-in-pass, k-segment) this warp serves -- all shifts, computed before the dependency wait
+    const int G = g.g;
+    const int seg = warp & (G - 1);
+    const int row_in_pass = warp >> g.log2g;
+    const int rows_per_pass = kConsumerWarps >> g.log2g;
+    const int b0 = seg * kSegBlocks;  // first block of the segment
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; s++) {
@@ -386,12 +397,6 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
     consumer_bar_sync();
     if (threadIdx.x == 0) stamp(p.trace, 3);
 
-    // ---- which (row-in-pass, k-segment) this warp serves ----
-    const int G = g.g;
-    const int seg = warp % G;
-    const int row_in_pass = warp / G;
-    const int rows_per_pass = kConsumerWarps / G;
-    const int b0 = seg * kSegBlocks;  // first block of the segment
 
     const uint32_t ring_a = smem_u32(ring), act_a = smem_u32(act);
     const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
@@ -424,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
     // wait for the stages they live in, kU independent row dots, one joint shuffle reduction, release the stages.
     // All stage/pass bookkeeping is incremental (no divisions) and all shared addresses are 32-bit.
     constexpr int kU = NCOLS == 1 ? 4 : (NCOLS <= 2 ? 2 : 1);
-    const int ppst = g.rs / rows_per_pass;            // passes per stage
+    const int ppst = g.ppst;                          // passes per stage
     const int total_slots = nstage_iters * ppst;
     int rows_in_chunk = 0, chunk_row0 = 0, cpar = 0;  // k-split bookkeeping (G > 1, where ppst == 1)
     int it = 0, ps = 0, st = 0;                       // stage use / pass / ring slot of the next slot
@@ -599,6 +604,8 @@ bool stream_geometry(const b200_gemv_params &p, StreamGeom *g) {
     rs = rs / rows_per_pass * rows_per_pass;
     g->rs = rs;
     g->g = G;
+    g->log2g = G == 1 ? 0 : (G == 2 ? 1 : (G == 4 ? 2 : 3));
+    g->ppst = rs / rows_per_pass;
     g->stage_qs = rs * row_qs;
     g->stage_sc = rs * row_sc;
     g->stage_bytes = (int)b200_align_up((size_t)g->stage_qs + g->stage_sc, 128);
@@ -631,6 +638,9 @@ int launch_stream_typed(b200_ctx *ctx, const b200_gemv_params &p, const StreamGe
     B200_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     int64_t ctas = ctx->sm_count;
     if (ctas > p.m) ctas = p.m;
+    StreamGeom gg = g;
+    gg.rows_q = (int)(p.m / ctas);
+    gg.rows_rem = (int)(p.m % ctas);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)ctas, 1, 1);
@@ -650,7 +660,7 @@ int launch_stream_typed(b200_ctx *ctx, const b200_gemv_params &p, const StreamGe
     memset(&gd, 0, sizeof(gd));
     if (p.gather) gd = *p.gather;
     pp.gather = NULL;
-    B200_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kern, pp, g, gd));
+    B200_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kern, pp, gg, gd));
     ctx->launches++;
     return B200_OK;
 }
