@@ -13,7 +13,7 @@
 //   warp 1      MMA issuer: 4 x tcgen05.mma (K=32 each) per stage, each into its own 128-column TMEM buffer
 //               (4 buffers = all 512 columns), tcgen05.commit -> mbarriers (TMEM full, smem stage empty)
 //   warp 2      TMEM allocator / deallocator
-//   warps 4-19  epilogue: warp w reads TMEM lanes 32*(w%4).. (its hardware quadrant), columns 32*((w-4)/4)..;
+//   warps 4..   epilogue (B200_GEMM_EPI_WARPS = 8 or 16): warp w reads TMEM lanes 32*(w%4).. (its hardware quadrant), columns 32*((w-4)/4)..;
 //               thread = one weight row: d_w is a per-thread scalar, d_x a warp-uniform (broadcast) load;
 //               32 fp32 accumulators per thread; final store is coalesced along m.
 // Q4_0 weights are expanded to int8 (nib - 8) by expand_q4_0_kernel into scratch first (v1; fusing the expansion
@@ -27,7 +27,10 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 128;  // BK bytes of int8 = one 128-byte swizzle atom = 4 quant blocks
 constexpr int kStages = 4;
 constexpr int kTmemBufs = 4;
-constexpr int kEpiWarps = 16;                // 4 per TMEM lane quadrant, BN / 4 = 32 columns each
+#ifndef B200_GEMM_EPI_WARPS
+#define B200_GEMM_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = B200_GEMM_EPI_WARPS;   // a multiple of 4 (one per TMEM lane quadrant); each takes BN / (kEpiWarps/4) columns
 constexpr int kGemmThreads = 128 + kEpiWarps * 32;
 constexpr int kScaleBytes = (BK / 32) * BN * 4;            // activation scales of the stage's 4 k-blocks: [4][128] fp32
 constexpr int kStageBytes = BM * BK + BN * BK + kScaleBytes;  // 34 KB (a multiple of 1024: operand tiles stay 1024-aligned)
@@ -214,7 +217,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int row_c = row < g.m ? row : g.m - 1;
         const __half *dwp = g.dw + (int64_t)row_c * nb;
         constexpr int kCols = BN / (kEpiWarps / 4);
-        static_assert(kCols == 32, "one tcgen05.ld.32x32b.x32 per k-block per warp");
+        static_assert(kCols % 32 == 0, "whole tcgen05.ld.32x32b.x32 loads per k-block per warp");
         float acc[kCols];
         unsigned long long acc2[kCols / 2];   // packed pairs of fp32 accumulators
 #pragma unroll
@@ -236,8 +239,39 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             return make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
         };
         dwq = load_dw(0);
+        static_assert(kCols == 64, "software pipeline below is written for two 32-column halves per k-block");
+        const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cgrp * kCols);
+        // scale math for 32 columns of one k-block: acc += float(p) * (d_w * d_x), packed f32x2
+        auto scale_acc = [&](const uint32_t (&pv)[32], uint32_t sdx_kb, unsigned long long dw2, int half) {
+#pragma unroll
+            for (int c4 = 0; c4 < 8; c4++) {
+                unsigned long long d01, d23;   // d_x of 4 columns: warp-uniform shared-memory broadcast
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(d01), "=l"(d23) : "r"(sdx_kb + (uint32_t)(half * 128 + c4 * 16)));
+                const unsigned long long s01 = mul2(dw2, d01), s23 = mul2(dw2, d23);
+                const unsigned long long v01 = pack2((float)(int32_t)pv[c4 * 4 + 0], (float)(int32_t)pv[c4 * 4 + 1]);
+                const unsigned long long v23 = pack2((float)(int32_t)pv[c4 * 4 + 2], (float)(int32_t)pv[c4 * 4 + 3]);
+                acc2[half * 16 + c4 * 2 + 0] = fma2(v01, s01, acc2[half * 16 + c4 * 2 + 0]);
+                acc2[half * 16 + c4 * 2 + 1] = fma2(v23, s23, acc2[half * 16 + c4 * 2 + 1]);
+            }
+        };
+        auto dump_dots = [&](const uint32_t (&pv)[32], int kb, int half) {
+            if (row < g.m) {
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    const int col = n0 + cgrp * kCols + half * 32 + c;
+                    if (col < g.n) g.dots[((int64_t)col * g.m + row) * nb + kb] = (int32_t)pv[c];
+                }
+            }
+        };
+        // Software pipeline over (k-block, half): the TMEM load of the NEXT half is in flight while the scale math of the
+        // current one runs (two register sets pa / pb); the TMEM buffer is handed back to the MMA warp as soon as its second
+        // half has landed in registers.
+        uint32_t pa[32], pb[32];
         int st = 0;
         uint32_t tph = 0;
+        mbar_wait(&tfull_bar[0], 0);
+        tc_fence_after();
+        tc_ld32(tcol, pa);                                   // (kb 0, half 0) in flight
         for (int it = 0; it < kiters; it++) {
             const uint2 dwcur = dwq;
             if (it + 1 < kiters) dwq = load_dw(it + 1);
@@ -248,36 +282,22 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (kb < nb) {
                     const uint32_t hbits = (j < 2 ? dwcur.x : dwcur.y) >> ((j & 1) * 16);
                     const float dw = __half2float(__ushort_as_half((unsigned short)(hbits & 0xffffu)));
-                    mbar_wait(&tfull_bar[j], tph);
-                    tc_fence_after();
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * BN + cgrp * kCols);
-                    uint32_t pv[32];
-                    tc_ld32(taddr, pv);
-                    tc_wait_ld();
+                    const unsigned long long dw2 = pack2(dw, dw);
+                    const uint32_t tbuf = tcol + (uint32_t)(j * BN);
+                    tc_wait_ld();                            // pa = (kb, half 0)
+                    tc_ld32(tbuf + 32, pb);                  // (kb, half 1) in flight
+                    if (DOTS) dump_dots(pa, kb, 0); else scale_acc(pa, sdx + (uint32_t)(j * BN * 4), dw2, 0);
+                    tc_wait_ld();                            // pb = (kb, half 1): this warp is done with TMEM buffer j
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[j]);   // TMEM buffer j may be overwritten by the next stage's MMA
-                    if (DOTS) {
-                        if (row < g.m) {
-#pragma unroll
-                            for (int c = 0; c < kCols; c++) {
-                                const int col = n0 + cgrp * kCols + c;
-                                if (col < g.n) g.dots[((int64_t)col * g.m + row) * nb + kb] = (int32_t)pv[c];
-                            }
-                        }
-                    } else {
-                        const unsigned long long dw2 = pack2(dw, dw);
-#pragma unroll
-                        for (int c4 = 0; c4 < kCols / 4; c4++) {
-                            unsigned long long d01, d23;   // d_x of 4 columns: warp-uniform shared-memory broadcast
-                            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(d01), "=l"(d23) : "r"(sdx + (uint32_t)(j * BN * 4 + c4 * 16)));
-                            const unsigned long long s01 = mul2(dw2, d01), s23 = mul2(dw2, d23);
-                            const unsigned long long v01 = pack2((float)(int32_t)pv[c4 * 4 + 0], (float)(int32_t)pv[c4 * 4 + 1]);
-                            const unsigned long long v23 = pack2((float)(int32_t)pv[c4 * 4 + 2], (float)(int32_t)pv[c4 * 4 + 3]);
-                            acc2[c4 * 2 + 0] = fma2(v01, s01, acc2[c4 * 2 + 0]);
-                            acc2[c4 * 2 + 1] = fma2(v23, s23, acc2[c4 * 2 + 1]);
-                        }
+                    if (lane == 0) mbar_arrive(&tempty_bar[j]);
+                    if (kb + 1 < nb) {                       // next k-block's first half: buffer (j + 1) % 4
+                        const int jn = (j + 1) & 3;
+                        mbar_wait(&tfull_bar[jn], jn == 0 ? (tph ^ 1u) : tph);
+                        tc_fence_after();
+                        tc_ld32(tcol + (uint32_t)(jn * BN), pa);
                     }
+                    if (DOTS) dump_dots(pb, kb, 1); else scale_acc(pb, sdx + (uint32_t)(j * BN * 4), dw2, 1);
                 }
             }
             // done with this stage's scales: let the producer refill it
