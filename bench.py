@@ -43,9 +43,26 @@ WIRE = {Q4_0: 18, Q8_0: 34}
 
 # GPT-J 6B (examples/gpt-j/main.cpp:22-27, :225-257): n_embd 4096, n_layer 28, n_vocab 50400, ffn 4*n_embd
 N_EMBD, N_LAYER, N_VOCAB, N_FF = 4096, 28, 50400, 16384
-LAYER_MATS = [("q", N_EMBD, N_EMBD), ("k", N_EMBD, N_EMBD), ("v", N_EMBD, N_EMBD), ("o", N_EMBD, N_EMBD),
-              ("fc_in", N_FF, N_EMBD), ("fc_out", N_EMBD, N_FF)]          # (name, m, k)
-WORKLOAD = "gptj6b_q4_0_decode_mul_mat_chain(28x[4x4096^2,16384x4096,4096x16384]+50400x4096,n=1)"
+# per block, in graph order, with the dependency structure of examples/gpt-j/main.cpp:462-551: q, k, v and fc_in all read the
+# block input (":534 this is independent of the self-attention result"), o reads the attention output (stand-in: v),
+# fc_out reads fc_in; the next block reads fc_out (stand-in for the residual sum, which is glue outside this path)
+LAYER_MATS = [("q", N_EMBD, N_EMBD), ("k", N_EMBD, N_EMBD), ("v", N_EMBD, N_EMBD), ("fc_in", N_FF, N_EMBD),
+              ("o", N_EMBD, N_EMBD), ("fc_out", N_EMBD, N_FF)]          # (name, m, k)
+WORKLOAD = "gptj6b_q4_0_decode_mul_mat_graph(28x[q,k,v,fc_in<-x; o<-v; fc_out<-fc_in]+lm_head 50400x4096, n=1)"
+
+
+def gptj_dag():
+    """[(name, m, k, src)]: src = index of the node whose output is this node's src1, -1 = the token's input vector"""
+    nodes, prev = [], -1
+    for l in range(N_LAYER):
+        b = len(nodes)
+        for name, m, k in LAYER_MATS[:4]:
+            nodes.append((name, m, k, prev))
+        nodes.append(("o", N_EMBD, N_EMBD, b + 2))
+        nodes.append(("fc_out", N_EMBD, N_FF, b + 3))
+        prev = b + 5
+    nodes.append(("lm_head", N_VOCAB, N_EMBD, prev))
+    return nodes
 
 
 def _load(name, path):
@@ -62,14 +79,6 @@ def load_qmm():
 
 def load_rowsplit():
     return _load("ggml_imax_b200_rowsplit", PKG / "rowsplit.py")
-
-
-def chain_mats():
-    mats = []
-    for _ in range(N_LAYER):
-        mats.extend(LAYER_MATS)
-    mats.append(("lm_head", N_VOCAB, N_EMBD))
-    return mats
 
 
 def algorithmic_bytes(m, k, n, wire):
@@ -154,7 +163,8 @@ def run_b200(args):
     P = peaks()
 
     # ---- weights: random-init in wire format, one host copy per distinct shape, row-split, set_tensor (repack) per matrix
-    mats = chain_mats()
+    dag = gptj_dag()
+    mats = [(name, m, k) for name, m, k, _ in dag]
     host_w = {}
     for name, m, k in set(mats):
         host_w[(m, k)] = qmm.random_wire_weights(Q4_0, k, m, seed=1234 + m + k)
@@ -169,61 +179,86 @@ def run_b200(args):
         if split.rows > 0:
             t.set(host_w[(m, k)][split.r0:split.r1])
         weights.append((t, split, k))
-    # activations: ping-pong full vectors sized for the largest padded m
-    max_len = max(((m + world - 1) // world) * world for _, m, _ in mats)
-    act = [torch.zeros(max_len, dtype=torch.float32, device=dev) for _ in range(2)]
+    # activations: every node of a block writes its own vector; two sets (block parity) + one for the logits
+    def padded(m):
+        return ((m + world - 1) // world) * world
+    out_len = [padded(m) for _, m, _ in LAYER_MATS]
+    out_off = [sum(out_len[:i]) for i in range(6)]
+    set_len = sum(out_len)
+    lm_off = 2 * set_len
+    total_len = lm_off + padded(N_VOCAB)
+
+    def node_off(i):          # element offset of node i's output vector
+        return lm_off if i == len(dag) - 1 else ((i // 6) & 1) * set_len + out_off[i % 6]
+    act = torch.zeros(total_len, dtype=torch.float32, device=dev)
     x_in = torch.zeros(N_EMBD, dtype=torch.float32, device=dev)
     x_host = torch.empty(N_EMBD, dtype=torch.float32).pin_memory()
     x_host.copy_(torch.from_numpy(np.random.default_rng(1234).uniform(-1, 1, N_EMBD).astype(np.float32)))
     logits_host = torch.empty(N_VOCAB, dtype=torch.float32).pin_memory()
     x_in.copy_(x_host)
 
-    def token_step():
-        """one token: 169 mul_mats (each ONE fused quantize+GEMV launch) [+ all-gather of the dst slices]"""
-        src = x_in
-        for i, (t, split, k) in enumerate(weights):
-            dst = act[i & 1]
-            rs.gathered_mul_mat(dist, split, 1, lambda out, ld, t=t, src=src, split=split:
-                                ctx.mul_mat_device(t, src.data_ptr(), 1, out.data_ptr(), m=split.rows), dst)
-            src = dst
-        return src
+    def node_src_ptr(i, base_ptr, esz):
+        src = dag[i][3]
+        return x_in.data_ptr() if src < 0 else base_ptr + node_off(src) * esz
 
-    # ---- fused path (N > 1): GEMV epilogue stores into every rank's activation vector over NVLink, flags instead of a collective
+    # launch groups: runs of consecutive nodes that read the same vector (q, k, v, fc_in of a block) go down as ONE batch
+    groups, i = [], 0
+    while i < len(dag):
+        j = i + 1
+        while j < len(dag) and dag[j][3] == dag[i][3] and dag[j][2] == dag[i][2]:
+            j += 1
+        groups.append(list(range(i, j)))
+        i = j
+
+    def token_step():
+        """one token: the 169 mul_mats of the GPT-J decode graph.  N == 1: 85 launches (same-input projections batched,
+        quantize fused into every GEMV); N > 1 on this (NCCL) path: one launch + one all-gather per mul_mat"""
+        base = act.data_ptr()
+        if world == 1:
+            for grp in groups:
+                ctx.mul_mat_batch([ctx.make_args(weights[i][0], node_src_ptr(i, base, 4), 1, base + node_off(i) * 4) for i in grp])
+        else:
+            for i, (t, split, k) in enumerate(weights):
+                o = node_off(i)
+                dst = act[o:o + padded(dag[i][1])]
+                src_ptr = node_src_ptr(i, base, 4)
+                rs.gathered_mul_mat(dist, split, 1, lambda out, ld, t=t, src_ptr=src_ptr, split=split:
+                                    ctx.mul_mat_device(t, src_ptr, 1, out.data_ptr(), m=split.rows), dst)
+        return act[lm_off:lm_off + N_VOCAB]
+
+    # ---- fused path (N > 1): GEMV epilogue stores into every rank's activation vector over NVLink, tags instead of a collective
     fused = None
     out_ptr_fused = None
     if world > 1 and args.gather == "fused":
         try:
             n_slots = len(weights) + 1
-            abuf = [ctx.alloc(max_len * 8), ctx.alloc(max_len * 8)]          # LL activation vectors: {fp32, tag} per element
+            abuf = ctx.alloc(total_len * 8)                                  # LL activation vectors: {fp32, tag} per element
             state = ctx.alloc(n_slots * 2 * 4)
             dense = ctx.alloc(N_VOCAB * 4)
-            for b in abuf + [state, dense]:
+            for b in (abuf, state, dense):
                 ctx._check(ctx.lib.b200_memset(ctx.h, b.ptr, 0, b.nbytes))
-            mine = [ctx.ipc_export(b.ptr) for b in abuf]
             allh = [None] * world
-            dist.all_gather_object(allh, mine)
-            peers = [[abuf[0].ptr, abuf[1].ptr] if r == rank else [ctx.ipc_import(h) for h in allh[r]] for r in range(world)]
+            dist.all_gather_object(allh, ctx.ipc_export(abuf.ptr))
+            peers = [abuf.ptr if r == rank else ctx.ipc_import(allh[r]) for r in range(world)]
             dist.barrier()
             gathers = []
             for i, (t, split, k) in enumerate(weights):
                 g = qmm.Gather()
-                g.world, g.rank, g.slot, g.wait_slot, g.row0 = world, rank, i, i - 1, split.r0
+                g.world, g.rank, g.slot, g.wait_slot, g.row0 = world, rank, i, dag[i][3], split.r0
                 for r in range(world):
-                    g.peer_dst[r] = peers[r][i & 1]
+                    g.peer_dst[r] = peers[r] + node_off(i) * 8
                 g.state = state.ptr
                 gathers.append(g)
             gw = qmm.Gather()
             gw.world, gw.rank, gw.slot, gw.wait_slot, gw.row0 = world, rank, n_slots - 1, len(weights) - 1, 0
             for r in range(world):
-                gw.peer_dst[r] = peers[r][0]
+                gw.peer_dst[r] = peers[r]
             gw.state = state.ptr
 
             def token_step_fused():
-                src = x_in.data_ptr()
                 for i, (t, split, k) in enumerate(weights):
-                    ctx.mul_mat_gather(t, src, gathers[i], m=split.rows)
-                    src = abuf[i & 1].ptr
-                ctx.gather_finish(gw, src, dense.ptr, N_VOCAB)      # logits complete on this rank, as plain fp32
+                    ctx.mul_mat_gather(t, node_src_ptr(i, abuf.ptr, 8), gathers[i], m=split.rows)
+                ctx.gather_finish(gw, abuf.ptr + lm_off * 8, dense.ptr, N_VOCAB)      # logits complete on this rank, as plain fp32
                 return dense.ptr
             fused = token_step_fused
             out_ptr_fused = dense.ptr
@@ -231,7 +266,7 @@ def run_b200(args):
             print(f"[bench] fused all-gather unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
             fused = None
 
-    launches_per_step = sum(1 for w in weights if w[1].rows > 0)
+    launches_per_step = len(groups) if world == 1 else sum(1 for w in weights if w[1].rows > 0)
     # ---- capture the step once (our kernels + NCCL) into a CUDA graph: decode is launch-bound otherwise
     use_graph = not args.no_graph
     graph = None
@@ -241,7 +276,7 @@ def run_b200(args):
     step_fn = token_step
     if fused is not None:
         # same arithmetic, same row partition -> the fused path must reproduce the NCCL path bit for bit
-        ref_logits = out_t[:N_VOCAB].clone()
+        ref_logits = out_t.clone()
         fused()
         torch.cuda.synchronize()
         got = np.empty(N_VOCAB, np.float32)
@@ -324,7 +359,7 @@ def run_b200(args):
         names = ["entry", "primed", "pred done", "quantized", "first w", "last row", "flags seen", "flags out"]
         print(f"[trace r{rank}] launch " + " ".join(f"{n:>19s}" for n in names), file=sys.stderr)
         for i in range(min(14, launches_per_step)):
-            ctas = min(148, weights[i][1].rows)
+            ctas = 148
             row = []
             for sidx in range(8):
                 v = tr[i, :ctas, sidx]
@@ -355,7 +390,7 @@ def run_b200(args):
     line = None
     if rank == 0:
         line = {
-            "metric": "GPT-J-6B Q4_0 decode tokens/s (quantized mul_mat chain)", "value": round(tok_s, 2), "unit": "tokens/s",
+            "metric": "GPT-J-6B Q4_0 decode tokens/s (quantized mul_mat graph)", "value": round(tok_s, 2), "unit": "tokens/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8 dots (dp4a) + fp32 accumulate; Q4_0 weights, Q8_0 activations",
             "data": "synthetic (random-init Q4_0 blocks, U(-1,1) activations, seed 1234)",
@@ -502,32 +537,31 @@ def random_wire(qtype, k, m, seed):
 
 
 def cpu_reference_tok_s(budget_s, steps, warmup=1):
-    """GPT-J-6B Q4_0 decode chain on the host CPU.  Full 169-mat chain per token in ONE ggml graph, cycling over 2 distinct
-    layer weight sets (226 MB, far beyond any L2; keeps host RAM at ~0.4 GB).  steps=None: as many tokens as fit budget_s."""
+    """The GPT-J-6B Q4_0 decode mul_mat graph (same 169 nodes, same dependencies as our arm) on the host CPU as ONE ggml graph
+    per token, cycling over 2 distinct block weight sets (226 MB, far beyond any L2; keeps host RAM at ~0.4 GB).
+    steps=None: as many tokens as fit budget_s."""
     threads = host_threads()
     vp = C.c_void_p
-    mats = chain_mats()
+    dag = gptj_dag()
     nsets = 2
     x = np.random.default_rng(1234).uniform(-1, 1, N_EMBD).astype(np.float32)
-    sample = f"full 169-mul_mat token chain, 28 layers cycling over {nsets} distinct layer weight sets + lm_head, {threads} threads"
+    sample = f"full 169-mul_mat token graph, 28 blocks cycling over {nsets} distinct block weight sets + lm_head, {threads} threads"
+    # weight table: nsets x 6 block matrices + lm_head
+    wk, wm = [], []
+    for s in range(nsets):
+        for _, m, k in LAYER_MATS:
+            wk.append(k); wm.append(m)
+    wk.append(N_EMBD); wm.append(N_VOCAB)
+    node_w = [((i // 6) % nsets) * 6 + (i % 6) for i in range(len(dag) - 1)] + [nsets * 6]
+    node_src = [src for _, _, _, src in dag]
     if REF_SHIM.exists():
         r = C.CDLL(str(REF_SHIM))
-        r.ref_chain_create.restype = vp
+        r.ref_dag_create.restype = vp
         r.ref_chain_compute.restype = C.c_double
         r.ref_chain_compute.argtypes = [vp]
         r.ref_time_init()
-        wk, wm, wid = [], [], []
-        for s in range(nsets):
-            for _, m, k in LAYER_MATS:
-                wk.append(k); wm.append(m)
-        wk.append(N_EMBD); wm.append(N_VOCAB)
-        for l in range(N_LAYER):
-            wid.extend(range((l % nsets) * 6, (l % nsets) * 6 + 6))
-        wid.append(nsets * 6)
-        arr_wk = (C.c_int64 * len(wk))(*wk)
-        arr_wm = (C.c_int64 * len(wm))(*wm)
-        arr_wid = (C.c_int * len(wid))(*wid)
-        h = vp(r.ref_chain_create(Q4_0, len(wid), arr_wid, len(wk), arr_wk, arr_wm, C.c_int64(1), threads))
+        h = vp(r.ref_dag_create(Q4_0, len(dag), (C.c_int * len(dag))(*node_w), (C.c_int * len(dag))(*node_src), len(wk),
+                                (C.c_int64 * len(wk))(*wk), (C.c_int64 * len(wm))(*wm), C.c_int64(1), threads))
         for j, (k, m) in enumerate(zip(wk, wm)):
             w = random_wire(Q4_0, k, m, seed=1234 + m + k + j)
             r.ref_chain_set_weight(h, j, w.ctypes.data_as(vp))
@@ -551,25 +585,18 @@ def cpu_reference_tok_s(budget_s, steps, warmup=1):
     if not ORACLE_SO.exists():
         subprocess.check_call(["make", "-C", str(ROOT / "oracle"), "oracle"])
     o = C.CDLL(str(ORACLE_SO))
-    ws = {}
-    for s in range(nsets):
-        for name, m, k in LAYER_MATS:
-            ws[(s, name)] = random_wire(Q4_0, k, m, seed=1234 + m + k + s)
-    ws["lm"] = random_wire(Q4_0, N_EMBD, N_VOCAB, seed=99)
+    ws = [random_wire(Q4_0, k, m, seed=1234 + m + k + j) for j, (k, m) in enumerate(zip(wk, wm))]
     wdata = np.zeros(N_FF // 32 * 34, np.uint8)
 
     def token():
-        cur = x
-        for l in range(N_LAYER):
-            for name, m, k in LAYER_MATS:
-                dst = np.zeros(m, np.float32)
-                o.oracle_mul_mat_mt(Q4_0, ws[(l % nsets, name)].ctypes.data_as(vp), C.c_int64(k), C.c_int64(m), cur.ctypes.data_as(vp),
-                                    C.c_int64(1), dst.ctypes.data_as(vp), wdata.ctypes.data_as(vp), threads)
-                cur = dst
-        dst = np.zeros(N_VOCAB, np.float32)
-        o.oracle_mul_mat_mt(Q4_0, ws["lm"].ctypes.data_as(vp), C.c_int64(N_EMBD), C.c_int64(N_VOCAB), cur.ctypes.data_as(vp), C.c_int64(1),
-                            dst.ctypes.data_as(vp), wdata.ctypes.data_as(vp), threads)
-        return dst
+        outs = []
+        for i, (_, m, k, src) in enumerate(dag):
+            cur = x if src < 0 else outs[src]
+            dst = np.zeros(m, np.float32)
+            o.oracle_mul_mat_mt(Q4_0, ws[node_w[i]].ctypes.data_as(vp), C.c_int64(k), C.c_int64(m), cur.ctypes.data_as(vp),
+                                C.c_int64(1), dst.ctypes.data_as(vp), wdata.ctypes.data_as(vp), threads)
+            outs.append(dst)
+        return outs[-1]
     token()
     times, t_start = [], time.time()
     while True:
@@ -590,7 +617,7 @@ def run_reference(args):
     steps = min(args.steps, 30)
     cb = cpu_reference_tok_s(budget_s=120.0, steps=steps, warmup=min(max(args.warmup, 1), 3))
     line = {
-        "impl": "reference", "metric": "GPT-J-6B Q4_0 decode tokens/s (quantized mul_mat chain)", "value": cb["value"], "unit": "tokens/s",
+        "impl": "reference", "metric": "GPT-J-6B Q4_0 decode tokens/s (quantized mul_mat graph)", "value": cb["value"], "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": min(max(args.warmup, 1), 3), "ms_per_step": cb["ms_per_token"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "int8 dots (AVX2 maddubs) + fp32 accumulate; Q4_0 weights, Q8_0 activations",
         "data": "synthetic (random-init Q4_0 blocks, U(-1,1) activations, seed 1234)",

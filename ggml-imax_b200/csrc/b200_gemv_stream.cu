@@ -79,7 +79,22 @@ struct StreamGeom {
     // division-free bookkeeping, precomputed on the host
     int log2g;        // g == 1 << log2g
     int ppst;         // passes per stage = rs / (8 / g)
-    int rows_q, rows_rem;   // CTA c owns rows [c*rows_q + min(c, rows_rem), +rows_q + (c < rows_rem))
+};
+
+// Up to 4 independent decode mul_mats that share src1 (same k, same activations: q/k/v/fc_in of a transformer block) run
+// as ONE launch: the CTAs are divided among the matrices in proportion to their bytes, every CTA works on one matrix.
+constexpr int kMaxBatch = 4;
+struct StreamBatch {
+    int count;
+    int total_ctas;            // host side only: gridDim.x
+    struct Sub {
+        const uint8_t *qs;
+        const __half *d;
+        float *dst;
+        int m;
+        int cta0;              // first CTA of this matrix
+        int rows_q, rows_rem;  // CTA c (relative) owns rows [c*rows_q + min(c, rows_rem), +rows_q + (c < rows_rem))
+    } sub[kMaxBatch];
 };
 
 __host__ __device__ inline size_t stream_act_col_bytes(int type, int k) {
@@ -246,7 +261,7 @@ __global__ void __launch_bounds__(1024) gather_finish_kernel(const b200_gather g
 }
 
 template <int TYPE, int NCOLS, bool DOTS>
-__global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gemv_params p, const StreamGeom g, const b200_gather gd) {
+__global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gemv_params p, const StreamGeom g, const b200_gather gd, const StreamBatch sb) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int QSB = TYPE == B200_TYPE_Q4_0 ? 16 : 32;
     const int k = (int)p.k, nb = k >> 5;
@@ -260,9 +275,18 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
     uint64_t *empty_bar = full_bar + kMaxStages;
 
     // this CTA's contiguous run of rows
-    const int bx = (int)blockIdx.x;
-    const int64_t r_begin = (int64_t)bx * g.rows_q + min(bx, g.rows_rem);
-    const int nrows = g.rows_q + (bx < g.rows_rem ? 1 : 0);
+    // which matrix of the batch this CTA serves (count == 1: the plain single-matrix launch)
+    int si = 0;
+#pragma unroll
+    for (int j = 1; j < kMaxBatch; j++)
+        if (j < sb.count && (int)blockIdx.x >= sb.sub[j].cta0) si = j;
+    const uint8_t *const m_qs = sb.sub[si].qs;
+    const __half *const m_d = sb.sub[si].d;
+    float *const m_dst = sb.sub[si].dst;
+    const int64_t m_rows = sb.sub[si].m;
+    const int bx = (int)blockIdx.x - sb.sub[si].cta0;
+    const int64_t r_begin = (int64_t)bx * sb.sub[si].rows_q + min(bx, sb.sub[si].rows_rem);
+    const int nrows = sb.sub[si].rows_q + (bx < sb.sub[si].rows_rem ? 1 : 0);
     int nstage_iters = 0;
     for (int r = 0; r < nrows; r += g.rs) nstage_iters++;   // ceil(nrows / rs) without a division (a handful of iterations)
     // which (row-in-pass, k-segment) this warp serves -- all shifts, computed before the dependency wait
@@ -287,8 +311,8 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
     // issue_stage(f, slot): bulk-copy stage use f (rows f*rs ..) into ring slot `slot`.  The first `stages` uses are issued
     // by thread 0 right here, BEFORE waiting for the previous grid.  Afterwards the ring refills itself: every warp counts
     // itself out of a stage (shared-memory counter), and the warp that leaves last re-issues that slot for use f + stages.
-    const uint8_t *gq0 = p.qs + r_begin * row_qs;
-    const uint8_t *gs0 = reinterpret_cast<const uint8_t *>(p.d) + r_begin * row_sc;
+    const uint8_t *gq0 = m_qs + r_begin * row_qs;
+    const uint8_t *gs0 = reinterpret_cast<const uint8_t *>(m_d) + r_begin * row_sc;
     int *stage_cnt = reinterpret_cast<int *>(empty_bar);   // [kMaxStages] ints, reusing the (now unused) empty-barrier words
     auto issue_stage = [&](int f, int slot) {
         const int rows = min(g.rs, nrows - f * g.rs);
@@ -490,7 +514,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
                             const int sx = TYPE == B200_TYPE_Q4_0 ? lds_s32(col + (uint32_t)k + (uint32_t)nb * 4 + b * 4) : 0;
                             const int sumi = block_dot<TYPE>(w0, w1, xlo, xhi, sx);
                             if (DOTS) {
-                                if (blive[i] && rlive[u]) p.dots[((int64_t)c * p.m + r_begin + grow[u]) * nb + b] = sumi;
+                                if (blive[i] && rlive[u]) p.dots[((int64_t)c * m_rows + r_begin + grow[u]) * nb + b] = sumi;
                             } else if (blive[i]) {
                                 acc[u][c] = fmaf((float)sumi, dw * dx, acc[u][c]);
                             }
@@ -545,7 +569,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
                             // fused all-gather, producer side: the element goes to every rank's full vector (NVLink stores)
                             for (int r = 0; r < gd.world; r++) ll_store(gd.peer_dst[r], gd.row0 + r_begin + gr, v, gd_tag);
                         } else {
-                            p.dst[(int64_t)c * p.m + r_begin + gr] = v;
+                            m_dst[(int64_t)c * m_rows + r_begin + gr] = v;
                         }
                     }
                     else part[((cpar * g.pr + pr) * kConsumerWarps + seg) * NCOLS + c] = v;   // k-split: park the partial
@@ -565,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
                     if (gd.world > 1) {
                         for (int pr = 0; pr < gd.world; pr++) ll_store(gd.peer_dst[pr], gd.row0 + r_begin + chunk_row0 + r, v, gd_tag);
                     } else {
-                        p.dst[(int64_t)c * p.m + r_begin + chunk_row0 + r] = v;
+                        m_dst[(int64_t)c * m_rows + r_begin + chunk_row0 + r] = v;
                     }
                 }
                 chunk_row0 += rows_in_chunk;
@@ -633,14 +657,28 @@ bool stream_geometry(const b200_gemv_params &p, StreamGeom *g) {
 }
 
 template <int TYPE, int NCOLS>
-int launch_stream_typed(b200_ctx *ctx, const b200_gemv_params &p, const StreamGeom &g, bool dots) {
+int launch_stream_typed(b200_ctx *ctx, const b200_gemv_params &p, const StreamGeom &g, bool dots, const StreamBatch *batch = nullptr) {
     auto kern = dots ? gemv_stream_kernel<TYPE, NCOLS, true> : gemv_stream_kernel<TYPE, NCOLS, false>;
     B200_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    int64_t ctas = ctx->sm_count;
-    if (ctas > p.m) ctas = p.m;
     StreamGeom gg = g;
-    gg.rows_q = (int)(p.m / ctas);
-    gg.rows_rem = (int)(p.m % ctas);
+    StreamBatch sb;
+    memset(&sb, 0, sizeof(sb));
+    int64_t ctas;
+    if (batch) {
+        sb = *batch;
+        ctas = sb.total_ctas;
+    } else {
+        ctas = ctx->sm_count;
+        if (ctas > p.m) ctas = p.m;
+        sb.count = 1;
+        sb.sub[0].qs = p.qs;
+        sb.sub[0].d = p.d;
+        sb.sub[0].dst = p.dst;
+        sb.sub[0].m = (int)p.m;
+        sb.sub[0].cta0 = 0;
+        sb.sub[0].rows_q = (int)(p.m / ctas);
+        sb.sub[0].rows_rem = (int)(p.m % ctas);
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)ctas, 1, 1);
@@ -660,9 +698,52 @@ int launch_stream_typed(b200_ctx *ctx, const b200_gemv_params &p, const StreamGe
     memset(&gd, 0, sizeof(gd));
     if (p.gather) gd = *p.gather;
     pp.gather = NULL;
-    B200_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kern, pp, gg, gd));
+    B200_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kern, pp, gg, gd, sb));
     ctx->launches++;
     return B200_OK;
+}
+
+// divide the grid among the matrices of a batch in proportion to their rows (same k => same bytes per row)
+void build_batch(const b200_ctx *ctx, const b200_gemv_params *ps, int count, StreamBatch *sb) {
+    memset(sb, 0, sizeof(*sb));
+    sb->count = count;
+    int64_t rows = 0;
+    for (int j = 0; j < count; j++) rows += ps[j].m;
+    int64_t grid = ctx->sm_count;
+    if (grid > rows) grid = rows;
+    int64_t given = 0;
+    int share[kMaxBatch];
+    for (int j = 0; j < count; j++) {
+        int64_t c = grid * ps[j].m / rows;
+        if (c < 1) c = 1;
+        if (c > ps[j].m) c = ps[j].m;
+        share[j] = (int)c;
+        given += c;
+    }
+    // hand out what integer division left over to the matrices with the most rows per CTA
+    while (given < grid) {
+        int best = -1;
+        double worst = 0;
+        for (int j = 0; j < count; j++) {
+            const double load = (double)ps[j].m / share[j];
+            if (share[j] < ps[j].m && load > worst) { worst = load; best = j; }
+        }
+        if (best < 0) break;
+        share[best]++;
+        given++;
+    }
+    int cta0 = 0;
+    for (int j = 0; j < count; j++) {
+        sb->sub[j].qs = ps[j].qs;
+        sb->sub[j].d = ps[j].d;
+        sb->sub[j].dst = ps[j].dst;
+        sb->sub[j].m = (int)ps[j].m;
+        sb->sub[j].cta0 = cta0;
+        sb->sub[j].rows_q = (int)(ps[j].m / share[j]);
+        sb->sub[j].rows_rem = (int)(ps[j].m % share[j]);
+        cta0 += share[j];
+    }
+    sb->total_ctas = cta0;
 }
 
 template <int TYPE>
@@ -687,6 +768,28 @@ int b200_launch_gather_finish(b200_ctx *ctx, const b200_gather &gd, const void *
     ctx->launches++;
     B200_CUDA_TRY(ctx, cudaGetLastError());
     return B200_OK;
+}
+
+// One launch for `count` (2..4) decode mul_mats that share type, k and src1 (n == 1).  Returns false when the batch does
+// not qualify (the caller then launches them one by one).
+bool b200_try_launch_gemv_stream_batch(b200_ctx *ctx, const b200_gemv_params *ps, int count, int *rc) {
+    if (count < 2 || count > kMaxBatch) return false;
+    for (int j = 0; j < count; j++) {
+        const b200_gemv_params &p = ps[j];
+        if (p.n != 1 || p.dst_n != 1 || p.dots || p.gather) return false;
+        if (p.ne12 != 1 || p.ne13 != 1 || p.ne02 != 1 || p.ne03 != 1) return false;
+        if (p.k % 256 != 0 || p.k > 32768 || p.m < 1 || p.m >= (1ll << 31)) return false;
+        if (((uintptr_t)p.qs & 15) != 0 || ((uintptr_t)p.d & 15) != 0) return false;
+        if (p.type != ps[0].type || p.k != ps[0].k || p.x != ps[0].x) return false;
+    }
+    StreamGeom g;
+    if (!stream_geometry(ps[0], &g)) return false;
+    StreamBatch sb;
+    build_batch(ctx, ps, count, &sb);
+    if (ps[0].type == B200_TYPE_Q4_0) *rc = launch_stream_typed<B200_TYPE_Q4_0, 1>(ctx, ps[0], g, false, &sb);
+    else if (ps[0].type == B200_TYPE_Q8_0) *rc = launch_stream_typed<B200_TYPE_Q8_0, 1>(ctx, ps[0], g, false, &sb);
+    else return false;
+    return true;
 }
 
 // returns true when the streaming kernel takes this shape; *rc then holds the launch status

@@ -90,6 +90,7 @@ struct b200_gemv_params {
 };
 int b200_launch_gemv(b200_ctx *ctx, const b200_gemv_params &p);
 bool b200_try_launch_gemv_stream(b200_ctx *ctx, const b200_gemv_params &p, int *rc);
+bool b200_try_launch_gemv_stream_batch(b200_ctx *ctx, const b200_gemv_params *ps, int count, int *rc);
 int b200_launch_gather_finish(b200_ctx *ctx, const b200_gather &gd, const void *ll_src, float *out, int64_t count);
 
 struct b200_gemm_params {

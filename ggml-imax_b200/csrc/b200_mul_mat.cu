@@ -104,6 +104,54 @@ int b200_mul_mat(b200_ctx *ctx, const b200_mul_mat_args *a) {
     return run_gemv_chunks(ctx, a, qs, d);
 }
 
+static bool decode_params(const b200_ctx *ctx, const b200_mul_mat_args *a, b200_gemv_params *p) {
+    if (!quant_type_ok(a->type) || (a->flags & B200_MM_FORCE_GEMM)) return false;
+    if (a->ne11 != 1 || a->ne12 != 1 || a->ne13 != 1 || a->ne02 != 1 || a->ne03 != 1) return false;
+    if (a->ne00 <= 0 || a->ne00 % B200_QK != 0 || a->ne01 <= 0 || !a->src0_dev || !a->src1_dev || !a->dst_dev) return false;
+    const int64_t nb = a->ne00 / B200_QK;
+    if (a->src0_block_off < 0 || a->src0_block_off + nb * a->ne01 > a->src0_nblocks_total) return false;
+    if (((uintptr_t)a->src1_dev & 15) != 0) return false;
+    (void)ctx;
+    const int qsb = b200_qs_bytes(a->type);
+    memset(p, 0, sizeof(*p));
+    p->type = a->type;
+    p->qs = (const uint8_t *)a->src0_dev + a->src0_block_off * qsb;
+    p->d = (const __half *)((const uint8_t *)a->src0_dev + a->src0_nblocks_total * qsb) + a->src0_block_off;
+    p->k = a->ne00; p->m = a->ne01; p->ne02 = 1; p->ne03 = 1;
+    p->x = a->src1_dev;
+    p->n = 1; p->ne12 = 1; p->ne13 = 1;
+    p->nb11 = a->nb11; p->nb12 = a->nb12; p->nb13 = a->nb13;
+    p->dst = a->dst_dev;
+    p->dst_n = 1;
+    return true;
+}
+
+int b200_mul_mat_batch(b200_ctx *ctx, const b200_mul_mat_args *args, int count) {
+    B200_REQUIRE(ctx, ctx && args && count >= 0, B200_ERR_INVALID);
+    int i = 0;
+    while (i < count) {
+        // longest run (<= 4) starting at i that one streaming launch can take
+        b200_gemv_params ps[4];
+        int run = 0;
+        while (run < 4 && i + run < count && ctx->opt_gemv_stream && decode_params(ctx, &args[i + run], &ps[run]) &&
+               ps[run].type == ps[0].type && ps[run].k == ps[0].k && ps[run].x == ps[0].x)
+            run++;
+        int rc = B200_OK;
+        if (run >= 2) {
+            B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+            if (b200_try_launch_gemv_stream_batch(ctx, ps, run, &rc)) {
+                if (rc != B200_OK) return rc;
+                i += run;
+                continue;
+            }
+        }
+        rc = b200_mul_mat(ctx, &args[i]);
+        if (rc != B200_OK) return rc;
+        i++;
+    }
+    return B200_OK;
+}
+
 static bool gather_ok(const b200_gather *g) {
     if (!g || g->world < 1 || g->world > B200_MAX_RANKS || g->rank < 0 || g->rank >= g->world || g->slot < 0 || g->slot >= 1024 ||
         g->wait_slot >= 1024 || !g->state)

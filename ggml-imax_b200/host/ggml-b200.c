@@ -22,6 +22,7 @@
 #include <string.h>
 
 #define B200_BUFFER_ALIGNMENT 256
+#define B200_MAX_RUN 8
 
 /* ---- per-device shared state ----------------------------------------------------------------- */
 
@@ -352,27 +353,36 @@ GGML_CALL static bool b200_backend_supports_op(ggml_backend_t backend, const str
     return false;
 }
 
-static enum ggml_status b200_compute_mul_mat(struct b200_backend_context *bc, struct ggml_tensor *dst) {
+static bool b200_fill_mul_mat_args(struct ggml_tensor *dst, b200_mul_mat_args *args) {
     const struct ggml_tensor *a = dst->src[0], *b = dst->src[1];
     if (!b200_mul_mat_supported(dst)) {
         fprintf(stderr, "ggml-b200: MUL_MAT %s x %s not supported by this backend (no CPU fallback)\n",
-                ggml_type_name(a->type), ggml_type_name(b->type));
-        return GGML_STATUS_FAILED;
+                a ? ggml_type_name(a->type) : "?", b ? ggml_type_name(b->type) : "?");
+        return false;
     }
     struct b200_qloc loc;
     b200_locate_quantized(a, &loc);
-    b200_mul_mat_args args;
-    memset(&args, 0, sizeof(args));
-    args.type = (int32_t)a->type;
-    args.src0_dev = loc.base;
-    args.src0_nblocks_total = loc.total_blocks;
-    args.src0_block_off = loc.block_off;
-    args.ne00 = a->ne[0]; args.ne01 = a->ne[1]; args.ne02 = a->ne[2]; args.ne03 = a->ne[3];
-    args.src1_dev = (const float *)b->data;
-    args.ne11 = b->ne[1]; args.ne12 = b->ne[2]; args.ne13 = b->ne[3];
-    args.nb11 = b->nb[1]; args.nb12 = b->nb[2]; args.nb13 = b->nb[3];
-    args.dst_dev = (float *)dst->data;
-    const int rc = b200_mul_mat(bc->ctx, &args);
+    memset(args, 0, sizeof(*args));
+    args->type = (int32_t)a->type;
+    args->src0_dev = loc.base;
+    args->src0_nblocks_total = loc.total_blocks;
+    args->src0_block_off = loc.block_off;
+    args->ne00 = a->ne[0]; args->ne01 = a->ne[1]; args->ne02 = a->ne[2]; args->ne03 = a->ne[3];
+    args->src1_dev = (const float *)b->data;
+    args->ne11 = b->ne[1]; args->ne12 = b->ne[2]; args->ne13 = b->ne[3];
+    args->nb11 = b->nb[1]; args->nb12 = b->nb[2]; args->nb13 = b->nb[3];
+    args->dst_dev = (float *)dst->data;
+    return true;
+}
+
+/* nodes[0..n) are MUL_MAT nodes that read the SAME src1 tensor and none of which feeds another (their src0 are
+ * weights): e.g. the q/k/v projections of a transformer block.  They go down as one batch so that decode-shaped ones
+ * share a launch (b200_mul_mat_batch). */
+static enum ggml_status b200_compute_mul_mat_run(struct b200_backend_context *bc, struct ggml_tensor **nodes, int n) {
+    b200_mul_mat_args args[B200_MAX_RUN];
+    for (int i = 0; i < n; i++)
+        if (!b200_fill_mul_mat_args(nodes[i], &args[i])) return GGML_STATUS_FAILED;
+    const int rc = n == 1 ? b200_mul_mat(bc->ctx, &args[0]) : b200_mul_mat_batch(bc->ctx, args, n);
     if (rc != B200_OK) {
         fprintf(stderr, "ggml-b200: b200_mul_mat failed (%d): %s\n", rc, b200_last_error(bc->ctx));
         return rc == B200_ERR_ALLOC ? GGML_STATUS_ALLOC_FAILED : GGML_STATUS_FAILED;
@@ -386,7 +396,21 @@ GGML_CALL static enum ggml_status b200_backend_graph_compute(ggml_backend_t back
         struct ggml_tensor *node = cgraph->nodes[i];
         if (ggml_is_empty(node) || b200_op_is_noop(node->op)) continue;
         if (node->op == GGML_OP_MUL_MAT) {
-            const enum ggml_status st = b200_compute_mul_mat(bc, node);
+            /* gather the run of consecutive MUL_MAT nodes that share this node's src1 and do not depend on one another */
+            struct ggml_tensor *run[B200_MAX_RUN];
+            int n = 0;
+            run[n++] = node;
+            while (n < B200_MAX_RUN && i + 1 < cgraph->n_nodes) {
+                struct ggml_tensor *next = cgraph->nodes[i + 1];
+                if (next->op != GGML_OP_MUL_MAT || next->src[1] != node->src[1] || ggml_is_empty(next)) break;
+                bool dep = false;
+                for (int j = 0; j < n; j++)
+                    if (next->src[0] == run[j] || next->src[0]->view_src == run[j]) dep = true;
+                if (dep) break;
+                run[n++] = next;
+                i++;
+            }
+            const enum ggml_status st = b200_compute_mul_mat_run(bc, run, n);
             if (st != GGML_STATUS_SUCCESS) return st;
             continue;
         }

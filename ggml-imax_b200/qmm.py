@@ -94,6 +94,7 @@ _SIGNATURES = {
     "b200_quantize_q8_0": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_size_t, C.c_void_p, C.c_void_p]),
     "b200_quantize_q8_0_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_size_t, C.c_void_p]),
     "b200_mul_mat": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs)]),
+    "b200_mul_mat_batch": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs), C.c_int]),
     "b200_mul_mat_gather": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs), C.POINTER(Gather)]),
     "b200_gather_finish": (C.c_int, [C.c_void_p, C.POINTER(Gather), C.c_void_p, C.c_void_p, C.c_int64]),
     "b200_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -349,6 +350,24 @@ class Context:
 
     def gather_finish(self, gather: "Gather", ll_src_ptr: int, dense_out_ptr: int, count: int):
         self._check(self.lib.b200_gather_finish(self.h, C.byref(gather), C.c_void_p(ll_src_ptr), C.c_void_p(dense_out_ptr), count))
+
+    def make_args(self, w: QTensor, x_ptr: int, n: int, dst_ptr: int, m: int | None = None) -> MulMatArgs:
+        a = MulMatArgs()
+        a.type = w.type
+        a.src0_dev = w.ptr
+        a.src0_nblocks_total = w.nblocks
+        a.ne00, a.ne01, a.ne02, a.ne03 = w.k, (w.m if m is None else m), w.ne02, w.ne03
+        a.src1_dev = x_ptr
+        a.ne11, a.ne12, a.ne13 = n, 1, 1
+        a.nb11 = w.k * 4
+        a.nb12 = a.nb13 = a.nb11 * n
+        a.dst_dev = dst_ptr
+        return a
+
+    def mul_mat_batch(self, args_list):
+        """independent mul_mats in one call (b200_mul_mat_batch); same-input decode entries share a launch"""
+        arr = (MulMatArgs * len(args_list))(*args_list)
+        self._check(self.lib.b200_mul_mat_batch(self.h, arr, len(args_list)))
 
     def mul_mat(self, w: QTensor, x: np.ndarray, flags: int = 0) -> np.ndarray:
         """x: [ne13, ne12, n, k] (or [n, k]) float32 host.  Returns dst [ne13, ne12, n, m] float32 (ggml dst[m,n,ne12,ne13])."""

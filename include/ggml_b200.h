@@ -159,6 +159,11 @@ typedef struct b200_mul_mat_args {
 #define B200_MM_FORCE_GEMM  2   /* use the tcgen05 GEMM for any n */
 
 B200_API int b200_mul_mat(b200_ctx *ctx, const b200_mul_mat_args *args);
+/* `count` mul_mats with NO data dependencies among them (e.g. the q/k/v/fc_in projections of a GPT-J block, which all
+ * read the same normalised activations: examples/gpt-j/main.cpp:462-467, :535-538).  Decode-shaped entries that share
+ * type, k and src1 are streamed by ONE launch (one activation quantization, the grid divided among the matrices);
+ * everything else falls back to b200_mul_mat one by one.  Same result as `count` separate calls. */
+B200_API int b200_mul_mat_batch(b200_ctx *ctx, const b200_mul_mat_args *args, int count);
 
 /* ---- row-split decode across GPUs: GEMV fused with its all-gather -----------------------------------
  * Replaces the reference's multi-device mul_mat (split buffer + peer memcpys to a main GPU,

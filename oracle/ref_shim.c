@@ -168,3 +168,35 @@ void ref_chain_free(ref_chain *h) {
     free(h->w);
     free(h);
 }
+
+/*
+ * A DAG of MUL_MAT nodes in ONE ggml graph on the reference CPU backend (one ggml_backend_graph_compute per token, the
+ * way examples/gpt-j/main.cpp:593 evaluates its graph): node i = W[node_w[i]] x (node_src[i] < 0 ? x : node[node_src[i]]).
+ * Every node is expanded into the graph (q and k of a block have no consumer among the mul_mats but are computed, as in the
+ * model); the result read back is the last node.  x: F32 [wk[node_w[first node reading x]], n].
+ */
+ref_chain *ref_dag_create(int type, int n_nodes, const int *node_w, const int *node_src, int n_weights, const int64_t *wk,
+                          const int64_t *wm, int64_t n, int n_threads) {
+    ref_init();
+    ref_chain *h = (ref_chain *)calloc(1, sizeof(ref_chain));
+    struct ggml_init_params ip = { ggml_tensor_overhead() * (size_t)(n_nodes + n_weights + 8) + ggml_graph_overhead_custom(n_nodes + n_weights + 64, false), NULL, true };
+    h->ctx = ggml_init(ip);
+    h->n_weights = n_weights;
+    h->w = (struct ggml_tensor **)calloc((size_t)n_weights, sizeof(*h->w));
+    for (int j = 0; j < n_weights; j++) h->w[j] = ggml_new_tensor_2d(h->ctx, (enum ggml_type)type, wk[j], wm[j]);
+    int64_t kx = 0;
+    for (int i = 0; i < n_nodes; i++) if (node_src[i] < 0) { kx = wk[node_w[i]]; break; }
+    h->x = ggml_new_tensor_2d(h->ctx, GGML_TYPE_F32, kx, n);
+    struct ggml_tensor **nodes = (struct ggml_tensor **)calloc((size_t)n_nodes, sizeof(*nodes));
+    h->gf = ggml_new_graph_custom(h->ctx, (size_t)(n_nodes + n_weights + 64), false);
+    for (int i = 0; i < n_nodes; i++) {
+        nodes[i] = ggml_mul_mat(h->ctx, h->w[node_w[i]], node_src[i] < 0 ? h->x : nodes[node_src[i]]);
+        ggml_build_forward_expand(h->gf, nodes[i]);
+    }
+    h->out = nodes[n_nodes - 1];
+    free(nodes);
+    h->backend = ggml_backend_cpu_init();
+    ggml_backend_cpu_set_n_threads(h->backend, n_threads);
+    h->buf = ggml_backend_alloc_ctx_tensors(h->ctx, h->backend);
+    return h;
+}

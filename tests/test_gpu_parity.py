@@ -214,6 +214,37 @@ def test_mul_mat_row_range_view(gpu_ctx, qmm, oracle, qtype):
         b.free()
 
 
+@pytest.mark.parametrize("qtype", [Q4_0, Q8_0])
+@pytest.mark.parametrize("k,ms", [(4096, [4096, 4096, 4096, 16384]), (768, [2304, 3072]), (1024, [5, 300, 1]), (256, [148, 149, 147, 2000])])
+def test_mul_mat_batch_same_input(gpu_ctx, qmm, oracle, qtype, k, ms):
+    """b200_mul_mat_batch: independent decode mul_mats on the same src1 in one launch == the separate calls, bit for bit."""
+    rng = np.random.default_rng(k + len(ms))
+    x = rng.uniform(-1, 1, (1, k)).astype(np.float32)
+    xd = gpu_ctx.to_device(x)
+    ws, outs, refs = [], [], []
+    for i, m in enumerate(ms):
+        t, wire = make_w(oracle, qmm, gpu_ctx, qtype, m, k, seed=100 + i)
+        ws.append(t)
+        outs.append(gpu_ctx.alloc(m * 4))
+        refs.append(gpu_ctx.mul_mat(t, x)[0])
+    gpu_ctx.mul_mat_batch([gpu_ctx.make_args(t, xd.ptr, 1, o.ptr) for t, o in zip(ws, outs)])
+    gpu_ctx.synchronize()
+    for m, o, ref in zip(ms, outs, refs):
+        got = o.download(np.float32, m)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # a mixed batch (different k / n > 1 entries) silently falls back to one launch per entry
+    t2, wire2 = make_w(oracle, qmm, gpu_ctx, qtype, 64, 512, seed=7)
+    x2 = rng.uniform(-1, 1, (3, 512)).astype(np.float32)
+    x2d = gpu_ctx.to_device(x2)
+    o2 = gpu_ctx.alloc(3 * 64 * 4)
+    gpu_ctx.mul_mat_batch([gpu_ctx.make_args(ws[0], xd.ptr, 1, outs[0].ptr), gpu_ctx.make_args(t2, x2d.ptr, 3, o2.ptr)])
+    gpu_ctx.synchronize()
+    ref2 = oracle.mul_mat(qtype, wire2, 512, 64, 1, 1, x2[None, None])[0, 0]
+    assert nmse(o2.download(np.float32, 3 * 64).reshape(3, 64), ref2) <= 1e-9
+    for b in ws + outs + [xd, t2, x2d, o2]:
+        b.free()
+
+
 def test_mul_mat_errors(gpu_ctx, qmm):
     """Same rejections as the reference's asserts; reported as error codes, never a silent fallback."""
     t = qmm.QTensor(gpu_ctx, Q4_0, 64, 4)
