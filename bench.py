@@ -3,15 +3,18 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-Workload (config.workload): GPT-J-6B-shaped Q4_0 decode -- the chain of the 169 quantized mul_mats one token
-runs through (28 layers x {q,k,v,o: 4096x4096, fc_in: 16384x4096, fc_out: 4096x16384} + lm_head 50400x4096),
-random-init weights made directly in the Q4_0 wire format, 3.287 GB of weights per token (inputs larger than
-L2, no flush needed).  A "step" = one token through the chain.  metric = tokens/s (BASELINE.json: "GPT-J-6B
-Q4_0 tok/s at 1/2/4/8 B200"); at N > 1 every weight matrix is row-split across the ranks and the dst slices
-are re-assembled with an NCCL all-gather (torch.distributed), total work fixed -> "scaling": "strong".
-At N = 1 the same JSON line also carries the other two parts of BASELINE.json's metric under "extra":
-the C1 decode GEMV (m=k=4096, n=1) in GB/s and the C2 prefill GEMM (m=11008, k=4096, n=512; q4_0 and q8_0)
-in int8 TOPS, each with its own roofline fraction.
+Workload (config.workload): the quantized mul_mats of one GPT-J-6B Q4_0 decode token, as a graph with the model's own
+dependencies (examples/gpt-j/main.cpp:462-551): per block q, k, v and fc_in read the block input, o reads the attention
+output (stand-in: v), fc_out reads fc_in; 28 blocks + lm_head 50400x4096 = 169 mul_mats, 3.287 GB of Q4_0 weights per
+token (inputs larger than L2, no flush needed), random-init weights made directly in the wire format.  A "step" = one
+token.  metric = tokens/s (BASELINE.json: "GPT-J-6B Q4_0 tok/s at 1/2/4/8 B200").
+  N = 1: the four same-input projections of a block go down as ONE launch (b200_mul_mat_batch), every launch has the
+         activation quantization fused in: 85 launches per token, replayed as one CUDA graph.
+  N > 1: every weight matrix is row-split across the ranks (total work fixed -> "scaling": "strong"); the dst slices
+         are exchanged by the GEMV epilogue itself (tagged 8-byte peer stores over NVLink, b200_mul_mat_gather) and checked
+         bit for bit against the NCCL all-gather path (--gather nccl selects that one).
+At N = 1 the same JSON line also carries the other two parts of BASELINE.json's metric under "extra": the C1 decode GEMV
+(m=k=4096, n=1) in GB/s and the C2 prefill GEMM (m=11008, k=4096, n=512; q4_0 and q8_0) in int8 TOPS.
 
 value  : device-timed (CUDA events on the launch stream), inputs resident in HBM.
 e2e    : same metric through the C ABI with HOST buffers: per token a pinned-host -> device copy of the input
@@ -19,7 +22,8 @@ e2e    : same metric through the C ABI with HOST buffers: per token a pinned-hos
 roofline: dominant kernel = the decode GEMV (HBM-bound).  achieved = algorithmic bytes per launch / average launch
          duration (all launches of a step are that kernel; bytes = m*(k/32)*18 + k*4 + m*4 per mul_mat).
 cpu_baseline / --impl reference: the reference's own CPU path (oracle/_ref/libref_shim.so = unmodified ggml CPU
-         backend, one graph per token, all host threads) or, when that prebuilt file is absent, the oracle port.
+         backend, the same 169-node graph as ONE ggml graph per token, all host threads) or, when that prebuilt file is
+         absent, the oracle port.
 """
 import argparse
 import ctypes as C
@@ -160,6 +164,9 @@ def run_b200(args):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx = qmm.Context(local_rank, stream=stream.cuda_stream)   # our launches go to torch's stream: plumbing only
+    # a second stream/context: independent nodes of the graph (o and fc_out of a block) run concurrently, fork/join by events
+    side = torch.cuda.Stream(device=dev)
+    ctx2 = qmm.Context(local_rank, stream=side.cuda_stream)
     P = peaks()
 
     # ---- weights: random-init in wire format, one host copy per distinct shape, row-split, set_tensor (repack) per matrix
@@ -210,13 +217,23 @@ def run_b200(args):
         groups.append(list(range(i, j)))
         i = j
 
-    def token_step():
+    def token_step(overlap=True):
         """one token: the 169 mul_mats of the GPT-J decode graph.  N == 1: 85 launches (same-input projections batched,
         quantize fused into every GEMV); N > 1 on this (NCCL) path: one launch + one all-gather per mul_mat"""
         base = act.data_ptr()
         if world == 1:
             for grp in groups:
-                ctx.mul_mat_batch([ctx.make_args(weights[i][0], node_src_ptr(i, base, 4), 1, base + node_off(i) * 4) for i in grp])
+                i0 = grp[0]
+                argv = [ctx.make_args(weights[i][0], node_src_ptr(i, base, 4), 1, base + node_off(i) * 4) for i in grp]
+                if dag[i0][0] == "o" and overlap and not args.no_overlap:
+                    # o reads v, fc_out (the next group) reads fc_in: independent -> o goes to the side stream
+                    side.wait_stream(stream)
+                    ctx2.mul_mat_batch(argv)
+                elif dag[i0][0] == "fc_out" and overlap and not args.no_overlap:
+                    ctx.mul_mat_batch(argv)
+                    stream.wait_stream(side)      # join before the next block reads anything
+                else:
+                    ctx.mul_mat_batch(argv)
         else:
             for i, (t, split, k) in enumerate(weights):
                 o = node_off(i)
@@ -333,12 +350,21 @@ def run_b200(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
+    # the timed path (graph replay, batched launches, two streams) must reproduce the plain one-stream eager walk bit for bit
+    plain_check = None
+    if world == 1:
+        torch.cuda.synchronize()
+        got = act[lm_off:lm_off + N_VOCAB].clone()
+        token_step(overlap=False)
+        torch.cuda.synchronize()
+        plain_check = bool(torch.equal(got, act[lm_off:lm_off + N_VOCAB]))
+        step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = ctx.launch_count()
+    l0 = ctx.launch_count() + ctx2.launch_count()
     ms_total = timed(step, args.steps)
-    eager_launches = ctx.launch_count() - l0
+    eager_launches = ctx.launch_count() + ctx2.launch_count() - l0
     ms_per_step = ms_total / args.steps
     tok_s = 1000.0 / ms_per_step
 
@@ -396,7 +422,8 @@ def run_b200(args):
             "data": "synthetic (random-init Q4_0 blocks, U(-1,1) activations, seed 1234)",
             "config": {"workload": WORKLOAD, "l2": "inputs larger than L2 (3.29 GB of weights per step)", "cuda_graph": graph is not None,
                        "parallelism": (f"row-split x{world} + " + ("all-gather fused into the GEMV epilogue (NVLink peer stores + flags)" if fused is not None else "NCCL all-gather")) if world > 1 else "single GPU",
-                       "gather_check_vs_nccl": gather_check,
+                       "gather_check_vs_nccl": gather_check, "graph_vs_plain_walk_bitwise": plain_check,
+                       "streams": 2 if (world == 1 and not args.no_overlap) else 1,
                        "weights_bytes_per_token": sum(m * (k // 32) * 18 for _, m, k in mats)},
             "e2e": {"value": round(1000.0 / ms_e2e, 2), "unit": "tokens/s", "h2d_bytes_per_step": N_EMBD * 4, "d2h_bytes_per_step": N_VOCAB * 4,
                     "ms_per_step": round(ms_e2e, 4), "logits_finite": logits_ok},
@@ -651,6 +678,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a captured CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N = 1: keep o and fc_out of a block on one stream")
     ap.add_argument("--no-extras", action="store_true", help="skip the C1/C2 sub-benchmarks (A/B runs)")
     ap.add_argument("--trace", action="store_true", help="dump a device-side timeline of the first launches of a step to stderr")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N > 1: how dst slices are re-assembled")
