@@ -280,13 +280,21 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
 #pragma unroll
     for (int j = 1; j < kMaxBatch; j++)
         if (j < sb.count && (int)blockIdx.x >= sb.sub[j].cta0) si = j;
-    const uint8_t *const m_qs = sb.sub[si].qs;
-    const __half *const m_d = sb.sub[si].d;
-    float *const m_dst = sb.sub[si].dst;
-    const int64_t m_rows = sb.sub[si].m;
-    const int bx = (int)blockIdx.x - sb.sub[si].cta0;
-    const int64_t r_begin = (int64_t)bx * sb.sub[si].rows_q + min(bx, sb.sub[si].rows_rem);
-    const int nrows = sb.sub[si].rows_q + (bx < sb.sub[si].rows_rem ? 1 : 0);
+    // (selected with compile-time indices: a runtime index into kernel parameters would force a local-memory copy)
+    const uint8_t *m_qs = sb.sub[0].qs;
+    const __half *m_d = sb.sub[0].d;
+    float *m_dst = sb.sub[0].dst;
+    int m_rows32 = sb.sub[0].m, m_cta0 = sb.sub[0].cta0, m_rows_q = sb.sub[0].rows_q, m_rows_rem = sb.sub[0].rows_rem;
+#pragma unroll
+    for (int j = 1; j < kMaxBatch; j++)
+        if (j == si) {
+            m_qs = sb.sub[j].qs; m_d = sb.sub[j].d; m_dst = sb.sub[j].dst;
+            m_rows32 = sb.sub[j].m; m_cta0 = sb.sub[j].cta0; m_rows_q = sb.sub[j].rows_q; m_rows_rem = sb.sub[j].rows_rem;
+        }
+    const int64_t m_rows = m_rows32;
+    const int bx = (int)blockIdx.x - m_cta0;
+    const int64_t r_begin = (int64_t)bx * m_rows_q + min(bx, m_rows_rem);
+    const int nrows = m_rows_q + (bx < m_rows_rem ? 1 : 0);
     int nstage_iters = 0;
     for (int r = 0; r < nrows; r += g.rs) nstage_iters++;   // ceil(nrows / rs) without a division (a handful of iterations)
     // which (row-in-pass, k-segment) this warp serves -- all shifts, computed before the dependency wait
@@ -351,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
     // division per 16 elements, and the lane's 16 int8 are exactly one 16-byte store into the lo/hi plane.
     // All loads of a batch are issued before any use (one L2 round trip per 8192 elements per CTA).
     {
-        constexpr int kQB = 2;
+        constexpr int kQB = 4;   // 4 lane-tasks (64 floats) in flight per thread: k = 16384 is one L2 round trip, not two
         const int tpc = nb * 2;   // lane-tasks per column; even, and a lane's partner (lane ^ 1) shares its block
 #pragma unroll 1
         for (int c = 0; c < NCOLS; c++) {
@@ -370,6 +378,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
 #pragma unroll
                 for (int u = 0; u < kQB; u++) {
                     const int t = min(base + u * kConsumerThreads + (int)threadIdx.x, tpc - 1);
+                    if (base + u * kConsumerThreads + warp * 32 >= tpc) continue;   // whole warp past the end: nothing to load
                     if (ll_in) {
                         // src1 is the LL vector the previous launch scattered to every rank: 8 bytes per element
                         const int tb = base + u * kConsumerThreads + warp * 32;   // first lane-task of this warp
@@ -386,6 +395,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
                 if (ll_in && threadIdx.x == 0 && base == 0) stamp(p.trace, 6);
 #pragma unroll
                 for (int u = 0; u < kQB; u++) {
+                    if (base + u * kConsumerThreads + warp * 32 >= tpc) continue;   // (warp-uniform, so the shuffles below stay full)
                     const int tt = base + u * kConsumerThreads + (int)threadIdx.x;
                     const bool live = tt < tpc;
                     const int t = live ? tt : tpc - 1;
@@ -567,7 +577,9 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
                     if (G == 1) {
                         if (gd.world > 1) {
                             // fused all-gather, producer side: the element goes to every rank's full vector (NVLink stores)
-                            for (int r = 0; r < gd.world; r++) ll_store(gd.peer_dst[r], gd.row0 + r_begin + gr, v, gd_tag);
+#pragma unroll
+                            for (int r = 0; r < B200_MAX_RANKS; r++)
+                                if (r < gd.world) ll_store(gd.peer_dst[r], gd.row0 + r_begin + gr, v, gd_tag);
                         } else {
                             m_dst[(int64_t)c * m_rows + r_begin + gr] = v;
                         }
@@ -587,7 +599,9 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
                     float v = 0.0f;
                     for (int sg = 0; sg < G; sg++) v += part[((cpar * g.pr + r) * kConsumerWarps + sg) * NCOLS + c];
                     if (gd.world > 1) {
-                        for (int pr = 0; pr < gd.world; pr++) ll_store(gd.peer_dst[pr], gd.row0 + r_begin + chunk_row0 + r, v, gd_tag);
+#pragma unroll
+                        for (int pr = 0; pr < B200_MAX_RANKS; pr++)
+                            if (pr < gd.world) ll_store(gd.peer_dst[pr], gd.row0 + r_begin + chunk_row0 + r, v, gd_tag);
                     } else {
                         m_dst[(int64_t)c * m_rows + r_begin + chunk_row0 + r] = v;
                     }
