@@ -398,7 +398,7 @@ def run_b200(args):
     bytes_rank = sum(algorithmic_bytes(sp.rows, k, 1, 18) for (_, sp, k) in weights if sp.rows > 0)
     launch_us = ms_per_step * 1e3 / launches_per_step
     achieved = bytes_rank / launches_per_step / (launch_us * 1e-6) / 1e9
-    roofline = {"bound": "hbm", "kernel": "gemv_kernel<Q4_0,1> (fused quantize_row_q8_0 + dp4a GEMV)", "achieved": round(achieved, 1),
+    roofline = {"bound": "hbm", "kernel": "gemv_stream_kernel<Q4_0,1> (fused quantize_row_q8_0 + dp4a GEMV, bulk-copy ring)", "achieved": round(achieved, 1),
                 "peak": P["hbm_gbs"], "unit": "GB/s", "frac": round(achieved / P["hbm_gbs"], 4), "traffic": None,
                 "peak_source": P["source"], "launch_us": round(launch_us, 3),
                 "note": "per rank; at N>1 the step time includes the exchange of the dst slices"}
@@ -673,7 +673,7 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a captured CUDA graph")
