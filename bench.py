@@ -246,7 +246,7 @@ def run_b200(args):
     # ---- fused path (N > 1): GEMV epilogue stores into every rank's activation vector over NVLink, tags instead of a collective
     fused = None
     out_ptr_fused = None
-    if world > 1 and args.gather == "fused":
+    if (world > 1 and args.gather == "fused") or (world == 1 and not args.no_extras):
         try:
             n_slots = len(weights) + 1
             abuf = ctx.alloc(total_len * 8)                                  # LL activation vectors: {fp32, tag} per element
@@ -254,10 +254,13 @@ def run_b200(args):
             dense = ctx.alloc(N_VOCAB * 4)
             for b in (abuf, state, dense):
                 ctx._check(ctx.lib.b200_memset(ctx.h, b.ptr, 0, b.nbytes))
-            allh = [None] * world
-            dist.all_gather_object(allh, ctx.ipc_export(abuf.ptr))
-            peers = [abuf.ptr if r == rank else ctx.ipc_import(allh[r]) for r in range(world)]
-            dist.barrier()
+            if world > 1:
+                allh = [None] * world
+                dist.all_gather_object(allh, ctx.ipc_export(abuf.ptr))
+                peers = [abuf.ptr if r == rank else ctx.ipc_import(allh[r]) for r in range(world)]
+                dist.barrier()
+            else:
+                peers = [abuf.ptr]
             gathers = []
             for i, (t, split, k) in enumerate(weights):
                 g = qmm.Gather()
@@ -273,8 +276,8 @@ def run_b200(args):
             gw.state = state.ptr
 
             def token_step_fused():
-                for i, (t, split, k) in enumerate(weights):
-                    ctx.mul_mat_gather(t, node_src_ptr(i, abuf.ptr, 8), gathers[i], m=split.rows)
+                for grp in groups:      # same-input slices (q, k, v, fc_in) share one launch here too
+                    ctx.mul_mat_gather_batch([(weights[i][0], node_src_ptr(i, abuf.ptr, 8), gathers[i], weights[i][1].rows) for i in grp])
                 ctx.gather_finish(gw, abuf.ptr + lm_off * 8, dense.ptr, N_VOCAB)      # logits complete on this rank, as plain fp32
                 return dense.ptr
             fused = token_step_fused
@@ -283,7 +286,6 @@ def run_b200(args):
             print(f"[bench] fused all-gather unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
             fused = None
 
-    launches_per_step = len(groups) if world == 1 else sum(1 for w in weights if w[1].rows > 0)
     # ---- capture the step once (our kernels + NCCL) into a CUDA graph: decode is launch-bound otherwise
     use_graph = not args.no_graph
     graph = None
@@ -291,8 +293,9 @@ def run_b200(args):
     torch.cuda.synchronize()
     gather_check = None
     step_fn = token_step
+    ll_chain_fn = None          # N = 1: the tagged-activation chain, reported under "extra" only
     if fused is not None:
-        # same arithmetic, same row partition -> the fused path must reproduce the NCCL path bit for bit
+        # same arithmetic, same row partition -> the fused path must reproduce the dense / NCCL path bit for bit
         ref_logits = out_t.clone()
         fused()
         torch.cuda.synchronize()
@@ -300,13 +303,17 @@ def run_b200(args):
         ctx._check(ctx.lib.b200_download(ctx.h, got.ctypes.data, out_ptr_fused, N_VOCAB * 4))
         ok = bool(np.array_equal(got, ref_logits.cpu().numpy()))
         okt = torch.tensor([1 if ok else 0], device=dev)
-        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if world > 1:
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         gather_check = bool(okt.item())
-        if gather_check:
+        if not gather_check:
+            print("[bench] fused (tagged-activation) path differs from the dense path; not using it", file=sys.stderr)
+            fused = None
+        elif world > 1:
             step_fn = fused
         else:
-            print("[bench] fused all-gather result differs from the NCCL path; using NCCL", file=sys.stderr)
-            fused = None
+            ll_chain_fn, fused = fused, None      # N = 1 headline stays on the dense drop-in path
+    launches_per_step = len(groups) if (world == 1 or fused is not None) else sum(1 for w in weights if w[1].rows > 0)
     trace_buf = None
     if args.trace:
         trace_buf = ctx.alloc(launches_per_step * 160 * 8 * 8)
@@ -406,6 +413,21 @@ def run_b200(args):
     extra = {}
     if world == 1 and not args.no_extras:
         extra = run_extras(torch, qmm, ctx, stream, P, args)
+        if ll_chain_fn is not None:
+            # the same graph with activations handed from launch to launch as tagged 8-byte elements (the mechanism the
+            # multi-GPU path uses, here with a single rank): no grid-completion wait between dependent launches
+            try:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, stream=stream):
+                    ll_chain_fn()
+                for _ in range(3):
+                    g2.replay()
+                ms_ll = timed(g2.replay, args.steps) / args.steps
+                extra["n1_tagged_activation_chain"] = {"tokens/s": round(1000.0 / ms_ll, 2), "ms_per_step": round(ms_ll, 4),
+                                                       "bitwise_equal_to_dense_path": gather_check,
+                                                       "note": "b200_mul_mat_gather_batch with world = 1; the N > 1 lines use this mechanism"}
+            except Exception as e:
+                extra["n1_tagged_activation_chain"] = {"error": f"{type(e).__name__}: {e}"}
         tr = ROOT / "profiles" / "traffic.json"
         if tr.exists():
             try:
@@ -673,7 +695,7 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a captured CUDA graph")

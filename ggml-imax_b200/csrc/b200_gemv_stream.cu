@@ -94,6 +94,11 @@ struct StreamBatch {
         int m;
         int cta0;              // first CTA of this matrix
         int rows_q, rows_rem;  // CTA c (relative) owns rows [c*rows_q + min(c, rows_rem), +rows_q + (c < rows_rem))
+        // fused all-gather only: where this matrix's LL vector sits relative to gather.peer_dst[r], its first global row,
+        // its launch slot (tag + execution count) and how many CTAs serve it
+        long long ll_off;
+        long long row0;
+        int slot, ctas;
     } sub[kMaxBatch];
 };
 
@@ -285,11 +290,14 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
     const __half *m_d = sb.sub[0].d;
     float *m_dst = sb.sub[0].dst;
     int m_rows32 = sb.sub[0].m, m_cta0 = sb.sub[0].cta0, m_rows_q = sb.sub[0].rows_q, m_rows_rem = sb.sub[0].rows_rem;
+    long long m_ll0 = sb.sub[0].ll_off + sb.sub[0].row0;
+    int m_slot = sb.sub[0].slot, m_ctas = sb.sub[0].ctas;
 #pragma unroll
     for (int j = 1; j < kMaxBatch; j++)
         if (j == si) {
             m_qs = sb.sub[j].qs; m_d = sb.sub[j].d; m_dst = sb.sub[j].dst;
             m_rows32 = sb.sub[j].m; m_cta0 = sb.sub[j].cta0; m_rows_q = sb.sub[j].rows_q; m_rows_rem = sb.sub[j].rows_rem;
+            m_ll0 = sb.sub[j].ll_off + sb.sub[j].row0; m_slot = sb.sub[j].slot; m_ctas = sb.sub[j].ctas;
         }
     const int64_t m_rows = m_rows32;
     const int bx = (int)blockIdx.x - m_cta0;
@@ -339,20 +347,20 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
     // activations (and dst, for write-after-read) belong to the previous grid until here -- except in the fused
     // all-gather chain, where src1 arrives as tagged LL elements: the tags ARE the dependency (a matching tag proves the
     // producing CTA, local or remote, is past its own input reads), so the kernel does not wait for grid completion at all
-    if (!(gd.world > 1 && gd.wait_slot >= 0)) pdl_wait();
+    if (!(gd.world > 0 && gd.wait_slot >= 0)) pdl_wait();
     if (threadIdx.x == 0) stamp(p.trace, 2);
     // fused all-gather: tags are (execution count + 1) << 10 | producing slot -- unique per (launch, replay), so a stale
     // element of the ping-pong buffer (written by slot - 2 in the same replay) can never be mistaken for the new one.
     // Every slot runs once per sequence, so this launch's own execution count is also its producer's.
     uint32_t gd_tag = 0, gd_src_tag = 0;
-    if (gd.world > 1) {
+    if (gd.world > 0) {
         uint32_t *s_tag = reinterpret_cast<uint32_t *>(empty_bar + kMaxStages);
-        if (threadIdx.x == 0) *s_tag = gd.state[2 * (size_t)gd.slot + 1] + 1u;
+        if (threadIdx.x == 0) *s_tag = gd.state[2 * (size_t)m_slot + 1] + 1u;
         consumer_bar_sync();
-        gd_tag = (*s_tag << 10) | (uint32_t)gd.slot;
+        gd_tag = (*s_tag << 10) | (uint32_t)m_slot;
         gd_src_tag = (*s_tag << 10) | (uint32_t)(gd.wait_slot & 1023);
     }
-    const bool ll_in = gd.world > 1 && gd.wait_slot >= 0;
+    const bool ll_in = gd.world > 0 && gd.wait_slot >= 0;
 
     // ---- quantize the activation columns into shared memory: quantize_row_q8_0, bit-exact ----
     // Two lanes per block, 16 consecutive floats (4 x 128-bit loads) per lane: one amax shuffle, ONE 127/amax
@@ -575,11 +583,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
                 const int c = lane % NCOLS;
                 if (lv) {
                     if (G == 1) {
-                        if (gd.world > 1) {
+                        if (gd.world > 0) {
                             // fused all-gather, producer side: the element goes to every rank's full vector (NVLink stores)
 #pragma unroll
                             for (int r = 0; r < B200_MAX_RANKS; r++)
-                                if (r < gd.world) ll_store(gd.peer_dst[r], gd.row0 + r_begin + gr, v, gd_tag);
+                                if (r < gd.world) ll_store(gd.peer_dst[r], m_ll0 + r_begin + gr, v, gd_tag);
                         } else {
                             m_dst[(int64_t)c * m_rows + r_begin + gr] = v;
                         }
@@ -598,10 +606,10 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
                     const int r = t / NCOLS, c = t - r * NCOLS;
                     float v = 0.0f;
                     for (int sg = 0; sg < G; sg++) v += part[((cpar * g.pr + r) * kConsumerWarps + sg) * NCOLS + c];
-                    if (gd.world > 1) {
+                    if (gd.world > 0) {
 #pragma unroll
                         for (int pr = 0; pr < B200_MAX_RANKS; pr++)
-                            if (pr < gd.world) ll_store(gd.peer_dst[pr], gd.row0 + r_begin + chunk_row0 + r, v, gd_tag);
+                            if (pr < gd.world) ll_store(gd.peer_dst[pr], m_ll0 + r_begin + chunk_row0 + r, v, gd_tag);
                     } else {
                         m_dst[(int64_t)c * m_rows + r_begin + chunk_row0 + r] = v;
                     }
@@ -613,13 +621,13 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
         }
     }
     if (threadIdx.x == 0) stamp(p.trace, 5);
-    if (gd.world > 1) {
+    if (gd.world > 0) {
         // bookkeeping only (device-scope): the last CTA of the grid bumps the slot's execution count
         consumer_bar_sync();
         if (threadIdx.x == 0) {
-            uint32_t *st = gd.state + 2 * (size_t)gd.slot;
+            uint32_t *st = gd.state + 2 * (size_t)m_slot;
             const uint32_t arrived = atomicAdd(st, 1u);
-            if (arrived == gridDim.x - 1) {
+            if (arrived == (uint32_t)m_ctas - 1u) {
                 st[0] = 0;
                 st[1] = gd_tag >> 10;
             }
@@ -692,6 +700,10 @@ int launch_stream_typed(b200_ctx *ctx, const b200_gemv_params &p, const StreamGe
         sb.sub[0].cta0 = 0;
         sb.sub[0].rows_q = (int)(p.m / ctas);
         sb.sub[0].rows_rem = (int)(p.m % ctas);
+        sb.sub[0].ll_off = 0;
+        sb.sub[0].row0 = p.gather ? p.gather->row0 : 0;
+        sb.sub[0].slot = p.gather ? p.gather->slot : 0;
+        sb.sub[0].ctas = (int)ctas;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -755,6 +767,13 @@ void build_batch(const b200_ctx *ctx, const b200_gemv_params *ps, int count, Str
         sb->sub[j].cta0 = cta0;
         sb->sub[j].rows_q = (int)(ps[j].m / share[j]);
         sb->sub[j].rows_rem = (int)(ps[j].m % share[j]);
+        sb->sub[j].ctas = share[j];
+        if (ps[j].gather) {
+            const b200_gather *g0 = ps[0].gather, *gj = ps[j].gather;
+            sb->sub[j].ll_off = ((const char *)gj->peer_dst[gj->rank] - (const char *)g0->peer_dst[g0->rank]) / 8;
+            sb->sub[j].row0 = gj->row0;
+            sb->sub[j].slot = gj->slot;
+        }
         cta0 += share[j];
     }
     sb->total_ctas = cta0;
@@ -790,7 +809,18 @@ bool b200_try_launch_gemv_stream_batch(b200_ctx *ctx, const b200_gemv_params *ps
     if (count < 2 || count > kMaxBatch) return false;
     for (int j = 0; j < count; j++) {
         const b200_gemv_params &p = ps[j];
-        if (p.n != 1 || p.dst_n != 1 || p.dots || p.gather) return false;
+        if (p.n != 1 || p.dst_n != 1 || p.dots) return false;
+        if ((p.gather != NULL) != (ps[0].gather != NULL)) return false;
+        if (p.gather) {
+            // one gather description must fit all: same group, same state, same producer to wait for, and the matrices' LL
+            // vectors at the same relative offset on every rank (symmetric buffers)
+            const b200_gather *g0 = ps[0].gather, *gj = p.gather;
+            if (gj->world != g0->world || gj->rank != g0->rank || gj->state != g0->state || gj->wait_slot != g0->wait_slot) return false;
+            const ptrdiff_t delta = (const char *)gj->peer_dst[gj->rank] - (const char *)g0->peer_dst[g0->rank];
+            if (delta % 8 != 0) return false;
+            for (int r = 0; r < g0->world; r++)
+                if ((const char *)gj->peer_dst[r] - (const char *)g0->peer_dst[r] != delta) return false;
+        }
         if (p.ne12 != 1 || p.ne13 != 1 || p.ne02 != 1 || p.ne03 != 1) return false;
         if (p.k % 256 != 0 || p.k > 32768 || p.m < 1 || p.m >= (1ll << 31)) return false;
         if (((uintptr_t)p.qs & 15) != 0 || ((uintptr_t)p.d & 15) != 0) return false;

@@ -192,6 +192,34 @@ int b200_mul_mat_gather(b200_ctx *ctx, const b200_mul_mat_args *a, const b200_ga
     return rc;
 }
 
+int b200_mul_mat_gather_batch(b200_ctx *ctx, const b200_mul_mat_args *args, const b200_gather *gathers, int count) {
+    B200_REQUIRE(ctx, ctx && args && gathers && count >= 1, B200_ERR_INVALID);
+    int i = 0;
+    while (i < count) {
+        b200_gemv_params ps[4];
+        int run = 0;
+        while (run < 4 && i + run < count && gather_ok(&gathers[i + run]) && decode_params(ctx, &args[i + run], &ps[run]) &&
+               ps[run].k % 256 == 0 && ps[run].type == ps[0].type && ps[run].k == ps[0].k && ps[run].x == ps[0].x) {
+            ps[run].gather = &gathers[i + run];
+            ps[run].dst = NULL;
+            run++;
+        }
+        int rc = B200_OK;
+        if (run >= 2) {
+            B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+            if (b200_try_launch_gemv_stream_batch(ctx, ps, run, &rc)) {
+                if (rc != B200_OK) return rc;
+                i += run;
+                continue;
+            }
+        }
+        rc = b200_mul_mat_gather(ctx, &args[i], &gathers[i]);
+        if (rc != B200_OK) return rc;
+        i++;
+    }
+    return B200_OK;
+}
+
 int b200_gather_finish(b200_ctx *ctx, const b200_gather *g, const void *ll_src_dev, float *dense_out_dev, int64_t count) {
     B200_REQUIRE(ctx, ctx && gather_ok(g) && g->wait_slot >= 0 && ll_src_dev && dense_out_dev && count > 0, B200_ERR_INVALID);
     B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));

@@ -96,6 +96,7 @@ _SIGNATURES = {
     "b200_mul_mat": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs)]),
     "b200_mul_mat_batch": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs), C.c_int]),
     "b200_mul_mat_gather": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs), C.POINTER(Gather)]),
+    "b200_mul_mat_gather_batch": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs), C.POINTER(Gather), C.c_int]),
     "b200_gather_finish": (C.c_int, [C.c_void_p, C.POINTER(Gather), C.c_void_p, C.c_void_p, C.c_int64]),
     "b200_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -347,6 +348,17 @@ class Context:
         a.nb11 = a.nb12 = a.nb13 = w.k * 4
         a.dst_dev = gather.peer_dst[gather.rank]   # unused: results leave as LL elements
         self._check(self.lib.b200_mul_mat_gather(self.h, C.byref(a), C.byref(gather)))
+
+    def mul_mat_gather_batch(self, items):
+        """items: [(QTensor slice, x_ptr, Gather, rows)] -- independent same-input slices, one launch when possible"""
+        args = (MulMatArgs * len(items))()
+        gs = (Gather * len(items))()
+        for j, (w, x_ptr, g, m) in enumerate(items):
+            a = self.make_args(w, x_ptr, 1, g.peer_dst[g.rank], m=m)
+            a.ne02 = a.ne03 = 1
+            args[j] = a
+            gs[j] = g
+        self._check(self.lib.b200_mul_mat_gather_batch(self.h, args, gs, len(items)))
 
     def gather_finish(self, gather: "Gather", ll_src_ptr: int, dense_out_ptr: int, count: int):
         self._check(self.lib.b200_gather_finish(self.h, C.byref(gather), C.c_void_p(ll_src_ptr), C.c_void_p(dense_out_ptr), count))

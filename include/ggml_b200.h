@@ -190,6 +190,9 @@ typedef struct b200_gather {
     uint32_t *state;
 } b200_gather;
 B200_API int b200_mul_mat_gather(b200_ctx *ctx, const b200_mul_mat_args *args, const b200_gather *gather);
+/* b200_mul_mat_batch for the fused path: independent same-input slices share one launch when their gather descriptions
+ * agree (same group, state, wait_slot; LL vectors at the same relative offset on every rank); else one by one */
+B200_API int b200_mul_mat_gather_batch(b200_ctx *ctx, const b200_mul_mat_args *args, const b200_gather *gathers, int count);
 /* end of a sequence: wait for the LL vector ll_src_dev (count elements, produced by gather->wait_slot) to be complete
  * and write it out as plain fp32 (dense_out_dev), e.g. the logits before they are read back */
 B200_API int b200_gather_finish(b200_ctx *ctx, const b200_gather *gather, const void *ll_src_dev, float *dense_out_dev, int64_t count);
