@@ -157,6 +157,8 @@ def run_b200(args):
             sys.exit("--gpus N > 1 must be launched with torch.distributed.run --nproc-per-node N")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.trace:
+        os.environ["B200_PLAN_TRACE"] = "1"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     qmm = load_qmm()
@@ -288,6 +290,49 @@ def run_b200(args):
             print(f"[bench] fused all-gather unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
             fused = None
 
+    # ---- decode plan: the whole token as ONE persistent launch (b200_plan_*), row-split across ranks when N > 1
+    plan = None
+    plan_fn = None
+    plan_out = None
+    if args.path == "plan":
+        try:
+            node_len = [((m + 15) // 16) * 16 for _, m, _ in mats]
+            node_at = np.concatenate([[0], np.cumsum(node_len)]).astype(np.int64)
+            act_plan = torch.zeros(int(node_at[-1]), dtype=torch.float32, device=dev)     # one plain vector per node (no aliasing)
+            pargs = []
+            for i, (t, split, k) in enumerate(weights):
+                src = dag[i][3]
+                sp = x_in.data_ptr() if src < 0 else act_plan.data_ptr() + int(node_at[src]) * 4
+                a = ctx.make_args(t, sp, 1, act_plan.data_ptr() + int(node_at[i]) * 4, m=split.rows)
+                a.ne02 = a.ne03 = 1
+                if i == len(weights) - 1:
+                    a.flags |= qmm.MM_EXPORT
+                pargs.append(a)
+            psplit = None
+            if world > 1:
+                psplit = qmm.PlanSplit()
+                psplit.world, psplit.rank = world, rank
+                row0_arr = (C.c_int64 * len(pargs))(*[w[1].r0 for w in weights])
+                mtot_arr = (C.c_int64 * len(pargs))(*[m for _, m, _ in mats])
+                psplit.row0, psplit.m_total = row0_arr, mtot_arr
+                arena = ctx.alloc(ctx.plan_arena_bytes(pargs, psplit))
+                ctx._check(ctx.lib.b200_memset(ctx.h, arena.ptr, 0, arena.nbytes))
+                allh = [None] * world
+                dist.all_gather_object(allh, ctx.ipc_export(arena.ptr))
+                for r in range(world):
+                    psplit.peer_arena[r] = arena.ptr if r == rank else ctx.ipc_import(allh[r])
+                dist.barrier()
+            plan = ctx.plan_create(pargs, psplit)
+            plan_out = act_plan[int(node_at[len(mats) - 1]):int(node_at[len(mats) - 1]) + N_VOCAB]
+
+            def plan_fn():
+                ctx.plan_launch(plan)
+                return plan_out
+        except Exception as e:
+            print(f"[bench] decode plan unavailable ({type(e).__name__}: {e}); using the launch-per-node path", file=sys.stderr)
+            plan = None
+            plan_fn = None
+
     # ---- capture the step once (our kernels + NCCL) into a CUDA graph: decode is launch-bound otherwise
     use_graph = not args.no_graph
     graph = None
@@ -315,9 +360,33 @@ def run_b200(args):
             step_fn = fused
         else:
             ll_chain_fn, fused = fused, None      # N = 1 headline stays on the dense drop-in path
-    launches_per_step = len(groups) if (world == 1 or fused is not None) else sum(1 for w in weights if w[1].rows > 0)
+    plan_check = None
+    if plan_fn is not None:
+        # the plan computes every mul_mat with the arithmetic of the per-launch kernels: bit-identical logits required
+        torch.cuda.synchronize()
+        ref_logits2 = torch.empty(N_VOCAB, dtype=torch.float32, device=dev)
+        if fused is not None:
+            ctx._check(ctx.lib.b200_copy_d2d(ctx.h, ref_logits2.data_ptr(), out_ptr_fused, N_VOCAB * 4))
+            ctx.synchronize()
+        else:
+            ref_logits2.copy_(out_t[:N_VOCAB])
+        for _ in range(2):
+            plan_fn()
+        torch.cuda.synchronize()
+        okt = torch.tensor([1 if torch.equal(plan_out, ref_logits2) else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        plan_check = bool(okt.item())
+        if not plan_check:
+            print("[bench] decode plan differs from the launch-per-node path; not using it", file=sys.stderr)
+            plan_fn = None
+    other_fn = step_fn             # what the plan replaces (reported under extra at N = 1)
+    if plan_fn is not None:
+        step_fn = plan_fn
+        use_graph = False          # one launch per token: nothing to capture
+    launches_per_step = 1 if plan_fn is not None else (len(groups) if (world == 1 or fused is not None) else sum(1 for w in weights if w[1].rows > 0))
     trace_buf = None
-    if args.trace:
+    if args.trace and plan_fn is None:
         trace_buf = ctx.alloc(launches_per_step * 160 * 8 * 8)
         ctx._check(ctx.lib.b200_memset(ctx.h, trace_buf.ptr, 0, trace_buf.nbytes))
         ctx.set_trace(trace_buf, launches_per_step)
@@ -357,13 +426,15 @@ def run_b200(args):
             ms = float(tt.item())
         return ms
 
+    result_ptr = plan_out.data_ptr() if plan_fn is not None else (out_ptr_fused if fused is not None else out_t.data_ptr())
     for _ in range(max(args.warmup, 3)):
         step()
     # the timed path (graph replay, batched launches, two streams) must reproduce the plain one-stream eager walk bit for bit
     plain_check = None
     if world == 1:
         torch.cuda.synchronize()
-        got = act[lm_off:lm_off + N_VOCAB].clone()
+        got = (plan_out if plan_fn is not None else act[lm_off:lm_off + N_VOCAB]).clone()
+        act[lm_off:lm_off + N_VOCAB].zero_()
         token_step(overlap=False)
         torch.cuda.synchronize()
         plain_check = bool(torch.equal(got, act[lm_off:lm_off + N_VOCAB]))
@@ -381,14 +452,33 @@ def run_b200(args):
     def e2e_step():
         ctx._check(ctx.lib.b200_upload_async(ctx.h, x_in.data_ptr(), x_host.data_ptr(), N_EMBD * 4))
         step()
-        ctx._check(ctx.lib.b200_download_async(ctx.h, logits_host.data_ptr(), out_ptr_fused if fused is not None else out_t.data_ptr(), N_VOCAB * 4))
+        ctx._check(ctx.lib.b200_download_async(ctx.h, logits_host.data_ptr(), result_ptr, N_VOCAB * 4))
         ctx.synchronize()
 
     for _ in range(3):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps) / args.steps
     clocks = sampler.stop() if rank == 0 else None
-    if trace_buf is not None:
+    if args.trace and plan_fn is not None:
+        tr_all = ctx.plan_trace(plan).astype(np.int64)      # [nops + 1, grid, 4]
+        tr, tot = tr_all[:-1], tr_all[-1]
+        print(f"[plan trace r{rank}] per-CTA totals (us, mean/max): producer blocked on a full ring {tot[:, 0].mean() / 1e3:.1f}/{tot[:, 0].max() / 1e3:.1f}; "
+              f"consumer warp blocked on an empty ring {tot[:, 1].mean() / 1e3:.1f}/{tot[:, 1].max() / 1e3:.1f}; "
+              f"quantization phases {tot[:, 2].mean() / 1e3:.1f}/{tot[:, 2].max() / 1e3:.1f}", file=sys.stderr)
+        live = tr[tr > 0]
+        t0 = live.min() if live.size else 0
+        names = ["src1 complete", "quantized", "first weights", "last row"]
+        print(f"[plan trace r{rank}] whole launch: {(live.max() - t0) / 1e3:.1f} us   (ns since the first stamp, min..max over CTAs)", file=sys.stderr)
+        print(f"[plan trace r{rank}]  op name      " + " ".join(f"{n:>19s}" for n in names), file=sys.stderr)
+        show = list(range(min(14, len(dag)))) + list(range(max(14, len(dag) - 4), len(dag)))
+        for i in show:
+            row = []
+            for sidx in range(4):
+                v = tr[i, :, sidx]
+                v = v[v > 0] - t0
+                row.append(f"{v.min():8d}..{v.max():8d}" if v.size else " " * 18)
+            print(f"[plan trace r{rank}] {i:3d} {dag[i][0]:8s} " + "  ".join(row), file=sys.stderr)
+    elif trace_buf is not None:
         tr = trace_buf.download(np.uint64, launches_per_step * 160 * 8).reshape(launches_per_step, 160, 8).astype(np.int64)
         t0 = tr[0, :148, 0].min()
         names = ["entry", "primed", "pred done", "quantized", "first w", "last row", "flags seen", "flags out"]
@@ -407,7 +497,9 @@ def run_b200(args):
     bytes_rank = sum(algorithmic_bytes(sp.rows, k, 1, 18) for (_, sp, k) in weights if sp.rows > 0)
     launch_us = ms_per_step * 1e3 / launches_per_step
     achieved = bytes_rank / launches_per_step / (launch_us * 1e-6) / 1e9
-    roofline = {"bound": "hbm", "kernel": "gemv_stream_kernel<Q4_0,1> (fused quantize_row_q8_0 + dp4a GEMV, bulk-copy ring)", "achieved": round(achieved, 1),
+    kernel_name = ("plan_kernel<Q4_0> (persistent: the token's 169 mul_mats in one launch; fused quantize_row_q8_0 + dp4a GEMV, bulk-copy ring, tagged hand-off)"
+                   if plan_fn is not None else "gemv_stream_kernel<Q4_0,1> (fused quantize_row_q8_0 + dp4a GEMV, bulk-copy ring)")
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": round(achieved, 1),
                 "peak": P["hbm_gbs"], "unit": "GB/s", "frac": round(achieved / P["hbm_gbs"], 4), "traffic": None,
                 "peak_source": P["source"], "launch_us": round(launch_us, 3),
                 "note": "per rank; at N>1 the step time includes the exchange of the dst slices"}
@@ -415,6 +507,19 @@ def run_b200(args):
     extra = {}
     if world == 1 and not args.no_extras:
         extra = run_extras(torch, qmm, ctx, stream, P, args)
+        if plan_fn is not None:
+            # what the plan replaces: one launch per same-input group (85 per token), two streams, replayed as a CUDA graph
+            try:
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1, stream=stream):
+                    other_fn()
+                for _ in range(3):
+                    g1.replay()
+                ms_g = timed(g1.replay, args.steps) / args.steps
+                extra["n1_launch_per_group_cuda_graph"] = {"tokens/s": round(1000.0 / ms_g, 2), "ms_per_step": round(ms_g, 4), "launches_per_token": len(groups),
+                                                           "note": "b200_mul_mat_batch per same-input group, o/fc_out on two streams; bit-identical to the plan"}
+            except Exception as e:
+                extra["n1_launch_per_group_cuda_graph"] = {"error": f"{type(e).__name__}: {e}"}
         if ll_chain_fn is not None:
             # the same graph with activations handed from launch to launch as tagged 8-byte elements (the mechanism the
             # multi-GPU path uses, here with a single rank): no grid-completion wait between dependent launches
@@ -445,9 +550,10 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8 dots (dp4a) + fp32 accumulate; Q4_0 weights, Q8_0 activations",
             "data": "synthetic (random-init Q4_0 blocks, U(-1,1) activations, seed 1234)",
             "config": {"workload": WORKLOAD, "l2": "inputs larger than L2 (3.29 GB of weights per step)", "cuda_graph": graph is not None,
-                       "parallelism": (f"row-split x{world} + " + ("all-gather fused into the GEMV epilogue (NVLink peer stores + flags)" if fused is not None else "NCCL all-gather")) if world > 1 else "single GPU",
-                       "gather_check_vs_nccl": gather_check, "graph_vs_plain_walk_bitwise": plain_check,
-                       "streams": 2 if (world == 1 and not args.no_overlap) else 1,
+                       "path": "decode plan: one persistent launch per token (b200_plan_launch)" if plan_fn is not None else "one launch per same-input group",
+                       "parallelism": (f"row-split x{world} + " + ("all-gather fused into the GEMV epilogue (tagged NVLink peer stores)" if (fused is not None or plan_fn is not None) else "NCCL all-gather")) if world > 1 else "single GPU",
+                       "gather_check_vs_nccl": gather_check, "plan_vs_launch_per_node_bitwise": plan_check, "graph_vs_plain_walk_bitwise": plain_check,
+                       "streams": 1 if plan_fn is not None else (2 if (world == 1 and not args.no_overlap) else 1),
                        "weights_bytes_per_token": sum(m * (k // 32) * 18 for _, m, k in mats)},
             "e2e": {"value": round(1000.0 / ms_e2e, 2), "unit": "tokens/s", "h2d_bytes_per_step": N_EMBD * 4, "d2h_bytes_per_step": N_VOCAB * 4,
                     "ms_per_step": round(ms_e2e, 4), "logits_finite": logits_ok},
@@ -705,6 +811,7 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="N = 1: keep o and fc_out of a block on one stream")
     ap.add_argument("--no-extras", action="store_true", help="skip the C1/C2 sub-benchmarks (A/B runs)")
     ap.add_argument("--trace", action="store_true", help="dump a device-side timeline of the first launches of a step to stderr")
+    ap.add_argument("--path", default="plan", choices=["plan", "launches"], help="plan: one persistent launch per token; launches: one launch per same-input group")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N > 1: how dst slices are re-assembled")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -1,0 +1,779 @@
+// b200_plan.cu -- a whole dependent sequence of decode mul_mats (n == 1) as ONE persistent launch.
+//
+// Stands in for ggml_backend_graph_plan_create / _compute (src/ggml-backend-impl.h:94-99; the reference's CUDA backend has
+// the opt-in CUDA-graph replay of a cgraph, src/ggml-cuda.cu:2461-2709) for graphs whose nodes are
+// GGML_OP_MUL_MAT{Q4_0|Q8_0} x F32 with one activation column.  Arithmetic per mul_mat is exactly that of
+// gemv_stream_kernel (fused quantize_row_q8_0, src/ggml-quants.c:535-618; exact per-block int32 dots scaled by d_w*d_x and
+// accumulated in fp32, src/ggml-quants.c:3858-3869 / :5010-5015; same lane -> block mapping and summation order, so results
+// are bit-identical to the one-launch-per-mul_mat path).
+//
+// What a decode token looks like to the memory system: ~170 matrices of 9-150 MB, each streamed once.  Launch boundaries
+// cost ~2.6 us each of idle HBM (profiles/r01_stream_bw_microbench.txt), a third of the step.  Here there are none:
+//   * grid = one persistent CTA per SM; every CTA walks the op list; in op i it owns a contiguous run of rows of W_i;
+//   * warp 8 is the producer: ONE elected thread streams the CTA's byte ranges of op 0, 1, 2, ... back to back into a
+//     shared-memory ring (cp.async.bulk + mbarrier complete_tx), ~180 KB in flight per SM (~27 MB per GPU = 4 us of HBM).
+//     Weights never depend on activations, so the producer runs arbitrarily far ahead of the consumers: HBM keeps
+//     streaming W_{i+1} while the grid exchanges the result of op i;
+//   * dependencies between ops travel as tagged 8-byte elements {fp32 value, u32 tag} ("LL" vectors, one per op, in an
+//     arena): the GEMV epilogue stores them, the next op's activation loads re-read until every tag matches.  No grid
+//     barrier, no flags, no fences; with world > 1 the same stores go to every rank's arena over NVLink, which makes the
+//     all-gather of a row-split mul_mat part of the epilogue;
+//   * consecutive ops that read the same vector (q, k, v, fc_in) share one activation quantization: the lane's int8
+//     activation blocks simply stay in registers.
+#include "b200_stream_common.cuh"
+
+#include <stdlib.h>
+#include <vector>
+
+using namespace b200s;
+
+namespace {
+
+constexpr int kCW = 8;                       // consumer warps
+constexpr int kCT = kCW * 32;                // consumer threads
+constexpr int kPlanThreads = (kCW + 1) * 32;         // consumers + the producer warp
+constexpr int kSegBlocks = 128;              // blocks of k per warp-segment (4 per lane)
+constexpr int kMaxSlots = 24;
+constexpr int kPartFloats = 4096;            // k-split partials parked per CTA per op: rows_per_cta * G (aliases the LL staging)
+constexpr int kMaxOps = 1023;
+constexpr int kDescCap = 128;                // op descriptors staged in shared memory per window
+
+enum : int { OPF_SAME_INPUT = 1, OPF_WRITE_LL = 2, OPF_EXPORT = 4 };
+
+struct __align__(16) PDesc {                 // what the producer needs of an op
+    const uint8_t *qs;       // qs plane, first row of this rank's slice
+    const __half *d;         // d plane, same
+    int k;
+    int rows_q, rows_rem;    // CTA c owns local rows [c*rows_q + min(c, rows_rem), + rows_q + (c < rows_rem))
+    int rs;                  // rows per ring slot (host copy of op_geom().rs: the producer thread must not divide)
+};
+static_assert(sizeof(PDesc) == 32, "PDesc layout");
+struct __align__(16) CDesc {                 // what the consumers need (staged in shared memory, kDescCap at a time)
+    float *dst_plain;        // local plain fp32 vector [m_total] or null
+    const float *src_plain;  // src1 when it comes from outside the plan (src_op < 0)
+    int ll_dst, ll_src;      // element offsets in the arena of this op's / its producer's LL vector
+    int k, flags;
+    int rows_q, rows_rem;
+    int src_op, row0;        // producing op or -1; global row of local row 0
+};
+static_assert(sizeof(CDesc) == 48, "CDesc layout");
+struct ExportDesc {
+    float *dst;
+    int ll, m_total, op, pad;
+};
+
+struct PlanGeom {
+    int slot_bytes, nslots;
+    int l2_ahead;            // ops: when the producer starts op i it prefetches its rows of op i + l2_ahead into L2 (0 = off)
+    int ring_off, act_off, ll_off, desc_off, bar_off, total;
+};
+
+struct PlanArgs {
+    const PDesc *pdesc;
+    const CDesc *cdesc;
+    const ExportDesc *exports;
+    int nops, nexports;
+    int world, rank;
+    void *arena[B200_MAX_RANKS];   // [rank] local; LL vectors live at the same offsets on every rank
+    uint32_t *state;               // {arrived CTAs, completed launches}
+    unsigned long long *trace;     // optional: [nops][gridDim.x][4] globaltimer stamps
+};
+
+__device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar_addr, uint32_t count) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(count) : "memory");
+}
+
+// per-op stage geometry: both producer and consumers derive it from (k, slot_bytes) alone
+struct OpGeom {
+    int nb, row_qs, row_sc, G, log2g, rpp, rs;
+};
+template <int TYPE>
+__device__ __forceinline__ OpGeom op_geom(int k, int slot_bytes) {
+    constexpr int QSB = TYPE == B200_TYPE_Q4_0 ? 16 : 32;
+    OpGeom g;
+    g.nb = k >> 5;
+    g.row_qs = g.nb * QSB;
+    g.row_sc = g.nb * 2;
+    const int segs = (g.nb + kSegBlocks - 1) >> 7;                // 1..8
+    g.log2g = segs <= 1 ? 0 : (segs <= 2 ? 1 : (segs <= 4 ? 2 : 3));
+    g.G = 1 << g.log2g;
+    g.rpp = kCW >> g.log2g;
+    int rs = slot_bytes / (g.row_qs + g.row_sc);
+    if (rs > 64) rs = 64;
+    g.rs = rs;                                                     // >= rpp >= 1 by construction of slot_bytes
+    return g;
+}
+
+// everything a warp needs to turn rows of a ring slot into results
+template <int TYPE>
+struct RowCtx {
+    uint4 alo[4], ahi[4];     // the lane's activation blocks b0 + lane + 32 i (int8), resident across same-input ops
+    float da[4];
+    int s8[4];
+    bool blive[4];
+    uint32_t woff0, soff0;    // lane offsets inside a row / inside the scale area
+    int row_qs, row_sc;
+};
+
+// exact dots of one row segment (4 blocks per lane) against the resident activations
+template <int TYPE>
+__device__ __forceinline__ float row_dots(const RowCtx<TYPE> &c, const uint4 (&w0)[4], const uint4 (&w1)[4], const unsigned short (&sc)[4]) {
+    float a = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int sumi = block_dot<TYPE>(w0[i], w1[i], c.alo[i], c.ahi[i], c.s8[i]);
+        const float dw = __half2float(__ushort_as_half(sc[i]));
+        if (c.blive[i]) a = fmaf((float)sumi, dw * c.da[i], a);
+    }
+    return a;
+}
+
+// NR (4, 2 or 1) rows r .. r+NR-1 of the stage at stage_a (rows past `rows` are clamped and dropped): two rows' loads are in
+// flight together, the NR row sums share one transposed butterfly.  Returns with lane (32/NR)*u holding row r+u.
+template <int TYPE, int NR>
+__device__ __forceinline__ float chunk_rows(const RowCtx<TYPE> &c, uint32_t stage_a, int r, int rows, int lane) {
+    constexpr int QSB = TYPE == B200_TYPE_Q4_0 ? 16 : 32;
+    constexpr int NU = NR >= 2 ? 2 : 1;       // rows whose loads are in flight together
+    float acc[NR];
+#pragma unroll
+    for (int h = 0; h < NR; h += NU) {
+        uint4 w0[NU][4], w1[NU][4];
+        unsigned short sc[NU][4];
+#pragma unroll
+        for (int u = 0; u < NU; u++) {
+            const int rr = min(r + h + u, rows - 1);
+            const uint32_t wbase = stage_a + (uint32_t)(rr * c.row_qs) + c.woff0;
+            const uint32_t sbase = stage_a + (uint32_t)(rr * c.row_sc) + c.soff0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                w0[u][i] = lds128(wbase + (uint32_t)(i * 32 * QSB));
+                if (TYPE == B200_TYPE_Q8_0) w1[u][i] = lds128(wbase + (uint32_t)(i * 32 * QSB + 16));
+                else w1[u][i] = make_uint4(0, 0, 0, 0);
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(sc[u][i]) : "r"(sbase + (uint32_t)(i * 64)));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NU; u++) acc[h + u] = row_dots<TYPE>(c, w0[u], w1[u], sc[u]);
+    }
+    // transposed butterfly: the same pairings -- hence the same bits -- as acc += shfl_xor(acc, 16, 8, 4, 2, 1) per row
+    float kk;
+    if (NR == 4) {
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+        float k0 = up16 ? acc[2] : acc[0], k1 = up16 ? acc[NR - 1] : acc[1];
+        const float s0 = up16 ? acc[0] : acc[2], s1 = up16 ? acc[1] : acc[NR - 1];
+        k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        kk = up8 ? k1 : k0;
+        const float ss = up8 ? k0 : k1;
+        kk += __shfl_xor_sync(0xffffffffu, ss, 8);
+    } else if (NR == 2) {
+        const bool up16 = (lane & 16) != 0;
+        kk = up16 ? acc[NR - 1] : acc[0];
+        const float ss = up16 ? acc[0] : acc[NR - 1];
+        kk += __shfl_xor_sync(0xffffffffu, ss, 16);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 8);
+    } else {
+        kk = acc[0];
+        kk += __shfl_xor_sync(0xffffffffu, kk, 16);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 8);
+    }
+    kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+    kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+    kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+    return kk;
+}
+
+// 32 lane-tasks (16 LL elements = 128 bytes each) of a tagged vector -> 16 floats per lane.  Coalesced 128-bit volatile loads
+// (L2 is where peer stores land), tags verified warp-wide, values transposed through a 2 KB per-warp staging area.  The
+// first attempt goes straight for the data (one L2 round trip when the vector is already complete); after a miss the warp
+// spins on its run's LAST element only (one sector per poll) before trying again.
+__device__ __forceinline__ void ll_fetch_warp(const char *wbase, int nvalid, uint32_t tag, float *wstage, int lane, float4 (&out)[4]) {
+    uint4 w[8];
+    const int nv8 = nvalid * 8;
+    for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int idx = j * 32 + lane < nv8 ? j * 32 + lane : 0;
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[j].x), "=r"(w[j].y), "=r"(w[j].z), "=r"(w[j].w) : "l"(wbase + (size_t)idx * 16));
+            ok = ok && w[j].y == tag && w[j].w == tag;
+        }
+        if (__all_sync(0xffffffffu, ok)) break;
+        ll_probe(wbase + (size_t)nvalid * 128 - 8, tag);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (j * 32 + lane < nv8) *reinterpret_cast<float2 *>(wstage + 2 * (j * 32 + lane)) = make_float2(__uint_as_float(w[j].x), __uint_as_float(w[j].z));
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; j++) out[j] = *reinterpret_cast<const float4 *>(wstage + lane * 16 + j * 4);
+    __syncwarp();
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_constant__ PlanArgs pa, const __grid_constant__ PlanGeom pg) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int QSB = TYPE == B200_TYPE_Q4_0 ? 16 : 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cta = blockIdx.x;
+
+    unsigned char *ring = smem + pg.ring_off;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + pg.bar_off);
+    uint64_t *empty_bar = full_bar + kMaxSlots;
+    uint32_t *s_epoch = reinterpret_cast<uint32_t *>(empty_bar + kMaxSlots);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < pg.nslots; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kCW);       // a slot's consumers (one team of G warps) arrive with 8/G each
+        }
+        *s_epoch = pa.state[1] + 1u;    // every CTA reads it before any CTA can finish (the bump needs all of them)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t epoch = *s_epoch;
+    const int nslots = pg.nslots;
+    const char *arena_local = reinterpret_cast<const char *>(pa.arena[0]);
+#pragma unroll
+    for (int r = 1; r < B200_MAX_RANKS; r++)
+        if (r == pa.rank) arena_local = reinterpret_cast<const char *>(pa.arena[r]);
+
+    if (warp == kCW) {
+        // ===== producer: ONE thread streams this CTA's rows of every op, in op order, through the ring.  The next op's
+        // descriptor is loaded while this op's copies are issued (the op's own copies take at least its HBM time, longer
+        // than an L2 round trip, so the load never stalls a busy stream). =====
+        if (lane == 0) {
+            int st = 0;
+            uint32_t par = 0;
+            unsigned long long prod_blocked = 0;
+            const uint32_t ring_a = smem_u32(ring);
+            PDesc cur = pa.pdesc[0];
+#pragma unroll 1
+            for (int op = 0; op < pa.nops; op++) {
+                PDesc nxt = cur;
+                if (op + 1 < pa.nops) nxt = pa.pdesc[op + 1];
+                if (pg.l2_ahead > 0 && op + pg.l2_ahead < pa.nops) {
+                    // HBM -> L2 for an op the ring will reach later (optional; off by default)
+                    const PDesc pf = pa.pdesc[op + pg.l2_ahead];
+                    const int nbp = pf.k >> 5;
+                    const long long rb = (long long)cta * pf.rows_q + min(cta, pf.rows_rem);
+                    const int nr = pf.rows_q + (cta < pf.rows_rem ? 1 : 0);
+                    if (nr > 0) {
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf.qs + rb * nbp * QSB), "r"((uint32_t)(nr * nbp * QSB)) : "memory");
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint8_t *>(pf.d) + rb * nbp * 2), "r"((uint32_t)(nr * nbp * 2)) : "memory");
+                    }
+                }
+                const int nb = cur.k >> 5, row_qs = nb * QSB, row_sc = nb * 2, rs_c = cur.rs;
+                const long long r_begin = (long long)cta * cur.rows_q + min(cta, cur.rows_rem);
+                const int nrows = cur.rows_q + (cta < cur.rows_rem ? 1 : 0);
+                const uint8_t *gq = cur.qs + r_begin * row_qs;
+                const uint8_t *gs = reinterpret_cast<const uint8_t *>(cur.d) + r_begin * row_sc;
+                const uint32_t stage_qs = (uint32_t)(rs_c * row_qs);
+                for (int r = 0; r < nrows; r += rs_c) {
+                    const int rows = min(rs_c, nrows - r);
+                    const uint32_t fb = smem_u32(&full_bar[st]);
+                    if (pa.trace) {
+                        const unsigned long long t0 = gtime();
+                        mbar_wait(&empty_bar[st], par ^ 1u);
+                        prod_blocked += gtime() - t0;
+                    } else {
+                        mbar_wait(&empty_bar[st], par ^ 1u);
+                    }
+                    const uint32_t dst = ring_a + (uint32_t)(st * pg.slot_bytes);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)(rows * (row_qs + row_sc))) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                                 "l"(gq + (size_t)r * row_qs), "r"((uint32_t)(rows * row_qs)), "r"(fb) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + stage_qs),
+                                 "l"(gs + (size_t)r * row_sc), "r"((uint32_t)(rows * row_sc)), "r"(fb) : "memory");
+                    if (++st == nslots) { st = 0; par ^= 1u; }
+                }
+                cur = nxt;
+            }
+            if (pa.trace) pa.trace[(size_t)pa.nops * gridDim.x * 4 + (size_t)cta * 4 + 0] = prod_blocked;
+        }
+    } else {
+        // ===== consumers =====
+        const uint32_t ring_a = smem_u32(ring);
+        const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+        CDesc *sdesc = reinterpret_cast<CDesc *>(smem + pg.desc_off);
+        unsigned char *act = smem + pg.act_off;
+        const uint32_t act_a = smem_u32(act);
+        float *llstage = reinterpret_cast<float *>(smem + pg.ll_off) + warp * 512;
+        float *part = reinterpret_cast<float *>(smem + pg.ll_off);      // same bytes, other phase (bar.sync in between)
+        int st0 = 0;                // ring position of the op's first stage
+        uint32_t par0 = 0;
+        unsigned long long cons_blocked = 0, quant_time = 0;
+        RowCtx<TYPE> c;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { c.alo[i] = c.ahi[i] = make_uint4(0, 0, 0, 0); c.da[i] = 0.0f; c.s8[i] = 0; c.blive[i] = false; }
+
+#pragma unroll 1
+        for (int op = 0; op < pa.nops; op++) {
+            const int di = op & (kDescCap - 1);
+            if (di == 0) {
+                // next window of op descriptors -> shared memory: an op boundary must not cost an L2 round trip (~0.7 us
+                // under full streaming load)
+                cbar();
+                const int n3 = min(kDescCap, pa.nops - op) * 3;
+                const uint4 *src = reinterpret_cast<const uint4 *>(pa.cdesc + op);
+                for (int t = threadIdx.x; t < n3; t += kCT) reinterpret_cast<uint4 *>(sdesc)[t] = src[t];
+                cbar();
+            }
+            const CDesc *o = sdesc + di;
+            // geometry comes precomputed in the descriptor (flags: bits 8..15 rows per slot, 16..19 log2 of the k-split)
+            const int k = o->k, flags = o->flags;
+            const int nb = k >> 5;
+            const int rs = (flags >> 8) & 0xff, log2g = (flags >> 16) & 0xf;
+            const int rows_q = o->rows_q, rows_rem = o->rows_rem;
+            const int r_begin = cta * rows_q + min(cta, rows_rem);
+            const int nrows = rows_q + (cta < rows_rem ? 1 : 0);
+            const int G = 1 << log2g, seg = warp & (G - 1), team = warp >> log2g, team_mask = (kCW >> log2g) - 1;   // 8/G teams of G warps
+            const int b0 = seg * kSegBlocks;
+            const uint32_t tag = (epoch << 10) | (uint32_t)op;
+            unsigned long long *tr = pa.trace ? pa.trace + ((size_t)op * gridDim.x + cta) * 4 : nullptr;
+
+            if (!(flags & OPF_SAME_INPUT)) {
+                // ---- quantize_row_q8_0 of src1 into shared memory, bit-exact (same code path as gemv_stream_kernel) ----
+                // (this barrier-separated phase is also what makes a change of team size safe: every earlier fill of the ring
+                //  has been consumed before any warp waits on a slot it has not been watching)
+                const unsigned long long tq0 = tr ? gtime() : 0ull;
+                const int src_op = o->src_op;
+                const bool ll_in = src_op >= 0;
+                const uint32_t src_tag = (epoch << 10) | (uint32_t)(src_op & 1023);
+                const char *xsrc = ll_in ? arena_local + (size_t)o->ll_src * 8 : reinterpret_cast<const char *>(o->src_plain);
+                constexpr int kQB = 4;
+                const int tpc = nb * 2;      // lane-tasks: (block, half) = 16 consecutive floats
+#pragma unroll 1
+                for (int base = 0; base < tpc; base += kCT * kQB) {
+                    float4 v[kQB][4];
+#pragma unroll
+                    for (int u = 0; u < kQB; u++) {
+                        const int tb = base + u * kCT + warp * 32;      // first lane-task of this warp
+                        if (tb >= tpc) continue;
+                        if (ll_in) {
+                            ll_fetch_warp(xsrc + (size_t)tb * 128, min(32, tpc - tb), src_tag, llstage, lane, v[u]);
+                        } else {
+                            const int t = min(tb + lane, tpc - 1);
+                            const float4 *src = reinterpret_cast<const float4 *>(xsrc) + (size_t)t * 4;
+#pragma unroll
+                            for (int j = 0; j < 4; j++) v[u][j] = src[j];
+                        }
+                    }
+                    if (tr && threadIdx.x == 0 && base == 0) tr[0] = gtime();
+#pragma unroll
+                    for (int u = 0; u < kQB; u++) {
+                        const int tb = base + u * kCT + warp * 32;
+                        if (tb >= tpc) continue;                        // warp-uniform: the shuffles below stay full
+                        const int tt = tb + lane;
+                        const bool live = tt < tpc;
+                        const int t = live ? tt : tpc - 1;
+                        const int b = t >> 1, h = t & 1;
+                        float amax = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[u][j].x), fabsf(v[u][j].y)), fmaxf(fabsf(v[u][j].z), fabsf(v[u][j].w))));
+                        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                        const float id = amax != 0.0f ? __fdiv_rn(127.f, amax) : 0.0f;
+                        uint32_t pk[4];
+                        int sq = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int q0 = __float2int_rn(__fmul_rn(v[u][j].x, id)), q1 = __float2int_rn(__fmul_rn(v[u][j].y, id));
+                            const int q2 = __float2int_rn(__fmul_rn(v[u][j].z, id)), q3 = __float2int_rn(__fmul_rn(v[u][j].w, id));
+                            sq += q0 + q1 + q2 + q3;
+                            pk[j] = (uint32_t)(q0 & 0xff) | ((uint32_t)(q1 & 0xff) << 8) | ((uint32_t)(q2 & 0xff) << 16) | ((uint32_t)(q3 & 0xff) << 24);
+                        }
+                        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                        if (live) {
+                            *reinterpret_cast<uint4 *>(act + (size_t)h * (k >> 1) + (size_t)b * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            if (h == 0) {
+                                reinterpret_cast<float *>(act + k)[b] = __half2float(__float2half_rn(__fdiv_rn(amax, 127.f)));
+                                if (TYPE == B200_TYPE_Q4_0) reinterpret_cast<int *>(act + k + (size_t)nb * 4)[b] = 8 * sq;
+                            }
+                        }
+                    }
+                }
+                cbar();
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t b = (uint32_t)min(b0 + lane + 32 * i, nb - 1);
+                    c.alo[i] = lds128(act_a + b * 16);
+                    c.ahi[i] = lds128(act_a + (uint32_t)(k >> 1) + b * 16);
+                    c.da[i] = lds_f32(act_a + (uint32_t)k + b * 4);
+                    c.s8[i] = TYPE == B200_TYPE_Q4_0 ? lds_s32(act_a + (uint32_t)k + (uint32_t)nb * 4 + b * 4) : 0;
+                    c.blive[i] = b0 + lane + 32 * i < nb;
+                }
+                cbar();     // every warp holds its blocks in registers: the next quantization may overwrite `act`
+                if (tr && threadIdx.x == 0) tr[1] = gtime();
+                if (tr) quant_time += gtime() - tq0;
+            }
+
+            // ---- the CTA's rows: whole ring slots are dealt round-robin to teams of G warps (one warp when k <= 4096) ----
+            c.row_qs = nb * QSB;
+            c.row_sc = nb * 2;
+            c.woff0 = (uint32_t)((b0 + lane) * QSB);
+            c.soff0 = (uint32_t)(rs * c.row_qs + (b0 + lane) * 2);
+            float *dst_plain = o->dst_plain;
+            const int ll_dst = o->ll_dst + o->row0 + r_begin;
+            const int prow0 = o->row0 + r_begin;
+            const bool write_ll = (flags & OPF_WRITE_LL) != 0;
+            if (tr && threadIdx.x == 0) tr[2] = gtime();
+            int st = st0;
+            uint32_t par = par0;
+#pragma unroll 1
+            for (int rbase = 0; rbase < nrows; rbase += rs) {
+                // A ring slot always belongs to the same team (slot % teams): its warps see every fill of the slot in order, so
+                // the parity wait can never be a lap off (fills complete out of order; a warp that skipped a fill could
+                // mistake the previous lap's phase for its own).
+                if ((st & team_mask) == team) {
+                    if (tr && warp == 2) {
+                        const unsigned long long t0 = gtime();
+                        mbar_wait_a(full_a + 8u * (uint32_t)st, par);
+                        cons_blocked += gtime() - t0;
+                    } else {
+                        mbar_wait_a(full_a + 8u * (uint32_t)st, par);
+                    }
+                    const int rows = min(rs, nrows - rbase);
+                    const uint32_t stage_a = ring_a + (uint32_t)(st * pg.slot_bytes);
+#pragma unroll 1
+                    for (int r = 0; r < rows;) {
+                        float v;
+                        int u, step;
+                        bool holder;
+                        if (rows - r > 2) {
+                            v = chunk_rows<TYPE, 4>(c, stage_a, r, rows, lane);
+                            u = lane >> 3; holder = (lane & 7) == 0; step = 4;
+                        } else if (rows - r == 2) {
+                            v = chunk_rows<TYPE, 2>(c, stage_a, r, rows, lane);
+                            u = lane >> 4; holder = (lane & 15) == 0; step = 2;
+                        } else {
+                            v = chunk_rows<TYPE, 1>(c, stage_a, r, rows, lane);
+                            u = 0; holder = lane == 0; step = 1;
+                        }
+                        if (holder && r + u < rows) {
+                            const int gr = rbase + r + u;     // row relative to r_begin
+                            if (G == 1) {
+                                if (dst_plain) dst_plain[prow0 + gr] = v;
+                                if (write_ll) {
+#pragma unroll
+                                    for (int rk = 0; rk < B200_MAX_RANKS; rk++)
+                                        if (rk < pa.world) ll_store(pa.arena[rk], ll_dst + gr, v, tag);
+                                }
+                            } else {
+                                part[gr * G + seg] = v;
+                            }
+                        }
+                        r += step;
+                    }
+                    // every lane's weights of this slot have been consumed by the dots: hand it back to the producer
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cnt(empty_a + 8u * (uint32_t)st, (uint32_t)(kCW >> log2g));
+                }
+                if (++st == nslots) { st = 0; par ^= 1u; }
+            }
+            st0 = st;
+            par0 = par;
+            if (G > 1) {
+                // k-split rows: combine the segments' partials in segment order (fixed summation order)
+                cbar();
+                for (int t = threadIdx.x; t < nrows; t += kCT) {
+                    float v = 0.0f;
+                    for (int sg = 0; sg < G; sg++) v += part[t * G + sg];
+                    if (dst_plain) dst_plain[prow0 + t] = v;
+                    if (write_ll) {
+#pragma unroll
+                        for (int rk = 0; rk < B200_MAX_RANKS; rk++)
+                            if (rk < pa.world) ll_store(pa.arena[rk], ll_dst + t, v, tag);
+                    }
+                }
+                cbar();
+            }
+            if (tr && threadIdx.x == 0) tr[3] = gtime();
+        }
+        if (pa.trace && lane == 0 && warp == 2) {
+            pa.trace[(size_t)pa.nops * gridDim.x * 4 + (size_t)cta * 4 + 1] = cons_blocked;
+            pa.trace[(size_t)pa.nops * gridDim.x * 4 + (size_t)cta * 4 + 2] = quant_time;
+        }
+        // ---- row-split plans: ops marked EXPORT leave their COMPLETE vector (all ranks' slices) in the local plain dst ----
+        for (int e = 0; e < pa.nexports; e++) {
+            const ExportDesc x = pa.exports[e];
+            const uint32_t tag = (epoch << 10) | (uint32_t)x.op;
+            const uint2 *ll = reinterpret_cast<const uint2 *>(arena_local) + x.ll;
+            for (int i = cta * kCT + (int)threadIdx.x; i < x.m_total; i += gridDim.x * kCT) {
+                uint32_t v, t;
+                do {
+                    asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v), "=r"(t) : "l"(ll + i));
+                } while (t != tag);
+                x.dst[i] = __uint_as_float(v);
+            }
+        }
+    }
+
+    // bookkeeping: the last CTA to finish publishes the launch count (tags of the next launch)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t arrived = atomicAdd(&pa.state[0], 1u);
+        if (arrived == gridDim.x - 1u) {
+            pa.state[0] = 0;
+            __threadfence();
+            pa.state[1] = epoch;
+        }
+    }
+}
+
+}  // namespace
+
+struct b200_plan {
+    int type, nops, grid, world, rank;
+    PlanGeom geom;
+    PDesc *pdesc_dev;
+    CDesc *cdesc_dev;
+    ExportDesc *exports_dev;
+    void *arena_own;            // allocated here when world == 1
+    uint32_t *state_dev;
+    unsigned long long *trace_dev;
+    PlanArgs args;
+    size_t arena_bytes;
+};
+
+static size_t plan_arena_elems(const b200_mul_mat_args *args, int count, const b200_plan_split *split, std::vector<long long> *offs) {
+    size_t total = 0;
+    for (int i = 0; i < count; i++) {
+        const long long mt = split && split->m_total ? split->m_total[i] : args[i].ne01;
+        if (offs) offs->push_back((long long)total);
+        total += (size_t)((mt + 15) / 16 * 16);      // 128-byte aligned LL vectors
+    }
+    return total;
+}
+
+static bool ranges_overlap(const void *a, size_t an, const void *b, size_t bn) {
+    const uintptr_t a0 = (uintptr_t)a, b0 = (uintptr_t)b;
+    return a0 < b0 + bn && b0 < a0 + an;
+}
+
+extern "C" {
+
+size_t b200_plan_arena_bytes(const b200_mul_mat_args *args, int count, const b200_plan_split *split) {
+    if (!args || count <= 0) return 0;
+    return plan_arena_elems(args, count, split, nullptr) * 8;
+}
+
+void b200_plan_destroy(b200_plan *p) {
+    if (!p) return;
+    if (p->pdesc_dev) cudaFree(p->pdesc_dev);
+    if (p->cdesc_dev) cudaFree(p->cdesc_dev);
+    if (p->exports_dev) cudaFree(p->exports_dev);
+    if (p->arena_own) cudaFree(p->arena_own);
+    if (p->state_dev) cudaFree(p->state_dev);
+    if (p->trace_dev) cudaFree(p->trace_dev);
+    free(p);
+}
+
+int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, const b200_plan_split *split, b200_plan **out) {
+    B200_REQUIRE(ctx, ctx && args && out && count >= 1, B200_ERR_INVALID);
+    *out = NULL;
+    B200_REQUIRE(ctx, count <= kMaxOps, B200_ERR_UNSUPPORTED);
+    const int world = split ? split->world : 1, rank = split ? split->rank : 0;
+    B200_REQUIRE(ctx, world >= 1 && world <= B200_MAX_RANKS && rank >= 0 && rank < world, B200_ERR_INVALID);
+    if (split) {
+        B200_REQUIRE(ctx, split->row0 && split->m_total, B200_ERR_INVALID);
+        for (int r = 0; r < world; r++) B200_REQUIRE(ctx, split->peer_arena[r] != NULL, B200_ERR_INVALID);
+    }
+    const int type = args[0].type;
+    B200_REQUIRE(ctx, type == B200_TYPE_Q4_0 || type == B200_TYPE_Q8_0, B200_ERR_UNSUPPORTED);
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int grid = ctx->sm_count;
+    const int qsb = b200_qs_bytes(type);
+    // ring slot = `slot_rows` rows of a 4096-wide k-segment (8 -> 18432 B for Q4_0 = one row of k = 32768).  The producer
+    // thread needs ~250 ns per slot (measured: 4-row slots cap the stream at 5.4 TB/s), so slots must not be small.
+    int slot_rows = 8;
+    if (const char *e = getenv("B200_PLAN_SLOT_ROWS")) { const int v = atoi(e); if (v >= 8 && v <= 16) slot_rows = v; }
+    const int slot_bytes = slot_rows * 128 * (qsb + 2);
+
+    std::vector<long long> ll_off;
+    const size_t arena_elems = plan_arena_elems(args, count, split, &ll_off);
+    B200_REQUIRE(ctx, arena_elems < (1ull << 30), B200_ERR_UNSUPPORTED);
+    std::vector<PDesc> pd((size_t)count);
+    std::vector<CDesc> cd((size_t)count);
+    std::vector<int> m_total((size_t)count);
+    std::vector<ExportDesc> ex;
+    int kmax = 0;
+    for (int i = 0; i < count; i++) {
+        const b200_mul_mat_args *a = &args[i];
+        // decode shapes the streaming kernels take; anything else is the caller's node-by-node path
+        B200_REQUIRE(ctx, a->type == type && !(a->flags & B200_MM_FORCE_GEMM), B200_ERR_UNSUPPORTED);
+        B200_REQUIRE(ctx, a->ne11 == 1 && a->ne12 == 1 && a->ne13 == 1 && a->ne02 == 1 && a->ne03 == 1, B200_ERR_UNSUPPORTED);
+        B200_REQUIRE(ctx, a->ne00 > 0 && a->ne00 % 256 == 0 && a->ne00 <= 32768, B200_ERR_UNSUPPORTED);
+        B200_REQUIRE(ctx, a->ne01 >= 0 && a->ne01 < (1ll << 30), B200_ERR_UNSUPPORTED);
+        B200_REQUIRE(ctx, a->src0_dev && a->src1_dev, B200_ERR_INVALID);
+        const int64_t nb = a->ne00 / B200_QK;
+        B200_REQUIRE(ctx, a->src0_block_off >= 0 && a->src0_block_off + nb * a->ne01 <= a->src0_nblocks_total, B200_ERR_INVALID);
+        const int64_t mt = split ? split->m_total[i] : a->ne01;
+        const int64_t row0 = split ? split->row0[i] : 0;
+        B200_REQUIRE(ctx, row0 >= 0 && row0 + a->ne01 <= mt && mt < (1ll << 30), B200_ERR_INVALID);
+        m_total[i] = (int)mt;
+        PDesc &p = pd[i];
+        CDesc &c = cd[i];
+        memset(&p, 0, sizeof(p));
+        memset(&c, 0, sizeof(c));
+        p.qs = (const uint8_t *)a->src0_dev + a->src0_block_off * qsb;
+        p.d = (const __half *)((const uint8_t *)a->src0_dev + a->src0_nblocks_total * qsb) + a->src0_block_off;
+        B200_REQUIRE(ctx, ((uintptr_t)p.qs & 15) == 0 && ((uintptr_t)p.d & 15) == 0, B200_ERR_UNSUPPORTED);
+        p.k = c.k = (int)a->ne00;
+        p.rows_q = c.rows_q = (int)(a->ne01 / grid);
+        p.rows_rem = c.rows_rem = (int)(a->ne01 % grid);
+        {
+            int rs = slot_bytes / (int)(nb * (qsb + 2));             // rows per ring slot
+            p.rs = rs > 64 ? 64 : rs;
+        }
+        c.dst_plain = a->dst_dev;
+        c.row0 = (int)row0;
+        c.ll_dst = (int)ll_off[i];
+        if (a->flags & B200_MM_EXPORT) {
+            c.flags |= OPF_EXPORT;
+            if (world > 1 && a->dst_dev) {
+                c.flags |= OPF_WRITE_LL;
+                ExportDesc e;
+                e.dst = a->dst_dev; e.ll = c.ll_dst; e.m_total = (int)mt; e.op = i; e.pad = 0;
+                ex.push_back(e);
+            }
+        }
+        const int G = (int)((nb + kSegBlocks - 1) / kSegBlocks);
+        const int Gp = G <= 1 ? 1 : (G <= 2 ? 2 : (G <= 4 ? 4 : 8));
+        c.flags |= (p.rs << 8) | ((Gp == 1 ? 0 : Gp == 2 ? 1 : Gp == 4 ? 2 : 3) << 16);
+        B200_REQUIRE(ctx, Gp == 1 || (size_t)(c.rows_q + 1) * Gp <= (size_t)kPartFloats, B200_ERR_UNSUPPORTED);
+        if (c.k > kmax) kmax = c.k;
+        // dataflow: src1 is the dst of the latest earlier op with that address, else an outside vector
+        c.src_op = -1;
+        c.src_plain = a->src1_dev;
+        for (int j = i - 1; j >= 0; j--) {
+            if (!args[j].dst_dev) continue;
+            if (!ranges_overlap(a->src1_dev, (size_t)a->ne00 * 4, args[j].dst_dev, (size_t)m_total[j] * 4)) continue;
+            // must be exactly that vector
+            B200_REQUIRE(ctx, (const void *)a->src1_dev == (const void *)args[j].dst_dev && m_total[j] == c.k, B200_ERR_UNSUPPORTED);
+            c.src_op = j;
+            c.ll_src = cd[j].ll_dst;
+            c.src_plain = NULL;
+            cd[j].flags |= OPF_WRITE_LL;
+            break;
+        }
+        if (c.src_op < 0) B200_REQUIRE(ctx, ((uintptr_t)a->src1_dev & 15) == 0, B200_ERR_UNSUPPORTED);
+        // ops that read the vector the previous op read keep the activation blocks in registers
+        if (i > 0 && c.k == cd[i - 1].k && c.src_op == cd[i - 1].src_op && (c.src_op >= 0 || c.src_plain == cd[i - 1].src_plain))
+            c.flags |= OPF_SAME_INPUT;
+    }
+    // Hazards sequential execution would hide but dataflow execution does not: plain dst vectors that alias each other or an
+    // outside input (buffer reuse by a graph allocator).  Those graphs stay on the node-by-node path.
+    for (int i = 0; i < count; i++) {
+        if (!args[i].dst_dev) continue;
+        const size_t di = (size_t)m_total[i] * 4;
+        for (int j = 0; j < count; j++) {
+            if (j > i && args[j].dst_dev && ranges_overlap(args[i].dst_dev, di, args[j].dst_dev, (size_t)m_total[j] * 4)) {
+                b200_set_error(ctx, "b200_plan_create: dst of op %d aliases dst of op %d", i, j);
+                return B200_ERR_UNSUPPORTED;
+            }
+            if (cd[j].src_op < 0 && ranges_overlap(args[i].dst_dev, di, cd[j].src_plain, (size_t)cd[j].k * 4)) {
+                b200_set_error(ctx, "b200_plan_create: dst of op %d aliases the outside input of op %d", i, j);
+                return B200_ERR_UNSUPPORTED;
+            }
+        }
+    }
+
+    b200_plan *p = (b200_plan *)calloc(1, sizeof(b200_plan));
+    if (!p) return B200_ERR_ALLOC;
+    p->type = type; p->nops = count; p->grid = grid; p->world = world; p->rank = rank;
+    p->arena_bytes = arena_elems * 8;
+    // shared-memory geometry
+    PlanGeom &g = p->geom;
+    g.slot_bytes = slot_bytes;
+    g.l2_ahead = 0;
+    if (const char *e = getenv("B200_PLAN_L2_AHEAD")) { const int v = atoi(e); if (v >= 0 && v <= 31) g.l2_ahead = v; }
+    const int act_bytes = (int)b200_align_up((size_t)kmax + (size_t)(kmax / 32) * 8, 128);
+    const int ll_bytes = kCW * 2048 > kPartFloats * 4 ? kCW * 2048 : kPartFloats * 4;
+    const int desc_bytes = kDescCap * (int)sizeof(CDesc);
+    const int bar_bytes = 2 * kMaxSlots * 8 + 64;
+    const int max_smem = 227 * 1024;
+    int nslots = (max_smem - act_bytes - ll_bytes - desc_bytes - bar_bytes) / g.slot_bytes;
+    if (nslots > kMaxSlots) nslots = kMaxSlots;
+    if (nslots >= kCW) nslots = nslots / kCW * kCW;     // every consumer warp owns the same number of slots
+    if (const char *e = getenv("B200_PLAN_SLOTS")) { const int v = atoi(e); if (v >= 2 && v <= kMaxSlots && v * g.slot_bytes <= max_smem - act_bytes - ll_bytes - desc_bytes - bar_bytes) nslots = v; }
+    if (nslots < 2) { free(p); b200_set_error(ctx, "b200_plan_create: k = %d leaves no room for the weight ring", kmax); return B200_ERR_UNSUPPORTED; }
+    g.nslots = nslots;
+    g.ring_off = 0;
+    g.act_off = nslots * g.slot_bytes;
+    g.ll_off = g.act_off + act_bytes;
+    g.desc_off = g.ll_off + ll_bytes;
+    g.bar_off = g.desc_off + desc_bytes;
+    g.total = g.bar_off + bar_bytes;
+
+    cudaError_t e = cudaMalloc((void **)&p->pdesc_dev, sizeof(PDesc) * (size_t)count);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->cdesc_dev, sizeof(CDesc) * (size_t)count);
+    if (e == cudaSuccess && !ex.empty()) e = cudaMalloc((void **)&p->exports_dev, sizeof(ExportDesc) * ex.size());
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->state_dev, 16);
+    if (e == cudaSuccess && world == 1) e = cudaMalloc(&p->arena_own, p->arena_bytes);
+    if (e == cudaSuccess && getenv("B200_PLAN_TRACE")) {
+        e = cudaMalloc((void **)&p->trace_dev, (size_t)(count + 1) * grid * 4 * 8);
+        if (e == cudaSuccess) e = cudaMemset(p->trace_dev, 0, (size_t)(count + 1) * grid * 4 * 8);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(p->pdesc_dev, pd.data(), sizeof(PDesc) * (size_t)count, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->cdesc_dev, cd.data(), sizeof(CDesc) * (size_t)count, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !ex.empty()) e = cudaMemcpy(p->exports_dev, ex.data(), sizeof(ExportDesc) * ex.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(p->state_dev, 0, 16);
+    if (e == cudaSuccess && world == 1) e = cudaMemset(p->arena_own, 0, p->arena_bytes);
+    if (e == cudaSuccess) {
+        auto kern = type == B200_TYPE_Q4_0 ? plan_kernel<B200_TYPE_Q4_0> : plan_kernel<B200_TYPE_Q8_0>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.total);
+    }
+    if (e != cudaSuccess) {
+        b200_set_error(ctx, "b200_plan_create: %s", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        b200_plan_destroy(p);
+        return e == cudaErrorMemoryAllocation ? B200_ERR_ALLOC : B200_ERR_CUDA;
+    }
+    PlanArgs &pa = p->args;
+    memset(&pa, 0, sizeof(pa));
+    pa.pdesc = p->pdesc_dev;
+    pa.cdesc = p->cdesc_dev;
+    pa.exports = p->exports_dev;
+    pa.nops = count;
+    pa.nexports = (int)ex.size();
+    pa.world = world;
+    pa.rank = rank;
+    for (int r = 0; r < world; r++) pa.arena[r] = split ? split->peer_arena[r] : p->arena_own;
+    pa.state = p->state_dev;
+    pa.trace = p->trace_dev;
+    *out = p;
+    return B200_OK;
+}
+
+int b200_plan_launch(b200_ctx *ctx, b200_plan *p) {
+    B200_REQUIRE(ctx, ctx && p, B200_ERR_INVALID);
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (p->type == B200_TYPE_Q4_0)
+        plan_kernel<B200_TYPE_Q4_0><<<p->grid, kPlanThreads, p->geom.total, ctx->stream>>>(p->args, p->geom);
+    else
+        plan_kernel<B200_TYPE_Q8_0><<<p->grid, kPlanThreads, p->geom.total, ctx->stream>>>(p->args, p->geom);
+    ctx->launches++;
+    B200_CUDA_TRY(ctx, cudaGetLastError());
+    return B200_OK;
+}
+
+int b200_plan_trace(b200_ctx *ctx, b200_plan *p, unsigned long long *out_host, size_t capacity_u64, int *nops, int *grid) {
+    B200_REQUIRE(ctx, ctx && p, B200_ERR_INVALID);
+    if (nops) *nops = p->nops;
+    if (grid) *grid = p->grid;
+    if (!p->trace_dev || !out_host) return B200_ERR_UNSUPPORTED;
+    const size_t n = (size_t)(p->nops + 1) * p->grid * 4;     // + one row of per-CTA totals
+    B200_REQUIRE(ctx, capacity_u64 >= n, B200_ERR_INVALID);
+    B200_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    B200_CUDA_TRY(ctx, cudaMemcpy(out_host, p->trace_dev, n * 8, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+}  // extern "C"

@@ -24,7 +24,7 @@ TYPE_F32, TYPE_Q4_0, TYPE_Q8_0 = 0, 2, 8
 QK = 32
 WIRE_BYTES = {TYPE_Q4_0: 18, TYPE_Q8_0: 34}
 TYPE_NAMES = {TYPE_Q4_0: "q4_0", TYPE_Q8_0: "q8_0"}
-MM_FORCE_GEMV, MM_FORCE_GEMM = 1, 2
+MM_FORCE_GEMV, MM_FORCE_GEMM, MM_EXPORT = 1, 2, 4
 
 OK, ERR_CUDA, ERR_INVALID, ERR_UNSUPPORTED, ERR_ALLOC = 0, -1, -2, -3, -4
 
@@ -54,6 +54,13 @@ class Gather(C.Structure):
     _fields_ = [
         ("world", C.c_int32), ("rank", C.c_int32), ("slot", C.c_int32), ("wait_slot", C.c_int32), ("row0", C.c_int64),
         ("peer_dst", C.c_void_p * MAX_RANKS), ("state", C.c_void_p),
+    ]
+
+
+class PlanSplit(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32), ("rank", C.c_int32), ("peer_arena", C.c_void_p * MAX_RANKS),
+        ("row0", C.POINTER(C.c_int64)), ("m_total", C.POINTER(C.c_int64)),
     ]
 
 
@@ -101,6 +108,11 @@ _SIGNATURES = {
     "b200_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "b200_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200_plan_arena_bytes": (C.c_size_t, [C.POINTER(MulMatArgs), C.c_int, C.POINTER(PlanSplit)]),
+    "b200_plan_create": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs), C.c_int, C.POINTER(PlanSplit), C.POINTER(C.c_void_p)]),
+    "b200_plan_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200_plan_destroy": (None, [C.c_void_p]),
+    "b200_plan_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b200_block_dots": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "b200_mul_mat_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
 }
@@ -380,6 +392,32 @@ class Context:
         """independent mul_mats in one call (b200_mul_mat_batch); same-input decode entries share a launch"""
         arr = (MulMatArgs * len(args_list))(*args_list)
         self._check(self.lib.b200_mul_mat_batch(self.h, arr, len(args_list)))
+
+    # -- decode plans (b200_plan_*): a dependent sequence of decode mul_mats as one persistent launch
+    def plan_arena_bytes(self, args_list, split: "PlanSplit | None" = None) -> int:
+        arr = (MulMatArgs * len(args_list))(*args_list)
+        return int(self.lib.b200_plan_arena_bytes(arr, len(args_list), C.byref(split) if split is not None else None))
+
+    def plan_create(self, args_list, split: "PlanSplit | None" = None) -> int:
+        arr = (MulMatArgs * len(args_list))(*args_list)
+        h = C.c_void_p()
+        self._check(self.lib.b200_plan_create(self.h, arr, len(args_list), C.byref(split) if split is not None else None, C.byref(h)))
+        return h.value
+
+    def plan_launch(self, plan: int):
+        self._check(self.lib.b200_plan_launch(self.h, C.c_void_p(plan)))
+
+    def plan_destroy(self, plan: int):
+        self.lib.b200_plan_destroy(C.c_void_p(plan))
+
+    def plan_trace(self, plan: int) -> np.ndarray:
+        """[nops + 1, grid, 4] ns stamps of the last launch (needs env B200_PLAN_TRACE at plan_create); the last row holds
+        per-CTA totals: producer blocked on a full ring, a consumer warp blocked on an empty ring, time in quantization phases"""
+        nops, grid = C.c_int(), C.c_int()
+        self.lib.b200_plan_trace(self.h, C.c_void_p(plan), None, 0, C.byref(nops), C.byref(grid))
+        out = np.zeros((nops.value + 1, grid.value, 4), dtype=np.uint64)   # last row: per-CTA totals
+        self._check(self.lib.b200_plan_trace(self.h, C.c_void_p(plan), _ptr(out), out.size, C.byref(nops), C.byref(grid)))
+        return out
 
     def mul_mat(self, w: QTensor, x: np.ndarray, flags: int = 0) -> np.ndarray:
         """x: [ne13, ne12, n, k] (or [n, k]) float32 host.  Returns dst [ne13, ne12, n, m] float32 (ggml dst[m,n,ne12,ne13])."""

@@ -157,6 +157,7 @@ typedef struct b200_mul_mat_args {
 
 #define B200_MM_FORCE_GEMV  1   /* use the dp4a GEMV for any n (column chunks of <= 8) */
 #define B200_MM_FORCE_GEMM  2   /* use the tcgen05 GEMM for any n */
+#define B200_MM_EXPORT      4   /* b200_plan_create on a row-split plan: leave the COMPLETE dst (all ranks' slices) in dst_dev */
 
 B200_API int b200_mul_mat(b200_ctx *ctx, const b200_mul_mat_args *args);
 /* `count` mul_mats with NO data dependencies among them (e.g. the q/k/v/fc_in projections of a GPT-J block, which all
@@ -200,6 +201,42 @@ B200_API int b200_gather_finish(b200_ctx *ctx, const b200_gather *gather, const 
 B200_API int b200_ipc_export(b200_ctx *ctx, void *dptr, void *handle64_out);
 B200_API int b200_ipc_import(b200_ctx *ctx, const void *handle64, void **peer_ptr_out);
 B200_API int b200_ipc_close(b200_ctx *ctx, void *peer_ptr);
+
+/* ---- decode plans: a dependent sequence of decode mul_mats as ONE persistent launch -----------------------
+ * Replaces ggml_backend_graph_plan_create / _compute / _free (src/ggml-backend-impl.h:94-99; the reference's CUDA backend
+ * replays a captured CUDA graph of the cgraph instead, src/ggml-cuda.cu:2461-2709) for graphs whose compute nodes are
+ * MUL_MAT{Q4_0|Q8_0} x F32 with ONE activation column (ne11 == 1, 2-D weights, ne00 % 256 == 0, ne00 <= 32768).
+ * args[0..count) are executed with ggml's dataflow semantics: op j reads the result of the latest earlier op i whose
+ * dst_dev == args[j].src1_dev (and ne01 of i == ne00 of j), otherwise src1_dev is a vector produced outside the plan.
+ * One persistent CTA per SM walks the list; a producer thread per CTA streams the weights of op 0, 1, 2, ... back to
+ * back through a shared-memory ring (HBM never idles at an op boundary), and results travel between ops as tagged
+ * 8-byte elements, so there is no grid-wide barrier anywhere.  Results are bit-identical to `count` b200_mul_mat calls.
+ * Every dst_dev is still written as plain fp32 (may be NULL for intermediates nobody outside reads).
+ * B200_ERR_UNSUPPORTED: a shape outside the above, or plain vectors that alias each other (buffer reuse by a graph
+ * allocator) -- the caller then runs the nodes one by one through b200_mul_mat / b200_mul_mat_batch.
+ *
+ * Row-split plans (split != NULL, one process per GPU): args[i] describes THIS rank's row slice of op i (ne01 = local
+ * rows, src0 = local slice), split->row0[i] / m_total[i] place it in the whole matrix.  The tagged stores go to every
+ * rank's arena over NVLink (peer_arena[r] from b200_ipc_export/import of a zero-initialised b200_malloc'ed buffer of
+ * b200_plan_arena_bytes() on each rank), i.e. the all-gather is part of the GEMV epilogue.  dst_dev receives only the
+ * local rows unless the op carries B200_MM_EXPORT.  The LAST op of a row-split plan must carry B200_MM_EXPORT (that is
+ * also what keeps ranks within one token of each other). */
+typedef struct b200_plan b200_plan;
+typedef struct b200_plan_split {
+    int32_t        world, rank;
+    void          *peer_arena[B200_MAX_RANKS];
+    const int64_t *row0;      /* [count] */
+    const int64_t *m_total;   /* [count] */
+} b200_plan_split;
+B200_API size_t b200_plan_arena_bytes(const b200_mul_mat_args *args, int count, const b200_plan_split *split);
+B200_API int  b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, const b200_plan_split *split, b200_plan **out);
+B200_API int  b200_plan_launch(b200_ctx *ctx, b200_plan *plan);      /* asynchronous on the context's stream */
+B200_API void b200_plan_destroy(b200_plan *plan);
+/* device-side timeline of the last launch (plan created with env B200_PLAN_TRACE set): [nops + 1][grid][4] ns stamps
+ * (src1 complete, activations quantized, first weights landed, last row done; the last row holds per-CTA totals: ns the
+ * producer spent blocked on a full ring, ns one consumer warp spent blocked on an empty ring, ns spent in quantization
+ * phases); B200_ERR_UNSUPPORTED when not tracing */
+B200_API int  b200_plan_trace(b200_ctx *ctx, b200_plan *plan, unsigned long long *out_host, size_t capacity_u64, int *nops, int *grid);
 
 /* parity instrumentation: per-block int32 partial sums exactly as the kernels form them.
  * out_dev [n][m][k/32] int32.  path 0 = GEMV inner loop (dp4a), path 1 = GEMM (tcgen05 accumulators).

@@ -1,0 +1,115 @@
+"""Decode plans (b200_plan_*): a dependent sequence of decode mul_mats as one persistent launch, against the oracle
+(ggml_compute_forward_mul_mat, src/ggml.c:11808, applied node by node) and against the node-by-node CUDA path
+(bit-identical by construction)."""
+import numpy as np
+import pytest
+
+from conftest import Q4_0, Q8_0, MUL_MAT_NMSE_TOL, nmse
+
+pytestmark = pytest.mark.gpu
+
+
+def build_dag(oracle, qmm, ctx, qtype, nodes, seed):
+    """nodes: [(m, k, src)] with src = producing node or -1 (the outside vector)."""
+    rng = np.random.default_rng(seed)
+    ws = []
+    for i, (m, k, _) in enumerate(nodes):
+        w = rng.uniform(-1, 1, (m, k)).astype(np.float32) * (2.0 / np.sqrt(k))
+        wire = oracle.quantize_weights(qtype, w)
+        t = qmm.QTensor(ctx, qtype, k, m)
+        t.set(wire)
+        ws.append((t, wire))
+    return ws
+
+
+def run_oracle(oracle, qtype, nodes, ws, x):
+    outs = []
+    for i, (m, k, src) in enumerate(nodes):
+        cur = x if src < 0 else outs[src]
+        outs.append(oracle.mul_mat(qtype, ws[i][1], k, m, 1, 1, cur.reshape(1, 1, 1, k))[0, 0, 0])
+    return outs
+
+
+DAGS = {
+    # a GPT-J-like block pair at reduced width: q,k,v,fc_in <- x; o <- v; fc_out <- fc_in (k-split, G = 4); next block <- fc_out
+    "block_pair": [(512, 512, -1), (512, 512, -1), (512, 512, -1), (16384, 512, -1), (512, 512, 2), (512, 16384, 3),
+                   (512, 512, 5), (768, 512, 5), (1000, 512, 5), (8192, 512, 5), (512, 768, 7), (301, 8192, 9)],
+    # fewer rows than CTAs, odd row counts, a chain
+    "ragged_chain": [(1024, 256, -1), (7, 1024, 0), (256, 256, -1), (2049, 256, 2), (33, 256, 2), (4352, 256, 2), (5, 4352, 5)],
+    "single": [(4096, 4096, -1)],
+    # many same-input ops: no barrier between them, warps free-run around the ring for many laps
+    "free_run": [(4096, 4096, -1)] * 6 + [(2048, 4096, -1)] * 6 + [(1000, 4096, 0)] * 4,
+}
+
+
+@pytest.mark.parametrize("qtype", [Q4_0, Q8_0])
+@pytest.mark.parametrize("dag", sorted(DAGS))
+def test_plan_matches_oracle_and_node_by_node(gpu_ctx, oracle, qmm, qtype, dag):
+    nodes = DAGS[dag]
+    ws = build_dag(oracle, qmm, gpu_ctx, qtype, nodes, seed=len(nodes) * 7 + qtype)
+    rng = np.random.default_rng(99)
+    k0 = next(k for (_, k, s) in nodes if s < 0)
+    xs = {}
+    for (_, k, s) in nodes:
+        if s < 0 and k not in xs:
+            xs[k] = rng.uniform(-1, 1, k).astype(np.float32)
+    assert len(xs) == 1, "test DAGs use one outside vector"
+    x = xs[k0]
+    xd = gpu_ctx.to_device(x)
+    outs = [gpu_ctx.alloc(m * 4) for (m, _, _) in nodes]
+    for o in outs:
+        gpu_ctx._check(gpu_ctx.lib.b200_memset(gpu_ctx.h, o.ptr, 0xff, o.nbytes))
+    args = [gpu_ctx.make_args(ws[i][0], xd.ptr if s < 0 else outs[s].ptr, 1, outs[i].ptr) for i, (m, k, s) in enumerate(nodes)]
+    plan = gpu_ctx.plan_create(args)
+    try:
+        ref = run_oracle(oracle, qtype, nodes, ws, x)
+        for rep in range(3):          # replays: tags must stay unique from launch to launch
+            gpu_ctx.plan_launch(plan)
+        gpu_ctx.synchronize()
+        got = [outs[i].download(np.float32, nodes[i][0]) for i in range(len(nodes))]
+        for i in range(len(nodes)):
+            assert np.isfinite(got[i]).all(), f"node {i}"
+            assert nmse(got[i], ref[i]) <= MUL_MAT_NMSE_TOL, f"node {i}: nmse {nmse(got[i], ref[i])}"
+        # node by node through b200_mul_mat: same arithmetic, same summation order -> same bits
+        for o in outs:
+            gpu_ctx._check(gpu_ctx.lib.b200_memset(gpu_ctx.h, o.ptr, 0, o.nbytes))
+        for a in args:
+            gpu_ctx._check(gpu_ctx.lib.b200_mul_mat(gpu_ctx.h, a))
+        gpu_ctx.synchronize()
+        for i in range(len(nodes)):
+            assert np.array_equal(got[i], outs[i].download(np.float32, nodes[i][0])), f"node {i} differs from b200_mul_mat"
+        # a new input through the same plan
+        x2 = rng.uniform(-2, 2, k0).astype(np.float32)
+        xd.upload(x2)
+        gpu_ctx.plan_launch(plan)
+        gpu_ctx.synchronize()
+        ref2 = run_oracle(oracle, qtype, nodes, ws, x2)
+        last = len(nodes) - 1
+        assert nmse(outs[last].download(np.float32, nodes[last][0]), ref2[last]) <= MUL_MAT_NMSE_TOL
+    finally:
+        gpu_ctx.plan_destroy(plan)
+        xd.free()
+        for o in outs:
+            o.free()
+        for t, _ in ws:
+            t.free()
+
+
+def test_plan_rejects_what_it_cannot_run(gpu_ctx, oracle, qmm):
+    ws = build_dag(oracle, qmm, gpu_ctx, Q4_0, [(64, 256, -1), (64, 256, -1)], seed=1)
+    x = gpu_ctx.alloc(256 * 4)
+    y = gpu_ctx.alloc(64 * 4)
+    try:
+        a0 = gpu_ctx.make_args(ws[0][0], x.ptr, 1, y.ptr)
+        a1 = gpu_ctx.make_args(ws[1][0], x.ptr, 1, y.ptr)         # two nodes writing the same plain vector
+        with pytest.raises(qmm.B200Error) as e:
+            gpu_ctx.plan_create([a0, a1])
+        assert e.value.code == qmm.ERR_UNSUPPORTED
+        a2 = gpu_ctx.make_args(ws[1][0], x.ptr, 4, y.ptr)         # not a decode shape
+        with pytest.raises(qmm.B200Error) as e:
+            gpu_ctx.plan_create([a2])
+        assert e.value.code == qmm.ERR_UNSUPPORTED
+    finally:
+        x.free(); y.free()
+        for t, _ in ws:
+            t.free()
