@@ -8,11 +8,13 @@ dependencies (examples/gpt-j/main.cpp:462-551): per block q, k, v and fc_in read
 output (stand-in: v), fc_out reads fc_in; 28 blocks + lm_head 50400x4096 = 169 mul_mats, 3.287 GB of Q4_0 weights per
 token (inputs larger than L2, no flush needed), random-init weights made directly in the wire format.  A "step" = one
 token.  metric = tokens/s (BASELINE.json: "GPT-J-6B Q4_0 tok/s at 1/2/4/8 B200").
-  N = 1: the four same-input projections of a block go down as ONE launch (b200_mul_mat_batch), every launch has the
-         activation quantization fused in: 85 launches per token, replayed as one CUDA graph.
-  N > 1: every weight matrix is row-split across the ranks (total work fixed -> "scaling": "strong"); the dst slices
-         are exchanged by the GEMV epilogue itself (tagged 8-byte peer stores over NVLink, b200_mul_mat_gather) and checked
-         bit for bit against the NCCL all-gather path (--gather nccl selects that one).
+  default (--path plan): the whole token is ONE persistent launch (b200_plan_*): a producer thread per SM streams the
+         weights of op 0, 1, 2, ... back to back through a shared-memory ring, results travel between ops as tagged 8-byte
+         elements, the activation quantization is fused in.  N > 1: every weight matrix is row-split across the ranks
+         (total work fixed -> "scaling": "strong") and the tagged stores go to every rank over NVLink, i.e. the all-gather
+         of the dst slices is part of the GEMV epilogue.  Checked bit for bit against the launch-per-node path in every run.
+  --path launches: N = 1: one launch per same-input group (b200_mul_mat_batch), 85 per token, replayed as a CUDA graph;
+         N > 1: b200_mul_mat_gather per group (--gather fused) or kernel + NCCL all-gather per mul_mat (--gather nccl).
 At N = 1 the same JSON line also carries the other two parts of BASELINE.json's metric under "extra": the C1 decode GEMV
 (m=k=4096, n=1) in GB/s and the C2 prefill GEMM (m=11008, k=4096, n=512; q4_0 and q8_0) in int8 TOPS.
 
@@ -50,9 +52,15 @@ N_EMBD, N_LAYER, N_VOCAB, N_FF = 4096, 28, 50400, 16384
 # per block, in graph order, with the dependency structure of examples/gpt-j/main.cpp:462-551: q, k, v and fc_in all read the
 # block input (":534 this is independent of the self-attention result"), o reads the attention output (stand-in: v),
 # fc_out reads fc_in; the next block reads fc_out (stand-in for the residual sum, which is glue outside this path)
-LAYER_MATS = [("q", N_EMBD, N_EMBD), ("k", N_EMBD, N_EMBD), ("v", N_EMBD, N_EMBD), ("fc_in", N_FF, N_EMBD),
+# Node order inside a block is a topological order of that graph chosen so that a vector is needed as late as possible after
+# it is produced (fc_in first, v second: o and fc_out then find their inputs long finished; only fc_out -> next block is a
+# back-to-back dependency).  Every arm (ours, launch-per-group, the CPU reference) walks the same order.
+LAYER_MATS = [("fc_in", N_FF, N_EMBD), ("v", N_EMBD, N_EMBD), ("q", N_EMBD, N_EMBD), ("k", N_EMBD, N_EMBD),
               ("o", N_EMBD, N_EMBD), ("fc_out", N_EMBD, N_FF)]          # (name, m, k)
-WORKLOAD = "gptj6b_q4_0_decode_mul_mat_graph(28x[q,k,v,fc_in<-x; o<-v; fc_out<-fc_in]+lm_head 50400x4096, n=1)"
+WORKLOAD = "gptj6b_q4_0_decode_mul_mat_graph(28x[fc_in,v,q,k<-x; o<-v; fc_out<-fc_in]+lm_head 50400x4096, n=1)"
+if os.environ.get("B200_BENCH_ORDER") == "qkv_first":      # A/B runs only: the graph in the order of examples/gpt-j/main.cpp
+    LAYER_MATS = [LAYER_MATS[2], LAYER_MATS[3], LAYER_MATS[1], LAYER_MATS[0], LAYER_MATS[4], LAYER_MATS[5]]
+    WORKLOAD = "gptj6b_q4_0_decode_mul_mat_graph(28x[q,k,v,fc_in<-x; o<-v; fc_out<-fc_in]+lm_head 50400x4096, n=1)"
 
 
 def gptj_dag():
@@ -62,8 +70,9 @@ def gptj_dag():
         b = len(nodes)
         for name, m, k in LAYER_MATS[:4]:
             nodes.append((name, m, k, prev))
-        nodes.append(("o", N_EMBD, N_EMBD, b + 2))
-        nodes.append(("fc_out", N_EMBD, N_FF, b + 3))
+        names = [nm for nm, _, _ in LAYER_MATS]
+        nodes.append(("o", N_EMBD, N_EMBD, b + names.index("v")))
+        nodes.append(("fc_out", N_EMBD, N_FF, b + names.index("fc_in")))
         prev = b + 5
     nodes.append(("lm_head", N_VOCAB, N_EMBD, prev))
     return nodes
