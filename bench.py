@@ -547,7 +547,7 @@ def run_b200(args):
         tr = ROOT / "profiles" / "traffic.json"
         if tr.exists():
             try:
-                roofline["traffic"] = json.loads(tr.read_text()).get("gemv_q4_0_n1_bytes_per_launch")
+                roofline["traffic"] = json.loads(tr.read_text()).get("plan_q4_0_gptj_bytes_per_launch" if plan_fn is not None else "gemv_q4_0_n1_bytes_per_launch")
             except Exception:
                 pass
 

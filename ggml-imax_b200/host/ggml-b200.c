@@ -285,10 +285,22 @@ GGML_CALL ggml_backend_buffer_type_t ggml_backend_b200_host_buffer_type(void) {
 
 /* ---- backend --------------------------------------------------------------------------------- */
 
+/* a decode plan cached for a cgraph: valid while the graph's MUL_MAT nodes keep their addresses and shapes */
+#define B200_PLAN_CACHE 4
+struct b200_cached_plan {
+    uint64_t   key;        /* hash over (src0, src1, dst addresses, shapes) of the graph's MUL_MAT nodes; 0 = empty slot */
+    int        n_nodes;
+    b200_plan *plan;       /* NULL: this graph cannot run as a plan (remembered, so it is not analysed again) */
+};
+
 struct b200_backend_context {
     int       device;
     b200_ctx *ctx;
     char      name[32];
+    struct b200_cached_plan plans[B200_PLAN_CACHE];
+    int       plan_next;   /* round-robin eviction */
+    int       opt_plans;   /* 0: never build decode plans (env GGML_B200_NO_PLANS) */
+    int64_t   plan_launches;
 };
 
 static ggml_guid_t b200_backend_guid(void) {
@@ -311,6 +323,9 @@ GGML_CALL static const char *b200_backend_name(ggml_backend_t backend) {
 
 GGML_CALL static void b200_backend_free(ggml_backend_t backend) {
     struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
+    b200_synchronize(bc->ctx);
+    for (int i = 0; i < B200_PLAN_CACHE; i++)
+        if (bc->plans[i].plan) b200_plan_destroy(bc->plans[i].plan);
     b200_ctx_destroy(bc->ctx);
     free(bc);
     free(backend);
@@ -390,8 +405,83 @@ static enum ggml_status b200_compute_mul_mat_run(struct b200_backend_context *bc
     return GGML_STATUS_SUCCESS;
 }
 
+/*
+ * Decode graphs: when every compute node of the cgraph is a decode-shaped MUL_MAT (one activation column, 2-D weights), the
+ * whole graph goes down as ONE persistent launch (b200_plan_*, include/ggml_b200.h) -- what ggml_backend_graph_plan_create /
+ * _compute would be for this backend, done transparently and cached per graph like the reference's CUDA-graph replay
+ * (src/ggml-cuda.cu:2461-2709).  Returns 1 when the graph was computed that way, 0 when it has to go node by node (other
+ * shapes, or tensors that share memory as a graph allocator arranges them), -1 on a hard error.
+ */
+static int b200_try_graph_as_plan(struct b200_backend_context *bc, struct ggml_cgraph *cgraph) {
+    if (!bc->opt_plans) return 0;
+    int n = 0;
+    uint64_t key = 1469598103934665603ull;     /* FNV-1a */
+    for (int i = 0; i < cgraph->n_nodes; i++) {
+        struct ggml_tensor *node = cgraph->nodes[i];
+        if (ggml_is_empty(node) || b200_op_is_noop(node->op)) continue;
+        if (node->op != GGML_OP_MUL_MAT) return 0;
+        const struct ggml_tensor *a = node->src[0], *b = node->src[1];
+        if (!a || !b || b->ne[1] != 1 || b->ne[2] != 1 || b->ne[3] != 1 || a->ne[2] != 1 || a->ne[3] != 1) return 0;
+        const uint64_t words[6] = {(uint64_t)(uintptr_t)a->data, (uint64_t)(uintptr_t)b->data, (uint64_t)(uintptr_t)node->data,
+                                   (uint64_t)a->ne[0], (uint64_t)a->ne[1], (uint64_t)a->type};
+        for (int w = 0; w < 6; w++)
+            for (int sh = 0; sh < 64; sh += 8) key = (key ^ ((words[w] >> sh) & 0xff)) * 1099511628211ull;
+        n++;
+    }
+    if (n < 2) return 0;
+    if (key == 0) key = 1;
+    struct b200_cached_plan *slot = NULL;
+    for (int i = 0; i < B200_PLAN_CACHE; i++)
+        if (bc->plans[i].key == key && bc->plans[i].n_nodes == n) slot = &bc->plans[i];
+    if (!slot) {
+        slot = &bc->plans[bc->plan_next];
+        bc->plan_next = (bc->plan_next + 1) % B200_PLAN_CACHE;
+        if (slot->plan) {
+            b200_synchronize(bc->ctx);
+            b200_plan_destroy(slot->plan);
+        }
+        slot->key = key;
+        slot->n_nodes = n;
+        slot->plan = NULL;
+        b200_mul_mat_args *args = (b200_mul_mat_args *)malloc(sizeof(b200_mul_mat_args) * (size_t)n);
+        if (!args) return -1;
+        int k = 0;
+        bool ok = true;
+        for (int i = 0; i < cgraph->n_nodes && ok; i++) {
+            struct ggml_tensor *node = cgraph->nodes[i];
+            if (ggml_is_empty(node) || b200_op_is_noop(node->op)) continue;
+            ok = b200_mul_mat_supported(node) && b200_fill_mul_mat_args(node, &args[k++]);
+        }
+        if (ok) {
+            const int rc = b200_plan_create(bc->ctx, args, n, NULL, &slot->plan);
+            if (rc != B200_OK) {
+                slot->plan = NULL;     /* B200_ERR_UNSUPPORTED: node by node (remembered); anything else is reported below */
+                if (rc != B200_ERR_UNSUPPORTED) {
+                    fprintf(stderr, "ggml-b200: b200_plan_create failed (%d): %s\n", rc, b200_last_error(bc->ctx));
+                    free(args);
+                    return -1;
+                }
+            }
+        }
+        free(args);
+    }
+    if (!slot->plan) return 0;
+    const int rc = b200_plan_launch(bc->ctx, slot->plan);
+    if (rc != B200_OK) {
+        fprintf(stderr, "ggml-b200: b200_plan_launch failed (%d): %s\n", rc, b200_last_error(bc->ctx));
+        return -1;
+    }
+    bc->plan_launches++;
+    return 1;
+}
+
 GGML_CALL static enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, struct ggml_cgraph *cgraph) {
     struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
+    {
+        const int as_plan = b200_try_graph_as_plan(bc, cgraph);
+        if (as_plan < 0) return GGML_STATUS_FAILED;
+        if (as_plan > 0) return GGML_STATUS_SUCCESS;
+    }
     for (int i = 0; i < cgraph->n_nodes; i++) {
         struct ggml_tensor *node = cgraph->nodes[i];
         if (ggml_is_empty(node) || b200_op_is_noop(node->op)) continue;
@@ -450,6 +540,7 @@ GGML_CALL ggml_backend_t ggml_backend_b200_init(int device) {
     struct b200_backend_context *bc = (struct b200_backend_context *)calloc(1, sizeof(*bc));
     if (!bc) return NULL;
     bc->device = device;
+    bc->opt_plans = getenv("GGML_B200_NO_PLANS") ? 0 : 1;
     snprintf(bc->name, sizeof(bc->name), "%s%d", GGML_B200_NAME, device);
     if (b200_ctx_create(device, &bc->ctx) != B200_OK) {
         fprintf(stderr, "ggml-b200: %s\n", b200_last_error(NULL));
@@ -489,8 +580,17 @@ GGML_CALL int64_t ggml_backend_b200_launch_count(ggml_backend_t backend) {
     return b200_ctx_launch_count(((struct b200_backend_context *)backend->context)->ctx);
 }
 
+GGML_CALL int64_t ggml_backend_b200_plan_launch_count(ggml_backend_t backend) {
+    GGML_ASSERT(ggml_backend_is_b200(backend));
+    return ((struct b200_backend_context *)backend->context)->plan_launches;
+}
+
 GGML_CALL int ggml_backend_b200_set_option(ggml_backend_t backend, const char *key, int64_t value) {
     GGML_ASSERT(ggml_backend_is_b200(backend));
+    if (strcmp(key, "plans") == 0) {
+        ((struct b200_backend_context *)backend->context)->opt_plans = value != 0;
+        return B200_OK;
+    }
     return b200_ctx_set_option(((struct b200_backend_context *)backend->context)->ctx, key, value);
 }
 

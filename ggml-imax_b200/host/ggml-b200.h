@@ -34,7 +34,10 @@ GGML_API GGML_CALL void                       ggml_backend_b200_get_device_memor
 GGML_API GGML_CALL int                        ggml_backend_b200_reg_devices(void);             /* registers "B200", "B2001", ... */
 /* number of CUDA kernels the backend has launched (instrumentation for benches/tests) */
 GGML_API GGML_CALL int64_t                    ggml_backend_b200_launch_count(ggml_backend_t backend);
-/* forwards to b200_ctx_set_option (include/ggml_b200.h) */
+/* number of cgraphs computed as ONE persistent launch (decode plan, see graph_compute in ggml-b200.c) */
+GGML_API GGML_CALL int64_t                    ggml_backend_b200_plan_launch_count(ggml_backend_t backend);
+/* "plans" (0/1: compute all-decode-MUL_MAT cgraphs as one persistent launch); everything else forwards to
+ * b200_ctx_set_option (include/ggml_b200.h) */
 GGML_API GGML_CALL int                        ggml_backend_b200_set_option(ggml_backend_t backend, const char *key, int64_t value);
 
 #ifdef __cplusplus

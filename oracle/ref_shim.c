@@ -9,6 +9,7 @@
 #include "ggml-backend.h"
 
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -22,6 +23,27 @@ static void ref_init(void) {
     ggml_free(c);
     done = 1;
 }
+
+/* Which backend the graph helpers below run on: NULL = the reference CPU backend; otherwise a name from the reference's
+ * backend registry (src/ggml-backend.c:397-470).  The drop-in build of this file (_ref/libdropin_shim.so, linked against
+ * the reference core + our backend) uses "B2000" to run the very same ggml graph on the B200 backend. */
+static char g_backend_name[64] = "";
+void ref_select_backend(const char *name) { snprintf(g_backend_name, sizeof(g_backend_name), "%s", name ? name : ""); }
+static ggml_backend_t ref_backend_new(int n_threads) {
+    if (g_backend_name[0] == 0) {
+        ggml_backend_t b = ggml_backend_cpu_init();
+        ggml_backend_cpu_set_n_threads(b, n_threads);
+        return b;
+    }
+    const size_t n = ggml_backend_reg_get_count();
+    for (size_t i = 0; i < n; i++)
+        if (strcmp(ggml_backend_reg_get_name(i), g_backend_name) == 0) return ggml_backend_reg_init_backend(i, NULL);
+    fprintf(stderr, "ref_shim: backend %s is not in the registry\n", g_backend_name);
+    return NULL;
+}
+#ifdef REF_SHIM_DROPIN
+#include "ggml-b200.h"
+#endif
 
 /* runtime from_float of a type: type_traits[type].from_float (src/ggml.c:617-632, :697-712) */
 void ref_from_float(int type, const float *x, void *y, int64_t k) {
@@ -143,8 +165,8 @@ ref_chain *ref_chain_create(int type, int n_mats, const int *wid, int n_weights,
     h->out = cur;
     h->gf = ggml_new_graph_custom(h->ctx, (size_t)(n_mats + n_weights + 64), false);
     ggml_build_forward_expand(h->gf, h->out);
-    h->backend = ggml_backend_cpu_init();
-    ggml_backend_cpu_set_n_threads(h->backend, n_threads);
+    h->backend = ref_backend_new(n_threads);
+    if (!h->backend) return NULL;
     h->buf = ggml_backend_alloc_ctx_tensors(h->ctx, h->backend);
     return h;
 }
@@ -195,8 +217,18 @@ ref_chain *ref_dag_create(int type, int n_nodes, const int *node_w, const int *n
     }
     h->out = nodes[n_nodes - 1];
     free(nodes);
-    h->backend = ggml_backend_cpu_init();
-    ggml_backend_cpu_set_n_threads(h->backend, n_threads);
+    h->backend = ref_backend_new(n_threads);
+    if (!h->backend) return NULL;
     h->buf = ggml_backend_alloc_ctx_tensors(h->ctx, h->backend);
     return h;
 }
+
+/* any node of the last graph, by position in the cgraph (to compare intermediates between backends) */
+int ref_chain_n_nodes(ref_chain *h) { return h->gf->n_nodes; }
+int64_t ref_chain_node_elements(ref_chain *h, int i) { return ggml_nelements(h->gf->nodes[i]); }
+void ref_chain_get_node(ref_chain *h, int i, float *out) { ggml_backend_tensor_get(h->gf->nodes[i], out, 0, ggml_nbytes(h->gf->nodes[i])); }
+#ifdef REF_SHIM_DROPIN
+/* how many of the graph_compute calls on this handle's backend went down as one persistent launch (decode plan) */
+int64_t ref_chain_plan_launches(ref_chain *h) { return ggml_backend_is_b200(h->backend) ? ggml_backend_b200_plan_launch_count(h->backend) : -1; }
+int64_t ref_chain_kernel_launches(ref_chain *h) { return ggml_backend_is_b200(h->backend) ? ggml_backend_b200_launch_count(h->backend) : -1; }
+#endif
