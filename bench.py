@@ -636,6 +636,20 @@ def run_extras(torch, qmm, ctx, stream, P, args):
         gbs = by / (ms * 1e-3) / 1e9
         out[f"c1_gemv_{name}_m4096_k4096_n1"] = {"us_per_launch": round(ms * 1e3, 3), "GB/s": round(gbs, 1), "frac_of_hbm_peak": round(gbs / P["hbm_gbs"], 4),
                                                   "peak": P["hbm_gbs"], "l2": f"rotating over {nrot} distinct weight matrices ({nrot * by / 1e6:.0f} MB)"}
+        # the same 40 mul_mats as ONE decode plan (no launch boundaries): what the kernel streams when the caller hands it the
+        # sequence instead of one mul_mat at a time
+        try:
+            ys = torch.empty(nrot * m, dtype=torch.float32, device=dev)
+            pargs = [ctx.make_args(t, x.data_ptr(), 1, ys.data_ptr() + i * m * 4) for i, t in enumerate(ts)]
+            plan = ctx.plan_create(pargs)
+            ms_p = time_graph(lambda: ctx.plan_launch(plan), 20) / nrot
+            gbs_p = by / (ms_p * 1e-3) / 1e9
+            out[f"c1_gemv_{name}_m4096_k4096_n1"]["as_one_plan_of_40"] = {"us_per_mul_mat": round(ms_p * 1e3, 3), "GB/s": round(gbs_p, 1),
+                                                                         "frac_of_hbm_peak": round(gbs_p / P["hbm_gbs"], 4)}
+            torch.cuda.synchronize()
+            ctx.plan_destroy(plan)
+        except Exception as e:
+            out[f"c1_gemv_{name}_m4096_k4096_n1"]["as_one_plan_of_40"] = {"error": f"{type(e).__name__}: {e}"}
         del bufs, ts
 
     # ---- C2: m=11008 k=4096 n=512 (prefill)
