@@ -14,7 +14,7 @@ def build_dag(oracle, qmm, ctx, qtype, nodes, seed):
     rng = np.random.default_rng(seed)
     ws = []
     for i, (m, k, _) in enumerate(nodes):
-        w = rng.uniform(-1, 1, (m, k)).astype(np.float32) * (2.0 / np.sqrt(k))
+        w = rng.uniform(-1, 1, (m, k)).astype(np.float32) * np.float32(np.sqrt(3.0 / k))      # unit gain: deep chains stay O(1)
         wire = oracle.quantize_weights(qtype, w)
         t = qmm.QTensor(ctx, qtype, k, m)
         t.set(wire)
@@ -22,10 +22,13 @@ def build_dag(oracle, qmm, ctx, qtype, nodes, seed):
     return ws
 
 
-def run_oracle(oracle, qtype, nodes, ws, x):
+def run_oracle(oracle, qtype, nodes, ws, x, inputs=None):
+    """node i = W_i x src.  inputs = the vectors the device actually fed each node (per-node parity: a deep chain amplifies
+    the ~1e-9 summation-order differences through its quantization steps, which is not what is being tested); None = chain
+    the oracle's own outputs."""
     outs = []
     for i, (m, k, src) in enumerate(nodes):
-        cur = x if src < 0 else outs[src]
+        cur = x if src < 0 else (outs[src] if inputs is None else inputs[src])
         outs.append(oracle.mul_mat(qtype, ws[i][1], k, m, 1, 1, cur.reshape(1, 1, 1, k))[0, 0, 0])
     return outs
 
@@ -39,6 +42,10 @@ DAGS = {
     "single": [(4096, 4096, -1)],
     # many same-input ops: no barrier between them, warps free-run around the ring for many laps
     "free_run": [(4096, 4096, -1)] * 6 + [(2048, 4096, -1)] * 6 + [(1000, 4096, 0)] * 4,
+    # more ops than one shared-memory descriptor window (128) holds; op numbers above 127 in the tags
+    "many_ops": [(256, 256, -1)] + [(256, 256, i) for i in range(139)],
+    # k split over 8 warps (k > 16384): Llama-2-70B-like up / down at reduced m, and the largest k the path takes
+    "k_split_8": [(28672, 512, -1), (512, 28672, 0), (32768, 512, -1), (100, 32768, 2)],
 }
 
 
@@ -62,11 +69,11 @@ def test_plan_matches_oracle_and_node_by_node(gpu_ctx, oracle, qmm, qtype, dag):
     args = [gpu_ctx.make_args(ws[i][0], xd.ptr if s < 0 else outs[s].ptr, 1, outs[i].ptr) for i, (m, k, s) in enumerate(nodes)]
     plan = gpu_ctx.plan_create(args)
     try:
-        ref = run_oracle(oracle, qtype, nodes, ws, x)
         for rep in range(3):          # replays: tags must stay unique from launch to launch
             gpu_ctx.plan_launch(plan)
         gpu_ctx.synchronize()
         got = [outs[i].download(np.float32, nodes[i][0]) for i in range(len(nodes))]
+        ref = run_oracle(oracle, qtype, nodes, ws, x, inputs=got)
         for i in range(len(nodes)):
             assert np.isfinite(got[i]).all(), f"node {i}"
             assert nmse(got[i], ref[i]) <= MUL_MAT_NMSE_TOL, f"node {i}: nmse {nmse(got[i], ref[i])}"
@@ -76,16 +83,23 @@ def test_plan_matches_oracle_and_node_by_node(gpu_ctx, oracle, qmm, qtype, dag):
         for a in args:
             gpu_ctx._check(gpu_ctx.lib.b200_mul_mat(gpu_ctx.h, a))
         gpu_ctx.synchronize()
+        # (b200_mul_mat serves Q8_0 rows of k = 32768 with the generic GEMV, whose summation order differs: NMSE there)
+        exact = not (qtype == Q8_0 and dag == "k_split_8")
         for i in range(len(nodes)):
-            assert np.array_equal(got[i], outs[i].download(np.float32, nodes[i][0])), f"node {i} differs from b200_mul_mat"
+            one = outs[i].download(np.float32, nodes[i][0])
+            if exact:
+                assert np.array_equal(got[i], one), f"node {i} differs from b200_mul_mat"
+            else:
+                assert nmse(got[i], one) <= 1e-9, f"node {i}: nmse vs b200_mul_mat {nmse(got[i], one)}"
         # a new input through the same plan
         x2 = rng.uniform(-2, 2, k0).astype(np.float32)
         xd.upload(x2)
         gpu_ctx.plan_launch(plan)
         gpu_ctx.synchronize()
-        ref2 = run_oracle(oracle, qtype, nodes, ws, x2)
-        last = len(nodes) - 1
-        assert nmse(outs[last].download(np.float32, nodes[last][0]), ref2[last]) <= MUL_MAT_NMSE_TOL
+        got2 = [outs[i].download(np.float32, nodes[i][0]) for i in range(len(nodes))]
+        ref2 = run_oracle(oracle, qtype, nodes, ws, x2, inputs=got2)
+        for i in (0, len(nodes) // 2, len(nodes) - 1):
+            assert nmse(got2[i], ref2[i]) <= MUL_MAT_NMSE_TOL, f"second input, node {i}"
     finally:
         gpu_ctx.plan_destroy(plan)
         xd.free()
@@ -112,4 +126,48 @@ def test_plan_rejects_what_it_cannot_run(gpu_ctx, oracle, qmm):
     finally:
         x.free(); y.free()
         for t, _ in ws:
+            t.free()
+
+
+def test_plan_c5_full_size_llama70b_ffn(gpu_ctx, oracle, qmm):
+    """BASELINE.json C5 at full size: gate and up 28672 x 8192 read x, down 8192 x 28672 reads up (the gating product is glue
+    outside this path).  Bitwise against node-by-node b200_mul_mat, sampled rows against the oracle."""
+    E, F = 8192, 28672
+    shapes = [(F, E, -1), (F, E, -1), (E, F, 1)]
+    rng = np.random.default_rng(5)
+    ws, wires = [], []
+    for i, (m, k, _) in enumerate(shapes):
+        wire = qmm.random_wire_weights(Q4_0, k, m, seed=50 + i)
+        t = qmm.QTensor(gpu_ctx, Q4_0, k, m)
+        t.set(wire)
+        ws.append(t); wires.append(wire)
+    x = rng.uniform(-1, 1, E).astype(np.float32)
+    xd = gpu_ctx.to_device(x)
+    outs = [gpu_ctx.alloc(m * 4) for (m, _, _) in shapes]
+    args = [gpu_ctx.make_args(ws[i], xd.ptr if s < 0 else outs[s].ptr, 1, outs[i].ptr) for i, (m, k, s) in enumerate(shapes)]
+    plan = gpu_ctx.plan_create(args)
+    try:
+        gpu_ctx.plan_launch(plan)
+        gpu_ctx.plan_launch(plan)
+        gpu_ctx.synchronize()
+        got = [outs[i].download(np.float32, shapes[i][0]) for i in range(3)]
+        for o in outs:
+            gpu_ctx._check(gpu_ctx.lib.b200_memset(gpu_ctx.h, o.ptr, 0, o.nbytes))
+        for a in args:
+            gpu_ctx._check(gpu_ctx.lib.b200_mul_mat(gpu_ctx.h, a))
+        gpu_ctx.synchronize()
+        for i in range(3):
+            assert np.array_equal(got[i], outs[i].download(np.float32, shapes[i][0])), f"node {i} differs from b200_mul_mat"
+        # sampled rows of every node against the oracle on the same inputs
+        for i, (m, k, s) in enumerate(shapes):
+            rows = np.unique(np.concatenate([[0, 1, m - 1], rng.integers(0, m, 29)]))
+            src = x if s < 0 else got[s]
+            ref = oracle.mul_mat(Q4_0, np.ascontiguousarray(wires[i][rows]), k, len(rows), 1, 1, src.reshape(1, 1, 1, k))[0, 0, 0]
+            assert nmse(got[i][rows], ref) <= MUL_MAT_NMSE_TOL, f"node {i}: nmse {nmse(got[i][rows], ref)}"
+    finally:
+        gpu_ctx.plan_destroy(plan)
+        xd.free()
+        for o in outs:
+            o.free()
+        for t in ws:
             t.free()
