@@ -18,8 +18,11 @@
 //     arena): the GEMV epilogue stores them, the next op's activation loads re-read until every tag matches.  No grid
 //     barrier, no flags, no fences; with world > 1 the same stores go to every rank's arena over NVLink, which makes the
 //     all-gather of a row-split mul_mat part of the epilogue;
-//   * consecutive ops that read the same vector (q, k, v, fc_in) share one activation quantization: the lane's int8
-//     activation blocks simply stay in registers.
+//   * consumers: 8 warps; a ring slot (8 rows of a 4096-wide k-segment) always belongs to the same team of warps (one warp for
+//     k <= 4096), which turns the whole slot into results: up to four rows' loads in flight, exact dp4a block dots against
+//     the quantized src1 in shared memory, four row sums reduced together by a transposed butterfly;
+//   * consecutive ops that read the same vector (fc_in, v, q, k) share one activation quantization (two shared-memory buffers,
+//     so a new src1 can be quantized while rows of the previous one are still running in other warps).
 #include "b200_stream_common.cuh"
 
 #include <stdlib.h>
@@ -32,17 +35,14 @@ namespace {
 
 constexpr int kCW = 8;                       // consumer warps
 constexpr int kCT = kCW * 32;                // consumer threads
-constexpr int kAW = 3;                       // activation warps (registers are allocated per 4 warps: 8 + 1 + 3 = 12 costs nothing)
-constexpr int kAT = kAW * 32;
-constexpr int kPlanThreads = (kCW + 1 + kAW) * 32;   // consumers, the producer warp, activation warps
-constexpr int kInCap = 128;                  // early-input descriptors staged in shared memory per window
+constexpr int kPlanThreads = (kCW + 1) * 32;         // consumers + the producer warp
 constexpr int kSegBlocks = 128;              // blocks of k per warp-segment (4 per lane)
 constexpr int kMaxSlots = 24;
 constexpr int kPartFloats = 4096;            // k-split partials parked per CTA per op: rows_per_cta * G (aliases the LL staging)
 constexpr int kMaxOps = 1023;
 constexpr int kDescCap = 128;                // op descriptors staged in shared memory per window
 
-enum : int { OPF_SAME_INPUT = 1, OPF_WRITE_LL = 2, OPF_EXPORT = 4, OPF_EARLY_INPUT = 8 };
+enum : int { OPF_SAME_INPUT = 1, OPF_WRITE_LL = 2, OPF_EXPORT = 4 };
 
 struct __align__(16) PDesc {                 // what the producer needs of an op
     const uint8_t *qs;       // qs plane, first row of this rank's slice
@@ -61,15 +61,6 @@ struct __align__(16) CDesc {                 // what the consumers need (staged 
     int src_op, row0;        // producing op or -1; global row of local row 0
 };
 static_assert(sizeof(CDesc) == 48, "CDesc layout");
-struct __align__(16) InDesc {                // one EARLY src1 vector (see OPF_EARLY_INPUT), in the order the activation warps make them
-    const float *src_plain;  // outside vector (src_op < 0)
-    int ll_src;              // element offset of the producer's LL vector
-    int src_op;              // producing op or -1
-    int nb;                  // k / 32
-    int cons_idx;            // position in the order the consumers read early inputs: buffer = cons_idx % nactb
-    int pad[2];
-};
-static_assert(sizeof(InDesc) == 32, "InDesc layout");
 struct ExportDesc {
     float *dst;
     int ll, m_total, op, pad;
@@ -78,15 +69,14 @@ struct ExportDesc {
 struct PlanGeom {
     int slot_bytes, nslots;
     int l2_ahead;            // ops: when the producer starts op i it prefetches its rows of op i + l2_ahead into L2 (0 = off)
-    int ring_off, act_off, actb_off, actb_stride, nactb, ll_off, all_off, desc_off, in_off, bar_off, total;
+    int ring_off, act_off, act_stride, ll_off, desc_off, bar_off, total;   // act: two buffers of act_stride bytes
 };
 
 struct PlanArgs {
     const PDesc *pdesc;
     const CDesc *cdesc;
     const ExportDesc *exports;
-    const InDesc *inputs;
-    int nops, nexports, ninputs;
+    int nops, nexports;
     int world, rank;
     void *arena[B200_MAX_RANKS];   // [rank] local; LL vectors live at the same offsets on every rank
     uint32_t *state;               // {arrived CTAs, completed launches}
@@ -127,9 +117,10 @@ __device__ __forceinline__ OpGeom op_geom(int k, int slot_bytes) {
 // everything a warp needs to turn rows of a ring slot into results
 template <int TYPE>
 struct RowCtx {
-    uint4 alo[4], ahi[4];     // the lane's activation blocks b0 + lane + 32 i (int8), resident across same-input ops
-    float da[4];
-    int s8[4];
+    // shared-window addresses of the lane's first block (b0 + lane; blocks i = 1..3 are 32 blocks further each) in the planes
+    // of the current quantized src1: int8 elements 0..15 / 16..31 of every block, fp32 scale, 8 * sum(q).  (Reading them per
+    // row instead of keeping 40 registers resident leaves room for four rows' loads in flight: measured 5.9 vs 5.4 TB/s.)
+    uint32_t a_lo, a_hi, a_d, a_s;
     bool blive[4];
     uint32_t woff0, soff0;    // lane offsets inside a row / inside the scale area
     int row_qs, row_sc;
@@ -141,9 +132,12 @@ __device__ __forceinline__ float row_dots(const RowCtx<TYPE> &c, const uint4 (&w
     float a = 0.0f;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const int sumi = block_dot<TYPE>(w0[i], w1[i], c.alo[i], c.ahi[i], c.s8[i]);
+        const uint4 alo = lds128(c.a_lo + (uint32_t)(i * 512)), ahi = lds128(c.a_hi + (uint32_t)(i * 512));
+        const float da = lds_f32(c.a_d + (uint32_t)(i * 128));
+        const int s8 = TYPE == B200_TYPE_Q4_0 ? lds_s32(c.a_s + (uint32_t)(i * 128)) : 0;
+        const int sumi = block_dot<TYPE>(w0[i], w1[i], alo, ahi, s8);
         const float dw = __half2float(__ushort_as_half(sc[i]));
-        if (c.blive[i]) a = fmaf((float)sumi, dw * c.da[i], a);
+        if (c.blive[i]) a = fmaf((float)sumi, dw * da, a);
     }
     return a;
 }
@@ -153,7 +147,7 @@ __device__ __forceinline__ float row_dots(const RowCtx<TYPE> &c, const uint4 (&w
 template <int TYPE, int NR>
 __device__ __forceinline__ float chunk_rows(const RowCtx<TYPE> &c, uint32_t stage_a, int r, int rows, int lane) {
     constexpr int QSB = TYPE == B200_TYPE_Q4_0 ? 16 : 32;
-    constexpr int NU = NR >= 2 ? 2 : 1;       // rows whose loads are in flight together
+    constexpr int NU = NR >= 4 ? 4 : (NR >= 2 ? 2 : 1);       // rows whose loads are in flight together
     float acc[NR];
 #pragma unroll
     for (int h = 0; h < NR; h += NU) {
@@ -230,143 +224,6 @@ __device__ __forceinline__ void ll_fetch_warp(const char *wbase, int nvalid, uin
     __syncwarp();
 }
 
-// 16 floats of lane-task tt (block tt / 2, half tt % 2) -> int8 + scale (+ 8 * sum for Q4_0) in the activation buffer:
-// quantize_row_q8_0 (src/ggml-quants.c:535-618), bit-exact; lanes tt and tt ^ 1 share a block
-template <int TYPE>
-__device__ __forceinline__ void quantize_task(const float4 (&v)[4], int tt, int tpc, int k, int nb, unsigned char *act) {
-    const bool live = tt < tpc;
-    const int t = live ? tt : tpc - 1;
-    const int b = t >> 1, h = t & 1;
-    float amax = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 4; j++) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
-    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-    const float id = amax != 0.0f ? __fdiv_rn(127.f, amax) : 0.0f;
-    uint32_t pk[4];
-    int sq = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int q0 = __float2int_rn(__fmul_rn(v[j].x, id)), q1 = __float2int_rn(__fmul_rn(v[j].y, id));
-        const int q2 = __float2int_rn(__fmul_rn(v[j].z, id)), q3 = __float2int_rn(__fmul_rn(v[j].w, id));
-        sq += q0 + q1 + q2 + q3;
-        pk[j] = (uint32_t)(q0 & 0xff) | ((uint32_t)(q1 & 0xff) << 8) | ((uint32_t)(q2 & 0xff) << 16) | ((uint32_t)(q3 & 0xff) << 24);
-    }
-    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-    if (live) {
-        *reinterpret_cast<uint4 *>(act + (size_t)h * (k >> 1) + (size_t)b * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        if (h == 0) {
-            reinterpret_cast<float *>(act + k)[b] = __half2float(__float2half_rn(__fdiv_rn(amax, 127.f)));
-            if (TYPE == B200_TYPE_Q4_0) reinterpret_cast<int *>(act + k + (size_t)nb * 4)[b] = 8 * sq;
-        }
-    }
-}
-
-// ===== activation warps: src1 vectors that are complete long before their first consumer op (OPF_EARLY_INPUT) are fetched and
-// quantized HERE, ahead of the consumers and off their path, into buffers of their own.  A function of its own so that its
-// registers (96 of loads in flight) are allocated separately from the consumers' resident activation blocks. =====
-template <int TYPE>
-__device__ __noinline__ void act_warps_main(const PlanArgs &pa, const PlanGeom &pg, unsigned char *smem, uint64_t *act_full, uint64_t *act_empty,
-                                            uint32_t epoch, const char *arena_local, int warp, int lane) {
-    const int aw = warp - (kCW + 1);
-    InDesc *sin = reinterpret_cast<InDesc *>(smem + pg.in_off);
-    float *llstage = reinterpret_cast<float *>(smem + pg.all_off) + aw * 512;
-    const int nactb = pg.nactb;
-#pragma unroll 1
-    for (int inp = 0; inp < pa.ninputs; inp++) {
-        const int ii = inp & (kInCap - 1);
-        if (ii == 0) {
-            asm volatile("bar.sync 2, %0;" ::"n"(kAT) : "memory");
-            const int n = min(kInCap, pa.ninputs - inp);
-            for (int t = aw * 32 + lane; t < 2 * n; t += kAT) reinterpret_cast<uint4 *>(sin)[t] = reinterpret_cast<const uint4 *>(pa.inputs + inp)[t];
-            asm volatile("bar.sync 2, %0;" ::"n"(kAT) : "memory");
-        }
-        const InDesc in = sin[ii];
-        const int nb = in.nb, k = nb << 5;
-        const int src_op = in.src_op;
-        const bool ll_in = src_op >= 0;
-        const uint32_t src_tag = (epoch << 10) | (uint32_t)(src_op & 1023);
-        const char *xsrc = ll_in ? arena_local + (size_t)in.ll_src * 8 : reinterpret_cast<const char *>(in.src_plain);
-        const int buf = nactb == 2 ? (in.cons_idx & 1) : 0;
-        const uint32_t use = (uint32_t)(nactb == 2 ? (in.cons_idx >> 1) : in.cons_idx);    // earlier fills of this buffer
-        unsigned char *act = smem + pg.actb_off + buf * pg.actb_stride;
-        mbar_wait(&act_empty[buf], (use & 1u) ^ 1u);     // the consumers have the previous contents in registers
-        const int tpc = nb * 2;                  // lane-tasks: (block, half) = 16 consecutive floats
-        const int nruns = (tpc + 31) >> 5;       // a run = 32 lane-tasks = 512 consecutive elements = one warp-load
-        constexpr int kRuns = 3;                 // runs per warp whose loads are in flight together
-#pragma unroll 1
-        for (int rbase = 0; rbase < nruns; rbase += kAW * kRuns) {
-            if (ll_in) {
-                uint4 w[kRuns][8];
-                int last_run = -1;
-#pragma unroll
-                for (int u = 0; u < kRuns; u++)
-                    if (rbase + u * kAW + aw < nruns) last_run = rbase + u * kAW + aw;
-                if (last_run < 0) continue;
-                for (;;) {
-                    bool ok = true;
-#pragma unroll
-                    for (int u = 0; u < kRuns; u++) {
-                        const int run = rbase + u * kAW + aw;
-                        if (run < nruns) {
-                            const int nv8 = min(32, tpc - run * 32) * 8;
-                            const char *wbase = xsrc + (size_t)run * 4096;
-#pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                const int idx = j * 32 + lane < nv8 ? j * 32 + lane : 0;
-                                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                             : "=r"(w[u][j].x), "=r"(w[u][j].y), "=r"(w[u][j].z), "=r"(w[u][j].w) : "l"(wbase + (size_t)idx * 16));
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < kRuns; u++)
-                        if (rbase + u * kAW + aw < nruns) {
-#pragma unroll
-                            for (int j = 0; j < 8; j++) ok = ok && w[u][j].y == src_tag && w[u][j].w == src_tag;
-                        }
-                    if (__all_sync(0xffffffffu, ok)) break;
-                    ll_probe(xsrc + (size_t)min(tpc, (last_run + 1) * 32) * 128 - 8, src_tag);
-                }
-#pragma unroll
-                for (int u = 0; u < kRuns; u++) {
-                    const int run = rbase + u * kAW + aw;
-                    if (run >= nruns) continue;                 // warp-uniform
-                    const int nv8 = min(32, tpc - run * 32) * 8;
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        if (j * 32 + lane < nv8)
-                            *reinterpret_cast<float2 *>(llstage + 2 * (j * 32 + lane)) = make_float2(__uint_as_float(w[u][j].x), __uint_as_float(w[u][j].z));
-                    __syncwarp();
-                    float4 v[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) v[j] = *reinterpret_cast<const float4 *>(llstage + lane * 16 + j * 4);
-                    __syncwarp();
-                    quantize_task<TYPE>(v, run * 32 + lane, tpc, k, nb, act);
-                }
-            } else {
-                float4 v[kRuns][4];
-#pragma unroll
-                for (int u = 0; u < kRuns; u++) {
-                    const int run = rbase + u * kAW + aw;
-                    if (run >= nruns) continue;
-                    const int t = min(run * 32 + lane, tpc - 1);
-                    const float4 *src = reinterpret_cast<const float4 *>(xsrc) + (size_t)t * 4;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) v[u][j] = src[j];
-                }
-#pragma unroll
-                for (int u = 0; u < kRuns; u++) {
-                    const int run = rbase + u * kAW + aw;
-                    if (run >= nruns) continue;
-                    quantize_task<TYPE>(v[u], run * 32 + lane, tpc, k, nb, act);
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&act_full[buf]);
-    }
-}
-
 template <int TYPE>
 __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_constant__ PlanArgs pa, const __grid_constant__ PlanGeom pg) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -377,18 +234,12 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
     unsigned char *ring = smem + pg.ring_off;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + pg.bar_off);
     uint64_t *empty_bar = full_bar + kMaxSlots;
-    uint64_t *act_full = empty_bar + kMaxSlots;      // [2] activation warps -> consumers
-    uint64_t *act_empty = act_full + 2;              // [2] consumers -> activation warps
-    uint32_t *s_epoch = reinterpret_cast<uint32_t *>(act_empty + 2);
+    uint32_t *s_epoch = reinterpret_cast<uint32_t *>(empty_bar + kMaxSlots);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < pg.nslots; s++) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], kCW);       // a slot's consumers (one team of G warps) arrive with 8/G each
-        }
-        for (int b = 0; b < 2; b++) {
-            mbar_init(&act_full[b], kAW);
-            mbar_init(&act_empty[b], kCW);
         }
         *s_epoch = pa.state[1] + 1u;    // every CTA reads it before any CTA can finish (the bump needs all of them)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -454,25 +305,22 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
             }
             if (pa.trace) pa.trace[(size_t)pa.nops * gridDim.x * 4 + (size_t)cta * 4 + 0] = prod_blocked;
         }
-    } else if (warp > kCW) {
-        act_warps_main<TYPE>(pa, pg, smem, act_full, act_empty, epoch, arena_local, warp, lane);
     } else {
         // ===== consumers =====
         const uint32_t ring_a = smem_u32(ring);
         const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
         CDesc *sdesc = reinterpret_cast<CDesc *>(smem + pg.desc_off);
-        unsigned char *act = smem + pg.act_off;
-        const uint32_t act_a = smem_u32(act);
+        int act_sel = 1;            // which of the two activation buffers holds the current src1
         float *llstage = reinterpret_cast<float *>(smem + pg.ll_off) + warp * 512;
         float *part = reinterpret_cast<float *>(smem + pg.ll_off);      // same bytes, other phase (bar.sync in between)
         int st0 = 0;                // ring position of the op's first stage
         uint32_t par0 = 0;
-        int ebuf = 0, prevG = 1;    // early-input buffer to read next / how often it has been read before
-        uint32_t euse = 0;
+        int prevG = 1;
         unsigned long long cons_blocked = 0, quant_time = 0;
         RowCtx<TYPE> c;
+        c.a_lo = c.a_hi = c.a_d = c.a_s = smem_u32(smem + pg.act_off);
 #pragma unroll
-        for (int i = 0; i < 4; i++) { c.alo[i] = c.ahi[i] = make_uint4(0, 0, 0, 0); c.da[i] = 0.0f; c.s8[i] = 0; c.blive[i] = false; }
+        for (int i = 0; i < 4; i++) c.blive[i] = false;
 
 #pragma unroll 1
         for (int op = 0; op < pa.nops; op++) {
@@ -505,37 +353,15 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
                 cbar();
                 prevG = G;
             }
-            if (!(flags & OPF_SAME_INPUT) && (flags & OPF_EARLY_INPUT)) {
-                // ---- a new src1 that the activation warps have (or will have) ready: pick the lane's blocks up ----
+            if (!(flags & OPF_SAME_INPUT)) {
+                // ---- a new src1: all 8 consumer warps fetch and quantize it (quantize_row_q8_0, bit-exact, same code path as
+                // gemv_stream_kernel) into one of two shared-memory buffers ----
                 const unsigned long long tq0 = tr ? gtime() : 0ull;
-                const uint32_t eb_a = smem_u32(smem + pg.actb_off + ebuf * pg.actb_stride);
-                mbar_wait(&act_full[ebuf], euse & 1u);
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const uint32_t b = (uint32_t)min(b0 + lane + 32 * i, nb - 1);
-                    c.alo[i] = lds128(eb_a + b * 16);
-                    c.ahi[i] = lds128(eb_a + (uint32_t)(k >> 1) + b * 16);
-                    c.da[i] = lds_f32(eb_a + (uint32_t)k + b * 4);
-                    c.s8[i] = TYPE == B200_TYPE_Q4_0 ? lds_s32(eb_a + (uint32_t)k + (uint32_t)nb * 4 + b * 4) : 0;
-                    c.blive[i] = b0 + lane + 32 * i < nb;
-                }
-                // the buffer may be overwritten as soon as act_empty completes: make every lane's loads RETURN first (a warp
-                // vote on a value that depends on all of them cannot issue before they have)
-                {
-                    uint32_t dep = 0;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) dep |= c.alo[i].x | c.ahi[i].x | __float_as_uint(c.da[i]) | (uint32_t)c.s8[i];
-                    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %0, 0x7fffffff;\n\tvote.sync.any.pred p, p, 0xffffffff;\n\t}" ::"r"(dep) : "memory");
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&act_empty[ebuf]);
-                if (++ebuf == pg.nactb) { ebuf = 0; euse++; }
-                if (tr && threadIdx.x == 0) tr[1] = gtime();
-                if (tr) quant_time += gtime() - tq0;
-            } else if (!(flags & OPF_SAME_INPUT)) {
-                // ---- a src1 finished just before this op: all 8 consumer warps fetch and quantize it themselves (shortest
-                // path from the last tagged store to the first dot product) ----
-                const unsigned long long tq0 = tr ? gtime() : 0ull;
+                // two buffers: rows of the previous input may still be running in other warps; the barrier after THIS
+                // quantization guarantees they are done before that buffer is written again two inputs later
+                act_sel ^= 1;
+                unsigned char *act = smem + pg.act_off + act_sel * pg.act_stride;
+                const uint32_t act_a = smem_u32(act);
                 const int src_op = o->src_op;
                 const bool ll_in = src_op >= 0;
                 const uint32_t src_tag = (epoch << 10) | (uint32_t)(src_op & 1023);
@@ -593,16 +419,15 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
                     }
                 }
                 cbar();
+                {
+                    const uint32_t b = (uint32_t)(b0 + lane);       // (dead lanes read past nb into the next plane: predicated off)
+                    c.a_lo = act_a + b * 16;
+                    c.a_hi = act_a + (uint32_t)(k >> 1) + b * 16;
+                    c.a_d = act_a + (uint32_t)k + b * 4;
+                    c.a_s = act_a + (uint32_t)k + (uint32_t)nb * 4 + b * 4;
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const uint32_t b = (uint32_t)min(b0 + lane + 32 * i, nb - 1);
-                    c.alo[i] = lds128(act_a + b * 16);
-                    c.ahi[i] = lds128(act_a + (uint32_t)(k >> 1) + b * 16);
-                    c.da[i] = lds_f32(act_a + (uint32_t)k + b * 4);
-                    c.s8[i] = TYPE == B200_TYPE_Q4_0 ? lds_s32(act_a + (uint32_t)k + (uint32_t)nb * 4 + b * 4) : 0;
-                    c.blive[i] = b0 + lane + 32 * i < nb;
+                    for (int i = 0; i < 4; i++) c.blive[i] = b0 + lane + 32 * i < nb;
                 }
-                cbar();     // every warp holds its blocks in registers: the next quantization may overwrite `act`
                 if (tr && threadIdx.x == 0) tr[1] = gtime();
                 if (tr) quant_time += gtime() - tq0;
             }
@@ -728,7 +553,6 @@ struct b200_plan {
     PDesc *pdesc_dev;
     CDesc *cdesc_dev;
     ExportDesc *exports_dev;
-    InDesc *inputs_dev;
     void *arena_own;            // allocated here when world == 1
     uint32_t *state_dev;
     unsigned long long *trace_dev;
@@ -763,7 +587,6 @@ void b200_plan_destroy(b200_plan *p) {
     if (p->pdesc_dev) cudaFree(p->pdesc_dev);
     if (p->cdesc_dev) cudaFree(p->cdesc_dev);
     if (p->exports_dev) cudaFree(p->exports_dev);
-    if (p->inputs_dev) cudaFree(p->inputs_dev);
     if (p->arena_own) cudaFree(p->arena_own);
     if (p->state_dev) cudaFree(p->state_dev);
     if (p->trace_dev) cudaFree(p->trace_dev);
@@ -798,16 +621,7 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     std::vector<CDesc> cd((size_t)count);
     std::vector<int> m_total((size_t)count);
     std::vector<ExportDesc> ex;
-    std::vector<InDesc> ins;
-    std::vector<double> wbytes((size_t)count + 1, 0.0);    // prefix sums of this rank's weight bytes
-    int kmax = 0, kmax_early = 0, kmax_late = 0;
-    // Measured on the GPT-J graph (profiles/r01_plan_experiments.md): handing early vectors to the three activation warps is
-    // SLOWER than letting the eight consumer warps fetch every vector themselves (1152 vs 1245 tokens/s): under full streaming
-    // load a dependent L2 round trip costs ~1 us and three warps cannot keep enough loads in flight.  Off unless asked for.
-    const bool use_act_warps = getenv("B200_PLAN_ACT_WARPS") != NULL;
-    // a vector counts as EARLY when the ops between its producer and its first consumer stream at least this much (~2.5 us of
-    // HBM): then the activation warps have it quantized before the consumers ask for it
-    const double early_bytes = 16e6;
+    int kmax = 0;
     for (int i = 0; i < count; i++) {
         const b200_mul_mat_args *a = &args[i];
         // decode shapes the streaming kernels take; anything else is the caller's node-by-node path
@@ -868,29 +682,9 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
             break;
         }
         if (c.src_op < 0) B200_REQUIRE(ctx, ((uintptr_t)a->src1_dev & 15) == 0, B200_ERR_UNSUPPORTED);
-        wbytes[i + 1] = wbytes[i] + (double)a->ne01 * (double)nb * (qsb + 2);
-        // ops that read the vector the previous op read keep the activation blocks in registers
+        // ops that read the vector the previous op read keep using the quantized activations already in shared memory
         if (i > 0 && c.k == cd[i - 1].k && c.src_op == cd[i - 1].src_op && (c.src_op >= 0 || c.src_plain == cd[i - 1].src_plain))
             c.flags |= OPF_SAME_INPUT;
-        if (!(c.flags & OPF_SAME_INPUT)) {
-            // (only vectors the three activation warps fetch in ONE round of loads, k <= 4608: a longer vector costs them a memory
-            //  round trip per 4608 elements under full streaming load, more than the 8 consumer warps need for all of it)
-            const bool early = use_act_warps && (c.k + 511) / 512 <= kAW * 3 && (c.src_op < 0 || wbytes[i] - wbytes[c.src_op + 1] >= early_bytes);
-            if (early) {
-                c.flags |= OPF_EARLY_INPUT;
-                InDesc in;
-                memset(&in, 0, sizeof(in));
-                in.src_plain = c.src_plain;
-                in.ll_src = c.ll_src;
-                in.src_op = c.src_op;
-                in.nb = c.k / 32;
-                in.cons_idx = (int)ins.size();
-                ins.push_back(in);
-                if (c.k > kmax_early) kmax_early = c.k;
-            } else if (c.k > kmax_late) {
-                kmax_late = c.k;
-            }
-        }
     }
     // Hazards sequential execution would hide but dataflow execution does not: plain dst vectors that alias each other or an
     // outside input (buffer reuse by a graph allocator).  Those graphs stay on the node-by-node path.
@@ -918,49 +712,30 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     g.slot_bytes = slot_bytes;
     g.l2_ahead = 0;
     if (const char *e = getenv("B200_PLAN_L2_AHEAD")) { const int v = atoi(e); if (v >= 0 && v <= 31) g.l2_ahead = v; }
-    auto act_size = [](int k) { return k > 0 ? (int)b200_align_up((size_t)k + (size_t)(k / 32) * 8, 128) : 128; };
-    const int act_bytes = act_size(kmax_late);                  // quantized by the consumers themselves
-    const int actb_bytes = act_size(kmax_early);                // quantized by the activation warps (1 or 2 buffers)
-    const int ll_bytes = kCW * 2048 > kPartFloats * 4 ? kCW * 2048 : kPartFloats * 4;
-    const int all_bytes = kAW * 2048;
+    const int act_bytes = (int)b200_align_up((size_t)kmax + (size_t)(kmax / 32) * 8, 128);   // int8 planes + fp32 scales + 8 * sums
+    const int ll_bytes = kCW * 2048 > kPartFloats * 4 ? kCW * 2048 : kPartFloats * 4;       // LL staging, aliased by the k-split partials
     const int desc_bytes = kDescCap * (int)sizeof(CDesc);
-    const int in_bytes = kInCap * (int)sizeof(InDesc);
-    const int bar_bytes = (2 * kMaxSlots + 4) * 8 + 64;
+    const int bar_bytes = 2 * kMaxSlots * 8 + 64;
     const int max_smem = 227 * 1024;
-    const int fixed = act_bytes + ll_bytes + all_bytes + desc_bytes + in_bytes + bar_bytes;
-    // ring: as many slots as fit beside ONE early buffer, a multiple of the consumer warps when possible (every warp then owns
-    // the same number of slots); a second early buffer if there is still room
-    int nslots = (max_smem - fixed - actb_bytes) / g.slot_bytes;
+    const int fixed = 2 * act_bytes + ll_bytes + desc_bytes + bar_bytes;
+    // ring: as many slots as fit, a multiple of the consumer warps when possible (every warp then owns the same number)
+    int nslots = (max_smem - fixed) / g.slot_bytes;
     if (nslots > kMaxSlots) nslots = kMaxSlots;
     if (nslots >= kCW) nslots = nslots / kCW * kCW;
-    if (const char *e = getenv("B200_PLAN_SLOTS")) { const int v = atoi(e); if (v >= 2 && v <= kMaxSlots && v * g.slot_bytes <= max_smem - fixed - actb_bytes) nslots = v; }
+    if (const char *e = getenv("B200_PLAN_SLOTS")) { const int v = atoi(e); if (v >= 2 && v <= kMaxSlots && v * g.slot_bytes <= max_smem - fixed) nslots = v; }
     if (nslots < 2) { free(p); b200_set_error(ctx, "b200_plan_create: k = %d leaves no room for the weight ring", kmax); return B200_ERR_UNSUPPORTED; }
     g.nslots = nslots;
-    g.nactb = (max_smem - fixed - nslots * g.slot_bytes) >= 2 * actb_bytes ? 2 : 1;
     g.ring_off = 0;
     g.act_off = nslots * g.slot_bytes;
-    g.actb_off = g.act_off + act_bytes;
-    g.actb_stride = actb_bytes;
-    g.ll_off = g.actb_off + g.nactb * actb_bytes;
-    g.all_off = g.ll_off + ll_bytes;
-    g.desc_off = g.all_off + all_bytes;
-    g.in_off = g.desc_off + desc_bytes;
-    g.bar_off = g.in_off + in_bytes;
+    g.act_stride = act_bytes;
+    g.ll_off = g.act_off + 2 * act_bytes;
+    g.desc_off = g.ll_off + ll_bytes;
+    g.bar_off = g.desc_off + desc_bytes;
     g.total = g.bar_off + bar_bytes;
 
-    // The activation warps make early inputs in the order they become AVAILABLE where that is safe: with two buffers, input e + 1
-    // may be made before input e (never before e - 1: its buffer is the one e - 1 still occupies).  E.g. fc_out's input (fc_in,
-    // finished first) before o's input (v).
-    for (size_t e = 0; g.nactb == 2 && e + 1 < ins.size(); e++)
-        if (ins[e + 1].src_op < ins[e].src_op) {
-            std::swap(ins[e], ins[e + 1]);
-            e++;
-        }
     cudaError_t e = cudaMalloc((void **)&p->pdesc_dev, sizeof(PDesc) * (size_t)count);
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->cdesc_dev, sizeof(CDesc) * (size_t)count);
     if (e == cudaSuccess && !ex.empty()) e = cudaMalloc((void **)&p->exports_dev, sizeof(ExportDesc) * ex.size());
-    if (e == cudaSuccess && !ins.empty()) e = cudaMalloc((void **)&p->inputs_dev, sizeof(InDesc) * ins.size());
-    if (e == cudaSuccess && !ins.empty()) e = cudaMemcpy(p->inputs_dev, ins.data(), sizeof(InDesc) * ins.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->state_dev, 16);
     if (e == cudaSuccess && world == 1) e = cudaMalloc(&p->arena_own, p->arena_bytes);
     if (e == cudaSuccess && getenv("B200_PLAN_TRACE")) {
@@ -989,8 +764,6 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     pa.exports = p->exports_dev;
     pa.nops = count;
     pa.nexports = (int)ex.size();
-    pa.inputs = p->inputs_dev;
-    pa.ninputs = (int)ins.size();
     pa.world = world;
     pa.rank = rank;
     for (int r = 0; r < world; r++) pa.arena[r] = split ? split->peer_arena[r] : p->arena_own;
