@@ -33,7 +33,11 @@ using namespace b200s;
 
 namespace {
 
-constexpr int kCW = 8;                       // consumer warps
+#ifndef B200_PLAN_ROW_SPLIT
+#define B200_PLAN_ROW_SPLIT 1                // 2: the rows of a ring slot are shared by two warps (16 consumer warps, 96 registers each)
+#endif
+constexpr int kRowSplit = B200_PLAN_ROW_SPLIT;
+constexpr int kCW = 8 * kRowSplit;           // consumer warps
 constexpr int kCT = kCW * 32;                // consumer threads
 constexpr int kPlanThreads = (kCW + 1) * 32;         // consumers + the producer warp
 constexpr int kSegBlocks = 128;              // blocks of k per warp-segment (4 per lane)
@@ -107,7 +111,7 @@ __device__ __forceinline__ OpGeom op_geom(int k, int slot_bytes) {
     const int segs = (g.nb + kSegBlocks - 1) >> 7;                // 1..8
     g.log2g = segs <= 1 ? 0 : (segs <= 2 ? 1 : (segs <= 4 ? 2 : 3));
     g.G = 1 << g.log2g;
-    g.rpp = kCW >> g.log2g;
+    g.rpp = 8 >> g.log2g;
     int rs = slot_bytes / (g.row_qs + g.row_sc);
     if (rs > 64) rs = 64;
     g.rs = rs;                                                     // >= rpp >= 1 by construction of slot_bytes
@@ -147,7 +151,7 @@ __device__ __forceinline__ float row_dots(const RowCtx<TYPE> &c, const uint4 (&w
 template <int TYPE, int NR>
 __device__ __forceinline__ float chunk_rows(const RowCtx<TYPE> &c, uint32_t stage_a, int r, int rows, int lane) {
     constexpr int QSB = TYPE == B200_TYPE_Q4_0 ? 16 : 32;
-    constexpr int NU = NR >= 4 ? 4 : (NR >= 2 ? 2 : 1);       // rows whose loads are in flight together
+    constexpr int NU = (NR >= 4 && kRowSplit == 1) ? 4 : (NR >= 2 ? 2 : 1);       // rows whose loads are in flight together
     float acc[NR];
 #pragma unroll
     for (int h = 0; h < NR; h += NU) {
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
     if (threadIdx.x == 0) {
         for (int s = 0; s < pg.nslots; s++) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kCW);       // a slot's consumers (one team of G warps) arrive with 8/G each
+            mbar_init(&empty_bar[s], kCW);       // a slot's consumers (one team of G [x 2] warps) arrive with 8/G each
         }
         *s_epoch = pa.state[1] + 1u;    // every CTA reads it before any CTA can finish (the bump needs all of them)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -342,7 +346,10 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
             const int rows_q = o->rows_q, rows_rem = o->rows_rem;
             const int r_begin = cta * rows_q + min(cta, rows_rem);
             const int nrows = rows_q + (cta < rows_rem ? 1 : 0);
-            const int G = 1 << log2g, seg = warp & (G - 1), team = warp >> log2g, team_mask = (kCW >> log2g) - 1;   // 8/G teams of G warps
+            // 8/G teams; a team = G warps splitting k (x kRowSplit warps splitting the slot's rows)
+            constexpr int kLog2Split = kRowSplit == 2 ? 1 : 0;
+            const int G = 1 << log2g, seg = warp & (G - 1), half = (warp >> log2g) & (kRowSplit - 1);
+            const int team = warp >> (log2g + kLog2Split), team_mask = (8 >> log2g) - 1;
             const int b0 = seg * kSegBlocks;
             const uint32_t tag = (epoch << 10) | (uint32_t)op;
             unsigned long long *tr = pa.trace ? pa.trace + ((size_t)op * gridDim.x + cta) * 4 : nullptr;
@@ -366,7 +373,7 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
                 const bool ll_in = src_op >= 0;
                 const uint32_t src_tag = (epoch << 10) | (uint32_t)(src_op & 1023);
                 const char *xsrc = ll_in ? arena_local + (size_t)o->ll_src * 8 : reinterpret_cast<const char *>(o->src_plain);
-                constexpr int kQB = 4;
+                constexpr int kQB = 4 / kRowSplit;
                 const int tpc = nb * 2;      // lane-tasks: (block, half) = 16 consecutive floats
 #pragma unroll 1
                 for (int base = 0; base < tpc; base += kCT * kQB) {
@@ -457,10 +464,13 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
                     } else {
                         mbar_wait_a(full_a + 8u * (uint32_t)st, par);
                     }
-                    const int rows = min(rs, nrows - rbase);
+                    const int rows_slot = min(rs, nrows - rbase);
+                    // with two warps per slot: the first takes rows [0, split), the second [split, rows_slot)
+                    const int split = kRowSplit == 2 ? (rows_slot + 1) >> 1 : rows_slot;
+                    const int rows = half == 0 ? split : rows_slot;
                     const uint32_t stage_a = ring_a + (uint32_t)(st * pg.slot_bytes);
 #pragma unroll 1
-                    for (int r = 0; r < rows;) {
+                    for (int r = half == 0 ? 0 : split; r < rows;) {
                         float v;
                         int u, step;
                         bool holder;
@@ -491,7 +501,7 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
                     }
                     // every lane's weights of this slot have been consumed by the dots: hand it back to the producer
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cnt(empty_a + 8u * (uint32_t)st, (uint32_t)(kCW >> log2g));
+                    if (lane == 0) mbar_arrive_cnt(empty_a + 8u * (uint32_t)st, (uint32_t)(8 >> log2g));
                 }
                 if (++st == nslots) { st = 0; par ^= 1u; }
             }
@@ -721,7 +731,7 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     // ring: as many slots as fit, a multiple of the consumer warps when possible (every warp then owns the same number)
     int nslots = (max_smem - fixed) / g.slot_bytes;
     if (nslots > kMaxSlots) nslots = kMaxSlots;
-    if (nslots >= kCW) nslots = nslots / kCW * kCW;
+    if (nslots >= 8) nslots = nslots / 8 * 8;
     if (const char *e = getenv("B200_PLAN_SLOTS")) { const int v = atoi(e); if (v >= 2 && v <= kMaxSlots && v * g.slot_bytes <= max_smem - fixed) nslots = v; }
     if (nslots < 2) { free(p); b200_set_error(ctx, "b200_plan_create: k = %d leaves no room for the weight ring", kmax); return B200_ERR_UNSUPPORTED; }
     g.nslots = nslots;
