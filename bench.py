@@ -341,6 +341,12 @@ def run_b200(args):
             print(f"[bench] decode plan unavailable ({type(e).__name__}: {e}); using the launch-per-node path", file=sys.stderr)
             plan = None
             plan_fn = None
+        if world > 1:
+            # every rank or none: a rank without the plan would leave the others waiting for its tagged stores
+            okp = torch.tensor([1 if plan_fn is not None else 0], device=dev)
+            dist.all_reduce(okp, op=dist.ReduceOp.MIN)
+            if int(okp.item()) == 0:
+                plan_fn = None
 
     # ---- capture the step once (our kernels + NCCL) into a CUDA graph: decode is launch-bound otherwise
     use_graph = not args.no_graph
