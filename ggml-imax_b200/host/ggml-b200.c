@@ -405,15 +405,37 @@ static enum ggml_status b200_compute_mul_mat_run(struct b200_backend_context *bc
     return GGML_STATUS_SUCCESS;
 }
 
-/*
- * Decode graphs: when every compute node of the cgraph is a decode-shaped MUL_MAT (one activation column, 2-D weights), the
- * whole graph goes down as ONE persistent launch (b200_plan_*, include/ggml_b200.h) -- what ggml_backend_graph_plan_create /
- * _compute would be for this backend, done transparently and cached per graph like the reference's CUDA-graph replay
- * (src/ggml-cuda.cu:2461-2709).  Returns 1 when the graph was computed that way, 0 when it has to go node by node (other
- * shapes, or tensors that share memory as a graph allocator arranges them), -1 on a hard error.
- */
-static int b200_try_graph_as_plan(struct b200_backend_context *bc, struct ggml_cgraph *cgraph) {
-    if (!bc->opt_plans) return 0;
+/* args of the graph's n MUL_MAT nodes -> b200_plan_create.  *out stays NULL when the graph cannot run as a plan
+ * (B200_ERR_UNSUPPORTED: other shapes, aliased vectors); returns -1 on a hard error, 0 otherwise. */
+static int b200_build_plan(struct b200_backend_context *bc, const struct ggml_cgraph *cgraph, int n, b200_plan **out) {
+    *out = NULL;
+    b200_mul_mat_args *args = (b200_mul_mat_args *)malloc(sizeof(b200_mul_mat_args) * (size_t)n);
+    if (!args) return -1;
+    int k = 0;
+    bool ok = true;
+    for (int i = 0; i < cgraph->n_nodes && ok; i++) {
+        struct ggml_tensor *node = cgraph->nodes[i];
+        if (ggml_is_empty(node) || b200_op_is_noop(node->op)) continue;
+        ok = b200_mul_mat_supported(node) && b200_fill_mul_mat_args(node, &args[k++]);
+    }
+    int ret = 0;
+    if (ok) {
+        const int rc = b200_plan_create(bc->ctx, args, n, NULL, out);
+        if (rc != B200_OK) {
+            *out = NULL;
+            if (rc != B200_ERR_UNSUPPORTED) {
+                fprintf(stderr, "ggml-b200: b200_plan_create failed (%d): %s\n", rc, b200_last_error(bc->ctx));
+                ret = -1;
+            }
+        }
+    }
+    free(args);
+    return ret;
+}
+
+/* number of decode-shaped MUL_MAT compute nodes if the graph consists of nothing else (and has at least two), else 0;
+ * *key = hash over their addresses and shapes */
+static int b200_decode_graph_nodes(const struct ggml_cgraph *cgraph, uint64_t *key_out) {
     int n = 0;
     uint64_t key = 1469598103934665603ull;     /* FNV-1a */
     for (int i = 0; i < cgraph->n_nodes; i++) {
@@ -428,8 +450,23 @@ static int b200_try_graph_as_plan(struct b200_backend_context *bc, struct ggml_c
             for (int sh = 0; sh < 64; sh += 8) key = (key ^ ((words[w] >> sh) & 0xff)) * 1099511628211ull;
         n++;
     }
-    if (n < 2) return 0;
     if (key == 0) key = 1;
+    if (key_out) *key_out = key;
+    return n >= 2 ? n : 0;
+}
+
+/*
+ * Decode graphs: when every compute node of the cgraph is a decode-shaped MUL_MAT (one activation column, 2-D weights), the
+ * whole graph goes down as ONE persistent launch (b200_plan_*, include/ggml_b200.h) -- what ggml_backend_graph_plan_create /
+ * _compute would be for this backend, done transparently and cached per graph like the reference's CUDA-graph replay
+ * (src/ggml-cuda.cu:2461-2709).  Returns 1 when the graph was computed that way, 0 when it has to go node by node (other
+ * shapes, or tensors that share memory as a graph allocator arranges them), -1 on a hard error.
+ */
+static int b200_try_graph_as_plan(struct b200_backend_context *bc, struct ggml_cgraph *cgraph) {
+    if (!bc->opt_plans) return 0;
+    uint64_t key = 0;
+    const int n = b200_decode_graph_nodes(cgraph, &key);
+    if (n == 0) return 0;
     struct b200_cached_plan *slot = NULL;
     for (int i = 0; i < B200_PLAN_CACHE; i++)
         if (bc->plans[i].key == key && bc->plans[i].n_nodes == n) slot = &bc->plans[i];
@@ -443,27 +480,7 @@ static int b200_try_graph_as_plan(struct b200_backend_context *bc, struct ggml_c
         slot->key = key;
         slot->n_nodes = n;
         slot->plan = NULL;
-        b200_mul_mat_args *args = (b200_mul_mat_args *)malloc(sizeof(b200_mul_mat_args) * (size_t)n);
-        if (!args) return -1;
-        int k = 0;
-        bool ok = true;
-        for (int i = 0; i < cgraph->n_nodes && ok; i++) {
-            struct ggml_tensor *node = cgraph->nodes[i];
-            if (ggml_is_empty(node) || b200_op_is_noop(node->op)) continue;
-            ok = b200_mul_mat_supported(node) && b200_fill_mul_mat_args(node, &args[k++]);
-        }
-        if (ok) {
-            const int rc = b200_plan_create(bc->ctx, args, n, NULL, &slot->plan);
-            if (rc != B200_OK) {
-                slot->plan = NULL;     /* B200_ERR_UNSUPPORTED: node by node (remembered); anything else is reported below */
-                if (rc != B200_ERR_UNSUPPORTED) {
-                    fprintf(stderr, "ggml-b200: b200_plan_create failed (%d): %s\n", rc, b200_last_error(bc->ctx));
-                    free(args);
-                    return -1;
-                }
-            }
-        }
-        free(args);
+        if (b200_build_plan(bc, cgraph, n, &slot->plan) < 0) return -1;
     }
     if (!slot->plan) return 0;
     const int rc = b200_plan_launch(bc->ctx, slot->plan);
@@ -475,13 +492,62 @@ static int b200_try_graph_as_plan(struct b200_backend_context *bc, struct ggml_c
     return 1;
 }
 
+static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc, struct ggml_cgraph *cgraph);
+
 GGML_CALL static enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, struct ggml_cgraph *cgraph) {
     struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
-    {
-        const int as_plan = b200_try_graph_as_plan(bc, cgraph);
-        if (as_plan < 0) return GGML_STATUS_FAILED;
-        if (as_plan > 0) return GGML_STATUS_SUCCESS;
+    const int as_plan = b200_try_graph_as_plan(bc, cgraph);
+    if (as_plan < 0) return GGML_STATUS_FAILED;
+    if (as_plan > 0) return GGML_STATUS_SUCCESS;
+    return b200_graph_compute_nodes(bc, cgraph);
+}
+
+/* ggml_backend_graph_plan_create / _free / _compute (src/ggml-backend-impl.h:94-99, src/ggml-backend.c:257-273): the explicit
+ * form of the above.  Like the reference CPU backend's plan (src/ggml-backend.c:761-790) it keeps a shallow copy of the cgraph,
+ * so the graph has to outlive the plan.  A graph that cannot be one persistent launch is computed node by node. */
+struct b200_graph_plan {
+    struct ggml_cgraph cgraph;
+    b200_plan *plan;
+};
+
+GGML_CALL static ggml_backend_graph_plan_t b200_backend_graph_plan_create(ggml_backend_t backend, const struct ggml_cgraph *cgraph) {
+    struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
+    struct b200_graph_plan *gp = (struct b200_graph_plan *)calloc(1, sizeof(*gp));
+    if (!gp) return NULL;
+    gp->cgraph = *cgraph;
+    const int n = bc->opt_plans ? b200_decode_graph_nodes(cgraph, NULL) : 0;
+    if (n > 0 && b200_build_plan(bc, cgraph, n, &gp->plan) < 0) {
+        free(gp);
+        return NULL;
     }
+    return (ggml_backend_graph_plan_t)gp;
+}
+
+GGML_CALL static void b200_backend_graph_plan_free(ggml_backend_t backend, ggml_backend_graph_plan_t plan) {
+    struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
+    struct b200_graph_plan *gp = (struct b200_graph_plan *)plan;
+    if (!gp) return;
+    if (gp->plan) {
+        b200_synchronize(bc->ctx);
+        b200_plan_destroy(gp->plan);
+    }
+    free(gp);
+}
+
+GGML_CALL static enum ggml_status b200_backend_graph_plan_compute(ggml_backend_t backend, ggml_backend_graph_plan_t plan) {
+    struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
+    struct b200_graph_plan *gp = (struct b200_graph_plan *)plan;
+    if (!gp->plan) return b200_graph_compute_nodes(bc, &gp->cgraph);
+    const int rc = b200_plan_launch(bc->ctx, gp->plan);
+    if (rc != B200_OK) {
+        fprintf(stderr, "ggml-b200: b200_plan_launch failed (%d): %s\n", rc, b200_last_error(bc->ctx));
+        return GGML_STATUS_FAILED;
+    }
+    bc->plan_launches++;
+    return GGML_STATUS_SUCCESS;
+}
+
+static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc, struct ggml_cgraph *cgraph) {
     for (int i = 0; i < cgraph->n_nodes; i++) {
         struct ggml_tensor *node = cgraph->nodes[i];
         if (ggml_is_empty(node) || b200_op_is_noop(node->op)) continue;
@@ -519,9 +585,9 @@ static struct ggml_backend_i b200_backend_interface = {
     /* .get_tensor_async        = */ NULL,
     /* .cpy_tensor_async        = */ NULL,
     /* .synchronize             = */ b200_backend_synchronize,
-    /* .graph_plan_create       = */ NULL,
-    /* .graph_plan_free         = */ NULL,
-    /* .graph_plan_compute      = */ NULL,
+    /* .graph_plan_create       = */ b200_backend_graph_plan_create,
+    /* .graph_plan_free         = */ b200_backend_graph_plan_free,
+    /* .graph_plan_compute      = */ b200_backend_graph_plan_compute,
     /* .graph_compute           = */ b200_backend_graph_compute,
     /* .supports_op             = */ b200_backend_supports_op,
     /* .offload_op              = */ NULL,

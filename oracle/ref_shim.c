@@ -147,6 +147,7 @@ typedef struct ref_chain {
     struct ggml_tensor **w;
     struct ggml_tensor *x, *out;
     struct ggml_cgraph *gf;
+    ggml_backend_graph_plan_t plan;
     int n_weights;
 } ref_chain;
 
@@ -182,8 +183,18 @@ double ref_chain_compute(ref_chain *h) {
     return (double)(ggml_time_us() - t0);
 }
 
+/* the same graph through the explicit plan API: ggml_backend_graph_plan_create once, _compute per call (src/ggml-backend.c:257-273) */
+double ref_chain_compute_planned(ref_chain *h) {
+    if (!h->plan) h->plan = ggml_backend_graph_plan_create(h->backend, h->gf);
+    const int64_t t0 = ggml_time_us();
+    ggml_backend_graph_plan_compute(h->backend, h->plan);
+    ggml_backend_synchronize(h->backend);
+    return (double)(ggml_time_us() - t0);
+}
+
 void ref_chain_free(ref_chain *h) {
     if (!h) return;
+    if (h->plan) ggml_backend_graph_plan_free(h->backend, h->plan);
     ggml_backend_buffer_free(h->buf);
     ggml_backend_free(h->backend);
     ggml_free(h->ctx);

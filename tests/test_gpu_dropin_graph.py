@@ -24,6 +24,8 @@ def load(name):
     lib.ref_dag_create.restype = vp
     lib.ref_chain_compute.restype = C.c_double
     lib.ref_chain_compute.argtypes = [vp]
+    lib.ref_chain_compute_planned.restype = C.c_double
+    lib.ref_chain_compute_planned.argtypes = [vp]
     lib.ref_chain_node_elements.restype = C.c_int64
     lib.ref_chain_node_elements.argtypes = [vp, C.c_int]
     lib.ref_chain_n_nodes.argtypes = [vp]
@@ -62,9 +64,11 @@ NODES = [(0, -1), (1, -1), (2, -1), (3, -1), (4, 1), (5, 0),
          (0, 5), (1, 5), (2, 5), (3, 5), (4, 7), (5, 6), (6, 11)]
 
 
+@pytest.mark.parametrize("planned", [False, True])
 @pytest.mark.parametrize("qtype", [Q4_0, Q8_0])
 @pytest.mark.parametrize("ncols", [1, 3])
-def test_same_ggml_graph_on_cpu_backend_and_on_b200_backend(oracle, qtype, ncols):
+def test_same_ggml_graph_on_cpu_backend_and_on_b200_backend(oracle, qtype, ncols, planned):
+    """planned: through ggml_backend_graph_plan_create / _compute instead of ggml_backend_graph_compute"""
     cpu = load("libref_shim.so")
     gpu = load("libdropin_shim.so")
     gpu.ref_select_backend(b"B2000")
@@ -82,7 +86,7 @@ def test_same_ggml_graph_on_cpu_backend_and_on_b200_backend(oracle, qtype, ncols
             cpu.ref_chain_set_x(hc, x.ctypes.data_as(vp))
             gpu.ref_chain_set_x(hg, x.ctypes.data_as(vp))
             cpu.ref_chain_compute(hc)
-            gpu.ref_chain_compute(hg)
+            (gpu.ref_chain_compute_planned if planned else gpu.ref_chain_compute)(hg)
             want, got = node_outputs(cpu, hc), node_outputs(gpu, hg)
             assert len(want) == len(got) == len(NODES)
             for i, (a, b) in enumerate(zip(got, want)):
