@@ -684,6 +684,17 @@ GGML_API GGML_CALL ggml_backend_t ggml_backend_cuda_init(int device) { return gg
 GGML_API GGML_CALL bool ggml_backend_is_cuda(ggml_backend_t backend) { return ggml_backend_is_b200(backend); }
 GGML_API GGML_CALL ggml_backend_buffer_type_t ggml_backend_cuda_buffer_type(int device) { return ggml_backend_b200_buffer_type(device); }
 GGML_API GGML_CALL ggml_backend_buffer_type_t ggml_backend_cuda_host_buffer_type(void) { return ggml_backend_b200_host_buffer_type(); }
+/* src/ggml-cuda.h:28-29.  The reference splits a matrix by rows across the devices of ONE process (src/ggml-cuda.cu:578-975).
+ * Here rows are split across processes, one per GPU, and the slices are exchanged by the decode plan itself
+ * (b200_plan_create with a b200_plan_split, include/ggml_b200.h): there is no single-process split buffer to hand out.
+ * The symbol exists so that hosts written against ggml-cuda.h link; NULL = "not available", which callers must handle
+ * like any failed buffer-type lookup. */
+GGML_API GGML_CALL ggml_backend_buffer_type_t ggml_backend_cuda_split_buffer_type(const float *tensor_split) {
+    GGML_UNUSED(tensor_split);
+    fprintf(stderr, "ggml-b200: ggml_backend_cuda_split_buffer_type: row split is one process per GPU in this backend "
+                    "(b200_plan_create + b200_plan_split); no single-process split buffer type\n");
+    return NULL;
+}
 GGML_API GGML_CALL int ggml_backend_cuda_get_device_count(void) { return ggml_backend_b200_get_device_count(); }
 GGML_API GGML_CALL void ggml_backend_cuda_get_device_description(int device, char *description, size_t description_size) {
     ggml_backend_b200_get_device_description(device, description, description_size);
