@@ -557,6 +557,37 @@ def run_b200(args):
             except Exception:
                 pass
 
+    if world == 1 and not args.no_extras:
+        # configs[3] also names the 512-token prefill: the same 169-node graph with 512 activation columns per node, i.e. every
+        # mul_mat goes through quantize_q8_0 + the tcgen05 int8 GEMM (b200_mul_mat, one call per node, eager)
+        try:
+            npf = 512
+            xin = torch.rand(npf * N_EMBD, dtype=torch.float32, device=dev) * 2 - 1
+            blk = [torch.empty(npf * m, dtype=torch.float32, device=dev) for _, m, _ in LAYER_MATS]
+            blk2 = [torch.empty(npf * m, dtype=torch.float32, device=dev) for _, m, _ in LAYER_MATS]
+            head = torch.empty(npf * N_VOCAB, dtype=torch.float32, device=dev)
+            for _, m, k in set(mats):
+                ctx.reserve_workspace(Q4_0, k, m, npf)
+
+            def pf_out(i):
+                return head if i == len(dag) - 1 else ((blk, blk2)[(i // 6) & 1])[i % 6]
+
+            def prefill():
+                for i, (t, split, k) in enumerate(weights):
+                    src = dag[i][3]
+                    ctx.mul_mat_device(t, xin.data_ptr() if src < 0 else pf_out(src).data_ptr(), npf, pf_out(i).data_ptr())
+            prefill()
+            torch.cuda.synchronize()
+            ms_pf = timed(prefill, 3) / 3
+            ops_pf = 2.0 * npf * sum(m * k for _, m, k in mats)
+            extra["gptj6b_q4_0_prefill_512_tokens"] = {"ms": round(ms_pf, 2), "prompt_tokens/s": round(npf * 1000.0 / ms_pf, 1),
+                                                       "int8_TOPS": round(ops_pf / (ms_pf * 1e-3) / 1e12, 1),
+                                                       "finite": bool(torch.isfinite(head[:N_VOCAB]).all()),
+                                                       "note": "169 mul_mats x 512 columns, one b200_mul_mat per node (quantize_q8_0 + Q4_0 expansion + tcgen05 int8 GEMM)"}
+            del xin, blk, blk2, head
+        except Exception as e:
+            extra["gptj6b_q4_0_prefill_512_tokens"] = {"error": f"{type(e).__name__}: {e}"}
+
     line = None
     if rank == 0:
         line = {
