@@ -11,7 +11,7 @@
 // cost ~2.6 us each of idle HBM (profiles/r01_stream_bw_microbench.txt), a third of the step.  Here there are none:
 //   * grid = one persistent CTA per SM; every CTA walks the op list; in op i it owns a contiguous run of rows of W_i;
 //   * warp 8 is the producer: ONE elected thread streams the CTA's byte ranges of op 0, 1, 2, ... back to back into a
-//     shared-memory ring (cp.async.bulk + mbarrier complete_tx), ~180 KB in flight per SM (~27 MB per GPU = 4 us of HBM).
+//     shared-memory ring (cp.async.bulk + mbarrier complete_tx), 8 slots x 18 KB in flight per SM (~22 MB per GPU = 3 us of HBM).
 //     Weights never depend on activations, so the producer runs arbitrarily far ahead of the consumers: HBM keeps
 //     streaming W_{i+1} while the grid exchanges the result of op i;
 //   * dependencies between ops travel as tagged 8-byte elements {fp32 value, u32 tag} ("LL" vectors, one per op, in an
@@ -26,7 +26,6 @@
 #include "b200_stream_common.cuh"
 
 #include <stdlib.h>
-#include <utility>
 #include <vector>
 
 using namespace b200s;
