@@ -192,17 +192,23 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint32_t sa = smem_u32(smem + s * kStageBytes);
                 const uint32_t sb = sa + BM * BK;
                 const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sb);
+                // Two k-blocks per hand-shake: TMEM buffers {0,1} and {2,3} form two groups that ping-pong between this thread
+                // and the epilogue.  One wait, two MMAs (each a fresh accumulator: one quant block), one commit per group --
+                // the per-k-block barrier traffic of both sides is what bounded the kernel (profiles/r01_gemm_experiments.md).
+                const uint32_t tph = (uint32_t)it & 1u;                  // every group is used once per stage
 #pragma unroll
-                for (int j = 0; j < BK / 32; j++) {
-                    const int kb = it * (BK / 32) + j;
-                    if (kb < nb) {
-                        const int buf = kb % kTmemBufs;
-                        const uint32_t tph = (uint32_t)(kb / kTmemBufs) & 1u;
-                        mbar_wait(&tempty_bar[buf], tph ^ 1u);   // epilogue has drained this TMEM buffer
+                for (int grp = 0; grp < 2; grp++) {
+                    const int kb0 = it * (BK / 32) + 2 * grp;
+                    if (kb0 < nb) {
+                        mbar_wait(&tempty_bar[grp], tph ^ 1u);           // epilogue has drained both buffers of the group
                         tc_fence_after();
-                        // K advance inside the 128-byte swizzle atom: +32 bytes = +2 in the (>>4) start-address field
-                        tc_mma_i8(tmem_base + (uint32_t)(buf * BN), da + (uint64_t)(j * 2), db + (uint64_t)(j * 2), kIdescI8, 0u);
-                        tc_commit(&tfull_bar[buf]);              // arrives when this MMA has written TMEM
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int j = 2 * grp + h;
+                            // K advance inside the 128-byte swizzle atom: +32 bytes = +2 in the (>>4) start-address field
+                            if (kb0 + h < nb) tc_mma_i8(tmem_base + (uint32_t)(j * BN), da + (uint64_t)(j * 2), db + (uint64_t)(j * 2), kIdescI8, 0u);
+                        }
+                        tc_commit(&tfull_bar[grp]);                      // arrives when both MMAs have written TMEM
                     }
                 }
                 tc_commit(&empty_bar[s]);                        // smem stage reusable once its MMAs have read it
@@ -288,13 +294,17 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tc_ld32(tbuf + 32, pb);                  // (kb, half 1) in flight
                     if (DOTS) dump_dots(pa, kb, 0); else scale_acc(pa, sdx + (uint32_t)(j * BN * 4), dw2, 0);
                     tc_wait_ld();                            // pb = (kb, half 1): this warp is done with TMEM buffer j
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[j]);
+                    if ((j & 1) == 1 || kb + 1 >= nb) {      // ... and, after the group's second k-block, with the group
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[j >> 1]);
+                    }
                     if (kb + 1 < nb) {                       // next k-block's first half: buffer (j + 1) % 4
                         const int jn = (j + 1) & 3;
-                        mbar_wait(&tfull_bar[jn], jn == 0 ? (tph ^ 1u) : tph);
-                        tc_fence_after();
+                        if ((jn & 1) == 0) {                 // first k-block of the next group: one wait per two k-blocks
+                            mbar_wait(&tfull_bar[jn >> 1], jn == 0 ? (tph ^ 1u) : tph);
+                            tc_fence_after();
+                        }
                         tc_ld32(tcol + (uint32_t)(jn * BN), pa);
                     }
                     if (DOTS) dump_dots(pb, kb, 1); else scale_acc(pb, sdx + (uint32_t)(j * BN * 4), dw2, 1);
