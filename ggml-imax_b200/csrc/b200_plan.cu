@@ -52,7 +52,7 @@ struct __align__(16) PDesc {                 // what the producer needs of an op
     const __half *d;         // d plane, same
     int k;
     int rows_q, rows_rem;    // CTA c owns local rows [c*rows_q + min(c, rows_rem), + rows_q + (c < rows_rem))
-    int rs;                  // rows per ring slot (host copy of op_geom().rs: the producer thread must not divide)
+    int rs;                  // rows per ring slot (computed on the host: the producer thread must not divide)
 };
 static_assert(sizeof(PDesc) == 32, "PDesc layout");
 struct __align__(16) CDesc {                 // what the consumers need (staged in shared memory, kDescCap at a time)
@@ -94,27 +94,6 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 __device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar_addr, uint32_t count) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(count) : "memory");
-}
-
-// per-op stage geometry: both producer and consumers derive it from (k, slot_bytes) alone
-struct OpGeom {
-    int nb, row_qs, row_sc, G, log2g, rpp, rs;
-};
-template <int TYPE>
-__device__ __forceinline__ OpGeom op_geom(int k, int slot_bytes) {
-    constexpr int QSB = TYPE == B200_TYPE_Q4_0 ? 16 : 32;
-    OpGeom g;
-    g.nb = k >> 5;
-    g.row_qs = g.nb * QSB;
-    g.row_sc = g.nb * 2;
-    const int segs = (g.nb + kSegBlocks - 1) >> 7;                // 1..8
-    g.log2g = segs <= 1 ? 0 : (segs <= 2 ? 1 : (segs <= 4 ? 2 : 3));
-    g.G = 1 << g.log2g;
-    g.rpp = 8 >> g.log2g;
-    int rs = slot_bytes / (g.row_qs + g.row_sc);
-    if (rs > 64) rs = 64;
-    g.rs = rs;                                                     // >= rpp >= 1 by construction of slot_bytes
-    return g;
 }
 
 // everything a warp needs to turn rows of a ring slot into results
