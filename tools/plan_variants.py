@@ -91,10 +91,7 @@ del a, b
 
 n = len(dag)
 run("deps (bench graph)", [(i, dag[i][3]) for i in range(n)])
-run("deps, 20 slots x 4 rows", [(i, dag[i][3]) for i in range(n)], slots=20)
-run("deps, 8 slots x 8 rows", [(i, dag[i][3]) for i in range(n)], rows=8)
-run("deps, 10 slots x 8 rows", [(i, dag[i][3]) for i in range(n)], rows=8, slots=10)
-run("nodeps, 8 slots x 8 rows", [(i, -1) for i in range(n)], rows=8)
+run("deps, 6 ring slots", [(i, dag[i][3]) for i in range(n)], slots=6)
 run("nodeps", [(i, -1) for i in range(n)])
 k4 = [i for i in range(n) if dag[i][2] == 4096 and dag[i][1] == 4096]
 run("k4096 m4096 nodeps", [(i, -1) for i in k4])
