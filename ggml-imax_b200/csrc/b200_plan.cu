@@ -108,22 +108,6 @@ struct RowCtx {
     int row_qs, row_sc;
 };
 
-// exact dots of one row segment (4 blocks per lane) against the resident activations
-template <int TYPE>
-__device__ __forceinline__ float row_dots(const RowCtx<TYPE> &c, const uint4 (&w0)[4], const uint4 (&w1)[4], const unsigned short (&sc)[4]) {
-    float a = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint4 alo = lds128(c.a_lo + (uint32_t)(i * 512)), ahi = lds128(c.a_hi + (uint32_t)(i * 512));
-        const float da = lds_f32(c.a_d + (uint32_t)(i * 128));
-        const int s8 = TYPE == B200_TYPE_Q4_0 ? lds_s32(c.a_s + (uint32_t)(i * 128)) : 0;
-        const int sumi = block_dot<TYPE>(w0[i], w1[i], alo, ahi, s8);
-        const float dw = __half2float(__ushort_as_half(sc[i]));
-        if (c.blive[i]) a = fmaf((float)sumi, dw * da, a);
-    }
-    return a;
-}
-
 // NR (4, 2 or 1) rows r .. r+NR-1 of the stage at stage_a (rows past `rows` are clamped and dropped): two rows' loads are in
 // flight together, the NR row sums share one transposed butterfly.  Returns with lane (32/NR)*u holding row r+u.
 template <int TYPE, int NR>
@@ -148,8 +132,22 @@ __device__ __forceinline__ float chunk_rows(const RowCtx<TYPE> &c, uint32_t stag
                 asm volatile("ld.shared.u16 %0, [%1];" : "=h"(sc[u][i]) : "r"(sbase + (uint32_t)(i * 64)));
             }
         }
+        // block by block: the activation block (two 16-byte planes, scale, 8 * sum) is read ONCE and used for all NU rows;
+        // every row still accumulates its blocks in the order i = 0..3 (the summation order of gemv_stream_kernel)
 #pragma unroll
-        for (int u = 0; u < NU; u++) acc[h + u] = row_dots<TYPE>(c, w0[u], w1[u], sc[u]);
+        for (int u = 0; u < NU; u++) acc[h + u] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint4 alo = lds128(c.a_lo + (uint32_t)(i * 512)), ahi = lds128(c.a_hi + (uint32_t)(i * 512));
+            const float da = lds_f32(c.a_d + (uint32_t)(i * 128));
+            const int s8 = TYPE == B200_TYPE_Q4_0 ? lds_s32(c.a_s + (uint32_t)(i * 128)) : 0;
+#pragma unroll
+            for (int u = 0; u < NU; u++) {
+                const int sumi = block_dot<TYPE>(w0[u][i], w1[u][i], alo, ahi, s8);
+                const float dw = __half2float(__ushort_as_half(sc[u][i]));
+                if (c.blive[i]) acc[h + u] = fmaf((float)sumi, dw * da, acc[h + u]);
+            }
+        }
     }
     // transposed butterfly: the same pairings -- hence the same bits -- as acc += shfl_xor(acc, 16, 8, 4, 2, 1) per row
     float kk;
