@@ -561,11 +561,78 @@ static bool ranges_overlap(const void *a, size_t an, const void *b, size_t bn) {
     return a0 < b0 + bn && b0 < a0 + an;
 }
 
+// Host-only part of b200_plan_create (no CUDA call, so it is testable without a device): shapes, and ggml's dataflow between
+// the ops.  src_op[i] = index of the op whose dst is op i's src1, or -1 for a vector from outside the plan.
+static int plan_analyze(b200_ctx *ctx, const b200_mul_mat_args *args, int count, const b200_plan_split *split, std::vector<int> *src_op,
+                        std::vector<int> *m_total_out) {
+    B200_REQUIRE(ctx, args && count >= 1, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, count <= kMaxOps, B200_ERR_UNSUPPORTED);
+    const int world = split ? split->world : 1, rank = split ? split->rank : 0;
+    B200_REQUIRE(ctx, world >= 1 && world <= B200_MAX_RANKS && rank >= 0 && rank < world, B200_ERR_INVALID);
+    if (split) B200_REQUIRE(ctx, split->row0 && split->m_total, B200_ERR_INVALID);
+    const int type = args[0].type;
+    B200_REQUIRE(ctx, type == B200_TYPE_Q4_0 || type == B200_TYPE_Q8_0, B200_ERR_UNSUPPORTED);
+    std::vector<int> &so = *src_op;
+    std::vector<int> &m_total = *m_total_out;
+    so.assign((size_t)count, -1);
+    m_total.assign((size_t)count, 0);
+    for (int i = 0; i < count; i++) {
+        const b200_mul_mat_args *a = &args[i];
+        // decode shapes the streaming kernels take; anything else is the caller's node-by-node path
+        B200_REQUIRE(ctx, a->type == type && !(a->flags & B200_MM_FORCE_GEMM), B200_ERR_UNSUPPORTED);
+        B200_REQUIRE(ctx, a->ne11 == 1 && a->ne12 == 1 && a->ne13 == 1 && a->ne02 == 1 && a->ne03 == 1, B200_ERR_UNSUPPORTED);
+        B200_REQUIRE(ctx, a->ne00 > 0 && a->ne00 % 256 == 0 && a->ne00 <= 32768, B200_ERR_UNSUPPORTED);
+        B200_REQUIRE(ctx, a->ne01 >= 0 && a->ne01 < (1ll << 30), B200_ERR_UNSUPPORTED);
+        B200_REQUIRE(ctx, a->src0_dev && a->src1_dev, B200_ERR_INVALID);
+        const int64_t nb = a->ne00 / B200_QK;
+        B200_REQUIRE(ctx, a->src0_block_off >= 0 && a->src0_block_off + nb * a->ne01 <= a->src0_nblocks_total, B200_ERR_INVALID);
+        const int64_t mt = split ? split->m_total[i] : a->ne01;
+        const int64_t row0 = split ? split->row0[i] : 0;
+        B200_REQUIRE(ctx, row0 >= 0 && row0 + a->ne01 <= mt && mt < (1ll << 30), B200_ERR_INVALID);
+        m_total[i] = (int)mt;
+        // dataflow: src1 is the dst of the latest earlier op with that address, else an outside vector
+        for (int j = i - 1; j >= 0; j--) {
+            if (!args[j].dst_dev) continue;
+            if (!ranges_overlap(a->src1_dev, (size_t)a->ne00 * 4, args[j].dst_dev, (size_t)m_total[j] * 4)) continue;
+            // must be exactly that vector
+            B200_REQUIRE(ctx, (const void *)a->src1_dev == (const void *)args[j].dst_dev && m_total[j] == a->ne00, B200_ERR_UNSUPPORTED);
+            so[i] = j;
+            break;
+        }
+        if (so[i] < 0) B200_REQUIRE(ctx, ((uintptr_t)a->src1_dev & 15) == 0, B200_ERR_UNSUPPORTED);
+    }
+    // Hazards sequential execution would hide but dataflow execution does not: plain dst vectors that alias each other or an
+    // outside input (buffer reuse by a graph allocator).  Those graphs stay on the node-by-node path.
+    for (int i = 0; i < count; i++) {
+        if (!args[i].dst_dev) continue;
+        const size_t di = (size_t)m_total[i] * 4;
+        for (int j = 0; j < count; j++) {
+            if (j > i && args[j].dst_dev && ranges_overlap(args[i].dst_dev, di, args[j].dst_dev, (size_t)m_total[j] * 4)) {
+                b200_set_error(ctx, "b200_plan: dst of op %d aliases dst of op %d", i, j);
+                return B200_ERR_UNSUPPORTED;
+            }
+            if (so[j] < 0 && ranges_overlap(args[i].dst_dev, di, args[j].src1_dev, (size_t)args[j].ne00 * 4)) {
+                b200_set_error(ctx, "b200_plan: dst of op %d aliases the outside input of op %d", i, j);
+                return B200_ERR_UNSUPPORTED;
+            }
+        }
+    }
+    return B200_OK;
+}
+
 extern "C" {
 
 size_t b200_plan_arena_bytes(const b200_mul_mat_args *args, int count, const b200_plan_split *split) {
     if (!args || count <= 0) return 0;
     return plan_arena_elems(args, count, split, nullptr) * 8;
+}
+
+int b200_plan_analyze(const b200_mul_mat_args *args, int count, const b200_plan_split *split, int32_t *src_op_out) {
+    std::vector<int> so, mt;
+    const int rc = plan_analyze(NULL, args, count, split, &so, &mt);
+    if (rc == B200_OK && src_op_out)
+        for (int i = 0; i < count; i++) src_op_out[i] = so[(size_t)i];
+    return rc;
 }
 
 void b200_plan_destroy(b200_plan *p) {
@@ -582,13 +649,14 @@ void b200_plan_destroy(b200_plan *p) {
 int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, const b200_plan_split *split, b200_plan **out) {
     B200_REQUIRE(ctx, ctx && args && out && count >= 1, B200_ERR_INVALID);
     *out = NULL;
-    B200_REQUIRE(ctx, count <= kMaxOps, B200_ERR_UNSUPPORTED);
-    const int world = split ? split->world : 1, rank = split ? split->rank : 0;
-    B200_REQUIRE(ctx, world >= 1 && world <= B200_MAX_RANKS && rank >= 0 && rank < world, B200_ERR_INVALID);
-    if (split) {
-        B200_REQUIRE(ctx, split->row0 && split->m_total, B200_ERR_INVALID);
-        for (int r = 0; r < world; r++) B200_REQUIRE(ctx, split->peer_arena[r] != NULL, B200_ERR_INVALID);
+    std::vector<int> src_op, m_total;
+    {
+        const int rc = plan_analyze(ctx, args, count, split, &src_op, &m_total);     // shapes, dataflow, aliasing hazards
+        if (rc != B200_OK) return rc;
     }
+    const int world = split ? split->world : 1, rank = split ? split->rank : 0;
+    if (split)
+        for (int r = 0; r < world; r++) B200_REQUIRE(ctx, split->peer_arena[r] != NULL, B200_ERR_INVALID);
     const int type = args[0].type;
     B200_REQUIRE(ctx, type == B200_TYPE_Q4_0 || type == B200_TYPE_Q8_0, B200_ERR_UNSUPPORTED);
     B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -605,23 +673,13 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     B200_REQUIRE(ctx, arena_elems < (1ull << 30), B200_ERR_UNSUPPORTED);
     std::vector<PDesc> pd((size_t)count);
     std::vector<CDesc> cd((size_t)count);
-    std::vector<int> m_total((size_t)count);
     std::vector<ExportDesc> ex;
     int kmax = 0;
     for (int i = 0; i < count; i++) {
         const b200_mul_mat_args *a = &args[i];
-        // decode shapes the streaming kernels take; anything else is the caller's node-by-node path
-        B200_REQUIRE(ctx, a->type == type && !(a->flags & B200_MM_FORCE_GEMM), B200_ERR_UNSUPPORTED);
-        B200_REQUIRE(ctx, a->ne11 == 1 && a->ne12 == 1 && a->ne13 == 1 && a->ne02 == 1 && a->ne03 == 1, B200_ERR_UNSUPPORTED);
-        B200_REQUIRE(ctx, a->ne00 > 0 && a->ne00 % 256 == 0 && a->ne00 <= 32768, B200_ERR_UNSUPPORTED);
-        B200_REQUIRE(ctx, a->ne01 >= 0 && a->ne01 < (1ll << 30), B200_ERR_UNSUPPORTED);
-        B200_REQUIRE(ctx, a->src0_dev && a->src1_dev, B200_ERR_INVALID);
         const int64_t nb = a->ne00 / B200_QK;
-        B200_REQUIRE(ctx, a->src0_block_off >= 0 && a->src0_block_off + nb * a->ne01 <= a->src0_nblocks_total, B200_ERR_INVALID);
-        const int64_t mt = split ? split->m_total[i] : a->ne01;
+        const int64_t mt = m_total[i];
         const int64_t row0 = split ? split->row0[i] : 0;
-        B200_REQUIRE(ctx, row0 >= 0 && row0 + a->ne01 <= mt && mt < (1ll << 30), B200_ERR_INVALID);
-        m_total[i] = (int)mt;
         PDesc &p = pd[i];
         CDesc &c = cd[i];
         memset(&p, 0, sizeof(p));
@@ -653,42 +711,18 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
         c.flags |= (p.rs << 8) | ((Gp == 1 ? 0 : Gp == 2 ? 1 : Gp == 4 ? 2 : 3) << 16);
         B200_REQUIRE(ctx, Gp == 1 || (size_t)(c.rows_q + 1) * Gp <= (size_t)kPartFloats, B200_ERR_UNSUPPORTED);
         if (c.k > kmax) kmax = c.k;
-        // dataflow: src1 is the dst of the latest earlier op with that address, else an outside vector
-        c.src_op = -1;
+        // dataflow (plan_analyze): src1 is the dst of an earlier op, else an outside vector
+        c.src_op = src_op[i];
         c.src_plain = a->src1_dev;
-        for (int j = i - 1; j >= 0; j--) {
-            if (!args[j].dst_dev) continue;
-            if (!ranges_overlap(a->src1_dev, (size_t)a->ne00 * 4, args[j].dst_dev, (size_t)m_total[j] * 4)) continue;
-            // must be exactly that vector
-            B200_REQUIRE(ctx, (const void *)a->src1_dev == (const void *)args[j].dst_dev && m_total[j] == c.k, B200_ERR_UNSUPPORTED);
-            c.src_op = j;
-            c.ll_src = cd[j].ll_dst;
+        if (c.src_op >= 0) {
+            c.ll_src = cd[c.src_op].ll_dst;
             c.src_plain = NULL;
-            cd[j].flags |= OPF_WRITE_LL;
-            break;
+            cd[c.src_op].flags |= OPF_WRITE_LL;
         }
-        if (c.src_op < 0) B200_REQUIRE(ctx, ((uintptr_t)a->src1_dev & 15) == 0, B200_ERR_UNSUPPORTED);
         // ops that read the vector the previous op read keep using the quantized activations already in shared memory
         if (i > 0 && c.k == cd[i - 1].k && c.src_op == cd[i - 1].src_op && (c.src_op >= 0 || c.src_plain == cd[i - 1].src_plain))
             c.flags |= OPF_SAME_INPUT;
     }
-    // Hazards sequential execution would hide but dataflow execution does not: plain dst vectors that alias each other or an
-    // outside input (buffer reuse by a graph allocator).  Those graphs stay on the node-by-node path.
-    for (int i = 0; i < count; i++) {
-        if (!args[i].dst_dev) continue;
-        const size_t di = (size_t)m_total[i] * 4;
-        for (int j = 0; j < count; j++) {
-            if (j > i && args[j].dst_dev && ranges_overlap(args[i].dst_dev, di, args[j].dst_dev, (size_t)m_total[j] * 4)) {
-                b200_set_error(ctx, "b200_plan_create: dst of op %d aliases dst of op %d", i, j);
-                return B200_ERR_UNSUPPORTED;
-            }
-            if (cd[j].src_op < 0 && ranges_overlap(args[i].dst_dev, di, cd[j].src_plain, (size_t)cd[j].k * 4)) {
-                b200_set_error(ctx, "b200_plan_create: dst of op %d aliases the outside input of op %d", i, j);
-                return B200_ERR_UNSUPPORTED;
-            }
-        }
-    }
-
     b200_plan *p = (b200_plan *)calloc(1, sizeof(b200_plan));
     if (!p) return B200_ERR_ALLOC;
     p->type = type; p->nops = count; p->grid = grid; p->world = world; p->rank = rank;

@@ -230,6 +230,10 @@ typedef struct b200_plan_split {
 } b200_plan_split;
 B200_API size_t b200_plan_arena_bytes(const b200_mul_mat_args *args, int count, const b200_plan_split *split);
 B200_API int  b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, const b200_plan_split *split, b200_plan **out);
+/* the host-only analysis b200_plan_create starts with (no device needed): same status codes; src_op_out[i] (may be NULL)
+ * receives the index of the op whose dst is op i's src1, or -1 for a vector from outside the plan */
+B200_API int  b200_plan_analyze(const b200_mul_mat_args *args, int count, const b200_plan_split *split, int32_t *src_op_out);
+/* a plan must not be launched concurrently with itself (its hand-off arena and launch counter are per plan) */
 B200_API int  b200_plan_launch(b200_ctx *ctx, b200_plan *plan);      /* asynchronous on the context's stream */
 B200_API void b200_plan_destroy(b200_plan *plan);
 /* device-side timeline of the last launch (plan created with env B200_PLAN_TRACE set): [nops + 1][grid][4] ns stamps
