@@ -319,11 +319,7 @@ def run_b200(args):
                 pargs.append(a)
             psplit = None
             if world > 1:
-                psplit = qmm.PlanSplit()
-                psplit.world, psplit.rank = world, rank
-                row0_arr = (C.c_int64 * len(pargs))(*[w[1].r0 for w in weights])
-                mtot_arr = (C.c_int64 * len(pargs))(*[m for _, m, _ in mats])
-                psplit.row0, psplit.m_total = row0_arr, mtot_arr
+                psplit = rs.plan_split(qmm.PlanSplit, [w[1] for w in weights], world, rank)
                 arena = ctx.alloc(ctx.plan_arena_bytes(pargs, psplit))
                 ctx._check(ctx.lib.b200_memset(ctx.h, arena.ptr, 0, arena.nbytes))
                 allh = [None] * world

@@ -83,3 +83,16 @@ def gathered_mul_mat(dist, split: RowSplit, n: int, compute_slice, dst_full, sta
         if b > a:
             out[:, a:b].copy_(gv[r, :, : b - a])
     return out
+
+
+def plan_split(plan_split_cls, splits, world: int, rank: int):
+    """The b200_plan_split (include/ggml_b200.h) of a row-split decode plan for this rank: op i is this rank's slice
+    splits[i] (a RowSplit) of a matrix with splits[i].m rows.  peer_arena[] is left for the caller (IPC handles)."""
+    import ctypes as C
+    ps = plan_split_cls()
+    ps.world, ps.rank = world, rank
+    row0 = (C.c_int64 * len(splits))(*[s.r0 for s in splits])
+    mtot = (C.c_int64 * len(splits))(*[s.m for s in splits])
+    ps.row0, ps.m_total = row0, mtot
+    ps._keepalive = (row0, mtot)        # the struct only holds pointers
+    return ps
