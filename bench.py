@@ -61,6 +61,9 @@ WORKLOAD = "gptj6b_q4_0_decode_mul_mat_graph(28x[fc_in,v,q,k<-x; o<-v; fc_out<-f
 if os.environ.get("B200_BENCH_ORDER") == "qkv_first":      # A/B runs only: the graph in the order of examples/gpt-j/main.cpp
     LAYER_MATS = [LAYER_MATS[2], LAYER_MATS[3], LAYER_MATS[1], LAYER_MATS[0], LAYER_MATS[4], LAYER_MATS[5]]
     WORKLOAD = "gptj6b_q4_0_decode_mul_mat_graph(28x[q,k,v,fc_in<-x; o<-v; fc_out<-fc_in]+lm_head 50400x4096, n=1)"
+elif os.environ.get("B200_BENCH_ORDER") == "v_first":      # A/B runs only: v before fc_in (o <- v then lies 22 ring slots back)
+    LAYER_MATS = [LAYER_MATS[1], LAYER_MATS[0], LAYER_MATS[2], LAYER_MATS[3], LAYER_MATS[4], LAYER_MATS[5]]
+    WORKLOAD = "gptj6b_q4_0_decode_mul_mat_graph(28x[v,fc_in,q,k<-x; o<-v; fc_out<-fc_in]+lm_head 50400x4096, n=1)"
 
 
 def gptj_dag():

@@ -45,7 +45,7 @@ constexpr int kPartFloats = 4096;            // k-split partials parked per CTA 
 constexpr int kMaxOps = 1023;
 constexpr int kDescCap = 128;                // op descriptors staged in shared memory per window
 
-enum : int { OPF_SAME_INPUT = 1, OPF_WRITE_LL = 2, OPF_EXPORT = 4 };
+enum : int { OPF_SAME_INPUT = 1, OPF_WRITE_LL = 2, OPF_EXPORT = 4, OPF_SRC_RING = 8 };
 
 struct __align__(16) PDesc {                 // what the producer needs of an op
     const uint8_t *qs;       // qs plane, first row of this rank's slice
@@ -72,6 +72,7 @@ struct ExportDesc {
 struct PlanGeom {
     int slot_bytes, nslots;
     int l2_ahead;            // ops: when the producer starts op i it prefetches its rows of op i + l2_ahead into L2 (0 = off)
+    int l2_slots;            // MODE & 2: ring slots the L2 prefetch cursor runs ahead of the copies
     int ring_off, act_off, act_stride, ll_off, desc_off, bar_off, total;   // act: two buffers of act_stride bytes
 };
 
@@ -84,6 +85,7 @@ struct PlanArgs {
     void *arena[B200_MAX_RANKS];   // [rank] local; LL vectors live at the same offsets on every rank
     uint32_t *state;               // {arrived CTAs, completed launches}
     unsigned long long *trace;     // optional: [nops][gridDim.x][4] globaltimer stamps
+    const int *p_ll;               // LLRING kernels: per op, arena element offset of a src1 vector the producer feeds through the ring, or -1
 };
 
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }
@@ -204,12 +206,52 @@ __device__ __forceinline__ void ll_fetch_warp(const char *wbase, int nvalid, uin
     __syncwarp();
 }
 
-template <int TYPE>
+// The same 32 lane-tasks when the producer thread has pushed the tagged vector through the weight ring (a src1 that was complete
+// long before its consumer: no L2 round trips, the bytes are already in shared memory).  The vector lies in consecutive ring
+// slots starting at position st0; byte0 = offset of the run's first task in the vector.  Returns false (warp-uniform) when a
+// tag does not match -- the copy was taken before some CTA had stored its rows -- and the caller falls back to ll_fetch_warp.
+__device__ __forceinline__ bool ll_fetch_ring(uint32_t ring_a, uint32_t full_a, int st0, uint32_t par0, int nslots, int slot_bytes, uint32_t byte0,
+                                              int nvalid, uint32_t tag, float *wstage, int lane, float4 (&out)[4]) {
+    const int j0 = (int)(byte0 / (uint32_t)slot_bytes), j1 = (int)((byte0 + (uint32_t)nvalid * 128u - 1u) / (uint32_t)slot_bytes);
+    int p0 = st0 + j0, p1 = st0 + j1;
+    uint32_t q0 = par0, q1 = par0;
+    if (p0 >= nslots) { p0 -= nslots; q0 ^= 1u; }
+    if (p1 >= nslots) { p1 -= nslots; q1 ^= 1u; }
+    mbar_wait_a(full_a + 8u * (uint32_t)p0, q0);
+    if (j1 != j0) mbar_wait_a(full_a + 8u * (uint32_t)p1, q1);
+    const uint32_t bound = (uint32_t)(j0 + 1) * (uint32_t)slot_bytes;
+    const uint32_t base0 = ring_a + (uint32_t)p0 * (uint32_t)slot_bytes - (uint32_t)j0 * (uint32_t)slot_bytes;   // + byte offset in the vector
+    const uint32_t base1 = ring_a + (uint32_t)p1 * (uint32_t)slot_bytes - (uint32_t)j1 * (uint32_t)slot_bytes;
+    uint4 w[8];
+    const int nv8 = nvalid * 8;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int idx = j * 32 + lane < nv8 ? j * 32 + lane : 0;
+        const uint32_t b = byte0 + (uint32_t)idx * 16u;
+        w[j] = lds128((b < bound ? base0 : base1) + b);
+        ok = ok && w[j].y == tag && w[j].w == tag;
+    }
+    if (!__all_sync(0xffffffffu, ok)) return false;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (j * 32 + lane < nv8) *reinterpret_cast<float2 *>(wstage + 2 * (j * 32 + lane)) = make_float2(__uint_as_float(w[j].x), __uint_as_float(w[j].z));
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; j++) out[j] = *reinterpret_cast<const float4 *>(wstage + lane * 16 + j * 4);
+    __syncwarp();
+    return true;
+}
+
+// MODE bit 0: ring-fed src1 vectors (B200_PLAN_LL_RING); bit 1: per-slot L2 prefetch ahead of the ring (B200_PLAN_L2_SLOTS).
+// MODE 0 is the shipped kernel; the others are experiments kept out of its code.
+template <int TYPE, int MODE>
 __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_constant__ PlanArgs pa, const __grid_constant__ PlanGeom pg) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int QSB = TYPE == B200_TYPE_Q4_0 ? 16 : 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cta = blockIdx.x;
+    constexpr bool LLRING = (MODE & 1) != 0, L2SLOTS = (MODE & 2) != 0;
 
     unsigned char *ring = smem + pg.ring_off;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + pg.bar_off);
@@ -242,10 +284,38 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
             unsigned long long prod_blocked = 0;
             const uint32_t ring_a = smem_u32(ring);
             PDesc cur = pa.pdesc[0];
+            int cur_ll = LLRING ? pa.p_ll[0] : -1;
+            // L2SLOTS: a second cursor walks the same rows pg.l2_slots ring slots ahead of the copies and asks L2 for them
+            // (cp.async.bulk.prefetch.L2): while the consumers are busy with a hand-off and the ring is full, HBM keeps
+            // delivering into L2, and the ring restarts from L2 instead of from DRAM.
+            int pf_op = 0, pf_r = 0, pf_nrows = 0, pf_skip = L2SLOTS ? pg.l2_slots : 0;
+            PDesc pfd = cur, pfn = cur;
+            if (L2SLOTS) {
+                pf_nrows = pfd.rows_q + (cta < pfd.rows_rem ? 1 : 0);
+                if (pa.nops > 1) pfn = pa.pdesc[1];
+            }
 #pragma unroll 1
             for (int op = 0; op < pa.nops; op++) {
                 PDesc nxt = cur;
-                if (op + 1 < pa.nops) nxt = pa.pdesc[op + 1];
+                int nxt_ll = -1;
+                if (op + 1 < pa.nops) {
+                    nxt = pa.pdesc[op + 1];
+                    if (LLRING) nxt_ll = pa.p_ll[op + 1];
+                }
+                if (LLRING && cur_ll >= 0) {
+                    // this op's src1 was finished long ago: its tagged vector travels through the ring ahead of the op's weights
+                    const char *src = arena_local + (size_t)cur_ll * 8;
+                    const int bytes = cur.k * 8;
+                    for (int off = 0; off < bytes; off += pg.slot_bytes) {
+                        const uint32_t nbytes = (uint32_t)min(pg.slot_bytes, bytes - off);
+                        const uint32_t fb = smem_u32(&full_bar[st]);
+                        mbar_wait(&empty_bar[st], par ^ 1u);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(nbytes) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ring_a + (uint32_t)(st * pg.slot_bytes)),
+                                     "l"(src + off), "r"(nbytes), "r"(fb) : "memory");
+                        if (++st == nslots) { st = 0; par ^= 1u; }
+                    }
+                }
                 if (pg.l2_ahead > 0 && op + pg.l2_ahead < pa.nops) {
                     // HBM -> L2 for an op the ring will reach later (optional; off by default)
                     const PDesc pf = pa.pdesc[op + pg.l2_ahead];
@@ -274,6 +344,28 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
                         mbar_wait(&empty_bar[st], par ^ 1u);
                     }
                     const uint32_t dst = ring_a + (uint32_t)(st * pg.slot_bytes);
+                    if (L2SLOTS) {
+                        // one slot's worth at the prefetch cursor (the first l2_slots steps only move it ahead)
+                        while (pf_op < pa.nops && pf_r >= pf_nrows) {
+                            pf_op++;
+                            pfd = pfn;
+                            pf_r = 0;
+                            pf_nrows = pfd.rows_q + (cta < pfd.rows_rem ? 1 : 0);
+                            if (pf_op + 1 < pa.nops) pfn = pa.pdesc[pf_op + 1];      // consumed at the next crossing
+                        }
+                        if (pf_op < pa.nops) {
+                            if (pf_skip > 0) {
+                                pf_skip--;
+                            } else {
+                                const int pnb = pfd.k >> 5;
+                                const long long prow = (long long)cta * pfd.rows_q + min(cta, pfd.rows_rem) + pf_r;
+                                const int prows = min(pfd.rs, pf_nrows - pf_r);
+                                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pfd.qs + prow * pnb * QSB), "r"((uint32_t)(prows * pnb * QSB)) : "memory");
+                                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint8_t *>(pfd.d) + prow * pnb * 2), "r"((uint32_t)(prows * pnb * 2)) : "memory");
+                            }
+                            pf_r += pfd.rs;
+                        }
+                    }
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)(rows * (row_qs + row_sc))) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                                  "l"(gq + (size_t)r * row_qs), "r"((uint32_t)(rows * row_qs)), "r"(fb) : "memory");
@@ -282,6 +374,7 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
                     if (++st == nslots) { st = 0; par ^= 1u; }
                 }
                 cur = nxt;
+                cur_ll = nxt_ll;
             }
             if (pa.trace) pa.trace[(size_t)pa.nops * gridDim.x * 4 + (size_t)cta * 4 + 0] = prod_blocked;
         }
@@ -297,6 +390,7 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
         uint32_t par0 = 0;
         int prevG = 1;
         unsigned long long cons_blocked = 0, quant_time = 0;
+        unsigned ring_miss = 0;     // LLRING: runs of a ring-fed vector this warp had to re-fetch from L2
         RowCtx<TYPE> c;
         c.a_lo = c.a_hi = c.a_d = c.a_s = smem_u32(smem + pg.act_off);
 #pragma unroll
@@ -348,6 +442,10 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
                 const int src_op = o->src_op;
                 const bool ll_in = src_op >= 0;
                 const uint32_t src_tag = (epoch << 10) | (uint32_t)(src_op & 1023);
+                const bool ring_src = LLRING && (flags & OPF_SRC_RING) != 0;
+                // ring-fed src1: every warp reads slots it does not own, so all earlier fills must have been consumed first
+                // (a parity wait on a slot whose previous fill is still pending would pass a lap early)
+                if (ring_src) cbar();
                 const char *xsrc = ll_in ? arena_local + (size_t)o->ll_src * 8 : reinterpret_cast<const char *>(o->src_plain);
                 constexpr int kQB = 4 / kRowSplit;
                 const int tpc = nb * 2;      // lane-tasks: (block, half) = 16 consecutive floats
@@ -359,7 +457,12 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
                         const int tb = base + u * kCT + warp * 32;      // first lane-task of this warp
                         if (tb >= tpc) continue;
                         if (ll_in) {
-                            ll_fetch_warp(xsrc + (size_t)tb * 128, min(32, tpc - tb), src_tag, llstage, lane, v[u]);
+                            bool got = false;
+                            if (ring_src) {
+                                got = ll_fetch_ring(ring_a, full_a, st0, par0, nslots, pg.slot_bytes, (uint32_t)tb * 128u, min(32, tpc - tb), src_tag, llstage, lane, v[u]);
+                                if (!got) ring_miss++;
+                            }
+                            if (!got) ll_fetch_warp(xsrc + (size_t)tb * 128, min(32, tpc - tb), src_tag, llstage, lane, v[u]);
                         } else {
                             const int t = min(tb + lane, tpc - 1);
                             const float4 *src = reinterpret_cast<const float4 *>(xsrc) + (size_t)t * 4;
@@ -399,6 +502,15 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
                                 if (TYPE == B200_TYPE_Q4_0) reinterpret_cast<int *>(act + k + (size_t)nb * 4)[b] = 8 * sq;
                             }
                         }
+                    }
+                }
+                if (ring_src) {
+                    // this warp is done with the vector's slots (each of the 8 warps arrives once per slot)
+                    __syncwarp();
+                    const int nls = (k * 8 + pg.slot_bytes - 1) / pg.slot_bytes;
+                    for (int j = 0; j < nls; j++) {
+                        if (lane == 0) mbar_arrive_cnt(empty_a + 8u * (uint32_t)st0, 1u);
+                        if (++st0 == nslots) { st0 = 0; par0 ^= 1u; }
                     }
                 }
                 cbar();
@@ -503,6 +615,7 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
         if (pa.trace && lane == 0 && warp == 2) {
             pa.trace[(size_t)pa.nops * gridDim.x * 4 + (size_t)cta * 4 + 1] = cons_blocked;
             pa.trace[(size_t)pa.nops * gridDim.x * 4 + (size_t)cta * 4 + 2] = quant_time;
+            pa.trace[(size_t)pa.nops * gridDim.x * 4 + (size_t)cta * 4 + 3] = ring_miss;
         }
         // ---- row-split plans: ops marked EXPORT leave their COMPLETE vector (all ranks' slices) in the local plain dst ----
         for (int e = 0; e < pa.nexports; e++) {
@@ -533,12 +646,20 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
 
 }  // namespace
 
+typedef void (*plan_kernel_fn)(const PlanArgs, const PlanGeom);
+static plan_kernel_fn plan_kernel_for(int type, int mode) {
+    if (type == B200_TYPE_Q4_0) return mode == 1 ? plan_kernel<B200_TYPE_Q4_0, 1> : mode == 2 ? plan_kernel<B200_TYPE_Q4_0, 2> : plan_kernel<B200_TYPE_Q4_0, 0>;
+    return mode == 1 ? plan_kernel<B200_TYPE_Q8_0, 1> : mode == 2 ? plan_kernel<B200_TYPE_Q8_0, 2> : plan_kernel<B200_TYPE_Q8_0, 0>;
+}
+
 struct b200_plan {
     int type, nops, grid, world, rank;
     PlanGeom geom;
     PDesc *pdesc_dev;
     CDesc *cdesc_dev;
     ExportDesc *exports_dev;
+    int *pll_dev;               // ring-fed src1 vectors (null: none)
+    int mode;                   // kernel variant: 0 = shipped; bit 0 ring-fed src1, bit 1 per-slot L2 prefetch
     void *arena_own;            // allocated here when world == 1
     uint32_t *state_dev;
     unsigned long long *trace_dev;
@@ -640,6 +761,7 @@ void b200_plan_destroy(b200_plan *p) {
     if (p->pdesc_dev) cudaFree(p->pdesc_dev);
     if (p->cdesc_dev) cudaFree(p->cdesc_dev);
     if (p->exports_dev) cudaFree(p->exports_dev);
+    if (p->pll_dev) cudaFree(p->pll_dev);
     if (p->arena_own) cudaFree(p->arena_own);
     if (p->state_dev) cudaFree(p->state_dev);
     if (p->trace_dev) cudaFree(p->trace_dev);
@@ -732,6 +854,8 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     g.slot_bytes = slot_bytes;
     g.l2_ahead = 0;
     if (const char *e = getenv("B200_PLAN_L2_AHEAD")) { const int v = atoi(e); if (v >= 0 && v <= 31) g.l2_ahead = v; }
+    g.l2_slots = 0;
+    if (const char *e = getenv("B200_PLAN_L2_SLOTS")) { const int v = atoi(e); if (v >= 0 && v <= 256) g.l2_slots = v; }
     const int act_bytes = (int)b200_align_up((size_t)kmax + (size_t)(kmax / 32) * 8, 128);   // int8 planes + fp32 scales + 8 * sums
     const int ll_bytes = kCW * 2048 > kPartFloats * 4 ? kCW * 2048 : kPartFloats * 4;       // LL staging, aliased by the k-split partials
     const int desc_bytes = kDescCap * (int)sizeof(CDesc);
@@ -745,6 +869,33 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     if (const char *e = getenv("B200_PLAN_SLOTS")) { const int v = atoi(e); if (v >= 2 && v <= kMaxSlots && v * g.slot_bytes <= max_smem - fixed) nslots = v; }
     if (nslots < 2) { free(p); b200_set_error(ctx, "b200_plan_create: k = %d leaves no room for the weight ring", kmax); return B200_ERR_UNSUPPORTED; }
     g.nslots = nslots;
+    // Ring-fed src1 (B200_PLAN_LL_RING = n > 0, experimental): a src1 produced by an op that lies at least n ring slots (per
+    // CTA) back in the stream is complete on every CTA long before the producer thread reaches its consumer, so the
+    // producer copies the tagged vector through the ring like weights and the consumers skip the L2 round trips.  A copy
+    // taken too early is caught by its tags (the consumers then fetch from L2 as usual).
+    std::vector<int> pll((size_t)count, -1);
+    bool any_ring = false;
+    if (const char *e = getenv("B200_PLAN_LL_RING")) {
+        // n > 0: at least n slots in between; -1: every src1 produced two or more ops back; -2: every src1 produced in the plan
+        // (the negative settings exist for the tests: copies taken too early must be caught by their tags)
+        const int min_slots = atoi(e);
+        for (int i = 0; min_slots != 0 && i < count; i++) {
+            CDesc &c = cd[i];
+            if (c.src_op < 0 || (c.flags & OPF_SAME_INPUT)) continue;
+            const int nls = (c.k * 8 + g.slot_bytes - 1) / g.slot_bytes;
+            if (nls > nslots) continue;
+            long long between = 0;
+            for (int j = c.src_op + 1; j < i; j++) {
+                between += cd[j].rows_q / pd[j].rs;
+                if (pll[j] >= 0) between += (cd[j].k * 8 + g.slot_bytes - 1) / g.slot_bytes;
+            }
+            if (min_slots > 0 && between < min_slots) continue;
+            if (min_slots == -1 && c.src_op > i - 2) continue;
+            pll[i] = c.ll_src;
+            c.flags |= OPF_SRC_RING;
+            any_ring = true;
+        }
+    }
     g.ring_off = 0;
     g.act_off = nslots * g.slot_bytes;
     g.act_stride = act_bytes;
@@ -756,6 +907,8 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     cudaError_t e = cudaMalloc((void **)&p->pdesc_dev, sizeof(PDesc) * (size_t)count);
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->cdesc_dev, sizeof(CDesc) * (size_t)count);
     if (e == cudaSuccess && !ex.empty()) e = cudaMalloc((void **)&p->exports_dev, sizeof(ExportDesc) * ex.size());
+    if (e == cudaSuccess && any_ring) e = cudaMalloc((void **)&p->pll_dev, sizeof(int) * (size_t)count);
+    if (e == cudaSuccess && any_ring) e = cudaMemcpy(p->pll_dev, pll.data(), sizeof(int) * (size_t)count, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->state_dev, 16);
     if (e == cudaSuccess && world == 1) e = cudaMalloc(&p->arena_own, p->arena_bytes);
     if (e == cudaSuccess && getenv("B200_PLAN_TRACE")) {
@@ -767,10 +920,8 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     if (e == cudaSuccess && !ex.empty()) e = cudaMemcpy(p->exports_dev, ex.data(), sizeof(ExportDesc) * ex.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(p->state_dev, 0, 16);
     if (e == cudaSuccess && world == 1) e = cudaMemset(p->arena_own, 0, p->arena_bytes);
-    if (e == cudaSuccess) {
-        auto kern = type == B200_TYPE_Q4_0 ? plan_kernel<B200_TYPE_Q4_0> : plan_kernel<B200_TYPE_Q8_0>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.total);
-    }
+    p->mode = any_ring ? 1 : (g.l2_slots > 0 ? 2 : 0);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel_for(type, p->mode), cudaFuncAttributeMaxDynamicSharedMemorySize, g.total);
     if (e != cudaSuccess) {
         b200_set_error(ctx, "b200_plan_create: %s", cudaGetErrorString(e));
         (void)cudaGetLastError();
@@ -789,6 +940,7 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     for (int r = 0; r < world; r++) pa.arena[r] = split ? split->peer_arena[r] : p->arena_own;
     pa.state = p->state_dev;
     pa.trace = p->trace_dev;
+    pa.p_ll = p->pll_dev;
     *out = p;
     return B200_OK;
 }
@@ -796,10 +948,7 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
 int b200_plan_launch(b200_ctx *ctx, b200_plan *p) {
     B200_REQUIRE(ctx, ctx && p, B200_ERR_INVALID);
     B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    if (p->type == B200_TYPE_Q4_0)
-        plan_kernel<B200_TYPE_Q4_0><<<p->grid, kPlanThreads, p->geom.total, ctx->stream>>>(p->args, p->geom);
-    else
-        plan_kernel<B200_TYPE_Q8_0><<<p->grid, kPlanThreads, p->geom.total, ctx->stream>>>(p->args, p->geom);
+    plan_kernel_for(p->type, p->mode)<<<p->grid, kPlanThreads, p->geom.total, ctx->stream>>>(p->args, p->geom);
     ctx->launches++;
     B200_CUDA_TRY(ctx, cudaGetLastError());
     return B200_OK;

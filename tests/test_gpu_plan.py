@@ -52,6 +52,22 @@ DAGS = {
 @pytest.mark.parametrize("qtype", [Q4_0, Q8_0])
 @pytest.mark.parametrize("dag", sorted(DAGS))
 def test_plan_matches_oracle_and_node_by_node(gpu_ctx, oracle, qmm, qtype, dag):
+    check_dag(gpu_ctx, oracle, qmm, qtype, dag)
+
+
+@pytest.mark.parametrize("case", [(Q4_0, "block_pair"), (Q8_0, "block_pair"), (Q4_0, "ragged_chain"), (Q4_0, "many_ops"), (Q8_0, "k_split_8")],
+                         ids=lambda c: f"{c[1]}-{c[0]}")
+@pytest.mark.parametrize("ring", ["-2", "-1", "3"])
+def test_plan_with_ring_fed_src1(gpu_ctx, oracle, qmm, monkeypatch, case, ring):
+    """B200_PLAN_LL_RING: src1 vectors produced inside the plan travel through the weight ring (copied by the producer
+    thread) instead of being fetched from L2 by the consumers.  -2 feeds EVERY such vector that way, also those whose
+    producer is the op right before (the copy is then always taken too early: the tag check must catch it and fall back),
+    -1 those produced two or more ops back, 3 the production rule (at least 3 ring slots in between).  Same bits as ever."""
+    monkeypatch.setenv("B200_PLAN_LL_RING", ring)
+    check_dag(gpu_ctx, oracle, qmm, case[0], case[1])
+
+
+def check_dag(gpu_ctx, oracle, qmm, qtype, dag):
     nodes = DAGS[dag]
     ws = build_dag(oracle, qmm, gpu_ctx, qtype, nodes, seed=len(nodes) * 7 + qtype)
     rng = np.random.default_rng(99)
