@@ -39,13 +39,14 @@ constexpr int kRowSplit = B200_PLAN_ROW_SPLIT;
 constexpr int kCW = 8 * kRowSplit;           // consumer warps
 constexpr int kCT = kCW * 32;                // consumer threads
 constexpr int kPlanThreads = (kCW + 1) * 32;         // consumers + the producer warp
+constexpr int plan_threads(int mode) { return (mode & 4) ? kPlanThreads + 32 : kPlanThreads; }   // MODE 4: + the publisher warp
 constexpr int kSegBlocks = 128;              // blocks of k per warp-segment (4 per lane)
 constexpr int kMaxSlots = 24;
 constexpr int kPartFloats = 4096;            // k-split partials parked per CTA per op: rows_per_cta * G (aliases the LL staging)
 constexpr int kMaxOps = 1023;
 constexpr int kDescCap = 128;                // op descriptors staged in shared memory per window
 
-enum : int { OPF_SAME_INPUT = 1, OPF_WRITE_LL = 2, OPF_EXPORT = 4, OPF_SRC_RING = 8 };
+enum : int { OPF_SAME_INPUT = 1, OPF_WRITE_LL = 2, OPF_EXPORT = 4, OPF_SRC_RING = 8, OPF_SRC_LLQ = 16 };
 
 struct __align__(16) PDesc {                 // what the producer needs of an op
     const uint8_t *qs;       // qs plane, first row of this rank's slice
@@ -57,7 +58,7 @@ struct __align__(16) PDesc {                 // what the producer needs of an op
 static_assert(sizeof(PDesc) == 32, "PDesc layout");
 struct __align__(16) CDesc {                 // what the consumers need (staged in shared memory, kDescCap at a time)
     float *dst_plain;        // local plain fp32 vector [m_total] or null
-    const float *src_plain;  // src1 when it comes from outside the plan (src_op < 0)
+    const float *src_plain;  // src1 when it comes from outside the plan (src_op < 0); OPF_SRC_LLQ: the arena offset of the quantized vector
     int ll_dst, ll_src;      // element offsets in the arena of this op's / its producer's LL vector
     int k, flags;
     int rows_q, rows_rem;
@@ -68,12 +69,16 @@ struct ExportDesc {
     float *dst;
     int ll, m_total, op, pad;
 };
+struct PubDesc {             // MODE 4: an in-plan src1 vector that is quantized once per GPU (for the op `op` that reads it)
+    int ll_src, k, src_op, llq, op, pad[3];
+};
 
 struct PlanGeom {
     int slot_bytes, nslots;
     int l2_ahead;            // ops: when the producer starts op i it prefetches its rows of op i + l2_ahead into L2 (0 = off)
     int l2_slots;            // MODE & 2: ring slots the L2 prefetch cursor runs ahead of the copies
     int ring_off, act_off, act_stride, ll_off, desc_off, bar_off, total;   // act: two buffers of act_stride bytes
+    int pub_off;             // MODE 4: 2 KB of staging for the publisher warp
 };
 
 struct PlanArgs {
@@ -86,6 +91,8 @@ struct PlanArgs {
     uint32_t *state;               // {arrived CTAs, completed launches}
     unsigned long long *trace;     // optional: [nops][gridDim.x][4] globaltimer stamps
     const int *p_ll;               // LLRING kernels: per op, arena element offset of a src1 vector the producer feeds through the ring, or -1
+    const PubDesc *pub;            // MODE 4: the publisher warp's work list, in op order
+    int npub;
 };
 
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }
@@ -244,14 +251,16 @@ __device__ __forceinline__ bool ll_fetch_ring(uint32_t ring_a, uint32_t full_a, 
 }
 
 // MODE bit 0: ring-fed src1 vectors (B200_PLAN_LL_RING); bit 1: per-slot L2 prefetch ahead of the ring (B200_PLAN_L2_SLOTS).
+// bit 2: a long src1 (B200_PLAN_LLQ) is quantized ONCE per GPU -- every CTA does 1/grid of its blocks and publishes them as tagged
+// words -- instead of once per CTA; each CTA then fetches 80 bytes per block instead of 256 and does no arithmetic.
 // MODE 0 is the shipped kernel; the others are experiments kept out of its code.
 template <int TYPE, int MODE>
-__global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_constant__ PlanArgs pa, const __grid_constant__ PlanGeom pg) {
+__global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __grid_constant__ PlanArgs pa, const __grid_constant__ PlanGeom pg) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int QSB = TYPE == B200_TYPE_Q4_0 ? 16 : 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cta = blockIdx.x;
-    constexpr bool LLRING = (MODE & 1) != 0, L2SLOTS = (MODE & 2) != 0;
+    constexpr bool LLRING = (MODE & 1) != 0, L2SLOTS = (MODE & 2) != 0, LLQ = (MODE & 4) != 0;
 
     unsigned char *ring = smem + pg.ring_off;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + pg.bar_off);
@@ -378,7 +387,50 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
             }
             if (pa.trace) pa.trace[(size_t)pa.nops * gridDim.x * 4 + (size_t)cta * 4 + 0] = prod_blocked;
         }
-    } else {
+    } else if (LLQ && warp == kCW + 1) {
+        // ===== publisher (MODE 4): for every long in-plan src1, in op order, this CTA's share of the blocks
+        // [cta * nb / grid, (cta + 1) * nb / grid): wait for the fp32 values (tagged vector of the producing op), quantize_row_q8_0,
+        // publish.  Runs as far ahead of the consumers as the data allows; every rank does the same for its own arena. =====
+        float *pstage = reinterpret_cast<float *>(smem + pg.pub_off);
+        uint2 *arena_w = reinterpret_cast<uint2 *>(const_cast<char *>(arena_local));
+#pragma unroll 1
+        for (int i = 0; i < pa.npub; i++) {
+            const PubDesc d = pa.pub[i];
+            const int nb = d.k >> 5;
+            const int b_lo = (cta * nb) / (int)gridDim.x, b_hi = ((cta + 1) * nb) / (int)gridDim.x;
+            const int nt = 2 * (b_hi - b_lo);
+            if (nt <= 0) continue;
+            const uint32_t src_tag = (epoch << 10) | (uint32_t)(d.src_op & 1023), tag = (epoch << 10) | (uint32_t)d.op;
+            float4 vv[4];
+            ll_fetch_warp(arena_local + (size_t)d.ll_src * 8 + (size_t)(2 * b_lo) * 128, nt, src_tag, pstage, lane, vv);
+            const int b = b_lo + (lane >> 1), h = lane & 1;
+            float amax = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(vv[j].x), fabsf(vv[j].y)), fmaxf(fabsf(vv[j].z), fabsf(vv[j].w))));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+            const float id = amax != 0.0f ? __fdiv_rn(127.f, amax) : 0.0f;
+            uint32_t pk[4];
+            int sq = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int q0 = __float2int_rn(__fmul_rn(vv[j].x, id)), q1 = __float2int_rn(__fmul_rn(vv[j].y, id));
+                const int q2 = __float2int_rn(__fmul_rn(vv[j].z, id)), q3 = __float2int_rn(__fmul_rn(vv[j].w, id));
+                sq += q0 + q1 + q2 + q3;
+                pk[j] = (uint32_t)(q0 & 0xff) | ((uint32_t)(q1 & 0xff) << 8) | ((uint32_t)(q2 & 0xff) << 16) | ((uint32_t)(q3 & 0xff) << 24);
+            }
+            sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+            if (lane < nt) {
+                uint2 *blk = arena_w + (size_t)d.llq + (size_t)b * 10;
+#pragma unroll
+                for (int j = 0; j < 4; j++) ll_store(blk, h * 4 + j, __uint_as_float(pk[j]), tag);
+                if (h == 0) {
+                    ll_store(blk, 8, __half2float(__float2half_rn(__fdiv_rn(amax, 127.f))), tag);
+                    ll_store(blk, 9, __int_as_float(8 * sq), tag);
+                }
+            }
+        }
+    } else if (!LLQ || warp < kCW) {
         // ===== consumers =====
         const uint32_t ring_a = smem_u32(ring);
         const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
@@ -449,6 +501,46 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
                 const char *xsrc = ll_in ? arena_local + (size_t)o->ll_src * 8 : reinterpret_cast<const char *>(o->src_plain);
                 constexpr int kQB = 4 / kRowSplit;
                 const int tpc = nb * 2;      // lane-tasks: (block, half) = 16 consecutive floats
+                const bool llq_src = LLQ && (flags & OPF_SRC_LLQ) != 0;
+                if (llq_src) {
+                    // ---- the vector was quantized once per GPU by the publisher warps (below): 10 tagged words per block
+                    // {q[0..31] as 8 words, fp32 d, 8 * sum(q)} in the local arena.
+                    uint2 *llq = reinterpret_cast<uint2 *>(const_cast<char *>(arena_local)) + (size_t)(uintptr_t)o->src_plain;
+                    if (tr && threadIdx.x == 0) tr[0] = gtime();
+                    // every warp: two blocks per thread and round trip, straight into the activation planes
+#pragma unroll 1
+                    for (int bb = 0; bb < nb; bb += 2 * kCT) {
+                        const int bA = bb + (int)threadIdx.x, bB = bb + kCT + (int)threadIdx.x;
+                        const uint4 *pA = reinterpret_cast<const uint4 *>(llq + (size_t)min(bA, nb - 1) * 10);
+                        const uint4 *pB = reinterpret_cast<const uint4 *>(llq + (size_t)min(bB, nb - 1) * 10);
+                        const int wlast = min(bb + warp * 32 + 31, nb - 1);       // probe target after a miss: this warp's last block
+                        uint4 wa[5], wb[5];
+                        for (;;) {
+                            bool ok = true;
+#pragma unroll
+                            for (int j = 0; j < 5; j++) {
+                                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wa[j].x), "=r"(wa[j].y), "=r"(wa[j].z), "=r"(wa[j].w) : "l"(pA + j));
+                                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wb[j].x), "=r"(wb[j].y), "=r"(wb[j].z), "=r"(wb[j].w) : "l"(pB + j));
+                            }
+#pragma unroll
+                            for (int j = 0; j < 5; j++) ok = ok && wa[j].y == tag && wa[j].w == tag && wb[j].y == tag && wb[j].w == tag;
+                            if (__all_sync(0xffffffffu, ok)) break;
+                            ll_probe(llq + (size_t)wlast * 10 + 9, tag);
+                        }
+                        if (bA < nb) {
+                            *reinterpret_cast<uint4 *>(act + (size_t)bA * 16) = make_uint4(wa[0].x, wa[0].z, wa[1].x, wa[1].z);
+                            *reinterpret_cast<uint4 *>(act + (size_t)(k >> 1) + (size_t)bA * 16) = make_uint4(wa[2].x, wa[2].z, wa[3].x, wa[3].z);
+                            reinterpret_cast<uint32_t *>(act + k)[bA] = wa[4].x;
+                            if (TYPE == B200_TYPE_Q4_0) reinterpret_cast<uint32_t *>(act + k + (size_t)nb * 4)[bA] = wa[4].z;
+                        }
+                        if (bB < nb) {
+                            *reinterpret_cast<uint4 *>(act + (size_t)bB * 16) = make_uint4(wb[0].x, wb[0].z, wb[1].x, wb[1].z);
+                            *reinterpret_cast<uint4 *>(act + (size_t)(k >> 1) + (size_t)bB * 16) = make_uint4(wb[2].x, wb[2].z, wb[3].x, wb[3].z);
+                            reinterpret_cast<uint32_t *>(act + k)[bB] = wb[4].x;
+                            if (TYPE == B200_TYPE_Q4_0) reinterpret_cast<uint32_t *>(act + k + (size_t)nb * 4)[bB] = wb[4].z;
+                        }
+                    }
+                } else {
 #pragma unroll 1
                 for (int base = 0; base < tpc; base += kCT * kQB) {
                     float4 v[kQB][4];
@@ -503,6 +595,7 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
                             }
                         }
                     }
+                }
                 }
                 if (ring_src) {
                     // this warp is done with the vector's slots (each of the 8 warps arrives once per slot)
@@ -648,8 +741,9 @@ __global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const __grid_cons
 
 typedef void (*plan_kernel_fn)(const PlanArgs, const PlanGeom);
 static plan_kernel_fn plan_kernel_for(int type, int mode) {
-    if (type == B200_TYPE_Q4_0) return mode == 1 ? plan_kernel<B200_TYPE_Q4_0, 1> : mode == 2 ? plan_kernel<B200_TYPE_Q4_0, 2> : plan_kernel<B200_TYPE_Q4_0, 0>;
-    return mode == 1 ? plan_kernel<B200_TYPE_Q8_0, 1> : mode == 2 ? plan_kernel<B200_TYPE_Q8_0, 2> : plan_kernel<B200_TYPE_Q8_0, 0>;
+    if (type == B200_TYPE_Q4_0)
+        return mode == 1 ? plan_kernel<B200_TYPE_Q4_0, 1> : mode == 2 ? plan_kernel<B200_TYPE_Q4_0, 2> : mode == 4 ? plan_kernel<B200_TYPE_Q4_0, 4> : plan_kernel<B200_TYPE_Q4_0, 0>;
+    return mode == 1 ? plan_kernel<B200_TYPE_Q8_0, 1> : mode == 2 ? plan_kernel<B200_TYPE_Q8_0, 2> : mode == 4 ? plan_kernel<B200_TYPE_Q8_0, 4> : plan_kernel<B200_TYPE_Q8_0, 0>;
 }
 
 struct b200_plan {
@@ -659,6 +753,7 @@ struct b200_plan {
     CDesc *cdesc_dev;
     ExportDesc *exports_dev;
     int *pll_dev;               // ring-fed src1 vectors (null: none)
+    PubDesc *pub_dev;           // MODE 4 publisher work list
     int mode;                   // kernel variant: 0 = shipped; bit 0 ring-fed src1, bit 1 per-slot L2 prefetch
     void *arena_own;            // allocated here when world == 1
     uint32_t *state_dev;
@@ -667,12 +762,29 @@ struct b200_plan {
     size_t arena_bytes;
 };
 
-static size_t plan_arena_elems(const b200_mul_mat_args *args, int count, const b200_plan_split *split, std::vector<long long> *offs) {
+// Smallest k whose in-plan src1 is quantized once per GPU (kernel MODE 4).  Default 8192 on one GPU (measured: GPT-J fc_out,
+// k = 16384, 722 vs 741 us per token; at k = 4096 the second exchange costs more than it saves: 811), off for row-split plans
+// (not measured there yet); B200_PLAN_LLQ=k overrides, 0 = off.
+static int plan_llq_min_k(int world) {
+    const char *e = getenv("B200_PLAN_LLQ");
+    const int v = e ? atoi(e) : (world == 1 ? 8192 : 0);
+    return v > 0 ? v : 0;
+}
+
+static size_t plan_arena_elems(const b200_mul_mat_args *args, int count, const b200_plan_split *split, std::vector<long long> *offs,
+                               std::vector<long long> *llq_offs = nullptr) {
     size_t total = 0;
     for (int i = 0; i < count; i++) {
         const long long mt = split && split->m_total ? split->m_total[i] : args[i].ne01;
         if (offs) offs->push_back((long long)total);
         total += (size_t)((mt + 15) / 16 * 16);      // 128-byte aligned LL vectors
+    }
+    // quantized src1 vectors (kernel MODE 4): 10 tagged words per block of 32, room for every op that is long enough
+    const int mink = plan_llq_min_k(split ? split->world : 1);
+    for (int i = 0; i < count; i++) {
+        const bool room = mink > 0 && args[i].ne00 >= mink;
+        if (llq_offs) llq_offs->push_back(room ? (long long)total : -1);
+        if (room) total += (size_t)((args[i].ne00 / B200_QK * 10 + 15) / 16 * 16);
     }
     return total;
 }
@@ -762,6 +874,7 @@ void b200_plan_destroy(b200_plan *p) {
     if (p->cdesc_dev) cudaFree(p->cdesc_dev);
     if (p->exports_dev) cudaFree(p->exports_dev);
     if (p->pll_dev) cudaFree(p->pll_dev);
+    if (p->pub_dev) cudaFree(p->pub_dev);
     if (p->arena_own) cudaFree(p->arena_own);
     if (p->state_dev) cudaFree(p->state_dev);
     if (p->trace_dev) cudaFree(p->trace_dev);
@@ -790,8 +903,11 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     if (const char *e = getenv("B200_PLAN_SLOT_ROWS")) { const int v = atoi(e); if (v >= 8 && v <= 16) slot_rows = v; }
     const int slot_bytes = slot_rows * 128 * (qsb + 2);
 
-    std::vector<long long> ll_off;
-    const size_t arena_elems = plan_arena_elems(args, count, split, &ll_off);
+    std::vector<long long> ll_off, llq_off;
+    const size_t arena_elems = plan_arena_elems(args, count, split, &ll_off, &llq_off);
+    std::vector<PubDesc> pubs;
+    int llq_dist = 2;
+    if (const char *e = getenv("B200_PLAN_LLQ_DIST")) { const int v = atoi(e); if (v >= 1) llq_dist = v; }
     B200_REQUIRE(ctx, arena_elems < (1ull << 30), B200_ERR_UNSUPPORTED);
     std::vector<PDesc> pd((size_t)count);
     std::vector<CDesc> cd((size_t)count);
@@ -844,6 +960,17 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
         // ops that read the vector the previous op read keep using the quantized activations already in shared memory
         if (i > 0 && c.k == cd[i - 1].k && c.src_op == cd[i - 1].src_op && (c.src_op >= 0 || c.src_plain == cd[i - 1].src_plain))
             c.flags |= OPF_SAME_INPUT;
+        // a long in-plan src1: quantized once per GPU, every CTA 1/grid of the blocks (at most 16 blocks per CTA: one warp's run)
+        // (only vectors produced at least B200_PLAN_LLQ_DIST ops back, default 2: behind a producer that has just finished, the
+        // publication would be a second exchange on the critical path)
+        if (c.src_op >= 0 && !(c.flags & OPF_SAME_INPUT) && llq_off[i] >= 0 && (nb + grid - 1) / grid + 1 <= 16 && i - c.src_op >= llq_dist) {
+            c.flags |= OPF_SRC_LLQ;
+            c.src_plain = (const float *)(uintptr_t)llq_off[i];
+            PubDesc pb;
+            memset(&pb, 0, sizeof(pb));
+            pb.ll_src = c.ll_src; pb.k = c.k; pb.src_op = c.src_op; pb.llq = (int)llq_off[i]; pb.op = i;
+            pubs.push_back(pb);
+        }
     }
     b200_plan *p = (b200_plan *)calloc(1, sizeof(b200_plan));
     if (!p) return B200_ERR_ALLOC;
@@ -861,7 +988,7 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     const int desc_bytes = kDescCap * (int)sizeof(CDesc);
     const int bar_bytes = 2 * kMaxSlots * 8 + 64;
     const int max_smem = 227 * 1024;
-    const int fixed = 2 * act_bytes + ll_bytes + desc_bytes + bar_bytes;
+    const int fixed = 2 * act_bytes + ll_bytes + desc_bytes + bar_bytes + (pubs.empty() ? 0 : 2048);
     // ring: as many slots as fit, a multiple of the consumer warps when possible (every warp then owns the same number)
     int nslots = (max_smem - fixed) / g.slot_bytes;
     if (nslots > kMaxSlots) nslots = kMaxSlots;
@@ -903,6 +1030,8 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     g.desc_off = g.ll_off + ll_bytes;
     g.bar_off = g.desc_off + desc_bytes;
     g.total = g.bar_off + bar_bytes;
+    g.pub_off = g.total;
+    if (!pubs.empty()) g.total += 2048;          // the publisher warp's staging (MODE 4)
 
     cudaError_t e = cudaMalloc((void **)&p->pdesc_dev, sizeof(PDesc) * (size_t)count);
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->cdesc_dev, sizeof(CDesc) * (size_t)count);
@@ -920,7 +1049,10 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     if (e == cudaSuccess && !ex.empty()) e = cudaMemcpy(p->exports_dev, ex.data(), sizeof(ExportDesc) * ex.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(p->state_dev, 0, 16);
     if (e == cudaSuccess && world == 1) e = cudaMemset(p->arena_own, 0, p->arena_bytes);
-    p->mode = any_ring ? 1 : (g.l2_slots > 0 ? 2 : 0);
+    const bool any_llq = !any_ring && !pubs.empty();
+    p->mode = any_ring ? 1 : any_llq ? 4 : (g.l2_slots > 0 ? 2 : 0);
+    if (e == cudaSuccess && any_llq) e = cudaMalloc((void **)&p->pub_dev, sizeof(PubDesc) * pubs.size());
+    if (e == cudaSuccess && any_llq) e = cudaMemcpy(p->pub_dev, pubs.data(), sizeof(PubDesc) * pubs.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel_for(type, p->mode), cudaFuncAttributeMaxDynamicSharedMemorySize, g.total);
     if (e != cudaSuccess) {
         b200_set_error(ctx, "b200_plan_create: %s", cudaGetErrorString(e));
@@ -941,6 +1073,8 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     pa.state = p->state_dev;
     pa.trace = p->trace_dev;
     pa.p_ll = p->pll_dev;
+    pa.pub = p->pub_dev;
+    pa.npub = p->pub_dev ? (int)pubs.size() : 0;
     *out = p;
     return B200_OK;
 }
@@ -948,7 +1082,7 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
 int b200_plan_launch(b200_ctx *ctx, b200_plan *p) {
     B200_REQUIRE(ctx, ctx && p, B200_ERR_INVALID);
     B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    plan_kernel_for(p->type, p->mode)<<<p->grid, kPlanThreads, p->geom.total, ctx->stream>>>(p->args, p->geom);
+    plan_kernel_for(p->type, p->mode)<<<p->grid, plan_threads(p->mode), p->geom.total, ctx->stream>>>(p->args, p->geom);
     ctx->launches++;
     B200_CUDA_TRY(ctx, cudaGetLastError());
     return B200_OK;

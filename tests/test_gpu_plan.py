@@ -67,6 +67,24 @@ def test_plan_with_ring_fed_src1(gpu_ctx, oracle, qmm, monkeypatch, case, ring):
     check_dag(gpu_ctx, oracle, qmm, case[0], case[1])
 
 
+@pytest.mark.parametrize("case", [(Q4_0, "block_pair"), (Q8_0, "block_pair"), (Q4_0, "ragged_chain"), (Q4_0, "many_ops"), (Q4_0, "k_split_8"),
+                                  (Q8_0, "k_split_8")], ids=lambda c: f"{c[1]}-{c[0]}")
+def test_plan_with_src1_quantized_once_per_gpu(gpu_ctx, oracle, qmm, monkeypatch, case):
+    """B200_PLAN_LLQ=k_min: an in-plan src1 of k >= k_min is quantized once per GPU (every CTA 1/grid of the blocks, published
+    as tagged words) instead of once per CTA.  quantize_row_q8_0 on the same fp32 values: the same bits as ever."""
+    monkeypatch.setenv("B200_PLAN_LLQ", "256")
+    monkeypatch.setenv("B200_PLAN_LLQ_DIST", "1")       # also right behind the producing op (the publisher then waits for it)
+    check_dag(gpu_ctx, oracle, qmm, case[0], case[1])
+
+
+@pytest.mark.parametrize("qtype", [Q4_0, Q8_0])
+def test_plan_with_every_src1_quantized_per_cta(gpu_ctx, oracle, qmm, monkeypatch, qtype):
+    """B200_PLAN_LLQ=0: the kernel without the publisher warp (what row-split plans run), on the DAG whose k = 16384 node takes
+    the quantized-once path by default."""
+    monkeypatch.setenv("B200_PLAN_LLQ", "0")
+    check_dag(gpu_ctx, oracle, qmm, qtype, "block_pair")
+
+
 def check_dag(gpu_ctx, oracle, qmm, qtype, dag):
     nodes = DAGS[dag]
     ws = build_dag(oracle, qmm, gpu_ctx, qtype, nodes, seed=len(nodes) * 7 + qtype)
