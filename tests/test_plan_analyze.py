@@ -120,3 +120,33 @@ def test_row_split_description_is_checked(qmm):
     mtot[0] = 256
     s.rank = 2
     assert analyze(qmm, args, s)[0] == qmm.ERR_INVALID
+
+
+def test_arena_bytes_cover_tagged_vectors_and_published_blocks(qmm, monkeypatch):
+    """b200_plan_arena_bytes is what a row-split caller allocates (and shares over CUDA IPC) before b200_plan_create: one
+    tagged vector per op (8 B per element, padded to 128 B), plus -- for every op whose k reaches B200_PLAN_LLQ -- room for the
+    src1 blocks the publisher warps quantize once per GPU (10 tagged words per block of 32).  Default: k >= 8192 on one GPU,
+    nothing for row-split plans."""
+    lib = qmm.load_library()
+    nodes = [(16384, 4096, -1), (4096, 4096, -1), (4096, 16384, 0), (1000, 4096, 2)]
+    args = args_for(qmm, nodes)
+    pad16 = lambda n: (n + 15) // 16 * 16
+    ll = sum(pad16(m) for m, _, _ in nodes) * 8
+    llq = lambda kmin: sum(pad16(k // 32 * 10) for _, k, _ in nodes if k >= kmin) * 8
+    monkeypatch.delenv("B200_PLAN_LLQ", raising=False)
+    assert lib.b200_plan_arena_bytes(args, len(nodes), None) == ll + llq(8192)
+    monkeypatch.setenv("B200_PLAN_LLQ", "0")
+    assert lib.b200_plan_arena_bytes(args, len(nodes), None) == ll
+    monkeypatch.setenv("B200_PLAN_LLQ", "4096")
+    assert lib.b200_plan_arena_bytes(args, len(nodes), None) == ll + llq(4096)
+    # row-split plans: off unless asked for
+    split = qmm.PlanSplit()
+    split.world, split.rank = 2, 0
+    row0 = (C.c_int64 * len(nodes))(*[0] * len(nodes))
+    mtot = (C.c_int64 * len(nodes))(*[2 * m for m, _, _ in nodes])
+    split.row0, split.m_total = row0, mtot
+    ll2 = sum(pad16(2 * m) for m, _, _ in nodes) * 8
+    monkeypatch.delenv("B200_PLAN_LLQ", raising=False)
+    assert lib.b200_plan_arena_bytes(args, len(nodes), C.byref(split)) == ll2
+    monkeypatch.setenv("B200_PLAN_LLQ", "8192")
+    assert lib.b200_plan_arena_bytes(args, len(nodes), C.byref(split)) == ll2 + llq(8192)
