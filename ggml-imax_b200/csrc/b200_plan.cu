@@ -39,7 +39,7 @@ constexpr int kRowSplit = B200_PLAN_ROW_SPLIT;
 constexpr int kCW = 8 * kRowSplit;           // consumer warps
 constexpr int kCT = kCW * 32;                // consumer threads
 constexpr int kPlanThreads = (kCW + 1) * 32;         // consumers + the producer warp
-constexpr int plan_threads(int mode) { return (mode & 4) ? kPlanThreads + 32 : kPlanThreads; }   // MODE 4: + the publisher warp
+constexpr int plan_threads(int mode) { return (mode & 12) ? kPlanThreads + 32 : kPlanThreads; }   // MODE 4 / 8: + the publisher warp
 constexpr int kSegBlocks = 128;              // blocks of k per warp-segment (4 per lane)
 constexpr int kMaxSlots = 24;
 constexpr int kPartFloats = 4096;            // k-split partials parked per CTA per op: rows_per_cta * G (aliases the LL staging)
@@ -70,7 +70,7 @@ struct ExportDesc {
     int ll, m_total, op, pad;
 };
 struct PubDesc {             // MODE 4: an in-plan src1 vector that is quantized once per GPU (for the op `op` that reads it)
-    int ll_src, k, src_op, llq, op, pad[3];
+    int ll_src, k, src_op, llq, op, pad[3];      // llq: arena element offset of the published vector
 };
 
 struct PlanGeom {
@@ -91,8 +91,9 @@ struct PlanArgs {
     uint32_t *state;               // {arrived CTAs, completed launches}
     unsigned long long *trace;     // optional: [nops][gridDim.x][4] globaltimer stamps
     const int *p_ll;               // LLRING kernels: per op, arena element offset of a src1 vector the producer feeds through the ring, or -1
-    const PubDesc *pub;            // MODE 4: the publisher warp's work list, in op order
+    const PubDesc *pub;            // MODE 4 / 8: the publisher warp's work list, in op order
     int npub;
+    uint32_t *pub_count;           // MODE 8: per work-list entry, CTAs that have published (never reset: grid per launch)
 };
 
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }
@@ -253,6 +254,9 @@ __device__ __forceinline__ bool ll_fetch_ring(uint32_t ring_a, uint32_t full_a, 
 // MODE bit 0: ring-fed src1 vectors (B200_PLAN_LL_RING); bit 1: per-slot L2 prefetch ahead of the ring (B200_PLAN_L2_SLOTS).
 // bit 2: a long src1 (B200_PLAN_LLQ) is quantized ONCE per GPU -- every CTA does 1/grid of its blocks and publishes them as tagged
 // words -- instead of once per CTA; each CTA then fetches 80 bytes per block instead of 256 and does no arithmetic.
+// bit 3 (B200_PLAN_PUBQ=1, NOT YET RUN ON A GPU): the same once-per-GPU quantization, published as the plain activation planes
+// + a per-vector arrival counter (release / acquire) instead of tagged words, so that a CTA takes the whole quantized vector
+// with ONE bulk copy straight into its activation buffer -- no registers, no tag checks, 40 bytes per block instead of 80.
 // MODE 0 is the shipped kernel; the others are experiments kept out of its code.
 template <int TYPE, int MODE>
 __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __grid_constant__ PlanArgs pa, const __grid_constant__ PlanGeom pg) {
@@ -260,12 +264,14 @@ __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __gri
     constexpr int QSB = TYPE == B200_TYPE_Q4_0 ? 16 : 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cta = blockIdx.x;
-    constexpr bool LLRING = (MODE & 1) != 0, L2SLOTS = (MODE & 2) != 0, LLQ = (MODE & 4) != 0;
+    constexpr bool LLRING = (MODE & 1) != 0, L2SLOTS = (MODE & 2) != 0, LLQ = (MODE & 4) != 0, PUBQ = (MODE & 8) != 0;
+    constexpr bool PUBW = LLQ || PUBQ;           // a publisher warp exists
 
     unsigned char *ring = smem + pg.ring_off;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + pg.bar_off);
     uint64_t *empty_bar = full_bar + kMaxSlots;
     uint32_t *s_epoch = reinterpret_cast<uint32_t *>(empty_bar + kMaxSlots);
+    uint64_t *act_bar = empty_bar + kMaxSlots + 2;       // MODE 8: completion of the bulk copy of a published vector
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < pg.nslots; s++) {
@@ -273,6 +279,7 @@ __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __gri
             mbar_init(&empty_bar[s], kCW);       // a slot's consumers (one team of G [x 2] warps) arrive with 8/G each
         }
         *s_epoch = pa.state[1] + 1u;    // every CTA reads it before any CTA can finish (the bump needs all of them)
+        if (PUBQ) mbar_init(act_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -387,8 +394,8 @@ __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __gri
             }
             if (pa.trace) pa.trace[(size_t)pa.nops * gridDim.x * 4 + (size_t)cta * 4 + 0] = prod_blocked;
         }
-    } else if (LLQ && warp == kCW + 1) {
-        // ===== publisher (MODE 4): for every long in-plan src1, in op order, this CTA's share of the blocks
+    } else if (PUBW && warp == kCW + 1) {
+        // ===== publisher (MODE 4 / 8): for every long in-plan src1, in op order, this CTA's share of the blocks
         // [cta * nb / grid, (cta + 1) * nb / grid): wait for the fp32 values (tagged vector of the producing op), quantize_row_q8_0,
         // publish.  Runs as far ahead of the consumers as the data allows; every rank does the same for its own arena. =====
         float *pstage = reinterpret_cast<float *>(smem + pg.pub_off);
@@ -399,7 +406,10 @@ __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __gri
             const int nb = d.k >> 5;
             const int b_lo = (cta * nb) / (int)gridDim.x, b_hi = ((cta + 1) * nb) / (int)gridDim.x;
             const int nt = 2 * (b_hi - b_lo);
-            if (nt <= 0) continue;
+            if (nt <= 0) {
+                if (PUBQ && lane == 0) atomicAdd(pa.pub_count + i, 1u);      // nothing to publish, but the count is per CTA
+                continue;
+            }
             const uint32_t src_tag = (epoch << 10) | (uint32_t)(d.src_op & 1023), tag = (epoch << 10) | (uint32_t)d.op;
             float4 vv[4];
             ll_fetch_warp(arena_local + (size_t)d.ll_src * 8 + (size_t)(2 * b_lo) * 128, nt, src_tag, pstage, lane, vv);
@@ -420,7 +430,22 @@ __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __gri
                 pk[j] = (uint32_t)(q0 & 0xff) | ((uint32_t)(q1 & 0xff) << 8) | ((uint32_t)(q2 & 0xff) << 16) | ((uint32_t)(q3 & 0xff) << 24);
             }
             sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-            if (lane < nt) {
+            if (PUBQ) {
+                // the consumers' activation-buffer layout, plain: int8 elements 0..15 / 16..31 of every block, fp32 d, 8 * sum(q)
+                if (lane < nt) {
+                    unsigned char *reg = reinterpret_cast<unsigned char *>(arena_w + (size_t)d.llq);
+                    *reinterpret_cast<uint4 *>(reg + (size_t)h * (d.k >> 1) + (size_t)b * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    if (h == 0) {
+                        reinterpret_cast<float *>(reg + d.k)[b] = __half2float(__float2half_rn(__fdiv_rn(amax, 127.f)));
+                        reinterpret_cast<int *>(reg + d.k + (size_t)nb * 4)[b] = 8 * sq;
+                    }
+                }
+                // release: this warp's stores before its arrival, for readers in the generic AND the async proxy
+                __threadfence();
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) atomicAdd(pa.pub_count + i, 1u);
+            } else if (lane < nt) {
                 uint2 *blk = arena_w + (size_t)d.llq + (size_t)b * 10;
 #pragma unroll
                 for (int j = 0; j < 4; j++) ll_store(blk, h * 4 + j, __uint_as_float(pk[j]), tag);
@@ -430,7 +455,7 @@ __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __gri
                 }
             }
         }
-    } else if (!LLQ || warp < kCW) {
+    } else if (!PUBW || warp < kCW) {
         // ===== consumers =====
         const uint32_t ring_a = smem_u32(ring);
         const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
@@ -443,6 +468,7 @@ __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __gri
         int prevG = 1;
         unsigned long long cons_blocked = 0, quant_time = 0;
         unsigned ring_miss = 0;     // LLRING: runs of a ring-fed vector this warp had to re-fetch from L2
+        uint32_t act_par = 0;       // MODE 8: phase of act_bar
         RowCtx<TYPE> c;
         c.a_lo = c.a_hi = c.a_d = c.a_s = smem_u32(smem + pg.act_off);
 #pragma unroll
@@ -502,7 +528,26 @@ __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __gri
                 constexpr int kQB = 4 / kRowSplit;
                 const int tpc = nb * 2;      // lane-tasks: (block, half) = 16 consecutive floats
                 const bool llq_src = LLQ && (flags & OPF_SRC_LLQ) != 0;
-                if (llq_src) {
+                if (PUBQ && (flags & OPF_SRC_LLQ) != 0) {
+                    // ---- the publisher warps of all CTAs have left (or will leave) the quantized vector in the arena in exactly
+                    // the layout of the activation buffer: wait for the arrival count, then ONE bulk copy brings it in.
+                    if (threadIdx.x == 0) {
+                        const uint32_t target = epoch * gridDim.x;        // the counters are never reset: grid arrivals per launch
+                        const uint32_t *cnt = pa.pub_count + o->ll_src;   // (ll_src carries the work-list index for these ops)
+                        uint32_t seen;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+                        } while ((int32_t)(seen - target) < 0);
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
+                        const uint32_t ab = smem_u32(act_bar), abytes = (uint32_t)(k + nb * 8);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ab), "r"(abytes) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(act_a),
+                                     "l"(arena_local + (size_t)(uintptr_t)o->src_plain * 8), "r"(abytes), "r"(ab) : "memory");
+                    }
+                    if (tr && threadIdx.x == 0) tr[0] = gtime();
+                    mbar_wait_a(smem_u32(act_bar), act_par);
+                    act_par ^= 1u;
+                } else if (llq_src) {
                     // ---- the vector was quantized once per GPU by the publisher warps (below): 10 tagged words per block
                     // {q[0..31] as 8 words, fp32 d, 8 * sum(q)} in the local arena.
                     uint2 *llq = reinterpret_cast<uint2 *>(const_cast<char *>(arena_local)) + (size_t)(uintptr_t)o->src_plain;
@@ -742,8 +787,10 @@ __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __gri
 typedef void (*plan_kernel_fn)(const PlanArgs, const PlanGeom);
 static plan_kernel_fn plan_kernel_for(int type, int mode) {
     if (type == B200_TYPE_Q4_0)
-        return mode == 1 ? plan_kernel<B200_TYPE_Q4_0, 1> : mode == 2 ? plan_kernel<B200_TYPE_Q4_0, 2> : mode == 4 ? plan_kernel<B200_TYPE_Q4_0, 4> : plan_kernel<B200_TYPE_Q4_0, 0>;
-    return mode == 1 ? plan_kernel<B200_TYPE_Q8_0, 1> : mode == 2 ? plan_kernel<B200_TYPE_Q8_0, 2> : mode == 4 ? plan_kernel<B200_TYPE_Q8_0, 4> : plan_kernel<B200_TYPE_Q8_0, 0>;
+        return mode == 1 ? plan_kernel<B200_TYPE_Q4_0, 1> : mode == 2 ? plan_kernel<B200_TYPE_Q4_0, 2> : mode == 4 ? plan_kernel<B200_TYPE_Q4_0, 4> :
+               mode == 8 ? plan_kernel<B200_TYPE_Q4_0, 8> : plan_kernel<B200_TYPE_Q4_0, 0>;
+    return mode == 1 ? plan_kernel<B200_TYPE_Q8_0, 1> : mode == 2 ? plan_kernel<B200_TYPE_Q8_0, 2> : mode == 4 ? plan_kernel<B200_TYPE_Q8_0, 4> :
+           mode == 8 ? plan_kernel<B200_TYPE_Q8_0, 8> : plan_kernel<B200_TYPE_Q8_0, 0>;
 }
 
 struct b200_plan {
@@ -754,7 +801,8 @@ struct b200_plan {
     ExportDesc *exports_dev;
     int *pll_dev;               // ring-fed src1 vectors (null: none)
     PubDesc *pub_dev;           // MODE 4 publisher work list
-    int mode;                   // kernel variant: 0 = shipped; bit 0 ring-fed src1, bit 1 per-slot L2 prefetch
+    int mode;                   // kernel variant: 0 = plain; bit 0 ring-fed src1, bit 1 per-slot L2 prefetch, bit 2 / 3 publisher warp
+    uint32_t *pubcnt_dev;       // MODE 8 arrival counters
     void *arena_own;            // allocated here when world == 1
     uint32_t *state_dev;
     unsigned long long *trace_dev;
@@ -875,6 +923,7 @@ void b200_plan_destroy(b200_plan *p) {
     if (p->exports_dev) cudaFree(p->exports_dev);
     if (p->pll_dev) cudaFree(p->pll_dev);
     if (p->pub_dev) cudaFree(p->pub_dev);
+    if (p->pubcnt_dev) cudaFree(p->pubcnt_dev);
     if (p->arena_own) cudaFree(p->arena_own);
     if (p->state_dev) cudaFree(p->state_dev);
     if (p->trace_dev) cudaFree(p->trace_dev);
@@ -906,6 +955,8 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     std::vector<long long> ll_off, llq_off;
     const size_t arena_elems = plan_arena_elems(args, count, split, &ll_off, &llq_off);
     std::vector<PubDesc> pubs;
+    // experimental protocol (MODE 8); not combinable with the ring-fed experiment, which needs ll_src as it is
+    const bool pubq = getenv("B200_PLAN_PUBQ") && atoi(getenv("B200_PLAN_PUBQ")) != 0 && !getenv("B200_PLAN_LL_RING");
     int llq_dist = 2;
     if (const char *e = getenv("B200_PLAN_LLQ_DIST")) { const int v = atoi(e); if (v >= 1) llq_dist = v; }
     B200_REQUIRE(ctx, arena_elems < (1ull << 30), B200_ERR_UNSUPPORTED);
@@ -969,6 +1020,7 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
             PubDesc pb;
             memset(&pb, 0, sizeof(pb));
             pb.ll_src = c.ll_src; pb.k = c.k; pb.src_op = c.src_op; pb.llq = (int)llq_off[i]; pb.op = i;
+            if (pubq) c.ll_src = (int)pubs.size();      // MODE 8 consumers need the work-list index, not the fp32 vector
             pubs.push_back(pb);
         }
     }
@@ -1050,7 +1102,9 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     if (e == cudaSuccess) e = cudaMemset(p->state_dev, 0, 16);
     if (e == cudaSuccess && world == 1) e = cudaMemset(p->arena_own, 0, p->arena_bytes);
     const bool any_llq = !any_ring && !pubs.empty();
-    p->mode = any_ring ? 1 : any_llq ? 4 : (g.l2_slots > 0 ? 2 : 0);
+    p->mode = any_ring ? 1 : any_llq ? (pubq ? 8 : 4) : (g.l2_slots > 0 ? 2 : 0);
+    if (e == cudaSuccess && p->mode == 8) e = cudaMalloc((void **)&p->pubcnt_dev, sizeof(uint32_t) * pubs.size());
+    if (e == cudaSuccess && p->mode == 8) e = cudaMemset(p->pubcnt_dev, 0, sizeof(uint32_t) * pubs.size());
     if (e == cudaSuccess && any_llq) e = cudaMalloc((void **)&p->pub_dev, sizeof(PubDesc) * pubs.size());
     if (e == cudaSuccess && any_llq) e = cudaMemcpy(p->pub_dev, pubs.data(), sizeof(PubDesc) * pubs.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(plan_kernel_for(type, p->mode), cudaFuncAttributeMaxDynamicSharedMemorySize, g.total);
@@ -1075,6 +1129,7 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     pa.p_ll = p->pll_dev;
     pa.pub = p->pub_dev;
     pa.npub = p->pub_dev ? (int)pubs.size() : 0;
+    pa.pub_count = p->pubcnt_dev;
     *out = p;
     return B200_OK;
 }

@@ -1,6 +1,8 @@
 """Decode plans (b200_plan_*): a dependent sequence of decode mul_mats as one persistent launch, against the oracle
 (ggml_compute_forward_mul_mat, src/ggml.c:11808, applied node by node) and against the node-by-node CUDA path
 (bit-identical by construction)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -74,6 +76,19 @@ def test_plan_with_src1_quantized_once_per_gpu(gpu_ctx, oracle, qmm, monkeypatch
     as tagged words) instead of once per CTA.  quantize_row_q8_0 on the same fp32 values: the same bits as ever."""
     monkeypatch.setenv("B200_PLAN_LLQ", "256")
     monkeypatch.setenv("B200_PLAN_LLQ_DIST", "1")       # also right behind the producing op (the publisher then waits for it)
+    check_dag(gpu_ctx, oracle, qmm, case[0], case[1])
+
+
+@pytest.mark.skipif(os.environ.get("B200_TEST_EXPERIMENTAL") != "1", reason="unvalidated kernel mode: set B200_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("dist", ["1", "2"])
+@pytest.mark.parametrize("case", [(Q4_0, "block_pair"), (Q8_0, "block_pair"), (Q4_0, "ragged_chain"), (Q4_0, "many_ops"), (Q4_0, "k_split_8"),
+                                  (Q8_0, "k_split_8")], ids=lambda c: f"{c[1]}-{c[0]}")
+def test_plan_with_published_planes_experimental(gpu_ctx, oracle, qmm, monkeypatch, case, dist):
+    """B200_PLAN_PUBQ=1 (kernel MODE 8, written without GPU time left in round 1 and never run): the once-per-GPU quantization
+    published as plain activation planes + an arrival counter, taken by every CTA with one bulk copy.  Same bits as ever."""
+    monkeypatch.setenv("B200_PLAN_PUBQ", "1")
+    monkeypatch.setenv("B200_PLAN_LLQ", "256")
+    monkeypatch.setenv("B200_PLAN_LLQ_DIST", dist)
     check_dag(gpu_ctx, oracle, qmm, case[0], case[1])
 
 
