@@ -362,8 +362,10 @@ __global__ void __launch_bounds__(256) transpose_scales_kernel(const __half *__r
 
 
 // =====================================================================================================================
-// EXPERIMENTAL, selected by B200_GEMM_F16=1, and NOT YET RUN ON A GPU (written at the end of round 1 without GPU time left;
-// tests/test_gpu_gemm_f16_experimental.py is skipped unless B200_TEST_EXPERIMENTAL=1).  DESIGN.md section 9, item 2.
+// EXPERIMENTAL, selected by B200_GEMM_F16=1.  Written at the end of round 1; the last GPU seconds of the round went into ONE run
+// of four small cases of tests/test_gpu_gemm_f16_experimental.py (m,k,n = 300,256,64 and 128,64,256, both types: NMSE <= 1e-6
+// against the exact kernel and the oracle) -- the large and ragged-k cases and every timing are still open, so the tests stay
+// skipped unless B200_TEST_EXPERIMENTAL=1 and the path stays off by default.  DESIGN.md section 9, item 2.
 //
 // The exact kernel above spends its time on CUDA cores: m * n * k / 32 accumulator updates (int32 -> fp32, x d_w * d_x).
 // This variant moves the scaling into the tensor core the way the reference's own CUDA backend does for large batches

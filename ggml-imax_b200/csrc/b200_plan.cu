@@ -254,7 +254,7 @@ __device__ __forceinline__ bool ll_fetch_ring(uint32_t ring_a, uint32_t full_a, 
 // MODE bit 0: ring-fed src1 vectors (B200_PLAN_LL_RING); bit 1: per-slot L2 prefetch ahead of the ring (B200_PLAN_L2_SLOTS).
 // bit 2: a long src1 (B200_PLAN_LLQ) is quantized ONCE per GPU -- every CTA does 1/grid of its blocks and publishes them as tagged
 // words -- instead of once per CTA; each CTA then fetches 80 bytes per block instead of 256 and does no arithmetic.
-// bit 3 (B200_PLAN_PUBQ=1, NOT YET RUN ON A GPU): the same once-per-GPU quantization, published as the plain activation planes
+// bit 3 (B200_PLAN_PUBQ=1; first GPU run at the very end of round 1: 4 DAG cases pass bit for bit, speed not measured yet): the same once-per-GPU quantization, published as the plain activation planes
 // + a per-vector arrival counter (release / acquire) instead of tagged words, so that a CTA takes the whole quantized vector
 // with ONE bulk copy straight into its activation buffer -- no registers, no tag checks, 40 bytes per block instead of 80.
 // MODE 0 is the shipped kernel; the others are experiments kept out of its code.

@@ -1,8 +1,8 @@
 """EXPERIMENTAL prefill path (B200_GEMM_F16=1, gemm_f16_kernel in b200_gemm_tc.cu): operands dequantized to fp16, fp32
 accumulation over the whole k on the tensor cores -- what the reference's CUDA backend does for large batches
-(ggml_cuda_op_mul_mat_cublas, src/ggml-cuda.cu:1208-1270).  The kernel was written without GPU time left in round 1 and has
-never run; these tests are therefore skipped unless B200_TEST_EXPERIMENTAL=1, so that the default `-m gpu` run only covers
-paths that have been validated.  First thing to run in round 2:
+(ggml_cuda_op_mul_mat_cublas, src/ggml-cuda.cu:1208-1270).  The kernel was written at the end of round 1; only four small cases
+(300,256,64 and 128,64,256, both types) have run on a GPU so far (they pass, profiles/r01_experimental_kernels_first_run.log), so these
+tests stay skipped unless B200_TEST_EXPERIMENTAL=1 and the default `-m gpu` run only covers fully validated paths.  First thing to run in round 2:
     B200_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_gemm_f16_experimental.py -x -q
 Bounds: NMSE <= 5e-4 against the oracle is the reference's bar (tests/test-backend-ops.cpp:921-923); fp16 rounding of both
 operands (relative 2^-12 each) should leave it below 1e-6, and as close to the exact int8 kernel."""

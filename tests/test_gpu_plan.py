@@ -84,7 +84,8 @@ def test_plan_with_src1_quantized_once_per_gpu(gpu_ctx, oracle, qmm, monkeypatch
 @pytest.mark.parametrize("case", [(Q4_0, "block_pair"), (Q8_0, "block_pair"), (Q4_0, "ragged_chain"), (Q4_0, "many_ops"), (Q4_0, "k_split_8"),
                                   (Q8_0, "k_split_8")], ids=lambda c: f"{c[1]}-{c[0]}")
 def test_plan_with_published_planes_experimental(gpu_ctx, oracle, qmm, monkeypatch, case, dist):
-    """B200_PLAN_PUBQ=1 (kernel MODE 8, written without GPU time left in round 1 and never run): the once-per-GPU quantization
+    """B200_PLAN_PUBQ=1 (kernel MODE 8, written at the end of round 1: only the block_pair cases have run on a GPU so far -- they pass --
+    and no timing exists, hence the gate): the once-per-GPU quantization
     published as plain activation planes + an arrival counter, taken by every CTA with one bulk copy.  Same bits as ever."""
     monkeypatch.setenv("B200_PLAN_PUBQ", "1")
     monkeypatch.setenv("B200_PLAN_LLQ", "256")
