@@ -530,6 +530,202 @@ __global__ void __launch_bounds__(256) dequant_f16_kernel(const uint8_t *__restr
     }
 }
 
+// ---- v2 of the fp16 path (B200_GEMM_F16=2; written after the last GPU second of round 1 was spent: NEVER RUN) --------------
+// Same MMA loop, but W' is never materialised in global memory: the raw repacked blocks of the tile (128 rows x 2 blocks of the
+// qs plane per 64-wide k-step) come in by TMA, four warps (thread = weight row) turn them into fp16 -- the integer goes into
+// the mantissa of 1024.0 (bits 0x6400 | q), minus the bias, times d_w: one rounding, the same bits as dequant_f16_kernel --
+// and store them where TMA with SWIZZLE_128B would have put them: 16-byte chunk c of row r at r * 128 + ((c ^ (r & 7)) << 4)
+// of the 1024-byte-aligned tile.  Saves the m * k * 2 bytes written and read back per GEMM (90 MB for C2).
+template <int TYPE> struct FusedGeom {
+    static constexpr int kQsb = TYPE == B200_TYPE_Q4_0 ? 16 : 32;
+    static constexpr int kRawRow = 2 * kQsb;                           // bytes of the qs plane per row and k-step (2 blocks)
+    static constexpr int kRawBytes = FBM * kRawRow;                    // 4 KB / 8 KB
+    static constexpr int kStage = FBM * BK + FBN * BK + kRawBytes;     // A tile, B tile, raw blocks: 52 KB / 56 KB
+    static constexpr int kSmem = kFStages * kStage + 1024 + 256;
+};
+
+__device__ __forceinline__ uint4 lds128_(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128_(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// two small unsigned integers (< 1024) already placed at bits 0.. and 16.. -> half2((u0 - bias) * d, (u1 - bias) * d)
+__device__ __forceinline__ uint32_t cvt_pair(uint32_t bits, __half2 bias, __half2 d2) {
+    const uint32_t hb = bits | 0x64006400u;                            // 1024 + u, exact
+    __half2 h = *reinterpret_cast<const __half2 *>(&hb);
+    h = __hmul2(__hsub2(h, bias), d2);                                 // (u - bias) exact, product rounded once
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(kFThreads, 1)
+gemm_f16_fused_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_b, const __half *__restrict__ dw_plane,
+                      const GemmF16Args g) {
+    using G = FusedGeom<TYPE>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kFStages * G::kStage);
+    uint64_t *full_bar = bars;                       // [kFStages] TMA (raw blocks + X') -> dequant warps, MMA
+    uint64_t *empty_bar = bars + kFStages;           // [kFStages] MMA -> TMA
+    uint64_t *aready_bar = bars + 2 * kFStages;      // [kFStages] dequant warps -> MMA
+    uint64_t *tfull_bar = bars + 3 * kFStages;       // accumulator complete -> epilogue
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tfull_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * FBM, n0 = blockIdx.y * FBN;
+    const int nb = g.k >> 5;
+    const int kiters = (nb + 1) >> 1;                // 2 blocks per k-step; a ragged last step has one
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_raw) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kFStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&aready_bar[s], 4); }
+        mbar_init(tfull_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(FBN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < kiters; it++) {
+                const int s = it % kFStages;
+                const uint32_t ph = (uint32_t)(it / kFStages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                unsigned char *st = smem + s * G::kStage;
+                mbar_expect_tx(&full_bar[s], FBN * BK + G::kRawBytes);
+                tma_load_2d(st + FBM * BK + FBN * BK, &map_raw, it * G::kRawRow, m0, &full_bar[s]);   // 128 rows x 2 blocks of the qs plane
+                tma_load_2d(st + FBM * BK, &map_b, it * BK, n0, &full_bar[s]);                        // 256 rows x 128 bytes of X'
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int it = 0; it < kiters; it++) {
+                const int s = it % kFStages;
+                const uint32_t ph = (uint32_t)(it / kFStages) & 1u;
+                mbar_wait(&full_bar[s], ph);         // X' has landed
+                mbar_wait(&aready_bar[s], ph);       // W' tile written and fenced by the four dequant warps
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * G::kStage);
+                const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sa + FBM * BK);
+#pragma unroll
+                for (int j = 0; j < BK / 32; j++)
+                    tc_mma_f16(tmem_base, da + (uint64_t)(j * 2), db + (uint64_t)(j * 2), kIdescF16, (it | j) != 0 ? 1u : 0u);
+                tc_commit(&empty_bar[s]);
+            }
+            tc_commit(tfull_bar);
+        }
+    }
+    if (warp >= 4 && warp < 8) {
+        // ===== dequant warps: thread = weight row of the tile =====
+        const int r = (warp - 4) * 32 + lane;
+        const int row_c = min(m0 + r, g.m - 1);
+        const unsigned short *dwp = reinterpret_cast<const unsigned short *>(dw_plane) + (int64_t)row_c * nb;
+        const __half2 bias = TYPE == B200_TYPE_Q4_0 ? __floats2half2_rn(1032.f, 1032.f) : __floats2half2_rn(1152.f, 1152.f);
+        unsigned short d0 = dwp[0], d1 = nb > 1 ? dwp[1] : (unsigned short)0;
+        for (int it = 0; it < kiters; it++) {
+            const int s = it % kFStages;
+            const uint32_t ph = (uint32_t)(it / kFStages) & 1u;
+            const unsigned short c0 = d0, c1 = d1;
+            if (it + 1 < kiters) {                   // next step's scales: in flight while this step is converted
+                d0 = dwp[2 * it + 2];
+                d1 = 2 * it + 3 < nb ? dwp[2 * it + 3] : (unsigned short)0;      // past the end: zero scale -> zero weights
+            }
+            mbar_wait(&full_bar[s], ph);
+            const uint32_t st = smem_u32(smem + s * G::kStage);
+            const uint32_t raw = st + FBM * BK + FBN * BK + (uint32_t)(r * G::kRawRow);
+            const uint32_t arow = st + (uint32_t)(r * 128);
+            const uint32_t sw = (uint32_t)(r & 7);
+#pragma unroll
+            for (int blk = 0; blk < 2; blk++) {
+                const __half dh = __ushort_as_half(blk == 0 ? c0 : c1);
+                const __half2 d2 = __halves2half2(dh, dh);
+                if (TYPE == B200_TYPE_Q4_0) {
+                    const uint4 q = lds128_(raw + (uint32_t)(blk * 16));
+                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int hi = 0; hi < 2; hi++)            // elements 0..15 = low nibbles of bytes 0..15, 16..31 = high nibbles
+#pragma unroll
+                        for (int half8 = 0; half8 < 2; half8++) {       // bytes 0..7 / 8..15 -> one 16-byte chunk of 8 fp16
+                            uint32_t o[4];
+#pragma unroll
+                            for (int t = 0; t < 2; t++) {
+                                const uint32_t x = w[half8 * 2 + t] >> (hi * 4);
+                                o[t * 2 + 0] = cvt_pair((x & 0x0000000Fu) | ((x & 0x00000F00u) << 8), bias, d2);
+                                o[t * 2 + 1] = cvt_pair(((x >> 16) & 0x0000000Fu) | ((x >> 8) & 0x000F0000u), bias, d2);
+                            }
+                            const uint32_t c = (uint32_t)(blk * 4 + hi * 2 + half8);
+                            sts128_(arow + ((c ^ sw) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+                        }
+                } else {
+#pragma unroll
+                    for (int h16 = 0; h16 < 2; h16++) {
+                        const uint4 q = lds128_(raw + (uint32_t)(blk * 32 + h16 * 16));
+                        const uint32_t w[4] = {q.x ^ 0x80808080u, q.y ^ 0x80808080u, q.z ^ 0x80808080u, q.w ^ 0x80808080u};   // int8 + 128
+#pragma unroll
+                        for (int half8 = 0; half8 < 2; half8++) {
+                            uint32_t o[4];
+#pragma unroll
+                            for (int t = 0; t < 2; t++) {
+                                const uint32_t x = w[half8 * 2 + t];
+                                o[t * 2 + 0] = cvt_pair((x & 0x000000FFu) | ((x & 0x0000FF00u) << 8), bias, d2);
+                                o[t * 2 + 1] = cvt_pair(((x >> 16) & 0x000000FFu) | ((x >> 8) & 0x00FF0000u), bias, d2);
+                            }
+                            const uint32_t c = (uint32_t)(blk * 4 + h16 * 2 + half8);
+                            sts128_(arow + ((c ^ sw) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+                        }
+                    }
+                }
+            }
+            // generic-proxy stores -> visible to the tensor core (async proxy), then one arrival per warp
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&aready_bar[s]);
+        }
+    }
+    if (warp >= 4) {
+        // ===== epilogue (all eight warps; the first four have finished converting by now) =====
+        const int ew = warp - 4;
+        const int quad = warp & 3;
+        const int chalf = ew >> 2;
+        const int row = m0 + quad * 32 + lane;
+        mbar_wait(tfull_bar, 0);
+        tc_fence_after();
+        const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(chalf * 128);
+#pragma unroll 1
+        for (int c32 = 0; c32 < 4; c32++) {
+            uint32_t v[32];
+            tc_ld32(tcol + (uint32_t)(c32 * 32), v);
+            tc_wait_ld();
+            if (row < g.m) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int c = n0 + chalf * 128 + c32 * 32 + j;
+                    if (c < g.n) g.dst[(int64_t)c * g.m + row] = __uint_as_float(v[j]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(FBN) : "memory");
+    }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -579,9 +775,49 @@ bool make_map_bytes(CUtensorMap *map, const void *base, int64_t rows, int64_t ro
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-bool gemm_f16_enabled() {       // read per call: tests switch it inside one process
+int gemm_f16_mode() {           // 0 off, 1 operands materialised, 2 weights dequantized in the kernel; read per call: tests switch it
     const char *e = getenv("B200_GEMM_F16");
-    return e && atoi(e) != 0;
+    return e ? atoi(e) : 0;
+}
+bool gemm_f16_enabled() { return gemm_f16_mode() != 0; }
+
+// the qs plane as bytes: rows x (nb * qsb), box = 128 rows x 2 blocks, no swizzle; out-of-bounds -> zeros
+bool make_raw_map(CUtensorMap *map, const void *base, int64_t rows, int64_t row_bytes, int box_bytes) {
+    auto fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box_bytes, (cuuint32_t)FBM};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int TYPE>
+int launch_gemm_f16_fused(b200_ctx *ctx, const b200_gemm_params &p) {
+    using G = FusedGeom<TYPE>;
+    const int64_t nb = p.k / 32;
+    __half *x16 = (__half *)p.scratch;
+    const int64_t xblocks = p.n * nb;
+    dequant_f16_kernel<B200_TYPE_Q8_0><<<(unsigned)((xblocks + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t *)p.aq, p.ad, (uint4 *)x16, xblocks);
+    ctx->launches++;
+    B200_CUDA_TRY(ctx, cudaGetLastError());
+    CUtensorMap map_raw, map_b;
+    if (!make_raw_map(&map_raw, p.qs, p.m, nb * G::kQsb, G::kRawRow) || !make_map_bytes(&map_b, x16, p.n, p.k * 2, FBN)) {
+        b200_set_error(ctx, "cuTensorMapEncodeTiled failed (fused fp16 path, m=%lld n=%lld k=%lld)", (long long)p.m, (long long)p.n, (long long)p.k);
+        return B200_ERR_CUDA;
+    }
+    GemmF16Args g;
+    g.dst = p.dst;
+    g.m = (int)p.m;
+    g.n = (int)p.n;
+    g.k = (int)p.k;
+    dim3 grid((unsigned)((p.m + FBM - 1) / FBM), (unsigned)((p.n + FBN - 1) / FBN), 1);
+    B200_CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_f16_fused_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmem));
+    gemm_f16_fused_kernel<TYPE><<<grid, kFThreads, G::kSmem, ctx->stream>>>(map_raw, map_b, p.d, g);
+    ctx->launches++;
+    B200_CUDA_TRY(ctx, cudaGetLastError());
+    return B200_OK;
 }
 size_t gemm_f16_scratch_bytes(int64_t k, int64_t m, int64_t n) { return b200_align_up((size_t)m * k * 2, 1024) + b200_align_up((size_t)n * k * 2, 1024); }
 
@@ -632,6 +868,8 @@ int b200_launch_gemm(b200_ctx *ctx, const b200_gemm_params &p) {
     B200_REQUIRE(ctx, p.k % 32 == 0 && p.k >= 32 && p.m >= 1 && p.n >= 1, B200_ERR_INVALID);
     B200_REQUIRE(ctx, p.scratch != NULL, B200_ERR_INVALID);
     B200_REQUIRE(ctx, p.m < (1 << 30) && p.n < (1 << 30) && p.k < (1 << 30), B200_ERR_UNSUPPORTED);
+    if (!p.dots && gemm_f16_mode() == 2 && p.k >= 64)                        // experimental (see gemm_f16_fused_kernel)
+        return p.type == B200_TYPE_Q4_0 ? launch_gemm_f16_fused<B200_TYPE_Q4_0>(ctx, p) : launch_gemm_f16_fused<B200_TYPE_Q8_0>(ctx, p);
     if (!p.dots && gemm_f16_enabled()) return launch_gemm_f16(ctx, p);       // experimental (see gemm_f16_kernel)
     const int64_t nb = p.k / 32, ldn = (p.n + BN - 1) / BN * BN;
     float *dxT = (float *)p.scratch;

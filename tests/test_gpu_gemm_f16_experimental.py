@@ -17,10 +17,11 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("B200_TEST_EXPERIMENTAL") != "1", reason="unvalidated kernel: set B200_TEST_EXPERIMENTAL=1")]
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])      # 1: both operands materialised as fp16 (four small cases have run); 2: weights dequantized in the kernel (never run)
 @pytest.mark.parametrize("qtype", [Q4_0, Q8_0])
 @pytest.mark.parametrize("m,k,n", [(128, 64, 256), (128, 256, 256), (300, 256, 64), (1000, 4096, 512), (257, 96, 9), (64, 32, 300),
                                    (11008, 4096, 512)])
-def test_f16_gemm_vs_oracle_and_exact_kernel(gpu_ctx, qmm, oracle, monkeypatch, qtype, m, k, n):
+def test_f16_gemm_vs_oracle_and_exact_kernel(gpu_ctx, qmm, oracle, monkeypatch, qtype, m, k, n, mode):
     rng = np.random.default_rng(m * 31 + k + n)
     big = m * k > (1 << 24)
     wire = qmm.random_wire_weights(qtype, k, m, seed=m + k) if big else oracle.quantize_weights(qtype, rng.uniform(-1, 1, (m, k)).astype(np.float32))
@@ -30,7 +31,7 @@ def test_f16_gemm_vs_oracle_and_exact_kernel(gpu_ctx, qmm, oracle, monkeypatch, 
         t.set(wire)
         monkeypatch.delenv("B200_GEMM_F16", raising=False)
         exact = gpu_ctx.mul_mat(t, x, flags=qmm.MM_FORCE_GEMM)
-        monkeypatch.setenv("B200_GEMM_F16", "1")
+        monkeypatch.setenv("B200_GEMM_F16", mode)
         got = gpu_ctx.mul_mat(t, x, flags=qmm.MM_FORCE_GEMM)
         assert got.shape == exact.shape and np.isfinite(got).all()
         assert nmse(got, exact) <= 1e-6, f"fp16 path vs exact int8 path: nmse {nmse(got, exact)}"
