@@ -58,7 +58,10 @@ struct __align__(16) PDesc {                 // what the producer needs of an op
 static_assert(sizeof(PDesc) == 32, "PDesc layout");
 struct __align__(16) CDesc {                 // what the consumers need (staged in shared memory, kDescCap at a time)
     float *dst_plain;        // local plain fp32 vector [m_total] or null
-    const float *src_plain;  // src1 when it comes from outside the plan (src_op < 0); OPF_SRC_LLQ: the arena offset of the quantized vector
+    union {
+        const float *src_plain;  // src1 when it comes from outside the plan (src_op < 0)
+        long long src_pub;       // OPF_SRC_LLQ: arena element offset of the vector the publisher warps quantize once per GPU
+    };
     int ll_dst, ll_src;      // element offsets in the arena of this op's / its producer's LL vector
     int k, flags;
     int rows_q, rows_rem;
@@ -542,7 +545,7 @@ __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __gri
                         const uint32_t ab = smem_u32(act_bar), abytes = (uint32_t)(k + nb * 8);
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ab), "r"(abytes) : "memory");
                         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(act_a),
-                                     "l"(arena_local + (size_t)(uintptr_t)o->src_plain * 8), "r"(abytes), "r"(ab) : "memory");
+                                     "l"(arena_local + (size_t)o->src_pub * 8), "r"(abytes), "r"(ab) : "memory");
                     }
                     if (tr && threadIdx.x == 0) tr[0] = gtime();
                     mbar_wait_a(smem_u32(act_bar), act_par);
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __gri
                 } else if (llq_src) {
                     // ---- the vector was quantized once per GPU by the publisher warps (below): 10 tagged words per block
                     // {q[0..31] as 8 words, fp32 d, 8 * sum(q)} in the local arena.
-                    uint2 *llq = reinterpret_cast<uint2 *>(const_cast<char *>(arena_local)) + (size_t)(uintptr_t)o->src_plain;
+                    uint2 *llq = reinterpret_cast<uint2 *>(const_cast<char *>(arena_local)) + (size_t)o->src_pub;
                     if (tr && threadIdx.x == 0) tr[0] = gtime();
                     // every warp: two blocks per thread and round trip, straight into the activation planes
 #pragma unroll 1
@@ -1016,7 +1019,7 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
         // publication would be a second exchange on the critical path)
         if (c.src_op >= 0 && !(c.flags & OPF_SAME_INPUT) && llq_off[i] >= 0 && (nb + grid - 1) / grid + 1 <= 16 && i - c.src_op >= llq_dist) {
             c.flags |= OPF_SRC_LLQ;
-            c.src_plain = (const float *)(uintptr_t)llq_off[i];
+            c.src_pub = llq_off[i];
             PubDesc pb;
             memset(&pb, 0, sizeof(pb));
             pb.ll_src = c.ll_src; pb.k = c.k; pb.src_op = c.src_op; pb.llq = (int)llq_off[i]; pb.op = i;
