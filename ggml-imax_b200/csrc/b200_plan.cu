@@ -260,6 +260,9 @@ __device__ __forceinline__ bool ll_fetch_ring(uint32_t ring_a, uint32_t full_a, 
 // bit 3 (B200_PLAN_PUBQ=1; first GPU run at the very end of round 1: 4 DAG cases pass bit for bit, speed not measured yet): the same once-per-GPU quantization, published as the plain activation planes
 // + a per-vector arrival counter (release / acquire) instead of tagged words, so that a CTA takes the whole quantized vector
 // with ONE bulk copy straight into its activation buffer -- no registers, no tag checks, 40 bytes per block instead of 80.
+// bit 4 (B200_PLAN_NOSPLIT=1, NEVER RUN): ops with k > 4096 are not split over a team of warps; the slot's warp walks the 4096-wide
+// segments itself (a butterfly per segment, the partials added in segment order: the same bits), so there is no partials pass,
+// no barrier around it, no barrier when the team size changes, and the rows leave slot by slot instead of at the end of the op.
 // MODE 0 is the shipped kernel; the others are experiments kept out of its code.
 template <int TYPE, int MODE>
 __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __grid_constant__ PlanArgs pa, const __grid_constant__ PlanGeom pg) {
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __gri
     const int cta = blockIdx.x;
     constexpr bool LLRING = (MODE & 1) != 0, L2SLOTS = (MODE & 2) != 0, LLQ = (MODE & 4) != 0, PUBQ = (MODE & 8) != 0;
     constexpr bool PUBW = LLQ || PUBQ;           // a publisher warp exists
+    constexpr bool NOSPLIT = (MODE & 16) != 0;
 
     unsigned char *ring = smem + pg.ring_off;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + pg.bar_off);
@@ -493,7 +497,9 @@ __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __gri
             // geometry comes precomputed in the descriptor (flags: bits 8..15 rows per slot, 16..19 log2 of the k-split)
             const int k = o->k, flags = o->flags;
             const int nb = k >> 5;
-            const int rs = (flags >> 8) & 0xff, log2g = (flags >> 16) & 0xf;
+            const int rs = (flags >> 8) & 0xff, log2g_op = (flags >> 16) & 0xf;
+            const int log2g = NOSPLIT ? 0 : log2g_op;             // NOSPLIT: every slot belongs to one warp ...
+            const int nseg = NOSPLIT ? (1 << log2g_op) : 1;       // ... which walks the op's k-segments itself
             const int rows_q = o->rows_q, rows_rem = o->rows_rem;
             const int r_begin = cta * rows_q + min(cta, rows_rem);
             const int nrows = rows_q + (cta < rows_rem ? 1 : 0);
@@ -703,7 +709,28 @@ __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __gri
                         float v;
                         int u, step;
                         bool holder;
-                        if (rows - r > 2) {
+                        if (NOSPLIT && nseg > 1) {
+                            // all segments of these rows in this warp: v = ((0 + p_0) + p_1) + ... exactly as the partials pass adds them
+                            const int nr = rows - r > 2 ? 4 : (rows - r == 2 ? 2 : 1);
+                            v = 0.0f;
+#pragma unroll 1
+                            for (int sg = 0; sg < nseg; sg++) {
+                                RowCtx<TYPE> cs = c;
+                                cs.a_lo += (uint32_t)(sg * kSegBlocks * 16);
+                                cs.a_hi += (uint32_t)(sg * kSegBlocks * 16);
+                                cs.a_d += (uint32_t)(sg * kSegBlocks * 4);
+                                cs.a_s += (uint32_t)(sg * kSegBlocks * 4);
+                                cs.woff0 += (uint32_t)(sg * kSegBlocks * QSB);
+                                cs.soff0 += (uint32_t)(sg * kSegBlocks * 2);
+#pragma unroll
+                                for (int i = 0; i < 4; i++) cs.blive[i] = sg * kSegBlocks + lane + 32 * i < nb;
+                                v += nr == 4 ? chunk_rows<TYPE, 4>(cs, stage_a, r, rows, lane)
+                                             : (nr == 2 ? chunk_rows<TYPE, 2>(cs, stage_a, r, rows, lane) : chunk_rows<TYPE, 1>(cs, stage_a, r, rows, lane));
+                            }
+                            u = nr == 4 ? lane >> 3 : (nr == 2 ? lane >> 4 : 0);
+                            holder = nr == 4 ? (lane & 7) == 0 : (nr == 2 ? (lane & 15) == 0 : lane == 0);
+                            step = nr;
+                        } else if (rows - r > 2) {
                             v = chunk_rows<TYPE, 4>(c, stage_a, r, rows, lane);
                             u = lane >> 3; holder = (lane & 7) == 0; step = 4;
                         } else if (rows - r == 2) {
@@ -789,6 +816,10 @@ __global__ void __launch_bounds__(plan_threads(MODE), 1) plan_kernel(const __gri
 
 typedef void (*plan_kernel_fn)(const PlanArgs, const PlanGeom);
 static plan_kernel_fn plan_kernel_for(int type, int mode) {
+    if (mode & 16) {        // experimental: no k-split teams
+        if (type == B200_TYPE_Q4_0) return mode == 20 ? plan_kernel<B200_TYPE_Q4_0, 20> : mode == 24 ? plan_kernel<B200_TYPE_Q4_0, 24> : plan_kernel<B200_TYPE_Q4_0, 16>;
+        return mode == 20 ? plan_kernel<B200_TYPE_Q8_0, 20> : mode == 24 ? plan_kernel<B200_TYPE_Q8_0, 24> : plan_kernel<B200_TYPE_Q8_0, 16>;
+    }
     if (type == B200_TYPE_Q4_0)
         return mode == 1 ? plan_kernel<B200_TYPE_Q4_0, 1> : mode == 2 ? plan_kernel<B200_TYPE_Q4_0, 2> : mode == 4 ? plan_kernel<B200_TYPE_Q4_0, 4> :
                mode == 8 ? plan_kernel<B200_TYPE_Q4_0, 8> : plan_kernel<B200_TYPE_Q4_0, 0>;
@@ -1106,6 +1137,7 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     if (e == cudaSuccess && world == 1) e = cudaMemset(p->arena_own, 0, p->arena_bytes);
     const bool any_llq = !any_ring && !pubs.empty();
     p->mode = any_ring ? 1 : any_llq ? (pubq ? 8 : 4) : (g.l2_slots > 0 ? 2 : 0);
+    if (getenv("B200_PLAN_NOSPLIT") && atoi(getenv("B200_PLAN_NOSPLIT")) != 0 && (p->mode == 0 || p->mode == 4 || p->mode == 8)) p->mode |= 16;
     if (e == cudaSuccess && p->mode == 8) e = cudaMalloc((void **)&p->pubcnt_dev, sizeof(uint32_t) * pubs.size());
     if (e == cudaSuccess && p->mode == 8) e = cudaMemset(p->pubcnt_dev, 0, sizeof(uint32_t) * pubs.size());
     if (e == cudaSuccess && any_llq) e = cudaMalloc((void **)&p->pub_dev, sizeof(PubDesc) * pubs.size());

@@ -93,6 +93,19 @@ def test_plan_with_published_planes_experimental(gpu_ctx, oracle, qmm, monkeypat
     check_dag(gpu_ctx, oracle, qmm, case[0], case[1])
 
 
+@pytest.mark.skipif(os.environ.get("B200_TEST_EXPERIMENTAL") != "1", reason="unvalidated kernel mode: set B200_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("llq", ["0", "256"])
+@pytest.mark.parametrize("case", [(Q4_0, "block_pair"), (Q8_0, "block_pair"), (Q4_0, "k_split_8"), (Q8_0, "k_split_8"), (Q4_0, "ragged_chain")],
+                         ids=lambda c: f"{c[1]}-{c[0]}")
+def test_plan_without_k_split_teams_experimental(gpu_ctx, oracle, qmm, monkeypatch, case, llq):
+    """B200_PLAN_NOSPLIT=1 (kernel MODE bit 16, never run): ops with k > 4096 are walked segment by segment by the slot's one
+    warp instead of being split over a team of warps with a partials pass.  Partials are added in the same order: same bits
+    (except the Q8_0 k = 32768 node, which b200_mul_mat itself serves with another kernel: NMSE there, as in check_dag)."""
+    monkeypatch.setenv("B200_PLAN_NOSPLIT", "1")
+    monkeypatch.setenv("B200_PLAN_LLQ", llq)
+    check_dag(gpu_ctx, oracle, qmm, case[0], case[1])
+
+
 @pytest.mark.parametrize("qtype", [Q4_0, Q8_0])
 def test_plan_with_every_src1_quantized_per_cta(gpu_ctx, oracle, qmm, monkeypatch, qtype):
     """B200_PLAN_LLQ=0: the kernel without the publisher warp (what row-split plans run), on the DAG whose k = 16384 node takes

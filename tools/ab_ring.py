@@ -44,7 +44,7 @@ def v_first(nodes):
     return [(old, -1 if nodes[old][1] < 0 else pos[nodes[old][1]]) for old in order]
 
 
-KNOBS = ("B200_PLAN_PUBQ", "B200_PLAN_LLQ", "B200_PLAN_LLQ_DIST", "B200_PLAN_LL_RING", "B200_PLAN_L2_SLOTS", "B200_PLAN_L2_AHEAD", "B200_PLAN_SLOTS", "B200_PLAN_TRACE")
+KNOBS = ("B200_PLAN_NOSPLIT", "B200_PLAN_PUBQ", "B200_PLAN_LLQ", "B200_PLAN_LLQ_DIST", "B200_PLAN_LL_RING", "B200_PLAN_L2_SLOTS", "B200_PLAN_L2_AHEAD", "B200_PLAN_SLOTS", "B200_PLAN_TRACE")
 
 
 def run(label, nodes, env=None, trace=False, reps=60, timeline=False):
@@ -115,11 +115,13 @@ elif which == "llq":
         got = run(oname, nodes, env)
         assert np.array_equal(base.view(np.uint32), got.view(np.uint32)), f"{env}: plan output differs"
     run(oname + " [traced]", nodes, {"B200_PLAN_LLQ": 8192}, trace=True, reps=5, timeline=True)
-elif which == "pubq":          # kernel MODE 8 (experimental): published planes + arrival counter + one bulk copy per CTA
+elif which == "pubq":          # the experimental kernel modes: 8 = published planes + arrival counter + one bulk copy per CTA, 16 = no k-split teams
     oname, nodes = orders[0]
     base = run(oname, nodes)
     for env in ({"B200_PLAN_LLQ": 8192}, {"B200_PLAN_LLQ": 8192, "B200_PLAN_PUBQ": 1}, {"B200_PLAN_LLQ": 4096, "B200_PLAN_PUBQ": 1},
-                {"B200_PLAN_LLQ": 4096, "B200_PLAN_PUBQ": 1, "B200_PLAN_LLQ_DIST": 1}):
+                {"B200_PLAN_LLQ": 4096, "B200_PLAN_PUBQ": 1, "B200_PLAN_LLQ_DIST": 1},
+                {"B200_PLAN_NOSPLIT": 1}, {"B200_PLAN_LLQ": 8192, "B200_PLAN_NOSPLIT": 1}, {"B200_PLAN_LLQ": 8192, "B200_PLAN_PUBQ": 1, "B200_PLAN_NOSPLIT": 1},
+                {"B200_PLAN_LLQ": 4096, "B200_PLAN_PUBQ": 1, "B200_PLAN_NOSPLIT": 1}):
         got = run(oname, nodes, env)
         assert np.array_equal(base.view(np.uint32), got.view(np.uint32)), f"{env}: plan output differs"
     run(oname + " [traced]", nodes, {"B200_PLAN_LLQ": 8192, "B200_PLAN_PUBQ": 1}, trace=True, reps=5, timeline=True)
