@@ -935,7 +935,40 @@ static int plan_analyze(b200_ctx *ctx, const b200_mul_mat_args *args, int count,
     return B200_OK;
 }
 
+static int plan_llq_dist() {        // B200_PLAN_LLQ_DIST: the producing op must lie at least this many ops back (default 2)
+    const char *e = getenv("B200_PLAN_LLQ_DIST");
+    const int v = e ? atoi(e) : 2;
+    return v >= 1 ? v : 2;
+}
+
+// Host-only: which ops take their src1 from the publisher warps (quantized once per GPU, kernel MODE 4 / 8)?  A vector produced
+// inside the plan, long enough (B200_PLAN_LLQ), not shared with the previous op (that one already brought it in), produced
+// far enough back (behind a producer that has just finished the publication would be a second exchange on the critical
+// path), and small enough per CTA: every CTA quantizes 1/grid of the blocks in one warp's run of at most 16 blocks.
+static std::vector<char> plan_published(const b200_mul_mat_args *args, int count, const b200_plan_split *split, const std::vector<int> &src_op, int grid) {
+    std::vector<char> pub((size_t)count, 0);
+    const int mink = plan_llq_min_k(split ? split->world : 1), dist = plan_llq_dist();
+    if (mink <= 0 || grid <= 0) return pub;
+    for (int i = 0; i < count; i++) {
+        const int64_t k = args[i].ne00, nb = k / B200_QK;
+        const bool same_input = i > 0 && k == args[i - 1].ne00 && src_op[(size_t)i] == src_op[(size_t)i - 1] &&
+                                (src_op[(size_t)i] >= 0 || args[i].src1_dev == args[i - 1].src1_dev);
+        pub[(size_t)i] = src_op[(size_t)i] >= 0 && !same_input && k >= mink && (nb + grid - 1) / grid + 1 <= 16 && i - src_op[(size_t)i] >= dist;
+    }
+    return pub;
+}
+
 extern "C" {
+
+int b200_plan_published(const b200_mul_mat_args *args, int count, const b200_plan_split *split, int sm_count, int32_t *published_out) {
+    std::vector<int> so, mt;
+    const int rc = plan_analyze(NULL, args, count, split, &so, &mt);
+    if (rc != B200_OK) return rc;
+    if (sm_count <= 0 || !published_out) return B200_ERR_INVALID;
+    const std::vector<char> pub = plan_published(args, count, split, so, sm_count);
+    for (int i = 0; i < count; i++) published_out[i] = pub[(size_t)i];
+    return B200_OK;
+}
 
 size_t b200_plan_arena_bytes(const b200_mul_mat_args *args, int count, const b200_plan_split *split) {
     if (!args || count <= 0) return 0;
@@ -991,8 +1024,7 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
     std::vector<PubDesc> pubs;
     // experimental protocol (MODE 8); not combinable with the ring-fed experiment, which needs ll_src as it is
     const bool pubq = getenv("B200_PLAN_PUBQ") && atoi(getenv("B200_PLAN_PUBQ")) != 0 && !getenv("B200_PLAN_LL_RING");
-    int llq_dist = 2;
-    if (const char *e = getenv("B200_PLAN_LLQ_DIST")) { const int v = atoi(e); if (v >= 1) llq_dist = v; }
+    const std::vector<char> published = plan_published(args, count, split, src_op, grid);
     B200_REQUIRE(ctx, arena_elems < (1ull << 30), B200_ERR_UNSUPPORTED);
     std::vector<PDesc> pd((size_t)count);
     std::vector<CDesc> cd((size_t)count);
@@ -1045,10 +1077,8 @@ int b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int count, co
         // ops that read the vector the previous op read keep using the quantized activations already in shared memory
         if (i > 0 && c.k == cd[i - 1].k && c.src_op == cd[i - 1].src_op && (c.src_op >= 0 || c.src_plain == cd[i - 1].src_plain))
             c.flags |= OPF_SAME_INPUT;
-        // a long in-plan src1: quantized once per GPU, every CTA 1/grid of the blocks (at most 16 blocks per CTA: one warp's run)
-        // (only vectors produced at least B200_PLAN_LLQ_DIST ops back, default 2: behind a producer that has just finished, the
-        // publication would be a second exchange on the critical path)
-        if (c.src_op >= 0 && !(c.flags & OPF_SAME_INPUT) && llq_off[i] >= 0 && (nb + grid - 1) / grid + 1 <= 16 && i - c.src_op >= llq_dist) {
+        // a long in-plan src1 that the publisher warps quantize once per GPU (plan_published)
+        if (published[(size_t)i] && llq_off[i] >= 0 && !(c.flags & OPF_SAME_INPUT)) {
             c.flags |= OPF_SRC_LLQ;
             c.src_pub = llq_off[i];
             PubDesc pb;

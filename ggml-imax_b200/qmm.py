@@ -111,6 +111,7 @@ _SIGNATURES = {
     "b200_plan_arena_bytes": (C.c_size_t, [C.POINTER(MulMatArgs), C.c_int, C.POINTER(PlanSplit)]),
     "b200_plan_create": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs), C.c_int, C.POINTER(PlanSplit), C.POINTER(C.c_void_p)]),
     "b200_plan_analyze": (C.c_int, [C.POINTER(MulMatArgs), C.c_int, C.POINTER(PlanSplit), C.POINTER(C.c_int32)]),
+    "b200_plan_published": (C.c_int, [C.POINTER(MulMatArgs), C.c_int, C.POINTER(PlanSplit), C.c_int, C.POINTER(C.c_int32)]),
     "b200_plan_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_plan_destroy": (None, [C.c_void_p]),
     "b200_plan_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -233,6 +233,9 @@ B200_API int  b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int
 /* the host-only analysis b200_plan_create starts with (no device needed): same status codes; src_op_out[i] (may be NULL)
  * receives the index of the op whose dst is op i's src1, or -1 for a vector from outside the plan */
 B200_API int  b200_plan_analyze(const b200_mul_mat_args *args, int count, const b200_plan_split *split, int32_t *src_op_out);
+/* host-only as well: published_out[i] = 1 when op i takes its src1 from the once-per-GPU quantization of a long in-plan vector
+ * (the publisher warps of the plan kernel; B200_PLAN_LLQ / B200_PLAN_LLQ_DIST) on a device with sm_count SMs, else 0 */
+B200_API int  b200_plan_published(const b200_mul_mat_args *args, int count, const b200_plan_split *split, int sm_count, int32_t *published_out);
 /* a plan must not be launched concurrently with itself (its hand-off arena and launch counter are per plan) */
 B200_API int  b200_plan_launch(b200_ctx *ctx, b200_plan *plan);      /* asynchronous on the context's stream */
 B200_API void b200_plan_destroy(b200_plan *plan);

@@ -150,3 +150,45 @@ def test_arena_bytes_cover_tagged_vectors_and_published_blocks(qmm, monkeypatch)
     assert lib.b200_plan_arena_bytes(args, len(nodes), C.byref(split)) == ll2
     monkeypatch.setenv("B200_PLAN_LLQ", "8192")
     assert lib.b200_plan_arena_bytes(args, len(nodes), C.byref(split)) == ll2 + llq(8192)
+
+
+def published(qmm, args, sm_count=148, split=None):
+    lib = qmm.load_library()
+    out = (C.c_int32 * len(args))()
+    rc = lib.b200_plan_published(args, len(args), C.byref(split) if split is not None else None, sm_count, out)
+    return rc, list(out)
+
+
+def test_which_src1_vectors_are_quantized_once_per_gpu(qmm, monkeypatch):
+    """b200_plan_published: the host-side choice behind the publisher warps.  GPT-J block:
+    fc_in, v, q, k <- x; o <- v; fc_out <- fc_in; the next block's fc_in, v <- fc_out."""
+    nodes = [(16384, 4096, -1), (4096, 4096, -1), (4096, 4096, -1), (4096, 4096, -1), (4096, 4096, 1), (4096, 16384, 0),
+             (16384, 4096, 5), (4096, 4096, 5)]
+    args = args_for(qmm, nodes)
+    for var in ("B200_PLAN_LLQ", "B200_PLAN_LLQ_DIST"):
+        monkeypatch.delenv(var, raising=False)
+    # default: k >= 8192, produced two or more ops back -> fc_out only
+    assert published(qmm, args) == (qmm.OK, [0, 0, 0, 0, 0, 1, 0, 0])
+    monkeypatch.setenv("B200_PLAN_LLQ", "4096")            # o <- v joins; fc_in <- fc_out is a true dependency (distance 1)
+    assert published(qmm, args) == (qmm.OK, [0, 0, 0, 0, 1, 1, 0, 0])
+    monkeypatch.setenv("B200_PLAN_LLQ_DIST", "1")          # ... unless asked for; v <- fc_out shares fc_in's input: never
+    assert published(qmm, args) == (qmm.OK, [0, 0, 0, 0, 1, 1, 1, 0])
+    monkeypatch.setenv("B200_PLAN_LLQ", "0")
+    assert published(qmm, args) == (qmm.OK, [0] * 8)
+    # a device with few SMs: 512 blocks over 8 CTAs are more than one warp's run of 16 blocks
+    monkeypatch.setenv("B200_PLAN_LLQ", "8192")
+    assert published(qmm, args, sm_count=8) == (qmm.OK, [0] * 8)
+    assert published(qmm, args, sm_count=64)[1][5] == 1
+    # row-split plans: off by default
+    monkeypatch.delenv("B200_PLAN_LLQ", raising=False)
+    split = qmm.PlanSplit()
+    split.world, split.rank = 2, 1
+    # rank 1 of 2 owns the second half of the rows of every matrix
+    nodes2 = [(m // 2, k, src) for m, k, src in nodes]
+    row0 = (C.c_int64 * len(nodes))(*[m // 2 for m, _, _ in nodes])
+    mtot = (C.c_int64 * len(nodes))(*[m for m, _, _ in nodes])
+    split.row0, split.m_total = row0, mtot
+    args2 = args_for(qmm, nodes2)
+    assert published(qmm, args2, split=split) == (qmm.OK, [0] * 8)
+    # bad arguments
+    assert published(qmm, args, sm_count=0)[0] == qmm.ERR_INVALID
