@@ -169,8 +169,6 @@ def run_b200(args):
             sys.exit("--gpus N > 1 must be launched with torch.distributed.run --nproc-per-node N")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if args.trace:
-        os.environ["B200_PLAN_TRACE"] = "1"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     qmm = load_qmm()
@@ -178,6 +176,8 @@ def run_b200(args):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx = qmm.Context(local_rank, stream=stream.cuda_stream)   # our launches go to torch's stream: plumbing only
+    if args.trace:
+        ctx.set_option("plan_trace", 1)
     # a second stream/context: independent nodes of the graph (o and fc_out of a block) run concurrently, fork/join by events
     side = torch.cuda.Stream(device=dev)
     ctx2 = qmm.Context(local_rank, stream=side.cuda_stream)
@@ -598,7 +598,7 @@ def run_b200(args):
                        "path": "decode plan: one persistent launch per token (b200_plan_launch)" if plan_fn is not None else "one launch per same-input group",
                        "parallelism": (f"row-split x{world} + " + ("all-gather fused into the GEMV epilogue (tagged NVLink peer stores)" if (fused is not None or plan_fn is not None) else "NCCL all-gather")) if world > 1 else "single GPU",
                        "gather_check_vs_nccl": gather_check, "plan_vs_launch_per_node_bitwise": plan_check,
-                       "plan_src1_quantized_once_per_gpu_k_min": (int(os.environ.get("B200_PLAN_LLQ", 8192 if world == 1 else 0)) if plan_fn is not None else None), "graph_vs_plain_walk_bitwise": plain_check,
+                       "plan_src1_quantized_once_per_gpu_k_min": (4096 if plan_fn is not None else None), "graph_vs_plain_walk_bitwise": plain_check,
                        "streams": 1 if plan_fn is not None else (2 if (world == 1 and not args.no_overlap) else 1),
                        "weights_bytes_per_token": sum(m * (k // 32) * 18 for _, m, k in mats)},
             "e2e": {"value": round(1000.0 / ms_e2e, 2), "unit": "tokens/s", "h2d_bytes_per_step": N_EMBD * 4, "d2h_bytes_per_step": N_VOCAB * 4,

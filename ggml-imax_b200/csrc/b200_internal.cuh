@@ -27,6 +27,18 @@ struct b200_ctx {
     int          opt_gemm;
     int          opt_gemv_max_n;
     int          opt_gemv_stream;
+    int          opt_gemm_exact;        // 1: prefill GEMM = exact int8 block dots + fp32 scaling (slow); 0: fp16 tcgen05 path
+    // decode plans (b200_plan.cu)
+    int          opt_plan_pub_min_k;    // shortest in-plan src1 that is quantized once per GPU (0 = never)
+    int          opt_plan_pub_dist;     // ... when its producer lies at least this many ops back
+    int          opt_plan_l2_window;    // ring slots the L2 prefetcher runs ahead of the weight stream (0 = off)
+    int          opt_plan_slots;        // ring slots (0 = as many as fit)
+    int          opt_plan_evict_first;  // ring copies carry the L2 evict-first policy
+    int          opt_plan_trace;        // plans created from now on record a device-side timeline
+    int          opt_plan_timeout_ms;   // bound of every wait on global memory inside a plan (0 = default)
+    // abort word: a kernel whose bounded wait expired leaves a code in abort_dev (device memory, polled by the other waits)
+    // and in abort_host (pinned host memory, abort_host_dev = its device alias), where b200_synchronize finds it for free
+    uint32_t    *abort_host, *abort_host_dev, *abort_dev;
     // optional device-side timeline: 8 x u64 %globaltimer stamps per (launch, CTA), see b200_ctx_set_trace
     unsigned long long *trace;
     int64_t      trace_capacity;   // in launches

@@ -78,15 +78,41 @@ static int ctx_create_common(int device, void *stream, bool own, b200_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->cc_major = prop.major;
     ctx->cc_minor = prop.minor;
-    ctx->opt_pdl = getenv("B200_NO_PDL") ? 0 : 1;
-    ctx->opt_gemm = getenv("B200_NO_GEMM") ? 0 : 1;
+    ctx->opt_pdl = 1;
+    ctx->opt_gemm = 1;
     ctx->opt_gemv_max_n = 8;
-    ctx->opt_gemv_stream = getenv("B200_NO_STREAM_GEMV") ? 0 : 1;
-    B200_CUDA_TRY(ctx, cudaSetDevice(device));
+    ctx->opt_gemv_stream = 1;
+    ctx->opt_gemm_exact = 0;
+    ctx->opt_plan_pub_min_k = 4096;
+    ctx->opt_plan_pub_dist = 2;
+    ctx->opt_plan_l2_window = 8;
+    ctx->opt_plan_evict_first = 1;
+    {
+        cudaError_t e0 = cudaSetDevice(device);
+        if (e0 == cudaSuccess) e0 = cudaHostAlloc((void **)&ctx->abort_host, 64, cudaHostAllocMapped);
+        if (e0 == cudaSuccess) {
+            memset(ctx->abort_host, 0, 64);
+            e0 = cudaHostGetDevicePointer((void **)&ctx->abort_host_dev, ctx->abort_host, 0);
+        }
+        if (e0 == cudaSuccess) e0 = cudaMalloc((void **)&ctx->abort_dev, 64);
+        if (e0 == cudaSuccess) e0 = cudaMemset(ctx->abort_dev, 0, 64);
+        if (e0 != cudaSuccess) {
+            b200_set_error(NULL, "context setup on device %d failed: %s", device, cudaGetErrorString(e0));
+            (void)cudaGetLastError();
+            if (ctx->abort_host) cudaFreeHost(ctx->abort_host);
+            if (ctx->abort_dev) cudaFree(ctx->abort_dev);
+            (void)cudaGetLastError();
+            free(ctx);
+            return B200_ERR_CUDA;
+        }
+    }
     if (own) {
         cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) {
             b200_set_error(NULL, "cudaStreamCreate: %s", cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            cudaFreeHost(ctx->abort_host);
+            cudaFree(ctx->abort_dev);
             free(ctx);
             return B200_ERR_CUDA;
         }
@@ -111,6 +137,9 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->abort_host) cudaFreeHost(ctx->abort_host);
+    if (ctx->abort_dev) cudaFree(ctx->abort_dev);
+    (void)cudaGetLastError();
     free(ctx);
 }
 
@@ -128,6 +157,14 @@ int b200_ctx_set_option(b200_ctx *ctx, const char *key, int64_t value) {
         ctx->opt_gemv_max_n = (int)value;
         return B200_OK;
     }
+    if (!strcmp(key, "gemm_exact")) { ctx->opt_gemm_exact = value != 0; return B200_OK; }
+    if (!strcmp(key, "plan_pub_min_k")) { ctx->opt_plan_pub_min_k = value > 0 ? (int)value : 0; return B200_OK; }
+    if (!strcmp(key, "plan_pub_dist")) { ctx->opt_plan_pub_dist = value >= 1 ? (int)value : 1; return B200_OK; }
+    if (!strcmp(key, "plan_l2_window")) { ctx->opt_plan_l2_window = value > 0 ? (int)(value > 4096 ? 4096 : value) : 0; return B200_OK; }
+    if (!strcmp(key, "plan_evict_first")) { ctx->opt_plan_evict_first = value != 0; return B200_OK; }
+    if (!strcmp(key, "plan_slots")) { ctx->opt_plan_slots = value > 0 ? (int)value : 0; return B200_OK; }
+    if (!strcmp(key, "plan_trace")) { ctx->opt_plan_trace = value != 0; return B200_OK; }
+    if (!strcmp(key, "plan_timeout_ms")) { ctx->opt_plan_timeout_ms = value > 0 ? (int)value : 0; return B200_OK; }
     b200_set_error(ctx, "unknown option '%s'", key);
     return B200_ERR_INVALID;
 }
@@ -213,6 +250,16 @@ int b200_synchronize(b200_ctx *ctx) {
     B200_REQUIRE(ctx, ctx != NULL, B200_ERR_INVALID);
     B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     B200_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->abort_host && *(volatile uint32_t *)ctx->abort_host != 0u) {
+        // a bounded wait inside a persistent kernel expired (b200_plan.cu): what 1 = tagged vector, 2 = publication count, 3 = export
+        const uint32_t code = *(volatile uint32_t *)ctx->abort_host;
+        *(volatile uint32_t *)ctx->abort_host = 0u;
+        B200_CUDA_TRY(ctx, cudaMemsetAsync(ctx->abort_dev, 0, 64, ctx->stream));
+        B200_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        b200_set_error(ctx, "a decode plan gave up waiting (wait kind %u, detail 0x%x): a peer rank died or launched a different sequence; results of this launch are invalid",
+                       code & 0xffu, (code & 0x7fffffffu) >> 8);
+        return B200_ERR_CUDA;
+    }
     return B200_OK;
 }
 

@@ -111,7 +111,8 @@ _SIGNATURES = {
     "b200_plan_arena_bytes": (C.c_size_t, [C.POINTER(MulMatArgs), C.c_int, C.POINTER(PlanSplit)]),
     "b200_plan_create": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs), C.c_int, C.POINTER(PlanSplit), C.POINTER(C.c_void_p)]),
     "b200_plan_analyze": (C.c_int, [C.POINTER(MulMatArgs), C.c_int, C.POINTER(PlanSplit), C.POINTER(C.c_int32)]),
-    "b200_plan_published": (C.c_int, [C.POINTER(MulMatArgs), C.c_int, C.POINTER(PlanSplit), C.c_int, C.POINTER(C.c_int32)]),
+    "b200_plan_published": (C.c_int, [C.POINTER(MulMatArgs), C.c_int, C.POINTER(PlanSplit), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
+    "b200_plan_plain_stores": (C.c_int, [C.POINTER(MulMatArgs), C.c_int, C.POINTER(PlanSplit), C.POINTER(C.c_int32)]),
     "b200_plan_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_plan_destroy": (None, [C.c_void_p]),
     "b200_plan_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -413,7 +414,7 @@ class Context:
         self.lib.b200_plan_destroy(C.c_void_p(plan))
 
     def plan_trace(self, plan: int) -> np.ndarray:
-        """[nops + 1, grid, 4] ns stamps of the last launch (needs env B200_PLAN_TRACE at plan_create); the last row holds
+        """[nops + 1, grid, 4] ns stamps of the last launch (needs set_option('plan_trace', 1) before plan_create); the last row holds
         per-CTA totals: producer blocked on a full ring, a consumer warp blocked on an empty ring, time in quantization phases"""
         nops, grid = C.c_int(), C.c_int()
         self.lib.b200_plan_trace(self.h, C.c_void_p(plan), None, 0, C.byref(nops), C.byref(grid))

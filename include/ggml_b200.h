@@ -62,8 +62,16 @@ B200_API void b200_ctx_destroy(b200_ctx *ctx);
 B200_API const char *b200_last_error(const b200_ctx *ctx);   /* ctx may be NULL: last global error */
 B200_API void *b200_ctx_stream(const b200_ctx *ctx);         /* the cudaStream_t launches go to     */
 B200_API int  b200_ctx_device(const b200_ctx *ctx);
-/* knobs: "pdl" (0/1 programmatic dependent launch on the decode GEMV), "gemm" (0 = never use the
- * tcgen05 GEMM, 1 = auto), "gemv_max_n" (largest n served by the GEMV), "gemv_stream" (0 = generic GEMV only). returns B200_ERR_INVALID if unknown */
+/* knobs (the library reads NO environment variables; every knob is a per-context option with a measured default):
+ *   "pdl" (0/1 programmatic dependent launch on the decode GEMV), "gemm" (0 = never use the tcgen05 GEMM, 1 = auto),
+ *   "gemv_max_n" (largest n served by the GEMV), "gemv_stream" (0 = generic GEMV only),
+ *   "gemm_exact" (1 = prefill GEMM keeps exact int32 block dots + fp32 scaling; 0 = fp16 tensor-core path, default),
+ *   decode plans created afterwards: "plan_pub_min_k" / "plan_pub_dist" (an in-plan src1 of at least that many elements whose
+ *   producer lies at least that many ops back is quantized once per GPU; 0 = never), "plan_l2_window" (ring slots the L2
+ *   prefetcher runs ahead of the weight stream; 0 = off), "plan_slots" (ring slots; 0 = as many as fit), "plan_trace"
+ *   (record a device-side timeline, see b200_plan_trace), "plan_timeout_ms" (bound of every in-kernel wait; 0 = default:
+ *   10 s on one GPU, 120 s for row-split plans).
+ * returns B200_ERR_INVALID if unknown */
 B200_API int  b200_ctx_set_option(b200_ctx *ctx, const char *key, int64_t value);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 B200_API int64_t b200_ctx_launch_count(const b200_ctx *ctx);
@@ -85,7 +93,9 @@ B200_API int b200_download(b200_ctx *ctx, void *dst_host, const void *src_dev, s
 B200_API int b200_upload_async(b200_ctx *ctx, void *dst_dev, const void *src_host, size_t size);
 B200_API int b200_download_async(b200_ctx *ctx, void *dst_host, const void *src_dev, size_t size);
 B200_API int b200_copy_d2d(b200_ctx *ctx, void *dst_dev, const void *src_dev, size_t size);  /* async */
-B200_API int b200_synchronize(b200_ctx *ctx);          /* ggml_backend_i.synchronize */
+/* ggml_backend_i.synchronize.  Also where a persistent kernel that gave up waiting (a dead peer rank, mismatched launch
+ * sequences) surfaces: B200_ERR_CUDA with the reason in b200_last_error; the results of that launch are invalid. */
+B200_API int b200_synchronize(b200_ctx *ctx);
 /* pinned host staging (ggml_backend_cuda_host_buffer_type, src/ggml-cuda.h:31) */
 B200_API int b200_host_malloc(void **hptr, size_t size);
 B200_API int b200_host_free(void *hptr);
@@ -211,9 +221,12 @@ B200_API int b200_ipc_close(b200_ctx *ctx, void *peer_ptr);
  * One persistent CTA per SM walks the list; a producer thread per CTA streams the weights of op 0, 1, 2, ... back to
  * back through a shared-memory ring (HBM never idles at an op boundary), and results travel between ops as tagged
  * 8-byte elements, so there is no grid-wide barrier anywhere.  Results are bit-identical to `count` b200_mul_mat calls.
- * Every dst_dev is still written as plain fp32 (may be NULL for intermediates nobody outside reads).
- * B200_ERR_UNSUPPORTED: a shape outside the above, or plain vectors that alias each other (buffer reuse by a graph
- * allocator) -- the caller then runs the nodes one by one through b200_mul_mat / b200_mul_mat_batch.
+ * Every dst_dev is still written as plain fp32 (may be NULL for intermediates nobody outside reads), EXCEPT a dst whose memory
+ * a later op's dst reuses (what ggml_gallocr does with dead intermediates, src/ggml-alloc.c): that store is dropped, see
+ * b200_plan_plain_stores.  The launch is cooperative (all CTAs resident or none), every in-kernel wait is bounded.
+ * B200_ERR_UNSUPPORTED: a shape outside the above, a src1 that is a partial view of another op's dst, or a dst that overwrites
+ * an outside input some CTA may still have to read -- the caller then runs the nodes one by one through b200_mul_mat /
+ * b200_mul_mat_batch.
  *
  * Row-split plans (split != NULL, one process per GPU): args[i] describes THIS rank's row slice of op i (ne01 = local
  * rows, src0 = local slice), split->row0[i] / m_total[i] place it in the whole matrix.  The tagged stores go to every
@@ -233,13 +246,19 @@ B200_API int  b200_plan_create(b200_ctx *ctx, const b200_mul_mat_args *args, int
 /* the host-only analysis b200_plan_create starts with (no device needed): same status codes; src_op_out[i] (may be NULL)
  * receives the index of the op whose dst is op i's src1, or -1 for a vector from outside the plan */
 B200_API int  b200_plan_analyze(const b200_mul_mat_args *args, int count, const b200_plan_split *split, int32_t *src_op_out);
-/* host-only as well: published_out[i] = 1 when op i takes its src1 from the once-per-GPU quantization of a long in-plan vector
- * (the publisher warps of the plan kernel; B200_PLAN_LLQ / B200_PLAN_LLQ_DIST) on a device with sm_count SMs, else 0 */
-B200_API int  b200_plan_published(const b200_mul_mat_args *args, int count, const b200_plan_split *split, int sm_count, int32_t *published_out);
+/* host-only as well: published_out[i] = 1 when op i takes its src1 from the once-per-GPU quantization of an in-plan vector
+ * (the publisher / fetcher warps of the plan kernel) on a device with sm_count SMs, else 0.  min_k / dist = the context options
+ * "plan_pub_min_k" / "plan_pub_dist"; <= 0 selects their defaults (4096, 2) */
+B200_API int  b200_plan_published(const b200_mul_mat_args *args, int count, const b200_plan_split *split, int sm_count,
+                                  int min_k, int dist, int32_t *published_out);
+/* host-only: plain_out[i] = 1 when the plan stores op i's result in args[i].dst_dev as plain fp32, 0 when it does not: dst_dev
+ * is NULL, or a LATER op's dst occupies the same memory (buffer reuse by a graph allocator such as ggml_gallocr,
+ * src/ggml-alloc.c: the earlier tensor is dead by the end of the graph; inside the plan its value travels as a tagged vector) */
+B200_API int  b200_plan_plain_stores(const b200_mul_mat_args *args, int count, const b200_plan_split *split, int32_t *plain_out);
 /* a plan must not be launched concurrently with itself (its hand-off arena and launch counter are per plan) */
 B200_API int  b200_plan_launch(b200_ctx *ctx, b200_plan *plan);      /* asynchronous on the context's stream */
 B200_API void b200_plan_destroy(b200_plan *plan);
-/* device-side timeline of the last launch (plan created with env B200_PLAN_TRACE set): [nops + 1][grid][4] ns stamps
+/* device-side timeline of the last launch (plan created with option "plan_trace" = 1): [nops + 1][grid][4] ns stamps
  * (src1 complete, activations quantized, first weights landed, last row done; the last row holds per-CTA totals: ns the
  * producer spent blocked on a full ring, ns one consumer warp spent blocked on an empty ring, ns spent in quantization
  * phases); B200_ERR_UNSUPPORTED when not tracing */

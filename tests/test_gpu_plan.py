@@ -1,7 +1,7 @@
 """Decode plans (b200_plan_*): a dependent sequence of decode mul_mats as one persistent launch, against the oracle
 (ggml_compute_forward_mul_mat, src/ggml.c:11808, applied node by node) and against the node-by-node CUDA path
 (bit-identical by construction)."""
-import os
+import ctypes as C
 
 import numpy as np
 import pytest
@@ -57,61 +57,124 @@ def test_plan_matches_oracle_and_node_by_node(gpu_ctx, oracle, qmm, qtype, dag):
     check_dag(gpu_ctx, oracle, qmm, qtype, dag)
 
 
-@pytest.mark.parametrize("case", [(Q4_0, "block_pair"), (Q8_0, "block_pair"), (Q4_0, "ragged_chain"), (Q4_0, "many_ops"), (Q8_0, "k_split_8")],
-                         ids=lambda c: f"{c[1]}-{c[0]}")
-@pytest.mark.parametrize("ring", ["-2", "-1", "3"])
-def test_plan_with_ring_fed_src1(gpu_ctx, oracle, qmm, monkeypatch, case, ring):
-    """B200_PLAN_LL_RING: src1 vectors produced inside the plan travel through the weight ring (copied by the producer
-    thread) instead of being fetched from L2 by the consumers.  -2 feeds EVERY such vector that way, also those whose
-    producer is the op right before (the copy is then always taken too early: the tag check must catch it and fall back),
-    -1 those produced two or more ops back, 3 the production rule (at least 3 ring slots in between).  Same bits as ever."""
-    monkeypatch.setenv("B200_PLAN_LL_RING", ring)
-    check_dag(gpu_ctx, oracle, qmm, case[0], case[1])
+PLAN_OPTION_DEFAULTS = {"plan_pub_min_k": 4096, "plan_pub_dist": 2, "plan_l2_window": 8, "plan_evict_first": 1, "plan_slots": 0}
 
 
+@pytest.fixture
+def plan_options(gpu_ctx):
+    """set decode-plan options on the shared context for one test, defaults restored afterwards"""
+    def set_(**kw):
+        for k, v in kw.items():
+            gpu_ctx.set_option(k, v)
+    yield set_
+    for k, v in PLAN_OPTION_DEFAULTS.items():
+        gpu_ctx.set_option(k, v)
+
+
+@pytest.mark.parametrize("dist", [1, 2])
 @pytest.mark.parametrize("case", [(Q4_0, "block_pair"), (Q8_0, "block_pair"), (Q4_0, "ragged_chain"), (Q4_0, "many_ops"), (Q4_0, "k_split_8"),
                                   (Q8_0, "k_split_8")], ids=lambda c: f"{c[1]}-{c[0]}")
-def test_plan_with_src1_quantized_once_per_gpu(gpu_ctx, oracle, qmm, monkeypatch, case):
-    """B200_PLAN_LLQ=k_min: an in-plan src1 of k >= k_min is quantized once per GPU (every CTA 1/grid of the blocks, published
-    as tagged words) instead of once per CTA.  quantize_row_q8_0 on the same fp32 values: the same bits as ever."""
-    monkeypatch.setenv("B200_PLAN_LLQ", "256")
-    monkeypatch.setenv("B200_PLAN_LLQ_DIST", "1")       # also right behind the producing op (the publisher then waits for it)
-    check_dag(gpu_ctx, oracle, qmm, case[0], case[1])
-
-
-@pytest.mark.skipif(os.environ.get("B200_TEST_EXPERIMENTAL") != "1", reason="unvalidated kernel mode: set B200_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("dist", ["1", "2"])
-@pytest.mark.parametrize("case", [(Q4_0, "block_pair"), (Q8_0, "block_pair"), (Q4_0, "ragged_chain"), (Q4_0, "many_ops"), (Q4_0, "k_split_8"),
-                                  (Q8_0, "k_split_8")], ids=lambda c: f"{c[1]}-{c[0]}")
-def test_plan_with_published_planes_experimental(gpu_ctx, oracle, qmm, monkeypatch, case, dist):
-    """B200_PLAN_PUBQ=1 (kernel MODE 8, written at the end of round 1: only the block_pair cases have run on a GPU so far -- they pass --
-    and no timing exists, hence the gate): the once-per-GPU quantization
-    published as plain activation planes + an arrival counter, taken by every CTA with one bulk copy.  Same bits as ever."""
-    monkeypatch.setenv("B200_PLAN_PUBQ", "1")
-    monkeypatch.setenv("B200_PLAN_LLQ", "256")
-    monkeypatch.setenv("B200_PLAN_LLQ_DIST", dist)
-    check_dag(gpu_ctx, oracle, qmm, case[0], case[1])
-
-
-@pytest.mark.skipif(os.environ.get("B200_TEST_EXPERIMENTAL") != "1", reason="unvalidated kernel mode: set B200_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("llq", ["0", "256"])
-@pytest.mark.parametrize("case", [(Q4_0, "block_pair"), (Q8_0, "block_pair"), (Q4_0, "k_split_8"), (Q8_0, "k_split_8"), (Q4_0, "ragged_chain")],
-                         ids=lambda c: f"{c[1]}-{c[0]}")
-def test_plan_without_k_split_teams_experimental(gpu_ctx, oracle, qmm, monkeypatch, case, llq):
-    """B200_PLAN_NOSPLIT=1 (kernel MODE bit 16, never run): ops with k > 4096 are walked segment by segment by the slot's one
-    warp instead of being split over a team of warps with a partials pass.  Partials are added in the same order: same bits
-    (except the Q8_0 k = 32768 node, which b200_mul_mat itself serves with another kernel: NMSE there, as in check_dag)."""
-    monkeypatch.setenv("B200_PLAN_NOSPLIT", "1")
-    monkeypatch.setenv("B200_PLAN_LLQ", llq)
+def test_plan_with_every_possible_src1_published(gpu_ctx, oracle, qmm, plan_options, case, dist):
+    """plan_pub_min_k = 256: EVERY in-plan src1 that is not shared with the previous op is quantized once per GPU by the
+    publisher warps (every CTA 1/grid of the blocks, plain activation planes + an arrival counter) and brought into a rotating
+    activation buffer by the fetcher's bulk copy.  dist = 1 also publishes right behind the producing op (the publisher then
+    waits for it).  quantize_row_q8_0 on the same fp32 values: the same bits as ever."""
+    plan_options(plan_pub_min_k=256, plan_pub_dist=dist)
     check_dag(gpu_ctx, oracle, qmm, case[0], case[1])
 
 
 @pytest.mark.parametrize("qtype", [Q4_0, Q8_0])
-def test_plan_with_every_src1_quantized_per_cta(gpu_ctx, oracle, qmm, monkeypatch, qtype):
-    """B200_PLAN_LLQ=0: the kernel without the publisher warp (what row-split plans run), on the DAG whose k = 16384 node takes
-    the quantized-once path by default."""
-    monkeypatch.setenv("B200_PLAN_LLQ", "0")
-    check_dag(gpu_ctx, oracle, qmm, qtype, "block_pair")
+@pytest.mark.parametrize("dag", ["block_pair", "k_split_8"])
+def test_plan_with_every_src1_quantized_per_cta(gpu_ctx, oracle, qmm, plan_options, qtype, dag):
+    """plan_pub_min_k = 0: no publisher / fetcher work at all; every CTA fetches and quantizes every vector itself."""
+    plan_options(plan_pub_min_k=0)
+    check_dag(gpu_ctx, oracle, qmm, qtype, dag)
+
+
+@pytest.mark.parametrize("window", [0, 2, 64])
+@pytest.mark.parametrize("slots", [0, 3])
+def test_plan_l2_prefetch_window_and_short_ring(gpu_ctx, oracle, qmm, plan_options, window, slots):
+    """the L2 prefetcher off / barely ahead / far ahead of the weight stream, with the full ring and with three slots
+    (every hand-off then stalls the producer): prefetching never changes a bit"""
+    plan_options(plan_l2_window=window, plan_slots=slots)
+    check_dag(gpu_ctx, oracle, qmm, Q4_0, "block_pair")
+    check_dag(gpu_ctx, oracle, qmm, Q8_0, "ragged_chain")
+
+
+def test_plan_accepts_allocator_style_buffer_reuse(gpu_ctx, oracle, qmm):
+    """ggml_gallocr hands the memory of a dead intermediate to a later tensor (src/ggml-alloc.c).  A chain x -> a -> b -> c -> d
+    with c in a's memory and d in b's: the plan keeps a and b out of plain memory (their values travel as tagged vectors) and
+    c, d come out right."""
+    nodes = [(1024, 512, -1), (768, 1024, 0), (1024, 768, 1), (768, 1024, 2), (300, 768, 3)]
+    ws = build_dag(oracle, qmm, gpu_ctx, Q4_0, nodes, seed=77)
+    rng = np.random.default_rng(7)
+    x = rng.uniform(-1, 1, 512).astype(np.float32)
+    xd = gpu_ctx.to_device(x)
+    bufA, bufB, bufE = gpu_ctx.alloc(1024 * 4), gpu_ctx.alloc(768 * 4), gpu_ctx.alloc(300 * 4)
+    dst = [bufA, bufB, bufA, bufB, bufE]
+    args = [gpu_ctx.make_args(ws[i][0], xd.ptr if s < 0 else dst[s].ptr, 1, dst[i].ptr) for i, (m, k, s) in enumerate(nodes)]
+    arr = (qmm.MulMatArgs * len(args))(*args)
+    so = (C.c_int32 * len(args))()
+    assert gpu_ctx.lib.b200_plan_analyze(arr, len(args), None, so) == qmm.OK and list(so) == [-1, 0, 1, 2, 3]
+    plain = (C.c_int32 * len(args))()
+    assert gpu_ctx.lib.b200_plan_plain_stores(arr, len(args), None, plain) == qmm.OK and list(plain) == [0, 0, 1, 1, 1]
+    plan = gpu_ctx.plan_create(args)
+    try:
+        for _ in range(3):
+            gpu_ctx.plan_launch(plan)
+        gpu_ctx.synchronize()
+        got_c, got_d, got_e = bufA.download(np.float32, 1024), bufB.download(np.float32, 768), bufE.download(np.float32, 300)
+        # sequential reference through b200_mul_mat (which is what ggml would run node by node on this very memory)
+        for a in args:
+            gpu_ctx._check(gpu_ctx.lib.b200_mul_mat(gpu_ctx.h, a))
+        gpu_ctx.synchronize()
+        assert np.array_equal(got_c, bufA.download(np.float32, 1024))
+        assert np.array_equal(got_d, bufB.download(np.float32, 768))
+        assert np.array_equal(got_e, bufE.download(np.float32, 300))
+        ref = run_oracle(oracle, Q4_0, nodes, ws, x)
+        assert nmse(got_e, ref[4]) <= 1e-4       # (a five-deep chain: the oracle's own inputs differ by summation order)
+    finally:
+        gpu_ctx.plan_destroy(plan)
+        xd.free(); bufA.free(); bufB.free(); bufE.free()
+        for t, _ in ws:
+            t.free()
+
+
+def test_plan_wait_is_bounded(gpu_ctx, oracle, qmm, plan_options):
+    """A row-split plan whose peer never shows up: the kernel must give up after plan_timeout_ms and b200_synchronize must
+    say so, instead of hanging the GPU (world = 2, both 'peer' arenas local, rank 1 never launched)."""
+    plan_options(plan_timeout_ms=300)
+    nodes = [(256, 256, -1), (256, 512, 0)]          # rank 0 owns rows 0..255 of a 512-row op 0; op 1 needs all 512
+    ws = build_dag(oracle, qmm, gpu_ctx, Q4_0, nodes, seed=3)
+    xd = gpu_ctx.to_device(np.ones(256, np.float32))
+    outs = [gpu_ctx.alloc(512 * 4), gpu_ctx.alloc(256 * 4)]
+    args = [gpu_ctx.make_args(ws[0][0], xd.ptr, 1, outs[0].ptr), gpu_ctx.make_args(ws[1][0], outs[0].ptr, 1, outs[1].ptr)]
+    args[1].flags |= qmm.MM_EXPORT
+    split = qmm.PlanSplit()
+    split.world, split.rank = 2, 0
+    row0 = (C.c_int64 * 2)(0, 0)
+    mtot = (C.c_int64 * 2)(512, 256)
+    split.row0, split.m_total = row0, mtot
+    nbytes = gpu_ctx.plan_arena_bytes(args, split)
+    arena0, arena1 = gpu_ctx.alloc(nbytes), gpu_ctx.alloc(nbytes)
+    for a in (arena0, arena1):
+        gpu_ctx._check(gpu_ctx.lib.b200_memset(gpu_ctx.h, a.ptr, 0, nbytes))
+    split.peer_arena[0], split.peer_arena[1] = arena0.ptr, arena1.ptr
+    plan = gpu_ctx.plan_create(args, split)
+    try:
+        gpu_ctx.plan_launch(plan)
+        with pytest.raises(qmm.B200Error) as e:
+            gpu_ctx.synchronize()
+        assert e.value.code == qmm.ERR_CUDA and "gave up waiting" in str(e.value)
+        gpu_ctx.synchronize()            # the context stays usable
+    finally:
+        gpu_ctx.set_option("plan_timeout_ms", 0)
+        gpu_ctx.plan_destroy(plan)
+        xd.free(); arena0.free(); arena1.free()
+        for o in outs:
+            o.free()
+        for t, _ in ws:
+            t.free()
 
 
 def check_dag(gpu_ctx, oracle, qmm, qtype, dag):
@@ -178,7 +241,7 @@ def test_plan_rejects_what_it_cannot_run(gpu_ctx, oracle, qmm):
     y = gpu_ctx.alloc(64 * 4)
     try:
         a0 = gpu_ctx.make_args(ws[0][0], x.ptr, 1, y.ptr)
-        a1 = gpu_ctx.make_args(ws[1][0], x.ptr, 1, y.ptr)         # two nodes writing the same plain vector
+        a1 = gpu_ctx.make_args(ws[1][0], x.ptr, 1, x.ptr)         # writes over the outside vector other CTAs may still have to read
         with pytest.raises(qmm.B200Error) as e:
             gpu_ctx.plan_create([a0, a1])
         assert e.value.code == qmm.ERR_UNSUPPORTED

@@ -52,14 +52,37 @@ def test_latest_writer_of_an_address_is_the_producer(qmm):
     assert rc == qmm.OK and so == [-1, 0, -1, 1]
 
 
-@pytest.mark.parametrize("case", ["dst_reuse", "partial_overlap", "dst_over_input", "src_inside_dst"])
-def test_aliasing_vectors_are_refused(qmm, case):
-    if case == "dst_reuse":          # a graph allocator gave two tensors the same memory
-        nodes = [(256, 256, -1, 0x20000000), (256, 256, 0), (256, 256, 1, 0x20000000)]
-    elif case == "partial_overlap":
-        nodes = [(256, 256, -1, 0x20000000), (256, 256, -1, 0x20000000 + 512)]
-    elif case == "dst_over_input":   # an op writes over the vector that came from outside
-        nodes = [(256, 256, -1), (256, 256, 0, 0x0F000000)]
+def plain_stores(qmm, args):
+    lib = qmm.load_library()
+    out = (C.c_int32 * len(args))()
+    rc = lib.b200_plan_plain_stores(args, len(args), None, out)
+    return rc, list(out)
+
+
+def test_allocator_style_buffer_reuse_drops_the_dead_store(qmm):
+    """ggml_gallocr gives a later tensor the memory of a dead intermediate (src/ggml-alloc.c).  Dataflow execution has no
+    global order between a slow CTA's store of the dead tensor and a fast CTA's store of the new one, so the dead store is
+    dropped; its value travels as a tagged vector.  Dataflow still follows the LATEST writer of an address."""
+    nodes = [(256, 256, -1, 0x20000000), (256, 256, 0), (256, 256, 1, 0x20000000), (128, 256, 2)]
+    args = args_for(qmm, nodes)
+    assert analyze(qmm, args) == (qmm.OK, [-1, 0, 1, 2])
+    assert plain_stores(qmm, args) == (qmm.OK, [0, 1, 1, 1])
+    # a smaller tensor inside the dead one's block
+    nodes = [(512, 256, -1, 0x20000000), (256, 512, 0), (64, 256, 1, 0x20000000 + 1024)]
+    args = args_for(qmm, nodes)
+    assert analyze(qmm, args) == (qmm.OK, [-1, 0, 1])
+    assert plain_stores(qmm, args) == (qmm.OK, [0, 1, 1])
+    # an op may take the memory of the outside input once its own producer has consumed it everywhere
+    nodes = [(256, 256, -1), (256, 256, 0, 0x0F000000)]
+    assert analyze(qmm, args_for(qmm, nodes))[0] == qmm.OK
+
+
+@pytest.mark.parametrize("case", ["dst_over_live_input", "dst_over_input_of_later_reader", "src_inside_dst"])
+def test_hazards_dataflow_execution_cannot_order_are_refused(qmm, case):
+    if case == "dst_over_live_input":      # op 1 does not wait for op 0: some CTA may still have to read x for op 0
+        nodes = [(256, 256, -1), (256, 256, -1, 0x0F000000)]
+    elif case == "dst_over_input_of_later_reader":   # op 2 waits only for op 0, but op 1 reads x too and may not have started
+        nodes = [(256, 256, -1), (512, 256, -1), (256, 256, 0, 0x0F000000)]
     else:                            # src1 points INTO another op's dst (a view): not "exactly that vector"
         nodes = [(512, 256, -1, 0x20000000), (256, 256, -1)]
     args = args_for(qmm, nodes)
@@ -122,73 +145,55 @@ def test_row_split_description_is_checked(qmm):
     assert analyze(qmm, args, s)[0] == qmm.ERR_INVALID
 
 
-def test_arena_bytes_cover_tagged_vectors_and_published_blocks(qmm, monkeypatch):
+def test_arena_bytes_cover_tagged_vectors_and_published_planes(qmm):
     """b200_plan_arena_bytes is what a row-split caller allocates (and shares over CUDA IPC) before b200_plan_create: one
-    tagged vector per op (8 B per element, padded to 128 B), plus -- for every op whose k reaches B200_PLAN_LLQ -- room for the
-    src1 blocks the publisher warps quantize once per GPU (10 tagged words per block of 32).  Default: k >= 8192 on one GPU,
-    nothing for row-split plans."""
+    tagged vector per op (8 B per element, padded to 128 B), plus room for the published planes of every op's src1
+    (k int8 + k/32 x (fp32 d, 8 * sum)), whatever the options -- every rank must compute the same layout."""
     lib = qmm.load_library()
     nodes = [(16384, 4096, -1), (4096, 4096, -1), (4096, 16384, 0), (1000, 4096, 2)]
     args = args_for(qmm, nodes)
     pad16 = lambda n: (n + 15) // 16 * 16
     ll = sum(pad16(m) for m, _, _ in nodes) * 8
-    llq = lambda kmin: sum(pad16(k // 32 * 10) for _, k, _ in nodes if k >= kmin) * 8
-    monkeypatch.delenv("B200_PLAN_LLQ", raising=False)
-    assert lib.b200_plan_arena_bytes(args, len(nodes), None) == ll + llq(8192)
-    monkeypatch.setenv("B200_PLAN_LLQ", "0")
-    assert lib.b200_plan_arena_bytes(args, len(nodes), None) == ll
-    monkeypatch.setenv("B200_PLAN_LLQ", "4096")
-    assert lib.b200_plan_arena_bytes(args, len(nodes), None) == ll + llq(4096)
-    # row-split plans: off unless asked for
+    pub = sum(pad16((k + k // 32 * 8) // 8) for _, k, _ in nodes) * 8
+    assert lib.b200_plan_arena_bytes(args, len(nodes), None) == ll + pub
     split = qmm.PlanSplit()
     split.world, split.rank = 2, 0
     row0 = (C.c_int64 * len(nodes))(*[0] * len(nodes))
     mtot = (C.c_int64 * len(nodes))(*[2 * m for m, _, _ in nodes])
     split.row0, split.m_total = row0, mtot
     ll2 = sum(pad16(2 * m) for m, _, _ in nodes) * 8
-    monkeypatch.delenv("B200_PLAN_LLQ", raising=False)
-    assert lib.b200_plan_arena_bytes(args, len(nodes), C.byref(split)) == ll2
-    monkeypatch.setenv("B200_PLAN_LLQ", "8192")
-    assert lib.b200_plan_arena_bytes(args, len(nodes), C.byref(split)) == ll2 + llq(8192)
+    assert lib.b200_plan_arena_bytes(args, len(nodes), C.byref(split)) == ll2 + pub
 
 
-def published(qmm, args, sm_count=148, split=None):
+def published(qmm, args, sm_count=148, split=None, min_k=0, dist=0):
     lib = qmm.load_library()
     out = (C.c_int32 * len(args))()
-    rc = lib.b200_plan_published(args, len(args), C.byref(split) if split is not None else None, sm_count, out)
+    rc = lib.b200_plan_published(args, len(args), C.byref(split) if split is not None else None, sm_count, min_k, dist, out)
     return rc, list(out)
 
 
-def test_which_src1_vectors_are_quantized_once_per_gpu(qmm, monkeypatch):
-    """b200_plan_published: the host-side choice behind the publisher warps.  GPT-J block:
+def test_which_src1_vectors_are_quantized_once_per_gpu(qmm):
+    """b200_plan_published: the host-side choice behind the publisher / fetcher warps.  GPT-J block:
     fc_in, v, q, k <- x; o <- v; fc_out <- fc_in; the next block's fc_in, v <- fc_out."""
     nodes = [(16384, 4096, -1), (4096, 4096, -1), (4096, 4096, -1), (4096, 4096, -1), (4096, 4096, 1), (4096, 16384, 0),
              (16384, 4096, 5), (4096, 4096, 5)]
     args = args_for(qmm, nodes)
-    for var in ("B200_PLAN_LLQ", "B200_PLAN_LLQ_DIST"):
-        monkeypatch.delenv(var, raising=False)
-    # default: k >= 8192, produced two or more ops back -> fc_out only
-    assert published(qmm, args) == (qmm.OK, [0, 0, 0, 0, 0, 1, 0, 0])
-    monkeypatch.setenv("B200_PLAN_LLQ", "4096")            # o <- v joins; fc_in <- fc_out is a true dependency (distance 1)
+    # default (min_k 4096, dist 2): o <- v and fc_out <- fc_in; fc_in <- fc_out is a true dependency (distance 1)
     assert published(qmm, args) == (qmm.OK, [0, 0, 0, 0, 1, 1, 0, 0])
-    monkeypatch.setenv("B200_PLAN_LLQ_DIST", "1")          # ... unless asked for; v <- fc_out shares fc_in's input: never
-    assert published(qmm, args) == (qmm.OK, [0, 0, 0, 0, 1, 1, 1, 0])
-    monkeypatch.setenv("B200_PLAN_LLQ", "0")
-    assert published(qmm, args) == (qmm.OK, [0] * 8)
+    assert published(qmm, args, min_k=8192) == (qmm.OK, [0, 0, 0, 0, 0, 1, 0, 0])
+    # ... unless asked for; v <- fc_out shares fc_in's input: never
+    assert published(qmm, args, min_k=4096, dist=1) == (qmm.OK, [0, 0, 0, 0, 1, 1, 1, 0])
     # a device with few SMs: 512 blocks over 8 CTAs are more than one warp's run of 16 blocks
-    monkeypatch.setenv("B200_PLAN_LLQ", "8192")
-    assert published(qmm, args, sm_count=8) == (qmm.OK, [0] * 8)
-    assert published(qmm, args, sm_count=64)[1][5] == 1
-    # row-split plans: off by default
-    monkeypatch.delenv("B200_PLAN_LLQ", raising=False)
+    assert published(qmm, args, sm_count=8, min_k=8192) == (qmm.OK, [0] * 8)
+    assert published(qmm, args, sm_count=64, min_k=8192)[1][5] == 1
+    # row-split plans: the same choice (every rank quantizes for its own arena)
     split = qmm.PlanSplit()
     split.world, split.rank = 2, 1
-    # rank 1 of 2 owns the second half of the rows of every matrix
     nodes2 = [(m // 2, k, src) for m, k, src in nodes]
     row0 = (C.c_int64 * len(nodes))(*[m // 2 for m, _, _ in nodes])
     mtot = (C.c_int64 * len(nodes))(*[m for m, _, _ in nodes])
     split.row0, split.m_total = row0, mtot
     args2 = args_for(qmm, nodes2)
-    assert published(qmm, args2, split=split) == (qmm.OK, [0] * 8)
+    assert published(qmm, args2, split=split) == (qmm.OK, [0, 0, 0, 0, 1, 1, 0, 0])
     # bad arguments
     assert published(qmm, args, sm_count=0)[0] == qmm.ERR_INVALID

@@ -122,7 +122,7 @@ def _plan_worker(rank, world, port, nodes, ret):
     so = (C.c_int32 * len(nodes))()
     rc = lib.b200_plan_analyze(args, len(nodes), C.byref(ps), so)
     arena = lib.b200_plan_arena_bytes(args, len(nodes), C.byref(ps))
-    ok = rc == qmm.OK and list(so) == [src for _, _, src in nodes] and arena == sum((m + 15) // 16 * 16 for m, _, _ in nodes) * 8
+    ok = rc == qmm.OK and list(so) == [src for _, _, src in nodes] and arena == (sum((m + 15) // 16 * 16 for m, _, _ in nodes) + sum(((k + k // 32 * 8) // 8 + 15) // 16 * 16 for _, k, _ in nodes)) * 8
     everyone = [None] * world
     dist.all_gather_object(everyone, (list(so), arena, [(s.r0, s.r1) for s in splits]))
     ok = ok and all(e[0] == everyone[0][0] and e[1] == everyone[0][1] for e in everyone)
