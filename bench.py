@@ -52,19 +52,13 @@ N_EMBD, N_LAYER, N_VOCAB, N_FF = 4096, 28, 50400, 16384
 # per block, in graph order, with the dependency structure of examples/gpt-j/main.cpp:462-551: q, k, v and fc_in all read the
 # block input (":534 this is independent of the self-attention result"), o reads the attention output (stand-in: v),
 # fc_out reads fc_in; the next block reads fc_out (stand-in for the residual sum, which is glue outside this path)
-# Node order inside a block is a topological order of that graph chosen so that a vector is needed as late as possible after
-# it is produced (fc_in first, v second: o and fc_out then find their inputs long finished; only fc_out -> next block is a
-# back-to-back dependency).  Every arm (ours, launch-per-group, the CPU reference) walks the same order.
-LAYER_MATS = [("fc_in", N_FF, N_EMBD), ("v", N_EMBD, N_EMBD), ("q", N_EMBD, N_EMBD), ("k", N_EMBD, N_EMBD),
+# Node order inside a block is a topological order of that graph chosen so that a vector is needed as late as possible after it is
+# produced (v first, fc_in second: o then finds v three ops back and fc_out finds fc_in three ops back, which is what lets the
+# decode plan quantize both once per GPU and prefetch them; only fc_out -> next block is a back-to-back dependency).  Every arm
+# (ours, launch-per-group, the CPU reference) walks the same order.
+LAYER_MATS = [("v", N_EMBD, N_EMBD), ("fc_in", N_FF, N_EMBD), ("q", N_EMBD, N_EMBD), ("k", N_EMBD, N_EMBD),
               ("o", N_EMBD, N_EMBD), ("fc_out", N_EMBD, N_FF)]          # (name, m, k)
-WORKLOAD = "gptj6b_q4_0_decode_mul_mat_graph(28x[fc_in,v,q,k<-x; o<-v; fc_out<-fc_in]+lm_head 50400x4096, n=1)"
-if os.environ.get("B200_BENCH_ORDER") == "qkv_first":      # A/B runs only: the graph in the order of examples/gpt-j/main.cpp
-    LAYER_MATS = [LAYER_MATS[2], LAYER_MATS[3], LAYER_MATS[1], LAYER_MATS[0], LAYER_MATS[4], LAYER_MATS[5]]
-    WORKLOAD = "gptj6b_q4_0_decode_mul_mat_graph(28x[q,k,v,fc_in<-x; o<-v; fc_out<-fc_in]+lm_head 50400x4096, n=1)"
-elif os.environ.get("B200_BENCH_ORDER") == "v_first":      # A/B runs only: v before fc_in (o <- v then lies 22 ring slots back)
-    LAYER_MATS = [LAYER_MATS[1], LAYER_MATS[0], LAYER_MATS[2], LAYER_MATS[3], LAYER_MATS[4], LAYER_MATS[5]]
-    WORKLOAD = "gptj6b_q4_0_decode_mul_mat_graph(28x[v,fc_in,q,k<-x; o<-v; fc_out<-fc_in]+lm_head 50400x4096, n=1)"
-
+WORKLOAD = "gptj6b_q4_0_decode_mul_mat_graph(28x[v,fc_in,q,k<-x; o<-v; fc_out<-fc_in]+lm_head 50400x4096, n=1)"
 
 def gptj_dag():
     """[(name, m, k, src)]: src = index of the node whose output is this node's src1, -1 = the token's input vector"""

@@ -1,0 +1,583 @@
+// b200_gemm_f16.cu -- the prefill path (n >= 32): dst[n][m] = W[m,k] x X[n,k]^T as ONE dense contraction on the 5th-generation
+// tensor cores, fp16 operands, fp32 accumulation in TMEM.
+//
+// Stands in for the COMPUTE phase of ggml_compute_forward_mul_mat (src/ggml.c:12056-12096) for prefill-sized batches, the way the
+// reference's own CUDA backend does it for large batches (ggml_cuda_op_mul_mat_cublas, src/ggml-cuda.cu:1208-1306:
+// to_fp16_cuda(src0), to_fp16_cuda(src1), fp16 GEMM):
+//   W'[m][k] = fp16_rn(quant * d_w)      -- dequantize_row_q4_0 / _q8_0 (src/ggml-quants.c:980-998, :1074-1088), rounded once to fp16
+//   X'[n][k] = fp16_rn(q * d_x)          -- the Q8_0-quantized activations (quantize_row_q8_0, src/ggml-quants.c:535-618): the
+//                                           same values the exact path multiplies, rounded once to fp16
+//   dst      = W' X'^T                   -- tcgen05.mma kind::f16, fp32 accumulators
+// Relative error 2^-12 per operand element: NMSE ~1e-7 against the 5e-4 bound of test-backend-ops (measured in
+// tests/test_gpu_gemm_f16.py against the oracle AND the exact kernel).  Bit-exact per-block int32 dots remain available through
+// b200_block_dots / the "gemm_exact" option (b200_gemm_tc.cu), which is tensor-pipe-starved by design: every 32-wide block's
+// partial must be scaled separately on CUDA cores (m*n*k/32 accumulator updates, profiles/r01_gemm_experiments.md).
+//
+// Why this shape (numbers: tools/mma_peak.cu on this pool's B200: 2230 TFLOP/s issue-only for kind::f16, 128 cycles per
+// M128/N256/K16 instruction; the round-1 fp16 kernels ran at 100 us on C2 = 21 % of that):
+//   * the round-1 kernels were L2-bandwidth-bound: a 128 x 256 tile re-reads X' for every 128 rows of W (360 MB for C2) and
+//     materialised W' (2 B per weight) in HBM.  Here the weights are dequantized INSIDE the kernel from the raw repacked blocks
+//     (0.56 B per weight from L2) and a CTA PAIR works on one 256 x 256 tile (tcgen05 cta_group::2: each CTA stages only its half
+//     of X', the tensor cores of the pair share it), so X' traffic halves and the per-SM shared-memory traffic fits;
+//   * persistent: one CTA pair per TPC walks a static list of work units; two 256-column accumulators in TMEM (all 512 columns)
+//     so the epilogue of one unit overlaps the MMAs of the next;
+//   * wave quantization (C2: 86 tiles on 74 pairs): the tiles of the last, partial round are split along k across the idle
+//     pairs; the partial accumulators meet in an L2-resident workspace and are summed in a FIXED order (part 0, 1, 2, ...), each
+//     pair reducing its own column slice -- deterministic, no atomics.
+//
+// CTA = 16 warps: warp 0 TMA producer (X' tile, raw weight chunks), warp 1 MMA issuer (leader CTA only), warp 2 TMEM
+// allocator, warps 4-7 epilogue (one per TMEM lane quadrant), warps 8-15 dequantization (thread = weight row x one block of 32).
+#include "b200_tc_common.cuh"
+
+using namespace b200tc;
+
+namespace {
+
+constexpr int TM = 128;                 // weight rows per CTA (tile M = 256 per pair)
+constexpr int TN = 256;                 // activation rows (dst columns) per tile; each CTA stages 128 of them
+constexpr int KSTEP = 64;               // k per pipeline stage = 128 bytes of fp16 = 2 quant blocks
+constexpr int kStagesF = 5;
+constexpr int kATile = TM * 128;        // 16 KB
+constexpr int kBTile = (TN / 2) * 128;  // 16 KB
+constexpr int kRawMax = 4 * TM * 16;    // 8 KB (Q8_0: 4 chunks of 16 B per row and k-step; Q4_0 uses half)
+constexpr int kStageF = kATile + kBTile + kRawMax;     // 40 KB, a multiple of 1024
+constexpr int kThreadsF = 16 * 32;
+constexpr int kDeqWarps = 8;
+constexpr int kEpiWarpsF = 4;
+constexpr int kBarsF = 5 * kStagesF + 4;               // raw_full, b_full, a_ready, empty (x stages), tmem_full[2], tmem_empty[2]
+constexpr int kSmemF = kStagesF * kStageF + 1024 + kBarsF * 8 + 64;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;            // shared::cluster address of the same location in the pair's leader CTA
+
+// instruction descriptor: dense, D = F32 (1 << 4), A = B = F16 (0), both K-major, N = 256, M = 256 (the pair)
+constexpr uint32_t kIdescF16x2 = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on a barrier that may live in the peer CTA (shared::cluster address).  Default (CTA-scope) semantics on purpose: what
+// crosses the pair is never generic-proxy data -- the W' tile is read by this SM's own tensor core (ordered by
+// fence.proxy.async), the accumulator by tcgen05.fence -- and a cluster-scope release / acquire costs a MEMBAR.ALL.GPU plus an
+// L1 invalidation (CCTL.IVALL) per k-step per warp: measured 4x the MMA time.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar_addr, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar_addr), "r"(parity) : "memory");
+}
+// X' tile of one CTA of the pair; the bytes are counted on the LEADER's barrier (the MMA needs both halves)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once every MMA issued so far has completed
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar_addr) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_addr), "h"((unsigned short)3)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 lds128f(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128f(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Work units of a launch.  Tile t = (tm, tn) with tn fastest (consecutive tiles share their weight rows in L2).  Pair p runs the
+// full tiles p, p + P, ... of the complete rounds, then -- when the last round is partial -- one k-slice of one of its tiles.
+struct Sched {
+    int tiles_n, tiles, pairs;
+    int full_rounds;      // rounds in which every pair has a whole tile
+    int rem, split;       // tiles of the partial round, k-slices per such tile (rem * split <= pairs)
+    int ksteps;           // k-steps of a whole tile
+};
+
+struct Unit {
+    int tm, tn, ks0, ks1;     // tile, k-step range
+    int part, nparts, rtile;  // k-slice index / count (1 = whole tile, stored directly) and index among the split tiles
+};
+
+__device__ __forceinline__ bool get_unit(const Sched &sc, int pair, int i, Unit &u) {
+    int tile;
+    if (i < sc.full_rounds) {
+        tile = i * sc.pairs + pair;
+        if (tile >= sc.tiles) return false;
+        u.ks0 = 0; u.ks1 = sc.ksteps; u.part = 0; u.nparts = 1; u.rtile = 0;
+    } else if (i == sc.full_rounds && sc.rem > 0 && pair < sc.rem * sc.split) {
+        u.rtile = pair / sc.split;
+        u.part = pair - u.rtile * sc.split;
+        u.nparts = sc.split;
+        tile = sc.full_rounds * sc.pairs + u.rtile;
+        u.ks0 = (int)((long long)sc.ksteps * u.part / sc.split);
+        u.ks1 = (int)((long long)sc.ksteps * (u.part + 1) / sc.split);
+    } else {
+        return false;
+    }
+    u.tm = tile / sc.tiles_n;
+    u.tn = tile - u.tm * sc.tiles_n;
+    return true;
+}
+
+struct GemmF16Args {
+    const __half *dw;        // weight scales [m][nb]
+    float *dst;              // [n][m]
+    float *partial;          // split-k workspace: [rem][split][TN][2 * TM] fp32
+    uint32_t *counters;      // [rem] arrivals of finished k-slices (zeroed before the launch)
+    uint32_t *abort_flag;    // the context's abort word (device memory)
+    uint32_t *abort_host;
+    int m, n, k;
+    Sched sc;
+};
+
+// two small unsigned integers (< 1024) at bits 0.. and 16.. of `bits`, already OR-ed into the mantissa of 2^e ->
+// half2((u0 - bias) * d, (u1 - bias) * d): the subtraction is exact, the product is rounded once
+__device__ __forceinline__ uint32_t cvt2(uint32_t hbits, __half2 bias, __half2 d2) {
+    __half2 h = *reinterpret_cast<const __half2 *>(&hbits);
+    h = __hmul2(__hsub2(h, bias), d2);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// k-order inside the operand tiles: within every aligned group of four k the order is (0, 2, 1, 3) -- what the masks below
+// produce without byte permutes; quantize_to_f16_kernel writes X' in the same order, and a contraction does not care.
+template <int TYPE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
+gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_b, const GemmF16Args g) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStagesF * kStageF);
+    uint64_t *raw_full = bars;                        // [stages] local: this CTA's raw weight chunks have landed
+    uint64_t *b_full = bars + kStagesF;               // [stages] leader: both halves of the X' tile have landed
+    uint64_t *a_ready = bars + 2 * kStagesF;          // [stages] leader: both CTAs' W' tiles are written (16 warp arrivals)
+    uint64_t *empty = bars + 3 * kStagesF;            // [stages] local: the MMAs that read this stage have completed
+    uint64_t *tmem_full = bars + 4 * kStagesF;        // [2] local: the unit's accumulator is complete
+    uint64_t *tmem_empty = tmem_full + 2;             // [2] leader: both CTAs' epilogues have drained the accumulator (8 arrivals)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    constexpr int QSB = TYPE == B200_TYPE_Q4_0 ? 16 : 32;
+    constexpr int CHUNKS = 2 * QSB / 16;              // 16-byte chunks of the qs plane per row and k-step (2 / 4)
+    constexpr uint32_t kRawBytes = CHUNKS * TM * 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const int pair = blockIdx.x >> 1;
+    const int nb = g.k >> 5;
+    const Sched sc = g.sc;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_raw) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStagesF; s++) {
+            mbar_init(&raw_full[s], 1);
+            mbar_init(&b_full[s], 1);
+            mbar_init(&a_ready[s], 2 * kDeqWarps);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 2 * kEpiWarpsF);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem_a = smem_u32(smem);
+
+    if (warp == 0) {
+        // ===== TMA producer (one thread per CTA): this CTA's 128 rows of X' and its raw weight chunks, stage by stage =====
+        if (lane == 0) {
+            int it = 0;
+            Unit u;
+            for (int i = 0; get_unit(sc, pair, i, u); i++) {
+                const int m0 = u.tm * 2 * TM + (int)rank * TM, n0 = u.tn * TN + (int)rank * (TN / 2);
+                for (int ks = u.ks0; ks < u.ks1; ks++, it++) {
+                    const int s = it % kStagesF;
+                    const uint32_t ph = (uint32_t)(it / kStagesF) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    const uint32_t st = smem_a + (uint32_t)(s * kStageF);
+                    mbar_expect_tx(&raw_full[s], kRawBytes);
+#pragma unroll
+                    for (int c = 0; c < CHUNKS; c++)      // chunk-major: [chunk][row][16 B] -> conflict-free 128-bit reads, thread = row
+                        tma_load_2d(smem + s * kStageF + kATile + kBTile + c * TM * 16, &map_raw, ks * 2 * QSB + c * 16, m0, &raw_full[s]);
+                    if (rank == 0) mbar_expect_tx(&b_full[s], 2 * kBTile);
+                    tma_load_2d_pair(st + kATile, &map_b, ks * 128, n0, smem_u32(&b_full[s]) & kPeerMask);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the LEADER CTA issues for the pair =====
+        if (lane == 0 && rank == 0) {
+            int it = 0, ui = 0;
+            Unit u;
+            for (int i = 0; get_unit(sc, pair, i, u); i++, ui++) {
+                const int acc = ui & 1;
+                const uint32_t aph = (uint32_t)(ui >> 1) & 1u;
+                mbar_wait_cluster(smem_u32(&tmem_empty[acc]), aph ^ 1u);     // both epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t td = tmem_base + (uint32_t)(acc * TN);
+                for (int ks = u.ks0; ks < u.ks1; ks++, it++) {
+                    const int s = it % kStagesF;
+                    const uint32_t ph = (uint32_t)(it / kStagesF) & 1u;
+                    mbar_wait_cluster(smem_u32(&b_full[s]), ph);
+                    mbar_wait_cluster(smem_u32(&a_ready[s]), ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_a + (uint32_t)(s * kStageF);
+                    const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sa + kATile);
+#pragma unroll
+                    for (int j = 0; j < 4; j++)      // K = 16 fp16 = 32 bytes per MMA: +2 in the (>>4) start-address field, inside the swizzle atom
+                        tc_mma_f16_pair(td, da + (uint64_t)(j * 2), db + (uint64_t)(j * 2), kIdescF16x2, (ks > u.ks0 || j > 0) ? 1u : 0u);
+                    tc_commit_pair(smem_u32(&empty[s]));          // both CTAs: stage s may be refilled
+                }
+                tc_commit_pair(smem_u32(&tmem_full[acc]));        // both CTAs: the accumulator is complete
+            }
+        }
+    } else if (warp >= 8) {
+        // ===== dequantization: thread = (weight row r of this CTA's 128, block blk of the k-step's two) =====
+        const int t = (int)threadIdx.x - 256;
+        const int r = t & (TM - 1), blk = t >> 7;
+        const __half2 bias_lo = TYPE == B200_TYPE_Q4_0 ? __floats2half2_rn(1032.f, 1032.f) : __floats2half2_rn(1152.f, 1152.f);
+        const __half2 bias_hi = __floats2half2_rn(72.f, 72.f);
+        const uint32_t leader_ready = smem_u32(a_ready) & kPeerMask;
+        const uint32_t sw = (uint32_t)(r & 7);
+        int it = 0;
+        Unit u;
+        for (int i = 0; get_unit(sc, pair, i, u); i++) {
+            const int row = min(u.tm * 2 * TM + (int)rank * TM + r, g.m - 1);      // (rows past m: TMA delivered zeros; any finite scale will do)
+            const unsigned short *dwp = reinterpret_cast<const unsigned short *>(g.dw) + (int64_t)row * nb;
+            // the block's scale two k-steps ahead of its use (an L2 miss costs more than one k-step)
+            auto ldd = [&](int ks) -> unsigned short {
+                const int b = 2 * ks + blk;
+                return (ks < u.ks1 && b < nb) ? __ldg(dwp + b) : (unsigned short)0;       // past the end of k: zero scale -> zero weights
+            };
+            unsigned short d0 = ldd(u.ks0), d1 = ldd(u.ks0 + 1);
+            for (int ks = u.ks0; ks < u.ks1; ks++, it++) {
+                const int s = it % kStagesF;
+                const uint32_t ph = (uint32_t)(it / kStagesF) & 1u;
+                const unsigned short dcur = d0;
+                d0 = d1;
+                d1 = ldd(ks + 2);
+                const __half dh = __ushort_as_half(dcur);
+                const __half2 d2 = __halves2half2(dh, dh);
+                mbar_wait(&raw_full[s], ph);
+                const uint32_t st = smem_a + (uint32_t)(s * kStageF);
+                const uint32_t raw = st + kATile + kBTile + (uint32_t)(r * 16);
+                const uint32_t arow = st + (uint32_t)(r * 128);
+                if (TYPE == B200_TYPE_Q4_0) {
+                    // chunk `blk` holds the block's 16 bytes: low nibbles = elements 0..15, high nibbles = elements 16..31
+                    const uint4 q = lds128f(raw + (uint32_t)(blk * TM * 16));
+                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                    uint32_t lo[8], hi[8];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t x = w[j], y = w[j] >> 8;
+                        lo[2 * j + 0] = cvt2((x & 0x000F000Fu) | 0x64006400u, bias_lo, d2);     // bytes 0, 2 of the word: 1024 + nib
+                        lo[2 * j + 1] = cvt2((y & 0x000F000Fu) | 0x64006400u, bias_lo, d2);     // bytes 1, 3
+                        hi[2 * j + 0] = cvt2((x & 0x00F000F0u) | 0x54005400u, bias_hi, d2);     // 64 + nib (the nibble sits 4 bits up: ulp 1/16)
+                        hi[2 * j + 1] = cvt2((y & 0x00F000F0u) | 0x54005400u, bias_hi, d2);
+                    }
+                    // 16-byte chunk c of the row goes where TMA with SWIZZLE_128B would put it: c ^ (row & 7)
+                    sts128f(arow + (((uint32_t)(blk * 4 + 0) ^ sw) << 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+                    sts128f(arow + (((uint32_t)(blk * 4 + 1) ^ sw) << 4), make_uint4(lo[4], lo[5], lo[6], lo[7]));
+                    sts128f(arow + (((uint32_t)(blk * 4 + 2) ^ sw) << 4), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+                    sts128f(arow + (((uint32_t)(blk * 4 + 3) ^ sw) << 4), make_uint4(hi[4], hi[5], hi[6], hi[7]));
+                } else {
+#pragma unroll
+                    for (int h16 = 0; h16 < 2; h16++) {
+                        const uint4 q = lds128f(raw + (uint32_t)((blk * 2 + h16) * TM * 16));
+                        const uint32_t w[4] = {q.x ^ 0x80808080u, q.y ^ 0x80808080u, q.z ^ 0x80808080u, q.w ^ 0x80808080u};   // int8 + 128
+                        uint32_t o[8];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            o[2 * j + 0] = cvt2((w[j] & 0x00FF00FFu) | 0x64006400u, bias_lo, d2);
+                            o[2 * j + 1] = cvt2(((w[j] >> 8) & 0x00FF00FFu) | 0x64006400u, bias_lo, d2);
+                        }
+                        sts128f(arow + (((uint32_t)(blk * 4 + h16 * 2 + 0) ^ sw) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+                        sts128f(arow + (((uint32_t)(blk * 4 + h16 * 2 + 1) ^ sw) << 4), make_uint4(o[4], o[5], o[6], o[7]));
+                    }
+                }
+                // generic-proxy stores -> visible to the tensor core (async proxy), then one arrival per warp on the leader's barrier
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_ready + (uint32_t)(s * 8));
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: warp q of 4 owns TMEM lanes 32q.. = weight rows; whole tiles go straight to dst, k-slices through
+        // the split-k workspace =====
+        const int quad = warp & 3;
+        const uint32_t leader_tempty = smem_u32(tmem_empty) & kPeerMask;
+        int ui = 0;
+        Unit u;
+        for (int i = 0; get_unit(sc, pair, i, u); i++, ui++) {
+            const int acc = ui & 1;
+            const uint32_t aph = (uint32_t)(ui >> 1) & 1u;
+            const int rloc = (int)rank * TM + quad * 32 + lane;      // row inside the 256-row tile
+            const int row = u.tm * 2 * TM + rloc;
+            const int n0 = u.tn * TN;
+            mbar_wait(&tmem_full[acc], aph);
+            tc_fence_after();
+            const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TN);
+            float *pbase = g.partial + ((size_t)(u.rtile * sc.split + u.part) * TN) * (2 * TM) + rloc;
+#pragma unroll 1
+            for (int c32 = 0; c32 < TN / 32; c32++) {
+                uint32_t v[32];
+                tc_ld32(tcol + (uint32_t)(c32 * 32), v);
+                tc_wait_ld();
+                if (c32 == TN / 32 - 1) {
+                    // the accumulator is in registers: hand it back to the MMA thread before the stores
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(leader_tempty + (uint32_t)(acc * 8));
+                }
+                if (u.nparts == 1) {
+                    if (row < g.m) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const int c = n0 + c32 * 32 + j;
+                            if (c < g.n) g.dst[(int64_t)c * g.m + row] = __uint_as_float(v[j]);   // 32 lanes -> 128 contiguous bytes
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) pbase[(size_t)(c32 * 32 + j) * (2 * TM)] = __uint_as_float(v[j]);
+                }
+            }
+            if (u.nparts > 1) {
+                // this warp's share of the k-slice is in the workspace: publish, then reduce this pair's column slice of the tile
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(g.counters + u.rtile, 1u);
+                const uint32_t target = (uint32_t)(u.nparts * 2 * kEpiWarpsF);
+                if (lane == 0) {
+                    unsigned long long t0 = 0;
+                    unsigned spins = 0;
+                    for (;;) {
+                        uint32_t seen;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(g.counters + u.rtile) : "memory");
+                        if (seen >= target) break;
+                        __nanosleep(100);
+                        if ((++spins & 255u) == 0u) {      // bounded: a pair that never delivers must not hang the GPU
+                            if (*reinterpret_cast<volatile uint32_t *>(g.abort_flag) != 0u) break;
+                            const unsigned long long now = gtimer();
+                            if (t0 == 0ull) t0 = now;
+                            else if (now - t0 > 5000000000ull) {
+                                if (atomicCAS(g.abort_flag, 0u, 0x80000004u) == 0u) *reinterpret_cast<volatile uint32_t *>(g.abort_host) = 0x80000004u;
+                                break;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                const int c_lo = TN * u.part / u.nparts, c_hi = min(TN * (u.part + 1) / u.nparts, g.n - n0);
+                const float *tp = g.partial + ((size_t)(u.rtile * sc.split) * TN) * (2 * TM) + rloc;
+                if (row < g.m) {
+                    // four columns at a time with every part's load in flight together (an L2 round trip per dependent load would
+                    // make this phase latency-bound); the sum itself runs in the fixed order part 0, 1, 2, ...
+                    for (int c = c_lo; c < c_hi; c += 4) {
+                        float acc4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                        for (int p0 = 0; p0 < u.nparts; p0 += 4) {
+                            float v[4][4];
+#pragma unroll
+                            for (int pp = 0; pp < 4; pp++)
+#pragma unroll
+                                for (int cc = 0; cc < 4; cc++)
+                                    v[pp][cc] = (p0 + pp < u.nparts && c + cc < c_hi) ? __ldcg(tp + ((size_t)(p0 + pp) * TN + (c + cc)) * (2 * TM)) : 0.0f;
+#pragma unroll
+                            for (int pp = 0; pp < 4; pp++)
+                                if (p0 + pp < u.nparts) {
+#pragma unroll
+                                    for (int cc = 0; cc < 4; cc++) acc4[cc] += v[pp][cc];
+                                }
+                        }
+#pragma unroll
+                        for (int cc = 0; cc < 4; cc++)
+                            if (c + cc < c_hi) g.dst[(int64_t)(n0 + c + cc) * g.m + row] = acc4[cc];
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+// F32 activations -> X'[n][k] fp16 = fp16_rn(q * d) of their Q8_0 quantization (quantize_row_q8_0, src/ggml-quants.c:535-618,
+// same explicitly rounded arithmetic as b200_quantize.cu), written in the k-order of the operand tiles: within every aligned
+// group of four the order is (0, 2, 1, 3).  8 lanes per block, one 128-bit load and one 64-bit store per lane.
+__global__ void __launch_bounds__(256) quantize_to_f16_kernel(const float *__restrict__ x, int64_t k, int64_t nrows, size_t row_stride, __half *__restrict__ out) {
+    const int64_t nb = k / 32;
+    const int64_t total = nrows * nb * 8;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)b200_align_up((size_t)total, 32); t += (int64_t)gridDim.x * blockDim.x) {
+        const bool live = t < total;
+        const int64_t blk = (live ? t : total - 1) >> 3;
+        const int sub = (int)(t & 7);
+        const int64_t row = blk / nb, b = blk - row * nb;
+        const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(x) + row * row_stride) + b * 32 + sub * 4;
+        const float4 v = *reinterpret_cast<const float4 *>(src);
+        float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+        const float id = amax != 0.0f ? __fdiv_rn(127.f, amax) : 0.0f;
+        const float d = __half2float(__float2half_rn(__fdiv_rn(amax, 127.f)));
+        const float q0 = (float)__float2int_rn(__fmul_rn(v.x, id)), q1 = (float)__float2int_rn(__fmul_rn(v.y, id));
+        const float q2 = (float)__float2int_rn(__fmul_rn(v.z, id)), q3 = (float)__float2int_rn(__fmul_rn(v.w, id));
+        if (!live) continue;
+        const __half2 h01 = __halves2half2(__float2half_rn(__fmul_rn(q0, d)), __float2half_rn(__fmul_rn(q2, d)));     // positions 0, 1 <- elements 0, 2
+        const __half2 h23 = __halves2half2(__float2half_rn(__fmul_rn(q1, d)), __float2half_rn(__fmul_rn(q3, d)));     // positions 2, 3 <- elements 1, 3
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t *>(&h01);
+        o.y = *reinterpret_cast<const uint32_t *>(&h23);
+        *reinterpret_cast<uint2 *>(out + row * k + b * 32 + sub * 4) = o;
+    }
+}
+
+// the qs plane as bytes: rows x row_bytes, box = 128 rows x 16 bytes, no swizzle; out-of-bounds -> zeros
+bool make_chunk_map(CUtensorMap *map, const void *base, int64_t rows, int64_t row_bytes) {
+    auto fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {16u, (cuuint32_t)TM};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// X' as bytes: n rows x (k * 2) bytes; box = 128 rows x 128 bytes, 128-byte swizzle, out-of-bounds -> zeros
+bool make_xp_map(CUtensorMap *map, const void *base, int64_t rows, int64_t row_bytes) {
+    auto fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {128u, (cuuint32_t)(TN / 2)};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+Sched make_sched(int64_t m, int64_t n, int64_t k, int pairs) {
+    Sched sc;
+    sc.tiles_n = (int)((n + TN - 1) / TN);
+    sc.tiles = (int)((m + 2 * TM - 1) / (2 * TM)) * sc.tiles_n;
+    sc.pairs = pairs;
+    sc.ksteps = (int)((k + KSTEP - 1) / KSTEP);
+    sc.full_rounds = sc.tiles / pairs;
+    sc.rem = sc.tiles % pairs;
+    sc.split = 1;
+    if (sc.rem > 0) {
+        int split = pairs / sc.rem;
+        const int max_split = sc.ksteps / 8 > 0 ? sc.ksteps / 8 : 1;      // at least 8 k-steps per slice
+        if (split > max_split) split = max_split;
+        if (split > 16) split = 16;
+        sc.split = split < 1 ? 1 : split;
+    }
+    if (sc.split == 1) {      // nothing to gain: the partial round runs as whole tiles
+        sc.full_rounds = (sc.tiles + pairs - 1) / pairs;
+        sc.rem = 0;
+    }
+    return sc;
+}
+
+}  // namespace
+
+// scratch of the fp16 path beyond the activations: X' [n][k] fp16, split-k partials, counters
+size_t b200_gemm_f16_scratch_bytes(int64_t k, int64_t m, int64_t n, int sm_count) {
+    const Sched sc = make_sched(m, n, k, sm_count / 2);
+    return b200_align_up((size_t)n * k * 2, 1024) + (size_t)sc.rem * sc.split * TN * 2 * TM * 4 + 1024;
+}
+
+int b200_launch_gemm_f16(b200_ctx *ctx, int type, const uint8_t *qs, const __half *d, int64_t k, int64_t m, const float *x, int64_t n,
+                         size_t x_row_stride, float *dst, void *scratch) {
+    B200_REQUIRE(ctx, k % 32 == 0 && k >= 32 && m >= 1 && n >= 1, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, scratch != NULL && dst != NULL, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, m < (1 << 30) && n < (1 << 30) && k < (1 << 30), B200_ERR_UNSUPPORTED);
+    B200_REQUIRE(ctx, ((uintptr_t)x & 15) == 0 && (x_row_stride & 15) == 0, B200_ERR_UNSUPPORTED);
+    const int pairs = ctx->sm_count / 2;
+    B200_REQUIRE(ctx, pairs >= 1, B200_ERR_UNSUPPORTED);
+    const int64_t nb = k / 32;
+    const int qsb = b200_qs_bytes(type);
+    const Sched sc = make_sched(m, n, k, pairs);
+    __half *xp = (__half *)scratch;
+    float *partial = (float *)((uint8_t *)scratch + b200_align_up((size_t)n * k * 2, 1024));
+    uint32_t *counters = (uint32_t *)((uint8_t *)partial + (size_t)sc.rem * sc.split * TN * 2 * TM * 4);
+    {
+        const int64_t total = n * nb * 8;
+        int64_t grid = (total + 255) / 256;
+        const int64_t cap = (int64_t)ctx->sm_count * 16;
+        if (grid > cap) grid = cap;
+        quantize_to_f16_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(x, k, n, x_row_stride, xp);
+        ctx->launches++;
+        B200_CUDA_TRY(ctx, cudaGetLastError());
+    }
+    if (sc.rem > 0) B200_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, (size_t)sc.rem * 4, ctx->stream));
+    CUtensorMap map_raw, map_b;
+    if (!make_chunk_map(&map_raw, qs, m, nb * qsb) || !make_xp_map(&map_b, xp, n, k * 2)) {
+        b200_set_error(ctx, "cuTensorMapEncodeTiled failed (fp16 prefill path, m=%lld n=%lld k=%lld)", (long long)m, (long long)n, (long long)k);
+        return B200_ERR_CUDA;
+    }
+    GemmF16Args g;
+    memset(&g, 0, sizeof(g));
+    g.dw = d;
+    g.dst = dst;
+    g.partial = partial;
+    g.counters = counters;
+    g.abort_flag = ctx->abort_dev;
+    g.abort_host = ctx->abort_host_dev;
+    g.m = (int)m;
+    g.n = (int)n;
+    g.k = (int)k;
+    g.sc = sc;
+    // one CTA pair per TPC, or fewer when the launch has fewer units than pairs (idle pairs would only spin up and exit)
+    int use_pairs = pairs;
+    const int units = sc.full_rounds > 0 ? (sc.tiles < pairs ? sc.tiles : pairs) : sc.rem * sc.split;
+    if (units < use_pairs) use_pairs = units;
+    if (type == B200_TYPE_Q4_0) {
+        B200_CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_f16_pair_kernel<B200_TYPE_Q4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemF));
+        gemm_f16_pair_kernel<B200_TYPE_Q4_0><<<2 * use_pairs, kThreadsF, kSmemF, ctx->stream>>>(map_raw, map_b, g);
+    } else {
+        B200_CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_f16_pair_kernel<B200_TYPE_Q8_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemF));
+        gemm_f16_pair_kernel<B200_TYPE_Q8_0><<<2 * use_pairs, kThreadsF, kSmemF, ctx->stream>>>(map_raw, map_b, g);
+    }
+    ctx->launches++;
+    B200_CUDA_TRY(ctx, cudaGetLastError());
+    return B200_OK;
+}

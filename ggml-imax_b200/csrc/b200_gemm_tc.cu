@@ -1,5 +1,8 @@
-// b200_gemm_tc.cu -- prefill path: dst[n][m] = W[m,k] (int8, per-32 fp16 scales) x Xq[n,k] (Q8_0 activations),
-// a dense contraction on the 5th-generation tensor cores (tcgen05.mma kind::i8, int32 accumulators in TMEM).
+// b200_gemm_tc.cu -- the EXACT prefill kernel: dst[n][m] = W[m,k] (int8, per-32 fp16 scales) x Xq[n,k] (Q8_0 activations),
+// tcgen05.mma kind::i8 with int32 accumulators in TMEM, one MMA per 32-wide quant block.  It is what b200_block_dots(path 1)
+// reads the bit-exact per-block partials from, what serves 9 <= n < 32, and what the "gemm_exact" option selects for any n;
+// the default for n >= 32 is the fp16 contraction in b200_gemm_f16.cu (the per-block fp32 scaling on CUDA cores bounds this
+// kernel at ~9 % of the int8 tensor peak, profiles/r01_gemm_experiments.md).
 //
 // Stands in for the COMPUTE phase of ggml_compute_forward_mul_mat (src/ggml.c:12056-12096) at n >= 9:
 //   dst[n][m] = sum_kb  d_w[m][kb] * d_x[n][kb] * ( sum_{j<32} w[m][32 kb + j] * q[n][32 kb + j] )
@@ -280,7 +283,9 @@ __global__ void __launch_bounds__(256) transpose_scales_kernel(const __half *__r
 }
 
 
-PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+}  // namespace
+
+PFN_cuTensorMapEncodeTiled_v12000 b200tc::get_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
         void *p = nullptr;
@@ -292,6 +297,8 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     }
     return fn;
 }
+
+namespace {
 
 // rows x k bytes of int8, row pitch k; box = 128 rows x 128 bytes, 128-byte swizzle, out-of-bounds -> zeros
 bool make_map(CUtensorMap *map, const void *base, int64_t rows, int64_t k) {
@@ -317,94 +324,6 @@ bool make_scale_map(CUtensorMap *map, const void *base, int64_t nb, int64_t ldn)
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// rows x row_bytes (fp16 operands addressed as bytes); box = box_rows x 128 bytes, 128-byte swizzle, out-of-bounds -> zeros
-bool make_map_bytes(CUtensorMap *map, const void *base, int64_t rows, int64_t row_bytes, int box_rows) {
-    auto fn = get_encode_fn();
-    if (!fn) return false;
-    cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-int gemm_f16_mode() {           // 0 off, 1 operands materialised, 2 weights dequantized in the kernel; read per call: tests switch it
-    const char *e = getenv("B200_GEMM_F16");
-    return e ? atoi(e) : 0;
-}
-bool gemm_f16_enabled() { return gemm_f16_mode() != 0; }
-
-// the qs plane as bytes: rows x (nb * qsb), box = 128 rows x 2 blocks, no swizzle; out-of-bounds -> zeros
-bool make_raw_map(CUtensorMap *map, const void *base, int64_t rows, int64_t row_bytes, int box_bytes) {
-    auto fn = get_encode_fn();
-    if (!fn) return false;
-    cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)box_bytes, (cuuint32_t)FBM};
-    cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-template <int TYPE>
-int launch_gemm_f16_fused(b200_ctx *ctx, const b200_gemm_params &p) {
-    using G = FusedGeom<TYPE>;
-    const int64_t nb = p.k / 32;
-    __half *x16 = (__half *)p.scratch;
-    const int64_t xblocks = p.n * nb;
-    dequant_f16_kernel<B200_TYPE_Q8_0><<<(unsigned)((xblocks + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t *)p.aq, p.ad, (uint4 *)x16, xblocks);
-    ctx->launches++;
-    B200_CUDA_TRY(ctx, cudaGetLastError());
-    CUtensorMap map_raw, map_b;
-    if (!make_raw_map(&map_raw, p.qs, p.m, nb * G::kQsb, G::kRawRow) || !make_map_bytes(&map_b, x16, p.n, p.k * 2, FBN)) {
-        b200_set_error(ctx, "cuTensorMapEncodeTiled failed (fused fp16 path, m=%lld n=%lld k=%lld)", (long long)p.m, (long long)p.n, (long long)p.k);
-        return B200_ERR_CUDA;
-    }
-    GemmF16Args g;
-    g.dst = p.dst;
-    g.m = (int)p.m;
-    g.n = (int)p.n;
-    g.k = (int)p.k;
-    dim3 grid((unsigned)((p.m + FBM - 1) / FBM), (unsigned)((p.n + FBN - 1) / FBN), 1);
-    B200_CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_f16_fused_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmem));
-    gemm_f16_fused_kernel<TYPE><<<grid, kFThreads, G::kSmem, ctx->stream>>>(map_raw, map_b, p.d, g);
-    ctx->launches++;
-    B200_CUDA_TRY(ctx, cudaGetLastError());
-    return B200_OK;
-}
-size_t gemm_f16_scratch_bytes(int64_t k, int64_t m, int64_t n) { return b200_align_up((size_t)m * k * 2, 1024) + b200_align_up((size_t)n * k * 2, 1024); }
-
-int launch_gemm_f16(b200_ctx *ctx, const b200_gemm_params &p) {
-    const int64_t nb = p.k / 32;
-    __half *w16 = (__half *)p.scratch;
-    __half *x16 = (__half *)((uint8_t *)p.scratch + b200_align_up((size_t)p.m * p.k * 2, 1024));
-    const int64_t wblocks = p.m * nb, xblocks = p.n * nb;
-    if (p.type == B200_TYPE_Q4_0)
-        dequant_f16_kernel<B200_TYPE_Q4_0><<<(unsigned)((wblocks + 255) / 256), 256, 0, ctx->stream>>>(p.qs, p.d, (uint4 *)w16, wblocks);
-    else
-        dequant_f16_kernel<B200_TYPE_Q8_0><<<(unsigned)((wblocks + 255) / 256), 256, 0, ctx->stream>>>(p.qs, p.d, (uint4 *)w16, wblocks);
-    dequant_f16_kernel<B200_TYPE_Q8_0><<<(unsigned)((xblocks + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t *)p.aq, p.ad, (uint4 *)x16, xblocks);
-    ctx->launches += 2;
-    B200_CUDA_TRY(ctx, cudaGetLastError());
-    CUtensorMap map_a, map_b;
-    if (!make_map_bytes(&map_a, w16, p.m, p.k * 2, FBM) || !make_map_bytes(&map_b, x16, p.n, p.k * 2, FBN)) {
-        b200_set_error(ctx, "cuTensorMapEncodeTiled failed (fp16 path, m=%lld n=%lld k=%lld)", (long long)p.m, (long long)p.n, (long long)p.k);
-        return B200_ERR_CUDA;
-    }
-    GemmF16Args g;
-    g.dst = p.dst;
-    g.m = (int)p.m;
-    g.n = (int)p.n;
-    g.k = (int)p.k;
-    dim3 grid((unsigned)((p.m + FBM - 1) / FBM), (unsigned)((p.n + FBN - 1) / FBN), 1);
-    B200_CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes));
-    gemm_f16_kernel<<<grid, kFThreads, kFSmemBytes, ctx->stream>>>(map_a, map_b, g);
-    ctx->launches++;
-    B200_CUDA_TRY(ctx, cudaGetLastError());
-    return B200_OK;
-}
-
 }  // namespace
 
 bool b200_gemm_available(void) { return get_encode_fn() != nullptr; }
@@ -414,7 +333,6 @@ size_t b200_gemm_scratch_bytes(int type, int64_t k, int64_t m, int64_t n) {
     const int64_t nb = k / 32, ldn = (n + BN - 1) / BN * BN;
     size_t b = b200_align_up((size_t)nb * ldn * 4, 256);
     if (type == B200_TYPE_Q4_0) b += b200_align_up((size_t)m * k, 256);
-    if (gemm_f16_enabled() && gemm_f16_scratch_bytes(k, m, n) > b) b = gemm_f16_scratch_bytes(k, m, n);
     return b;
 }
 
@@ -422,9 +340,6 @@ int b200_launch_gemm(b200_ctx *ctx, const b200_gemm_params &p) {
     B200_REQUIRE(ctx, p.k % 32 == 0 && p.k >= 32 && p.m >= 1 && p.n >= 1, B200_ERR_INVALID);
     B200_REQUIRE(ctx, p.scratch != NULL, B200_ERR_INVALID);
     B200_REQUIRE(ctx, p.m < (1 << 30) && p.n < (1 << 30) && p.k < (1 << 30), B200_ERR_UNSUPPORTED);
-    if (!p.dots && gemm_f16_mode() == 2 && p.k >= 64)                        // experimental (see gemm_f16_fused_kernel)
-        return p.type == B200_TYPE_Q4_0 ? launch_gemm_f16_fused<B200_TYPE_Q4_0>(ctx, p) : launch_gemm_f16_fused<B200_TYPE_Q8_0>(ctx, p);
-    if (!p.dots && gemm_f16_enabled()) return launch_gemm_f16(ctx, p);       // experimental (see gemm_f16_kernel)
     const int64_t nb = p.k / 32, ldn = (p.n + BN - 1) / BN * BN;
     float *dxT = (float *)p.scratch;
     const int8_t *a8 = (const int8_t *)p.qs;

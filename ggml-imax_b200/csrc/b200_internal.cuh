@@ -120,5 +120,9 @@ struct b200_gemm_params {
 int b200_launch_gemm(b200_ctx *ctx, const b200_gemm_params &p);
 bool b200_gemm_available(void);
 size_t b200_gemm_scratch_bytes(int type, int64_t k, int64_t m, int64_t n);
+// the fp16 prefill path (b200_gemm_f16.cu): quantize_row_q8_0 -> fp16 X' (one launch), then the persistent pair kernel
+size_t b200_gemm_f16_scratch_bytes(int64_t k, int64_t m, int64_t n, int sm_count);
+int b200_launch_gemm_f16(b200_ctx *ctx, int type, const uint8_t *qs, const __half *d, int64_t k, int64_t m, const float *x, int64_t n,
+                         size_t x_row_stride, float *dst, void *scratch);
 // activation scratch layout inside ctx->ws for one prefill mul_mat: [int8 plane n*k][fp16 scales n*k/32][gemm scratch]
 size_t b200_prefill_ws_bytes(int type, int64_t k, int64_t m, int64_t n);

@@ -44,11 +44,35 @@ static int run_gemv_chunks(b200_ctx *ctx, const b200_mul_mat_args *a, const uint
 }
 
 size_t b200_prefill_ws_bytes(int type, int64_t k, int64_t m, int64_t n) {
-    return b200_align_up((size_t)n * k, 256) + b200_align_up((size_t)n * (k / 32) * 2, 256) + b200_gemm_scratch_bytes(type, k, m, n);
+    const size_t exact = b200_align_up((size_t)n * k, 256) + b200_align_up((size_t)n * (k / 32) * 2, 256) + b200_gemm_scratch_bytes(type, k, m, n);
+    const size_t f16 = b200_gemm_f16_scratch_bytes(k, m, n, 160);      // (an upper bound on the pairs of any sm_100 part)
+    return exact > f16 ? exact : f16;
+}
+
+// n at which the fp16 tensor-core contraction takes over from the exact per-block kernel (its 256-column tiles are mostly
+// padding below that)
+static const int64_t kGemmF16MinN = 32;
+
+static int run_gemm_f16(b200_ctx *ctx, const b200_mul_mat_args *a, const uint8_t *qs, const __half *d) {
+    const int64_t k = a->ne00, m = a->ne01, n = a->ne11, nb = k / 32;
+    int rc = b200_ws_reserve(ctx, b200_gemm_f16_scratch_bytes(k, m, n, ctx->sm_count));
+    if (rc != B200_OK) return rc;
+    const int64_t r2 = a->ne12 / a->ne02, r3 = a->ne13 / a->ne03;
+    const int qsb = b200_qs_bytes(a->type);
+    for (int64_t i13 = 0; i13 < a->ne13; i13++)
+        for (int64_t i12 = 0; i12 < a->ne12; i12++) {
+            const float *x = reinterpret_cast<const float *>(reinterpret_cast<const char *>(a->src1_dev) + i13 * a->nb13 + i12 * a->nb12);
+            const int64_t wrow0 = ((i13 / r3) * a->ne02 + (i12 / r2)) * m;
+            rc = b200_launch_gemm_f16(ctx, a->type, qs + wrow0 * nb * qsb, d + wrow0 * nb, k, m, x, n, a->nb11,
+                                      a->dst_dev + (i13 * a->ne12 + i12) * n * m, ctx->ws);
+            if (rc != B200_OK) return rc;
+        }
+    return B200_OK;
 }
 
 static int run_gemm(b200_ctx *ctx, const b200_mul_mat_args *a, const uint8_t *qs, const __half *d) {
     const int64_t k = a->ne00, m = a->ne01, n = a->ne11, nb = k / 32;
+    if (!ctx->opt_gemm_exact && n >= kGemmF16MinN) return run_gemm_f16(ctx, a, qs, d);
     // scratch: int8 plane [n][k] + fp16 scales [n][nb] + GEMM scratch, reused per (i12,i13) slice
     const size_t q_bytes = b200_align_up((size_t)n * k, 256);
     const size_t d_bytes = b200_align_up((size_t)n * nb * 2, 256);

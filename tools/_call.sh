@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 400 python tools/ab_plan.py sweep > gpurun_out/r02_ab_plan3.log 2>&1; grep -E "us/token|bitwise|Error|error" gpurun_out/r02_ab_plan3.log | cut -c1-250
+timeout 300 python -m pytest tests/test_gpu_gemm_f16.py -x -q > gpurun_out/r02_gemm_tests.log 2>&1; tail -5 gpurun_out/r02_gemm_tests.log
+timeout 200 python tools/ab_gemm.py > gpurun_out/r02_ab_gemm.log 2>&1; tail -20 gpurun_out/r02_ab_gemm.log
