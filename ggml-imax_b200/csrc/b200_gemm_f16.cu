@@ -25,8 +25,8 @@
 //     pairs; the partial accumulators meet in an L2-resident workspace and are summed in a FIXED order (part 0, 1, 2, ...), each
 //     pair reducing its own column slice -- deterministic, no atomics.
 //
-// CTA = 16 warps: warp 0 TMA producer (X' tile, raw weight chunks), warp 1 MMA issuer (leader CTA only), warp 2 TMEM
-// allocator, warps 4-7 epilogue (one per TMEM lane quadrant), warps 8-15 dequantization (thread = weight row x one block of 32).
+// CTA = 16 warps: warp 0 TMA producer of the X' tile, warp 3 TMA producer of the raw weight rows (+ L2 prefetch), warp 1 MMA issuer
+// (leader CTA only), warp 2 TMEM allocator, warps 4-7 epilogue (one per TMEM lane quadrant), warps 8-15 dequantization (thread = weight row x one block of 32).
 #include "b200_tc_common.cuh"
 
 using namespace b200tc;
@@ -39,13 +39,21 @@ constexpr int KSTEP = 64;               // k per pipeline stage = 128 bytes of f
 constexpr int kStagesF = 5;
 constexpr int kATile = TM * 128;        // 16 KB
 constexpr int kBTile = (TN / 2) * 128;  // 16 KB
-constexpr int kRawMax = 4 * TM * 16;    // 8 KB (Q8_0: 4 chunks of 16 B per row and k-step; Q4_0 uses half)
-constexpr int kStageF = kATile + kBTile + kRawMax;     // 40 KB, a multiple of 1024
+constexpr int kStageF = kATile + kBTile;               // 32 KB, a multiple of 1024
 constexpr int kThreadsF = 16 * 32;
 constexpr int kDeqWarps = 8;
+constexpr int kDeqGroups = 2;             // groups of kDeqWarps / kDeqGroups warps that take alternate k-steps
 constexpr int kEpiWarpsF = 4;
-constexpr int kBarsF = 5 * kStagesF + 4;               // raw_full, b_full, a_ready, empty (x stages), tmem_full[2], tmem_empty[2]
-constexpr int kSmemF = kStagesF * kStageF + 1024 + kBarsF * 8 + 64;
+constexpr int kBarsF = 4 * kStagesF + 4;               // raw_full, b_full, a_ready, empty (x stages), tmem_full[2], tmem_empty[2]
+// raw weight tiles: per stage 128 rows x (32 | 64) bytes of the qs plane (both blocks of the k-step), TMA with the 32 / 64-byte
+// swizzle so that thread = row reads its 16-byte pieces without bank conflicts
+template <int TYPE> struct RawTile {
+    static constexpr int kRow = TYPE == B200_TYPE_Q4_0 ? 32 : 64;
+    static constexpr int kBytes = TM * kRow;                                 // 4 KB / 8 KB
+    static constexpr int kSmem = kStagesF * (kStageF + kBytes) + 1024 + kBarsF * 8 + 64;
+    static constexpr int kPfSteps = 256 / kRow;                              // k-steps per 256-byte L2 prefetch box row (8 / 4)
+};
+constexpr int kPfAhead = 24;             // k-steps the L2 prefetch cursor stays ahead of the copies (~6 us of MMAs)
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;            // shared::cluster address of the same location in the pair's leader CTA
 
 // instruction descriptor: dense, D = F32 (1 << 4), A = B = F16 (0), both K-major, N = 256, M = 256 (the pair)
@@ -82,6 +90,10 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
                  "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
                  : "memory");
+}
+// HBM -> L2 only: the box of a tensor map, no shared-memory destination, no barrier
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -154,6 +166,7 @@ struct GemmF16Args {
     uint32_t *abort_flag;    // the context's abort word (device memory)
     uint32_t *abort_host;
     int m, n, k;
+    int dw_pf;               // the scale plane can be prefetched through its tensor map (row pitch a multiple of 16 bytes)
     Sched sc;
 };
 
@@ -169,21 +182,22 @@ __device__ __forceinline__ uint32_t cvt2(uint32_t hbits, __half2 bias, __half2 d
 // produce without byte permutes; quantize_to_f16_kernel writes X' in the same order, and a contraction does not care.
 template <int TYPE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
-gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_b, const GemmF16Args g) {
+gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_raw_pf,
+                     const __grid_constant__ CUtensorMap map_dw_pf, const GemmF16Args g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStagesF * kStageF);
-    uint64_t *raw_full = bars;                        // [stages] local: this CTA's raw weight chunks have landed
+    using RT = RawTile<TYPE>;
+    unsigned char *rawtiles = smem + kStagesF * kStageF;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(rawtiles + kStagesF * RT::kBytes);
+    uint64_t *raw_full = bars;                        // [stages] local: this CTA's raw weight rows have landed
     uint64_t *b_full = bars + kStagesF;               // [stages] leader: both halves of the X' tile have landed
-    uint64_t *a_ready = bars + 2 * kStagesF;          // [stages] leader: both CTAs' W' tiles are written (16 warp arrivals)
+    uint64_t *a_ready = bars + 2 * kStagesF;          // [stages] leader: both CTAs' W' tiles are written (one group's warps of each CTA)
     uint64_t *empty = bars + 3 * kStagesF;            // [stages] local: the MMAs that read this stage have completed
     uint64_t *tmem_full = bars + 4 * kStagesF;        // [2] local: the unit's accumulator is complete
     uint64_t *tmem_empty = tmem_full + 2;             // [2] leader: both CTAs' epilogues have drained the accumulator (8 arrivals)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
 
     constexpr int QSB = TYPE == B200_TYPE_Q4_0 ? 16 : 32;
-    constexpr int CHUNKS = 2 * QSB / 16;              // 16-byte chunks of the qs plane per row and k-step (2 / 4)
-    constexpr uint32_t kRawBytes = CHUNKS * TM * 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
     const int pair = blockIdx.x >> 1;
@@ -191,14 +205,16 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
     const Sched sc = g.sc;
 
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_raw) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_raw) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_raw_pf) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dw_pf) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStagesF; s++) {
             mbar_init(&raw_full[s], 1);
             mbar_init(&b_full[s], 1);
-            mbar_init(&a_ready[s], 2 * kDeqWarps);
+            mbar_init(&a_ready[s], 2 * kDeqWarps / kDeqGroups);
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; b++) {
@@ -218,23 +234,61 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
     const uint32_t smem_a = smem_u32(smem);
 
     if (warp == 0) {
-        // ===== TMA producer (one thread per CTA): this CTA's 128 rows of X' and its raw weight chunks, stage by stage =====
+        // ===== TMA producer for X' (one thread per CTA): this CTA's 128 activation rows of the tile, stage by stage.  X' comes from
+        // the quantize kernel right before this one in the stream: with programmatic dependent launch this grid is already
+        // resident (weights are being staged and dequantized) when that kernel finishes. =====
         if (lane == 0) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
             int it = 0;
             Unit u;
             for (int i = 0; get_unit(sc, pair, i, u); i++) {
-                const int m0 = u.tm * 2 * TM + (int)rank * TM, n0 = u.tn * TN + (int)rank * (TN / 2);
+                const int n0 = u.tn * TN + (int)rank * (TN / 2);
                 for (int ks = u.ks0; ks < u.ks1; ks++, it++) {
                     const int s = it % kStagesF;
                     const uint32_t ph = (uint32_t)(it / kStagesF) & 1u;
                     mbar_wait(&empty[s], ph ^ 1u);
-                    const uint32_t st = smem_a + (uint32_t)(s * kStageF);
-                    mbar_expect_tx(&raw_full[s], kRawBytes);
-#pragma unroll
-                    for (int c = 0; c < CHUNKS; c++)      // chunk-major: [chunk][row][16 B] -> conflict-free 128-bit reads, thread = row
-                        tma_load_2d(smem + s * kStageF + kATile + kBTile + c * TM * 16, &map_raw, ks * 2 * QSB + c * 16, m0, &raw_full[s]);
                     if (rank == 0) mbar_expect_tx(&b_full[s], 2 * kBTile);
-                    tma_load_2d_pair(st + kATile, &map_b, ks * 128, n0, smem_u32(&b_full[s]) & kPeerMask);
+                    tma_load_2d_pair(smem_a + (uint32_t)(s * kStageF + kATile), &map_b, ks * 128, n0, smem_u32(&b_full[s]) & kPeerMask);
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===== TMA producer for the raw weight rows (its own thread: a bulk-class instruction occupies the issuing thread for
+        // ~150 cycles, and one k-step of MMAs is only 512).  The weights come from HBM (every byte exactly once per launch), ~2 us
+        // away, while the five stages of the ring cover ~1.3 us of MMAs: a second cursor runs kPfAhead k-steps ahead of the copies,
+        // across unit boundaries, and asks L2 for 256 bytes per row at a time (and for the block scales, 32 bytes per row). =====
+        if (lane == 0) {
+            int pf_i = 0, pf_ahead = 0;
+            Unit pu;
+            bool pf_live = get_unit(sc, pair, 0, pu);
+            int pf_ks = pf_live ? pu.ks0 : 0;
+            auto prefetch_more = [&]() {
+                while (pf_live && pf_ahead < kPfAhead) {
+                    const int pm0 = pu.tm * 2 * TM + (int)rank * TM;
+                    const int blk0 = pf_ks & ~(RT::kPfSteps - 1);       // aligned boxes: the innermost coordinate stays a multiple of 16 bytes
+                    tma_prefetch_2d(&map_raw_pf, blk0 * RT::kRow, pm0);
+                    if (g.dw_pf && (pf_ks == pu.ks0 || (blk0 & 7) == 0)) tma_prefetch_2d(&map_dw_pf, (pf_ks >> 3) * 32, pm0);     // 16 scales = 8 k-steps
+                    const int next = min(blk0 + RT::kPfSteps, pu.ks1);
+                    pf_ahead += next - pf_ks;
+                    pf_ks = next;
+                    if (pf_ks >= pu.ks1) {
+                        pf_live = get_unit(sc, pair, ++pf_i, pu);
+                        pf_ks = pf_live ? pu.ks0 : 0;
+                    }
+                }
+            };
+            int it = 0;
+            Unit u;
+            for (int i = 0; get_unit(sc, pair, i, u); i++) {
+                const int m0 = u.tm * 2 * TM + (int)rank * TM;
+                for (int ks = u.ks0; ks < u.ks1; ks++, it++) {
+                    prefetch_more();
+                    pf_ahead--;
+                    const int s = it % kStagesF;
+                    const uint32_t ph = (uint32_t)(it / kStagesF) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    mbar_expect_tx(&raw_full[s], RT::kBytes);
+                    tma_load_2d(rawtiles + s * RT::kBytes, &map_raw, ks * RT::kRow, m0, &raw_full[s]);
                 }
             }
         }
@@ -266,74 +320,89 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
             }
         }
     } else if (warp >= 8) {
-        // ===== dequantization: thread = (weight row r of this CTA's 128, block blk of the k-step's two) =====
-        const int t = (int)threadIdx.x - 256;
-        const int r = t & (TM - 1), blk = t >> 7;
+        // ===== dequantization: two groups of four warps take alternate k-steps; thread = one weight row of this CTA's 128, both
+        // blocks of the k-step (the whole 128-byte row of the W' tile).  Why groups: the generic -> async proxy fence that must
+        // precede the arrival costs a warp ~300 cycles (ncu: 40 % of these warps' time when every warp paid it every k-step);
+        // two groups halve the fences per k-step and give each warp two k-step periods per pass. =====
+        const int grp = (warp - 8) >> 2;
+        const int r = (warp & 3) * 32 + lane;
         const __half2 bias_lo = TYPE == B200_TYPE_Q4_0 ? __floats2half2_rn(1032.f, 1032.f) : __floats2half2_rn(1152.f, 1152.f);
         const __half2 bias_hi = __floats2half2_rn(72.f, 72.f);
         const uint32_t leader_ready = smem_u32(a_ready) & kPeerMask;
         const uint32_t sw = (uint32_t)(r & 7);
-        int it = 0;
+        // where TMA's 32 / 64-byte swizzle puts 16-byte piece j of this row: j ^ (bits 7.. of the row's offset)
+        const uint32_t rsw = TYPE == B200_TYPE_Q4_0 ? (uint32_t)((r >> 2) & 1) : (uint32_t)((r >> 1) & 3);
+        const uint32_t raw_a = smem_u32(rawtiles) + (uint32_t)(r * RT::kRow);
+        int it = grp, s = grp;                  // this group's k-steps of the pair's flattened sequence: grp, grp + 2, ...
+        uint32_t ph = 0;
+        int base = 0;                           // flattened index of the unit's first k-step
         Unit u;
         for (int i = 0; get_unit(sc, pair, i, u); i++) {
+            const int len = u.ks1 - u.ks0;
             const int row = min(u.tm * 2 * TM + (int)rank * TM + r, g.m - 1);      // (rows past m: TMA delivered zeros; any finite scale will do)
             const unsigned short *dwp = reinterpret_cast<const unsigned short *>(g.dw) + (int64_t)row * nb;
-            // the block's scale two k-steps ahead of its use (an L2 miss costs more than one k-step)
-            auto ldd = [&](int ks) -> unsigned short {
-                const int b = 2 * ks + blk;
-                return (ks < u.ks1 && b < nb) ? __ldg(dwp + b) : (unsigned short)0;       // past the end of k: zero scale -> zero weights
+            auto ldd = [&](int ks, int b) -> unsigned short {      // scale of block b of k-step ks; past the unit or past a ragged k: 0
+                const int blk = 2 * ks + b;
+                return (ks < u.ks1 && blk < nb) ? __ldg(dwp + blk) : (unsigned short)0;
             };
-            unsigned short d0 = ldd(u.ks0), d1 = ldd(u.ks0 + 1);
-            for (int ks = u.ks0; ks < u.ks1; ks++, it++) {
-                const int s = it % kStagesF;
-                const uint32_t ph = (uint32_t)(it / kStagesF) & 1u;
-                const unsigned short dcur = d0;
-                d0 = d1;
-                d1 = ldd(ks + 2);
-                const __half dh = __ushort_as_half(dcur);
-                const __half2 d2 = __halves2half2(dh, dh);
+            int ks = u.ks0 + (it - base);
+            // the scales two of this thread's k-steps (four k-steps of the stream) ahead of their use; L2 has them (prefetch above)
+            unsigned short a0 = ldd(ks, 0), a1 = ldd(ks, 1), b0 = ldd(ks + kDeqGroups, 0), b1 = ldd(ks + kDeqGroups, 1);
+            for (; ks < u.ks1; ks += kDeqGroups, it += kDeqGroups) {
+                const unsigned short c0 = a0, c1 = a1;
+                a0 = b0; a1 = b1;
+                b0 = ldd(ks + 2 * kDeqGroups, 0);
+                b1 = ldd(ks + 2 * kDeqGroups, 1);
                 mbar_wait(&raw_full[s], ph);
-                const uint32_t st = smem_a + (uint32_t)(s * kStageF);
-                const uint32_t raw = st + kATile + kBTile + (uint32_t)(r * 16);
-                const uint32_t arow = st + (uint32_t)(r * 128);
-                if (TYPE == B200_TYPE_Q4_0) {
-                    // chunk `blk` holds the block's 16 bytes: low nibbles = elements 0..15, high nibbles = elements 16..31
-                    const uint4 q = lds128f(raw + (uint32_t)(blk * TM * 16));
-                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-                    uint32_t lo[8], hi[8];
+                uint4 q[RT::kRow / 16];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t x = w[j], y = w[j] >> 8;
-                        lo[2 * j + 0] = cvt2((x & 0x000F000Fu) | 0x64006400u, bias_lo, d2);     // bytes 0, 2 of the word: 1024 + nib
-                        lo[2 * j + 1] = cvt2((y & 0x000F000Fu) | 0x64006400u, bias_lo, d2);     // bytes 1, 3
-                        hi[2 * j + 0] = cvt2((x & 0x00F000F0u) | 0x54005400u, bias_hi, d2);     // 64 + nib (the nibble sits 4 bits up: ulp 1/16)
-                        hi[2 * j + 1] = cvt2((y & 0x00F000F0u) | 0x54005400u, bias_hi, d2);
-                    }
-                    // 16-byte chunk c of the row goes where TMA with SWIZZLE_128B would put it: c ^ (row & 7)
-                    sts128f(arow + (((uint32_t)(blk * 4 + 0) ^ sw) << 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
-                    sts128f(arow + (((uint32_t)(blk * 4 + 1) ^ sw) << 4), make_uint4(lo[4], lo[5], lo[6], lo[7]));
-                    sts128f(arow + (((uint32_t)(blk * 4 + 2) ^ sw) << 4), make_uint4(hi[0], hi[1], hi[2], hi[3]));
-                    sts128f(arow + (((uint32_t)(blk * 4 + 3) ^ sw) << 4), make_uint4(hi[4], hi[5], hi[6], hi[7]));
-                } else {
+                for (int j = 0; j < RT::kRow / 16; j++) q[j] = lds128f(raw_a + (uint32_t)(s * RT::kBytes) + ((((uint32_t)j) ^ rsw) << 4));
+                const uint32_t arow = smem_a + (uint32_t)(s * kStageF + r * 128);
 #pragma unroll
-                    for (int h16 = 0; h16 < 2; h16++) {
-                        const uint4 q = lds128f(raw + (uint32_t)((blk * 2 + h16) * TM * 16));
-                        const uint32_t w[4] = {q.x ^ 0x80808080u, q.y ^ 0x80808080u, q.z ^ 0x80808080u, q.w ^ 0x80808080u};   // int8 + 128
-                        uint32_t o[8];
+                for (int b = 0; b < 2; b++) {
+                    const __half dh = __ushort_as_half(b == 0 ? c0 : c1);
+                    const __half2 d2 = __halves2half2(dh, dh);
+                    if (TYPE == B200_TYPE_Q4_0) {
+                        // the block's 16 bytes: low nibbles = elements 0..15, high nibbles = elements 16..31
+                        const uint32_t w[4] = {q[b].x, q[b].y, q[b].z, q[b].w};
+                        uint32_t lo[8], hi[8];
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            o[2 * j + 0] = cvt2((w[j] & 0x00FF00FFu) | 0x64006400u, bias_lo, d2);
-                            o[2 * j + 1] = cvt2(((w[j] >> 8) & 0x00FF00FFu) | 0x64006400u, bias_lo, d2);
+                            const uint32_t x = w[j], y = w[j] >> 8;
+                            lo[2 * j + 0] = cvt2((x & 0x000F000Fu) | 0x64006400u, bias_lo, d2);     // bytes 0, 2 of the word: 1024 + nib
+                            lo[2 * j + 1] = cvt2((y & 0x000F000Fu) | 0x64006400u, bias_lo, d2);     // bytes 1, 3
+                            hi[2 * j + 0] = cvt2((x & 0x00F000F0u) | 0x54005400u, bias_hi, d2);     // 64 + nib (the nibble sits 4 bits up: ulp 1/16)
+                            hi[2 * j + 1] = cvt2((y & 0x00F000F0u) | 0x54005400u, bias_hi, d2);
                         }
-                        sts128f(arow + (((uint32_t)(blk * 4 + h16 * 2 + 0) ^ sw) << 4), make_uint4(o[0], o[1], o[2], o[3]));
-                        sts128f(arow + (((uint32_t)(blk * 4 + h16 * 2 + 1) ^ sw) << 4), make_uint4(o[4], o[5], o[6], o[7]));
+                        // 16-byte chunk c of the row goes where TMA with SWIZZLE_128B would put it: c ^ (row & 7)
+                        sts128f(arow + (((uint32_t)(b * 4 + 0) ^ sw) << 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+                        sts128f(arow + (((uint32_t)(b * 4 + 1) ^ sw) << 4), make_uint4(lo[4], lo[5], lo[6], lo[7]));
+                        sts128f(arow + (((uint32_t)(b * 4 + 2) ^ sw) << 4), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+                        sts128f(arow + (((uint32_t)(b * 4 + 3) ^ sw) << 4), make_uint4(hi[4], hi[5], hi[6], hi[7]));
+                    } else {
+#pragma unroll
+                        for (int h16 = 0; h16 < 2; h16++) {
+                            const uint4 qq = q[(b * 2 + h16) % (RT::kRow / 16)];
+                            const uint32_t w[4] = {qq.x ^ 0x80808080u, qq.y ^ 0x80808080u, qq.z ^ 0x80808080u, qq.w ^ 0x80808080u};   // int8 + 128
+                            uint32_t o[8];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                o[2 * j + 0] = cvt2((w[j] & 0x00FF00FFu) | 0x64006400u, bias_lo, d2);
+                                o[2 * j + 1] = cvt2(((w[j] >> 8) & 0x00FF00FFu) | 0x64006400u, bias_lo, d2);
+                            }
+                            sts128f(arow + (((uint32_t)(b * 4 + h16 * 2 + 0) ^ sw) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+                            sts128f(arow + (((uint32_t)(b * 4 + h16 * 2 + 1) ^ sw) << 4), make_uint4(o[4], o[5], o[6], o[7]));
+                        }
                     }
                 }
                 // generic-proxy stores -> visible to the tensor core (async proxy), then one arrival per warp on the leader's barrier
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(leader_ready + (uint32_t)(s * 8));
+                s += kDeqGroups;
+                if (s >= kStagesF) { s -= kStagesF; ph ^= 1u; }
             }
+            base += len;
         }
     } else if (warp >= 4) {
         // ===== epilogue: warp q of 4 owns TMEM lanes 32q.. = weight rows; whole tiles go straight to dst, k-slices through
@@ -377,57 +446,73 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
                 }
             }
             if (u.nparts > 1) {
-                // this warp's share of the k-slice is in the workspace: publish, then reduce this pair's column slice of the tile
+                // this warp's share of the k-slice is in the workspace: publish (the reduction follows below, by all twelve warps)
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) atomicAdd(g.counters + u.rtile, 1u);
-                const uint32_t target = (uint32_t)(u.nparts * 2 * kEpiWarpsF);
-                if (lane == 0) {
-                    unsigned long long t0 = 0;
-                    unsigned spins = 0;
-                    for (;;) {
-                        uint32_t seen;
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(g.counters + u.rtile) : "memory");
-                        if (seen >= target) break;
-                        __nanosleep(100);
-                        if ((++spins & 255u) == 0u) {      // bounded: a pair that never delivers must not hang the GPU
-                            if (*reinterpret_cast<volatile uint32_t *>(g.abort_flag) != 0u) break;
-                            const unsigned long long now = gtimer();
-                            if (t0 == 0ull) t0 = now;
-                            else if (now - t0 > 5000000000ull) {
-                                if (atomicCAS(g.abort_flag, 0u, 0x80000004u) == 0u) *reinterpret_cast<volatile uint32_t *>(g.abort_host) = 0x80000004u;
-                                break;
-                            }
-                        }
+            }
+        }
+    }
+
+    // ===== split-k reduction: the pair's k-slice (always its last unit) is in the workspace; once every slice of the tile is,
+    // this pair sums ITS column range of the tile over all slices in the fixed order 0, 1, 2, ... and writes dst.  Twelve warps
+    // per CTA (epilogue + dequantization, idle by now): warp = 32 rows x a third of the columns, all loads of a batch in flight. =====
+    if (warp >= 4 && sc.rem > 0 && pair < sc.rem * sc.split) {
+        Unit u;
+        get_unit(sc, pair, sc.full_rounds, u);
+        const int wslot = warp - 4;                   // 0..11
+        const int rgrp = wslot & 3, cthird = wslot >> 2;
+        const int rloc = (int)rank * TM + rgrp * 32 + lane;
+        const int row = u.tm * 2 * TM + rloc;
+        const int n0 = u.tn * TN;
+        if (lane == 0) {
+            const uint32_t target = (uint32_t)(u.nparts * 2 * kEpiWarpsF);
+            unsigned long long t0 = 0;
+            unsigned spins = 0;
+            for (;;) {
+                uint32_t seen;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(g.counters + u.rtile) : "memory");
+                if (seen >= target) break;
+                __nanosleep(100);
+                if ((++spins & 255u) == 0u) {      // bounded: a pair that never delivers must not hang the GPU
+                    if (*reinterpret_cast<volatile uint32_t *>(g.abort_flag) != 0u) break;
+                    const unsigned long long now = gtimer();
+                    if (t0 == 0ull) t0 = now;
+                    else if (now - t0 > 5000000000ull) {
+                        if (atomicCAS(g.abort_flag, 0u, 0x80000004u) == 0u) *reinterpret_cast<volatile uint32_t *>(g.abort_host) = 0x80000004u;
+                        break;
                     }
                 }
-                __syncwarp();
-                const int c_lo = TN * u.part / u.nparts, c_hi = min(TN * (u.part + 1) / u.nparts, g.n - n0);
-                const float *tp = g.partial + ((size_t)(u.rtile * sc.split) * TN) * (2 * TM) + rloc;
-                if (row < g.m) {
-                    // four columns at a time with every part's load in flight together (an L2 round trip per dependent load would
-                    // make this phase latency-bound); the sum itself runs in the fixed order part 0, 1, 2, ...
-                    for (int c = c_lo; c < c_hi; c += 4) {
-                        float acc4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                        for (int p0 = 0; p0 < u.nparts; p0 += 4) {
-                            float v[4][4];
+            }
+        }
+        __syncwarp();
+        const int p_lo = TN * u.part / u.nparts, p_hi = min(TN * (u.part + 1) / u.nparts, g.n - n0);   // the pair's columns
+        const int span = p_hi - p_lo;
+        const int c_lo = p_lo + (span > 0 ? span * cthird / 3 : 0), c_hi = p_lo + (span > 0 ? span * (cthird + 1) / 3 : 0);
+        const float *tp = g.partial + ((size_t)(u.rtile * sc.split) * TN) * (2 * TM) + rloc;
+        if (row < g.m) {
+            constexpr int CB = 8, PB = 4;
+            for (int c = c_lo; c < c_hi; c += CB) {
+                float acc[CB];
 #pragma unroll
-                            for (int pp = 0; pp < 4; pp++)
+                for (int cc = 0; cc < CB; cc++) acc[cc] = 0.0f;
+                for (int p0 = 0; p0 < u.nparts; p0 += PB) {
+                    float v[PB][CB];
 #pragma unroll
-                                for (int cc = 0; cc < 4; cc++)
-                                    v[pp][cc] = (p0 + pp < u.nparts && c + cc < c_hi) ? __ldcg(tp + ((size_t)(p0 + pp) * TN + (c + cc)) * (2 * TM)) : 0.0f;
+                    for (int pp = 0; pp < PB; pp++)
 #pragma unroll
-                            for (int pp = 0; pp < 4; pp++)
-                                if (p0 + pp < u.nparts) {
+                        for (int cc = 0; cc < CB; cc++)
+                            v[pp][cc] = (p0 + pp < u.nparts && c + cc < c_hi) ? __ldcg(tp + ((size_t)(p0 + pp) * TN + (c + cc)) * (2 * TM)) : 0.0f;
 #pragma unroll
-                                    for (int cc = 0; cc < 4; cc++) acc4[cc] += v[pp][cc];
-                                }
+                    for (int pp = 0; pp < PB; pp++)
+                        if (p0 + pp < u.nparts) {
+#pragma unroll
+                            for (int cc = 0; cc < CB; cc++) acc[cc] += v[pp][cc];
                         }
-#pragma unroll
-                        for (int cc = 0; cc < 4; cc++)
-                            if (c + cc < c_hi) g.dst[(int64_t)(n0 + c + cc) * g.m + row] = acc4[cc];
-                    }
                 }
+#pragma unroll
+                for (int cc = 0; cc < CB; cc++)
+                    if (c + cc < c_hi) g.dst[(int64_t)(n0 + c + cc) * g.m + row] = acc[cc];
             }
         }
     }
@@ -444,6 +529,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
 // same explicitly rounded arithmetic as b200_quantize.cu), written in the k-order of the operand tiles: within every aligned
 // group of four the order is (0, 2, 1, 3).  8 lanes per block, one 128-bit load and one 64-bit store per lane.
 __global__ void __launch_bounds__(256) quantize_to_f16_kernel(const float *__restrict__ x, int64_t k, int64_t nrows, size_t row_stride, __half *__restrict__ out) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // the GEMM may take the SMs as they free up (it waits for X' itself)
     const int64_t nb = k / 32;
     const int64_t total = nrows * nb * 8;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)b200_align_up((size_t)total, 32); t += (int64_t)gridDim.x * blockDim.x) {
@@ -471,16 +557,17 @@ __global__ void __launch_bounds__(256) quantize_to_f16_kernel(const float *__res
     }
 }
 
-// the qs plane as bytes: rows x row_bytes, box = 128 rows x 16 bytes, no swizzle; out-of-bounds -> zeros
-bool make_chunk_map(CUtensorMap *map, const void *base, int64_t rows, int64_t row_bytes) {
+// a plane as bytes: rows x row_bytes; box = 128 rows x box_bytes with the given swizzle; out-of-bounds (rows past m, bytes past the
+// end of a ragged k) -> zeros
+bool make_rows_map(CUtensorMap *map, const void *base, int64_t rows, int64_t row_bytes, int box_bytes, CUtensorMapSwizzle swz) {
     auto fn = get_encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
-    cuuint32_t box[2] = {16u, (cuuint32_t)TM};
+    cuuint32_t box[2] = {(cuuint32_t)box_bytes, (cuuint32_t)TM};
     cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // X' as bytes: n rows x (k * 2) bytes; box = 128 rows x 128 bytes, 128-byte swizzle, out-of-bounds -> zeros
 bool make_xp_map(CUtensorMap *map, const void *base, int64_t rows, int64_t row_bytes) {
@@ -549,14 +636,21 @@ int b200_launch_gemm_f16(b200_ctx *ctx, int type, const uint8_t *qs, const __hal
         B200_CUDA_TRY(ctx, cudaGetLastError());
     }
     if (sc.rem > 0) B200_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, (size_t)sc.rem * 4, ctx->stream));
-    CUtensorMap map_raw, map_b;
-    if (!make_chunk_map(&map_raw, qs, m, nb * qsb) || !make_xp_map(&map_b, xp, n, k * 2)) {
+    CUtensorMap map_raw, map_b, map_raw_pf, map_dw_pf;
+    B200_REQUIRE(ctx, ((uintptr_t)qs & 15) == 0 && ((uintptr_t)d & 1) == 0, B200_ERR_UNSUPPORTED);
+    const bool dw_pf = (nb * 2) % 16 == 0 && nb >= 16 && ((uintptr_t)d & 15) == 0;
+    const int64_t row_bytes = nb * qsb;
+    const int pf_box = row_bytes >= 256 ? 256 : (int)row_bytes;
+    if (!make_rows_map(&map_raw, qs, m, row_bytes, 2 * qsb, type == B200_TYPE_Q4_0 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B) ||
+        !make_xp_map(&map_b, xp, n, k * 2) || !make_rows_map(&map_raw_pf, qs, m, row_bytes, pf_box, CU_TENSOR_MAP_SWIZZLE_NONE) ||
+        !(dw_pf ? make_rows_map(&map_dw_pf, d, m, nb * 2, 32, CU_TENSOR_MAP_SWIZZLE_NONE) : make_rows_map(&map_dw_pf, qs, m, row_bytes, pf_box, CU_TENSOR_MAP_SWIZZLE_NONE))) {
         b200_set_error(ctx, "cuTensorMapEncodeTiled failed (fp16 prefill path, m=%lld n=%lld k=%lld)", (long long)m, (long long)n, (long long)k);
         return B200_ERR_CUDA;
     }
     GemmF16Args g;
     memset(&g, 0, sizeof(g));
     g.dw = d;
+    g.dw_pf = dw_pf ? 1 : 0;
     g.dst = dst;
     g.partial = partial;
     g.counters = counters;
@@ -570,12 +664,23 @@ int b200_launch_gemm_f16(b200_ctx *ctx, int type, const uint8_t *qs, const __hal
     int use_pairs = pairs;
     const int units = sc.full_rounds > 0 ? (sc.tiles < pairs ? sc.tiles : pairs) : sc.rem * sc.split;
     if (units < use_pairs) use_pairs = units;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * use_pairs), 1, 1);
+    cfg.blockDim = dim3(kThreadsF, 1, 1);
+    cfg.dynamicSmemBytes = type == B200_TYPE_Q4_0 ? RawTile<B200_TYPE_Q4_0>::kSmem : RawTile<B200_TYPE_Q8_0>::kSmem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // overlap the prologue and the first weight stages with the quantize kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ctx->opt_pdl ? 1 : 0;
     if (type == B200_TYPE_Q4_0) {
-        B200_CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_f16_pair_kernel<B200_TYPE_Q4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemF));
-        gemm_f16_pair_kernel<B200_TYPE_Q4_0><<<2 * use_pairs, kThreadsF, kSmemF, ctx->stream>>>(map_raw, map_b, g);
+        B200_CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_f16_pair_kernel<B200_TYPE_Q4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RawTile<B200_TYPE_Q4_0>::kSmem));
+        B200_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, gemm_f16_pair_kernel<B200_TYPE_Q4_0>, map_raw, map_b, map_raw_pf, map_dw_pf, g));
     } else {
-        B200_CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_f16_pair_kernel<B200_TYPE_Q8_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemF));
-        gemm_f16_pair_kernel<B200_TYPE_Q8_0><<<2 * use_pairs, kThreadsF, kSmemF, ctx->stream>>>(map_raw, map_b, g);
+        B200_CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_f16_pair_kernel<B200_TYPE_Q8_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RawTile<B200_TYPE_Q8_0>::kSmem));
+        B200_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, gemm_f16_pair_kernel<B200_TYPE_Q8_0>, map_raw, map_b, map_raw_pf, map_dw_pf, g));
     }
     ctx->launches++;
     B200_CUDA_TRY(ctx, cudaGetLastError());
