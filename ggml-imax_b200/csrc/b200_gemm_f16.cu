@@ -44,7 +44,7 @@ constexpr int kThreadsF = 16 * 32;
 constexpr int kDeqWarps = 8;
 constexpr int kDeqGroups = 2;             // groups of kDeqWarps / kDeqGroups warps that take alternate k-steps
 constexpr int kEpiWarpsF = 4;
-constexpr int kBarsF = 4 * kStagesF + 4;               // raw_full, b_full, a_ready, empty (x stages), tmem_full[2], tmem_empty[2]
+constexpr int kBarsF = (3 + kDeqGroups) * kStagesF + 4;   // raw_full (x groups), b_full, a_ready, empty (x stages), tmem_full[2], tmem_empty[2]
 // raw weight tiles: per stage 128 rows x (32 | 64) bytes of the qs plane (both blocks of the k-step), TMA with the 32 / 64-byte
 // swizzle so that thread = row reads its 16-byte pieces without bank conflicts
 template <int TYPE> struct RawTile {
@@ -189,11 +189,14 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
     using RT = RawTile<TYPE>;
     unsigned char *rawtiles = smem + kStagesF * kStageF;
     uint64_t *bars = reinterpret_cast<uint64_t *>(rawtiles + kStagesF * RT::kBytes);
-    uint64_t *raw_full = bars;                        // [stages] local: this CTA's raw weight rows have landed
-    uint64_t *b_full = bars + kStagesF;               // [stages] leader: both halves of the X' tile have landed
-    uint64_t *a_ready = bars + 2 * kStagesF;          // [stages] leader: both CTAs' W' tiles are written (one group's warps of each CTA)
-    uint64_t *empty = bars + 3 * kStagesF;            // [stages] local: the MMAs that read this stage have completed
-    uint64_t *tmem_full = bars + 4 * kStagesF;        // [2] local: the unit's accumulator is complete
+    // raw_full: [group][stages], local: this CTA's raw weight rows of a k-step have landed.  One barrier per (group, stage): a
+    // group only waits for ITS k-steps (every other fill of a stage), and a parity wait that skips a phase can pass a fill early
+    // (seen as one warp's 32 rows of a tile going wrong once in ~40 launches): every waiter must see consecutive phases.
+    uint64_t *raw_full = bars;
+    uint64_t *b_full = bars + kDeqGroups * kStagesF;  // [stages] leader: both halves of the X' tile have landed
+    uint64_t *a_ready = b_full + kStagesF;            // [stages] leader: both CTAs' W' tiles are written (one group's warps of each CTA)
+    uint64_t *empty = a_ready + kStagesF;             // [stages] local: the MMAs that read this stage have completed
+    uint64_t *tmem_full = empty + kStagesF;           // [2] local: the unit's accumulator is complete
     uint64_t *tmem_empty = tmem_full + 2;             // [2] leader: both CTAs' epilogues have drained the accumulator (8 arrivals)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
 
@@ -211,8 +214,8 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dw_pf) : "memory");
     }
     if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kDeqGroups * kStagesF; s++) mbar_init(&raw_full[s], 1);
         for (int s = 0; s < kStagesF; s++) {
-            mbar_init(&raw_full[s], 1);
             mbar_init(&b_full[s], 1);
             mbar_init(&a_ready[s], 2 * kDeqWarps / kDeqGroups);
             mbar_init(&empty[s], 1);
@@ -287,8 +290,9 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
                     const int s = it % kStagesF;
                     const uint32_t ph = (uint32_t)(it / kStagesF) & 1u;
                     mbar_wait(&empty[s], ph ^ 1u);
-                    mbar_expect_tx(&raw_full[s], RT::kBytes);
-                    tma_load_2d(rawtiles + s * RT::kBytes, &map_raw, ks * RT::kRow, m0, &raw_full[s]);
+                    uint64_t *rf = &raw_full[(it % kDeqGroups) * kStagesF + s];      // the barrier of the group that takes this k-step
+                    mbar_expect_tx(rf, RT::kBytes);
+                    tma_load_2d(rawtiles + s * RT::kBytes, &map_raw, ks * RT::kRow, m0, rf);
                 }
             }
         }
@@ -334,6 +338,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
         const uint32_t rsw = TYPE == B200_TYPE_Q4_0 ? (uint32_t)((r >> 2) & 1) : (uint32_t)((r >> 1) & 3);
         const uint32_t raw_a = smem_u32(rawtiles) + (uint32_t)(r * RT::kRow);
         int it = grp, s = grp;                  // this group's k-steps of the pair's flattened sequence: grp, grp + 2, ...
+        int visits = 0;                         // ... of which every kStagesF-th comes back to the same stage: the phase of ITS barrier
         uint32_t ph = 0;
         int base = 0;                           // flattened index of the unit's first k-step
         Unit u;
@@ -353,7 +358,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
                 a0 = b0; a1 = b1;
                 b0 = ldd(ks + 2 * kDeqGroups, 0);
                 b1 = ldd(ks + 2 * kDeqGroups, 1);
-                mbar_wait(&raw_full[s], ph);
+                mbar_wait(&raw_full[grp * kStagesF + s], ph);
                 uint4 q[RT::kRow / 16];
 #pragma unroll
                 for (int j = 0; j < RT::kRow / 16; j++) q[j] = lds128f(raw_a + (uint32_t)(s * RT::kBytes) + ((((uint32_t)j) ^ rsw) << 4));
@@ -400,7 +405,8 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(leader_ready + (uint32_t)(s * 8));
                 s += kDeqGroups;
-                if (s >= kStagesF) { s -= kStagesF; ph ^= 1u; }
+                if (s >= kStagesF) s -= kStagesF;
+                if (++visits == kStagesF) { visits = 0; ph ^= 1u; }
             }
             base += len;
         }
