@@ -15,8 +15,13 @@ static bool use_gemm(const b200_ctx *ctx, const b200_mul_mat_args *a) {
 }
 
 static int run_gemv_chunks(b200_ctx *ctx, const b200_mul_mat_args *a, const uint8_t *qs, const __half *d) {
-    // column chunks of <= 8; each chunk re-streams the weights (only used when the GEMM cannot serve the shape)
-    for (int64_t c0 = 0; c0 < a->ne11; c0 += 8) {
+    // column chunks of <= 8; each chunk re-streams the weights (only used when the GEMM cannot serve the shape).  The generic
+    // GEMV keeps the chunk's quantized columns in shared memory (k + k/32 * 8 bytes each, 200 KB in all): long rows take
+    // narrower chunks, so that every shape supports_op accepts (k <= 131072) really runs.
+    const size_t col_bytes = (size_t)a->ne00 + (size_t)(a->ne00 / B200_QK) * 8 + 16;
+    int64_t chunk = 8;
+    while (chunk > 1 && (size_t)chunk * col_bytes > 200 * 1024) chunk--;
+    for (int64_t c0 = 0; c0 < a->ne11; c0 += chunk) {
         b200_gemv_params p;
         memset(&p, 0, sizeof(p));
         p.type = a->type;
@@ -27,7 +32,7 @@ static int run_gemv_chunks(b200_ctx *ctx, const b200_mul_mat_args *a, const uint
         p.ne02 = a->ne02;
         p.ne03 = a->ne03;
         p.x = reinterpret_cast<const float *>(reinterpret_cast<const char *>(a->src1_dev) + c0 * a->nb11);
-        p.n = (a->ne11 - c0) < 8 ? (a->ne11 - c0) : 8;
+        p.n = (a->ne11 - c0) < chunk ? (a->ne11 - c0) : chunk;
         p.ne12 = a->ne12;
         p.ne13 = a->ne13;
         p.nb11 = a->nb11;

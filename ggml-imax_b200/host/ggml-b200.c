@@ -299,8 +299,9 @@ struct b200_backend_context {
     char      name[32];
     struct b200_cached_plan plans[B200_PLAN_CACHE];
     int       plan_next;   /* round-robin eviction */
-    int       opt_plans;   /* 0: never build decode plans (env GGML_B200_NO_PLANS) */
+    int       opt_plans;   /* 0: never build decode plans (ggml_backend_b200_set_option "plans") */
     int64_t   plan_launches;
+    int       failed;      /* an asynchronous error surfaced in synchronize (which cannot return one): the next graph_compute reports it */
 };
 
 static ggml_guid_t b200_backend_guid(void) {
@@ -336,8 +337,14 @@ GGML_CALL static ggml_backend_buffer_type_t b200_backend_default_buft(ggml_backe
 }
 
 GGML_CALL static void b200_backend_synchronize(ggml_backend_t backend) {
+    /* ggml_backend_i.synchronize returns nothing (src/ggml-backend-impl.h:90); a failure here (e.g. a decode plan that gave up
+     * waiting for a peer) must not abort the host: it is logged, remembered, and returned by the next graph_compute */
     struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
-    B200_CHECK(bc->ctx, b200_synchronize(bc->ctx));
+    const int rc = b200_synchronize(bc->ctx);
+    if (rc != B200_OK) {
+        fprintf(stderr, "ggml-b200: synchronize failed (%d): %s\n", rc, b200_last_error(bc->ctx));
+        bc->failed = 1;
+    }
 }
 
 static bool b200_op_is_noop(enum ggml_op op) {
@@ -354,6 +361,10 @@ static bool b200_mul_mat_supported(const struct ggml_tensor *dst) {
     if (!b200_locate_quantized(a, &loc)) return false;
     if (b->nb[0] != sizeof(float)) return false;
     if (b->nb[1] % 16 != 0 || b->nb[2] % 16 != 0 || b->nb[3] % 16 != 0) return false;
+    /* activation rows are read with 128-bit loads: a view must start on a 16-byte boundary of its (256-byte aligned) parent;
+     * once allocated, the address itself is checked */
+    if (b->view_src != NULL && b->view_offs % 16 != 0) return false;
+    if (b->data != NULL && ((uintptr_t)b->data & 15) != 0) return false;
     if (!ggml_is_contiguous(dst)) return false;
     if (b->ne[2] % a->ne[2] != 0 || b->ne[3] % a->ne[3] != 0) return false;
     if (b->ne[2] * b->ne[3] > 65535) return false;
@@ -405,21 +416,50 @@ static enum ggml_status b200_compute_mul_mat_run(struct b200_backend_context *bc
     return GGML_STATUS_SUCCESS;
 }
 
-/* args of the graph's n MUL_MAT nodes -> b200_plan_create.  *out stays NULL when the graph cannot run as a plan
- * (B200_ERR_UNSUPPORTED: other shapes, aliased vectors); returns -1 on a hard error, 0 otherwise. */
-static int b200_build_plan(struct b200_backend_context *bc, const struct ggml_cgraph *cgraph, int n, b200_plan **out) {
+static bool b200_node_is_decode_mul_mat(const struct ggml_tensor *node) {
+    if (node->op != GGML_OP_MUL_MAT) return false;
+    const struct ggml_tensor *a = node->src[0], *b = node->src[1];
+    return a && b && b->ne[1] == 1 && b->ne[2] == 1 && b->ne[3] == 1 && a->ne[2] == 1 && a->ne[3] == 1 && a->ne[0] % 256 == 0 &&
+           a->ne[0] <= 32768 && b200_mul_mat_supported(node);
+}
+
+/* [first, last) = a maximal run of compute nodes that are all decode-shaped MUL_MATs (no-op nodes in between are skipped);
+ * returns how many such nodes it holds and a hash over their addresses and shapes */
+static int b200_decode_run(const struct ggml_cgraph *cgraph, int first, int *last_out, uint64_t *key_out) {
+    int n = 0, i = first;
+    uint64_t key = 1469598103934665603ull;     /* FNV-1a */
+    for (; i < cgraph->n_nodes; i++) {
+        struct ggml_tensor *node = cgraph->nodes[i];
+        if (ggml_is_empty(node) || b200_op_is_noop(node->op)) continue;
+        if (!b200_node_is_decode_mul_mat(node)) break;
+        const struct ggml_tensor *a = node->src[0], *b = node->src[1];
+        const uint64_t words[6] = {(uint64_t)(uintptr_t)a->data, (uint64_t)(uintptr_t)b->data, (uint64_t)(uintptr_t)node->data,
+                                   (uint64_t)a->ne[0], (uint64_t)a->ne[1], (uint64_t)a->type};
+        for (int w = 0; w < 6; w++)
+            for (int sh = 0; sh < 64; sh += 8) key = (key ^ ((words[w] >> sh) & 0xff)) * 1099511628211ull;
+        n++;
+    }
+    if (key == 0) key = 1;
+    *last_out = i;
+    if (key_out) *key_out = key;
+    return n;
+}
+
+/* args of the n decode MUL_MAT nodes in [first, last) -> b200_plan_create.  *out stays NULL when they cannot run as a plan
+ * (B200_ERR_UNSUPPORTED); returns -1 on a hard error, 0 otherwise. */
+static int b200_build_plan(struct b200_backend_context *bc, const struct ggml_cgraph *cgraph, int first, int last, int n, b200_plan **out) {
     *out = NULL;
     b200_mul_mat_args *args = (b200_mul_mat_args *)malloc(sizeof(b200_mul_mat_args) * (size_t)n);
     if (!args) return -1;
     int k = 0;
     bool ok = true;
-    for (int i = 0; i < cgraph->n_nodes && ok; i++) {
+    for (int i = first; i < last && ok; i++) {
         struct ggml_tensor *node = cgraph->nodes[i];
         if (ggml_is_empty(node) || b200_op_is_noop(node->op)) continue;
-        ok = b200_mul_mat_supported(node) && b200_fill_mul_mat_args(node, &args[k++]);
+        ok = k < n && b200_fill_mul_mat_args(node, &args[k++]);
     }
     int ret = 0;
-    if (ok) {
+    if (ok && k == n) {
         const int rc = b200_plan_create(bc->ctx, args, n, NULL, out);
         if (rc != B200_OK) {
             *out = NULL;
@@ -433,40 +473,16 @@ static int b200_build_plan(struct b200_backend_context *bc, const struct ggml_cg
     return ret;
 }
 
-/* number of decode-shaped MUL_MAT compute nodes if the graph consists of nothing else (and has at least two), else 0;
- * *key = hash over their addresses and shapes */
-static int b200_decode_graph_nodes(const struct ggml_cgraph *cgraph, uint64_t *key_out) {
-    int n = 0;
-    uint64_t key = 1469598103934665603ull;     /* FNV-1a */
-    for (int i = 0; i < cgraph->n_nodes; i++) {
-        struct ggml_tensor *node = cgraph->nodes[i];
-        if (ggml_is_empty(node) || b200_op_is_noop(node->op)) continue;
-        if (node->op != GGML_OP_MUL_MAT) return 0;
-        const struct ggml_tensor *a = node->src[0], *b = node->src[1];
-        if (!a || !b || b->ne[1] != 1 || b->ne[2] != 1 || b->ne[3] != 1 || a->ne[2] != 1 || a->ne[3] != 1) return 0;
-        const uint64_t words[6] = {(uint64_t)(uintptr_t)a->data, (uint64_t)(uintptr_t)b->data, (uint64_t)(uintptr_t)node->data,
-                                   (uint64_t)a->ne[0], (uint64_t)a->ne[1], (uint64_t)a->type};
-        for (int w = 0; w < 6; w++)
-            for (int sh = 0; sh < 64; sh += 8) key = (key ^ ((words[w] >> sh) & 0xff)) * 1099511628211ull;
-        n++;
-    }
-    if (key == 0) key = 1;
-    if (key_out) *key_out = key;
-    return n >= 2 ? n : 0;
-}
-
 /*
- * Decode graphs: when every compute node of the cgraph is a decode-shaped MUL_MAT (one activation column, 2-D weights), the
- * whole graph goes down as ONE persistent launch (b200_plan_*, include/ggml_b200.h) -- what ggml_backend_graph_plan_create /
- * _compute would be for this backend, done transparently and cached per graph like the reference's CUDA-graph replay
- * (src/ggml-cuda.cu:2461-2709).  Returns 1 when the graph was computed that way, 0 when it has to go node by node (other
- * shapes, or tensors that share memory as a graph allocator arranges them), -1 on a hard error.
+ * Decode runs: a maximal run of two or more decode-shaped MUL_MAT nodes (one activation column, 2-D weights) -- a whole
+ * mul_mat-only graph, or the part of a mixed graph between two other ops -- goes down as ONE persistent launch (b200_plan_*,
+ * include/ggml_b200.h): what ggml_backend_graph_plan_create / _compute would be for this backend, done transparently and cached
+ * per run like the reference's CUDA-graph replay (src/ggml-cuda.cu:2461-2709).  Tensors that share memory the way ggml_gallocr
+ * arranges them are fine (the plan keeps dead intermediates out of plain memory).  Returns 1 when the run was computed that
+ * way, 0 when it has to go node by node, -1 on a hard error.
  */
-static int b200_try_graph_as_plan(struct b200_backend_context *bc, struct ggml_cgraph *cgraph) {
-    if (!bc->opt_plans) return 0;
-    uint64_t key = 0;
-    const int n = b200_decode_graph_nodes(cgraph, &key);
-    if (n == 0) return 0;
+static int b200_try_run_as_plan(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int first, int last, int n, uint64_t key) {
+    if (!bc->opt_plans || n < 2) return 0;
     struct b200_cached_plan *slot = NULL;
     for (int i = 0; i < B200_PLAN_CACHE; i++)
         if (bc->plans[i].key == key && bc->plans[i].n_nodes == n) slot = &bc->plans[i];
@@ -480,10 +496,11 @@ static int b200_try_graph_as_plan(struct b200_backend_context *bc, struct ggml_c
         slot->key = key;
         slot->n_nodes = n;
         slot->plan = NULL;
-        if (b200_build_plan(bc, cgraph, n, &slot->plan) < 0) return -1;
+        if (b200_build_plan(bc, cgraph, first, last, n, &slot->plan) < 0) return -1;
     }
     if (!slot->plan) return 0;
     const int rc = b200_plan_launch(bc->ctx, slot->plan);
+    if (rc == B200_ERR_UNSUPPORTED) return 0;          /* the grid cannot be co-resident right now: node by node */
     if (rc != B200_OK) {
         fprintf(stderr, "ggml-b200: b200_plan_launch failed (%d): %s\n", rc, b200_last_error(bc->ctx));
         return -1;
@@ -492,63 +509,68 @@ static int b200_try_graph_as_plan(struct b200_backend_context *bc, struct ggml_c
     return 1;
 }
 
-static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc, struct ggml_cgraph *cgraph);
+static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int first, int last);
 
 GGML_CALL static enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, struct ggml_cgraph *cgraph) {
     struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
-    const int as_plan = b200_try_graph_as_plan(bc, cgraph);
-    if (as_plan < 0) return GGML_STATUS_FAILED;
-    if (as_plan > 0) return GGML_STATUS_SUCCESS;
-    return b200_graph_compute_nodes(bc, cgraph);
+    if (bc->failed) {
+        bc->failed = 0;
+        return GGML_STATUS_FAILED;
+    }
+    int i = 0;
+    while (i < cgraph->n_nodes) {
+        struct ggml_tensor *node = cgraph->nodes[i];
+        if (ggml_is_empty(node) || b200_op_is_noop(node->op)) { i++; continue; }
+        int last = i;
+        uint64_t key = 0;
+        const int n = b200_decode_run(cgraph, i, &last, &key);
+        if (n >= 2) {
+            const int as_plan = b200_try_run_as_plan(bc, cgraph, i, last, n, key);
+            if (as_plan < 0) return GGML_STATUS_FAILED;
+            if (as_plan == 0) {
+                const enum ggml_status st = b200_graph_compute_nodes(bc, cgraph, i, last);
+                if (st != GGML_STATUS_SUCCESS) return st;
+            }
+            i = last;
+            continue;
+        }
+        /* anything else, up to the next decode run: node by node */
+        int stop = n == 1 ? last : i + 1;
+        const enum ggml_status st = b200_graph_compute_nodes(bc, cgraph, i, stop);
+        if (st != GGML_STATUS_SUCCESS) return st;
+        i = stop;
+    }
+    return GGML_STATUS_SUCCESS;
 }
 
 /* ggml_backend_graph_plan_create / _free / _compute (src/ggml-backend-impl.h:94-99, src/ggml-backend.c:257-273): the explicit
  * form of the above.  Like the reference CPU backend's plan (src/ggml-backend.c:761-790) it keeps a shallow copy of the cgraph,
- * so the graph has to outlive the plan.  A graph that cannot be one persistent launch is computed node by node. */
+ * so the graph has to outlive the plan; the persistent-launch plans of its decode runs are built at the first compute and
+ * cached in the backend like any other. */
 struct b200_graph_plan {
     struct ggml_cgraph cgraph;
-    b200_plan *plan;
 };
 
 GGML_CALL static ggml_backend_graph_plan_t b200_backend_graph_plan_create(ggml_backend_t backend, const struct ggml_cgraph *cgraph) {
-    struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
+    GGML_UNUSED(backend);
     struct b200_graph_plan *gp = (struct b200_graph_plan *)calloc(1, sizeof(*gp));
     if (!gp) return NULL;
     gp->cgraph = *cgraph;
-    const int n = bc->opt_plans ? b200_decode_graph_nodes(cgraph, NULL) : 0;
-    if (n > 0 && b200_build_plan(bc, cgraph, n, &gp->plan) < 0) {
-        free(gp);
-        return NULL;
-    }
     return (ggml_backend_graph_plan_t)gp;
 }
 
 GGML_CALL static void b200_backend_graph_plan_free(ggml_backend_t backend, ggml_backend_graph_plan_t plan) {
-    struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
-    struct b200_graph_plan *gp = (struct b200_graph_plan *)plan;
-    if (!gp) return;
-    if (gp->plan) {
-        b200_synchronize(bc->ctx);
-        b200_plan_destroy(gp->plan);
-    }
-    free(gp);
+    GGML_UNUSED(backend);
+    free(plan);
 }
 
 GGML_CALL static enum ggml_status b200_backend_graph_plan_compute(ggml_backend_t backend, ggml_backend_graph_plan_t plan) {
-    struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
     struct b200_graph_plan *gp = (struct b200_graph_plan *)plan;
-    if (!gp->plan) return b200_graph_compute_nodes(bc, &gp->cgraph);
-    const int rc = b200_plan_launch(bc->ctx, gp->plan);
-    if (rc != B200_OK) {
-        fprintf(stderr, "ggml-b200: b200_plan_launch failed (%d): %s\n", rc, b200_last_error(bc->ctx));
-        return GGML_STATUS_FAILED;
-    }
-    bc->plan_launches++;
-    return GGML_STATUS_SUCCESS;
+    return b200_backend_graph_compute(backend, &gp->cgraph);
 }
 
-static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc, struct ggml_cgraph *cgraph) {
-    for (int i = 0; i < cgraph->n_nodes; i++) {
+static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int first, int last) {
+    for (int i = first; i < last; i++) {
         struct ggml_tensor *node = cgraph->nodes[i];
         if (ggml_is_empty(node) || b200_op_is_noop(node->op)) continue;
         if (node->op == GGML_OP_MUL_MAT) {
@@ -556,12 +578,15 @@ static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc
             struct ggml_tensor *run[B200_MAX_RUN];
             int n = 0;
             run[n++] = node;
-            while (n < B200_MAX_RUN && i + 1 < cgraph->n_nodes) {
+            while (n < B200_MAX_RUN && i + 1 < last) {
                 struct ggml_tensor *next = cgraph->nodes[i + 1];
                 if (next->op != GGML_OP_MUL_MAT || next->src[1] != node->src[1] || ggml_is_empty(next)) break;
                 bool dep = false;
                 for (int j = 0; j < n; j++)
                     if (next->src[0] == run[j] || next->src[0]->view_src == run[j]) dep = true;
+                /* (a graph allocator may have given `next` the memory of an earlier result of this run: keep them apart) */
+                for (int j = 0; j < n; j++)
+                    if (next->data == run[j]->data) dep = true;
                 if (dep) break;
                 run[n++] = next;
                 i++;
@@ -606,7 +631,7 @@ GGML_CALL ggml_backend_t ggml_backend_b200_init(int device) {
     struct b200_backend_context *bc = (struct b200_backend_context *)calloc(1, sizeof(*bc));
     if (!bc) return NULL;
     bc->device = device;
-    bc->opt_plans = getenv("GGML_B200_NO_PLANS") ? 0 : 1;
+    bc->opt_plans = 1;
     snprintf(bc->name, sizeof(bc->name), "%s%d", GGML_B200_NAME, device);
     if (b200_ctx_create(device, &bc->ctx) != B200_OK) {
         fprintf(stderr, "ggml-b200: %s\n", b200_last_error(NULL));

@@ -149,6 +149,8 @@ typedef struct ref_chain {
     struct ggml_cgraph *gf;
     ggml_backend_graph_plan_t plan;
     int n_weights;
+    struct ggml_context *ctx2;     /* ref_dag_create_galloc: the compute nodes live here, allocated by ggml_gallocr */
+    ggml_gallocr_t galloc;
 } ref_chain;
 
 ref_chain *ref_chain_create(int type, int n_mats, const int *wid, int n_weights, const int64_t *wk, const int64_t *wm,
@@ -195,8 +197,10 @@ double ref_chain_compute_planned(ref_chain *h) {
 void ref_chain_free(ref_chain *h) {
     if (!h) return;
     if (h->plan) ggml_backend_graph_plan_free(h->backend, h->plan);
+    if (h->galloc) ggml_gallocr_free(h->galloc);
     ggml_backend_buffer_free(h->buf);
     ggml_backend_free(h->backend);
+    if (h->ctx2) ggml_free(h->ctx2);
     ggml_free(h->ctx);
     free(h->w);
     free(h);
@@ -232,6 +236,51 @@ ref_chain *ref_dag_create(int type, int n_nodes, const int *node_w, const int *n
     if (!h->backend) return NULL;
     h->buf = ggml_backend_alloc_ctx_tensors(h->ctx, h->backend);
     return h;
+}
+
+/*
+ * The same DAG the way the reference's examples hold a model graph (examples/gpt-2/main-backend.cpp:442-770): weights and the
+ * input in a buffer of their own (ggml_backend_alloc_ctx_tensors), the compute nodes allocated by ggml_gallocr_alloc_graph, which
+ * REUSES the memory of dead intermediates for later nodes.  Only the last node (ggml_set_output) is meaningful afterwards.
+ */
+ref_chain *ref_dag_create_galloc(int type, int n_nodes, const int *node_w, const int *node_src, int n_weights, const int64_t *wk,
+                                 const int64_t *wm, int64_t n, int n_threads) {
+    ref_init();
+    ref_chain *h = (ref_chain *)calloc(1, sizeof(ref_chain));
+    struct ggml_init_params ip = { ggml_tensor_overhead() * (size_t)(n_weights + 8), NULL, true };
+    h->ctx = ggml_init(ip);
+    h->n_weights = n_weights;
+    h->w = (struct ggml_tensor **)calloc((size_t)n_weights, sizeof(*h->w));
+    for (int j = 0; j < n_weights; j++) h->w[j] = ggml_new_tensor_2d(h->ctx, (enum ggml_type)type, wk[j], wm[j]);
+    int64_t kx = 0;
+    for (int i = 0; i < n_nodes; i++) if (node_src[i] < 0) { kx = wk[node_w[i]]; break; }
+    h->x = ggml_new_tensor_2d(h->ctx, GGML_TYPE_F32, kx, n);
+    ggml_set_input(h->x);
+    h->backend = ref_backend_new(n_threads);
+    if (!h->backend) return NULL;
+    h->buf = ggml_backend_alloc_ctx_tensors(h->ctx, h->backend);
+    struct ggml_init_params ip2 = { ggml_tensor_overhead() * (size_t)(n_nodes + 8) + ggml_graph_overhead_custom(n_nodes + n_weights + 64, false), NULL, true };
+    h->ctx2 = ggml_init(ip2);
+    struct ggml_tensor **nodes = (struct ggml_tensor **)calloc((size_t)n_nodes, sizeof(*nodes));
+    h->gf = ggml_new_graph_custom(h->ctx2, (size_t)(n_nodes + n_weights + 64), false);
+    for (int i = 0; i < n_nodes; i++) {
+        nodes[i] = ggml_mul_mat(h->ctx2, h->w[node_w[i]], node_src[i] < 0 ? h->x : nodes[node_src[i]]);
+        if (i == n_nodes - 1) ggml_set_output(nodes[i]);
+        ggml_build_forward_expand(h->gf, nodes[i]);
+    }
+    h->out = nodes[n_nodes - 1];
+    free(nodes);
+    h->galloc = ggml_gallocr_new(ggml_backend_get_default_buffer_type(h->backend));
+    if (!ggml_gallocr_alloc_graph(h->galloc, h->gf)) return NULL;
+    return h;
+}
+/* how many of the graph's nodes share their data pointer with an earlier node (what the allocator reused) */
+int ref_chain_aliased_nodes(ref_chain *h) {
+    int n = 0;
+    for (int i = 0; i < h->gf->n_nodes; i++)
+        for (int j = 0; j < i; j++)
+            if (h->gf->nodes[i]->data == h->gf->nodes[j]->data) { n++; break; }
+    return n;
 }
 
 /* any node of the last graph, by position in the cgraph (to compare intermediates between backends) */

@@ -22,6 +22,11 @@ def load(name):
     assert path.exists(), f"{path} must be prebuilt (make -C oracle ref dropin) and travel with the snapshot"
     lib = C.CDLL(str(path))
     lib.ref_dag_create.restype = vp
+    lib.ref_dag_create_galloc.restype = vp
+    lib.ref_chain_aliased_nodes.argtypes = [vp]
+    lib.ref_chain_get_out.argtypes = [vp, vp]
+    lib.ref_chain_out_elements.restype = C.c_int64
+    lib.ref_chain_out_elements.argtypes = [vp]
     lib.ref_chain_compute.restype = C.c_double
     lib.ref_chain_compute.argtypes = [vp]
     lib.ref_chain_compute_planned.restype = C.c_double
@@ -38,10 +43,10 @@ def load(name):
     return lib
 
 
-def make_graph(lib, qtype, nodes, shapes, ncols, threads=4):
+def make_graph(lib, qtype, nodes, shapes, ncols, threads=4, galloc=False):
     """nodes: [(weight id, src node or -1)], shapes: [(k, m)] per weight id"""
     n = len(nodes)
-    h = lib.ref_dag_create(qtype, n, (C.c_int * n)(*[w for w, _ in nodes]), (C.c_int * n)(*[s for _, s in nodes]), len(shapes),
+    h = (lib.ref_dag_create_galloc if galloc else lib.ref_dag_create)(qtype, n, (C.c_int * n)(*[w for w, _ in nodes]), (C.c_int * n)(*[s for _, s in nodes]), len(shapes),
                            (C.c_int64 * len(shapes))(*[k for k, _ in shapes]), (C.c_int64 * len(shapes))(*[m for _, m in shapes]),
                            C.c_int64(ncols), threads)
     assert h, "ref_dag_create failed (backend not in the registry?)"
@@ -101,6 +106,50 @@ def test_same_ggml_graph_on_cpu_backend_and_on_b200_backend(oracle, qtype, ncols
             assert plans == 3 and kernels == 3, f"decode graph should be one persistent launch per compute ({plans} plans, {kernels} kernels)"
         else:
             assert plans == 0 and kernels >= 3 * len(NODES), (plans, kernels)
+    finally:
+        cpu.ref_chain_free(hc)
+        gpu.ref_chain_free(hg)
+
+
+@pytest.mark.parametrize("qtype", [Q4_0, Q8_0])
+@pytest.mark.parametrize("ncols", [1, 3])
+def test_graph_allocated_by_gallocr_runs_as_one_plan(oracle, qtype, ncols):
+    """The compute nodes allocated by ggml_gallocr_alloc_graph (examples/gpt-2/main-backend.cpp:744), which hands the memory of
+    dead intermediates to later nodes: the decode graph must STILL go down as one persistent launch (the plan keeps the dead
+    intermediates out of plain memory) and its output must match the CPU backend's."""
+    cpu = load("libref_shim.so")
+    gpu = load("libdropin_shim.so")
+    gpu.ref_select_backend(b"B2000")
+    rng = np.random.default_rng(17 + qtype + ncols)
+    hc = make_graph(cpu, qtype, NODES, SHAPES, ncols, galloc=True)
+    hg = make_graph(gpu, qtype, NODES, SHAPES, ncols, galloc=True)
+    try:
+        assert gpu.ref_chain_aliased_nodes(hg) > 0, "the allocator was expected to reuse memory in this graph"
+        for j, (k, m) in enumerate(SHAPES):
+            w = oracle.quantize_weights(qtype, rng.uniform(-1, 1, (m, k)).astype(np.float32) * (2.0 / np.sqrt(k)))
+            cpu.ref_chain_set_weight(hc, j, w.ctypes.data_as(vp))
+            gpu.ref_chain_set_weight(hg, j, w.ctypes.data_as(vp))
+        for rep in range(3):
+            x = rng.uniform(-1, 1, (ncols, E)).astype(np.float32)
+            cpu.ref_chain_set_x(hc, x.ctypes.data_as(vp))
+            gpu.ref_chain_set_x(hg, x.ctypes.data_as(vp))
+            cpu.ref_chain_compute(hc)
+            gpu.ref_chain_compute(hg)
+            want = np.zeros(cpu.ref_chain_out_elements(hc), np.float32)
+            got = np.zeros(gpu.ref_chain_out_elements(hg), np.float32)
+            cpu.ref_chain_get_out(hc, want.ctypes.data_as(vp))
+            gpu.ref_chain_get_out(hg, got.ctypes.data_as(vp))
+            # (the whole chain on both sides: a few quantization stages deep, summation order differs -> the bar, not bit equality)
+            assert np.isfinite(got).all() and nmse(got, want) <= MUL_MAT_NMSE_TOL, f"rep {rep}: nmse {nmse(got, want)}"
+        gpu.ref_chain_plan_launches.restype = C.c_int64
+        gpu.ref_chain_plan_launches.argtypes = [vp]
+        gpu.ref_chain_kernel_launches.restype = C.c_int64
+        gpu.ref_chain_kernel_launches.argtypes = [vp]
+        plans, kernels = gpu.ref_chain_plan_launches(hg), gpu.ref_chain_kernel_launches(hg)
+        if ncols == 1:
+            assert plans == 3 and kernels == 3, f"the aliased decode graph should be one persistent launch per compute ({plans} plans, {kernels} kernels)"
+        else:
+            assert plans == 0
     finally:
         cpu.ref_chain_free(hc)
         gpu.ref_chain_free(hg)
