@@ -242,7 +242,35 @@ int b200_copy_d2d(b200_ctx *ctx, void *dst_dev, const void *src_dev, size_t size
     B200_REQUIRE(ctx, ctx != NULL, B200_ERR_INVALID);
     if (!size) return B200_OK;
     B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    B200_CUDA_TRY(ctx, cudaMemcpyAsync(dst_dev, src_dev, size, cudaMemcpyDeviceToDevice, ctx->stream));
+    B200_CUDA_TRY(ctx, cudaMemcpyAsync(dst_dev, src_dev, size, cudaMemcpyDefault, ctx->stream));
+    return B200_OK;
+}
+
+int b200_copy_2d(b200_ctx *ctx, void *dst_dev, size_t dpitch, const void *src_dev, size_t spitch, size_t width, size_t height) {
+    B200_REQUIRE(ctx, ctx != NULL, B200_ERR_INVALID);
+    if (!width || !height) return B200_OK;
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, cudaMemcpy2DAsync(dst_dev, dpitch, src_dev, spitch, width, height, cudaMemcpyDefault, ctx->stream));
+    return B200_OK;
+}
+
+int b200_enable_peer_access(b200_ctx *ctx, int peer_device) {
+    B200_REQUIRE(ctx, ctx != NULL, B200_ERR_INVALID);
+    if (peer_device == ctx->device) return B200_OK;
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int can = 0;
+    B200_CUDA_TRY(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+    if (!can) {
+        b200_set_error(ctx, "device %d cannot access device %d directly", ctx->device, peer_device);
+        return B200_ERR_UNSUPPORTED;
+    }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        b200_set_error(ctx, "cudaDeviceEnablePeerAccess(%d -> %d): %s", ctx->device, peer_device, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return B200_ERR_CUDA;
+    }
+    (void)cudaGetLastError();
     return B200_OK;
 }
 

@@ -31,6 +31,10 @@ struct b200_device_state {
     struct ggml_backend_buffer_type buft;
     bool buft_init;
     char buft_name[32];
+    /* when this device serves row slices of tensors in a split buffer (ggml_backend_b200_split_buffer_type) */
+    b200_ctx *split_ctx;                         /* its compute context */
+    void *xstage, *ystage;                       /* src1 copy / dense dst slice [n][rows] */
+    size_t xstage_size, ystage_size;
 };
 
 static struct b200_device_state g_dev[GGML_B200_MAX_DEVICES];
@@ -54,6 +58,9 @@ static b200_ctx *b200_io_ctx(int device) {
             GGML_ASSERT(!"ggml-b200 error");                                                        \
         }                                                                                           \
     } while (0)
+
+GGML_CALL bool ggml_backend_is_b200(ggml_backend_t backend);
+GGML_CALL int ggml_backend_b200_get_device_count(void);
 
 static bool b200_type_is_repacked(enum ggml_type t) { return t == GGML_TYPE_Q4_0 || t == GGML_TYPE_Q8_0; }
 static int64_t b200_wire_bytes(enum ggml_type t) { return t == GGML_TYPE_Q4_0 ? B200_Q4_0_BYTES : B200_Q8_0_BYTES; }
@@ -283,14 +290,205 @@ GGML_CALL ggml_backend_buffer_type_t ggml_backend_b200_host_buffer_type(void) {
     return &t;
 }
 
+
+/* ---- split buffer type: rows of a matrix divided across the devices of ONE process ----------------------
+ * The reference's interface for multi-GPU weights (ggml_backend_cuda_split_buffer_type, src/ggml-cuda.h:28-29; implementation
+ * src/ggml-cuda.cu:578-975): a buffer type whose tensors are not in one device's memory -- every device holds a contiguous range
+ * of rows, per-device pointers live in tensor->extra, get_base is a dummy address, views are not supported and set/get_tensor take
+ * whole tensors only (:727-790).  Same contract here; each slice is stored repacked on its device.  MUL_MAT with such a src0 runs
+ * on every device that owns rows: a decode run as one persistent row-split plan per device (tagged peer stores over NVLink, the
+ * all-gather fused into the GEMV epilogue), anything else slice by slice with the dst rows copied into place. */
+struct b200_split_buft_context {
+    float cum[GGML_B200_MAX_DEVICES + 1];        /* cumulative row fractions: device d owns rows [cum[d], cum[d+1]) * nrows */
+    int   ndev;
+    char  name[48];
+    struct ggml_backend_buffer_type buft;
+    bool  used;
+};
+struct b200_split_extra {
+    int      ndev;
+    void    *ptr[GGML_B200_MAX_DEVICES];          /* repacked slice on device d (NULL: no rows) */
+    int64_t  row0[GGML_B200_MAX_DEVICES + 1];
+};
+struct b200_split_buffer_context {
+    struct b200_split_buft_context *bt;
+    struct b200_split_extra **extras;
+    int n, cap;
+};
+#define B200_MAX_SPLIT_TYPES 8
+static struct b200_split_buft_context g_split[B200_MAX_SPLIT_TYPES];
+
+GGML_CALL static const char *b200_split_buffer_get_name(ggml_backend_buffer_t buffer) {
+    GGML_UNUSED(buffer);
+    return GGML_B200_NAME "_Split";
+}
+static bool b200_buffer_is_split(ggml_backend_buffer_t buffer) { return buffer && buffer->iface.get_name == b200_split_buffer_get_name; }
+static bool b200_tensor_is_split(const struct ggml_tensor *t) { return t && b200_buffer_is_split(t->buffer) && t->extra != NULL; }
+
+GGML_CALL static void b200_split_buffer_free(ggml_backend_buffer_t buffer) {
+    struct b200_split_buffer_context *sc = (struct b200_split_buffer_context *)buffer->context;
+    for (int i = 0; i < sc->n; i++) {
+        struct b200_split_extra *e = sc->extras[i];
+        for (int d = 0; d < e->ndev; d++)
+            if (e->ptr[d]) {
+                b200_ctx *io = b200_io_ctx(d);
+                if (io) b200_free(io, e->ptr[d]);
+            }
+        free(e);
+    }
+    free(sc->extras);
+    free(sc);
+}
+GGML_CALL static void *b200_split_buffer_get_base(ggml_backend_buffer_t buffer) {
+    GGML_UNUSED(buffer);
+    return (void *)0x1000;          /* tensors are addressed through tensor->extra (src/ggml-cuda.cu:720-725 does the same) */
+}
+GGML_CALL static void b200_split_buffer_init_tensor(ggml_backend_buffer_t buffer, struct ggml_tensor *tensor) {
+    struct b200_split_buffer_context *sc = (struct b200_split_buffer_context *)buffer->context;
+    GGML_ASSERT(tensor->view_src == NULL && "ggml-b200: views of split tensors are not supported");
+    GGML_ASSERT(b200_type_is_repacked(tensor->type) && tensor->ne[2] == 1 && tensor->ne[3] == 1 &&
+                "ggml-b200: the split buffer type holds 2-D Q4_0 / Q8_0 matrices");
+    struct b200_split_extra *e = (struct b200_split_extra *)calloc(1, sizeof(*e));
+    GGML_ASSERT(e != NULL);
+    const int64_t nrows = tensor->ne[1], nb = tensor->ne[0] / B200_QK, wire = b200_wire_bytes(tensor->type);
+    e->ndev = sc->bt->ndev;
+    for (int d = 0; d <= e->ndev; d++) e->row0[d] = d == e->ndev ? nrows : (int64_t)((double)sc->bt->cum[d] * (double)nrows);
+    for (int d = 0; d < e->ndev; d++) {
+        const int64_t rows = e->row0[d + 1] - e->row0[d];
+        if (rows <= 0) continue;
+        b200_ctx *io = b200_io_ctx(d);
+        GGML_ASSERT(io != NULL);
+        B200_CHECK(io, b200_malloc(io, &e->ptr[d], (size_t)(rows * nb * wire)));
+    }
+    if (sc->n == sc->cap) {
+        sc->cap = sc->cap ? sc->cap * 2 : 64;
+        sc->extras = (struct b200_split_extra **)realloc(sc->extras, sizeof(*sc->extras) * (size_t)sc->cap);
+        GGML_ASSERT(sc->extras != NULL);
+    }
+    sc->extras[sc->n++] = e;
+    tensor->extra = e;
+}
+GGML_CALL static void b200_split_buffer_set_tensor(ggml_backend_buffer_t buffer, struct ggml_tensor *tensor, const void *data, size_t offset, size_t size) {
+    GGML_UNUSED(buffer);
+    GGML_ASSERT(offset == 0 && size == ggml_nbytes(tensor) && "ggml-b200: split tensors are set whole (src/ggml-cuda.cu:776-778)");
+    const struct b200_split_extra *e = (const struct b200_split_extra *)tensor->extra;
+    const int64_t nb = tensor->ne[0] / B200_QK, wire = b200_wire_bytes(tensor->type);
+    for (int d = 0; d < e->ndev; d++) {
+        const int64_t rows = e->row0[d + 1] - e->row0[d];
+        if (rows <= 0) continue;
+        b200_ctx *io = b200_io_ctx(d);
+        B200_CHECK(io, b200_set_quantized(io, (int)tensor->type, e->ptr[d], rows * nb, (const char *)data + e->row0[d] * nb * wire, 0, rows * nb));
+    }
+}
+GGML_CALL static void b200_split_buffer_get_tensor(ggml_backend_buffer_t buffer, const struct ggml_tensor *tensor, void *data, size_t offset, size_t size) {
+    GGML_UNUSED(buffer);
+    GGML_ASSERT(offset == 0 && size == ggml_nbytes(tensor) && "ggml-b200: split tensors are read whole");
+    const struct b200_split_extra *e = (const struct b200_split_extra *)tensor->extra;
+    const int64_t nb = tensor->ne[0] / B200_QK, wire = b200_wire_bytes(tensor->type);
+    for (int d = 0; d < e->ndev; d++) {
+        const int64_t rows = e->row0[d + 1] - e->row0[d];
+        if (rows <= 0) continue;
+        b200_ctx *io = b200_io_ctx(d);
+        B200_CHECK(io, b200_get_quantized(io, (int)tensor->type, e->ptr[d], rows * nb, (char *)data + e->row0[d] * nb * wire, 0, rows * nb));
+    }
+}
+GGML_CALL static void b200_split_buffer_clear(ggml_backend_buffer_t buffer, uint8_t value) {
+    GGML_UNUSED(buffer);
+    GGML_UNUSED(value);
+}
+static struct ggml_backend_buffer_i b200_split_buffer_interface = {
+    /* .get_name    = */ b200_split_buffer_get_name,
+    /* .free_buffer = */ b200_split_buffer_free,
+    /* .get_base    = */ b200_split_buffer_get_base,
+    /* .init_tensor = */ b200_split_buffer_init_tensor,
+    /* .set_tensor  = */ b200_split_buffer_set_tensor,
+    /* .get_tensor  = */ b200_split_buffer_get_tensor,
+    /* .cpy_tensor  = */ NULL,
+    /* .clear       = */ b200_split_buffer_clear,
+    /* .reset       = */ NULL,
+};
+GGML_CALL static const char *b200_split_buft_get_name(ggml_backend_buffer_type_t buft) {
+    return ((struct b200_split_buft_context *)buft->context)->name;
+}
+GGML_CALL static ggml_backend_buffer_t b200_split_buft_alloc_buffer(ggml_backend_buffer_type_t buft, size_t size) {
+    struct b200_split_buffer_context *sc = (struct b200_split_buffer_context *)calloc(1, sizeof(*sc));
+    if (!sc) return NULL;
+    sc->bt = (struct b200_split_buft_context *)buft->context;
+    return ggml_backend_buffer_init(buft, b200_split_buffer_interface, sc, size);     /* memory is allocated per tensor, in init_tensor */
+}
+GGML_CALL static size_t b200_split_buft_get_alignment(ggml_backend_buffer_type_t buft) {
+    GGML_UNUSED(buft);
+    return 128;
+}
+GGML_CALL static size_t b200_split_buft_get_alloc_size(ggml_backend_buffer_type_t buft, const struct ggml_tensor *tensor) {
+    GGML_UNUSED(buft);
+    return ggml_nbytes(tensor);
+}
+GGML_CALL static bool b200_split_buft_supports_backend(ggml_backend_buffer_type_t buft, ggml_backend_t backend) {
+    GGML_UNUSED(buft);
+    return ggml_backend_is_b200(backend);
+}
+GGML_CALL static bool b200_split_buft_is_host(ggml_backend_buffer_type_t buft) {
+    GGML_UNUSED(buft);
+    return false;
+}
+
+/* tensor_split: GGML_B200_MAX_DEVICES proportions (0 = device unused), or NULL for equal shares of every visible device.  One
+ * buffer type object per distinct split (at most B200_MAX_SPLIT_TYPES); NULL when no device is visible. */
+GGML_CALL ggml_backend_buffer_type_t ggml_backend_b200_split_buffer_type(const float *tensor_split) {
+    const int ndev = ggml_backend_b200_get_device_count();
+    if (ndev <= 0) return NULL;
+    float cum[GGML_B200_MAX_DEVICES + 1];
+    double total = 0;
+    for (int d = 0; d < ndev; d++) total += tensor_split ? (tensor_split[d] > 0 ? tensor_split[d] : 0) : 1.0;
+    if (total <= 0) return NULL;
+    double run = 0;
+    for (int d = 0; d < ndev; d++) {
+        cum[d] = (float)(run / total);
+        run += tensor_split ? (tensor_split[d] > 0 ? tensor_split[d] : 0) : 1.0;
+    }
+    cum[ndev] = 1.0f;
+    for (int i = 0; i < B200_MAX_SPLIT_TYPES; i++) {
+        struct b200_split_buft_context *bt = &g_split[i];
+        if (bt->used && bt->ndev == ndev && memcmp(bt->cum, cum, sizeof(float) * (size_t)(ndev + 1)) == 0) return &bt->buft;
+        if (!bt->used) {
+            bt->used = true;
+            bt->ndev = ndev;
+            memcpy(bt->cum, cum, sizeof(float) * (size_t)(ndev + 1));
+            snprintf(bt->name, sizeof(bt->name), "%s_Split%d", GGML_B200_NAME, i);
+            bt->buft.iface.get_name = b200_split_buft_get_name;
+            bt->buft.iface.alloc_buffer = b200_split_buft_alloc_buffer;
+            bt->buft.iface.get_alignment = b200_split_buft_get_alignment;
+            bt->buft.iface.get_max_size = NULL;
+            bt->buft.iface.get_alloc_size = b200_split_buft_get_alloc_size;
+            bt->buft.iface.supports_backend = b200_split_buft_supports_backend;
+            bt->buft.iface.is_host = b200_split_buft_is_host;
+            bt->buft.context = bt;
+            return &bt->buft;
+        }
+    }
+    fprintf(stderr, "ggml-b200: more than %d distinct tensor splits\n", B200_MAX_SPLIT_TYPES);
+    return NULL;
+}
+
 /* ---- backend --------------------------------------------------------------------------------- */
 
 /* a decode plan cached for a cgraph: valid while the graph's MUL_MAT nodes keep their addresses and shapes */
 #define B200_PLAN_CACHE 4
+#define B200_MAX_XIN 8
 struct b200_cached_plan {
-    uint64_t   key;        /* hash over (src0, src1, dst addresses, shapes) of the graph's MUL_MAT nodes; 0 = empty slot */
+    uint64_t   key;        /* hash over (src0, src1, dst addresses, shapes) of the run's MUL_MAT nodes; 0 = empty slot */
     int        n_nodes;
-    b200_plan *plan;       /* NULL: this graph cannot run as a plan (remembered, so it is not analysed again) */
+    b200_plan *plan;       /* NULL: this run cannot go down as a plan (remembered, so it is not analysed again) */
+    /* a run whose weights live in a split buffer: one row-split plan per device, launched together */
+    int        ndev;                                  /* 0: single-device plan */
+    b200_plan *dplan[GGML_B200_MAX_DEVICES];
+    void      *arena[GGML_B200_MAX_DEVICES];          /* exchange arenas (tagged vectors), peer-accessible */
+    void      *scratch[GGML_B200_MAX_DEVICES];        /* devices other than the backend's: their own (partial) dst vectors */
+    void      *xin[GGML_B200_MAX_DEVICES];            /* ... and copies of the vectors that come from outside the run */
+    int        n_xin;
+    const void *xin_src[B200_MAX_XIN];
+    size_t     xin_bytes[B200_MAX_XIN], xin_off[B200_MAX_XIN];
 };
 
 struct b200_backend_context {
@@ -322,11 +520,38 @@ GGML_CALL static const char *b200_backend_name(ggml_backend_t backend) {
     return ((struct b200_backend_context *)backend->context)->name;
 }
 
+/* compute context of device d for this backend: its own on the backend's device, a per-device one elsewhere (split tensors) */
+static b200_ctx *b200_device_compute_ctx(struct b200_backend_context *bc, int d) {
+    if (d == bc->device) return bc->ctx;
+    if (d < 0 || d >= GGML_B200_MAX_DEVICES) return NULL;
+    if (g_dev[d].split_ctx == NULL && b200_ctx_create(d, &g_dev[d].split_ctx) != B200_OK) {
+        fprintf(stderr, "ggml-b200: cannot create a context on device %d: %s\n", d, b200_last_error(NULL));
+        return NULL;
+    }
+    return g_dev[d].split_ctx;
+}
+
+static void b200_cached_plan_release(struct b200_backend_context *bc, struct b200_cached_plan *slot) {
+    if (slot->plan) {
+        b200_synchronize(bc->ctx);
+        b200_plan_destroy(slot->plan);
+    }
+    for (int d = 0; d < slot->ndev; d++) {
+        b200_ctx *cd = b200_device_compute_ctx(bc, d);
+        if (!cd) continue;
+        b200_synchronize(cd);
+        if (slot->dplan[d]) b200_plan_destroy(slot->dplan[d]);
+        if (slot->arena[d]) b200_free(cd, slot->arena[d]);
+        if (slot->scratch[d]) b200_free(cd, slot->scratch[d]);
+        if (slot->xin[d]) b200_free(cd, slot->xin[d]);
+    }
+    memset(slot, 0, sizeof(*slot));
+}
+
 GGML_CALL static void b200_backend_free(ggml_backend_t backend) {
     struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
     b200_synchronize(bc->ctx);
-    for (int i = 0; i < B200_PLAN_CACHE; i++)
-        if (bc->plans[i].plan) b200_plan_destroy(bc->plans[i].plan);
+    for (int i = 0; i < B200_PLAN_CACHE; i++) b200_cached_plan_release(bc, &bc->plans[i]);
     b200_ctx_destroy(bc->ctx);
     free(bc);
     free(backend);
@@ -357,6 +582,11 @@ static bool b200_mul_mat_supported(const struct ggml_tensor *dst) {
     const struct ggml_tensor *a = dst->src[0], *b = dst->src[1];
     if (!a || !b) return false;
     if (!b200_type_is_repacked(a->type) || b->type != GGML_TYPE_F32 || dst->type != GGML_TYPE_F32) return false;
+    if (b200_buffer_is_split(a->buffer)) {
+        /* rows of src0 live on several devices: 2-D weights, one dense 2-D activation matrix */
+        return a->view_src == NULL && a->ne[2] == 1 && a->ne[3] == 1 && b->ne[2] == 1 && b->ne[3] == 1 && b->nb[0] == sizeof(float) &&
+               b->nb[1] % 16 == 0 && ggml_is_contiguous(dst) && a->ne[0] <= 131072 && (b->view_src == NULL || b->view_offs % 16 == 0);
+    }
     struct b200_qloc loc;
     if (!b200_locate_quantized(a, &loc)) return false;
     if (b->nb[0] != sizeof(float)) return false;
@@ -386,6 +616,7 @@ static bool b200_fill_mul_mat_args(struct ggml_tensor *dst, b200_mul_mat_args *a
                 a ? ggml_type_name(a->type) : "?", b ? ggml_type_name(b->type) : "?");
         return false;
     }
+    if (b200_tensor_is_split(a)) return false;          /* (handled by b200_compute_split_mul_mat / the row-split plan) */
     struct b200_qloc loc;
     b200_locate_quantized(a, &loc);
     memset(args, 0, sizeof(*args));
@@ -416,6 +647,236 @@ static enum ggml_status b200_compute_mul_mat_run(struct b200_backend_context *bc
     return GGML_STATUS_SUCCESS;
 }
 
+
+/* ---- MUL_MAT with src0 in a split buffer ------------------------------------------------------------------------ */
+
+static bool b200_reserve_dev(b200_ctx *cd, void **p, size_t *cur, size_t bytes) {
+    if (*cur >= bytes) return true;
+    if (*p) b200_free(cd, *p);
+    *p = NULL;
+    *cur = 0;
+    if (b200_malloc(cd, p, bytes + bytes / 4 + 4096) != B200_OK) return false;
+    *cur = bytes + bytes / 4 + 4096;
+    return true;
+}
+
+/* one node, any n: every device that owns rows multiplies its slice (its own stream, src1 copied over NVLink), the dst rows are
+ * copied into place on the backend's device (strided for n > 1: dst is [n][m] with m contiguous, the layout issue the reference
+ * notes at src/ggml-cuda.cu:1592-1608).  Synchronous: the reference's loop waits on per-device events the same way (:1618-1647). */
+static enum ggml_status b200_compute_split_mul_mat(struct b200_backend_context *bc, struct ggml_tensor *dst) {
+    const struct ggml_tensor *a = dst->src[0], *b = dst->src[1];
+    if (!b200_mul_mat_supported(dst) || !b200_tensor_is_split(a)) {
+        fprintf(stderr, "ggml-b200: MUL_MAT on a split tensor with an unsupported layout\n");
+        return GGML_STATUS_FAILED;
+    }
+    const struct b200_split_extra *e = (const struct b200_split_extra *)a->extra;
+    const int64_t k = a->ne[0], m = a->ne[1], n = b->ne[1], nb = k / B200_QK;
+    if (b200_synchronize(bc->ctx) != B200_OK) return GGML_STATUS_FAILED;        /* src1 is complete on the backend's device */
+    b200_ctx *used[GGML_B200_MAX_DEVICES];
+    int n_used = 0;
+    for (int d = 0; d < e->ndev; d++) {
+        const int64_t rows = e->row0[d + 1] - e->row0[d];
+        if (rows <= 0) continue;
+        b200_ctx *cd = b200_device_compute_ctx(bc, d);
+        if (!cd) return GGML_STATUS_FAILED;
+        struct b200_device_state *ds = &g_dev[d];
+        const bool local = d == bc->device;
+        const float *x = (const float *)b->data;
+        size_t nb11 = b->nb[1];
+        if (!local) {
+            if (!b200_reserve_dev(cd, &ds->xstage, &ds->xstage_size, (size_t)(n * k * 4))) return GGML_STATUS_ALLOC_FAILED;
+            if (b200_copy_2d(cd, ds->xstage, (size_t)k * 4, b->data, b->nb[1], (size_t)k * 4, (size_t)n) != B200_OK) return GGML_STATUS_FAILED;
+            x = (const float *)ds->xstage;
+            nb11 = (size_t)k * 4;
+        }
+        float *y = (float *)dst->data + e->row0[d];
+        const bool direct = local && n == 1;                                   /* a contiguous run of dst */
+        if (!direct) {
+            if (!b200_reserve_dev(cd, &ds->ystage, &ds->ystage_size, (size_t)(n * rows * 4))) return GGML_STATUS_ALLOC_FAILED;
+            y = (float *)ds->ystage;
+        }
+        b200_mul_mat_args args;
+        memset(&args, 0, sizeof(args));
+        args.type = (int32_t)a->type;
+        args.src0_dev = e->ptr[d];
+        args.src0_nblocks_total = rows * nb;
+        args.ne00 = k; args.ne01 = rows; args.ne02 = 1; args.ne03 = 1;
+        args.src1_dev = x;
+        args.ne11 = n; args.ne12 = 1; args.ne13 = 1;
+        args.nb11 = nb11; args.nb12 = nb11 * (size_t)n; args.nb13 = args.nb12;
+        args.dst_dev = y;
+        int rc = b200_mul_mat(cd, &args);
+        if (rc == B200_OK && !direct)
+            rc = b200_copy_2d(cd, (float *)dst->data + e->row0[d], (size_t)m * 4, y, (size_t)rows * 4, (size_t)rows * 4, (size_t)n);
+        if (rc != B200_OK) {
+            fprintf(stderr, "ggml-b200: split mul_mat failed on device %d (%d): %s\n", d, rc, b200_last_error(cd));
+            return rc == B200_ERR_ALLOC ? GGML_STATUS_ALLOC_FAILED : GGML_STATUS_FAILED;
+        }
+        used[n_used++] = cd;
+    }
+    for (int i = 0; i < n_used; i++)
+        if (b200_synchronize(used[i]) != B200_OK) return GGML_STATUS_FAILED;
+    return GGML_STATUS_SUCCESS;
+}
+
+/* A decode run whose weights all live in (the same kind of) split buffer: one row-split plan per device (b200_plan_create with a
+ * b200_plan_split, peer arenas addressed directly: one process, peer access instead of CUDA IPC), launched together.  The
+ * backend's device holds the real src / dst tensors; the other devices get copies of the outside inputs and scratch vectors for
+ * their partial dsts.  *built = 0 when the run cannot go this way (then node by node).  Returns 0, or -1 on a hard error. */
+static int b200_build_split_plan(struct b200_backend_context *bc, const struct ggml_cgraph *cgraph, int first, int last, int n,
+                                 struct b200_cached_plan *slot, int *built) {
+    *built = 0;
+    struct ggml_tensor **nodes = (struct ggml_tensor **)malloc(sizeof(*nodes) * (size_t)n);
+    b200_mul_mat_args *args = (b200_mul_mat_args *)malloc(sizeof(*args) * (size_t)n);
+    int64_t *row0 = (int64_t *)malloc(sizeof(int64_t) * (size_t)n), *mtot = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+    size_t *soff = (size_t *)malloc(sizeof(size_t) * (size_t)n);
+    int32_t *plain = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+    int ret = 0, k = 0, ndev = 0;
+    bool ok = nodes && args && row0 && mtot && soff && plain;
+    for (int i = first; i < last && ok; i++) {
+        struct ggml_tensor *node = cgraph->nodes[i];
+        if (ggml_is_empty(node) || b200_op_is_noop(node->op)) continue;
+        ok = k < n && b200_tensor_is_split(node->src[0]);
+        if (ok) nodes[k++] = node;
+    }
+    ok = ok && k == n;
+    if (ok) {
+        ndev = ((const struct b200_split_extra *)nodes[0]->src[0]->extra)->ndev;
+        ok = ndev >= 2 && ndev <= B200_MAX_RANKS && bc->device < ndev;
+        for (int i = 0; i < n && ok; i++) ok = ((const struct b200_split_extra *)nodes[i]->src[0]->extra)->ndev == ndev;
+    }
+    /* scratch layout (other devices), outside inputs */
+    size_t scratch_bytes = 0, xin_bytes = 0;
+    slot->n_xin = 0;
+    for (int i = 0; i < n && ok; i++) {
+        soff[i] = scratch_bytes;
+        scratch_bytes += (size_t)((nodes[i]->src[0]->ne[1] + 63) / 64 * 64) * 4;
+        const struct ggml_tensor *b = nodes[i]->src[1];
+        bool inside = false;
+        for (int j = 0; j < i; j++) inside = inside || nodes[j] == b;
+        if (!inside) {
+            int f = -1;
+            for (int x = 0; x < slot->n_xin; x++)
+                if (slot->xin_src[x] == b->data) f = x;
+            if (f < 0) {
+                ok = slot->n_xin < B200_MAX_XIN;
+                if (ok) {
+                    slot->xin_src[slot->n_xin] = b->data;
+                    slot->xin_bytes[slot->n_xin] = (size_t)b->ne[0] * 4;
+                    slot->xin_off[slot->n_xin] = xin_bytes;
+                    xin_bytes += (size_t)((b->ne[0] + 63) / 64 * 64) * 4;
+                    slot->n_xin++;
+                }
+            }
+        }
+    }
+    b200_ctx *cds[GGML_B200_MAX_DEVICES];
+    for (int d = 0; d < ndev && ok; d++) {
+        cds[d] = b200_device_compute_ctx(bc, d);
+        ok = cds[d] != NULL;
+    }
+    for (int d = 0; d < ndev && ok; d++)
+        for (int p2 = 0; p2 < ndev && ok; p2++)
+            if (p2 != d) ok = b200_enable_peer_access(cds[d], p2) == B200_OK;
+    if (ok) {
+        slot->ndev = ndev;
+        for (int r = 0; r < ndev && ok; r++) {
+            const bool is_main = r == bc->device;
+            if (!is_main) {
+                ok = b200_malloc(cds[r], &slot->scratch[r], scratch_bytes + 256) == B200_OK && b200_malloc(cds[r], &slot->xin[r], xin_bytes + 256) == B200_OK;
+                if (!ok) break;
+            }
+        }
+    }
+    /* per rank: its slices, the dataflow expressed through ITS addresses (the producer's dst address is the consumer's src1).
+     * pass 0 = the backend's device only: which results the graph keeps in plain memory (b200_plan_plain_stores: not the dead
+     * intermediates whose memory a later node reuses) and the size of the exchange arena; pass 1 = one plan per device.  Every
+     * rank carries the SAME export set: an exported op is one whose rows every rank sends to every rank. */
+    for (int pass = 0; pass < 2 && ok; pass++) {
+        for (int r = 0; r < ndev && ok; r++) {
+            const bool is_main = r == bc->device;
+            if (pass == 0 && !is_main) continue;
+            for (int i = 0; i < n; i++) {
+                const struct ggml_tensor *a = nodes[i]->src[0], *b = nodes[i]->src[1];
+                const struct b200_split_extra *e = (const struct b200_split_extra *)a->extra;
+                const int64_t rows = e->row0[r + 1] - e->row0[r], nbk = a->ne[0] / B200_QK;
+                b200_mul_mat_args *g = &args[i];
+                memset(g, 0, sizeof(*g));
+                g->type = (int32_t)a->type;
+                g->src0_dev = rows > 0 ? e->ptr[r] : (const void *)nodes;       /* (no rows: never dereferenced) */
+                g->src0_nblocks_total = rows * nbk;
+                g->ne00 = a->ne[0]; g->ne01 = rows; g->ne02 = 1; g->ne03 = 1;
+                g->ne11 = 1; g->ne12 = 1; g->ne13 = 1;
+                g->nb11 = g->nb12 = g->nb13 = (size_t)a->ne[0] * 4;
+                int prod = -1;
+                for (int j = 0; j < i; j++)
+                    if (nodes[j] == b) prod = j;
+                if (is_main) {
+                    g->src1_dev = (const float *)b->data;
+                    g->dst_dev = (float *)nodes[i]->data;
+                } else {
+                    if (prod >= 0) g->src1_dev = (const float *)((char *)slot->scratch[r] + soff[prod]);
+                    else
+                        for (int x = 0; x < slot->n_xin; x++)
+                            if (slot->xin_src[x] == b->data) g->src1_dev = (const float *)((char *)slot->xin[r] + slot->xin_off[x]);
+                    g->dst_dev = (float *)((char *)slot->scratch[r] + soff[i]);
+                }
+                row0[i] = e->row0[r];
+                mtot[i] = a->ne[1];
+            }
+            b200_plan_split sp;
+            memset(&sp, 0, sizeof(sp));
+            sp.world = ndev; sp.rank = r; sp.row0 = row0; sp.m_total = mtot;
+            if (pass == 0) {
+                if (b200_plan_plain_stores(args, n, &sp, plain) != B200_OK) { ok = false; break; }
+                plain[n - 1] = 1;                                  /* (the last op is always exported: it keeps the ranks in step) */
+                const size_t abytes = b200_plan_arena_bytes(args, n, &sp);
+                for (int d = 0; d < ndev && ok; d++)
+                    ok = b200_malloc(cds[d], &slot->arena[d], abytes) == B200_OK && b200_memset(cds[d], slot->arena[d], 0, abytes) == B200_OK;
+                continue;
+            }
+            for (int d = 0; d < ndev; d++) sp.peer_arena[d] = slot->arena[d];
+            for (int i = 0; i < n; i++)
+                if (plain[i]) args[i].flags |= B200_MM_EXPORT;
+            const int rc = b200_plan_create(cds[r], args, n, &sp, &slot->dplan[r]);
+            if (rc != B200_OK) {
+                if (rc != B200_ERR_UNSUPPORTED) {
+                    fprintf(stderr, "ggml-b200: row-split b200_plan_create failed on device %d (%d): %s\n", r, rc, b200_last_error(cds[r]));
+                    ret = -1;
+                }
+                ok = false;
+            }
+        }
+    }
+    if (ok) *built = 1;
+    free(nodes); free(args); free(row0); free(mtot); free(soff); free(plain);
+    return ret;
+}
+
+static int b200_launch_split_plan(struct b200_backend_context *bc, struct b200_cached_plan *slot) {
+    if (b200_synchronize(bc->ctx) != B200_OK) return -1;                        /* the outside inputs are complete */
+    const void *main_ptr = NULL;
+    GGML_UNUSED(main_ptr);
+    for (int d = 0; d < slot->ndev; d++) {
+        if (d == bc->device) continue;
+        b200_ctx *cd = b200_device_compute_ctx(bc, d);
+        for (int x = 0; x < slot->n_xin; x++)
+            if (b200_copy_d2d(cd, (char *)slot->xin[d] + slot->xin_off[x], slot->xin_src[x], slot->xin_bytes[x]) != B200_OK) return -1;
+    }
+    for (int d = 0; d < slot->ndev; d++) {
+        b200_ctx *cd = b200_device_compute_ctx(bc, d);
+        const int rc = b200_plan_launch(cd, slot->dplan[d]);
+        if (rc != B200_OK) {
+            fprintf(stderr, "ggml-b200: row-split plan launch failed on device %d (%d): %s\n", d, rc, b200_last_error(cd));
+            return -1;
+        }
+    }
+    int bad = 0;
+    for (int d = 0; d < slot->ndev; d++)
+        if (b200_synchronize(b200_device_compute_ctx(bc, d)) != B200_OK) bad = 1;
+    return bad ? -1 : 0;
+}
+
 static bool b200_node_is_decode_mul_mat(const struct ggml_tensor *node) {
     if (node->op != GGML_OP_MUL_MAT) return false;
     const struct ggml_tensor *a = node->src[0], *b = node->src[1];
@@ -425,15 +886,18 @@ static bool b200_node_is_decode_mul_mat(const struct ggml_tensor *node) {
 
 /* [first, last) = a maximal run of compute nodes that are all decode-shaped MUL_MATs (no-op nodes in between are skipped);
  * returns how many such nodes it holds and a hash over their addresses and shapes */
-static int b200_decode_run(const struct ggml_cgraph *cgraph, int first, int *last_out, uint64_t *key_out) {
+static int b200_decode_run(const struct ggml_cgraph *cgraph, int first, int *last_out, uint64_t *key_out, bool *split_out) {
     int n = 0, i = first;
+    bool split = false;
     uint64_t key = 1469598103934665603ull;     /* FNV-1a */
     for (; i < cgraph->n_nodes; i++) {
         struct ggml_tensor *node = cgraph->nodes[i];
         if (ggml_is_empty(node) || b200_op_is_noop(node->op)) continue;
         if (!b200_node_is_decode_mul_mat(node)) break;
         const struct ggml_tensor *a = node->src[0], *b = node->src[1];
-        const uint64_t words[6] = {(uint64_t)(uintptr_t)a->data, (uint64_t)(uintptr_t)b->data, (uint64_t)(uintptr_t)node->data,
+        if (n == 0) split = b200_tensor_is_split(a);
+        else if (split != b200_tensor_is_split(a)) break;          /* weights in a split buffer and in one device's memory do not mix in a plan */
+        const uint64_t words[6] = {(uint64_t)(uintptr_t)(split ? a->extra : a->data), (uint64_t)(uintptr_t)b->data, (uint64_t)(uintptr_t)node->data,
                                    (uint64_t)a->ne[0], (uint64_t)a->ne[1], (uint64_t)a->type};
         for (int w = 0; w < 6; w++)
             for (int sh = 0; sh < 64; sh += 8) key = (key ^ ((words[w] >> sh) & 0xff)) * 1099511628211ull;
@@ -442,6 +906,7 @@ static int b200_decode_run(const struct ggml_cgraph *cgraph, int first, int *las
     if (key == 0) key = 1;
     *last_out = i;
     if (key_out) *key_out = key;
+    if (split_out) *split_out = split;
     return n;
 }
 
@@ -481,7 +946,7 @@ static int b200_build_plan(struct b200_backend_context *bc, const struct ggml_cg
  * arranges them are fine (the plan keeps dead intermediates out of plain memory).  Returns 1 when the run was computed that
  * way, 0 when it has to go node by node, -1 on a hard error.
  */
-static int b200_try_run_as_plan(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int first, int last, int n, uint64_t key) {
+static int b200_try_run_as_plan(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int first, int last, int n, uint64_t key, bool split) {
     if (!bc->opt_plans || n < 2) return 0;
     struct b200_cached_plan *slot = NULL;
     for (int i = 0; i < B200_PLAN_CACHE; i++)
@@ -489,14 +954,26 @@ static int b200_try_run_as_plan(struct b200_backend_context *bc, struct ggml_cgr
     if (!slot) {
         slot = &bc->plans[bc->plan_next];
         bc->plan_next = (bc->plan_next + 1) % B200_PLAN_CACHE;
-        if (slot->plan) {
-            b200_synchronize(bc->ctx);
-            b200_plan_destroy(slot->plan);
-        }
+        b200_cached_plan_release(bc, slot);
         slot->key = key;
         slot->n_nodes = n;
-        slot->plan = NULL;
-        if (b200_build_plan(bc, cgraph, first, last, n, &slot->plan) < 0) return -1;
+        if (split) {
+            int built = 0;
+            const int rc = b200_build_split_plan(bc, cgraph, first, last, n, slot, &built);
+            if (!built) {
+                b200_cached_plan_release(bc, slot);        /* frees what was allocated; remember the verdict */
+                slot->key = key;
+                slot->n_nodes = n;
+            }
+            if (rc < 0) return -1;
+        } else if (b200_build_plan(bc, cgraph, first, last, n, &slot->plan) < 0) {
+            return -1;
+        }
+    }
+    if (slot->ndev > 0) {
+        if (b200_launch_split_plan(bc, slot) < 0) return -1;
+        bc->plan_launches++;
+        return 1;
     }
     if (!slot->plan) return 0;
     const int rc = b200_plan_launch(bc->ctx, slot->plan);
@@ -523,9 +1000,10 @@ GGML_CALL static enum ggml_status b200_backend_graph_compute(ggml_backend_t back
         if (ggml_is_empty(node) || b200_op_is_noop(node->op)) { i++; continue; }
         int last = i;
         uint64_t key = 0;
-        const int n = b200_decode_run(cgraph, i, &last, &key);
+        bool split = false;
+        const int n = b200_decode_run(cgraph, i, &last, &key, &split);
         if (n >= 2) {
-            const int as_plan = b200_try_run_as_plan(bc, cgraph, i, last, n, key);
+            const int as_plan = b200_try_run_as_plan(bc, cgraph, i, last, n, key, split);
             if (as_plan < 0) return GGML_STATUS_FAILED;
             if (as_plan == 0) {
                 const enum ggml_status st = b200_graph_compute_nodes(bc, cgraph, i, last);
@@ -573,6 +1051,11 @@ static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc
     for (int i = first; i < last; i++) {
         struct ggml_tensor *node = cgraph->nodes[i];
         if (ggml_is_empty(node) || b200_op_is_noop(node->op)) continue;
+        if (node->op == GGML_OP_MUL_MAT && b200_tensor_is_split(node->src[0])) {
+            const enum ggml_status st = b200_compute_split_mul_mat(bc, node);
+            if (st != GGML_STATUS_SUCCESS) return st;
+            continue;
+        }
         if (node->op == GGML_OP_MUL_MAT) {
             /* gather the run of consecutive MUL_MAT nodes that share this node's src1 and do not depend on one another */
             struct ggml_tensor *run[B200_MAX_RUN];
@@ -580,7 +1063,7 @@ static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc
             run[n++] = node;
             while (n < B200_MAX_RUN && i + 1 < last) {
                 struct ggml_tensor *next = cgraph->nodes[i + 1];
-                if (next->op != GGML_OP_MUL_MAT || next->src[1] != node->src[1] || ggml_is_empty(next)) break;
+                if (next->op != GGML_OP_MUL_MAT || next->src[1] != node->src[1] || ggml_is_empty(next) || b200_tensor_is_split(next->src[0])) break;
                 bool dep = false;
                 for (int j = 0; j < n; j++)
                     if (next->src[0] == run[j] || next->src[0]->view_src == run[j]) dep = true;
@@ -709,16 +1192,9 @@ GGML_API GGML_CALL ggml_backend_t ggml_backend_cuda_init(int device) { return gg
 GGML_API GGML_CALL bool ggml_backend_is_cuda(ggml_backend_t backend) { return ggml_backend_is_b200(backend); }
 GGML_API GGML_CALL ggml_backend_buffer_type_t ggml_backend_cuda_buffer_type(int device) { return ggml_backend_b200_buffer_type(device); }
 GGML_API GGML_CALL ggml_backend_buffer_type_t ggml_backend_cuda_host_buffer_type(void) { return ggml_backend_b200_host_buffer_type(); }
-/* src/ggml-cuda.h:28-29.  The reference splits a matrix by rows across the devices of ONE process (src/ggml-cuda.cu:578-975).
- * Here rows are split across processes, one per GPU, and the slices are exchanged by the decode plan itself
- * (b200_plan_create with a b200_plan_split, include/ggml_b200.h): there is no single-process split buffer to hand out.
- * The symbol exists so that hosts written against ggml-cuda.h link; NULL = "not available", which callers must handle
- * like any failed buffer-type lookup. */
+/* src/ggml-cuda.h:28-29: rows of a matrix split across the devices of one process */
 GGML_API GGML_CALL ggml_backend_buffer_type_t ggml_backend_cuda_split_buffer_type(const float *tensor_split) {
-    GGML_UNUSED(tensor_split);
-    fprintf(stderr, "ggml-b200: ggml_backend_cuda_split_buffer_type: row split is one process per GPU in this backend "
-                    "(b200_plan_create + b200_plan_split); no single-process split buffer type\n");
-    return NULL;
+    return ggml_backend_b200_split_buffer_type(tensor_split);
 }
 GGML_API GGML_CALL int ggml_backend_cuda_get_device_count(void) { return ggml_backend_b200_get_device_count(); }
 GGML_API GGML_CALL void ggml_backend_cuda_get_device_description(int device, char *description, size_t description_size) {

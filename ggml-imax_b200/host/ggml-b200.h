@@ -28,6 +28,9 @@ GGML_API GGML_CALL ggml_backend_t             ggml_backend_b200_init(int device)
 GGML_API GGML_CALL bool                       ggml_backend_is_b200(ggml_backend_t backend);
 GGML_API GGML_CALL ggml_backend_buffer_type_t ggml_backend_b200_buffer_type(int device);      /* device buffers */
 GGML_API GGML_CALL ggml_backend_buffer_type_t ggml_backend_b200_host_buffer_type(void);       /* pinned host   */
+/* rows of 2-D Q4_0 / Q8_0 matrices split across the devices of this process (src/ggml-cuda.h:28-29): tensor_split = proportions
+ * per device (GGML_B200_MAX_DEVICES floats) or NULL for equal shares; MUL_MAT with such a src0 runs on every device that owns rows */
+GGML_API GGML_CALL ggml_backend_buffer_type_t ggml_backend_b200_split_buffer_type(const float *tensor_split);
 GGML_API GGML_CALL int                        ggml_backend_b200_get_device_count(void);
 GGML_API GGML_CALL void                       ggml_backend_b200_get_device_description(int device, char *description, size_t description_size);
 GGML_API GGML_CALL void                       ggml_backend_b200_get_device_memory(int device, size_t *free, size_t *total);

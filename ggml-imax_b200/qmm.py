@@ -86,6 +86,8 @@ _SIGNATURES = {
     "b200_upload_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "b200_download_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "b200_copy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "b200_copy_2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]),
+    "b200_enable_peer_access": (C.c_int, [C.c_void_p, C.c_int]),
     "b200_synchronize": (C.c_int, [C.c_void_p]),
     "b200_host_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "b200_host_free": (C.c_int, [C.c_void_p]),

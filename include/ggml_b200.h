@@ -92,7 +92,13 @@ B200_API int b200_upload(b200_ctx *ctx, void *dst_dev, const void *src_host, siz
 B200_API int b200_download(b200_ctx *ctx, void *dst_host, const void *src_dev, size_t size); /* sync */
 B200_API int b200_upload_async(b200_ctx *ctx, void *dst_dev, const void *src_host, size_t size);
 B200_API int b200_download_async(b200_ctx *ctx, void *dst_host, const void *src_dev, size_t size);
-B200_API int b200_copy_d2d(b200_ctx *ctx, void *dst_dev, const void *src_dev, size_t size);  /* async */
+B200_API int b200_copy_d2d(b200_ctx *ctx, void *dst_dev, const void *src_dev, size_t size);  /* async; the two may live on different devices */
+/* `height` rows of `width` bytes, rows dpitch / spitch bytes apart (a dst slice of a row-split mul_mat with n > 1); async */
+B200_API int b200_copy_2d(b200_ctx *ctx, void *dst_dev, size_t dpitch, const void *src_dev, size_t spitch, size_t width, size_t height);
+/* let kernels and copies of this context's device address memory of `peer_device` directly (NVLink / NVSwitch peer access): what
+ * a single-process row split needs where the one-process-per-GPU path uses b200_ipc_* (the reference enables it the same way,
+ * src/ggml-cuda.cu:1313-1351).  B200_OK if already enabled. */
+B200_API int b200_enable_peer_access(b200_ctx *ctx, int peer_device);
 /* ggml_backend_i.synchronize.  Also where a persistent kernel that gave up waiting (a dead peer rank, mismatched launch
  * sequences) surfaces: B200_ERR_CUDA with the reason in b200_last_error; the results of that launch are invalid. */
 B200_API int b200_synchronize(b200_ctx *ctx);
@@ -233,7 +239,9 @@ B200_API int b200_ipc_close(b200_ctx *ctx, void *peer_ptr);
  * rank's arena over NVLink (peer_arena[r] from b200_ipc_export/import of a zero-initialised b200_malloc'ed buffer of
  * b200_plan_arena_bytes() on each rank), i.e. the all-gather is part of the GEMV epilogue.  dst_dev receives only the
  * local rows unless the op carries B200_MM_EXPORT.  The LAST op of a row-split plan must carry B200_MM_EXPORT (that is
- * also what keeps ranks within one token of each other). */
+ * also what keeps ranks within one token of each other), and EVERY rank must pass the SAME export set: an exported op is one
+ * whose rows every rank sends to every rank (a rank that exports an op its peers do not would wait for rows that never come --
+ * until the plan's timeout). */
 typedef struct b200_plan b200_plan;
 typedef struct b200_plan_split {
     int32_t        world, rank;

@@ -151,6 +151,7 @@ typedef struct ref_chain {
     int n_weights;
     struct ggml_context *ctx2;     /* ref_dag_create_galloc: the compute nodes live here, allocated by ggml_gallocr */
     ggml_gallocr_t galloc;
+    ggml_backend_buffer_t buf2;    /* ref_dag_create_split: the activations' buffer */
 } ref_chain;
 
 ref_chain *ref_chain_create(int type, int n_mats, const int *wid, int n_weights, const int64_t *wk, const int64_t *wm,
@@ -198,6 +199,7 @@ void ref_chain_free(ref_chain *h) {
     if (!h) return;
     if (h->plan) ggml_backend_graph_plan_free(h->backend, h->plan);
     if (h->galloc) ggml_gallocr_free(h->galloc);
+    if (h->buf2) ggml_backend_buffer_free(h->buf2);
     ggml_backend_buffer_free(h->buf);
     ggml_backend_free(h->backend);
     if (h->ctx2) ggml_free(h->ctx2);
@@ -288,6 +290,44 @@ int ref_chain_n_nodes(ref_chain *h) { return h->gf->n_nodes; }
 int64_t ref_chain_node_elements(ref_chain *h, int i) { return ggml_nelements(h->gf->nodes[i]); }
 void ref_chain_get_node(ref_chain *h, int i, float *out) { ggml_backend_tensor_get(h->gf->nodes[i], out, 0, ggml_nbytes(h->gf->nodes[i])); }
 #ifdef REF_SHIM_DROPIN
+/*
+ * The same DAG with the WEIGHTS in the split buffer type of the dropped-in backend (ggml_backend_cuda_split_buffer_type,
+ * src/ggml-cuda.h:28-29: rows of every matrix divided across the devices of this process, equal shares) and the activations in
+ * the backend's default buffer -- how a host written against the reference uses several GPUs (examples/gpt-2/main-sched.cpp has
+ * the per-layer variant; llama.cpp's --split-mode row is the consumer of this interface).
+ */
+#include "ggml-cuda.h"
+ref_chain *ref_dag_create_split(int type, int n_nodes, const int *node_w, const int *node_src, int n_weights, const int64_t *wk,
+                                const int64_t *wm, int64_t n, int n_threads) {
+    ref_init();
+    ggml_backend_buffer_type_t split = ggml_backend_cuda_split_buffer_type(NULL);
+    if (!split) return NULL;
+    ref_chain *h = (ref_chain *)calloc(1, sizeof(ref_chain));
+    struct ggml_init_params ip = { ggml_tensor_overhead() * (size_t)(n_weights + 8), NULL, true };
+    h->ctx = ggml_init(ip);
+    h->n_weights = n_weights;
+    h->w = (struct ggml_tensor **)calloc((size_t)n_weights, sizeof(*h->w));
+    for (int j = 0; j < n_weights; j++) h->w[j] = ggml_new_tensor_2d(h->ctx, (enum ggml_type)type, wk[j], wm[j]);
+    h->backend = ref_backend_new(n_threads);
+    if (!h->backend) return NULL;
+    h->buf = ggml_backend_alloc_ctx_tensors_from_buft(h->ctx, split);
+    if (!h->buf) return NULL;
+    struct ggml_init_params ip2 = { ggml_tensor_overhead() * (size_t)(n_nodes + 8) + ggml_graph_overhead_custom(n_nodes + n_weights + 64, false), NULL, true };
+    h->ctx2 = ggml_init(ip2);
+    int64_t kx = 0;
+    for (int i = 0; i < n_nodes; i++) if (node_src[i] < 0) { kx = wk[node_w[i]]; break; }
+    h->x = ggml_new_tensor_2d(h->ctx2, GGML_TYPE_F32, kx, n);
+    struct ggml_tensor **nodes = (struct ggml_tensor **)calloc((size_t)n_nodes, sizeof(*nodes));
+    h->gf = ggml_new_graph_custom(h->ctx2, (size_t)(n_nodes + n_weights + 64), false);
+    for (int i = 0; i < n_nodes; i++) {
+        nodes[i] = ggml_mul_mat(h->ctx2, h->w[node_w[i]], node_src[i] < 0 ? h->x : nodes[node_src[i]]);
+        ggml_build_forward_expand(h->gf, nodes[i]);
+    }
+    h->out = nodes[n_nodes - 1];
+    free(nodes);
+    h->buf2 = ggml_backend_alloc_ctx_tensors(h->ctx2, h->backend);
+    return h->buf2 ? h : NULL;
+}
 /* how many of the graph_compute calls on this handle's backend went down as one persistent launch (decode plan) */
 int64_t ref_chain_plan_launches(ref_chain *h) { return ggml_backend_is_b200(h->backend) ? ggml_backend_b200_plan_launch_count(h->backend) : -1; }
 int64_t ref_chain_kernel_launches(ref_chain *h) { return ggml_backend_is_b200(h->backend) ? ggml_backend_b200_launch_count(h->backend) : -1; }

@@ -152,3 +152,50 @@ def test_row_split_on_two_gpus():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert all(ret.get(r, (False, ["no result"]))[0] for r in range(2)), dict(ret)
+
+
+def test_split_buffer_type_through_the_reference_api():
+    """ggml_backend_cuda_split_buffer_type (src/ggml-cuda.h:28-29) dropped in: the weights of a ggml graph live in the split buffer
+    type (rows divided across both GPUs of this process), the graph is computed through ggml_backend_graph_compute on the B200
+    backend, and every node matches the reference CPU backend.  Decode graphs go down as ONE row-split persistent launch per
+    device; n = 3 takes the slice-by-slice path (dst rows copied into place)."""
+    import ctypes as C
+    from conftest import Oracle, nmse, MUL_MAT_NMSE_TOL, WIRE
+    from test_gpu_dropin_graph import load, make_graph, node_outputs, NODES, SHAPES, E, vp
+    oracle = Oracle()
+    cpu = load("libref_shim.so")
+    gpu = load("libdropin_shim.so")
+    gpu.ref_dag_create_split.restype = vp
+    gpu.ref_select_backend(b"B2000")
+    for qtype in (Q4_0, Q8_0):
+        for ncols in (1, 3):
+            rng = np.random.default_rng(31 + qtype + ncols)
+            hc = make_graph(cpu, qtype, NODES, SHAPES, ncols)
+            n = len(NODES)
+            hg = gpu.ref_dag_create_split(qtype, n, (C.c_int * n)(*[w for w, _ in NODES]), (C.c_int * n)(*[s for _, s in NODES]), len(SHAPES),
+                                          (C.c_int64 * len(SHAPES))(*[k for k, _ in SHAPES]), (C.c_int64 * len(SHAPES))(*[m for _, m in SHAPES]),
+                                          C.c_int64(ncols), 4)
+            assert hg, "ref_dag_create_split failed"
+            hg = vp(hg)
+            try:
+                for j, (k, m) in enumerate(SHAPES):
+                    w = oracle.quantize_weights(qtype, rng.uniform(-1, 1, (m, k)).astype(np.float32) * (2.0 / np.sqrt(k)))
+                    cpu.ref_chain_set_weight(hc, j, w.ctypes.data_as(vp))
+                    gpu.ref_chain_set_weight(hg, j, w.ctypes.data_as(vp))
+                for rep in range(3):
+                    x = rng.uniform(-1, 1, (ncols, E)).astype(np.float32)
+                    cpu.ref_chain_set_x(hc, x.ctypes.data_as(vp))
+                    gpu.ref_chain_set_x(hg, x.ctypes.data_as(vp))
+                    cpu.ref_chain_compute(hc)
+                    gpu.ref_chain_compute(hg)
+                    want, got = node_outputs(cpu, hc), node_outputs(gpu, hg)
+                    for i, (a, b) in enumerate(zip(got, want)):
+                        assert np.isfinite(a).all(), f"node {i}"
+                        assert nmse(a, b) <= MUL_MAT_NMSE_TOL, f"type {qtype} ncols {ncols} rep {rep} node {i}: nmse {nmse(a, b)}"
+                gpu.ref_chain_plan_launches.restype = C.c_int64
+                gpu.ref_chain_plan_launches.argtypes = [vp]
+                plans = gpu.ref_chain_plan_launches(hg)
+                assert plans == (3 if ncols == 1 else 0), f"decode graph on split weights: {plans} plan launches"
+            finally:
+                cpu.ref_chain_free(hc)
+                gpu.ref_chain_free(hg)
