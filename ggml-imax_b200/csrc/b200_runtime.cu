@@ -134,8 +134,8 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->ws) cudaFree(ctx->ws);
-    if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->ws && cudaFree(ctx->ws) != cudaSuccess) (void)cudaGetLastError();
+    if (ctx->stage && cudaFree(ctx->stage) != cudaSuccess) (void)cudaGetLastError();
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->abort_host) cudaFreeHost(ctx->abort_host);
     if (ctx->abort_dev) cudaFree(ctx->abort_dev);
@@ -318,7 +318,11 @@ int b200_graph_end(b200_ctx *ctx, b200_graph **out) {
         return B200_ERR_CUDA;
     }
     b200_graph *h = (b200_graph *)calloc(1, sizeof(b200_graph));
-    if (!h) return B200_ERR_ALLOC;
+    if (!h) {
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(g);
+        return B200_ERR_ALLOC;
+    }
     h->graph = g;
     h->exec = exec;
     h->device = ctx->device;
