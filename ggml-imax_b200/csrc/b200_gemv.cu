@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(kThreads) gemv_kernel(const b200_gemv_params p
 #pragma unroll
                     for (int cc = 0; cc < NCOLS; cc++)
                         if (rr == r && cc == c) v = acc[rr][cc];
-                if (row + r < p.m) dst[(int64_t)c * p.m + row + r] = v;
+                if (row + r < p.m) dst[(int64_t)c * p.m + row + r] = b200_gemv_epilogue(p, v, row + r, (int64_t)c * p.m + row + r);
             }
         }
     }

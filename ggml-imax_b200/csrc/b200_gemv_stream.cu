@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
                             for (int r = 0; r < B200_MAX_RANKS; r++)
                                 if (r < gd.world) ll_store(gd.peer_dst[r], m_ll0 + r_begin + gr, v, gd_tag);
                         } else {
-                            m_dst[(int64_t)c * m_rows + r_begin + gr] = v;
+                            m_dst[(int64_t)c * m_rows + r_begin + gr] = b200_gemv_epilogue(p, v, r_begin + gr, (int64_t)c * m_rows + r_begin + gr);
                         }
                     }
                     else part[((cpar * g.pr + pr) * kConsumerWarps + seg) * NCOLS + c] = v;   // k-split: park the partial
@@ -448,7 +448,8 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
                         for (int pr = 0; pr < B200_MAX_RANKS; pr++)
                             if (pr < gd.world) ll_store(gd.peer_dst[pr], m_ll0 + r_begin + chunk_row0 + r, v, gd_tag);
                     } else {
-                        m_dst[(int64_t)c * m_rows + r_begin + chunk_row0 + r] = v;
+                        m_dst[(int64_t)c * m_rows + r_begin + chunk_row0 + r] =
+                            b200_gemv_epilogue(p, v, r_begin + chunk_row0 + r, (int64_t)c * m_rows + r_begin + chunk_row0 + r);
                     }
                 }
                 chunk_row0 += rows_in_chunk;
@@ -646,7 +647,7 @@ bool b200_try_launch_gemv_stream_batch(b200_ctx *ctx, const b200_gemv_params *ps
     if (count < 2 || count > kMaxBatch) return false;
     for (int j = 0; j < count; j++) {
         const b200_gemv_params &p = ps[j];
-        if (p.n != 1 || p.dst_n != 1 || p.dots) return false;
+        if (p.n != 1 || p.dst_n != 1 || p.dots || p.bias || p.residual || p.act) return false;
         if ((p.gather != NULL) != (ps[0].gather != NULL)) return false;
         if (p.gather) {
             // one gather description must fit all: same group, same state, same producer to wait for, and the matrices' LL
@@ -679,7 +680,7 @@ bool b200_try_launch_gemv_stream(b200_ctx *ctx, const b200_gemv_params &p, int *
     if (p.k % 256 != 0 || p.k > 32768 || p.n < 1 || p.n > 8) return false;
     if (((uintptr_t)p.qs & 15) != 0 || ((uintptr_t)p.d & 15) != 0) return false;
     if (p.dots == NULL && p.dst_n != p.n) return false;  // column-chunked dst keeps the generic addressing
-    if (p.gather && (p.n != 1 || p.dots)) return false;
+    if (p.gather && (p.n != 1 || p.dots || p.bias || p.residual || p.act)) return false;
     StreamGeom g;
     if (!stream_geometry(p, &g)) return false;
     const bool dots = p.dots != NULL;

@@ -99,7 +99,19 @@ struct b200_gemv_params {
     int32_t       *dots;       // non-null: dump per-block int32 partials [n][m][k/32] instead of dst
     unsigned long long *trace; // non-null: this launch's [gridDim.x][8] timestamp slots
     const b200_gather *gather; // host pointer (launcher copies it into a kernel parameter); null: plain local dst
+    // optional epilogue of a plain 2-D launch (b200_mul_mat_fused): dst = act(W x + bias) + residual
+    const float   *bias;       // [m] or null
+    const float   *residual;   // dense like dst ([n][m]) or null; may be dst itself
+    int            act;        // B200_EPI_NONE / B200_EPI_GELU
 };
+
+// the epilogue the GEMV kernels apply to a finished dst element (row = weight row, idx = its index in the dense dst)
+__device__ __forceinline__ float b200_gemv_epilogue(const b200_gemv_params &p, float v, int64_t row, int64_t idx) {
+    if (p.bias) v += p.bias[row];
+    if (p.act == B200_EPI_GELU) v = 0.5f * v * (1.0f + tanhf(0.79788456080286535587989211986876f * v * (1.0f + 0.044715f * v * v)));   // src/ggml.c:1966
+    if (p.residual) v += p.residual[idx];
+    return v;
+}
 int b200_launch_gemv(b200_ctx *ctx, const b200_gemv_params &p);
 bool b200_try_launch_gemv_stream(b200_ctx *ctx, const b200_gemv_params &p, int *rc);
 bool b200_try_launch_gemv_stream_batch(b200_ctx *ctx, const b200_gemv_params *ps, int count, int *rc);

@@ -14,7 +14,7 @@ static bool use_gemm(const b200_ctx *ctx, const b200_mul_mat_args *a) {
     return a->ne11 > ctx->opt_gemv_max_n;
 }
 
-static int run_gemv_chunks(b200_ctx *ctx, const b200_mul_mat_args *a, const uint8_t *qs, const __half *d) {
+static int run_gemv_chunks(b200_ctx *ctx, const b200_mul_mat_args *a, const uint8_t *qs, const __half *d, const b200_epilogue *epi = nullptr) {
     // column chunks of <= 8; each chunk re-streams the weights (only used when the GEMM cannot serve the shape).  The generic
     // GEMV keeps the chunk's quantized columns in shared memory (k + k/32 * 8 bytes each, 200 KB in all): long rows take
     // narrower chunks, so that every shape supports_op accepts (k <= 131072) really runs.
@@ -42,6 +42,11 @@ static int run_gemv_chunks(b200_ctx *ctx, const b200_mul_mat_args *a, const uint
         // dst batch stride must stay ne11*m: tell the kernel the full n for addressing via a second field
         // (the kernel addresses dst as ((i13*ne12+i12)*n_total + c)*m + row; n_total is carried in dst_n)
         p.dst_n = a->ne11;
+        if (epi) {
+            p.bias = epi->bias_dev;
+            p.residual = epi->residual_dev;
+            p.act = epi->act;
+        }
         int rc = b200_launch_gemv(ctx, p);
         if (rc != B200_OK) return rc;
     }
@@ -131,6 +136,33 @@ int b200_mul_mat(b200_ctx *ctx, const b200_mul_mat_args *a) {
     const __half *d = (const __half *)((const uint8_t *)a->src0_dev + a->src0_nblocks_total * qsb) + a->src0_block_off;
     if (use_gemm(ctx, a)) return run_gemm(ctx, a, qs, d);
     return run_gemv_chunks(ctx, a, qs, d);
+}
+
+int b200_mul_mat_fused(b200_ctx *ctx, const b200_mul_mat_args *a, const b200_epilogue *epi) {
+    B200_REQUIRE(ctx, ctx && a, B200_ERR_INVALID);
+    if (!epi || (!epi->bias_dev && !epi->residual_dev && epi->act == B200_EPI_NONE)) return b200_mul_mat(ctx, a);
+    B200_REQUIRE(ctx, epi->act == B200_EPI_NONE || epi->act == B200_EPI_GELU, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, quant_type_ok(a->type), B200_ERR_UNSUPPORTED);
+    B200_REQUIRE(ctx, a->ne00 > 0 && a->ne00 % B200_QK == 0 && a->ne01 > 0 && a->ne11 > 0, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, a->src0_dev && a->src1_dev && a->dst_dev, B200_ERR_INVALID);
+    // one GEMV launch only: 2-D, at most 8 columns (a chunked or tensor-core mul_mat keeps its operators separate)
+    if (a->ne02 != 1 || a->ne03 != 1 || a->ne12 != 1 || a->ne13 != 1 || a->ne11 > 8 || (a->flags & B200_MM_FORCE_GEMM) ||
+        (a->ne11 > ctx->opt_gemv_max_n && !(a->flags & B200_MM_FORCE_GEMV))) {
+        b200_set_error(ctx, "b200_mul_mat_fused: not a single-launch decode shape");
+        return B200_ERR_UNSUPPORTED;
+    }
+    const size_t col_bytes = (size_t)a->ne00 + (size_t)(a->ne00 / B200_QK) * 8 + 16;
+    if ((size_t)a->ne11 * col_bytes > 200 * 1024) {
+        b200_set_error(ctx, "b200_mul_mat_fused: the columns do not fit one launch");
+        return B200_ERR_UNSUPPORTED;
+    }
+    const int64_t nblk = (a->ne00 / B200_QK) * a->ne01;
+    B200_REQUIRE(ctx, a->src0_block_off >= 0 && a->src0_block_off + nblk <= a->src0_nblocks_total, B200_ERR_INVALID);
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int qsb = b200_qs_bytes(a->type);
+    const uint8_t *qs = (const uint8_t *)a->src0_dev + a->src0_block_off * qsb;
+    const __half *d = (const __half *)((const uint8_t *)a->src0_dev + a->src0_nblocks_total * qsb) + a->src0_block_off;
+    return run_gemv_chunks(ctx, a, qs, d, epi);
 }
 
 static bool decode_params(const b200_ctx *ctx, const b200_mul_mat_args *a, b200_gemv_params *p) {

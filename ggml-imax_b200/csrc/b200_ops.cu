@@ -1,0 +1,633 @@
+// b200_ops.cu -- the operators either side of the quantized mul_mat in a GPT-2 / GPT-J decode graph, so that the
+// reference's gpt-2-backend computes its WHOLE graph on this backend (examples/gpt-2/main-backend.cpp:442-717, :768).
+//
+// Each entry point stands in for one ggml_compute_forward_* of the reference CPU backend and is checked by the reference's own
+// tests/test-backend-ops.cpp cases for that op (unmodified, against the reference CPU backend):
+//   b200_op_get_rows       ggml_compute_forward_get_rows      src/ggml.c:13049 (_q :12874 -> dequantize_row_q4_0/_q8_0, _f16, _f32)
+//   b200_op_binary         ggml_compute_forward_add_f32 / mul_f32 / div_f32     src/ggml.c:8568, :9687 (broadcast of src1 in every dim)
+//   b200_op_unary          ggml_compute_forward_unary (gelu :10960, gelu_quick, silu, relu, tanh, ...)
+//   b200_op_norm           ggml_compute_forward_norm_f32 :11353 / rms_norm_f32, optionally fused with the MUL (gain) and ADD (bias)
+//                          that follow it in every transformer block
+//   b200_op_scale          ggml_compute_forward_scale_f32 :12637
+//   b200_op_diag_mask_inf  ggml_compute_forward_diag_mask_f32 :13301
+//   b200_op_soft_max       ggml_compute_forward_soft_max_f32 :13393 (mask, scale, ALiBi max_bias), optionally fused with the SCALE
+//                          and DIAG_MASK_INF in front of it
+//   b200_op_copy           ggml_compute_forward_dup / cpy / cont :8535, :12818, :12826 (strided 4-D, F32/F16 conversions)
+//   b200_op_mul_mat_dense  ggml_compute_forward_mul_mat :11808 with F32 / F16 src0 (K*Q and V*softmax(KQ) on permuted views)
+//
+// All of them are HBM-/latency-bound glue: coalesced 128-bit accesses where the layout allows, one CTA per row for the row
+// reductions, no tensor cores.  Every kernel is safe for dst == src0 (ggml_gallocr computes these ops in place).
+#include "b200_internal.cuh"
+
+#include <math.h>
+
+namespace {
+
+struct T4 {                      // a 4-D strided tensor as the kernels see it
+    char *p;
+    int64_t ne0, ne1, ne2, ne3;
+    int64_t nb0, nb1, nb2, nb3;
+};
+
+T4 view(const b200_tensor *t) {
+    T4 v;
+    v.p = static_cast<char *>(t->data);
+    v.ne0 = t->ne[0]; v.ne1 = t->ne[1]; v.ne2 = t->ne[2]; v.ne3 = t->ne[3];
+    v.nb0 = t->nb[0]; v.nb1 = t->nb[1]; v.nb2 = t->nb[2]; v.nb3 = t->nb[3];
+    return v;
+}
+
+int64_t nelements(const b200_tensor *t) { return t->ne[0] * t->ne[1] * t->ne[2] * t->ne[3]; }
+int64_t nrows(const b200_tensor *t) { return t->ne[1] * t->ne[2] * t->ne[3]; }
+int elt_size(int type) {
+    switch (type) {
+    case B200_TYPE_F32: case B200_TYPE_I32: return 4;
+    case B200_TYPE_F16: case B200_TYPE_I16: return 2;
+    default: return 0;
+    }
+}
+bool contiguous(const b200_tensor *t) {
+    const int64_t e = elt_size(t->type);
+    return e && t->nb[0] == e && t->nb[1] == t->nb[0] * t->ne[0] && t->nb[2] == t->nb[1] * t->ne[1] && t->nb[3] == t->nb[2] * t->ne[2];
+}
+bool same_shape(const b200_tensor *a, const b200_tensor *b) {
+    return a->ne[0] == b->ne[0] && a->ne[1] == b->ne[1] && a->ne[2] == b->ne[2] && a->ne[3] == b->ne[3];
+}
+bool aligned16(const b200_tensor *t) {
+    return ((uintptr_t)t->data & 15) == 0 && t->nb[1] % 16 == 0 && t->nb[2] % 16 == 0 && t->nb[3] % 16 == 0;
+}
+int grid_for(int64_t work, int threads, int sm_count) {
+    const int64_t g = (work + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block-wide reductions over up to 32 warps; `red` = 33 floats of shared memory; every thread gets the result
+template <bool MAX> __device__ __forceinline__ float block_reduce(float v, float *red) {
+    v = MAX ? warp_max(v) : warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();                       // `red` may still be read from the previous reduction
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float w = lane < nw ? red[lane] : (MAX ? -INFINITY : 0.0f);
+        w = MAX ? warp_max(w) : warp_sum(w);
+        if (lane == 0) red[32] = w;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+// ---- GET_ROWS ---------------------------------------------------------------------------------------------------------------------
+// dst[i10, i11, i12][0..nc) = row src1[i10, i11, i12] of src0[., i11, i12]; one thread per 4 consecutive output elements.
+// Quantized rows come straight from the repacked planes: block b of the root tensor has its quants at qs + b * QSB and its scale at
+// d[b]; Q4_0 element j < 16 is the low nibble of byte j, element j + 16 the high nibble (src/ggml-quants.c:980-998).
+template <int TYPE>
+__global__ void __launch_bounds__(256) get_rows_kernel(const char *__restrict__ src0, int64_t nb01, int64_t nb02, int64_t nb03, int64_t ne01,
+                                                       const uint8_t *__restrict__ qs, const __half *__restrict__ qd, int64_t qoff,
+                                                       const char *__restrict__ rows, int64_t nb10, int64_t nb11, int64_t nb12,
+                                                       int64_t ne10, int64_t ne11, float *__restrict__ dst, int64_t nb1, int64_t nb2, int64_t nb3,
+                                                       int64_t nc, int64_t nr, int *__restrict__ bad) {
+    const int64_t nc4 = nc >> 2;
+    const int64_t total = nr * nc4;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / nc4, c = (t - r * nc4) << 2;
+        const int64_t i12 = r / (ne11 * ne10), i11 = (r - i12 * ne11 * ne10) / ne10, i10 = r - i12 * ne11 * ne10 - i11 * ne10;
+        const int64_t row = *reinterpret_cast<const int32_t *>(rows + i10 * nb10 + i11 * nb11 + i12 * nb12);
+        float4 o;
+        if (row < 0 || row >= ne01) {       // the reference would read out of bounds; report instead
+            if (bad) *bad = 1;
+            o = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (TYPE == B200_TYPE_F32) {
+            o = *reinterpret_cast<const float4 *>(src0 + row * nb01 + i11 * nb02 + i12 * nb03 + c * 4);
+        } else if (TYPE == B200_TYPE_F16) {
+            const uint2 h = *reinterpret_cast<const uint2 *>(src0 + row * nb01 + i11 * nb02 + i12 * nb03 + c * 2);
+            const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&h.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&h.y));
+            o = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+            constexpr int WIRE = TYPE == B200_TYPE_Q4_0 ? B200_Q4_0_BYTES : B200_Q8_0_BYTES;
+            const int64_t blk = qoff + (row * nb01 + i11 * nb02 + i12 * nb03) / WIRE + (c >> 5);
+            const int j = (int)(c & 31);
+            const float d = __half2float(qd[blk]);
+            if (TYPE == B200_TYPE_Q4_0) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(qs + blk * 16 + (j & 15));
+                const uint32_t n = j < 16 ? (w & 0x0F0F0F0Fu) : ((w >> 4) & 0x0F0F0F0Fu);
+                o = make_float4(((int)(n & 0xff) - 8) * d, ((int)((n >> 8) & 0xff) - 8) * d, ((int)((n >> 16) & 0xff) - 8) * d, ((int)(n >> 24) - 8) * d);
+            } else {
+                const char4 q = *reinterpret_cast<const char4 *>(qs + blk * 32 + j);
+                o = make_float4(q.x * d, q.y * d, q.z * d, q.w * d);
+            }
+        }
+        *reinterpret_cast<float4 *>(reinterpret_cast<char *>(dst) + i10 * nb1 + i11 * nb2 + i12 * nb3 + c * 4) = o;
+    }
+}
+// any nc / alignment (F32 and F16 sources only): one thread per element
+template <int TYPE>
+__global__ void __launch_bounds__(256) get_rows_scalar_kernel(const char *__restrict__ src0, int64_t nb01, int64_t nb02, int64_t nb03, int64_t ne01,
+                                                              const char *__restrict__ rows, int64_t nb10, int64_t nb11, int64_t nb12, int64_t ne10,
+                                                              int64_t ne11, char *__restrict__ dst, int64_t nb1, int64_t nb2, int64_t nb3, int64_t nc,
+                                                              int64_t nr, int *__restrict__ bad) {
+    const int64_t total = nr * nc;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / nc, c = t - r * nc;
+        const int64_t i12 = r / (ne11 * ne10), i11 = (r - i12 * ne11 * ne10) / ne10, i10 = r - i12 * ne11 * ne10 - i11 * ne10;
+        const int64_t row = *reinterpret_cast<const int32_t *>(rows + i10 * nb10 + i11 * nb11 + i12 * nb12);
+        float v = 0.f;
+        if (row < 0 || row >= ne01) {
+            if (bad) *bad = 1;
+        } else if (TYPE == B200_TYPE_F32) {
+            v = *reinterpret_cast<const float *>(src0 + row * nb01 + i11 * nb02 + i12 * nb03 + c * 4);
+        } else {
+            v = __half2float(*reinterpret_cast<const __half *>(src0 + row * nb01 + i11 * nb02 + i12 * nb03 + c * 2));
+        }
+        *reinterpret_cast<float *>(dst + i10 * nb1 + i11 * nb2 + i12 * nb3 + c * 4) = v;
+    }
+}
+
+// ---- ADD / MUL / DIV with broadcast ------------------------------------------------------------------------------------------------
+template <int OP> __device__ __forceinline__ float bin(float a, float b) { return OP == B200_OP_ADD ? a + b : (OP == B200_OP_MUL ? a * b : a / b); }
+
+// rows are dense in all three tensors and src1 covers whole rows (ne10 == ne0): float4 per thread
+template <int OP>
+__global__ void __launch_bounds__(256) binary_rows_kernel(T4 a, T4 b, T4 d) {
+    const int64_t n4 = d.ne0 >> 2;
+    const int64_t total = n4 * d.ne1 * d.ne2 * d.ne3;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = t / n4;
+        const int64_t c = (t - r * n4) << 4;     // byte offset inside the row
+        const int64_t i3 = r / (d.ne2 * d.ne1);
+        r -= i3 * d.ne2 * d.ne1;
+        const int64_t i2 = r / d.ne1, i1 = r - i2 * d.ne1;
+        const float4 x = *reinterpret_cast<const float4 *>(a.p + i3 * a.nb3 + i2 * a.nb2 + i1 * a.nb1 + c);
+        const float4 y = *reinterpret_cast<const float4 *>(b.p + (i3 % b.ne3) * b.nb3 + (i2 % b.ne2) * b.nb2 + (i1 % b.ne1) * b.nb1 + c);
+        *reinterpret_cast<float4 *>(d.p + i3 * d.nb3 + i2 * d.nb2 + i1 * d.nb1 + c) =
+            make_float4(bin<OP>(x.x, y.x), bin<OP>(x.y, y.y), bin<OP>(x.z, y.z), bin<OP>(x.w, y.w));
+    }
+}
+// anything else: one thread per element, src1 indexed modulo its extent in every dimension (ggml_can_repeat(src1, src0))
+template <int OP>
+__global__ void __launch_bounds__(256) binary_generic_kernel(T4 a, T4 b, T4 d) {
+    const int64_t total = d.ne0 * d.ne1 * d.ne2 * d.ne3;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = t / d.ne0;
+        const int64_t i0 = t - r * d.ne0;
+        const int64_t i3 = r / (d.ne2 * d.ne1);
+        r -= i3 * d.ne2 * d.ne1;
+        const int64_t i2 = r / d.ne1, i1 = r - i2 * d.ne1;
+        const float x = *reinterpret_cast<const float *>(a.p + i3 * a.nb3 + i2 * a.nb2 + i1 * a.nb1 + i0 * a.nb0);
+        const float y = *reinterpret_cast<const float *>(b.p + (i3 % b.ne3) * b.nb3 + (i2 % b.ne2) * b.nb2 + (i1 % b.ne1) * b.nb1 + (i0 % b.ne0) * b.nb0);
+        *reinterpret_cast<float *>(d.p + i3 * d.nb3 + i2 * d.nb2 + i1 * d.nb1 + i0 * d.nb0) = bin<OP>(x, y);
+    }
+}
+
+// ---- unary / scale / diag_mask_inf: contiguous elementwise --------------------------------------------------------------------------
+__device__ __forceinline__ float unary_apply(int op, float x) {
+    switch (op) {
+    case B200_UNARY_ABS: return fabsf(x);
+    case B200_UNARY_SGN: return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f);
+    case B200_UNARY_NEG: return -x;
+    case B200_UNARY_STEP: return x > 0.f ? 1.f : 0.f;
+    case B200_UNARY_TANH: return tanhf(x);
+    case B200_UNARY_ELU: return x > 0.f ? x : expm1f(x);
+    case B200_UNARY_RELU: return fmaxf(x, 0.f);
+    case B200_UNARY_SIGMOID: return 1.0f / (1.0f + expf(-x));
+    case B200_UNARY_GELU: return 0.5f * x * (1.0f + tanhf(0.79788456080286535587989211986876f * x * (1.0f + 0.044715f * x * x)));   // src/ggml.c:1966
+    case B200_UNARY_GELU_QUICK: return x * (1.0f / (1.0f + expf(-1.702f * x)));                                                  // :2000
+    case B200_UNARY_SILU: return x / (1.0f + expf(-x));
+    case B200_UNARY_HARDSWISH: return x * fminf(1.0f, fmaxf(0.0f, (x + 3.0f) / 6.0f));
+    case B200_UNARY_HARDSIGMOID: return fminf(1.0f, fmaxf(0.0f, (x + 3.0f) / 6.0f));
+    default: return x;
+    }
+}
+// MODE 0: unary(op), 1: x * s, 2: diag_mask_inf(n_past = op; nc, nr)
+template <int MODE>
+__global__ void __launch_bounds__(256) elementwise_kernel(const float *__restrict__ x, float *__restrict__ y, int64_t n, int op, float s, int64_t nc, int64_t nr) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const float v = x[t];
+        float o;
+        if (MODE == 0) o = unary_apply(op, v);
+        else if (MODE == 1) o = v * s;
+        else {
+            const int64_t r = t / nc, i = t - r * nc, j = r % nr;
+            o = i > op + j ? -INFINITY : v;
+        }
+        y[t] = o;
+    }
+}
+
+// ---- NORM / RMS_NORM (+ gain, + bias) ---------------------------------------------------------------------------------------------------
+// one CTA per row; the row is read three times (sum, squared deviations, output) from L1; writes only after the last reduction, so
+// dst == src is fine.  gain / bias: optional row vectors of ne0 floats (the MUL and ADD that follow NORM in a transformer block).
+template <bool RMS>
+__global__ void __launch_bounds__(256) norm_kernel(T4 a, T4 d, const float *__restrict__ gain, const float *__restrict__ bias, float eps) {
+    __shared__ float red[33];
+    int64_t r = blockIdx.x;
+    const int64_t i3 = r / (a.ne2 * a.ne1);
+    r -= i3 * a.ne2 * a.ne1;
+    const int64_t i2 = r / a.ne1, i1 = r - i2 * a.ne1;
+    const float *x = reinterpret_cast<const float *>(a.p + i3 * a.nb3 + i2 * a.nb2 + i1 * a.nb1);
+    float *y = reinterpret_cast<float *>(d.p + i3 * d.nb3 + i2 * d.nb2 + i1 * d.nb1);
+    const int64_t n = a.ne0;
+    float mean = 0.f;
+    if (!RMS) {
+        float s = 0.f;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+        mean = block_reduce<false>(s, red) / (float)n;
+    }
+    float s2 = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = x[i] - mean;
+        s2 += v * v;
+    }
+    const float var = block_reduce<false>(s2, red) / (float)n;
+    const float scale = 1.0f / sqrtf(var + eps);
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        float v = (x[i] - mean) * scale;
+        if (gain) v *= gain[i];
+        if (bias) v += bias[i];
+        y[i] = v;
+    }
+}
+
+// ---- SOFT_MAX (+ scale, + mask with ALiBi slope, + causal mask) ------------------------------------------------------------------------------
+// one CTA per row: w = x * scale + slope * mask[row % ne1] (and -inf where i > n_past + row % ne1 when the DIAG_MASK_INF in front was
+// folded in), y = exp(w - max) / sum.  Three passes over the row, the last one writes: in-place safe.
+template <typename MASK_T>
+__global__ void __launch_bounds__(256) soft_max_kernel(const float *__restrict__ x, float *__restrict__ y, const MASK_T *__restrict__ mask, int64_t nc,
+                                                       int64_t ne1, int64_t ne2, float scale, float max_bias, float m0, float m1, uint32_t n_head_log2,
+                                                       int n_past) {
+    __shared__ float red[33];
+    const int64_t row = blockIdx.x;
+    const int64_t i1 = row % ne1;
+    const uint32_t h = (uint32_t)((row / ne1) % ne2);
+    const float slope = max_bias > 0.0f ? (h < n_head_log2 ? powf(m0, (float)(h + 1)) : powf(m1, (float)(2 * (h - n_head_log2) + 1))) : 1.0f;
+    const float *xr = x + row * nc;
+    float *yr = y + row * nc;
+    const MASK_T *mr = mask ? mask + i1 * nc : nullptr;
+    const int64_t lim = n_past >= 0 ? (int64_t)n_past + i1 : nc;     // columns i > lim are masked out
+    auto val = [&](int64_t i) -> float {
+        if (i > lim) return -INFINITY;
+        float w = __fmul_rn(xr[i], scale);            // rounded like the SCALE kernel's result, never contracted into the subtraction below
+        if (mr) w += slope * (float)mr[i];
+        return w;
+    };
+    float mx = -INFINITY;
+    for (int64_t i = threadIdx.x; i < nc; i += blockDim.x) mx = fmaxf(mx, val(i));
+    mx = block_reduce<true>(mx, red);
+    float sum = 0.f;
+    for (int64_t i = threadIdx.x; i < nc; i += blockDim.x) {
+        const float w = val(i);
+        sum += w == -INFINITY ? 0.f : expf(w - mx);
+    }
+    sum = block_reduce<false>(sum, red);
+    const float inv = 1.0f / sum;
+    for (int64_t i = threadIdx.x; i < nc; i += blockDim.x) {
+        const float w = val(i);
+        yr[i] = w == -INFINITY ? 0.f : expf(w - mx) * inv;
+    }
+}
+
+// ---- CPY / DUP / CONT ------------------------------------------------------------------------------------------------------------------
+// element t of the flattened source goes to element t of the flattened destination (shapes may differ, ggml_cpy only needs the same
+// element count); both sides strided.  Threads run along the DESTINATION's dim 0, so stores coalesce.
+template <typename S, typename D> __device__ __forceinline__ D convert(S v);
+template <> __device__ __forceinline__ float convert<float, float>(float v) { return v; }
+template <> __device__ __forceinline__ __half convert<float, __half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ float convert<__half, float>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ __half convert<__half, __half>(__half v) { return v; }
+template <> __device__ __forceinline__ uint16_t convert<uint16_t, uint16_t>(uint16_t v) { return v; }
+template <> __device__ __forceinline__ uint32_t convert<uint32_t, uint32_t>(uint32_t v) { return v; }
+
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) copy_kernel(T4 a, T4 d, int64_t total) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = t / d.ne0;
+        const int64_t j0 = t - r * d.ne0;
+        const int64_t j3 = r / (d.ne2 * d.ne1);
+        r -= j3 * d.ne2 * d.ne1;
+        const int64_t j2 = r / d.ne1, j1 = r - j2 * d.ne1;
+        r = t / a.ne0;
+        const int64_t i0 = t - r * a.ne0;
+        const int64_t i3 = r / (a.ne2 * a.ne1);
+        r -= i3 * a.ne2 * a.ne1;
+        const int64_t i2 = r / a.ne1, i1 = r - i2 * a.ne1;
+        const S v = *reinterpret_cast<const S *>(a.p + i3 * a.nb3 + i2 * a.nb2 + i1 * a.nb1 + i0 * a.nb0);
+        *reinterpret_cast<D *>(d.p + j3 * d.nb3 + j2 * d.nb2 + j1 * d.nb1 + j0 * d.nb0) = convert<S, D>(v);
+    }
+}
+// same shape, dense rows on both sides, 16-byte aligned: 128 bits per thread
+__global__ void __launch_bounds__(256) copy_rows16_kernel(T4 a, T4 d, int64_t row_bytes) {
+    const int64_t n16 = row_bytes >> 4;
+    const int64_t total = n16 * d.ne1 * d.ne2 * d.ne3;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = t / n16;
+        const int64_t c = (t - r * n16) << 4;
+        const int64_t i3 = r / (d.ne2 * d.ne1);
+        r -= i3 * d.ne2 * d.ne1;
+        const int64_t i2 = r / d.ne1, i1 = r - i2 * d.ne1;
+        *reinterpret_cast<uint4 *>(d.p + i3 * d.nb3 + i2 * d.nb2 + i1 * d.nb1 + c) = *reinterpret_cast<const uint4 *>(a.p + i3 * a.nb3 + i2 * a.nb2 + i1 * a.nb1 + c);
+    }
+}
+
+// ---- MUL_MAT with a dense (F32 / F16) src0 -----------------------------------------------------------------------------------------------
+// dst[i3][i2][n][m] = sum_k src0[i3 / r3][i2 / r2][m][k] * src1[i3][i2][n][k]   (src/ggml.c:11808; both operands k-contiguous, any row /
+// batch strides, so permuted views of the KV cache multiply in place).  CTA = TM x TN tile of one (i2, i3) slice, k in steps of 16
+// through shared memory, RM x RN accumulators per thread, fp32 FMA.
+template <typename A, int TM, int TN, int RM, int RN>
+__global__ void __launch_bounds__((TM / RM) * (TN / RN)) mul_mat_dense_kernel(T4 a, T4 b, T4 d, int64_t r2, int64_t r3) {
+    constexpr int KT = 16;
+    constexpr int NT = (TM / RM) * (TN / RN);
+    __shared__ float As[KT][TM + 1];
+    __shared__ float Bs[KT][TN + 1];
+    const int64_t i2 = blockIdx.z % d.ne2, i3 = blockIdx.z / d.ne2;
+    const int64_t m0 = (int64_t)blockIdx.x * TM, n0 = (int64_t)blockIdx.y * TN;
+    const char *ap = a.p + (i3 / r3) * a.nb3 + (i2 / r2) * a.nb2;
+    const char *bp = b.p + i3 * b.nb3 + i2 * b.nb2;
+    const int tm = threadIdx.x % (TM / RM), tn = threadIdx.x / (TM / RM);
+    const int64_t K = a.ne0, M = a.ne1, N = b.ne1;
+    float acc[RM][RN];
+#pragma unroll
+    for (int i = 0; i < RM; i++)
+#pragma unroll
+        for (int j = 0; j < RN; j++) acc[i][j] = 0.f;
+    for (int64_t k0 = 0; k0 < K; k0 += KT) {
+        for (int e = threadIdx.x; e < TM * KT; e += NT) {
+            const int kk = e % KT, mm = e / KT;
+            float v = 0.f;
+            if (m0 + mm < M && k0 + kk < K) {
+                const A *row = reinterpret_cast<const A *>(ap + (m0 + mm) * a.nb1);
+                v = (float)row[k0 + kk];
+            }
+            As[kk][mm] = v;
+        }
+        for (int e = threadIdx.x; e < TN * KT; e += NT) {
+            const int kk = e % KT, nn = e / KT;
+            float v = 0.f;
+            if (n0 + nn < N && k0 + kk < K) v = reinterpret_cast<const float *>(bp + (n0 + nn) * b.nb1)[k0 + kk];
+            Bs[kk][nn] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < KT; kk++) {
+            float av[RM], bv[RN];
+#pragma unroll
+            for (int i = 0; i < RM; i++) av[i] = As[kk][tm + i * (TM / RM)];
+#pragma unroll
+            for (int j = 0; j < RN; j++) bv[j] = Bs[kk][tn + j * (TN / RN)];
+#pragma unroll
+            for (int i = 0; i < RM; i++)
+#pragma unroll
+                for (int j = 0; j < RN; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    char *dp = d.p + i3 * d.nb3 + i2 * d.nb2;
+#pragma unroll
+    for (int j = 0; j < RN; j++) {
+        const int64_t n = n0 + tn + j * (TN / RN);
+        if (n >= N) continue;
+#pragma unroll
+        for (int i = 0; i < RM; i++) {
+            const int64_t m = m0 + tm + i * (TM / RM);
+            if (m < M) reinterpret_cast<float *>(dp + n * d.nb1)[m] = acc[i][j];
+        }
+    }
+}
+
+int finish(b200_ctx *ctx, const char *what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        b200_set_error(ctx, "%s launch failed: %s", what, cudaGetErrorString(e));
+        return B200_ERR_CUDA;
+    }
+    ctx->launches++;
+    return B200_OK;
+}
+
+}  // namespace
+
+#define OPS_ENTER(ctx)                                                       \
+    if (!(ctx)) return B200_ERR_INVALID;                                     \
+    B200_CUDA_TRY((ctx), cudaSetDevice((ctx)->device))
+
+extern "C" {
+
+int b200_op_get_rows(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *rows, const b200_tensor *dst) {
+    OPS_ENTER(ctx);
+    B200_REQUIRE(ctx, src0 && rows && dst, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, rows->type == B200_TYPE_I32 && dst->type == B200_TYPE_F32, B200_ERR_UNSUPPORTED);
+    B200_REQUIRE(ctx, dst->ne[0] == src0->ne[0] && dst->ne[1] == rows->ne[0] && dst->ne[2] == rows->ne[1] && dst->ne[3] == rows->ne[2], B200_ERR_INVALID);
+    B200_REQUIRE(ctx, src0->ne[2] == rows->ne[1] && rows->ne[3] == 1 && dst->nb[0] == 4, B200_ERR_INVALID);
+    const int64_t nc = src0->ne[0], nr = nelements(rows);
+    if (nc == 0 || nr == 0) return B200_OK;
+    const T4 r = view(rows), d = view(dst), a = view(src0);
+    const bool quant = src0->type == B200_TYPE_Q4_0 || src0->type == B200_TYPE_Q8_0;
+    if (quant) {
+        const int wire = b200_wire_bytes(src0->type);
+        B200_REQUIRE(ctx, nc % B200_QK == 0 && src0->nb[0] == wire && src0->nb[1] % wire == 0 && src0->nb[2] % wire == 0 && src0->nb[3] % wire == 0, B200_ERR_UNSUPPORTED);
+        B200_REQUIRE(ctx, aligned16(dst) && src0->q_total_blocks > 0, B200_ERR_UNSUPPORTED);
+        const uint8_t *qs = static_cast<const uint8_t *>(src0->data);
+        const __half *qd = reinterpret_cast<const __half *>(qs + src0->q_total_blocks * b200_qs_bytes(src0->type));
+        const int grid = grid_for(nr * (nc / 4), 256, ctx->sm_count);
+        if (src0->type == B200_TYPE_Q4_0)
+            get_rows_kernel<B200_TYPE_Q4_0><<<grid, 256, 0, ctx->stream>>>(nullptr, a.nb1, a.nb2, a.nb3, a.ne1, qs, qd, src0->q_block_off, r.p, r.nb0, r.nb1, r.nb2,
+                                                                         r.ne0, r.ne1, reinterpret_cast<float *>(d.p), d.nb1, d.nb2, d.nb3, nc, nr, nullptr);
+        else
+            get_rows_kernel<B200_TYPE_Q8_0><<<grid, 256, 0, ctx->stream>>>(nullptr, a.nb1, a.nb2, a.nb3, a.ne1, qs, qd, src0->q_block_off, r.p, r.nb0, r.nb1, r.nb2,
+                                                                         r.ne0, r.ne1, reinterpret_cast<float *>(d.p), d.nb1, d.nb2, d.nb3, nc, nr, nullptr);
+        return finish(ctx, "get_rows");
+    }
+    B200_REQUIRE(ctx, src0->type == B200_TYPE_F32 || src0->type == B200_TYPE_F16, B200_ERR_UNSUPPORTED);
+    B200_REQUIRE(ctx, src0->nb[0] == elt_size(src0->type), B200_ERR_UNSUPPORTED);
+    const bool vec = nc % 4 == 0 && aligned16(dst) && ((uintptr_t)src0->data & 15) == 0;
+    if (vec && src0->type == B200_TYPE_F32 && aligned16(src0)) {
+        get_rows_kernel<B200_TYPE_F32><<<grid_for(nr * (nc / 4), 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+            a.p, a.nb1, a.nb2, a.nb3, a.ne1, nullptr, nullptr, 0, r.p, r.nb0, r.nb1, r.nb2, r.ne0, r.ne1, reinterpret_cast<float *>(d.p), d.nb1, d.nb2, d.nb3, nc, nr, nullptr);
+    } else if (vec && src0->type == B200_TYPE_F16 && src0->nb[1] % 8 == 0 && src0->nb[2] % 8 == 0 && src0->nb[3] % 8 == 0) {
+        get_rows_kernel<B200_TYPE_F16><<<grid_for(nr * (nc / 4), 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+            a.p, a.nb1, a.nb2, a.nb3, a.ne1, nullptr, nullptr, 0, r.p, r.nb0, r.nb1, r.nb2, r.ne0, r.ne1, reinterpret_cast<float *>(d.p), d.nb1, d.nb2, d.nb3, nc, nr, nullptr);
+    } else if (src0->type == B200_TYPE_F32) {
+        get_rows_scalar_kernel<B200_TYPE_F32><<<grid_for(nr * nc, 256, ctx->sm_count), 256, 0, ctx->stream>>>(a.p, a.nb1, a.nb2, a.nb3, a.ne1, r.p, r.nb0, r.nb1, r.nb2,
+                                                                                                          r.ne0, r.ne1, d.p, d.nb1, d.nb2, d.nb3, nc, nr, nullptr);
+    } else {
+        get_rows_scalar_kernel<B200_TYPE_F16><<<grid_for(nr * nc, 256, ctx->sm_count), 256, 0, ctx->stream>>>(a.p, a.nb1, a.nb2, a.nb3, a.ne1, r.p, r.nb0, r.nb1, r.nb2,
+                                                                                                          r.ne0, r.ne1, d.p, d.nb1, d.nb2, d.nb3, nc, nr, nullptr);
+    }
+    return finish(ctx, "get_rows");
+}
+
+int b200_op_binary(b200_ctx *ctx, int op, const b200_tensor *src0, const b200_tensor *src1, const b200_tensor *dst) {
+    OPS_ENTER(ctx);
+    B200_REQUIRE(ctx, src0 && src1 && dst, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, op == B200_OP_ADD || op == B200_OP_MUL || op == B200_OP_DIV, B200_ERR_UNSUPPORTED);
+    B200_REQUIRE(ctx, src0->type == B200_TYPE_F32 && src1->type == B200_TYPE_F32 && dst->type == B200_TYPE_F32, B200_ERR_UNSUPPORTED);
+    B200_REQUIRE(ctx, same_shape(src0, dst), B200_ERR_INVALID);
+    for (int i = 0; i < 4; i++) B200_REQUIRE(ctx, src1->ne[i] > 0 && dst->ne[i] % src1->ne[i] == 0, B200_ERR_INVALID);   // ggml_can_repeat(src1, src0)
+    const int64_t n = nelements(dst);
+    if (n == 0) return B200_OK;
+    const T4 a = view(src0), b = view(src1), d = view(dst);
+    const bool rows = src1->ne[0] == dst->ne[0] && dst->ne[0] % 4 == 0 && src0->nb[0] == 4 && src1->nb[0] == 4 && dst->nb[0] == 4 && aligned16(src0) &&
+                      aligned16(src1) && aligned16(dst);
+    const int grid = grid_for(rows ? n / 4 : n, 256, ctx->sm_count);
+#define B200_BIN(OP)                                                                          \
+    if (rows) binary_rows_kernel<OP><<<grid, 256, 0, ctx->stream>>>(a, b, d);                 \
+    else binary_generic_kernel<OP><<<grid, 256, 0, ctx->stream>>>(a, b, d)
+    if (op == B200_OP_ADD) { B200_BIN(B200_OP_ADD); }
+    else if (op == B200_OP_MUL) { B200_BIN(B200_OP_MUL); }
+    else { B200_BIN(B200_OP_DIV); }
+#undef B200_BIN
+    return finish(ctx, "binary");
+}
+
+static int elementwise(b200_ctx *ctx, int mode, const b200_tensor *src0, const b200_tensor *dst, int op, float s) {
+    B200_REQUIRE(ctx, src0 && dst, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, src0->type == B200_TYPE_F32 && dst->type == B200_TYPE_F32, B200_ERR_UNSUPPORTED);
+    B200_REQUIRE(ctx, same_shape(src0, dst), B200_ERR_INVALID);
+    B200_REQUIRE(ctx, contiguous(src0) && contiguous(dst), B200_ERR_UNSUPPORTED);
+    const int64_t n = nelements(dst);
+    if (n == 0) return B200_OK;
+    const float *x = static_cast<const float *>(src0->data);
+    float *y = static_cast<float *>(dst->data);
+    const int grid = grid_for(n, 256, ctx->sm_count);
+    if (mode == 0) elementwise_kernel<0><<<grid, 256, 0, ctx->stream>>>(x, y, n, op, s, src0->ne[0], src0->ne[1]);
+    else if (mode == 1) elementwise_kernel<1><<<grid, 256, 0, ctx->stream>>>(x, y, n, op, s, src0->ne[0], src0->ne[1]);
+    else elementwise_kernel<2><<<grid, 256, 0, ctx->stream>>>(x, y, n, op, s, src0->ne[0], src0->ne[1]);
+    return finish(ctx, "elementwise");
+}
+
+int b200_op_unary(b200_ctx *ctx, int op, const b200_tensor *src0, const b200_tensor *dst) {
+    OPS_ENTER(ctx);
+    B200_REQUIRE(ctx, op >= 0 && op < B200_UNARY_COUNT, B200_ERR_UNSUPPORTED);
+    return elementwise(ctx, 0, src0, dst, op, 0.f);
+}
+int b200_op_scale(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *dst, float s) {
+    OPS_ENTER(ctx);
+    return elementwise(ctx, 1, src0, dst, 0, s);
+}
+int b200_op_diag_mask_inf(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *dst, int n_past) {
+    OPS_ENTER(ctx);
+    B200_REQUIRE(ctx, n_past >= 0, B200_ERR_INVALID);
+    return elementwise(ctx, 2, src0, dst, n_past, 0.f);
+}
+
+int b200_op_norm(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *gain, const b200_tensor *bias, const b200_tensor *dst, float eps, int rms) {
+    OPS_ENTER(ctx);
+    B200_REQUIRE(ctx, src0 && dst, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, src0->type == B200_TYPE_F32 && dst->type == B200_TYPE_F32, B200_ERR_UNSUPPORTED);
+    B200_REQUIRE(ctx, same_shape(src0, dst) && src0->nb[0] == 4 && dst->nb[0] == 4, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, rms ? eps >= 0.0f : eps > 0.0f, B200_ERR_INVALID);
+    for (const b200_tensor *v : {gain, bias})
+        if (v) B200_REQUIRE(ctx, v->type == B200_TYPE_F32 && v->ne[0] == src0->ne[0] && v->ne[1] * v->ne[2] * v->ne[3] == 1 && v->nb[0] == 4, B200_ERR_UNSUPPORTED);
+    const int64_t nr = nrows(src0);
+    if (nr == 0 || src0->ne[0] == 0) return B200_OK;
+    B200_REQUIRE(ctx, nr < (1ll << 31), B200_ERR_UNSUPPORTED);
+    const int threads = src0->ne[0] <= 64 ? 32 : (src0->ne[0] <= 256 ? 64 : (src0->ne[0] <= 1024 ? 128 : 256));
+    const float *g = gain ? static_cast<const float *>(gain->data) : nullptr, *b = bias ? static_cast<const float *>(bias->data) : nullptr;
+    if (rms) norm_kernel<true><<<(unsigned)nr, threads, 0, ctx->stream>>>(view(src0), view(dst), g, b, eps);
+    else norm_kernel<false><<<(unsigned)nr, threads, 0, ctx->stream>>>(view(src0), view(dst), g, b, eps);
+    return finish(ctx, "norm");
+}
+
+int b200_op_soft_max(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *mask, const b200_tensor *dst, float scale, float max_bias, int n_past) {
+    OPS_ENTER(ctx);
+    B200_REQUIRE(ctx, src0 && dst, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, src0->type == B200_TYPE_F32 && dst->type == B200_TYPE_F32, B200_ERR_UNSUPPORTED);
+    B200_REQUIRE(ctx, same_shape(src0, dst), B200_ERR_INVALID);
+    B200_REQUIRE(ctx, contiguous(src0) && contiguous(dst), B200_ERR_UNSUPPORTED);
+    if (mask) {
+        B200_REQUIRE(ctx, (mask->type == B200_TYPE_F32 || mask->type == B200_TYPE_F16) && contiguous(mask), B200_ERR_UNSUPPORTED);
+        B200_REQUIRE(ctx, mask->ne[0] == src0->ne[0] && mask->ne[1] >= src0->ne[1], B200_ERR_INVALID);
+    }
+    const int64_t nr = nrows(src0), nc = src0->ne[0];
+    if (nr == 0 || nc == 0) return B200_OK;
+    B200_REQUIRE(ctx, nr < (1ll << 31), B200_ERR_UNSUPPORTED);
+    const uint32_t n_head = (uint32_t)src0->ne[2];
+    const uint32_t n_head_log2 = 1u << (uint32_t)floor(log2((double)n_head));
+    const float m0 = powf(2.0f, -(max_bias) / n_head_log2), m1 = powf(2.0f, -(max_bias / 2.0f) / n_head_log2);      // src/ggml.c:13426-13430
+    const int threads = nc <= 32 ? 32 : (nc <= 128 ? 64 : (nc <= 1024 ? 128 : 256));
+    const float *x = static_cast<const float *>(src0->data);
+    float *y = static_cast<float *>(dst->data);
+    if (mask && mask->type == B200_TYPE_F16)
+        soft_max_kernel<__half><<<(unsigned)nr, threads, 0, ctx->stream>>>(x, y, static_cast<const __half *>(mask->data), nc, src0->ne[1], src0->ne[2], scale, max_bias,
+                                                                          m0, m1, n_head_log2, n_past);
+    else
+        soft_max_kernel<float><<<(unsigned)nr, threads, 0, ctx->stream>>>(x, y, mask ? static_cast<const float *>(mask->data) : nullptr, nc, src0->ne[1], src0->ne[2],
+                                                                         scale, max_bias, m0, m1, n_head_log2, n_past);
+    return finish(ctx, "soft_max");
+}
+
+int b200_op_copy(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *dst) {
+    OPS_ENTER(ctx);
+    B200_REQUIRE(ctx, src0 && dst, B200_ERR_INVALID);
+    const int64_t n = nelements(src0);
+    B200_REQUIRE(ctx, n == nelements(dst), B200_ERR_INVALID);
+    const int es = elt_size(src0->type), ed = elt_size(dst->type);
+    B200_REQUIRE(ctx, es && ed, B200_ERR_UNSUPPORTED);
+    const bool fp_s = src0->type == B200_TYPE_F32 || src0->type == B200_TYPE_F16, fp_d = dst->type == B200_TYPE_F32 || dst->type == B200_TYPE_F16;
+    B200_REQUIRE(ctx, src0->type == dst->type || (fp_s && fp_d), B200_ERR_UNSUPPORTED);
+    if (n == 0) return B200_OK;
+    if (src0->data == dst->data && src0->type == dst->type && contiguous(src0) && contiguous(dst)) return B200_OK;
+    const T4 a = view(src0), d = view(dst);
+    if (src0->type == dst->type) {
+        if (contiguous(src0) && contiguous(dst)) {
+            B200_CUDA_TRY(ctx, cudaMemcpyAsync(dst->data, src0->data, (size_t)n * es, cudaMemcpyDeviceToDevice, ctx->stream));
+            ctx->launches++;
+            return B200_OK;
+        }
+        const int64_t row_bytes = src0->ne[0] * es;
+        if (same_shape(src0, dst) && src0->nb[0] == es && dst->nb[0] == es && row_bytes % 16 == 0 && aligned16(src0) && aligned16(dst)) {
+            copy_rows16_kernel<<<grid_for(n * es / 16, 256, ctx->sm_count), 256, 0, ctx->stream>>>(a, d, row_bytes);
+            return finish(ctx, "copy");
+        }
+    }
+    const int grid = grid_for(n, 256, ctx->sm_count);
+    if (src0->type == dst->type && es == 4) copy_kernel<uint32_t, uint32_t><<<grid, 256, 0, ctx->stream>>>(a, d, n);
+    else if (src0->type == dst->type) copy_kernel<uint16_t, uint16_t><<<grid, 256, 0, ctx->stream>>>(a, d, n);
+    else if (src0->type == B200_TYPE_F32) copy_kernel<float, __half><<<grid, 256, 0, ctx->stream>>>(a, d, n);
+    else copy_kernel<__half, float><<<grid, 256, 0, ctx->stream>>>(a, d, n);
+    return finish(ctx, "copy");
+}
+
+int b200_op_mul_mat_dense(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *src1, const b200_tensor *dst) {
+    OPS_ENTER(ctx);
+    B200_REQUIRE(ctx, src0 && src1 && dst, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, (src0->type == B200_TYPE_F32 || src0->type == B200_TYPE_F16) && src1->type == B200_TYPE_F32 && dst->type == B200_TYPE_F32, B200_ERR_UNSUPPORTED);
+    B200_REQUIRE(ctx, src0->ne[0] == src1->ne[0] && dst->ne[0] == src0->ne[1] && dst->ne[1] == src1->ne[1] && dst->ne[2] == src1->ne[2] && dst->ne[3] == src1->ne[3],
+                 B200_ERR_INVALID);                                                                                   // ggml_can_mul_mat + the dst shape
+    B200_REQUIRE(ctx, src0->ne[2] > 0 && src0->ne[3] > 0 && src1->ne[2] % src0->ne[2] == 0 && src1->ne[3] % src0->ne[3] == 0, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, src0->nb[0] == elt_size(src0->type) && src1->nb[0] == 4 && dst->nb[0] == 4, B200_ERR_UNSUPPORTED);
+    if (nelements(dst) == 0) return B200_OK;
+    const int64_t M = src0->ne[1], N = src1->ne[1], batch = dst->ne[2] * dst->ne[3];
+    B200_REQUIRE(ctx, batch <= 65535, B200_ERR_UNSUPPORTED);
+    const T4 a = view(src0), b = view(src1), d = view(dst);
+    const int64_t r2 = src1->ne[2] / src0->ne[2], r3 = src1->ne[3] / src0->ne[3];
+    if (src0->ne[0] == 0) {                      // empty contraction: zeros
+        for (int64_t i3 = 0; i3 < dst->ne[3]; i3++)
+            for (int64_t i2 = 0; i2 < dst->ne[2]; i2++)
+                for (int64_t i1 = 0; i1 < dst->ne[1]; i1++)
+                    B200_CUDA_TRY(ctx, cudaMemsetAsync(d.p + i3 * d.nb3 + i2 * d.nb2 + i1 * d.nb1, 0, (size_t)M * 4, ctx->stream));
+        return B200_OK;
+    }
+    if (N <= 8) {
+        const dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 7) / 8), (unsigned)batch);
+        if (src0->type == B200_TYPE_F32) mul_mat_dense_kernel<float, 64, 8, 2, 1><<<grid, 256, 0, ctx->stream>>>(a, b, d, r2, r3);
+        else mul_mat_dense_kernel<__half, 64, 8, 2, 1><<<grid, 256, 0, ctx->stream>>>(a, b, d, r2, r3);
+    } else {
+        const dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64), (unsigned)batch);
+        if (src0->type == B200_TYPE_F32) mul_mat_dense_kernel<float, 64, 64, 4, 4><<<grid, 256, 0, ctx->stream>>>(a, b, d, r2, r3);
+        else mul_mat_dense_kernel<__half, 64, 64, 4, 4><<<grid, 256, 0, ctx->stream>>>(a, b, d, r2, r3);
+    }
+    return finish(ctx, "mul_mat_dense");
+}
+
+}  // extern "C"

@@ -4,7 +4,9 @@
  * (src/ggml-backend-impl.h:18-28 buffer type, :38-48 buffer, :78-117 backend) and registers through
  * ggml_backend_register (:135-137).  Written against the SPI, not derived from src/ggml-cuda.cu.
  *
- * Scope: GGML_OP_MUL_MAT with src0 in {Q4_0, Q8_0}, src1 F32, dst F32.  Everything
+ * Scope: GGML_OP_MUL_MAT with src0 in {Q4_0, Q8_0}, src1 F32, dst F32, plus the operators either side
+ * of it in a GPT-2 / GPT-J graph (GET_ROWS, ADD/MUL/DIV, NORM/RMS_NORM, SCALE, DIAG_MASK_INF, SOFT_MAX, UNARY,
+ * CPY/DUP/CONT, MUL_MAT with an F32/F16 src0) so that examples/gpt-2/main-backend.cpp computes its whole graph here.  Everything
  * else is reported through supports_op == false; graph_compute fails loudly on an unsupported node.
  * There is NO CPU fallback in here.
  *
@@ -498,7 +500,9 @@ struct b200_backend_context {
     struct b200_cached_plan plans[B200_PLAN_CACHE];
     int       plan_next;   /* round-robin eviction */
     int       opt_plans;   /* 0: never build decode plans (ggml_backend_b200_set_option "plans") */
+    int       opt_fuse;    /* 0: one kernel per glue node (ggml_backend_b200_set_option "fuse") */
     int64_t   plan_launches;
+    int64_t   fused_nodes; /* graph nodes that did not need a launch of their own */
     int       failed;      /* an asynchronous error surfaced in synchronize (which cannot return one): the next graph_compute reports it */
 };
 
@@ -602,11 +606,249 @@ static bool b200_mul_mat_supported(const struct ggml_tensor *dst) {
     return true;
 }
 
+
+/* ---- the operators either side of the path (b200_ops.cu) --------------------------------------------------------------------- */
+
+_Static_assert((int)GGML_UNARY_OP_ABS == B200_UNARY_ABS && (int)GGML_UNARY_OP_GELU == B200_UNARY_GELU && (int)GGML_UNARY_OP_SILU == B200_UNARY_SILU &&
+               (int)GGML_UNARY_OP_HARDSIGMOID == B200_UNARY_HARDSIGMOID && (int)GGML_UNARY_OP_COUNT == B200_UNARY_COUNT, "unary op numbering");
+_Static_assert((int)GGML_TYPE_F16 == B200_TYPE_F16 && (int)GGML_TYPE_I16 == B200_TYPE_I16 && (int)GGML_TYPE_I32 == B200_TYPE_I32, "type numbering");
+
+static bool b200_in_device_buffer(const struct ggml_tensor *t) {
+    /* unallocated (supports_op before allocation) or in one of our plain device buffers */
+    ggml_backend_buffer_t buf = t->view_src ? t->view_src->buffer : t->buffer;
+    return buf == NULL || b200_buffer_is_ours(buf);
+}
+static bool b200_is_f32(const struct ggml_tensor *t) { return t && t->type == GGML_TYPE_F32; }
+/* ggml_can_repeat (static in src/ggml.c): every extent of `big` is a multiple of the matching extent of `small` */
+static bool b200_can_repeat(const struct ggml_tensor *small, const struct ggml_tensor *big) {
+    for (int i = 0; i < 4; i++)
+        if (small->ne[i] <= 0 || big->ne[i] % small->ne[i] != 0) return false;
+    return true;
+}
+static bool b200_views_16(const struct ggml_tensor *t) { return t->view_src == NULL || t->view_offs % 16 == 0; }
+
+/* what the kernels see of a tensor; quantized tensors are addressed through their repacked root */
+static bool b200_fill_tensor(const struct ggml_tensor *t, b200_tensor *out) {
+    memset(out, 0, sizeof(*out));
+    out->type = (int32_t)t->type;
+    for (int i = 0; i < 4; i++) {
+        out->ne[i] = t->ne[i];
+        out->nb[i] = (int64_t)t->nb[i];
+    }
+    if (b200_type_is_repacked(t->type)) {
+        const struct ggml_tensor *root = t->view_src ? t->view_src : t;
+        const int64_t wire = b200_wire_bytes(t->type);
+        const size_t offs = t->view_src ? t->view_offs : 0;
+        if (root->type != t->type || !ggml_is_contiguous(root) || offs % wire != 0) return false;
+        out->data = root->data;
+        out->q_total_blocks = ggml_nelements(root) / B200_QK;
+        out->q_block_off = (int64_t)(offs / wire);
+        return true;
+    }
+    out->data = t->data;
+    return true;
+}
+
+static bool b200_copy_supported(const struct ggml_tensor *src, const struct ggml_tensor *dst) {
+    if (!src || ggml_nelements(src) != ggml_nelements(dst)) return false;
+    const bool fs = src->type == GGML_TYPE_F32 || src->type == GGML_TYPE_F16, fd = dst->type == GGML_TYPE_F32 || dst->type == GGML_TYPE_F16;
+    if (fs && fd) return true;
+    return src->type == dst->type && (src->type == GGML_TYPE_I32 || src->type == GGML_TYPE_I16);
+}
+
+static bool b200_dense_mul_mat_supported(const struct ggml_tensor *dst) {
+    const struct ggml_tensor *a = dst->src[0], *b = dst->src[1];
+    if (!a || !b || (a->type != GGML_TYPE_F32 && a->type != GGML_TYPE_F16) || b->type != GGML_TYPE_F32 || dst->type != GGML_TYPE_F32) return false;
+    if (a->nb[0] != ggml_type_size(a->type) || b->nb[0] != sizeof(float) || dst->nb[0] != sizeof(float)) return false;
+    if (b->ne[2] % a->ne[2] != 0 || b->ne[3] % a->ne[3] != 0) return false;
+    return dst->ne[2] * dst->ne[3] <= 65535;
+}
+
+static bool b200_glue_supported_srcs(const struct ggml_tensor *op) {
+    for (int i = 0; i < GGML_MAX_SRC; i++)
+        if (op->src[i] && (!b200_in_device_buffer(op->src[i]) || b200_tensor_is_split(op->src[i]))) return false;
+    return true;
+}
+
+static bool b200_glue_supported(const struct ggml_tensor *op) {
+    const struct ggml_tensor *a = op->src[0], *b = op->src[1];
+    if (!b200_glue_supported_srcs(op)) return false;
+    switch (op->op) {
+    case GGML_OP_GET_ROWS:
+        if (!a || !b || b->type != GGML_TYPE_I32 || op->type != GGML_TYPE_F32 || op->nb[0] != sizeof(float)) return false;
+        if (b200_type_is_repacked(a->type)) {
+            const struct ggml_tensor *root = a->view_src ? a->view_src : a;
+            const size_t wire = (size_t)b200_wire_bytes(a->type);
+            return root->type == a->type && ggml_is_contiguous(root) && (a->view_src == NULL || a->view_offs % wire == 0) && a->nb[0] == wire &&
+                   a->nb[1] % wire == 0 && a->nb[2] % wire == 0 && a->nb[3] % wire == 0 && b200_views_16(op) && op->nb[1] % 16 == 0 &&
+                   op->nb[2] % 16 == 0 && op->nb[3] % 16 == 0;
+        }
+        return (a->type == GGML_TYPE_F32 || a->type == GGML_TYPE_F16) && a->nb[0] == ggml_type_size(a->type);
+    case GGML_OP_ADD:
+    case GGML_OP_MUL:
+    case GGML_OP_DIV:
+        return b200_is_f32(a) && b200_is_f32(b) && op->type == GGML_TYPE_F32 && ggml_are_same_shape(a, op) && b200_can_repeat(b, a);
+    case GGML_OP_UNARY:
+        return b200_is_f32(a) && op->type == GGML_TYPE_F32 && ggml_is_contiguous(a) && ggml_is_contiguous(op) && (int)ggml_get_unary_op(op) < B200_UNARY_COUNT;
+    case GGML_OP_NORM:
+    case GGML_OP_RMS_NORM:
+        return b200_is_f32(a) && op->type == GGML_TYPE_F32 && a->nb[0] == sizeof(float) && op->nb[0] == sizeof(float) && ggml_nrows(a) < (1ll << 31);
+    case GGML_OP_SCALE:
+    case GGML_OP_DIAG_MASK_INF:
+        return b200_is_f32(a) && op->type == GGML_TYPE_F32 && ggml_is_contiguous(a) && ggml_is_contiguous(op);
+    case GGML_OP_SOFT_MAX:
+        if (!b200_is_f32(a) || op->type != GGML_TYPE_F32 || !ggml_is_contiguous(a) || !ggml_is_contiguous(op) || ggml_nrows(a) >= (1ll << 31)) return false;
+        if (op->src[2] != NULL) return false;
+        return b == NULL || ((b->type == GGML_TYPE_F32 || b->type == GGML_TYPE_F16) && ggml_is_contiguous(b) && b->ne[0] == a->ne[0] && b->ne[1] >= a->ne[1]);
+    case GGML_OP_CPY:
+    case GGML_OP_DUP:
+    case GGML_OP_CONT:
+        return b200_copy_supported(a, op);
+    default:
+        return false;
+    }
+}
+
+static enum ggml_status b200_glue_status(struct b200_backend_context *bc, const struct ggml_tensor *node, int rc);
+static bool b200_fill_mul_mat_args(struct ggml_tensor *dst, b200_mul_mat_args *args);
+
+/* one glue node (no fusion) */
+static enum ggml_status b200_compute_glue(struct b200_backend_context *bc, struct ggml_tensor *node) {
+    b200_tensor a, b, d;
+    if (!b200_glue_supported(node) && !(node->op == GGML_OP_MUL_MAT && b200_dense_mul_mat_supported(node))) {
+        fprintf(stderr, "ggml-b200: op %s (%s) is outside this backend's path (supports_op is false for it); no CPU fallback\n", ggml_op_name(node->op),
+                ggml_type_name(node->type));
+        return GGML_STATUS_FAILED;
+    }
+    if (!b200_fill_tensor(node, &d) || (node->src[0] && !b200_fill_tensor(node->src[0], &a)) || (node->src[1] && !b200_fill_tensor(node->src[1], &b)))
+        return GGML_STATUS_FAILED;
+    int rc;
+    switch (node->op) {
+    case GGML_OP_GET_ROWS: rc = b200_op_get_rows(bc->ctx, &a, &b, &d); break;
+    case GGML_OP_ADD: rc = b200_op_binary(bc->ctx, B200_OP_ADD, &a, &b, &d); break;
+    case GGML_OP_MUL: rc = b200_op_binary(bc->ctx, B200_OP_MUL, &a, &b, &d); break;
+    case GGML_OP_DIV: rc = b200_op_binary(bc->ctx, B200_OP_DIV, &a, &b, &d); break;
+    case GGML_OP_UNARY: rc = b200_op_unary(bc->ctx, (int)ggml_get_unary_op(node), &a, &d); break;
+    case GGML_OP_NORM:
+    case GGML_OP_RMS_NORM: {
+        float eps;
+        memcpy(&eps, node->op_params, sizeof(eps));
+        rc = b200_op_norm(bc->ctx, &a, NULL, NULL, &d, eps, node->op == GGML_OP_RMS_NORM);
+        break;
+    }
+    case GGML_OP_SCALE: {
+        float v;
+        memcpy(&v, node->op_params, sizeof(v));
+        rc = b200_op_scale(bc->ctx, &a, &d, v);
+        break;
+    }
+    case GGML_OP_DIAG_MASK_INF: rc = b200_op_diag_mask_inf(bc->ctx, &a, &d, ((const int32_t *)node->op_params)[0]); break;
+    case GGML_OP_SOFT_MAX: {
+        float scale, max_bias;
+        memcpy(&scale, (const float *)node->op_params + 0, sizeof(scale));
+        memcpy(&max_bias, (const float *)node->op_params + 1, sizeof(max_bias));
+        rc = b200_op_soft_max(bc->ctx, &a, node->src[1] ? &b : NULL, &d, scale, max_bias, -1);
+        break;
+    }
+    case GGML_OP_CPY:
+    case GGML_OP_DUP:
+    case GGML_OP_CONT: rc = b200_op_copy(bc->ctx, &a, &d); break;
+    case GGML_OP_MUL_MAT: rc = b200_op_mul_mat_dense(bc->ctx, &a, &b, &d); break;
+    default: rc = B200_ERR_UNSUPPORTED; break;
+    }
+    return b200_glue_status(bc, node, rc);
+}
+
+/*
+ * Fusions, only where the graph allocator has ALREADY proven that the intermediates are dead: ggml_gallocr
+ * computes an op in place of its parent exactly when nothing else reads the parent (src/ggml-alloc.c: n_children == 1, n_views == 0),
+ * so "the next node reads this one and writes the same memory" means the fused kernel loses no visible state.
+ *   NORM -> MUL(gain row) -> ADD(bias row)          one kernel (examples/gpt-2/main-backend.cpp:490-498, :634-642, :686-694)
+ *   SCALE -> DIAG_MASK_INF -> SOFT_MAX              one kernel (:567-583)
+ * Returns the number of nodes consumed (0 = no fusion here).
+ */
+static bool b200_row_vector(const struct ggml_tensor *v, int64_t ne0) {
+    return v && v->type == GGML_TYPE_F32 && v->ne[0] == ne0 && ggml_nrows(v) == 1 && v->nb[0] == sizeof(float) && b200_in_device_buffer(v);
+}
+static bool b200_inplace_child(const struct ggml_tensor *child, const struct ggml_tensor *parent) {
+    return child->src[0] == parent && child->data == parent->data && child->view_src == NULL && ggml_are_same_shape(child, parent) &&
+           !(parent->flags & GGML_TENSOR_FLAG_OUTPUT);
+}
+/*   MUL_MAT(quantized, decode shape) -> ADD(bias row) [-> GELU] [-> ADD(residual)]     the GEMV's epilogue (main-backend.cpp:614-625, :659-699)
+ * under the same rule: every follower computes in place of its predecessor.  Returns the nodes consumed (0 = no fusion). */
+static int b200_try_fuse_mul_mat(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int i, int last, enum ggml_status *st) {
+    struct ggml_tensor *mm = cgraph->nodes[i];
+    if (!bc->opt_fuse || i + 1 >= last || mm->src[1]->ne[1] > 8 || mm->ne[2] != 1 || mm->ne[3] != 1 || b200_tensor_is_split(mm->src[0])) return 0;
+    b200_epilogue epi;
+    memset(&epi, 0, sizeof(epi));
+    struct ggml_tensor *cur = mm;
+    int n = 1;
+    struct ggml_tensor *nx = cgraph->nodes[i + n];
+    if (nx->op == GGML_OP_ADD && b200_inplace_child(nx, cur) && b200_row_vector(nx->src[1], mm->ne[0]) && nx->src[1]->data != NULL) {
+        epi.bias_dev = (const float *)nx->src[1]->data;
+        cur = nx;
+        n++;
+    }
+    if (i + n < last) {
+        nx = cgraph->nodes[i + n];
+        if (nx->op == GGML_OP_UNARY && ggml_get_unary_op(nx) == GGML_UNARY_OP_GELU && b200_inplace_child(nx, cur)) {
+            epi.act = B200_EPI_GELU;
+            cur = nx;
+            n++;
+        }
+    }
+    if (i + n < last) {
+        nx = cgraph->nodes[i + n];
+        const struct ggml_tensor *r = nx->src[1];
+        if (nx->op == GGML_OP_ADD && b200_inplace_child(nx, cur) && r && r->type == GGML_TYPE_F32 && ggml_are_same_shape(r, mm) && ggml_is_contiguous(r) &&
+            b200_in_device_buffer(r) && r->data != NULL) {
+            epi.residual_dev = (const float *)r->data;
+            cur = nx;
+            n++;
+        }
+    }
+    if (n == 1) return 0;
+    b200_mul_mat_args args;
+    if (!b200_fill_mul_mat_args(mm, &args)) return 0;
+    const int rc = b200_mul_mat_fused(bc->ctx, &args, &epi);
+    if (rc == B200_ERR_UNSUPPORTED) return 0;          /* not a single-launch shape: the operators run one by one */
+    *st = b200_glue_status(bc, mm, rc);
+    return n;
+}
+
+static int b200_try_fuse(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int i, int last, enum ggml_status *st) {
+    struct ggml_tensor *n0 = cgraph->nodes[i];
+    if (!bc->opt_fuse || i + 2 >= last) return 0;
+    struct ggml_tensor *n1 = cgraph->nodes[i + 1], *n2 = cgraph->nodes[i + 2];
+    b200_tensor a, g, b, d;
+    if ((n0->op == GGML_OP_NORM || n0->op == GGML_OP_RMS_NORM) && n1->op == GGML_OP_MUL && n2->op == GGML_OP_ADD && b200_glue_supported(n0) &&
+        b200_inplace_child(n1, n0) && b200_inplace_child(n2, n1) && b200_row_vector(n1->src[1], n0->ne[0]) && b200_row_vector(n2->src[1], n0->ne[0]) &&
+        n2->nb[0] == sizeof(float)) {
+        float eps;
+        memcpy(&eps, n0->op_params, sizeof(eps));
+        if (!b200_fill_tensor(n0->src[0], &a) || !b200_fill_tensor(n1->src[1], &g) || !b200_fill_tensor(n2->src[1], &b) || !b200_fill_tensor(n2, &d)) return 0;
+        *st = b200_glue_status(bc, n2, b200_op_norm(bc->ctx, &a, &g, &b, &d, eps, n0->op == GGML_OP_RMS_NORM));
+        return 3;
+    }
+    if (n0->op == GGML_OP_SCALE && n1->op == GGML_OP_DIAG_MASK_INF && n2->op == GGML_OP_SOFT_MAX && b200_glue_supported(n0) && b200_glue_supported(n2) &&
+        b200_inplace_child(n1, n0) && b200_inplace_child(n2, n1) && n2->src[1] == NULL) {
+        float s, scale, max_bias;
+        memcpy(&s, n0->op_params, sizeof(s));
+        memcpy(&scale, (const float *)n2->op_params + 0, sizeof(scale));
+        memcpy(&max_bias, (const float *)n2->op_params + 1, sizeof(max_bias));
+        if (max_bias != 0.0f) return 0;
+        if (!b200_fill_tensor(n0->src[0], &a) || !b200_fill_tensor(n2, &d)) return 0;
+        *st = b200_glue_status(bc, n2, b200_op_soft_max(bc->ctx, &a, NULL, &d, s * scale, 0.0f, ((const int32_t *)n1->op_params)[0]));
+        return 3;
+    }
+    return 0;
+}
+
 GGML_CALL static bool b200_backend_supports_op(ggml_backend_t backend, const struct ggml_tensor *op) {
     GGML_UNUSED(backend);
     if (b200_op_is_noop(op->op)) return true;
-    if (op->op == GGML_OP_MUL_MAT) return b200_mul_mat_supported(op);
-    return false;
+    if (op->op == GGML_OP_MUL_MAT) return b200_mul_mat_supported(op) || (b200_dense_mul_mat_supported(op) && b200_glue_supported_srcs(op));
+    return b200_glue_supported(op);
 }
 
 static bool b200_fill_mul_mat_args(struct ggml_tensor *dst, b200_mul_mat_args *args) {
@@ -986,7 +1228,7 @@ static int b200_try_run_as_plan(struct b200_backend_context *bc, struct ggml_cgr
     return 1;
 }
 
-static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int first, int last);
+static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int first, int last, int *one_unit_next);
 
 GGML_CALL static enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, struct ggml_cgraph *cgraph) {
     struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
@@ -1006,17 +1248,18 @@ GGML_CALL static enum ggml_status b200_backend_graph_compute(ggml_backend_t back
             const int as_plan = b200_try_run_as_plan(bc, cgraph, i, last, n, key, split);
             if (as_plan < 0) return GGML_STATUS_FAILED;
             if (as_plan == 0) {
-                const enum ggml_status st = b200_graph_compute_nodes(bc, cgraph, i, last);
+                const enum ggml_status st = b200_graph_compute_nodes(bc, cgraph, i, last, NULL);
                 if (st != GGML_STATUS_SUCCESS) return st;
             }
             i = last;
             continue;
         }
-        /* anything else, up to the next decode run: node by node */
-        int stop = n == 1 ? last : i + 1;
-        const enum ggml_status st = b200_graph_compute_nodes(bc, cgraph, i, stop);
+        /* anything else: one unit at a time (a node, a same-input run of mul_mats, or a node with the in-place neighbours that fold
+         * into its kernel), so that the next decode run is found where it starts */
+        int next = i + 1;
+        const enum ggml_status st = b200_graph_compute_nodes(bc, cgraph, i, cgraph->n_nodes, &next);
         if (st != GGML_STATUS_SUCCESS) return st;
-        i = stop;
+        i = next;
     }
     return GGML_STATUS_SUCCESS;
 }
@@ -1047,16 +1290,34 @@ GGML_CALL static enum ggml_status b200_backend_graph_plan_compute(ggml_backend_t
     return b200_backend_graph_compute(backend, &gp->cgraph);
 }
 
-static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int first, int last) {
+/* nodes [first, last) one after the other; with one_unit_next: only the first unit of work found in that window (a node, a same-input
+ * run of mul_mats, a fused group), reporting where the caller continues */
+static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int first, int last, int *one_unit_next) {
+    bool done_one = false;
     for (int i = first; i < last; i++) {
         struct ggml_tensor *node = cgraph->nodes[i];
+        if (one_unit_next) {
+            *one_unit_next = i;
+            if (done_one) return GGML_STATUS_SUCCESS;
+        }
         if (ggml_is_empty(node) || b200_op_is_noop(node->op)) continue;
+        done_one = true;
         if (node->op == GGML_OP_MUL_MAT && b200_tensor_is_split(node->src[0])) {
             const enum ggml_status st = b200_compute_split_mul_mat(bc, node);
             if (st != GGML_STATUS_SUCCESS) return st;
             continue;
         }
-        if (node->op == GGML_OP_MUL_MAT) {
+        if (node->op == GGML_OP_MUL_MAT && b200_type_is_repacked(node->src[0]->type)) {
+            {
+                enum ggml_status st = GGML_STATUS_SUCCESS;
+                const int fused = b200_try_fuse_mul_mat(bc, cgraph, i, last, &st);
+                if (fused > 0) {
+                    if (st != GGML_STATUS_SUCCESS) return st;
+                    bc->fused_nodes += fused - 1;
+                    i += fused - 1;
+                    continue;
+                }
+            }
             /* gather the run of consecutive MUL_MAT nodes that share this node's src1 and do not depend on one another */
             struct ggml_tensor *run[B200_MAX_RUN];
             int n = 0;
@@ -1078,11 +1339,27 @@ static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc
             if (st != GGML_STATUS_SUCCESS) return st;
             continue;
         }
-        fprintf(stderr, "ggml-b200: op %s is outside this backend's path (supports_op is false for it); no CPU fallback\n",
-                ggml_op_name(node->op));
-        return GGML_STATUS_FAILED;
+        {
+            enum ggml_status st = GGML_STATUS_SUCCESS;
+            const int fused = b200_try_fuse(bc, cgraph, i, last, &st);
+            if (fused > 0) {
+                if (st != GGML_STATUS_SUCCESS) return st;
+                bc->fused_nodes += fused - 1;
+                i += fused - 1;
+                continue;
+            }
+            st = b200_compute_glue(bc, node);
+            if (st != GGML_STATUS_SUCCESS) return st;
+        }
     }
+    if (one_unit_next) *one_unit_next = last;
     return GGML_STATUS_SUCCESS;
+}
+
+static enum ggml_status b200_glue_status(struct b200_backend_context *bc, const struct ggml_tensor *node, int rc) {
+    if (rc == B200_OK) return GGML_STATUS_SUCCESS;
+    fprintf(stderr, "ggml-b200: %s failed (%d): %s\n", ggml_op_name(node->op), rc, b200_last_error(bc->ctx));
+    return rc == B200_ERR_ALLOC ? GGML_STATUS_ALLOC_FAILED : GGML_STATUS_FAILED;
 }
 
 static struct ggml_backend_i b200_backend_interface = {
@@ -1115,6 +1392,7 @@ GGML_CALL ggml_backend_t ggml_backend_b200_init(int device) {
     if (!bc) return NULL;
     bc->device = device;
     bc->opt_plans = 1;
+    bc->opt_fuse = 1;
     snprintf(bc->name, sizeof(bc->name), "%s%d", GGML_B200_NAME, device);
     if (b200_ctx_create(device, &bc->ctx) != B200_OK) {
         fprintf(stderr, "ggml-b200: %s\n", b200_last_error(NULL));
@@ -1159,10 +1437,19 @@ GGML_CALL int64_t ggml_backend_b200_plan_launch_count(ggml_backend_t backend) {
     return ((struct b200_backend_context *)backend->context)->plan_launches;
 }
 
+GGML_CALL int64_t ggml_backend_b200_fused_node_count(ggml_backend_t backend) {
+    GGML_ASSERT(ggml_backend_is_b200(backend));
+    return ((struct b200_backend_context *)backend->context)->fused_nodes;
+}
+
 GGML_CALL int ggml_backend_b200_set_option(ggml_backend_t backend, const char *key, int64_t value) {
     GGML_ASSERT(ggml_backend_is_b200(backend));
     if (strcmp(key, "plans") == 0) {
         ((struct b200_backend_context *)backend->context)->opt_plans = value != 0;
+        return B200_OK;
+    }
+    if (strcmp(key, "fuse") == 0) {
+        ((struct b200_backend_context *)backend->context)->opt_fuse = value != 0;
         return B200_OK;
     }
     return b200_ctx_set_option(((struct b200_backend_context *)backend->context)->ctx, key, value);

@@ -3,9 +3,10 @@
  *
  * A sibling of the reference's src/ggml-cuda.h: same shape of API, one backend per device, behind the
  * unchanged ggml_backend_i / ggml_backend_buffer_i / ggml_backend_buffer_type_i plugin interfaces
- * (src/ggml-backend-impl.h:18-117).  It accelerates ONE op: GGML_OP_MUL_MAT with Q4_0/Q8_0 src0 and
- * F32 src1 (supports_op is false for everything else except the no-op view family); there is no CPU
- * fallback inside the backend.
+ * (src/ggml-backend-impl.h:18-117).  It accelerates ONE path: GGML_OP_MUL_MAT with Q4_0/Q8_0 src0 and
+ * F32 src1, plus the operators either side of it in a GPT-2 / GPT-J graph (GET_ROWS, ADD/MUL/DIV, NORM, SCALE,
+ * DIAG_MASK_INF, SOFT_MAX, UNARY, CPY/DUP/CONT, F32/F16 MUL_MAT) so that gpt-2-backend runs on it unchanged;
+ * supports_op is false for everything else; there is no CPU fallback inside the backend.
  *
  * The ggml_backend_cuda_* names of src/ggml-cuda.h:19-39 (+ ggml_backend_cuda_reg_devices,
  * src/ggml-cuda.cu:3031-3042) are exported as thin aliases so that a reference core compiled with
@@ -39,7 +40,10 @@ GGML_API GGML_CALL int                        ggml_backend_b200_reg_devices(void
 GGML_API GGML_CALL int64_t                    ggml_backend_b200_launch_count(ggml_backend_t backend);
 /* number of cgraphs computed as ONE persistent launch (decode plan, see graph_compute in ggml-b200.c) */
 GGML_API GGML_CALL int64_t                    ggml_backend_b200_plan_launch_count(ggml_backend_t backend);
-/* "plans" (0/1: compute all-decode-MUL_MAT cgraphs as one persistent launch); everything else forwards to
+/* graph nodes that were folded into the kernel of a neighbour (NORM+MUL+ADD, SCALE+DIAG_MASK_INF+SOFT_MAX, ...) */
+GGML_API GGML_CALL int64_t                    ggml_backend_b200_fused_node_count(ggml_backend_t backend);
+/* "plans" (0/1: compute runs of decode MUL_MATs as one persistent launch), "fuse" (0/1: fold in-place neighbours into one kernel);
+ * everything else forwards to
  * b200_ctx_set_option (include/ggml_b200.h) */
 GGML_API GGML_CALL int                        ggml_backend_b200_set_option(ggml_backend_t backend, const char *key, int64_t value);
 

@@ -20,7 +20,10 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "lib" / "libggml_b200.so"
 BACKEND_LIB_PATH = PKG_DIR / "lib" / "libggml-b200-backend.so"
 
-TYPE_F32, TYPE_Q4_0, TYPE_Q8_0 = 0, 2, 8
+TYPE_F32, TYPE_F16, TYPE_Q4_0, TYPE_Q8_0, TYPE_I16, TYPE_I32 = 0, 1, 2, 8, 25, 26
+OP_ADD, OP_MUL, OP_DIV = 0, 1, 2
+UNARY = {n: i for i, n in enumerate(["abs", "sgn", "neg", "step", "tanh", "elu", "relu", "sigmoid", "gelu", "gelu_quick", "silu", "hardswish",
+                                     "hardsigmoid"])}          # enum ggml_unary_op
 QK = 32
 WIRE_BYTES = {TYPE_Q4_0: 18, TYPE_Q8_0: 34}
 TYPE_NAMES = {TYPE_Q4_0: "q4_0", TYPE_Q8_0: "q8_0"}
@@ -47,6 +50,17 @@ class MulMatArgs(C.Structure):
     ]
 
 
+class Tensor(C.Structure):
+    """b200_tensor: what a glue-operator kernel needs of a ggml_tensor (device address, type, ne[], nb[] in bytes)."""
+    _fields_ = [("data", C.c_void_p), ("type", C.c_int32), ("reserved", C.c_int32), ("ne", C.c_int64 * 4), ("nb", C.c_int64 * 4),
+                ("q_total_blocks", C.c_int64), ("q_block_off", C.c_int64)]
+
+
+class Epilogue(C.Structure):
+    _fields_ = [("bias_dev", C.c_void_p), ("residual_dev", C.c_void_p), ("act", C.c_int32), ("reserved", C.c_int32)]
+
+
+EPI_NONE, EPI_GELU = 0, 1
 MAX_RANKS = 8
 
 
@@ -103,6 +117,7 @@ _SIGNATURES = {
     "b200_quantize_q8_0": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_size_t, C.c_void_p, C.c_void_p]),
     "b200_quantize_q8_0_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_size_t, C.c_void_p]),
     "b200_mul_mat": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs)]),
+    "b200_mul_mat_fused": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs), C.POINTER(Epilogue)]),
     "b200_mul_mat_batch": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs), C.c_int]),
     "b200_mul_mat_gather": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs), C.POINTER(Gather)]),
     "b200_mul_mat_gather_batch": (C.c_int, [C.c_void_p, C.POINTER(MulMatArgs), C.POINTER(Gather), C.c_int]),
@@ -118,6 +133,15 @@ _SIGNATURES = {
     "b200_plan_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_plan_destroy": (None, [C.c_void_p]),
     "b200_plan_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b200_op_get_rows": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor)]),
+    "b200_op_binary": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor)]),
+    "b200_op_unary": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Tensor), C.POINTER(Tensor)]),
+    "b200_op_norm": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.c_float, C.c_int]),
+    "b200_op_scale": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.c_float]),
+    "b200_op_diag_mask_inf": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.c_int]),
+    "b200_op_soft_max": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.c_float, C.c_float, C.c_int]),
+    "b200_op_copy": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor)]),
+    "b200_op_mul_mat_dense": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor)]),
     "b200_block_dots": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "b200_mul_mat_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
 }
@@ -186,6 +210,45 @@ class DeviceBuffer:
         return out
 
 
+_NP_TYPES = {TYPE_F32: np.float32, TYPE_F16: np.float16, TYPE_I16: np.int16, TYPE_I32: np.int32}
+
+
+class DTensor:
+    """A dense tensor on the device for the glue operators: ggml shape order (ne[0] contiguous), optional byte strides / offset
+    into a parent buffer (views, permutes).  from_numpy takes an array whose LAST axis is ne[0]."""
+
+    def __init__(self, ctx: "Context", ttype: int, ne, nb=None, buf: DeviceBuffer | None = None, offset: int = 0):
+        ne = list(ne) + [1] * (4 - len(ne))
+        es = np.dtype(_NP_TYPES[ttype]).itemsize
+        if nb is None:
+            nb = [es, es * ne[0], es * ne[0] * ne[1], es * ne[0] * ne[1] * ne[2]]
+        self.ctx, self.type, self.ne, self.nb, self.offset = ctx, ttype, ne, list(nb), offset
+        self.buf = buf if buf is not None else ctx.alloc(max(16, es * ne[0] * ne[1] * ne[2] * ne[3]))
+
+    @classmethod
+    def from_numpy(cls, ctx: "Context", arr: np.ndarray) -> "DTensor":
+        ttype = {np.dtype(v): k for k, v in _NP_TYPES.items()}[arr.dtype]
+        t = cls(ctx, ttype, list(arr.shape[::-1]))
+        t.buf.upload(arr)
+        return t
+
+    def view(self, ne, nb, offset: int = 0) -> "DTensor":
+        return DTensor(self.ctx, self.type, ne, nb, self.buf, self.offset + offset)
+
+    def desc(self) -> Tensor:
+        t = Tensor()
+        t.data = self.buf.ptr + self.offset
+        t.type = self.type
+        t.ne = (C.c_int64 * 4)(*self.ne)
+        t.nb = (C.c_int64 * 4)(*self.nb)
+        return t
+
+    def numpy(self) -> np.ndarray:
+        """the dense contents (only for tensors that own their whole buffer contiguously)"""
+        n = self.ne[0] * self.ne[1] * self.ne[2] * self.ne[3]
+        return self.buf.download(_NP_TYPES[self.type], n, self.offset).reshape(self.ne[::-1])
+
+
 class QTensor:
     """A Q4_0/Q8_0 tensor [k, m, ne02, ne03] resident on the device in the repacked plane layout.
 
@@ -217,6 +280,19 @@ class QTensor:
         self.ctx._check(self.ctx.lib.b200_get_quantized(self.ctx.h, self.type, C.c_void_p(self.ptr), self.nblocks, _ptr(out),
                                                         block_off, nb))
         return out
+
+    def desc(self) -> Tensor:
+        """as a b200_tensor (wire strides, repacked root addressing) for b200_op_get_rows"""
+        w = WIRE_BYTES[self.type]
+        t = Tensor()
+        t.data = self.ptr
+        t.type = self.type
+        t.ne = (C.c_int64 * 4)(self.k, self.m, self.ne02, self.ne03)
+        nb1 = w * (self.k // QK)
+        t.nb = (C.c_int64 * 4)(w, nb1, nb1 * self.m, nb1 * self.m * self.ne02)
+        t.q_total_blocks = self.nblocks
+        t.q_block_off = 0
+        return t
 
     def free(self):
         if self.buf is not None:
@@ -252,6 +328,38 @@ class Context:
     def _check(self, rc: int):
         if rc != OK:
             raise B200Error(rc, (self.lib.b200_last_error(self.h) or b"").decode())
+
+    # -- the operators either side of the path (b200_ops.cu); every argument a DTensor / QTensor, asynchronous
+    @staticmethod
+    def _d(t):
+        return None if t is None else C.byref(t.desc())
+
+    def op_get_rows(self, src0, rows, dst):
+        self._check(self.lib.b200_op_get_rows(self.h, self._d(src0), self._d(rows), self._d(dst)))
+
+    def op_binary(self, op: int, a, b, dst):
+        self._check(self.lib.b200_op_binary(self.h, op, self._d(a), self._d(b), self._d(dst)))
+
+    def op_unary(self, name: str, a, dst):
+        self._check(self.lib.b200_op_unary(self.h, UNARY[name], self._d(a), self._d(dst)))
+
+    def op_norm(self, a, dst, eps: float, gain=None, bias=None, rms: bool = False):
+        self._check(self.lib.b200_op_norm(self.h, self._d(a), self._d(gain), self._d(bias), self._d(dst), C.c_float(eps), int(rms)))
+
+    def op_scale(self, a, dst, s: float):
+        self._check(self.lib.b200_op_scale(self.h, self._d(a), self._d(dst), C.c_float(s)))
+
+    def op_diag_mask_inf(self, a, dst, n_past: int):
+        self._check(self.lib.b200_op_diag_mask_inf(self.h, self._d(a), self._d(dst), n_past))
+
+    def op_soft_max(self, a, dst, mask=None, scale: float = 1.0, max_bias: float = 0.0, n_past: int = -1):
+        self._check(self.lib.b200_op_soft_max(self.h, self._d(a), self._d(mask), self._d(dst), C.c_float(scale), C.c_float(max_bias), n_past))
+
+    def op_copy(self, a, dst):
+        self._check(self.lib.b200_op_copy(self.h, self._d(a), self._d(dst)))
+
+    def op_mul_mat_dense(self, a, b, dst):
+        self._check(self.lib.b200_op_mul_mat_dense(self.h, self._d(a), self._d(b), self._d(dst)))
 
     # -- plumbing
     def set_option(self, key: str, value: int):
@@ -392,6 +500,13 @@ class Context:
         a.nb12 = a.nb13 = a.nb11 * n
         a.dst_dev = dst_ptr
         return a
+
+    def mul_mat_fused(self, w: QTensor, x_ptr: int, n: int, dst_ptr: int, bias_ptr: int = 0, residual_ptr: int = 0, act: int = EPI_NONE):
+        """decode mul_mat with bias / GELU / residual folded into the GEMV epilogue (b200_mul_mat_fused)"""
+        a = self.make_args(w, x_ptr, n, dst_ptr)
+        e = Epilogue()
+        e.bias_dev, e.residual_dev, e.act = bias_ptr or None, residual_ptr or None, act
+        self._check(self.lib.b200_mul_mat_fused(self.h, C.byref(a), C.byref(e)))
 
     def mul_mat_batch(self, args_list):
         """independent mul_mats in one call (b200_mul_mat_batch); same-input decode entries share a launch"""

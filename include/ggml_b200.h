@@ -39,8 +39,11 @@ extern "C" {
 
 /* tensor types: numeric values of enum ggml_type (include/ggml/ggml.h:347-355) */
 #define B200_TYPE_F32   0
+#define B200_TYPE_F16   1
 #define B200_TYPE_Q4_0  2
 #define B200_TYPE_Q8_0  8
+#define B200_TYPE_I16   25
+#define B200_TYPE_I32   26
 
 /* wire formats (src/ggml-common.h:144-149, :186-191) */
 #define B200_QK            32
@@ -176,6 +179,21 @@ typedef struct b200_mul_mat_args {
 #define B200_MM_EXPORT      4   /* b200_plan_create on a row-split plan: leave the COMPLETE dst (all ranks' slices) in dst_dev */
 
 B200_API int b200_mul_mat(b200_ctx *ctx, const b200_mul_mat_args *args);
+/* the same with the operators that follow a decode mul_mat in a transformer block folded into its epilogue:
+ *     dst = act(src0 x src1 + bias) + residual
+ * -- the ADD of a bias row, the GELU and the ADD of the residual stream (examples/gpt-2/main-backend.cpp:614-625, :659-672, :683-699) --
+ * for 2-D decode shapes that take the GEMV (ne11 <= 8, no batch dims).  bias_dev [ne01] or NULL, residual_dev dense like dst or NULL (may be
+ * dst_dev itself), act = B200_EPI_NONE / B200_EPI_GELU.  Same bits as b200_mul_mat followed by the separate operators.
+ * B200_ERR_UNSUPPORTED for any other shape: the caller runs the operators one by one. */
+#define B200_EPI_NONE 0
+#define B200_EPI_GELU 1
+typedef struct b200_epilogue {
+    const float *bias_dev;
+    const float *residual_dev;
+    int32_t      act;
+    int32_t      reserved;
+} b200_epilogue;
+B200_API int b200_mul_mat_fused(b200_ctx *ctx, const b200_mul_mat_args *args, const b200_epilogue *epilogue);
 /* `count` mul_mats with NO data dependencies among them (e.g. the q/k/v/fc_in projections of a GPT-J block, which all
  * read the same normalised activations: examples/gpt-j/main.cpp:462-467, :535-538).  Decode-shaped entries that share
  * type, k and src1 are streamed by ONE launch (one activation quantization, the grid divided among the matrices);
@@ -271,6 +289,61 @@ B200_API void b200_plan_destroy(b200_plan *plan);
  * producer spent blocked on a full ring, ns one consumer warp spent blocked on an empty ring, ns spent in quantization
  * phases); B200_ERR_UNSUPPORTED when not tracing */
 B200_API int  b200_plan_trace(b200_ctx *ctx, b200_plan *plan, unsigned long long *out_host, size_t capacity_u64, int *nops, int *grid);
+
+/* ---- the operators either side of the path ---------------------------------------------------------------
+ * What a GPT-2 / GPT-J graph computes between its quantized mul_mats, so that the reference's gpt-2-backend runs its WHOLE graph on
+ * this backend (examples/gpt-2/main-backend.cpp:442-717, computed by one ggml_backend_graph_compute at :768).  Each call stands in
+ * for one ggml_compute_forward_* of src/ggml.c (cited per entry) and is asynchronous on the context's stream.  A b200_tensor is
+ * the part of struct ggml_tensor (include/ggml/ggml.h:565-604) a kernel needs: device address, type, ne[], nb[] (bytes).  For a
+ * repacked Q4_0 / Q8_0 tensor `data` is the start of the ROOT tensor's qs plane, q_total_blocks the blocks of the root and
+ * q_block_off the first block of this tensor (as in b200_mul_mat_args); nb[] stay the wire strides of ggml.
+ * Every operator may run in place (dst->data == src0->data), as ggml_gallocr arranges it.
+ * B200_ERR_UNSUPPORTED = a type / layout the backend's supports_op must have declined. */
+typedef struct b200_tensor {
+    void   *data;
+    int32_t type;             /* B200_TYPE_* */
+    int32_t reserved;
+    int64_t ne[4];
+    int64_t nb[4];
+    int64_t q_total_blocks;   /* repacked quantized tensors only */
+    int64_t q_block_off;
+} b200_tensor;
+
+/* numeric values of enum ggml_unary_op (include/ggml/ggml.h:514-530) */
+enum { B200_UNARY_ABS = 0, B200_UNARY_SGN, B200_UNARY_NEG, B200_UNARY_STEP, B200_UNARY_TANH, B200_UNARY_ELU, B200_UNARY_RELU, B200_UNARY_SIGMOID,
+       B200_UNARY_GELU, B200_UNARY_GELU_QUICK, B200_UNARY_SILU, B200_UNARY_HARDSWISH, B200_UNARY_HARDSIGMOID, B200_UNARY_COUNT };
+enum { B200_OP_ADD = 0, B200_OP_MUL = 1, B200_OP_DIV = 2 };
+
+/* GGML_OP_GET_ROWS (ggml_compute_forward_get_rows, src/ggml.c:13049): dst[:, i10, i11, i12] = src0[:, rows[i10, i11, i12], i11, i12] as
+ * F32; src0 F32, F16 or repacked Q4_0 / Q8_0 (dequantize_row_q4_0 / _q8_0, src/ggml-quants.c:980-998, :1074-1088), rows I32 */
+B200_API int b200_op_get_rows(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *rows, const b200_tensor *dst);
+/* GGML_OP_ADD / MUL / DIV on F32 (ggml_compute_forward_add_f32, src/ggml.c:8568; mul_f32 :9687): src1 is repeated over src0 in every
+ * dimension (ggml_can_repeat) */
+B200_API int b200_op_binary(b200_ctx *ctx, int op, const b200_tensor *src0, const b200_tensor *src1, const b200_tensor *dst);
+/* GGML_OP_UNARY on contiguous F32 (ggml_compute_forward_unary; gelu = the tanh form of src/ggml.c:1966 in fp32 -- the CPU rounds x and
+ * the result through its fp16 table, :1978-1991) */
+B200_API int b200_op_unary(b200_ctx *ctx, int op, const b200_tensor *src0, const b200_tensor *dst);
+/* GGML_OP_NORM / GGML_OP_RMS_NORM over dim 0 (ggml_compute_forward_norm_f32, src/ggml.c:11353), optionally fused with the MUL by a
+ * gain row and the ADD of a bias row that follow it in a transformer block (examples/gpt-2/main-backend.cpp:490-498): dst = norm(src0)
+ * [* gain] [+ bias]; gain / bias: F32 vectors of ne[0] elements or NULL */
+B200_API int b200_op_norm(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *gain, const b200_tensor *bias, const b200_tensor *dst,
+                          float eps, int rms);
+/* GGML_OP_SCALE on contiguous F32 (ggml_compute_forward_scale_f32, src/ggml.c:12637) */
+B200_API int b200_op_scale(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *dst, float s);
+/* GGML_OP_DIAG_MASK_INF on contiguous F32 (ggml_compute_forward_diag_mask_f32, src/ggml.c:13301): dst[i, j, ...] = i > n_past + j ? -inf : src0 */
+B200_API int b200_op_diag_mask_inf(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *dst, int n_past);
+/* GGML_OP_SOFT_MAX over dim 0 of contiguous F32 (ggml_compute_forward_soft_max_f32, src/ggml.c:13393): softmax(src0 * scale + slope(head) *
+ * mask[:, i1]); mask F32 / F16 [ne0, >= ne1] or NULL; max_bias > 0 = ALiBi slopes per head (dim 2).  n_past >= 0 additionally applies the
+ * causal mask of a GGML_OP_DIAG_MASK_INF(n_past) in front (fused SCALE + DIAG_MASK_INF + SOFT_MAX, main-backend.cpp:567-583); -1 = none */
+B200_API int b200_op_soft_max(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *mask, const b200_tensor *dst, float scale, float max_bias,
+                              int n_past);
+/* GGML_OP_CPY / DUP / CONT (ggml_compute_forward_dup, src/ggml.c:8535): element i of the flattened src0 to element i of the flattened dst,
+ * both arbitrarily strided; F32 <-> F16 conversions, or any same-type pair of 2- / 4-byte elements (F32, F16, I32, I16) */
+B200_API int b200_op_copy(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *dst);
+/* GGML_OP_MUL_MAT with an F32 / F16 src0 (ggml_compute_forward_mul_mat, src/ggml.c:11808): dst[n][m] = sum_k src0[m][k] * src1[n][k] per
+ * (i2, i3) with the broadcast of src0 over src1's batch dims; both operands k-contiguous, any row / batch strides (K*Q and V*softmax(KQ) on
+ * permuted views of the KV cache, main-backend.cpp:567, :597); fp32 accumulation */
+B200_API int b200_op_mul_mat_dense(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *src1, const b200_tensor *dst);
 
 /* parity instrumentation: per-block int32 partial sums exactly as the kernels form them.
  * out_dev [n][m][k/32] int32.  path 0 = GEMV inner loop (dp4a), path 1 = GEMM (tcgen05 accumulators).

@@ -3,8 +3,10 @@
  * followed by decode steps, on the reference's own graph machinery.  TEST INFRASTRUCTURE (our code against the reference's public
  * API; built by oracle/Makefile into oracle/_ref/, linked with the reference core that has the B200 backend dropped in).
  *
- * Two arms compute the same model on the same tokens:
+ * Three arms compute the same model on the same tokens:
  *   cpu    every tensor and every op on ggml_backend_cpu (the reference path);
+ *   b200   every tensor and every op on the B200 backend, the way examples/gpt-2/main-backend.cpp:744-768 runs a model: compute
+ *          tensors from ggml_gallocr on the backend's default buffer type, ONE ggml_backend_graph_compute per step;
  *   sched  ggml_backend_sched over {B200, CPU} (src/ggml-backend.c:1683-1830, the way examples/gpt-2/main-sched.cpp:869-936 drives
  *          it): every GGML_OP_MUL_MAT with a quantized weight is pinned to the B200 backend (ggml_backend_sched_set_tensor_backend,
  *          src/ggml-backend.c:1874), the glue ops (GET_ROWS, ADD, MUL, NORM, SCALE, DIAG_MASK_INF, SOFT_MAX, GELU, CPY / CONT, the
@@ -31,6 +33,11 @@
 #define N_HEAD  12
 #define N_LAYER 12
 #define MAX_NODES 4096
+
+/* instrumentation of the B200 backend (ggml-imax_b200/host/ggml-b200.h) */
+extern int64_t ggml_backend_b200_launch_count(ggml_backend_t backend);
+extern int64_t ggml_backend_b200_fused_node_count(ggml_backend_t backend);
+extern int ggml_backend_b200_set_option(ggml_backend_t backend, const char *key, int64_t value);
 
 struct layer {
     struct ggml_tensor *ln1_g, *ln1_b, *ln2_g, *ln2_b;
@@ -188,9 +195,15 @@ int main(int argc, char **argv) {
         if (strncmp(ggml_backend_reg_get_name(i), "B200", 4) == 0) { gpu = ggml_backend_reg_init_backend(i, NULL); break; }
     if (!gpu) { printf("{\"error\": \"no B200 backend in the registry\"}\n"); return 2; }
 
-    static struct model ma, mb;
+    static struct model ma, mb, mc;
     model_build(&ma, qtype, ggml_backend_cpu_buffer_type(), ggml_backend_cpu_buffer_type());                          /* arm cpu   */
     model_build(&mb, qtype, ggml_backend_get_default_buffer_type(gpu), ggml_backend_cpu_buffer_type());              /* arm sched */
+
+    model_build(&mc, qtype, ggml_backend_get_default_buffer_type(gpu), ggml_backend_get_default_buffer_type(gpu));   /* arm b200  */
+    if (argc > 5) ggml_backend_b200_set_option(gpu, "fuse", atoi(argv[5]));
+    ggml_gallocr_t galloc_c = ggml_gallocr_new(ggml_backend_get_default_buffer_type(gpu));
+    float *lc = (float *)malloc(sizeof(float) * N_VOCAB);
+    int64_t launches_c = 0, nodes_c = 0;
 
     ggml_backend_t backends[2] = { gpu, cpu_b };
     ggml_backend_sched_t sched = ggml_backend_sched_new(backends, NULL, 2, MAX_NODES, false);
@@ -235,17 +248,35 @@ int main(int argc, char **argv) {
         if (st != GGML_STATUS_SUCCESS) { printf("], \"error\": \"sched compute failed (%d)\"}\n", (int)st); return 4; }
         gpu_splits_last = ggml_backend_sched_get_n_splits(sched);
         ggml_backend_tensor_get(Gb.logits, lb, (size_t)(N - 1) * N_VOCAB * sizeof(float), sizeof(float) * N_VOCAB);
-        const double e = nmse(lb, la, N_VOCAB);
+        /* arm b200: the whole graph on the B200 backend */
+        struct graph Gc = build_graph(&mc, n_past, N);
+        if (!ggml_gallocr_alloc_graph(galloc_c, Gc.gf)) { printf("], \"error\": \"gallocr on the B200 buffer type failed\"}\n"); return 5; }
+        ggml_backend_tensor_set(Gc.tokens, tokens + n_past, 0, sizeof(int32_t) * (size_t)N);
+        ggml_backend_tensor_set(Gc.positions, pos, 0, sizeof(int32_t) * (size_t)N);
+        const int64_t l0 = ggml_backend_b200_launch_count(gpu);
+        t0 = ggml_time_us();
+        const enum ggml_status stc = ggml_backend_graph_compute_async(gpu, Gc.gf);
+        const double ms_b200_enqueue = (double)(ggml_time_us() - t0) / 1e3;      /* host time to issue the step's launches */
+        ggml_backend_synchronize(gpu);
+        const double ms_b200 = (double)(ggml_time_us() - t0) / 1e3;
+        if (stc != GGML_STATUS_SUCCESS) { printf("], \"error\": \"B200 graph_compute failed (%d)\"}\n", (int)stc); return 6; }
+        launches_c = ggml_backend_b200_launch_count(gpu) - l0;
+        nodes_c = Gc.gf->n_nodes;
+        ggml_backend_tensor_get(Gc.logits, lc, (size_t)(N - 1) * N_VOCAB * sizeof(float), sizeof(float) * N_VOCAB);
+        const double e = nmse(lb, la, N_VOCAB), ec = nmse(lc, la, N_VOCAB);
         int fin = 1;
-        for (int i = 0; i < N_VOCAB; i++) if (!isfinite(lb[i])) fin = 0;
-        if (!(e <= 5e-4) || !fin) ok = 0;
-        printf("%s{\"n_past\": %d, \"n\": %d, \"logits_nmse_vs_cpu\": %.3e, \"finite\": %s, \"ms_cpu\": %.2f, \"ms_sched_b200\": %.2f}", step ? ", " : "", n_past, N, e,
-               fin ? "true" : "false", ms_cpu, ms_sched);
+        for (int i = 0; i < N_VOCAB; i++) if (!isfinite(lb[i]) || !isfinite(lc[i])) fin = 0;
+        if (!(e <= 5e-4) || !(ec <= 5e-4) || !fin) ok = 0;
+        printf("%s{\"n_past\": %d, \"n\": %d, \"logits_nmse_vs_cpu\": %.3e, \"b200_whole_graph_logits_nmse_vs_cpu\": %.3e, \"finite\": %s, \"ms_cpu\": %.2f, "
+               "\"ms_sched_b200\": %.2f, \"ms_b200_whole_graph\": %.3f, \"ms_b200_enqueue\": %.3f, \"b200_launches\": %lld, \"graph_nodes\": %lld}", step ? ", " : "", n_past, N, e, ec,
+               fin ? "true" : "false", ms_cpu, ms_sched, ms_b200, ms_b200_enqueue, (long long)launches_c, (long long)nodes_c);
         n_past += N;
         ggml_free(Ga.ctx);
         ggml_free(Gb.ctx);
+        ggml_free(Gc.ctx);
     }
-    printf("], \"quantized_mul_mat_nodes_on_b200\": %d, \"graph_splits\": %d, \"ok\": %s}\n", qmm_nodes, gpu_splits_last, ok ? "true" : "false");
+    printf("], \"quantized_mul_mat_nodes_on_b200\": %d, \"graph_splits\": %d, \"b200_fused_nodes_total\": %lld, \"ok\": %s}\n", qmm_nodes, gpu_splits_last,
+           (long long)ggml_backend_b200_fused_node_count(gpu), ok ? "true" : "false");
     ggml_backend_sched_free(sched);
     return ok ? 0 : 1;
 }

@@ -38,8 +38,24 @@ def test_backend_ops_mul_mat():
     assert re.search(r"\d+/\d+ tests passed", clean) and "FAIL" not in clean, clean[-2000:]
 
 
-def test_backend_ops_all_ops_do_not_crash():
-    """Every other op must be declined through supports_op (printed 'not supported'), never attempted."""
+GLUE = ["GET_ROWS(type=f32", "GET_ROWS(type=f16", "GET_ROWS(type=q4_0", "GET_ROWS(type=q8_0", "ADD(type=f32", "MUL(type=f32", "DIV(type=f32", "GELU(type=f32",
+        "GELU_QUICK(type=f32", "SILU(type=f32", "RELU(type=f32", "TANH(type=f32", "NORM(type=f32", "RMS_NORM(type=f32", "SCALE(type=f32", "DIAG_MASK_INF(type=f32",
+        "SOFT_MAX(type=f32", "CPY(type_src=f32,type_dst=f32", "CPY(type_src=f32,type_dst=f16", "CPY(type_src=f16,type_dst=f32", "DUP(type=f32", "DUP(type=i16",
+        "CONT(type=f32", "MUL_MAT(type_a=f32,type_b=f32", "MUL_MAT(type_a=f16,type_b=f32"]
+
+
+def test_backend_ops_whole_suite_glue_ops_green_rest_declined():
+    """The reference's whole conformance suite against this backend: every case of the operators either side of the path (SURVEY.md
+    8(f)-1: what a GPT-2 / GPT-J graph computes between its quantized mul_mats) must RUN and match the CPU backend within the
+    harness' own per-op bounds; everything else must be declined through supports_op (printed 'not supported'), never attempted."""
     exe = REF / "test-backend-ops"
     rc, out = run([str(exe), "test", "-b", "B2000"])
-    assert rc == 0, out[-4000:]
+    clean = re.sub(r"\x1b\[[0-9;]*m", "", out)
+    assert rc == 0 and "FAIL" not in clean, clean[-4000:]
+    lines = clean.splitlines()
+    for prefix in GLUE:
+        mine = [l for l in lines if l.strip().startswith(prefix)]
+        assert mine, f"no test case starts with {prefix}"
+        assert all(l.rstrip().endswith("OK") for l in mine), "\n".join(l for l in mine if not l.rstrip().endswith("OK"))
+    ran = sum(1 for l in lines if l.rstrip().endswith("OK"))
+    assert ran >= 240, ran

@@ -1,0 +1,47 @@
+"""The reference's own example, UNMODIFIED (examples/gpt-2/main-backend.cpp compiled with -DGGML_USE_CUDA into oracle/_ref/gpt-2-backend; its
+ggml_backend_cuda_init(0) is this backend's alias), on a random-init GPT-2 117M Q4_0 model file in the reference's legacy ggml format
+(oracle/make_gpt2_model.py): BASELINE.json configs[2] as north_star words it -- "the gpt-2-backend ... paths pick it up unchanged".  The same
+source compiled for the reference CPU backend (oracle/_ref/gpt-2-backend-cpu) runs beside it.  Logit-level parity of this graph is
+tests/test_gpu_gpt2_sched.py (arm b200); here the binary itself must load the file, tokenize, run prompt + decode on the GPU and exit 0."""
+import re
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+REF = ROOT / "oracle" / "_ref"
+PROMPT = "the quick brown fox jumps over the lazy dog and keeps running through the forest until the night falls over the quiet hills of the north"
+
+
+def run(exe, model, extra):
+    p = subprocess.run([str(exe), "-m", str(model), "-p", PROMPT, "-n", "16", "-s", "7", "--top_k", "1", "-b", "128", "-t", "8"] + extra,
+                       capture_output=True, text=True, timeout=600)
+    return p.returncode, p.stdout, p.stderr
+
+
+@pytest.mark.parametrize("qname", ["q4_0", "q8_0"])
+def test_reference_gpt2_backend_example_runs_unmodified_on_b200(tmp_path, qname):
+    gpu_exe, cpu_exe = REF / "gpt-2-backend", REF / "gpt-2-backend-cpu"
+    assert gpu_exe.exists() and cpu_exe.exists(), "oracle/_ref/gpt-2-backend[-cpu] must be prebuilt (make -C oracle dropin) and travel with the snapshot"
+    model = tmp_path / f"gpt2-117m-{qname}.bin"
+    subprocess.check_call([sys.executable, str(ROOT / "oracle" / "make_gpt2_model.py"), str(model), qname])
+    rc, out, err = run(gpu_exe, model, ["-ngl", "1"])
+    assert rc == 0, (out[-2000:], err[-2000:])
+    assert "using CUDA backend" in err and "using CPU backend" not in err, err[-2000:]          # (the alias: ggml_backend_cuda_init -> B200)
+    m = re.search(r"number of tokens in prompt = (\d+)", out)
+    assert m and int(m.group(1)) >= 128, out[-2000:]
+    gen = re.findall(r"<(\d+)>|\n", out.split(PROMPT)[-1].split("main:")[0])
+    t = re.search(r"predict time =\s*([\d.]+) ms / ([\d.]+) ms per token", out)
+    assert t, out[-2000:]
+    rc2, out2, err2 = run(cpu_exe, model, [])
+    assert rc2 == 0 and "using CPU backend" in err2
+    t2 = re.search(r"predict time =\s*([\d.]+) ms / ([\d.]+) ms per token", out2)
+    # greedy continuations: rounding-level logit differences may flip an argmax of a random-init model, so agreement is reported, not required
+    g1 = out.split(PROMPT)[-1].split("\n\n")[0]
+    g2 = out2.split(PROMPT)[-1].split("\n\n")[0]
+    print(f"\n[gpt-2-backend {qname}] B200: {t.group(1)} ms total, {t.group(2)} ms/token; CPU (8 threads): {t2.group(1)} ms total, {t2.group(2)} ms/token; "
+          f"same greedy continuation: {g1 == g2}")
+    assert len(g1) > 0 and gen is not None

@@ -2,7 +2,9 @@
 reference's own scheduler (ggml_backend_sched over {B200, CPU}, quantized MUL_MAT nodes pinned to the B200 backend, the glue ops on
 the CPU backend) against the same model computed entirely by the reference CPU backend: oracle/gpt2_sched_harness.c, built by
 oracle/Makefile into oracle/_ref/gpt2-sched-harness.  The tied wte lives repacked in a B200 buffer and reaches GET_ROWS on the
-CPU through the scheduler's tensor copy (get_tensor's exact un-repack).  Logits within test-backend-ops' NMSE bar 5e-4."""
+CPU through the scheduler's tensor copy (get_tensor's exact un-repack).  A third arm computes the WHOLE graph on the B200 backend
+(compute tensors from ggml_gallocr on its buffer type, one ggml_backend_graph_compute per step: what examples/gpt-2/main-backend.cpp does).
+Logits within test-backend-ops' NMSE bar 5e-4."""
 import json
 import subprocess
 
@@ -27,4 +29,7 @@ def test_gpt2_117m_prompt_and_decode_on_sched_b200_plus_cpu(qname):
     assert [s["n"] for s in steps] == [128, 1, 1, 1] and [s["n_past"] for s in steps] == [0, 128, 129, 130]
     for s in steps:
         assert s["finite"] and s["logits_nmse_vs_cpu"] <= MUL_MAT_NMSE_TOL, s
+        assert s["b200_whole_graph_logits_nmse_vs_cpu"] <= MUL_MAT_NMSE_TOL, s
+        assert 0 < s["b200_launches"] < s["graph_nodes"], s          # views cost nothing, in-place neighbours share a kernel
+    assert r["b200_fused_nodes_total"] > 0
     assert r["ok"] and p.returncode == 0
