@@ -254,7 +254,10 @@ int launch_typed(b200_ctx *ctx, const b200_gemv_params &p, bool dots) {
     const size_t smem = (size_t)NCOLS * gemv_col_bytes(TYPE, p.k);
     B200_REQUIRE(ctx, smem <= 200 * 1024, B200_ERR_UNSUPPORTED);
     auto kern = dots ? gemv_kernel<TYPE, NCOLS, true> : gemv_kernel<TYPE, NCOLS, false>;
-    if (smem > 48 * 1024) B200_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) {
+        if (dots) B200_SMEM_LIMIT_ONCE(ctx, (gemv_kernel<TYPE, NCOLS, true>), 200 * 1024);
+        else B200_SMEM_LIMIT_ONCE(ctx, (gemv_kernel<TYPE, NCOLS, false>), 200 * 1024);
+    }
     // persistent grid: a multiple of the SM count, no more CTAs than there are row pairs
     const int64_t row_groups = (p.m + kRows - 1) / kRows;
     int64_t ctas = (row_groups + kWarps - 1) / kWarps;

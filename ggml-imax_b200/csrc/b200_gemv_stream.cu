@@ -519,7 +519,8 @@ bool stream_geometry(const b200_gemv_params &p, StreamGeom *g) {
 template <int TYPE, int NCOLS>
 int launch_stream_typed(b200_ctx *ctx, const b200_gemv_params &p, const StreamGeom &g, bool dots, const StreamBatch *batch = nullptr) {
     auto kern = dots ? gemv_stream_kernel<TYPE, NCOLS, true> : gemv_stream_kernel<TYPE, NCOLS, false>;
-    B200_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    if (dots) B200_SMEM_LIMIT_ONCE(ctx, (gemv_stream_kernel<TYPE, NCOLS, true>), 112 * 1024);
+    else B200_SMEM_LIMIT_ONCE(ctx, (gemv_stream_kernel<TYPE, NCOLS, false>), 112 * 1024);
     StreamGeom gg = g;
     StreamBatch sb;
     memset(&sb, 0, sizeof(sb));

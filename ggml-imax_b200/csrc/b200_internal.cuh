@@ -27,6 +27,7 @@ struct b200_ctx {
     int          opt_gemm;
     int          opt_gemv_max_n;
     int          opt_gemv_stream;
+    int          opt_gemm_ablate;       // measurement only: see GemmF16Args::ablate
     int          opt_gemm_exact;        // 1: prefill GEMM = exact int8 block dots + fp32 scaling (slow); 0: fp16 tcgen05 path
     // decode plans (b200_plan.cu)
     int          opt_plan_pub_min_k;    // shortest in-plan src1 that is quantized once per GPU (0 = never)
@@ -69,6 +70,26 @@ void b200_set_error(b200_ctx *ctx, const char *fmt, ...);
             b200_set_error((ctx), "%s:%d: requirement failed: %s", __FILE__, __LINE__, #cond);     \
             return (code);                                                                         \
         }                                                                                          \
+    } while (0)
+
+// cudaSetDevice only when the calling thread is on another device (the query is a thread-local read; a redundant set is not free
+// on a launch-bound path such as a GPT-2 decode step)
+static inline cudaError_t b200_use_device(int device) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur == device) return cudaSuccess;
+    return cudaSetDevice(device);
+}
+// a kernel's dynamic shared-memory limit has to be raised once per device, not once per launch
+#define B200_SMEM_LIMIT_ONCE(ctx, kern, bytes)                                                                         \
+    do {                                                                                                               \
+        static unsigned long long done__ = 0;                                                                          \
+        static int bytes__ = 0;                                                                                        \
+        const unsigned long long bit__ = 1ull << ((ctx)->device & 63);                                                 \
+        if (!(done__ & bit__) || bytes__ < (int)(bytes)) {                                                             \
+            B200_CUDA_TRY((ctx), cudaFuncSetAttribute((kern), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            done__ |= bit__;                                                                                           \
+            if (bytes__ < (int)(bytes)) bytes__ = (int)(bytes);                                                        \
+        }                                                                                                              \
     } while (0)
 
 int b200_ws_reserve(b200_ctx *ctx, size_t bytes);     // ctx->ws >= bytes

@@ -130,7 +130,7 @@ int b200_mul_mat(b200_ctx *ctx, const b200_mul_mat_args *a) {
     const int64_t nb = a->ne00 / B200_QK;
     const int64_t nblk = nb * a->ne01 * a->ne02 * a->ne03;
     B200_REQUIRE(ctx, a->src0_block_off >= 0 && a->src0_block_off + nblk <= a->src0_nblocks_total, B200_ERR_INVALID);
-    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, b200_use_device(ctx->device));
     const int qsb = b200_qs_bytes(a->type);
     const uint8_t *qs = (const uint8_t *)a->src0_dev + a->src0_block_off * qsb;
     const __half *d = (const __half *)((const uint8_t *)a->src0_dev + a->src0_nblocks_total * qsb) + a->src0_block_off;
@@ -158,7 +158,7 @@ int b200_mul_mat_fused(b200_ctx *ctx, const b200_mul_mat_args *a, const b200_epi
     }
     const int64_t nblk = (a->ne00 / B200_QK) * a->ne01;
     B200_REQUIRE(ctx, a->src0_block_off >= 0 && a->src0_block_off + nblk <= a->src0_nblocks_total, B200_ERR_INVALID);
-    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, b200_use_device(ctx->device));
     const int qsb = b200_qs_bytes(a->type);
     const uint8_t *qs = (const uint8_t *)a->src0_dev + a->src0_block_off * qsb;
     const __half *d = (const __half *)((const uint8_t *)a->src0_dev + a->src0_nblocks_total * qsb) + a->src0_block_off;
@@ -199,7 +199,7 @@ int b200_mul_mat_batch(b200_ctx *ctx, const b200_mul_mat_args *args, int count) 
             run++;
         int rc = B200_OK;
         if (run >= 2) {
-            B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+            B200_CUDA_TRY(ctx, b200_use_device(ctx->device));
             if (b200_try_launch_gemv_stream_batch(ctx, ps, run, &rc)) {
                 if (rc != B200_OK) return rc;
                 i += run;
@@ -231,7 +231,7 @@ int b200_mul_mat_gather(b200_ctx *ctx, const b200_mul_mat_args *a, const b200_ga
     const int64_t nb = a->ne00 / B200_QK;
     B200_REQUIRE(ctx, a->src0_block_off >= 0 && a->src0_block_off + nb * a->ne01 <= a->src0_nblocks_total, B200_ERR_INVALID);
     B200_REQUIRE(ctx, ((uintptr_t)a->src1_dev & 15) == 0, B200_ERR_UNSUPPORTED);
-    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, b200_use_device(ctx->device));
     const int qsb = b200_qs_bytes(a->type);
     b200_gemv_params p;
     memset(&p, 0, sizeof(p));
@@ -267,7 +267,7 @@ int b200_mul_mat_gather_batch(b200_ctx *ctx, const b200_mul_mat_args *args, cons
         }
         int rc = B200_OK;
         if (run >= 2) {
-            B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+            B200_CUDA_TRY(ctx, b200_use_device(ctx->device));
             if (b200_try_launch_gemv_stream_batch(ctx, ps, run, &rc)) {
                 if (rc != B200_OK) return rc;
                 i += run;
@@ -283,7 +283,7 @@ int b200_mul_mat_gather_batch(b200_ctx *ctx, const b200_mul_mat_args *args, cons
 
 int b200_gather_finish(b200_ctx *ctx, const b200_gather *g, const void *ll_src_dev, float *dense_out_dev, int64_t count) {
     B200_REQUIRE(ctx, ctx && gather_ok(g) && g->wait_slot >= 0 && ll_src_dev && dense_out_dev && count > 0, B200_ERR_INVALID);
-    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, b200_use_device(ctx->device));
     return b200_launch_gather_finish(ctx, *g, ll_src_dev, dense_out_dev, count);
 }
 
@@ -291,7 +291,7 @@ int b200_block_dots(b200_ctx *ctx, int type, const void *src0_dev, int64_t k, in
                     int32_t *out_dev, int path) {
     B200_REQUIRE(ctx, ctx && quant_type_ok(type), B200_ERR_INVALID);
     B200_REQUIRE(ctx, k > 0 && k % B200_QK == 0 && m > 0 && n > 0, B200_ERR_INVALID);
-    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, b200_use_device(ctx->device));
     const int64_t nb = k / 32;
     const int qsb = b200_qs_bytes(type);
     const uint8_t *qs = (const uint8_t *)src0_dev;
@@ -335,7 +335,7 @@ int b200_mul_mat_host(b200_ctx *ctx, int type, const void *src0_dev, int64_t k, 
                       float *dst_host) {
     B200_REQUIRE(ctx, ctx && quant_type_ok(type), B200_ERR_INVALID);
     B200_REQUIRE(ctx, k > 0 && k % B200_QK == 0 && m > 0 && n > 0, B200_ERR_INVALID);
-    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, b200_use_device(ctx->device));
     // host-visible io scratch lives behind the activation scratch (the GEMM path grows ws itself, so use stage)
     const size_t x_bytes = b200_align_up((size_t)n * k * 4, 256), y_bytes = b200_align_up((size_t)n * m * 4, 256);
     int rc = b200_stage_reserve(ctx, x_bytes + y_bytes);

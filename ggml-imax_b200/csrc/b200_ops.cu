@@ -259,6 +259,55 @@ __global__ void __launch_bounds__(256) norm_kernel(T4 a, T4 d, const float *__re
     }
 }
 
+// rows of up to 128 * VPL floats, 16-byte aligned: ONE warp per row keeps the row in registers -- every load of the row (and of gain /
+// bias) is issued before the first reduction, so a decode step pays one memory latency instead of three, and no CTA barrier at all
+template <bool RMS, int VPL>
+__global__ void __launch_bounds__(128) norm_warp_kernel(T4 a, T4 d, const float *__restrict__ gain, const float *__restrict__ bias, float eps, int64_t nrows) {
+    const int lane = threadIdx.x & 31;
+    int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= nrows) return;
+    const int64_t i3 = r / (a.ne2 * a.ne1);
+    r -= i3 * a.ne2 * a.ne1;
+    const int64_t i2 = r / a.ne1, i1 = r - i2 * a.ne1;
+    const float4 *x = reinterpret_cast<const float4 *>(a.p + i3 * a.nb3 + i2 * a.nb2 + i1 * a.nb1);
+    float4 *y = reinterpret_cast<float4 *>(d.p + i3 * d.nb3 + i2 * d.nb2 + i1 * d.nb1);
+    const int n4 = (int)(a.ne0 >> 2);
+    float4 v[VPL], g[VPL], b[VPL];
+#pragma unroll
+    for (int j = 0; j < VPL; j++) {
+        const int i = lane + 32 * j;
+        v[j] = i < n4 ? x[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gain) g[j] = i < n4 ? reinterpret_cast<const float4 *>(gain)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) b[j] = i < n4 ? reinterpret_cast<const float4 *>(bias)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float inv_n = 1.0f / (float)a.ne0;
+    float mean = 0.f;
+    if (!RMS) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPL; j++) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+        mean = warp_sum(s) * inv_n;
+    }
+    float s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; j++) {
+        if (lane + 32 * j < n4) {
+            v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+            s2 += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+        }
+    }
+    const float scale = 1.0f / sqrtf(warp_sum(s2) * inv_n + eps);
+#pragma unroll
+    for (int j = 0; j < VPL; j++) {
+        const int i = lane + 32 * j;
+        if (i >= n4) continue;
+        float4 o = make_float4(v[j].x * scale, v[j].y * scale, v[j].z * scale, v[j].w * scale);
+        if (gain) { o.x *= g[j].x; o.y *= g[j].y; o.z *= g[j].z; o.w *= g[j].w; }
+        if (bias) { o.x += b[j].x; o.y += b[j].y; o.z += b[j].z; o.w += b[j].w; }
+        y[i] = o;
+    }
+}
+
 // ---- SOFT_MAX (+ scale, + mask with ALiBi slope, + causal mask) ------------------------------------------------------------------------------
 // one CTA per row: w = x * scale + slope * mask[row % ne1] (and -inf where i > n_past + row % ne1 when the DIAG_MASK_INF in front was
 // folded in), y = exp(w - max) / sum.  Three passes over the row, the last one writes: in-place safe.
@@ -404,6 +453,36 @@ __global__ void __launch_bounds__((TM / RM) * (TN / RN)) mul_mat_dense_kernel(T4
     }
 }
 
+// decode shapes (N <= 8 columns): one warp per row of src0, lanes along k, every load of the row in flight at once; the row of src0 is
+// read once for all N columns.  K*Q of a decode step is m = n_past + 1 rows of 64 floats per head, V*P is 64 rows of n_past + 1.
+template <typename A, int NC>
+__global__ void __launch_bounds__(256) mul_mat_dense_rows_kernel(T4 a, T4 b, T4 d, int64_t r2, int64_t r3) {
+    const int lane = threadIdx.x & 31;
+    const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= a.ne1) return;
+    const int64_t i2 = blockIdx.y % d.ne2, i3 = blockIdx.y / d.ne2;
+    const A *row = reinterpret_cast<const A *>(a.p + (i3 / r3) * a.nb3 + (i2 / r2) * a.nb2 + m * a.nb1);
+    const char *bp = b.p + i3 * b.nb3 + i2 * b.nb2;
+    const int64_t K = a.ne0;
+    float acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) acc[c] = 0.f;
+    for (int64_t k = lane; k < K; k += 32) {
+        const float w = (float)row[k];
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+            if (c < b.ne1) acc[c] = fmaf(w, reinterpret_cast<const float *>(bp + c * b.nb1)[k], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) acc[c] = warp_sum(acc[c]);
+    if (lane == 0) {
+        char *dp = d.p + i3 * d.nb3 + i2 * d.nb2;
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+            if (c < b.ne1) reinterpret_cast<float *>(dp + c * d.nb1)[m] = acc[c];
+    }
+}
+
 int finish(b200_ctx *ctx, const char *what) {
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -418,7 +497,7 @@ int finish(b200_ctx *ctx, const char *what) {
 
 #define OPS_ENTER(ctx)                                                       \
     if (!(ctx)) return B200_ERR_INVALID;                                     \
-    B200_CUDA_TRY((ctx), cudaSetDevice((ctx)->device))
+    B200_CUDA_TRY((ctx), b200_use_device((ctx)->device))
 
 extern "C" {
 
@@ -533,6 +612,16 @@ int b200_op_norm(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *gain
     B200_REQUIRE(ctx, nr < (1ll << 31), B200_ERR_UNSUPPORTED);
     const int threads = src0->ne[0] <= 64 ? 32 : (src0->ne[0] <= 256 ? 64 : (src0->ne[0] <= 1024 ? 128 : 256));
     const float *g = gain ? static_cast<const float *>(gain->data) : nullptr, *b = bias ? static_cast<const float *>(bias->data) : nullptr;
+    const int64_t ne0 = src0->ne[0];
+    if (ne0 % 4 == 0 && ne0 <= 1024 && aligned16(src0) && aligned16(dst) && ((uintptr_t)g & 15) == 0 && ((uintptr_t)b & 15) == 0) {
+        const unsigned blocks = (unsigned)((nr + 3) / 4);
+        const T4 a = view(src0), d = view(dst);
+#define B200_NORM_WARP(R, V) norm_warp_kernel<R, V><<<blocks, 128, 0, ctx->stream>>>(a, d, g, b, eps, nr)
+        if (ne0 <= 256) { if (rms) B200_NORM_WARP(true, 2); else B200_NORM_WARP(false, 2); }
+        else { if (rms) B200_NORM_WARP(true, 8); else B200_NORM_WARP(false, 8); }
+#undef B200_NORM_WARP
+        return finish(ctx, "norm");
+    }
     if (rms) norm_kernel<true><<<(unsigned)nr, threads, 0, ctx->stream>>>(view(src0), view(dst), g, b, eps);
     else norm_kernel<false><<<(unsigned)nr, threads, 0, ctx->stream>>>(view(src0), view(dst), g, b, eps);
     return finish(ctx, "norm");
@@ -619,9 +708,12 @@ int b200_op_mul_mat_dense(b200_ctx *ctx, const b200_tensor *src0, const b200_ten
         return B200_OK;
     }
     if (N <= 8) {
-        const dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 7) / 8), (unsigned)batch);
-        if (src0->type == B200_TYPE_F32) mul_mat_dense_kernel<float, 64, 8, 2, 1><<<grid, 256, 0, ctx->stream>>>(a, b, d, r2, r3);
-        else mul_mat_dense_kernel<__half, 64, 8, 2, 1><<<grid, 256, 0, ctx->stream>>>(a, b, d, r2, r3);
+        const dim3 grid((unsigned)((M + 7) / 8), (unsigned)batch, 1);
+#define B200_ROWS(NC)                                                                                                           \
+    if (src0->type == B200_TYPE_F32) mul_mat_dense_rows_kernel<float, NC><<<grid, 256, 0, ctx->stream>>>(a, b, d, r2, r3);     \
+    else mul_mat_dense_rows_kernel<__half, NC><<<grid, 256, 0, ctx->stream>>>(a, b, d, r2, r3)
+        if (N == 1) { B200_ROWS(1); } else if (N <= 4) { B200_ROWS(4); } else { B200_ROWS(8); }
+#undef B200_ROWS
     } else {
         const dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64), (unsigned)batch);
         if (src0->type == B200_TYPE_F32) mul_mat_dense_kernel<float, 64, 64, 4, 4><<<grid, 256, 0, ctx->stream>>>(a, b, d, r2, r3);

@@ -66,7 +66,7 @@ static int launch_quantize(b200_ctx *ctx, bool wire, const float *x_dev, int64_t
     B200_REQUIRE(ctx, k > 0 && k % 32 == 0 && nrows >= 0, B200_ERR_INVALID);
     B200_REQUIRE(ctx, ((uintptr_t)x_dev & 15) == 0 && (row_stride_bytes & 15) == 0, B200_ERR_UNSUPPORTED);
     if (nrows == 0) return B200_OK;
-    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, b200_use_device(ctx->device));
     const int64_t total = nrows * (k / 32) * 8;
     int64_t grid = (total + 255) / 256;
     const int64_t cap = (int64_t)ctx->sm_count * 16;

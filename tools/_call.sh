@@ -1,10 +1,5 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_ops.py -x -q > gpurun_out/r02_ops_tests.log 2>&1; tail -15 gpurun_out/r02_ops_tests.log
-for f in 1 0; do timeout 600 oracle/_ref/gpt2-sched-harness q4_0 128 8 8 $f > gpurun_out/r02_gpt2_q4_0_fuse$f.json 2> gpurun_out/r02_gpt2_q4_0.err; python - <<PY
-import json
-r=json.loads(open('gpurun_out/r02_gpt2_q4_0_fuse$f.json').read().strip().splitlines()[-1])
-print('fuse=$f', 'ok', r.get('ok'), 'fused', r.get('b200_fused_nodes_total'), [(s['n'], s['ms_b200_whole_graph'], s['b200_launches'], s['graph_nodes'], '%.2e'%s['b200_whole_graph_logits_nmse_vs_cpu']) for s in r['steps']])
-PY
-done
-tail -5 gpurun_out/r02_gpt2_q4_0.err
-timeout 900 python -m pytest tests/test_gpu_gpt2_backend.py tests/test_gpu_gpt2_sched.py tests/test_gpu_backend_ops.py tests/test_gpu_dropin_graph.py -x -q -s > gpurun_out/r02_gpt2_backend.log 2>&1; grep -E "gpt-2-backend|passed|failed|Error" gpurun_out/r02_gpt2_backend.log | tail -12
+timeout 900 python -m pytest tests/test_gpu_gemm_f16.py -x -q > gpurun_out/r02_gemm_tests.log 2>&1; tail -4 gpurun_out/r02_gemm_tests.log
+for a in 0 2; do timeout 300 python tools/gemm_timeline.py q4_0 28672 8192 512 $a 2>&1 | grep -E "launch|first MMA|unit 0: MMAs"; done
+timeout 300 python tools/gemm_timeline.py q4_0 2>&1 | tail -9
+timeout 600 python tools/ab_gemm.py > gpurun_out/r02_ab_gemm_ts2.log 2>&1; cat gpurun_out/r02_ab_gemm_ts2.log | tail -20
