@@ -60,7 +60,8 @@ template <int TYPE> struct RawTile {
     static constexpr int kSB = 8;
     static constexpr int kSR = 8;
     static_assert(kSR % kDeqGroups == 0, "a raw stage always belongs to the same dequantization group");
-    static constexpr int kBars = 2 * kSB + (1 + kDeqGroups) * kSR + 2 * kStagesF + 2;   // b_full, b_empty | raw_empty, raw_full (x groups) | a_ready, empty | tmem_full, tmem_empty
+    static constexpr int kBars = (1 + kDeqGroups) * kSR + 2 * kStagesF + 2;   // raw_empty, raw_full (x groups) | full, empty | tmem_full, tmem_empty
+    static_assert(kSB == kStagesF, "the X' stages and the W' stages share their barriers");
     static constexpr int kSmem = kSB * kStageF + kSR * kBytes + 1024 + kBars * 8 + 64;
     static_assert(kSmem <= 227 * 1024, "shared memory");
     static constexpr int kPfSteps = 256 / kRow;                              // k-steps per 256-byte L2 prefetch box row (8 / 4)
@@ -205,6 +206,13 @@ struct GemmF16Args {
                                  // first unit issued, 3 first accumulator complete, 4 first unit stored, 5 last unit stored, 6 all k-slices arrived, 7 end
     Sched sc;
 };
+// measurement only (ablate bit 2): cycle counters of one dequantization warp per group and of the MMA thread, written into the trace
+// region of the FOLLOWING launch slot: [blockIdx.x][8] = dequant g0 {raw wait, convert, flush, W' wait, st} / MMA {X' wait, W' wait, issue}
+__device__ __forceinline__ long long clk() {
+    long long c;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c));
+    return c;
+}
 __device__ __forceinline__ void gstamp(unsigned long long *trace, int slot) {
     if (trace) trace[(size_t)blockIdx.x * 8 + slot] = gtimer();
 }
@@ -229,17 +237,19 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
     constexpr int SB = RT::kSB, SR = RT::kSR;
     unsigned char *rawtiles = smem + SB * kStageF;
     uint64_t *bars = reinterpret_cast<uint64_t *>(rawtiles + SR * RT::kBytes);
-    uint64_t *b_full = bars;                          // [SB] leader: both halves of the X' tile of a k-step have landed
-    uint64_t *b_empty = b_full + SB;                  // [SB] local: the MMAs that read this X' stage have completed
+    // full: [kStagesF] LEADER: everything the MMAs of a k-step need -- both halves of the X' tile (transaction bytes, armed by the leader's
+    // producer) and both CTAs' W' columns (one arrival per dequantization warp of the group that owns the stage).  ONE barrier, and one
+    // tcgen05.commit per k-step: the single MMA-issuing thread is the kernel's critical resource (measured: two waits + four MMAs + two
+    // commits = 610 cycles per k-step, more than the 512 cycles the tensor pipe needs for them).
+    uint64_t *full = bars;
     // raw_full: [group][SR], local: this CTA's raw weight rows of a k-step have landed.  One barrier per (group, stage): a group
     // only waits for ITS k-steps, and a parity wait that skips a phase can pass a fill early (seen as one warp's 32 rows of a tile
     // going wrong once in ~40 launches): every waiter must see consecutive phases.
-    uint64_t *raw_full = b_empty + SB;
+    uint64_t *raw_full = full + kStagesF;
     // raw_empty: [SR] local: the dequantization warps have the stage's raw rows in registers (the raw ring is released here, not by
     // the MMAs)
     uint64_t *raw_empty = raw_full + kDeqGroups * SR;
-    uint64_t *a_ready = raw_empty + SR;               // [kStagesF] leader: both CTAs' W' columns are written (one group's warps of each CTA)
-    uint64_t *empty = a_ready + kStagesF;             // [kStagesF] local: the MMAs that read these W' columns have completed
+    uint64_t *empty = raw_empty + SR;                 // [kStagesF] local: the MMAs that read this stage (X' rows and W' columns) have completed
     uint64_t *tmem_full = empty + kStagesF;           // local: the unit's accumulator is complete
     uint64_t *tmem_empty = tmem_full + 1;             // leader: both CTAs' epilogues have drained the accumulator (8 arrivals)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
@@ -258,14 +268,10 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dw_pf) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < SB; s++) {
-            mbar_init(&b_full[s], 1);
-            mbar_init(&b_empty[s], 1);
-        }
         for (int s = 0; s < kDeqGroups * SR; s++) mbar_init(&raw_full[s], 1);
         for (int s = 0; s < SR; s++) mbar_init(&raw_empty[s], kDeqWarps / kDeqGroups);
         for (int s = 0; s < kStagesF; s++) {
-            mbar_init(&a_ready[s], 2 * kDeqWarps / kDeqGroups);
+            mbar_init(&full[s], 1 + 2 * kDeqWarps / kDeqGroups);      // the leader's arrive.expect_tx + the dequantization warps of both CTAs
             mbar_init(&empty[s], 1);
         }
         mbar_init(tmem_full, 1);
@@ -296,9 +302,9 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
                 for (int ks = u.ks0; ks < u.ks1; ks++, it++) {
                     const int s = it % SB;
                     const uint32_t ph = (uint32_t)(it / SB) & 1u;
-                    mbar_wait(&b_empty[s], ph ^ 1u);
-                    if (rank == 0) mbar_expect_tx(&b_full[s], 2 * kBTile);
-                    tma_load_2d_pair(smem_b + (uint32_t)(s * kStageF), &map_b, ks * 128, n0, smem_u32(&b_full[s]) & kPeerMask);
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    if (rank == 0) mbar_expect_tx(&full[s], 2 * kBTile);
+                    tma_load_2d_pair(smem_b + (uint32_t)(s * kStageF), &map_b, ks * 128, n0, smem_u32(&full[s]) & kPeerMask);
                 }
             }
         }
@@ -347,28 +353,54 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
         // ===== MMA issuer: one thread of the LEADER CTA issues for the pair =====
         if (lane == 0 && rank == 0) {
             int it = 0, ui = 0;
+            const bool mprof = (g.ablate & 4) && g.trace;
+            long long macc[4] = {0, 0, 0, 0}, macc_c0 = 0, macc_t0 = 0;
             Unit u;
             for (int i = 0; get_unit(sc, pair, i, u); i++, ui++) {
                 mbar_wait_cluster(smem_u32(tmem_empty), ((uint32_t)ui & 1u) ^ 1u);     // both epilogues have drained the accumulator of the previous unit
                 tc_fence_after();
                 const uint32_t td = tmem_base;
+                bool have = false;                   // the barrier of this k-step was already waited for (between the MMAs of the previous one)
                 for (int ks = u.ks0; ks < u.ks1; ks++, it++) {
-                    const int s = it % kStagesF, sb = it % SB;
-                    const uint32_t ph = (uint32_t)(it / kStagesF) & 1u, phb = (uint32_t)(it / SB) & 1u;
-                    mbar_wait_cluster(smem_u32(&b_full[sb]), phb);
-                    mbar_wait_cluster(smem_u32(&a_ready[s]), ph);
+                    const int s = it % kStagesF, sb = s;
+                    const uint32_t ph = (uint32_t)(it / kStagesF) & 1u;
+                    const long long m0k = mprof ? clk() : 0;
+                    if (!have) mbar_wait_cluster(smem_u32(&full[s]), ph);
                     tc_fence_after();
-                    if (it == 0) gstamp(g.trace, 1);
+                    const long long m2k = mprof ? clk() : 0;
+                    const long long m1k = m2k;
+                    if (it == 0) {
+                        gstamp(g.trace, 1);
+                        if (mprof) { macc_c0 = clk(); macc_t0 = (long long)gtimer(); }
+                    }
                     const uint32_t ta = tmem_base + (uint32_t)(kAccCols + s * kACols);
                     const uint64_t db = make_desc_sw128(smem_b + (uint32_t)(sb * kStageF));
 #pragma unroll
-                    for (int j = 0; j < 4; j++)      // K = 16 fp16 per MMA: 8 columns of the W' stage, 32 bytes (+2 in the >>4 start-address field) of the X' rows
+                    for (int j = 0; j < 4; j++) {    // K = 16 fp16 per MMA: 8 columns of the W' stage, 32 bytes (+2 in the >>4 start-address field) of the X' rows
+                        if (j == 3) {
+                            // the wait for the NEXT k-step goes here, while three MMAs are queued or running: the issuing thread is the
+                            // kernel's critical resource and a wait at the top of the loop lets the tensor pipe run dry (~100 cycles per k-step)
+                            have = ks + 1 < u.ks1;
+                            if (have) {
+                                const int s1 = (it + 1) % kStagesF;
+                                mbar_wait_cluster(smem_u32(&full[s1]), (uint32_t)((it + 1) / kStagesF) & 1u);
+                            }
+                        }
                         if (j == 0 || !(g.ablate & 2)) tc_mma_f16_pair_ts(td, ta + (uint32_t)(j * 8), db + (uint64_t)(j * 2), kIdescF16x2, (ks > u.ks0 || j > 0) ? 1u : 0u);
-                    tc_commit_pair(smem_u32(&b_empty[sb]));       // both CTAs: the X' stage may be refilled ...
-                    tc_commit_pair(smem_u32(&empty[s]));          // ... and the W' columns rewritten
+                    }
+                    tc_commit_pair(smem_u32(&empty[s]));          // both CTAs: the X' stage may be refilled and the W' columns rewritten
+                    if (mprof) {
+                        const long long m3k = clk();
+                        macc[0] += m1k - m0k; macc[1] += m2k - m1k; macc[2] += m3k - m2k; macc[3] += 1;
+                    }
                 }
                 tc_commit_pair(smem_u32(tmem_full));              // both CTAs: the accumulator is complete
                 if (ui == 0) gstamp(g.trace, 2);
+            }
+            if (mprof) {
+                for (int j = 0; j < 4; j++) g.trace[(size_t)(B200_TRACE_MAX_CTAS + blockIdx.x) * 8 + j] = (unsigned long long)macc[j];
+                g.trace[(size_t)(B200_TRACE_MAX_CTAS + blockIdx.x) * 8 + 4] = (unsigned long long)(clk() - macc_c0);              // SM cycles ...
+                g.trace[(size_t)(B200_TRACE_MAX_CTAS + blockIdx.x) * 8 + 5] = (unsigned long long)((long long)gtimer() - macc_t0);   // ... in this many ns
             }
         }
     } else if (warp >= 8) {
@@ -383,7 +415,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
         const int r = quad * 32 + lane;
         const __half2 bias_lo = TYPE == B200_TYPE_Q4_0 ? __floats2half2_rn(1032.f, 1032.f) : __floats2half2_rn(1152.f, 1152.f);
         const __half2 bias_hi = __floats2half2_rn(72.f, 72.f);
-        const uint32_t leader_ready = smem_u32(a_ready) & kPeerMask;
+        const uint32_t leader_ready = smem_u32(full) & kPeerMask;
         // where TMA's 32 / 64-byte swizzle puts 16-byte piece j of this row: j ^ (bits 7.. of the row's offset)
         const uint32_t rsw = TYPE == B200_TYPE_Q4_0 ? (uint32_t)((r >> 2) & 1) : (uint32_t)((r >> 1) & 3);
         const uint32_t raw_a = smem_u32(rawtiles) + (uint32_t)(r * RT::kRow);
@@ -391,6 +423,9 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
         int it = grp;                           // this group's k-steps of the pair's flattened sequence: grp, grp + 2, ... (stage it % kStagesF:
                                                 // always one of this group's stages, each revisited every kStagesF k-steps)
         int base = 0;                           // flattened index of the unit's first k-step
+        int pend_s = -1;                        // W' stage whose tcgen05.st is in flight (its arrival is still owed)
+        const bool prof = (g.ablate & 4) && g.trace && quad == 0 && lane == 0 && grp == 0;
+        long long pacc[6] = {0, 0, 0, 0, 0, 0};
         Unit u;
         for (int i = 0; get_unit(sc, pair, i, u); i++) {
             const int len = u.ks1 - u.ks0;
@@ -410,7 +445,9 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
                 b1 = ldd(ks + 2 * kDeqGroups, 1);
                 const int s = it % kStagesF, sr = it % SR;
                 const uint32_t ph = (uint32_t)(it / kStagesF) & 1u, phr = (uint32_t)(it / SR) & 1u;
+                const long long c0k = prof ? clk() : 0;
                 mbar_wait(&raw_full[grp * SR + sr], phr);
+                const long long c1k = prof ? clk() : 0;
                 uint4 q[RT::kRow / 16];
 #pragma unroll
                 for (int j = 0; j < RT::kRow / 16; j++) q[j] = lds128f(raw_a + (uint32_t)(sr * RT::kBytes) + ((((uint32_t)j) ^ rsw) << 4));
@@ -450,18 +487,37 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
                 // the raw rows are in registers (the conversions above consumed them): the stage may be refilled
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&raw_empty[sr]);
+                // the PREVIOUS k-step's tcgen05.st has had a whole conversion to complete: order it before the arrival, then one arrival
+                // per warp on the leader's barrier (software-pipelined so that no warp idles on tcgen05.wait::st)
+                const long long c2k = prof ? clk() : 0;
+                if (pend_s >= 0) {
+                    tc_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(leader_ready + (uint32_t)(pend_s * 8));
+                }
+                const long long c3k = prof ? clk() : 0;
                 // the stage's W' columns are free once the MMAs that read their previous contents have completed
                 mbar_wait(&empty[s], ph ^ 1u);
                 tc_fence_after();
+                const long long c4k = prof ? clk() : 0;
                 tc_st32(ta0 + (uint32_t)(s * kACols), wq);
-                tc_wait_st();
-                // the columns are written: order them before the arrival, then one arrival per warp on the leader's barrier
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(leader_ready + (uint32_t)(s * 8));
+                pend_s = s;
+                if (prof) {
+                    const long long c5k = clk();
+                    pacc[0] += c1k - c0k; pacc[1] += c2k - c1k; pacc[2] += c3k - c2k; pacc[3] += c4k - c3k; pacc[4] += c5k - c4k; pacc[5] += 1;
+                }
             }
             base += len;
         }
+        if (pend_s >= 0) {
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_ready + (uint32_t)(pend_s * 8));
+        }
+        if (prof && rank == 1)
+            for (int j = 0; j < 6; j++) g.trace[(size_t)(B200_TRACE_MAX_CTAS + blockIdx.x) * 8 + j] = (unsigned long long)pacc[j];
     } else if (warp >= 4) {
         // ===== epilogue: warp q of 4 owns TMEM lanes 32q.. = weight rows; whole tiles go straight to dst, k-slices through
         // the split-k workspace =====
@@ -679,7 +735,8 @@ int b200_launch_gemm_f16(b200_ctx *ctx, int type, const uint8_t *qs, const __hal
     B200_REQUIRE(ctx, scratch != NULL && dst != NULL, B200_ERR_INVALID);
     B200_REQUIRE(ctx, m < (1 << 30) && n < (1 << 30) && k < (1 << 30), B200_ERR_UNSUPPORTED);
     B200_REQUIRE(ctx, ((uintptr_t)x & 15) == 0 && (x_row_stride & 15) == 0, B200_ERR_UNSUPPORTED);
-    const int pairs = ctx->sm_count / 2;
+    int pairs = ctx->sm_count / 2;
+    if ((ctx->opt_gemm_ablate >> 8) > 0 && (ctx->opt_gemm_ablate >> 8) < pairs) pairs = ctx->opt_gemm_ablate >> 8;      // measurement only: fewer pairs
     B200_REQUIRE(ctx, pairs >= 1, B200_ERR_UNSUPPORTED);
     const int64_t nb = k / 32;
     const int qsb = b200_qs_bytes(type);

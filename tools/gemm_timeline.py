@@ -24,17 +24,28 @@ with qmm.Context(0) as ctx:
     for _ in range(3):
         ctx.mul_mat_device(w, x.ptr, n, y.ptr)
     ctx.synchronize()
-    nl = 4
+    nl = 4 if not (ablate & 4) else 2
     tb = ctx.alloc(nl * 160 * 8 * 8)
     ctx.memset(tb, 0, nl * 160 * 8 * 8) if hasattr(ctx, "memset") else tb.upload(np.zeros(nl * 160 * 8, np.uint64))
     ctx.set_trace(tb, nl)
-    for _ in range(nl):
+    for _ in range(nl if not (ablate & 4) else 1):
         ctx.mul_mat_device(w, x.ptr, n, y.ptr)
     ctx.synchronize()
     ctx.set_trace(None, 0)
     t = tb.download(np.uint64, nl * 160 * 8).reshape(nl, 160, 8).astype(np.int64)
     # the GEMV-class kernels (quantize) do not take slots; every slot is one GEMM launch
-    for l in range(nl - 1, nl):
+    if ablate & 4:
+        t2 = t[1]
+        mma = t2[0::2][t2[0::2, 3] > 0]
+        deq = t2[1::2][t2[1::2, 5] > 0]
+        if mma.size:
+            c = mma[:, 3].astype(np.float64)
+            print(f"MMA thread, cycles per k-step (median over {len(mma)} leaders, {int(np.median(c))} k-steps): wait X' {np.median(mma[:, 0] / c):7.1f}  wait W' {np.median(mma[:, 1] / c):7.1f}  issue+commit {np.median(mma[:, 2] / c):7.1f}   SM clock {np.median(mma[:, 4] / np.maximum(mma[:, 5], 1)):5.3f} GHz, {np.median(mma[:, 4] / c):6.1f} cycles per k-step in all")
+        if deq.size:
+            c = deq[:, 5].astype(np.float64)
+            print(f"dequant warp (group 0), cycles per own k-step (median over {len(deq)} CTAs, {int(np.median(c))} k-steps): wait raw {np.median(deq[:, 0] / c):7.1f}  lds+convert {np.median(deq[:, 1] / c):7.1f}  "
+                  f"flush prev st {np.median(deq[:, 2] / c):7.1f}  wait W' free {np.median(deq[:, 3] / c):7.1f}  st issue {np.median(deq[:, 4] / c):7.1f}")
+    for l in range(0 if ablate & 4 else nl - 1, 1 if ablate & 4 else nl):
         tl = t[l]
         live = tl[:, 0] > 0
         t0 = tl[live, 0].min()
