@@ -27,7 +27,6 @@ struct b200_ctx {
     int          opt_gemm;
     int          opt_gemv_max_n;
     int          opt_gemv_stream;
-    int          opt_gemm_ablate;       // measurement only: see GemmF16Args::ablate
     int          opt_gemm_exact;        // 1: prefill GEMM = exact int8 block dots + fp32 scaling (slow); 0: fp16 tcgen05 path
     // decode plans (b200_plan.cu)
     int          opt_plan_pub_min_k;    // shortest in-plan src1 that is quantized once per GPU (0 = never)

@@ -158,7 +158,6 @@ int b200_ctx_set_option(b200_ctx *ctx, const char *key, int64_t value) {
         return B200_OK;
     }
     if (!strcmp(key, "gemm_exact")) { ctx->opt_gemm_exact = value != 0; return B200_OK; }
-    if (!strcmp(key, "gemm_ablate")) { ctx->opt_gemm_ablate = (int)value; return B200_OK; }
     if (!strcmp(key, "plan_pub_min_k")) { ctx->opt_plan_pub_min_k = value > 0 ? (int)value : 0; return B200_OK; }
     if (!strcmp(key, "plan_pub_dist")) { ctx->opt_plan_pub_dist = value >= 1 ? (int)value : 1; return B200_OK; }
     if (!strcmp(key, "plan_l2_window")) { ctx->opt_plan_l2_window = value > 0 ? (int)(value > 4096 ? 4096 : value) : 0; return B200_OK; }

@@ -1,3 +1,5 @@
+// NOT PART OF THE PRODUCT BUILD.  The tensor-memory-A variant of ggml-imax_b200/csrc/b200_gemm_f16.cu measured in round 2 (profiles/r02_experiments.md, 'second pass'):
+// drop-in replacement for that file (same entry points; needs opt_gemm_ablate in b200_ctx), passes tests/test_gpu_gemm_f16.py; kept for the next round.
 // b200_gemm_f16.cu -- the prefill path (n >= 32): dst[n][m] = W[m,k] x X[n,k]^T as ONE dense contraction on the 5th-generation
 // tensor cores, fp16 operands, fp32 accumulation in TMEM.
 //
@@ -25,11 +27,6 @@
 //     pairs; the partial accumulators meet in an L2-resident workspace and are summed in a FIXED order (part 0, 1, 2, ...), each
 //     pair reducing its own column slice -- deterministic, no atomics.
 //
-// Measured alternative, not shipped (profiles/r02_experiments.md): W' written by tcgen05.st into TENSOR memory and taken from there as the A operand
-// (no shared-memory W' stages, no proxy fence) -- correct (all parity tests), +3-5 % on shapes with >= 3 tiles per pair, but it leaves room
-// for only ONE accumulator, so the ~3 us accumulator drain per tile is exposed: -6 % on C2 and -5 % on the GPT-J prefill.  The same pass showed
-// where the main loop stands: the MMA-issuing thread needs 520-580 cycles per k-step against the tensor pipe's 512.
-//
 // CTA = 16 warps: warp 0 TMA producer of the X' tile, warp 3 TMA producer of the raw weight rows (+ L2 prefetch), warp 1 MMA issuer
 // (leader CTA only), warp 2 TMEM allocator, warps 4-7 epilogue (one per TMEM lane quadrant), warps 8-15 dequantization (thread = weight row x one block of 32).
 #include "b200_tc_common.cuh"
@@ -41,21 +38,34 @@ namespace {
 constexpr int TM = 128;                 // weight rows per CTA (tile M = 256 per pair)
 constexpr int TN = 256;                 // activation rows (dst columns) per tile; each CTA stages 128 of them
 constexpr int KSTEP = 64;               // k per pipeline stage = 128 bytes of fp16 = 2 quant blocks
-constexpr int kStagesF = 5;
-constexpr int kATile = TM * 128;        // 16 KB
-constexpr int kBTile = (TN / 2) * 128;  // 16 KB
-constexpr int kStageF = kATile + kBTile;               // 32 KB, a multiple of 1024
+constexpr int kStagesF = 8;             // W' stages in tensor memory
+constexpr int kBTile = (TN / 2) * 128;  // 16 KB: this CTA's half of the X' tile of a k-step
+constexpr int kStageF = kBTile;         // shared memory per stage besides the raw weight rows (a multiple of 1024)
+constexpr int kAccCols = TN;            // TMEM: the accumulator, 256 fp32 columns ...
+constexpr int kACols = KSTEP / 2;       // ... then per stage the W' tile of a k-step: 128 lanes (rows) x 64 fp16 = 32 columns
+static_assert(kAccCols + kStagesF * kACols <= 512, "TMEM columns");
 constexpr int kThreadsF = 16 * 32;
 constexpr int kDeqWarps = 8;
 constexpr int kDeqGroups = 2;             // groups of kDeqWarps / kDeqGroups warps that take alternate k-steps
 constexpr int kEpiWarpsF = 4;
-constexpr int kBarsF = (3 + kDeqGroups) * kStagesF + 4;   // raw_full (x groups), b_full, a_ready, empty (x stages), tmem_full[2], tmem_empty[2]
+static_assert(kStagesF % kDeqGroups == 0, "a stage always belongs to the same dequantization group");
 // raw weight tiles: per stage 128 rows x (32 | 64) bytes of the qs plane (both blocks of the k-step), TMA with the 32 / 64-byte
 // swizzle so that thread = row reads its 16-byte pieces without bank conflicts
 template <int TYPE> struct RawTile {
     static constexpr int kRow = TYPE == B200_TYPE_Q4_0 ? 32 : 64;
     static constexpr int kBytes = TM * kRow;                                 // 4 KB / 8 KB
-    static constexpr int kSmem = kStagesF * (kStageF + kBytes) + 1024 + kBarsF * 8 + 64;
+    // THREE rings with their own depths: X' in shared memory (kSB stages of 16 KB, released by the MMAs that read them), the raw weight
+    // rows (kSR stages, released as soon as they are in registers) and the W' stages in tensor memory (kStagesF).  Deeper X' rings were
+    // measured SLOWER (11 stages: +8 % time): the loop is not latency-bound but bound by what L2 delivers -- per k-step every SM takes
+    // 16 KB of X' + 4-8 KB of raw rows, 39-47 B/clk/SM = 5800-6900 B/clk for the chip against ~6300 B/clk of L2 throughput -- and more
+    // loads in flight only add contention.
+    static constexpr int kSB = 8;
+    static constexpr int kSR = 8;
+    static_assert(kSR % kDeqGroups == 0, "a raw stage always belongs to the same dequantization group");
+    static constexpr int kBars = (1 + kDeqGroups) * kSR + 2 * kStagesF + 2;   // raw_empty, raw_full (x groups) | full, empty | tmem_full, tmem_empty
+    static_assert(kSB == kStagesF, "the X' stages and the W' stages share their barriers");
+    static constexpr int kSmem = kSB * kStageF + kSR * kBytes + 1024 + kBars * 8 + 64;
+    static_assert(kSmem <= 227 * 1024, "shared memory");
     static constexpr int kPfSteps = 256 / kRow;                              // k-steps per 256-byte L2 prefetch box row (8 / 4)
 };
 constexpr int kPfAhead = 24;             // k-steps the L2 prefetch cursor stays ahead of the copies (~6 us of MMAs)
@@ -109,6 +119,27 @@ __device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t desc_a
         "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the same with the A operand in tensor memory (lane = row, 32-bit column = two consecutive k): D[tmem] (+)= A[tmem] * B[smem desc]^T
+__device__ __forceinline__ void tc_mma_f16_pair_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// registers -> tensor memory: thread = lane (row) of its warp's quadrant, 32 consecutive 32-bit columns
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
+        "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+        "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrives on the barrier at this offset in BOTH CTAs of the pair once every MMA issued so far has completed
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar_addr) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_addr), "h"((unsigned short)3)
@@ -172,10 +203,18 @@ struct GemmF16Args {
     uint32_t *abort_host;
     int m, n, k;
     int dw_pf;               // the scale plane can be prefetched through its tensor map (row pitch a multiple of 16 bytes)
+    int ablate;              // measurement only (option "gemm_ablate", results wrong): 1 = no dequantization arithmetic, 2 = one MMA of four per k-step
     unsigned long long *trace;   // optional: this launch's [gridDim.x][8] %globaltimer stamps (b200_ctx_set_trace): 0 start, 1 first MMA, 2 MMAs of the
                                  // first unit issued, 3 first accumulator complete, 4 first unit stored, 5 last unit stored, 6 all k-slices arrived, 7 end
     Sched sc;
 };
+// measurement only (ablate bit 2): cycle counters of one dequantization warp per group and of the MMA thread, written into the trace
+// region of the FOLLOWING launch slot: [blockIdx.x][8] = dequant g0 {raw wait, convert, flush, W' wait, st} / MMA {X' wait, W' wait, issue}
+__device__ __forceinline__ long long clk() {
+    long long c;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c));
+    return c;
+}
 __device__ __forceinline__ void gstamp(unsigned long long *trace, int slot) {
     if (trace) trace[(size_t)blockIdx.x * 8 + slot] = gtimer();
 }
@@ -197,18 +236,25 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     using RT = RawTile<TYPE>;
-    unsigned char *rawtiles = smem + kStagesF * kStageF;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(rawtiles + kStagesF * RT::kBytes);
-    // raw_full: [group][stages], local: this CTA's raw weight rows of a k-step have landed.  One barrier per (group, stage): a
-    // group only waits for ITS k-steps (every other fill of a stage), and a parity wait that skips a phase can pass a fill early
-    // (seen as one warp's 32 rows of a tile going wrong once in ~40 launches): every waiter must see consecutive phases.
-    uint64_t *raw_full = bars;
-    uint64_t *b_full = bars + kDeqGroups * kStagesF;  // [stages] leader: both halves of the X' tile have landed
-    uint64_t *a_ready = b_full + kStagesF;            // [stages] leader: both CTAs' W' tiles are written (one group's warps of each CTA)
-    uint64_t *empty = a_ready + kStagesF;             // [stages] local: the MMAs that read this stage have completed
-    uint64_t *tmem_full = empty + kStagesF;           // [2] local: the unit's accumulator is complete
-    uint64_t *tmem_empty = tmem_full + 2;             // [2] leader: both CTAs' epilogues have drained the accumulator (8 arrivals)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    constexpr int SB = RT::kSB, SR = RT::kSR;
+    unsigned char *rawtiles = smem + SB * kStageF;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(rawtiles + SR * RT::kBytes);
+    // full: [kStagesF] LEADER: everything the MMAs of a k-step need -- both halves of the X' tile (transaction bytes, armed by the leader's
+    // producer) and both CTAs' W' columns (one arrival per dequantization warp of the group that owns the stage).  ONE barrier, and one
+    // tcgen05.commit per k-step: the single MMA-issuing thread is the kernel's critical resource (measured: two waits + four MMAs + two
+    // commits = 610 cycles per k-step, more than the 512 cycles the tensor pipe needs for them).
+    uint64_t *full = bars;
+    // raw_full: [group][SR], local: this CTA's raw weight rows of a k-step have landed.  One barrier per (group, stage): a group
+    // only waits for ITS k-steps, and a parity wait that skips a phase can pass a fill early (seen as one warp's 32 rows of a tile
+    // going wrong once in ~40 launches): every waiter must see consecutive phases.
+    uint64_t *raw_full = full + kStagesF;
+    // raw_empty: [SR] local: the dequantization warps have the stage's raw rows in registers (the raw ring is released here, not by
+    // the MMAs)
+    uint64_t *raw_empty = raw_full + kDeqGroups * SR;
+    uint64_t *empty = raw_empty + SR;                 // [kStagesF] local: the MMAs that read this stage (X' rows and W' columns) have completed
+    uint64_t *tmem_full = empty + kStagesF;           // local: the unit's accumulator is complete
+    uint64_t *tmem_empty = tmem_full + 1;             // leader: both CTAs' epilogues have drained the accumulator (8 arrivals)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
 
     constexpr int QSB = TYPE == B200_TYPE_Q4_0 ? 16 : 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -224,16 +270,14 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dw_pf) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kDeqGroups * kStagesF; s++) mbar_init(&raw_full[s], 1);
+        for (int s = 0; s < kDeqGroups * SR; s++) mbar_init(&raw_full[s], 1);
+        for (int s = 0; s < SR; s++) mbar_init(&raw_empty[s], kDeqWarps / kDeqGroups);
         for (int s = 0; s < kStagesF; s++) {
-            mbar_init(&b_full[s], 1);
-            mbar_init(&a_ready[s], 2 * kDeqWarps / kDeqGroups);
+            mbar_init(&full[s], 1 + 2 * kDeqWarps / kDeqGroups);      // the leader's arrive.expect_tx + the dequantization warps of both CTAs
             mbar_init(&empty[s], 1);
         }
-        for (int b = 0; b < 2; b++) {
-            mbar_init(&tmem_full[b], 1);
-            mbar_init(&tmem_empty[b], 2 * kEpiWarpsF);
-        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 2 * kEpiWarpsF);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -245,7 +289,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) gstamp(g.trace, 0);
-    const uint32_t smem_a = smem_u32(smem);
+    const uint32_t smem_b = smem_u32(smem);            // X' stages; the W' tiles live in tensor memory
 
     if (warp == 0) {
         // ===== TMA producer for X' (one thread per CTA): this CTA's 128 activation rows of the tile, stage by stage.  X' comes from
@@ -258,11 +302,11 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
             for (int i = 0; get_unit(sc, pair, i, u); i++) {
                 const int n0 = u.tn * TN + (int)rank * (TN / 2);
                 for (int ks = u.ks0; ks < u.ks1; ks++, it++) {
-                    const int s = it % kStagesF;
-                    const uint32_t ph = (uint32_t)(it / kStagesF) & 1u;
+                    const int s = it % SB;
+                    const uint32_t ph = (uint32_t)(it / SB) & 1u;
                     mbar_wait(&empty[s], ph ^ 1u);
-                    if (rank == 0) mbar_expect_tx(&b_full[s], 2 * kBTile);
-                    tma_load_2d_pair(smem_a + (uint32_t)(s * kStageF + kATile), &map_b, ks * 128, n0, smem_u32(&b_full[s]) & kPeerMask);
+                    if (rank == 0) mbar_expect_tx(&full[s], 2 * kBTile);
+                    tma_load_2d_pair(smem_b + (uint32_t)(s * kStageF), &map_b, ks * 128, n0, smem_u32(&full[s]) & kPeerMask);
                 }
             }
         }
@@ -298,10 +342,10 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
                 for (int ks = u.ks0; ks < u.ks1; ks++, it++) {
                     prefetch_more();
                     pf_ahead--;
-                    const int s = it % kStagesF;
-                    const uint32_t ph = (uint32_t)(it / kStagesF) & 1u;
-                    mbar_wait(&empty[s], ph ^ 1u);
-                    uint64_t *rf = &raw_full[(it % kDeqGroups) * kStagesF + s];      // the barrier of the group that takes this k-step
+                    const int s = it % SR;
+                    const uint32_t ph = (uint32_t)(it / SR) & 1u;
+                    mbar_wait(&raw_empty[s], ph ^ 1u);
+                    uint64_t *rf = &raw_full[(it % kDeqGroups) * SR + s];      // the barrier of the group that takes this k-step
                     mbar_expect_tx(rf, RT::kBytes);
                     tma_load_2d(rawtiles + s * RT::kBytes, &map_raw, ks * RT::kRow, m0, rf);
                 }
@@ -311,49 +355,79 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
         // ===== MMA issuer: one thread of the LEADER CTA issues for the pair =====
         if (lane == 0 && rank == 0) {
             int it = 0, ui = 0;
+            const bool mprof = (g.ablate & 4) && g.trace;
+            long long macc[4] = {0, 0, 0, 0}, macc_c0 = 0, macc_t0 = 0;
             Unit u;
             for (int i = 0; get_unit(sc, pair, i, u); i++, ui++) {
-                const int acc = ui & 1;
-                const uint32_t aph = (uint32_t)(ui >> 1) & 1u;
-                mbar_wait_cluster(smem_u32(&tmem_empty[acc]), aph ^ 1u);     // both epilogues have drained this accumulator
+                mbar_wait_cluster(smem_u32(tmem_empty), ((uint32_t)ui & 1u) ^ 1u);     // both epilogues have drained the accumulator of the previous unit
                 tc_fence_after();
-                const uint32_t td = tmem_base + (uint32_t)(acc * TN);
+                const uint32_t td = tmem_base;
+                bool have = false;                   // the barrier of this k-step was already waited for (between the MMAs of the previous one)
                 for (int ks = u.ks0; ks < u.ks1; ks++, it++) {
-                    const int s = it % kStagesF;
+                    const int s = it % kStagesF, sb = s;
                     const uint32_t ph = (uint32_t)(it / kStagesF) & 1u;
-                    mbar_wait_cluster(smem_u32(&b_full[s]), ph);
-                    mbar_wait_cluster(smem_u32(&a_ready[s]), ph);
+                    const long long m0k = mprof ? clk() : 0;
+                    if (!have) mbar_wait_cluster(smem_u32(&full[s]), ph);
                     tc_fence_after();
-                    if (it == 0) gstamp(g.trace, 1);
-                    const uint32_t sa = smem_a + (uint32_t)(s * kStageF);
-                    const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sa + kATile);
+                    const long long m2k = mprof ? clk() : 0;
+                    const long long m1k = m2k;
+                    if (it == 0) {
+                        gstamp(g.trace, 1);
+                        if (mprof) { macc_c0 = clk(); macc_t0 = (long long)gtimer(); }
+                    }
+                    const uint32_t ta = tmem_base + (uint32_t)(kAccCols + s * kACols);
+                    const uint64_t db = make_desc_sw128(smem_b + (uint32_t)(sb * kStageF));
 #pragma unroll
-                    for (int j = 0; j < 4; j++)      // K = 16 fp16 = 32 bytes per MMA: +2 in the (>>4) start-address field, inside the swizzle atom
-                        tc_mma_f16_pair(td, da + (uint64_t)(j * 2), db + (uint64_t)(j * 2), kIdescF16x2, (ks > u.ks0 || j > 0) ? 1u : 0u);
-                    tc_commit_pair(smem_u32(&empty[s]));          // both CTAs: stage s may be refilled
+                    for (int j = 0; j < 4; j++) {    // K = 16 fp16 per MMA: 8 columns of the W' stage, 32 bytes (+2 in the >>4 start-address field) of the X' rows
+                        if (j == 3) {
+                            // the wait for the NEXT k-step goes here, while three MMAs are queued or running: the issuing thread is the
+                            // kernel's critical resource and a wait at the top of the loop lets the tensor pipe run dry (~100 cycles per k-step)
+                            have = ks + 1 < u.ks1;
+                            if (have) {
+                                const int s1 = (it + 1) % kStagesF;
+                                mbar_wait_cluster(smem_u32(&full[s1]), (uint32_t)((it + 1) / kStagesF) & 1u);
+                            }
+                        }
+                        if (j == 0 || !(g.ablate & 2)) tc_mma_f16_pair_ts(td, ta + (uint32_t)(j * 8), db + (uint64_t)(j * 2), kIdescF16x2, (ks > u.ks0 || j > 0) ? 1u : 0u);
+                    }
+                    tc_commit_pair(smem_u32(&empty[s]));          // both CTAs: the X' stage may be refilled and the W' columns rewritten
+                    if (mprof) {
+                        const long long m3k = clk();
+                        macc[0] += m1k - m0k; macc[1] += m2k - m1k; macc[2] += m3k - m2k; macc[3] += 1;
+                    }
                 }
-                tc_commit_pair(smem_u32(&tmem_full[acc]));        // both CTAs: the accumulator is complete
+                tc_commit_pair(smem_u32(tmem_full));              // both CTAs: the accumulator is complete
                 if (ui == 0) gstamp(g.trace, 2);
+            }
+            if (mprof) {
+                for (int j = 0; j < 4; j++) g.trace[(size_t)(B200_TRACE_MAX_CTAS + blockIdx.x) * 8 + j] = (unsigned long long)macc[j];
+                g.trace[(size_t)(B200_TRACE_MAX_CTAS + blockIdx.x) * 8 + 4] = (unsigned long long)(clk() - macc_c0);              // SM cycles ...
+                g.trace[(size_t)(B200_TRACE_MAX_CTAS + blockIdx.x) * 8 + 5] = (unsigned long long)((long long)gtimer() - macc_t0);   // ... in this many ns
             }
         }
     } else if (warp >= 8) {
         // ===== dequantization: two groups of four warps take alternate k-steps; thread = one weight row of this CTA's 128, both
-        // blocks of the k-step (the whole 128-byte row of the W' tile).  Why groups: the generic -> async proxy fence that must
-        // precede the arrival costs a warp ~300 cycles (ncu: 40 % of these warps' time when every warp paid it every k-step);
-        // two groups halve the fences per k-step and give each warp two k-step periods per pass. =====
+        // blocks of the k-step = 64 fp16 = 32 registers, which go STRAIGHT INTO TENSOR MEMORY (tcgen05.st; lane = row, column = two
+        // consecutive k): the MMA takes its A operand from there.  Shared memory was the bound of the version that wrote the W' tile
+        // into a swizzled shared-memory stage (per k-step and SM: 16 KB written + 16 KB read back by the tensor core on top of the
+        // 48 KB of X' traffic and the raw rows = 176 B/clk against 128 B/clk of shared-memory bandwidth); it also needed a
+        // generic -> async proxy fence (~300 cycles) per warp and k-step, which tensor memory does not. =====
         const int grp = (warp - 8) >> 2;
-        const int r = (warp & 3) * 32 + lane;
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
         const __half2 bias_lo = TYPE == B200_TYPE_Q4_0 ? __floats2half2_rn(1032.f, 1032.f) : __floats2half2_rn(1152.f, 1152.f);
         const __half2 bias_hi = __floats2half2_rn(72.f, 72.f);
-        const uint32_t leader_ready = smem_u32(a_ready) & kPeerMask;
-        const uint32_t sw = (uint32_t)(r & 7);
+        const uint32_t leader_ready = smem_u32(full) & kPeerMask;
         // where TMA's 32 / 64-byte swizzle puts 16-byte piece j of this row: j ^ (bits 7.. of the row's offset)
         const uint32_t rsw = TYPE == B200_TYPE_Q4_0 ? (uint32_t)((r >> 2) & 1) : (uint32_t)((r >> 1) & 3);
         const uint32_t raw_a = smem_u32(rawtiles) + (uint32_t)(r * RT::kRow);
-        int it = grp, s = grp;                  // this group's k-steps of the pair's flattened sequence: grp, grp + 2, ...
-        int visits = 0;                         // ... of which every kStagesF-th comes back to the same stage: the phase of ITS barrier
-        uint32_t ph = 0;
+        const uint32_t ta0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)kAccCols;
+        int it = grp;                           // this group's k-steps of the pair's flattened sequence: grp, grp + 2, ... (stage it % kStagesF:
+                                                // always one of this group's stages, each revisited every kStagesF k-steps)
         int base = 0;                           // flattened index of the unit's first k-step
+        int pend_s = -1;                        // W' stage whose tcgen05.st is in flight (its arrival is still owed)
+        const bool prof = (g.ablate & 4) && g.trace && quad == 0 && lane == 0 && grp == 0;
+        long long pacc[6] = {0, 0, 0, 0, 0, 0};
         Unit u;
         for (int i = 0; get_unit(sc, pair, i, u); i++) {
             const int len = u.ks1 - u.ks0;
@@ -371,11 +445,19 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
                 a0 = b0; a1 = b1;
                 b0 = ldd(ks + 2 * kDeqGroups, 0);
                 b1 = ldd(ks + 2 * kDeqGroups, 1);
-                mbar_wait(&raw_full[grp * kStagesF + s], ph);
+                const int s = it % kStagesF, sr = it % SR;
+                const uint32_t ph = (uint32_t)(it / kStagesF) & 1u, phr = (uint32_t)(it / SR) & 1u;
+                const long long c0k = prof ? clk() : 0;
+                mbar_wait(&raw_full[grp * SR + sr], phr);
+                const long long c1k = prof ? clk() : 0;
                 uint4 q[RT::kRow / 16];
 #pragma unroll
-                for (int j = 0; j < RT::kRow / 16; j++) q[j] = lds128f(raw_a + (uint32_t)(s * RT::kBytes) + ((((uint32_t)j) ^ rsw) << 4));
-                const uint32_t arow = smem_a + (uint32_t)(s * kStageF + r * 128);
+                for (int j = 0; j < RT::kRow / 16; j++) q[j] = lds128f(raw_a + (uint32_t)(sr * RT::kBytes) + ((((uint32_t)j) ^ rsw) << 4));
+                uint32_t wq[32];                // the row's 64 fp16 of this k-step: block 0 in [0, 16), block 1 in [16, 32)
+                if (g.ablate & 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) wq[j] = q[j % (RT::kRow / 16)].x + (uint32_t)j;
+                } else
 #pragma unroll
                 for (int b = 0; b < 2; b++) {
                     const __half dh = __ushort_as_half(b == 0 ? c0 : c1);
@@ -383,46 +465,61 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
                     if (TYPE == B200_TYPE_Q4_0) {
                         // the block's 16 bytes: low nibbles = elements 0..15, high nibbles = elements 16..31
                         const uint32_t w[4] = {q[b].x, q[b].y, q[b].z, q[b].w};
-                        uint32_t lo[8], hi[8];
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             const uint32_t x = w[j], y = w[j] >> 8;
-                            lo[2 * j + 0] = cvt2((x & 0x000F000Fu) | 0x64006400u, bias_lo, d2);     // bytes 0, 2 of the word: 1024 + nib
-                            lo[2 * j + 1] = cvt2((y & 0x000F000Fu) | 0x64006400u, bias_lo, d2);     // bytes 1, 3
-                            hi[2 * j + 0] = cvt2((x & 0x00F000F0u) | 0x54005400u, bias_hi, d2);     // 64 + nib (the nibble sits 4 bits up: ulp 1/16)
-                            hi[2 * j + 1] = cvt2((y & 0x00F000F0u) | 0x54005400u, bias_hi, d2);
+                            wq[b * 16 + 2 * j + 0] = cvt2((x & 0x000F000Fu) | 0x64006400u, bias_lo, d2);         // bytes 0, 2 of the word: 1024 + nib
+                            wq[b * 16 + 2 * j + 1] = cvt2((y & 0x000F000Fu) | 0x64006400u, bias_lo, d2);         // bytes 1, 3
+                            wq[b * 16 + 8 + 2 * j + 0] = cvt2((x & 0x00F000F0u) | 0x54005400u, bias_hi, d2);     // 64 + nib (the nibble sits 4 bits up: ulp 1/16)
+                            wq[b * 16 + 8 + 2 * j + 1] = cvt2((y & 0x00F000F0u) | 0x54005400u, bias_hi, d2);
                         }
-                        // 16-byte chunk c of the row goes where TMA with SWIZZLE_128B would put it: c ^ (row & 7)
-                        sts128f(arow + (((uint32_t)(b * 4 + 0) ^ sw) << 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
-                        sts128f(arow + (((uint32_t)(b * 4 + 1) ^ sw) << 4), make_uint4(lo[4], lo[5], lo[6], lo[7]));
-                        sts128f(arow + (((uint32_t)(b * 4 + 2) ^ sw) << 4), make_uint4(hi[0], hi[1], hi[2], hi[3]));
-                        sts128f(arow + (((uint32_t)(b * 4 + 3) ^ sw) << 4), make_uint4(hi[4], hi[5], hi[6], hi[7]));
                     } else {
 #pragma unroll
                         for (int h16 = 0; h16 < 2; h16++) {
                             const uint4 qq = q[(b * 2 + h16) % (RT::kRow / 16)];
                             const uint32_t w[4] = {qq.x ^ 0x80808080u, qq.y ^ 0x80808080u, qq.z ^ 0x80808080u, qq.w ^ 0x80808080u};   // int8 + 128
-                            uint32_t o[8];
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
-                                o[2 * j + 0] = cvt2((w[j] & 0x00FF00FFu) | 0x64006400u, bias_lo, d2);
-                                o[2 * j + 1] = cvt2(((w[j] >> 8) & 0x00FF00FFu) | 0x64006400u, bias_lo, d2);
+                                wq[b * 16 + h16 * 8 + 2 * j + 0] = cvt2((w[j] & 0x00FF00FFu) | 0x64006400u, bias_lo, d2);
+                                wq[b * 16 + h16 * 8 + 2 * j + 1] = cvt2(((w[j] >> 8) & 0x00FF00FFu) | 0x64006400u, bias_lo, d2);
                             }
-                            sts128f(arow + (((uint32_t)(b * 4 + h16 * 2 + 0) ^ sw) << 4), make_uint4(o[0], o[1], o[2], o[3]));
-                            sts128f(arow + (((uint32_t)(b * 4 + h16 * 2 + 1) ^ sw) << 4), make_uint4(o[4], o[5], o[6], o[7]));
                         }
                     }
                 }
-                // generic-proxy stores -> visible to the tensor core (async proxy), then one arrival per warp on the leader's barrier
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                // the raw rows are in registers (the conversions above consumed them): the stage may be refilled
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(leader_ready + (uint32_t)(s * 8));
-                s += kDeqGroups;
-                if (s >= kStagesF) s -= kStagesF;
-                if (++visits == kStagesF) { visits = 0; ph ^= 1u; }
+                if (lane == 0) mbar_arrive(&raw_empty[sr]);
+                // the PREVIOUS k-step's tcgen05.st has had a whole conversion to complete: order it before the arrival, then one arrival
+                // per warp on the leader's barrier (software-pipelined so that no warp idles on tcgen05.wait::st)
+                const long long c2k = prof ? clk() : 0;
+                if (pend_s >= 0) {
+                    tc_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(leader_ready + (uint32_t)(pend_s * 8));
+                }
+                const long long c3k = prof ? clk() : 0;
+                // the stage's W' columns are free once the MMAs that read their previous contents have completed
+                mbar_wait(&empty[s], ph ^ 1u);
+                tc_fence_after();
+                const long long c4k = prof ? clk() : 0;
+                tc_st32(ta0 + (uint32_t)(s * kACols), wq);
+                pend_s = s;
+                if (prof) {
+                    const long long c5k = clk();
+                    pacc[0] += c1k - c0k; pacc[1] += c2k - c1k; pacc[2] += c3k - c2k; pacc[3] += c4k - c3k; pacc[4] += c5k - c4k; pacc[5] += 1;
+                }
             }
             base += len;
         }
+        if (pend_s >= 0) {
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_ready + (uint32_t)(pend_s * 8));
+        }
+        if (prof && rank == 1)
+            for (int j = 0; j < 6; j++) g.trace[(size_t)(B200_TRACE_MAX_CTAS + blockIdx.x) * 8 + j] = (unsigned long long)pacc[j];
     } else if (warp >= 4) {
         // ===== epilogue: warp q of 4 owns TMEM lanes 32q.. = weight rows; whole tiles go straight to dst, k-slices through
         // the split-k workspace =====
@@ -431,15 +528,14 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
         int ui = 0;
         Unit u;
         for (int i = 0; get_unit(sc, pair, i, u); i++, ui++) {
-            const int acc = ui & 1;
-            const uint32_t aph = (uint32_t)(ui >> 1) & 1u;
+            const uint32_t aph = (uint32_t)ui & 1u;
             const int rloc = (int)rank * TM + quad * 32 + lane;      // row inside the 256-row tile
             const int row = u.tm * 2 * TM + rloc;
             const int n0 = u.tn * TN;
-            mbar_wait(&tmem_full[acc], aph);
+            mbar_wait(tmem_full, aph);
             tc_fence_after();
             if (ui == 0 && quad == 0 && lane == 0) gstamp(g.trace, 3);
-            const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TN);
+            const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16);
             float *pbase = g.partial + ((size_t)(u.rtile * sc.split + u.part) * TN) * (2 * TM) + rloc;
 #pragma unroll 1
             for (int c32 = 0; c32 < TN / 32; c32++) {
@@ -450,7 +546,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
                     // the accumulator is in registers: hand it back to the MMA thread before the stores
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(leader_tempty + (uint32_t)(acc * 8));
+                    if (lane == 0) mbar_arrive_cluster(leader_tempty);
                 }
                 if (u.nparts == 1) {
                     if (row < g.m) {
@@ -641,7 +737,8 @@ int b200_launch_gemm_f16(b200_ctx *ctx, int type, const uint8_t *qs, const __hal
     B200_REQUIRE(ctx, scratch != NULL && dst != NULL, B200_ERR_INVALID);
     B200_REQUIRE(ctx, m < (1 << 30) && n < (1 << 30) && k < (1 << 30), B200_ERR_UNSUPPORTED);
     B200_REQUIRE(ctx, ((uintptr_t)x & 15) == 0 && (x_row_stride & 15) == 0, B200_ERR_UNSUPPORTED);
-    const int pairs = ctx->sm_count / 2;
+    int pairs = ctx->sm_count / 2;
+    if ((ctx->opt_gemm_ablate >> 8) > 0 && (ctx->opt_gemm_ablate >> 8) < pairs) pairs = ctx->opt_gemm_ablate >> 8;      // measurement only: fewer pairs
     B200_REQUIRE(ctx, pairs >= 1, B200_ERR_UNSUPPORTED);
     const int64_t nb = k / 32;
     const int qsb = b200_qs_bytes(type);
@@ -683,6 +780,7 @@ int b200_launch_gemm_f16(b200_ctx *ctx, int type, const uint8_t *qs, const __hal
     g.n = (int)n;
     g.k = (int)k;
     g.sc = sc;
+    g.ablate = ctx->opt_gemm_ablate;
     if (ctx->trace && ctx->trace_next < ctx->trace_capacity) g.trace = ctx->trace + (size_t)(ctx->trace_next++) * B200_TRACE_MAX_CTAS * B200_TRACE_STAMPS;
     // one CTA pair per TPC, or fewer when the launch has fewer units than pairs (idle pairs would only spin up and exit)
     int use_pairs = pairs;
@@ -700,10 +798,10 @@ int b200_launch_gemm_f16(b200_ctx *ctx, int type, const uint8_t *qs, const __hal
     cfg.attrs = attr;
     cfg.numAttrs = ctx->opt_pdl ? 1 : 0;
     if (type == B200_TYPE_Q4_0) {
-        B200_SMEM_LIMIT_ONCE(ctx, gemm_f16_pair_kernel<B200_TYPE_Q4_0>, RawTile<B200_TYPE_Q4_0>::kSmem);
+        B200_CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_f16_pair_kernel<B200_TYPE_Q4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RawTile<B200_TYPE_Q4_0>::kSmem));
         B200_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, gemm_f16_pair_kernel<B200_TYPE_Q4_0>, map_raw, map_b, map_raw_pf, map_dw_pf, g));
     } else {
-        B200_SMEM_LIMIT_ONCE(ctx, gemm_f16_pair_kernel<B200_TYPE_Q8_0>, RawTile<B200_TYPE_Q8_0>::kSmem);
+        B200_CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_f16_pair_kernel<B200_TYPE_Q8_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RawTile<B200_TYPE_Q8_0>::kSmem));
         B200_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, gemm_f16_pair_kernel<B200_TYPE_Q8_0>, map_raw, map_b, map_raw_pf, map_dw_pf, g));
     }
     ctx->launches++;

@@ -16,7 +16,8 @@ m, k, n = (int(a) for a in sys.argv[2:5]) if len(sys.argv) >= 5 else (11008, 409
 ablate = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 NAMES = ["start", "first MMA issued", "unit 0: MMAs issued", "unit 0: accumulator complete", "unit 0: stored", "last unit: stored", "all k-slices arrived", "end"]
 with qmm.Context(0) as ctx:
-    ctx.set_option("gemm_ablate", ablate)
+    if ablate:
+        raise SystemExit("the ablation switches belong to tools/experiments/b200_gemm_f16_tmem_a.cu (not in the shipped kernel)")
     w = qmm.QTensor(ctx, qtype, k, m)
     w.set(qmm.random_wire_weights(qtype, k, m, seed=3))
     x = ctx.to_device(np.random.default_rng(0).uniform(-1, 1, (n, k)).astype(np.float32))
