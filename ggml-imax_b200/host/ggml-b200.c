@@ -844,10 +844,75 @@ static int b200_try_fuse(struct b200_backend_context *bc, struct ggml_cgraph *cg
     return 0;
 }
 
+/* ---- GGML_OP_MUL_MAT_ID (ggml_compute_forward_mul_mat_id, src/ggml.c:12101): dst[:, s, t] = as[:, :, ids[s, t]] x b[:, s % ne11, t].
+ * The expert matrices are ordinary repacked Q4_0 / Q8_0 slices of `as`, so every (slot, token) pair is one mul_mat of the path; the pairs
+ * of one token go down as ONE b200_mul_mat_batch (a decode token whose experts share src1 -- b broadcast over the slots -- is one launch).
+ * The ids are read back to the host first, like the reference's CUDA backend does (src/ggml-cuda.cu: ggml_cuda_mul_mat_id). */
+#define B200_MAX_EXPERTS_USED 16
+
+static bool b200_mul_mat_id_supported(const struct ggml_tensor *dst) {
+    const struct ggml_tensor *as = dst->src[0], *b = dst->src[1], *ids = dst->src[2];
+    if (!as || !b || !ids || !b200_type_is_repacked(as->type) || b->type != GGML_TYPE_F32 || ids->type != GGML_TYPE_I32 || dst->type != GGML_TYPE_F32) return false;
+    if (b200_buffer_is_split(as->buffer) || !b200_glue_supported_srcs(dst)) return false;
+    struct b200_qloc loc;
+    if (!b200_locate_quantized(as, &loc)) return false;
+    if (as->ne[3] != 1 || b->ne[3] != 1 || ids->ne[2] != 1 || ids->ne[3] != 1 || ids->ne[0] > B200_MAX_EXPERTS_USED) return false;
+    if (b->nb[0] != sizeof(float) || b->nb[1] % 16 != 0 || b->nb[2] % 16 != 0 || !b200_views_16(b) || ids->nb[0] != sizeof(int32_t)) return false;
+    return ggml_is_contiguous(dst) && as->ne[0] <= 131072;
+}
+
+static enum ggml_status b200_compute_mul_mat_id(struct b200_backend_context *bc, struct ggml_tensor *dst) {
+    const struct ggml_tensor *as = dst->src[0], *b = dst->src[1], *ids = dst->src[2];
+    struct b200_qloc loc;
+    if (!b200_mul_mat_id_supported(dst) || !b200_locate_quantized(as, &loc)) {
+        fprintf(stderr, "ggml-b200: MUL_MAT_ID %s is outside this backend's path; no CPU fallback\n", as ? ggml_type_name(as->type) : "?");
+        return GGML_STATUS_FAILED;
+    }
+    const int64_t n_used = ids->ne[0], n_tok = ids->ne[1], n_as = as->ne[2], m = as->ne[1], nb = as->ne[0] / B200_QK;
+    if (n_used == 0 || n_tok == 0) return GGML_STATUS_SUCCESS;
+    /* the ids (possibly a column slice of a wider matrix: row pitch nb[1]) -> host; they may have been produced on this stream */
+    const size_t span = (size_t)(n_tok - 1) * ids->nb[1] + (size_t)n_used * sizeof(int32_t);
+    char *hids = (char *)malloc(span);
+    if (!hids) return GGML_STATUS_ALLOC_FAILED;
+    int rc = b200_synchronize(bc->ctx);
+    if (rc == B200_OK) rc = b200_download(bc->ctx, hids, ids->data, span);
+    enum ggml_status st = GGML_STATUS_SUCCESS;
+    for (int64_t t = 0; t < n_tok && rc == B200_OK; t++) {
+        b200_mul_mat_args args[B200_MAX_EXPERTS_USED];
+        for (int64_t s = 0; s < n_used; s++) {
+            const int32_t e = *(const int32_t *)(hids + (size_t)t * ids->nb[1] + (size_t)s * sizeof(int32_t));
+            if (e < 0 || e >= n_as) {
+                fprintf(stderr, "ggml-b200: MUL_MAT_ID expert id %d out of range [0, %lld)\n", (int)e, (long long)n_as);
+                free(hids);
+                return GGML_STATUS_FAILED;
+            }
+            b200_mul_mat_args *a = &args[s];
+            memset(a, 0, sizeof(*a));
+            a->type = (int32_t)as->type;
+            a->src0_dev = loc.base;
+            a->src0_nblocks_total = loc.total_blocks;
+            a->src0_block_off = loc.block_off + (int64_t)e * m * nb;
+            a->ne00 = as->ne[0]; a->ne01 = m; a->ne02 = 1; a->ne03 = 1;
+            a->src1_dev = (const float *)((const char *)b->data + (size_t)(s % b->ne[1]) * b->nb[1] + (size_t)t * b->nb[2]);
+            a->ne11 = 1; a->ne12 = 1; a->ne13 = 1;
+            a->nb11 = b->nb[1]; a->nb12 = b->nb[1]; a->nb13 = b->nb[1];
+            a->dst_dev = (float *)((char *)dst->data + (size_t)s * dst->nb[1] + (size_t)t * dst->nb[2]);
+        }
+        rc = b200_mul_mat_batch(bc->ctx, args, (int)n_used);
+    }
+    free(hids);
+    if (rc != B200_OK) {
+        fprintf(stderr, "ggml-b200: MUL_MAT_ID failed (%d): %s\n", rc, b200_last_error(bc->ctx));
+        st = rc == B200_ERR_ALLOC ? GGML_STATUS_ALLOC_FAILED : GGML_STATUS_FAILED;
+    }
+    return st;
+}
+
 GGML_CALL static bool b200_backend_supports_op(ggml_backend_t backend, const struct ggml_tensor *op) {
     GGML_UNUSED(backend);
     if (b200_op_is_noop(op->op)) return true;
     if (op->op == GGML_OP_MUL_MAT) return b200_mul_mat_supported(op) || (b200_dense_mul_mat_supported(op) && b200_glue_supported_srcs(op));
+    if (op->op == GGML_OP_MUL_MAT_ID) return b200_mul_mat_id_supported(op);
     return b200_glue_supported(op);
 }
 
@@ -1336,6 +1401,11 @@ static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc
                 i++;
             }
             const enum ggml_status st = b200_compute_mul_mat_run(bc, run, n);
+            if (st != GGML_STATUS_SUCCESS) return st;
+            continue;
+        }
+        if (node->op == GGML_OP_MUL_MAT_ID) {
+            const enum ggml_status st = b200_compute_mul_mat_id(bc, node);
             if (st != GGML_STATUS_SUCCESS) return st;
             continue;
         }

@@ -1,9 +1,4 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r02_gpu_tests.log 2>&1; tail -6 gpurun_out/r02_gpu_tests.log
-timeout 600 python tools/stress_gemm.py > gpurun_out/r02_stress_gemm.log 2>&1; tail -6 gpurun_out/r02_stress_gemm.log
-timeout 900 python bench.py > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err; tail -3 gpurun_out/r02_bench_n1.err; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r02_bench_n1.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['targets'], d['checks'].get('logits_vs_oracle_nmse'), d['clocks'])
-print(d['extra'].get('gptj6b_q4_0_prefill_512_tokens'))
-PY
+(cd oracle/_ref && timeout 600 ./test-backend-ops test -b B2000 -o MUL_MAT_ID > ../../gpurun_out/r02_backend_ops_mmid.log 2>&1; echo "rc $?"); sed 's/\x1b\[[0-9;]*m//g' gpurun_out/r02_backend_ops_mmid.log | grep -v "not supported" | tail -12; sed 's/\x1b\[[0-9;]*m//g' gpurun_out/r02_backend_ops_mmid.log | grep -c " OK$"
+timeout 900 python -m pytest tests/test_gpu_backend_ops.py -x -q > gpurun_out/r02_spi_tests.log 2>&1; tail -4 gpurun_out/r02_spi_tests.log
+(cd oracle/_ref && timeout 600 ./test-backend-ops test -b B2000 > ../../gpurun_out/r02_backend_ops_all.log 2>&1); sed 's/\x1b\[[0-9;]*m//g' gpurun_out/r02_backend_ops_all.log | grep -c " OK$"
