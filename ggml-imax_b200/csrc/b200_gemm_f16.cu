@@ -513,7 +513,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
         const int c_lo = p_lo + (span > 0 ? span * cthird / 3 : 0), c_hi = p_lo + (span > 0 ? span * (cthird + 1) / 3 : 0);
         const float *tp = g.partial + ((size_t)(u.rtile * sc.split) * TN) * (2 * TM) + rloc;
         if (row < g.m) {
-            constexpr int CB = 8, PB = 4;
+            constexpr int CB = 8, PB = 8;      // (all k-slices of eight columns in flight at once: one L2 round trip per batch for up to eight slices)
             for (int c = c_lo; c < c_hi; c += CB) {
                 float acc[CB];
 #pragma unroll
