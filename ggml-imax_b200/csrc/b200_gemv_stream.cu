@@ -85,17 +85,20 @@ __host__ __device__ inline size_t stream_act_col_bytes(int type, int k) {
 
 
 // one CTA: wait for an LL vector to be complete and write it out as plain fp32
-__global__ void __launch_bounds__(1024) gather_finish_kernel(const b200_gather gd, const uint2 *ll, float *out, int64_t count) {
+__global__ void __launch_bounds__(1024) gather_finish_kernel(const b200_gather gd, const uint2 *ll, float *out, int64_t count, const LLWait lw) {
     __shared__ uint32_t s_epoch;
     uint32_t *st = gd.state + 2 * (size_t)gd.slot;
     if (threadIdx.x == 0) s_epoch = st[1];
     __syncthreads();
     const uint32_t tag = ((s_epoch + 1u) << 10) | (uint32_t)gd.wait_slot;   // what the producing slot stamped this time round
+    unsigned polls = 0;
+    unsigned long long t0 = 0;
     for (int64_t i = threadIdx.x; i < count; i += blockDim.x) {
         uint32_t v, t;
-        do {
+        for (;;) {
             asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v), "=r"(t) : "l"(ll + i));
-        } while (t != tag);
+            if (t == tag || ll_wait_expired(lw, polls, t0, 6u | (tag << 8))) break;
+        }
         out[i] = __uint_as_float(v);
     }
     __syncthreads();
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
     const int k = (int)p.k, nb = k >> 5;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row_qs = nb * QSB, row_sc = nb * 2;
+    const LLWait lwait = {p.abort_dev, p.abort_host, p.wait_timeout_ns};
 
     unsigned char *ring = smem + g.ring_off;
     unsigned char *act = smem + g.act_off;
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
                     // every CTA needs the whole vector, so what matters is its LAST element to land: probe the end of
                     // this warp's span first (cheap, warp-uniform), then do the verified loads
                     const int tlast = min(base + (kQB - 1) * kConsumerThreads + warp * 32 + 31, tpc - 1);
-                    ll_probe(reinterpret_cast<const char *>(p.x) + (size_t)tlast * 128 + 120, gd_src_tag);
+                    ll_probe(reinterpret_cast<const char *>(p.x) + (size_t)tlast * 128 + 120, gd_src_tag, lwait);
                     if (threadIdx.x == 0 && base == 0) stamp(p.trace, 1);
                 }
 #pragma unroll
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_stream_kernel(const b200_gem
                         const int nvalid = max(0, min(32, tpc - tb));
                         if (nvalid > 0)
                             ll_load16_warp(reinterpret_cast<const char *>(p.x) + (size_t)tb * 128, nvalid, gd_src_tag,
-                                           reinterpret_cast<float *>(smem + g.llstage_off) + warp * 512, lane, v[u]);
+                                           reinterpret_cast<float *>(smem + g.llstage_off) + warp * 512, lane, v[u], lwait);
                     } else {
                         const float4 *src = reinterpret_cast<const float4 *>(xcol + (size_t)t * 16);
 #pragma unroll
@@ -556,6 +560,9 @@ int launch_stream_typed(b200_ctx *ctx, const b200_gemv_params &p, const StreamGe
     cfg.attrs = attr;
     cfg.numAttrs = ctx->opt_pdl ? 1 : 0;
     b200_gemv_params pp = p;
+    pp.abort_dev = ctx->abort_dev;
+    pp.abort_host = ctx->abort_host_dev;
+    pp.wait_timeout_ns = (unsigned long long)(ctx->opt_plan_timeout_ms > 0 ? ctx->opt_plan_timeout_ms : 120000) * 1000000ull;
     pp.trace = NULL;
     if (ctx->trace && ctx->trace_next < ctx->trace_capacity)
         pp.trace = ctx->trace + (size_t)(ctx->trace_next++) * B200_TRACE_MAX_CTAS * B200_TRACE_STAMPS;
@@ -636,7 +643,11 @@ int launch_stream_cols(b200_ctx *ctx, const b200_gemv_params &p, const StreamGeo
 }  // namespace
 
 int b200_launch_gather_finish(b200_ctx *ctx, const b200_gather &gd, const void *ll_src, float *out, int64_t count) {
-    gather_finish_kernel<<<1, 1024, 0, ctx->stream>>>(gd, (const uint2 *)ll_src, out, count);
+    LLWait lw;
+    lw.abort_dev = ctx->abort_dev;
+    lw.abort_host = ctx->abort_host_dev;
+    lw.timeout_ns = (unsigned long long)(ctx->opt_plan_timeout_ms > 0 ? ctx->opt_plan_timeout_ms : 120000) * 1000000ull;
+    gather_finish_kernel<<<1, 1024, 0, ctx->stream>>>(gd, (const uint2 *)ll_src, out, count, lw);
     ctx->launches++;
     B200_CUDA_TRY(ctx, cudaGetLastError());
     return B200_OK;

@@ -123,6 +123,9 @@ struct b200_gemv_params {
     const float   *bias;       // [m] or null
     const float   *residual;   // dense like dst ([n][m]) or null; may be dst itself
     int            act;        // B200_EPI_NONE / B200_EPI_GELU
+    // bound of the waits on peers' tagged stores (fused all-gather path); filled in by the launcher from the context
+    uint32_t      *abort_dev, *abort_host;
+    unsigned long long wait_timeout_ns;
 };
 
 // the epilogue the GEMV kernels apply to a finished dst element (row = weight row, idx = its index in the dense dst)

@@ -279,12 +279,13 @@ int b200_synchronize(b200_ctx *ctx) {
     B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     B200_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->abort_host && *(volatile uint32_t *)ctx->abort_host != 0u) {
-        // a bounded wait inside a persistent kernel expired (b200_plan.cu): what 1 = tagged vector, 2 = publication count, 3 = export
+        // a bounded wait inside a kernel expired: what 1 = tagged vector, 2 = publication count, 3 = export (b200_plan.cu), 4 = split-k slices
+        // (b200_gemm_f16.cu), 5 = tagged src1 of the fused all-gather GEMV, 6 = gather_finish (b200_gemv_stream.cu)
         const uint32_t code = *(volatile uint32_t *)ctx->abort_host;
         *(volatile uint32_t *)ctx->abort_host = 0u;
         B200_CUDA_TRY(ctx, cudaMemsetAsync(ctx->abort_dev, 0, 64, ctx->stream));
         B200_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        b200_set_error(ctx, "a decode plan gave up waiting (wait kind %u, detail 0x%x): a peer rank died or launched a different sequence; results of this launch are invalid",
+        b200_set_error(ctx, "a kernel gave up waiting (wait kind %u, detail 0x%x): a decode plan or fused all-gather whose peer rank died or launched a different sequence; results of this launch are invalid",
                        code & 0xffu, (code & 0x7fffffffu) >> 8);
         return B200_ERR_CUDA;
     }

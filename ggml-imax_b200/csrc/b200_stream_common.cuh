@@ -132,13 +132,37 @@ __device__ __forceinline__ void ll_load16(const void *src, uint32_t tag, float4 
         if (backoff < 512) backoff += 64;
     }
 }
+// Bounded waiting: every wait on a peer's tagged stores looks at the context's abort word and at %globaltimer every
+// 256th failed poll; on expiry it raises the abort word (device copy for the other waits, host copy for b200_synchronize, which then
+// returns B200_ERR_CUDA) and gives up with whatever it has.  A dead or diverged peer rank no longer hangs the GPU.
+struct LLWait {
+    uint32_t *abort_dev, *abort_host;
+    unsigned long long timeout_ns;
+};
+__device__ __forceinline__ bool ll_wait_expired(const LLWait &w, unsigned &polls, unsigned long long &t0, uint32_t what) {
+    if ((++polls & 255u) != 0u || w.abort_dev == nullptr) return false;
+    if (*reinterpret_cast<volatile uint32_t *>(w.abort_dev) != 0u) return true;
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0ull) {
+        t0 = now;
+        return false;
+    }
+    if (now - t0 > w.timeout_ns) {
+        if (atomicCAS(w.abort_dev, 0u, what | 0x80000000u) == 0u && w.abort_host) *reinterpret_cast<volatile uint32_t *>(w.abort_host) = what | 0x80000000u;
+        return true;
+    }
+    return false;
+}
 // Warp-cooperative form: the warp's 32 lane-tasks are one contiguous 4 KB run of LL elements.  It is read with fully
 // coalesced 128-bit volatile loads (lane stride 16 B; volatile loads bypass L1, so the per-lane form above costs 32 sector
 // requests per instruction), the tags are verified warp-wide, the values are parked in a 2 KB per-warp staging area and
 // each lane picks up its 16 consecutive floats.  nvalid = number of live lane-tasks of this warp (0..32).
-__device__ __forceinline__ void ll_load16_warp(const char *wbase, int nvalid, uint32_t tag, float *wstage, int lane, float4 (&out)[4]) {
+__device__ __forceinline__ void ll_load16_warp(const char *wbase, int nvalid, uint32_t tag, float *wstage, int lane, float4 (&out)[4], const LLWait &lw) {
     uint4 w[8];
     const int nv8 = nvalid * 8;
+    unsigned polls = 0;
+    unsigned long long t0 = 0;
     for (;;) {
         bool ok = true;
 #pragma unroll
@@ -150,6 +174,7 @@ __device__ __forceinline__ void ll_load16_warp(const char *wbase, int nvalid, ui
         }
         if (__all_sync(0xffffffffu, ok)) break;
         __nanosleep(64);
+        if (__shfl_sync(0xffffffffu, (int)ll_wait_expired(lw, polls, t0, 5u | (tag << 8)), 0) != 0) break;      // (lane 0 decides for the warp)
     }
 #pragma unroll
     for (int j = 0; j < 8; j++)
@@ -161,12 +186,15 @@ __device__ __forceinline__ void ll_load16_warp(const char *wbase, int nvalid, ui
 }
 // cheap readiness probe: spin on ONE element (a warp-uniform address -> one 32-byte sector per warp per poll) until it
 // carries the tag; the full loads that follow still verify every element, so this only has to be a good predictor
-__device__ __forceinline__ void ll_probe(const void *elem, uint32_t tag) {
+__device__ __forceinline__ void ll_probe(const void *elem, uint32_t tag, const LLWait &lw) {
     uint32_t v, t;
+    unsigned polls = 0;
+    unsigned long long t0 = 0;
     for (;;) {
         asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v), "=r"(t) : "l"(elem));
         if (t == tag) return;
         __nanosleep(32);
+        if (ll_wait_expired(lw, polls, t0, 5u | (tag << 8))) return;
     }
 }
 __device__ __forceinline__ void ll_store(void *vec, int64_t idx, float v, uint32_t tag) {

@@ -160,16 +160,16 @@ GGML_CALL static void b200_buffer_get_tensor(ggml_backend_buffer_t buffer, const
 }
 
 GGML_CALL static bool b200_buffer_cpy_tensor(ggml_backend_buffer_t buffer, const struct ggml_tensor *src, struct ggml_tensor *dst) {
-    /* same-device copies only; anything else goes through the core's get+set fallback
+    /* device-to-device copies between our buffers, on one device or across two (unified addressing; the copy goes over NVLink when
+     * peer access is enabled, else through the host); anything else goes through the core's get+set fallback
      * (src/ggml-backend.c:313-334), which also re-does the repack correctly. */
     struct b200_buffer_context *bc = (struct b200_buffer_context *)buffer->context;
     ggml_backend_buffer_t sbuf = src->view_src ? src->view_src->buffer : src->buffer;
     if (!b200_buffer_is_ours(sbuf)) return false;
-    if (((struct b200_buffer_context *)sbuf->context)->device != bc->device) return false;
+    if (!ggml_is_contiguous(src) || !ggml_is_contiguous(dst) || ggml_nbytes(src) != ggml_nbytes(dst)) return false;
     if (b200_type_is_repacked(src->type)) {
         /* plane layout is relative to the whole tensor: raw byte copies are only valid tensor-to-tensor */
-        if (src->view_src || dst->view_src) return false;
-        if (!ggml_is_contiguous(src) || !ggml_is_contiguous(dst)) return false;
+        if (src->view_src || dst->view_src || dst->type != src->type) return false;
     }
     b200_ctx *io = b200_io_ctx(bc->device);
     if (!io) return false;
