@@ -45,3 +45,44 @@ def test_reference_gpt2_backend_example_runs_unmodified_on_b200(tmp_path, qname)
     print(f"\n[gpt-2-backend {qname}] B200: {t.group(1)} ms total, {t.group(2)} ms/token; CPU (8 threads): {t2.group(1)} ms total, {t2.group(2)} ms/token; "
           f"same greedy continuation: {g1 == g2}")
     assert len(g1) > 0 and gen is not None
+
+
+@pytest.mark.parametrize("ngl", [12, 6])
+def test_reference_gpt2_sched_example_runs_unmodified_with_layers_on_b200(tmp_path, ngl):
+    """examples/gpt-2/main-sched.cpp, unmodified: the reference's scheduler splits the graph between this backend (the last `ngl` layers'
+    weights, and the KV cache / inputs when most layers are there) and the CPU backend by itself -- tensor copies between the two included"""
+    exe = REF / "gpt-2-sched"
+    assert exe.exists(), "oracle/_ref/gpt-2-sched must be prebuilt (make -C oracle dropin) and travel with the snapshot"
+    model = tmp_path / "gpt2-117m-q4_0.bin"
+    subprocess.check_call([sys.executable, str(ROOT / "oracle" / "make_gpt2_model.py"), str(model), "q4_0"])
+    rc, out, err = run(exe, model, ["-ngl", str(ngl)])
+    assert rc == 0, (out[-2000:], err[-2000:])
+    assert "using CUDA backend" in err, err[-2000:]
+    t = re.search(r"predict time =\s*([\d.]+) ms / ([\d.]+) ms per token", out)
+    assert t, out[-2000:]
+    rc2, out2, _ = run(REF / "gpt-2-backend-cpu", model, [])
+    g1 = out.split(PROMPT)[-1].split("\n\n")[0]
+    g2 = out2.split(PROMPT)[-1].split("\n\n")[0]
+    print(f"\n[gpt-2-sched -ngl {ngl}] {t.group(1)} ms total, {t.group(2)} ms/token; same greedy continuation as the CPU backend: {g1 == g2}")
+    assert len(g1) > 0
+
+
+def test_reference_gpt2_batched_example_runs_unmodified_on_b200(tmp_path):
+    """examples/gpt-2/main-batched.cpp, unmodified, 4 parallel sequences: F16 KV cache (CPY F32 -> F16, MUL_MAT with an F16 src0), an explicit
+    KQ mask broadcast over the heads (ADD), SOFT_MAX, a batched head"""
+    exe, cpu_exe = REF / "gpt-2-batched", REF / "gpt-2-batched-cpu"
+    assert exe.exists() and cpu_exe.exists(), "oracle/_ref/gpt-2-batched[-cpu] must be prebuilt (make -C oracle dropin) and travel with the snapshot"
+    model = tmp_path / "gpt2-117m-q4_0.bin"
+    subprocess.check_call([sys.executable, str(ROOT / "oracle" / "make_gpt2_model.py"), str(model), "q4_0"])
+    outs = []
+    for e, extra in ((exe, ["-ngl", "1"]), (cpu_exe, [])):
+        p = subprocess.run([str(e), "-m", str(model), "-p", PROMPT, "-n", "16", "-s", "7", "--top_k", "1", "-b", "256", "-t", "8", "-np", "4"] + extra,
+                           capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, (p.stdout[-2000:], p.stderr[-3000:])
+        outs.append(p.stdout + p.stderr)
+    assert "using CUDA backend" in outs[0], outs[0][-2000:]
+    t = [re.search(r"total time\s*=\s*([\d.]+) ms", o) for o in outs]
+    seqs = [re.findall(r"sequence \d+:\n\n(.*)", o) for o in outs]
+    print(f"\n[gpt-2-batched -np 4] B200 predict {t[0].group(1) if t[0] else '?'} ms, CPU predict {t[1].group(1) if t[1] else '?'} ms (prompt + 4 x 16 tokens); "
+          f"sequences equal to the CPU backend's: {sum(a == b for a, b in zip(seqs[0], seqs[1]))} of {len(seqs[1])}")
+    assert len(seqs[0]) == 4 and all(len(x) > 0 for x in seqs[0]), outs[0][-2000:]

@@ -1,15 +1,5 @@
 mkdir -p gpurun_out
-L=ggml-imax_b200/lib/libggml_b200.so
-cp $L /tmp/lib_ss.so
-for rep in 1 2; do
-  for v in ss ts; do
-    if [ $v = ss ]; then cp /tmp/lib_ss.so $L; else cp tools/_build/libggml_b200_ts.so $L; fi
-    timeout 600 python bench.py --steps 50 --warmup 3 --no-cpu-baseline > gpurun_out/ab_$v$rep.json 2> gpurun_out/ab_$v$rep.err
-    python - <<PY
-import json
-d=json.loads(open('gpurun_out/ab_$v$rep.json').read().strip().splitlines()[-1])
-t=d['targets']; print('$v$rep', 'C2 q4_0', t['c2_gemm_q4_0_us'], 'q8_0', t['c2_gemm_q8_0_us'], 'prefill512 ms', d['extra']['gptj6b_q4_0_prefill_512_tokens']['ms'], 'tok/s', d['value'])
-PY
-  done
-done
-cp /tmp/lib_ss.so $L
+timeout 900 python -m pytest tests/test_gpu_gpt2_backend.py -x -q -s -k batched > gpurun_out/r02_gpt2_batched.log 2>&1; grep -E "gpt-2-|passed|failed" gpurun_out/r02_gpt2_batched.log | tail -4
+python oracle/make_gpt2_model.py /tmp/m.bin q4_0 > /dev/null
+P="the quick brown fox jumps over the lazy dog and keeps running through the forest until the night falls over the quiet hills of the north"
+timeout 300 oracle/_ref/gpt-2-batched -m /tmp/m.bin -p "$P" -n 16 -s 7 --top_k 1 -b 256 -t 8 -np 4 -ngl 1 2>&1 | grep -E "time|n_decoded"
