@@ -86,3 +86,24 @@ def test_reference_gpt2_batched_example_runs_unmodified_on_b200(tmp_path):
     print(f"\n[gpt-2-batched -np 4] B200 predict {t[0].group(1) if t[0] else '?'} ms, CPU predict {t[1].group(1) if t[1] else '?'} ms (prompt + 4 x 16 tokens); "
           f"sequences equal to the CPU backend's: {sum(a == b for a, b in zip(seqs[0], seqs[1]))} of {len(seqs[1])}")
     assert len(seqs[0]) == 4 and all(len(x) > 0 for x in seqs[0]), outs[0][-2000:]
+
+
+def test_reference_simple_backend_example():
+    """examples/simple/simple-backend.cpp, unmodified: its 4x2 by 2x3 F32 mul_mat on this backend prints the result its README gives"""
+    exe = REF / "simple-backend"
+    assert exe.exists(), "oracle/_ref/simple-backend must be prebuilt (make -C oracle dropin)"
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0 and "using CUDA backend" in p.stderr, (p.stdout[-800:], p.stderr[-800:])
+    nums = [float(v) for v in re.findall(r"-?\d+\.\d+", p.stdout.split("transposed result")[-1])]
+    # (the example prints the 4 x 3 result with its own index arithmetic; the twelve values are what matters)
+    assert sorted(nums) == sorted([60.0, 55.0, 50.0, 110.0, 90.0, 54.0, 54.0, 126.0, 42.0, 29.0, 28.0, 64.0]), p.stdout
+
+
+def test_reference_test_mul_mat():
+    """tests/test-mul-mat.cpp, unmodified: CONT + F32 MUL_MAT on this backend against the values the reference's test expects (exact)"""
+    exe = REF / "test-mul-mat"
+    assert exe.exists(), "oracle/_ref/test-mul-mat must be prebuilt (make -C oracle dropin)"
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    clean = re.sub(r"\x1b\[[0-9;]*m", "", p.stdout)
+    assert p.returncode == 0 and "using CUDA backend" in p.stderr, (clean[-800:], p.stderr[-800:])
+    assert "ggml_mul_mat (64): PASSED" in clean and "FAILED" not in clean, clean[-1500:]
