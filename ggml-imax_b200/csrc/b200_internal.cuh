@@ -136,6 +136,9 @@ __device__ __forceinline__ float b200_gemv_epilogue(const b200_gemv_params &p, f
     return v;
 }
 int b200_launch_gemv(b200_ctx *ctx, const b200_gemv_params &p);
+// Q5_0 / IQ4_NL in wire format (b200_wire_formats.cu)
+int b200_launch_gemv_wire(b200_ctx *ctx, const b200_mul_mat_args *a);
+int b200_launch_get_rows_wire(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *rows, const b200_tensor *dst);
 bool b200_try_launch_gemv_stream(b200_ctx *ctx, const b200_gemv_params &p, int *rc);
 bool b200_try_launch_gemv_stream_batch(b200_ctx *ctx, const b200_gemv_params *ps, int count, int *rc);
 int b200_launch_gather_finish(b200_ctx *ctx, const b200_gather &gd, const void *ll_src, float *out, int64_t count);

@@ -121,6 +121,13 @@ extern "C" {
 
 int b200_mul_mat(b200_ctx *ctx, const b200_mul_mat_args *a) {
     B200_REQUIRE(ctx, ctx && a, B200_ERR_INVALID);
+    if (a->type == B200_TYPE_Q5_0 || a->type == B200_TYPE_IQ4_NL) {
+        // the sibling formats: wire-format blocks at src0_dev (+ src0_block_off blocks), plain correctness path
+        B200_REQUIRE(ctx, a->src0_dev && a->src1_dev && a->dst_dev && a->src0_block_off >= 0, B200_ERR_INVALID);
+        B200_REQUIRE(ctx, ((uintptr_t)a->src1_dev & 3) == 0 && a->nb11 % 4 == 0 && a->nb12 % 4 == 0 && a->nb13 % 4 == 0, B200_ERR_UNSUPPORTED);
+        B200_CUDA_TRY(ctx, b200_use_device(ctx->device));
+        return b200_launch_gemv_wire(ctx, a);
+    }
     B200_REQUIRE(ctx, quant_type_ok(a->type), B200_ERR_UNSUPPORTED);
     B200_REQUIRE(ctx, a->ne00 > 0 && a->ne00 % B200_QK == 0, B200_ERR_INVALID);   // assert(n % qk == 0)
     B200_REQUIRE(ctx, a->ne01 > 0 && a->ne02 > 0 && a->ne03 > 0, B200_ERR_INVALID);

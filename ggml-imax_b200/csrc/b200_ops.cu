@@ -510,6 +510,7 @@ int b200_op_get_rows(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *
     const int64_t nc = src0->ne[0], nr = nelements(rows);
     if (nc == 0 || nr == 0) return B200_OK;
     const T4 r = view(rows), d = view(dst), a = view(src0);
+    if (src0->type == B200_TYPE_Q5_0 || src0->type == B200_TYPE_IQ4_NL) return b200_launch_get_rows_wire(ctx, src0, rows, dst);
     const bool quant = src0->type == B200_TYPE_Q4_0 || src0->type == B200_TYPE_Q8_0;
     if (quant) {
         const int wire = b200_wire_bytes(src0->type);

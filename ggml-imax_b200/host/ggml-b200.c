@@ -65,6 +65,9 @@ GGML_CALL bool ggml_backend_is_b200(ggml_backend_t backend);
 GGML_CALL int ggml_backend_b200_get_device_count(void);
 
 static bool b200_type_is_repacked(enum ggml_type t) { return t == GGML_TYPE_Q4_0 || t == GGML_TYPE_Q8_0; }
+/* the sibling 32-element formats: kept in wire format, served by the plain path of b200_wire_formats.cu */
+static bool b200_type_is_wire(enum ggml_type t) { return t == GGML_TYPE_Q5_0 || t == GGML_TYPE_IQ4_NL; }
+_Static_assert((int)GGML_TYPE_Q5_0 == B200_TYPE_Q5_0 && (int)GGML_TYPE_IQ4_NL == B200_TYPE_IQ4_NL, "type numbering");
 static int64_t b200_wire_bytes(enum ggml_type t) { return t == GGML_TYPE_Q4_0 ? B200_Q4_0_BYTES : B200_Q8_0_BYTES; }
 
 /*
@@ -582,6 +585,14 @@ static bool b200_op_is_noop(enum ggml_op op) {
 
 /* the shapes/layouts the kernels take; mirrors the asserts of ggml_compute_forward_mul_mat
  * (src/ggml.c:11832-11845) plus 16-byte alignment of activation rows for 128-bit loads */
+static bool b200_wire_mul_mat_supported(const struct ggml_tensor *dst) {
+    const struct ggml_tensor *a = dst->src[0], *b = dst->src[1];
+    if (!a || !b || !b200_type_is_wire(a->type) || b->type != GGML_TYPE_F32 || dst->type != GGML_TYPE_F32) return false;
+    if (!ggml_is_contiguous(a) || !ggml_is_contiguous(dst) || b->nb[0] != sizeof(float)) return false;
+    if (b200_buffer_is_split(a->buffer) || b->ne[2] % a->ne[2] != 0 || b->ne[3] % a->ne[3] != 0) return false;
+    return b->ne[1] <= 65535 && b->ne[2] * b->ne[3] <= 65535 && a->ne[0] <= 131072;
+}
+
 static bool b200_mul_mat_supported(const struct ggml_tensor *dst) {
     const struct ggml_tensor *a = dst->src[0], *b = dst->src[1];
     if (!a || !b) return false;
@@ -683,6 +694,7 @@ static bool b200_glue_supported(const struct ggml_tensor *op) {
                    a->nb[1] % wire == 0 && a->nb[2] % wire == 0 && a->nb[3] % wire == 0 && b200_views_16(op) && op->nb[1] % 16 == 0 &&
                    op->nb[2] % 16 == 0 && op->nb[3] % 16 == 0;
         }
+        if (b200_type_is_wire(a->type)) return a->nb[0] == ggml_type_size(a->type) && a->ne[0] % B200_QK == 0;
         return (a->type == GGML_TYPE_F32 || a->type == GGML_TYPE_F16) && a->nb[0] == ggml_type_size(a->type);
     case GGML_OP_ADD:
     case GGML_OP_MUL:
@@ -715,6 +727,20 @@ static bool b200_fill_mul_mat_args(struct ggml_tensor *dst, b200_mul_mat_args *a
 /* one glue node (no fusion) */
 static enum ggml_status b200_compute_glue(struct b200_backend_context *bc, struct ggml_tensor *node) {
     b200_tensor a, b, d;
+    if (node->op == GGML_OP_MUL_MAT && b200_wire_mul_mat_supported(node)) {
+        const struct ggml_tensor *wa = node->src[0], *wb = node->src[1];
+        b200_mul_mat_args args;
+        memset(&args, 0, sizeof(args));
+        args.type = (int32_t)wa->type;
+        args.src0_dev = wa->data;
+        args.src0_nblocks_total = ggml_nelements(wa) / B200_QK;
+        args.ne00 = wa->ne[0]; args.ne01 = wa->ne[1]; args.ne02 = wa->ne[2]; args.ne03 = wa->ne[3];
+        args.src1_dev = (const float *)wb->data;
+        args.ne11 = wb->ne[1]; args.ne12 = wb->ne[2]; args.ne13 = wb->ne[3];
+        args.nb11 = wb->nb[1]; args.nb12 = wb->nb[2]; args.nb13 = wb->nb[3];
+        args.dst_dev = (float *)node->data;
+        return b200_glue_status(bc, node, b200_mul_mat(bc->ctx, &args));
+    }
     if (!b200_glue_supported(node) && !(node->op == GGML_OP_MUL_MAT && b200_dense_mul_mat_supported(node))) {
         fprintf(stderr, "ggml-b200: op %s (%s) is outside this backend's path (supports_op is false for it); no CPU fallback\n", ggml_op_name(node->op),
                 ggml_type_name(node->type));
@@ -852,10 +878,12 @@ static int b200_try_fuse(struct b200_backend_context *bc, struct ggml_cgraph *cg
 
 static bool b200_mul_mat_id_supported(const struct ggml_tensor *dst) {
     const struct ggml_tensor *as = dst->src[0], *b = dst->src[1], *ids = dst->src[2];
-    if (!as || !b || !ids || !b200_type_is_repacked(as->type) || b->type != GGML_TYPE_F32 || ids->type != GGML_TYPE_I32 || dst->type != GGML_TYPE_F32) return false;
+    if (!as || !b || !ids || !(b200_type_is_repacked(as->type) || b200_type_is_wire(as->type)) || b->type != GGML_TYPE_F32 || ids->type != GGML_TYPE_I32 ||
+        dst->type != GGML_TYPE_F32)
+        return false;
     if (b200_buffer_is_split(as->buffer) || !b200_glue_supported_srcs(dst)) return false;
     struct b200_qloc loc;
-    if (!b200_locate_quantized(as, &loc)) return false;
+    if (b200_type_is_wire(as->type) ? !ggml_is_contiguous(as) : !b200_locate_quantized(as, &loc)) return false;
     if (as->ne[3] != 1 || b->ne[3] != 1 || ids->ne[2] != 1 || ids->ne[3] != 1 || ids->ne[0] > B200_MAX_EXPERTS_USED) return false;
     if (b->nb[0] != sizeof(float) || b->nb[1] % 16 != 0 || b->nb[2] % 16 != 0 || !b200_views_16(b) || ids->nb[0] != sizeof(int32_t)) return false;
     return ggml_is_contiguous(dst) && as->ne[0] <= 131072;
@@ -864,7 +892,11 @@ static bool b200_mul_mat_id_supported(const struct ggml_tensor *dst) {
 static enum ggml_status b200_compute_mul_mat_id(struct b200_backend_context *bc, struct ggml_tensor *dst) {
     const struct ggml_tensor *as = dst->src[0], *b = dst->src[1], *ids = dst->src[2];
     struct b200_qloc loc;
-    if (!b200_mul_mat_id_supported(dst) || !b200_locate_quantized(as, &loc)) {
+    memset(&loc, 0, sizeof(loc));
+    if (as && b200_type_is_wire(as->type) && b200_mul_mat_id_supported(dst)) {
+        loc.base = as->data;                  /* wire-format blocks: the expert's slice starts e * m * nb blocks in */
+        loc.total_blocks = ggml_nelements(as) / B200_QK;
+    } else if (!b200_mul_mat_id_supported(dst) || !b200_locate_quantized(as, &loc)) {
         fprintf(stderr, "ggml-b200: MUL_MAT_ID %s is outside this backend's path; no CPU fallback\n", as ? ggml_type_name(as->type) : "?");
         return GGML_STATUS_FAILED;
     }
@@ -911,7 +943,8 @@ static enum ggml_status b200_compute_mul_mat_id(struct b200_backend_context *bc,
 GGML_CALL static bool b200_backend_supports_op(ggml_backend_t backend, const struct ggml_tensor *op) {
     GGML_UNUSED(backend);
     if (b200_op_is_noop(op->op)) return true;
-    if (op->op == GGML_OP_MUL_MAT) return b200_mul_mat_supported(op) || (b200_dense_mul_mat_supported(op) && b200_glue_supported_srcs(op));
+    if (op->op == GGML_OP_MUL_MAT)
+        return b200_mul_mat_supported(op) || ((b200_dense_mul_mat_supported(op) || b200_wire_mul_mat_supported(op)) && b200_glue_supported_srcs(op));
     if (op->op == GGML_OP_MUL_MAT_ID) return b200_mul_mat_id_supported(op);
     return b200_glue_supported(op);
 }

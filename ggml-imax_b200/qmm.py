@@ -21,6 +21,7 @@ LIB_PATH = PKG_DIR / "lib" / "libggml_b200.so"
 BACKEND_LIB_PATH = PKG_DIR / "lib" / "libggml-b200-backend.so"
 
 TYPE_F32, TYPE_F16, TYPE_Q4_0, TYPE_Q8_0, TYPE_I16, TYPE_I32 = 0, 1, 2, 8, 25, 26
+TYPE_Q5_0, TYPE_IQ4_NL = 6, 20      # kept in wire format on the device (b200_wire_formats.cu)
 OP_ADD, OP_MUL, OP_DIV = 0, 1, 2
 UNARY = {n: i for i, n in enumerate(["abs", "sgn", "neg", "step", "tanh", "elu", "relu", "sigmoid", "gelu", "gelu_quick", "silu", "hardswish",
                                      "hardsigmoid"])}          # enum ggml_unary_op

@@ -41,7 +41,9 @@ extern "C" {
 #define B200_TYPE_F32   0
 #define B200_TYPE_F16   1
 #define B200_TYPE_Q4_0  2
+#define B200_TYPE_Q5_0  6    /* sibling 32-element formats that share the Q8_0 activation path: kept in WIRE format on the device, */
 #define B200_TYPE_Q8_0  8
+#define B200_TYPE_IQ4_NL 20  /* served by a plain correctness path (b200_wire_formats.cu), not by the streaming / tensor-core kernels */
 #define B200_TYPE_I16   25
 #define B200_TYPE_I32   26
 

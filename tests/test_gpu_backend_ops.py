@@ -41,7 +41,10 @@ def test_backend_ops_mul_mat():
 GLUE = ["GET_ROWS(type=f32", "GET_ROWS(type=f16", "GET_ROWS(type=q4_0", "GET_ROWS(type=q8_0", "ADD(type=f32", "MUL(type=f32", "DIV(type=f32", "GELU(type=f32",
         "GELU_QUICK(type=f32", "SILU(type=f32", "RELU(type=f32", "TANH(type=f32", "NORM(type=f32", "RMS_NORM(type=f32", "SCALE(type=f32", "DIAG_MASK_INF(type=f32",
         "SOFT_MAX(type=f32", "CPY(type_src=f32,type_dst=f32", "CPY(type_src=f32,type_dst=f16", "CPY(type_src=f16,type_dst=f32", "DUP(type=f32", "DUP(type=i16",
-        "CONT(type=f32", "MUL_MAT(type_a=f32,type_b=f32", "MUL_MAT(type_a=f16,type_b=f32", "MUL_MAT_ID(type_a=q4_0,type_b=f32", "MUL_MAT_ID(type_a=q8_0,type_b=f32"]
+        "CONT(type=f32", "MUL_MAT(type_a=f32,type_b=f32", "MUL_MAT(type_a=f16,type_b=f32", "MUL_MAT_ID(type_a=q4_0,type_b=f32", "MUL_MAT_ID(type_a=q8_0,type_b=f32",
+        # the sibling 32-element formats that share the Q8_0 activation path
+        "MUL_MAT(type_a=q5_0,type_b=f32", "MUL_MAT(type_a=iq4_nl,type_b=f32", "GET_ROWS(type=q5_0", "GET_ROWS(type=iq4_nl", "MUL_MAT_ID(type_a=q5_0,type_b=f32",
+        "MUL_MAT_ID(type_a=iq4_nl,type_b=f32"]
 
 
 def test_backend_ops_whole_suite_glue_ops_green_rest_declined():
@@ -58,4 +61,4 @@ def test_backend_ops_whole_suite_glue_ops_green_rest_declined():
         assert mine, f"no test case starts with {prefix}"
         assert all(l.rstrip().endswith("OK") for l in mine), "\n".join(l for l in mine if not l.rstrip().endswith("OK"))
     ran = sum(1 for l in lines if l.rstrip().endswith("OK"))
-    assert ran >= 265, ran
+    assert ran >= 275, ran
