@@ -224,6 +224,59 @@ int b200_download_async(b200_ctx *ctx, void *dst_host, const void *src_dev, size
     return B200_OK;
 }
 
+struct b200_event {
+    cudaEvent_t ev;
+    int device;
+};
+
+int b200_event_create(b200_ctx *ctx, b200_event **out) {
+    B200_REQUIRE(ctx, ctx && out, B200_ERR_INVALID);
+    *out = NULL;
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    b200_event *e = (b200_event *)calloc(1, sizeof(b200_event));
+    if (!e) return B200_ERR_ALLOC;
+    e->device = ctx->device;
+    const cudaError_t rc = cudaEventCreateWithFlags(&e->ev, cudaEventDisableTiming);
+    if (rc != cudaSuccess) {
+        b200_set_error(ctx, "cudaEventCreateWithFlags failed: %s", cudaGetErrorString(rc));
+        (void)cudaGetLastError();
+        free(e);
+        return B200_ERR_CUDA;
+    }
+    *out = e;
+    return B200_OK;
+}
+
+void b200_event_destroy(b200_event *ev) {
+    if (!ev) return;
+    if (cudaSetDevice(ev->device) == cudaSuccess) (void)cudaEventDestroy(ev->ev);
+    (void)cudaGetLastError();
+    free(ev);
+}
+
+int b200_event_record(b200_ctx *ctx, b200_event *ev) {
+    B200_REQUIRE(ctx, ctx && ev && ev->device == ctx->device, B200_ERR_INVALID);
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, cudaEventRecord(ev->ev, ctx->stream));
+    return B200_OK;
+}
+
+int b200_event_wait(b200_ctx *ctx, b200_event *ev) {
+    B200_REQUIRE(ctx, ctx && ev, B200_ERR_INVALID);
+    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    B200_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ev->ev, 0));
+    return B200_OK;
+}
+
+int b200_event_synchronize(b200_event *ev) {
+    if (!ev) return B200_ERR_INVALID;
+    if (cudaSetDevice(ev->device) != cudaSuccess || cudaEventSynchronize(ev->ev) != cudaSuccess) {
+        b200_set_error(NULL, "cudaEventSynchronize failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return B200_ERR_CUDA;
+    }
+    return B200_OK;
+}
+
 int b200_upload(b200_ctx *ctx, void *dst_dev, const void *src_host, size_t size) {
     int rc = b200_upload_async(ctx, dst_dev, src_host, size);
     if (rc != B200_OK) return rc;

@@ -1465,13 +1465,79 @@ static enum ggml_status b200_glue_status(struct b200_backend_context *bc, const 
     return rc == B200_ERR_ALLOC ? GGML_STATUS_ALLOC_FAILED : GGML_STATUS_FAILED;
 }
 
+/* ---- optional SPI entries (src/ggml-backend-impl.h:86-90, :111-116): asynchronous tensor access on the backend's own stream, events ---- */
+
+static bool b200_tensor_on_backend_device(struct b200_backend_context *bc, const struct ggml_tensor *t) {
+    ggml_backend_buffer_t buf = t->view_src ? t->view_src->buffer : t->buffer;
+    return b200_buffer_is_ours(buf) && ((struct b200_buffer_context *)buf->context)->device == bc->device;
+}
+
+GGML_CALL static void b200_backend_set_tensor_async(ggml_backend_t backend, struct ggml_tensor *tensor, const void *data, size_t offset, size_t size) {
+    struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
+    ggml_backend_buffer_t buf = tensor->view_src ? tensor->view_src->buffer : tensor->buffer;
+    if (b200_tensor_on_backend_device(bc, tensor) && !b200_type_is_repacked(tensor->type)) {
+        /* ordered with the graphs computed on this backend: the copy rides the compute stream */
+        B200_CHECK(bc->ctx, b200_upload_async(bc->ctx, (char *)tensor->data + offset, data, size));
+        return;
+    }
+    buf->iface.set_tensor(buf, tensor, data, offset, size);      /* repacked types (and foreign buffers) keep the synchronous path */
+}
+
+GGML_CALL static void b200_backend_get_tensor_async(ggml_backend_t backend, const struct ggml_tensor *tensor, void *data, size_t offset, size_t size) {
+    struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
+    ggml_backend_buffer_t buf = tensor->view_src ? tensor->view_src->buffer : tensor->buffer;
+    if (b200_tensor_on_backend_device(bc, tensor) && !b200_type_is_repacked(tensor->type)) {
+        B200_CHECK(bc->ctx, b200_download_async(bc->ctx, data, (const char *)tensor->data + offset, size));
+        return;
+    }
+    buf->iface.get_tensor(buf, tensor, data, offset, size);
+}
+
+GGML_CALL static ggml_backend_event_t b200_backend_event_new(ggml_backend_t backend) {
+    struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
+    b200_event *ev = NULL;
+    if (b200_event_create(bc->ctx, &ev) != B200_OK) return NULL;
+    ggml_backend_event_t e = (ggml_backend_event_t)malloc(sizeof(struct ggml_backend_event));
+    if (!e) {
+        b200_event_destroy(ev);
+        return NULL;
+    }
+    e->backend = backend;
+    e->context = ev;
+    return e;
+}
+
+GGML_CALL static void b200_backend_event_free(ggml_backend_event_t event) {
+    b200_event_destroy((b200_event *)event->context);
+    free(event);
+}
+
+GGML_CALL static void b200_backend_event_record(ggml_backend_event_t event) {
+    struct b200_backend_context *bc = (struct b200_backend_context *)event->backend->context;
+    B200_CHECK(bc->ctx, b200_event_record(bc->ctx, (b200_event *)event->context));
+}
+
+GGML_CALL static void b200_backend_event_wait(ggml_backend_t backend, ggml_backend_event_t event) {
+    struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
+    if (ggml_backend_is_b200(event->backend)) {
+        B200_CHECK(bc->ctx, b200_event_wait(bc->ctx, (b200_event *)event->context));
+    } else {
+        ggml_backend_event_synchronize(event);      /* another backend's event: nothing to chain on the device, wait on the host */
+    }
+}
+
+GGML_CALL static void b200_backend_event_synchronize(ggml_backend_event_t event) {
+    struct b200_backend_context *bc = (struct b200_backend_context *)event->backend->context;
+    B200_CHECK(bc->ctx, b200_event_synchronize((b200_event *)event->context));
+}
+
 static struct ggml_backend_i b200_backend_interface = {
     /* .get_name                = */ b200_backend_name,
     /* .free                    = */ b200_backend_free,
     /* .get_default_buffer_type = */ b200_backend_default_buft,
-    /* .set_tensor_async        = */ NULL,
-    /* .get_tensor_async        = */ NULL,
-    /* .cpy_tensor_async        = */ NULL,
+    /* .set_tensor_async        = */ b200_backend_set_tensor_async,
+    /* .get_tensor_async        = */ b200_backend_get_tensor_async,
+    /* .cpy_tensor_async        = */ NULL,        /* (the core then synchronizes both backends and copies through the buffer interface) */
     /* .synchronize             = */ b200_backend_synchronize,
     /* .graph_plan_create       = */ b200_backend_graph_plan_create,
     /* .graph_plan_free         = */ b200_backend_graph_plan_free,
@@ -1479,11 +1545,11 @@ static struct ggml_backend_i b200_backend_interface = {
     /* .graph_compute           = */ b200_backend_graph_compute,
     /* .supports_op             = */ b200_backend_supports_op,
     /* .offload_op              = */ NULL,
-    /* .event_new               = */ NULL,
-    /* .event_free              = */ NULL,
-    /* .event_record            = */ NULL,
-    /* .event_wait              = */ NULL,
-    /* .event_synchronize       = */ NULL,
+    /* .event_new               = */ b200_backend_event_new,
+    /* .event_free              = */ b200_backend_event_free,
+    /* .event_record            = */ b200_backend_event_record,
+    /* .event_wait              = */ b200_backend_event_wait,
+    /* .event_synchronize       = */ b200_backend_event_synchronize,
 };
 
 GGML_CALL ggml_backend_t ggml_backend_b200_init(int device) {

@@ -104,6 +104,11 @@ _SIGNATURES = {
     "b200_copy_2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]),
     "b200_enable_peer_access": (C.c_int, [C.c_void_p, C.c_int]),
     "b200_synchronize": (C.c_int, [C.c_void_p]),
+    "b200_event_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200_event_destroy": (None, [C.c_void_p]),
+    "b200_event_record": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200_event_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200_event_synchronize": (C.c_int, [C.c_void_p]),
     "b200_host_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "b200_host_free": (C.c_int, [C.c_void_p]),
     "b200_graph_begin": (C.c_int, [C.c_void_p]),

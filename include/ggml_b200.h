@@ -108,6 +108,15 @@ B200_API int b200_enable_peer_access(b200_ctx *ctx, int peer_device);
  * sequences) surfaces: B200_ERR_CUDA with the reason in b200_last_error; the results of that launch are invalid. */
 B200_API int b200_synchronize(b200_ctx *ctx);
 /* pinned host staging (ggml_backend_cuda_host_buffer_type, src/ggml-cuda.h:31) */
+/* events: ggml_backend_i.event_new / _free / _record / _wait / _synchronize (src/ggml-backend-impl.h:112-116; used by ggml_backend_sched
+ * to overlap the copies of one split with the compute of another).  Record on one context's stream, wait from another context's stream
+ * (same or another device) or from the host. */
+typedef struct b200_event b200_event;
+B200_API int  b200_event_create(b200_ctx *ctx, b200_event **out);
+B200_API void b200_event_destroy(b200_event *ev);
+B200_API int  b200_event_record(b200_ctx *ctx, b200_event *ev);        /* after everything enqueued on ctx's stream so far */
+B200_API int  b200_event_wait(b200_ctx *ctx, b200_event *ev);          /* work enqueued on ctx's stream from now on waits for it */
+B200_API int  b200_event_synchronize(b200_event *ev);                  /* the host waits */
 B200_API int b200_host_malloc(void **hptr, size_t size);
 B200_API int b200_host_free(void *hptr);
 

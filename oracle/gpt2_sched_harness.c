@@ -206,7 +206,9 @@ int main(int argc, char **argv) {
     int64_t launches_c = 0, nodes_c = 0;
 
     ggml_backend_t backends[2] = { gpu, cpu_b };
-    ggml_backend_sched_t sched = ggml_backend_sched_new(backends, NULL, 2, MAX_NODES, false);
+    /* argv[6] = 1: the scheduler's pipelined mode (several copies of the split inputs, ggml_backend_event_* and the asynchronous tensor accessors) */
+    const bool parallel = argc > 6 && atoi(argv[6]) != 0;
+    ggml_backend_sched_t sched = ggml_backend_sched_new(backends, NULL, 2, MAX_NODES, parallel);
     ggml_gallocr_t galloc = ggml_gallocr_new(ggml_backend_cpu_buffer_type());
 
     int32_t *tokens = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_prompt + n_decode));

@@ -16,10 +16,12 @@ pytestmark = pytest.mark.gpu
 HARNESS = ROOT / "oracle" / "_ref" / "gpt2-sched-harness"
 
 
-@pytest.mark.parametrize("qname", ["q4_0", "q8_0"])
-def test_gpt2_117m_prompt_and_decode_on_sched_b200_plus_cpu(qname):
+@pytest.mark.parametrize("qname,parallel", [("q4_0", 0), ("q8_0", 0), ("q4_0", 1)])
+def test_gpt2_117m_prompt_and_decode_on_sched_b200_plus_cpu(qname, parallel):
+    """parallel = 1: ggml_backend_sched_new(..., parallel = true) -- the scheduler's pipelined mode, which goes through this backend's
+    event_new / event_record / event_wait / event_synchronize and set_tensor_async entries (src/ggml-backend.c:1640-1712)"""
     assert HARNESS.exists(), f"{HARNESS} must be prebuilt (make -C oracle dropin) and travel with the snapshot"
-    p = subprocess.run([str(HARNESS), qname, "128", "3", "8"], capture_output=True, text=True, timeout=900)
+    p = subprocess.run([str(HARNESS), qname, "128", "3", "8", "1", str(parallel)], capture_output=True, text=True, timeout=900)
     lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
     assert lines, f"no result line (rc {p.returncode}): {p.stdout[-400:]} {p.stderr[-800:]}"
     r = json.loads(lines[-1])

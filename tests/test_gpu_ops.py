@@ -317,3 +317,30 @@ def test_mul_mat_fused_refuses_prefill_shapes(qmm, gpu_ctx, oracle):
     with pytest.raises(qmm.B200Error) as e:
         gpu_ctx.mul_mat_fused(w, x.buf.ptr, 64, d.buf.ptr, bias_ptr=d.buf.ptr)
     assert e.value.code == qmm.ERR_UNSUPPORTED
+
+
+def test_events_order_two_streams(qmm, gpu_ctx):
+    """b200_event_*: work recorded on one context's stream, awaited from another context's stream and from the host (the SPI's event entries)"""
+    import ctypes as C
+    other = qmm.Context(0)
+    try:
+        n = 1 << 22
+        x = np.arange(n, dtype=np.float32)
+        a = qmm.DTensor(gpu_ctx, qmm.TYPE_F32, [n])
+        b = qmm.DTensor(gpu_ctx, qmm.TYPE_F32, [n])
+        ev = C.c_void_p()
+        gpu_ctx._check(gpu_ctx.lib.b200_event_create(gpu_ctx.h, C.byref(ev)))
+        for rep in range(5):
+            gpu_ctx._check(gpu_ctx.lib.b200_upload_async(gpu_ctx.h, C.c_void_p(a.buf.ptr), x.ctypes.data, x.nbytes))      # stream 1
+            gpu_ctx.op_scale(a, a, 2.0)
+            gpu_ctx._check(gpu_ctx.lib.b200_event_record(gpu_ctx.h, ev))
+            other._check(other.lib.b200_event_wait(other.h, ev))                                                             # stream 2 waits
+            other.op_scale(a, b, 0.5)
+            other.synchronize()
+            assert np.array_equal(b.numpy().reshape(-1), x)
+            x += 1.0
+        gpu_ctx._check(gpu_ctx.lib.b200_event_record(gpu_ctx.h, ev))
+        assert gpu_ctx.lib.b200_event_synchronize(ev) == 0
+        gpu_ctx.lib.b200_event_destroy(ev)
+    finally:
+        other.close()
