@@ -388,6 +388,77 @@ __global__ void __launch_bounds__(256) copy_rows16_kernel(T4 a, T4 d, int64_t ro
     }
 }
 
+// ---- ROPE (src/ggml.c:13775 f32, :13953 f16; forward only) -----------------------------------------------------------------------------
+// One thread per rotated pair.  The angle of pair j is pos * theta_scale^j built by j successive fp32 multiplications, as the CPU
+// loop builds it (ggml_rope_cache_init, :13750), so the argument of cosf / sinf is the CPU's bit for bit; YaRN mixing (rope_yarn,
+// :13726) and the xPos factor follow the same expressions.  NeoX mode keeps two of the reference's quirks: freq_scale is applied
+// twice (:13908 and inside rope_yarn) and the ramp index is the truncation of a value in (-1, 0], i.e. 0.  GLM mode is declined.
+struct RopeK {
+    int   n_dims, neox;
+    float theta_scale, freq_scale, ext_factor, attn_factor, corr0, corr1, xpos_base;
+    int   xpos_down;
+};
+__device__ __forceinline__ void rope_yarn_dev(float theta_extrap, const RopeK &r, int i0, float *c, float *s) {
+    const float theta_interp = r.freq_scale * theta_extrap;
+    float theta = theta_interp, mscale = r.attn_factor;
+    if (r.ext_factor != 0.0f) {
+        const float y = ((float)(i0 / 2) - r.corr0) / fmaxf(0.001f, r.corr1 - r.corr0);
+        const float ramp_mix = (1.0f - fminf(1.0f, fmaxf(0.0f, y))) * r.ext_factor;
+        theta = __fadd_rn(__fmul_rn(theta_interp, 1.0f - ramp_mix), __fmul_rn(theta_extrap, ramp_mix));   // no contraction: an ulp of a large angle is visible in its cosine
+        mscale *= 1.0f + 0.1f * logf(1.0f / r.freq_scale);
+    }
+    *c = cosf(theta) * mscale;
+    *s = sinf(theta) * mscale;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) rope_kernel(T4 a, T4 d, const int32_t *__restrict__ pos, RopeK r) {
+    const int64_t half = a.ne0 >> 1;
+    const int64_t total = half * a.ne1 * a.ne2 * a.ne3;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t row = t / half;
+        const int j = (int)(t - row * half);                 // pair index inside the row
+        const int64_t i3 = row / (a.ne2 * a.ne1);
+        row -= i3 * a.ne2 * a.ne1;
+        const int64_t i2 = row / a.ne1, i1 = row - i2 * a.ne1;
+        const T *src = reinterpret_cast<const T *>(a.p + i3 * a.nb3 + i2 * a.nb2 + i1 * a.nb1);
+        T *dst = reinterpret_cast<T *>(d.p + i3 * d.nb3 + i2 * d.nb2 + i1 * d.nb1);
+        const int p = pos[i2];
+        const int ic = 2 * j;
+        if (r.neox && ic >= r.n_dims) {                      // beyond the rotated part: plain copy of the pair
+            dst[ic] = src[ic];
+            dst[ic + 1] = src[ic + 1];
+            continue;
+        }
+        float theta = r.neox ? (float)p * r.freq_scale : (float)p;
+        for (int q = 0; q < j; ++q) theta *= r.theta_scale;
+        float c, s;
+        rope_yarn_dev(theta, r, r.neox ? 0 : ic, &c, &s);
+        const int i0 = r.neox ? j : ic, i1x = r.neox ? j + r.n_dims / 2 : ic + 1;
+        const float x0 = convert<T, float>(src[i0]), x1 = convert<T, float>(src[i1x]);
+        float zeta = 1.0f;
+        if (sizeof(T) == 4 && !r.neox && r.xpos_base != 0.0f) {
+            zeta = powf(((float)ic + 0.4f * (float)a.ne0) / (1.4f * (float)a.ne0), (float)p / r.xpos_base);
+            if (r.xpos_down) zeta = 1.0f / zeta;
+        }
+        dst[i0] = convert<float, T>(x0 * c * zeta - x1 * s * zeta);
+        dst[i1x] = convert<float, T>(x0 * s * zeta + x1 * c * zeta);
+    }
+}
+
+// ---- REPEAT (src/ggml.c:10323): dst[i] = src0[i mod src0 shape], 2- and 4-byte elements ------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) repeat_kernel(T4 a, T4 d, int64_t total) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = t / d.ne0;
+        const int64_t j0 = t - r * d.ne0;
+        const int64_t j3 = r / (d.ne2 * d.ne1);
+        r -= j3 * d.ne2 * d.ne1;
+        const int64_t j2 = r / d.ne1, j1 = r - j2 * d.ne1;
+        *reinterpret_cast<T *>(d.p + j3 * d.nb3 + j2 * d.nb2 + j1 * d.nb1 + j0 * d.nb0) =
+            *reinterpret_cast<const T *>(a.p + (j3 % a.ne3) * a.nb3 + (j2 % a.ne2) * a.nb2 + (j1 % a.ne1) * a.nb1 + (j0 % a.ne0) * a.nb0);
+    }
+}
+
 // ---- MUL_MAT with a dense (F32 / F16) src0 -----------------------------------------------------------------------------------------------
 // dst[i3][i2][n][m] = sum_k src0[i3 / r3][i2 / r2][m][k] * src1[i3][i2][n][k]   (src/ggml.c:11808; both operands k-contiguous, any row /
 // batch strides, so permuted views of the KV cache multiply in place).  CTA = TM x TN tile of one (i2, i3) slice, k in steps of 16
@@ -686,6 +757,50 @@ int b200_op_copy(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *dst)
     else if (src0->type == B200_TYPE_F32) copy_kernel<float, __half><<<grid, 256, 0, ctx->stream>>>(a, d, n);
     else copy_kernel<__half, float><<<grid, 256, 0, ctx->stream>>>(a, d, n);
     return finish(ctx, "copy");
+}
+
+int b200_op_rope(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *pos, const b200_tensor *dst, const b200_rope_params *rp) {
+    OPS_ENTER(ctx);
+    B200_REQUIRE(ctx, src0 && pos && dst && rp, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, (src0->type == B200_TYPE_F32 || src0->type == B200_TYPE_F16) && dst->type == src0->type && pos->type == B200_TYPE_I32, B200_ERR_UNSUPPORTED);
+    B200_REQUIRE(ctx, (rp->mode & 4) == 0, B200_ERR_UNSUPPORTED);                                  // GLM layout: not built
+    B200_REQUIRE(ctx, same_shape(src0, dst) && src0->nb[0] == elt_size(src0->type) && dst->nb[0] == src0->nb[0], B200_ERR_INVALID);
+    B200_REQUIRE(ctx, rp->n_dims > 0 && rp->n_dims % 2 == 0 && rp->n_dims <= src0->ne[0] && src0->ne[0] % 2 == 0, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, pos->ne[0] >= src0->ne[2] && pos->nb[0] == 4, B200_ERR_INVALID);
+    const int64_t n = nelements(src0);
+    if (n == 0) return B200_OK;
+    RopeK r;
+    r.n_dims = rp->n_dims;
+    r.neox = (rp->mode & 2) != 0;
+    r.theta_scale = powf(rp->freq_base, -2.0f / rp->n_dims);
+    r.freq_scale = rp->freq_scale; r.ext_factor = rp->ext_factor; r.attn_factor = rp->attn_factor;
+    // ggml_rope_yarn_corr_dims (src/ggml.c:13765)
+    const float two_pi = 2.0f * 3.14159265358979323846f;
+    const float lo = floorf(rp->n_dims * logf(rp->n_orig_ctx / (rp->beta_fast * two_pi)) / (2 * logf(rp->freq_base)));
+    const float hi = ceilf(rp->n_dims * logf(rp->n_orig_ctx / (rp->beta_slow * two_pi)) / (2 * logf(rp->freq_base)));
+    r.corr0 = lo > 0 ? lo : 0;
+    r.corr1 = hi < rp->n_dims - 1 ? hi : (float)(rp->n_dims - 1);
+    r.xpos_base = rp->xpos_base; r.xpos_down = rp->xpos_down;
+    const T4 a = view(src0), d = view(dst);
+    const int grid = grid_for(n / 2, 256, ctx->sm_count);
+    if (src0->type == B200_TYPE_F32) rope_kernel<float><<<grid, 256, 0, ctx->stream>>>(a, d, static_cast<const int32_t *>(pos->data), r);
+    else rope_kernel<__half><<<grid, 256, 0, ctx->stream>>>(a, d, static_cast<const int32_t *>(pos->data), r);
+    return finish(ctx, "rope");
+}
+
+int b200_op_repeat(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *dst) {
+    OPS_ENTER(ctx);
+    B200_REQUIRE(ctx, src0 && dst, B200_ERR_INVALID);
+    const int es = elt_size(src0->type);
+    B200_REQUIRE(ctx, es && src0->type == dst->type, B200_ERR_UNSUPPORTED);
+    for (int i = 0; i < 4; ++i) B200_REQUIRE(ctx, src0->ne[i] > 0 && dst->ne[i] % src0->ne[i] == 0, B200_ERR_INVALID);
+    const int64_t n = nelements(dst);
+    if (n == 0) return B200_OK;
+    const T4 a = view(src0), d = view(dst);
+    const int grid = grid_for(n, 256, ctx->sm_count);
+    if (es == 4) repeat_kernel<uint32_t><<<grid, 256, 0, ctx->stream>>>(a, d, n);
+    else repeat_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(a, d, n);
+    return finish(ctx, "repeat");
 }
 
 int b200_op_mul_mat_dense(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *src1, const b200_tensor *dst) {

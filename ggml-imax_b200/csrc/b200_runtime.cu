@@ -277,6 +277,74 @@ int b200_event_synchronize(b200_event *ev) {
     return B200_OK;
 }
 
+// ---- a sequence of this context's launches recorded once and replayed as one CUDA graph ---------------------------------------
+// (what the reference's CUDA backend does for a decode step, src/ggml-cuda.cu:2461-2709; here behind ggml_backend_graph_plan_*)
+struct b200_graph {
+    cudaGraphExec_t exec;
+    int device;
+    int64_t kernel_nodes;
+};
+
+int b200_graph_begin(b200_ctx *ctx) {
+    B200_REQUIRE(ctx, ctx != NULL, B200_ERR_INVALID);
+    B200_CUDA_TRY(ctx, b200_use_device(ctx->device));
+    // relaxed: the recording thread may still allocate (a scratch area that has to grow invalidates nothing)
+    B200_CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    return B200_OK;
+}
+
+int b200_graph_end(b200_ctx *ctx, b200_graph **out) {
+    B200_REQUIRE(ctx, ctx != NULL, B200_ERR_INVALID);
+    if (out) *out = NULL;
+    cudaGraph_t graph = NULL;
+    const cudaError_t rc = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc != cudaSuccess || graph == NULL) {
+        b200_set_error(ctx, "the recorded sequence cannot be a CUDA graph: %s", cudaGetErrorString(rc));
+        (void)cudaGetLastError();
+        if (graph) (void)cudaGraphDestroy(graph);
+        return B200_ERR_UNSUPPORTED;
+    }
+    if (!out) {
+        (void)cudaGraphDestroy(graph);
+        return B200_OK;
+    }
+    b200_graph *g = (b200_graph *)calloc(1, sizeof(b200_graph));
+    if (!g) {
+        (void)cudaGraphDestroy(graph);
+        return B200_ERR_ALLOC;
+    }
+    g->device = ctx->device;
+    size_t n = 0;
+    if (cudaGraphGetNodes(graph, NULL, &n) == cudaSuccess) g->kernel_nodes = (int64_t)n;
+    const cudaError_t ri = cudaGraphInstantiate(&g->exec, graph, 0);
+    (void)cudaGraphDestroy(graph);
+    if (ri != cudaSuccess) {
+        b200_set_error(ctx, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ri));
+        (void)cudaGetLastError();
+        free(g);
+        return B200_ERR_UNSUPPORTED;
+    }
+    *out = g;
+    return B200_OK;
+}
+
+int b200_graph_launch(b200_ctx *ctx, b200_graph *g) {
+    B200_REQUIRE(ctx, ctx && g && g->device == ctx->device, B200_ERR_INVALID);
+    B200_CUDA_TRY(ctx, b200_use_device(ctx->device));
+    B200_CUDA_TRY(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+    ctx->launches += g->kernel_nodes;
+    return B200_OK;
+}
+
+int64_t b200_graph_node_count(const b200_graph *g) { return g ? g->kernel_nodes : 0; }
+
+void b200_graph_destroy(b200_graph *g) {
+    if (!g) return;
+    if (cudaSetDevice(g->device) == cudaSuccess) (void)cudaGraphExecDestroy(g->exec);
+    (void)cudaGetLastError();
+    free(g);
+}
+
 int b200_upload(b200_ctx *ctx, void *dst_dev, const void *src_host, size_t size) {
     int rc = b200_upload_async(ctx, dst_dev, src_host, size);
     if (rc != B200_OK) return rc;
@@ -343,60 +411,6 @@ int b200_synchronize(b200_ctx *ctx) {
         return B200_ERR_CUDA;
     }
     return B200_OK;
-}
-
-struct b200_graph {
-    cudaGraph_t graph;
-    cudaGraphExec_t exec;
-    int device;
-};
-
-int b200_graph_begin(b200_ctx *ctx) {
-    B200_REQUIRE(ctx, ctx != NULL, B200_ERR_INVALID);
-    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    B200_CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    return B200_OK;
-}
-
-int b200_graph_end(b200_ctx *ctx, b200_graph **out) {
-    B200_REQUIRE(ctx, ctx && out, B200_ERR_INVALID);
-    *out = NULL;
-    cudaGraph_t g = NULL;
-    B200_CUDA_TRY(ctx, cudaStreamEndCapture(ctx->stream, &g));
-    cudaGraphExec_t exec = NULL;
-    cudaError_t e = cudaGraphInstantiate(&exec, g, 0);
-    if (e != cudaSuccess) {
-        b200_set_error(ctx, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
-        (void)cudaGetLastError();
-        cudaGraphDestroy(g);
-        return B200_ERR_CUDA;
-    }
-    b200_graph *h = (b200_graph *)calloc(1, sizeof(b200_graph));
-    if (!h) {
-        cudaGraphExecDestroy(exec);
-        cudaGraphDestroy(g);
-        return B200_ERR_ALLOC;
-    }
-    h->graph = g;
-    h->exec = exec;
-    h->device = ctx->device;
-    *out = h;
-    return B200_OK;
-}
-
-int b200_graph_launch(b200_ctx *ctx, b200_graph *graph) {
-    B200_REQUIRE(ctx, ctx && graph, B200_ERR_INVALID);
-    B200_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    B200_CUDA_TRY(ctx, cudaGraphLaunch(graph->exec, ctx->stream));
-    return B200_OK;
-}
-
-void b200_graph_destroy(b200_graph *graph) {
-    if (!graph) return;
-    cudaSetDevice(graph->device);
-    if (graph->exec) cudaGraphExecDestroy(graph->exec);
-    if (graph->graph) cudaGraphDestroy(graph->graph);
-    free(graph);
 }
 
 int b200_reserve_workspace(b200_ctx *ctx, int type, int64_t k, int64_t m, int64_t n) {

@@ -504,6 +504,7 @@ struct b200_backend_context {
     int       plan_next;   /* round-robin eviction */
     int       opt_plans;   /* 0: never build decode plans (ggml_backend_b200_set_option "plans") */
     int       opt_fuse;    /* 0: one kernel per glue node (ggml_backend_b200_set_option "fuse") */
+    int       opt_graphs;  /* 0: graph plans never record a CUDA graph (ggml_backend_b200_set_option "graphs") */
     int64_t   plan_launches;
     int64_t   fused_nodes; /* graph nodes that did not need a launch of their own */
     int       failed;      /* an asynchronous error surfaced in synchronize (which cannot return one): the next graph_compute reports it */
@@ -716,6 +717,13 @@ static bool b200_glue_supported(const struct ggml_tensor *op) {
     case GGML_OP_DUP:
     case GGML_OP_CONT:
         return b200_copy_supported(a, op);
+    case GGML_OP_ROPE:          /* forward, normal and NeoX pairing (GPT-J: examples/gpt-j/main.cpp:473-474); the GLM layout is declined */
+        return a && b && (a->type == GGML_TYPE_F32 || a->type == GGML_TYPE_F16) && op->type == a->type && b->type == GGML_TYPE_I32 &&
+               (((const int32_t *)op->op_params)[2] & 4) == 0 && a->nb[0] == ggml_type_size(a->type) && op->nb[0] == a->nb[0] && a->ne[0] % 2 == 0 &&
+               ggml_is_contiguous(b) && b->ne[0] >= a->ne[2];
+    case GGML_OP_REPEAT:
+        return a && a->type == op->type && (a->type == GGML_TYPE_F32 || a->type == GGML_TYPE_F16 || a->type == GGML_TYPE_I32 || a->type == GGML_TYPE_I16) &&
+               b200_can_repeat(a, op);
     default:
         return false;
     }
@@ -779,6 +787,23 @@ static enum ggml_status b200_compute_glue(struct b200_backend_context *bc, struc
     case GGML_OP_CPY:
     case GGML_OP_DUP:
     case GGML_OP_CONT: rc = b200_op_copy(bc->ctx, &a, &d); break;
+    case GGML_OP_ROPE: {        /* op_params as ggml_rope_impl lays them out (src/ggml.c:5866-5889) */
+        const int32_t *op = (const int32_t *)node->op_params;
+        b200_rope_params rp;
+        memset(&rp, 0, sizeof(rp));
+        rp.n_dims = op[1]; rp.mode = op[2]; rp.n_ctx = op[3]; rp.n_orig_ctx = op[4];
+        memcpy(&rp.freq_base, op + 5, sizeof(float));
+        memcpy(&rp.freq_scale, op + 6, sizeof(float));
+        memcpy(&rp.ext_factor, op + 7, sizeof(float));
+        memcpy(&rp.attn_factor, op + 8, sizeof(float));
+        memcpy(&rp.beta_fast, op + 9, sizeof(float));
+        memcpy(&rp.beta_slow, op + 10, sizeof(float));
+        memcpy(&rp.xpos_base, op + 11, sizeof(float));
+        { bool down; memcpy(&down, op + 12, sizeof(bool)); rp.xpos_down = down ? 1 : 0; }
+        rc = b200_op_rope(bc->ctx, &a, &b, &d, &rp);
+        break;
+    }
+    case GGML_OP_REPEAT: rc = b200_op_repeat(bc->ctx, &a, &d); break;
     case GGML_OP_MUL_MAT: rc = b200_op_mul_mat_dense(bc->ctx, &a, &b, &d); break;
     default: rc = B200_ERR_UNSUPPORTED; break;
     }
@@ -1362,13 +1387,47 @@ GGML_CALL static enum ggml_status b200_backend_graph_compute(ggml_backend_t back
     return GGML_STATUS_SUCCESS;
 }
 
-/* ggml_backend_graph_plan_create / _free / _compute (src/ggml-backend-impl.h:94-99, src/ggml-backend.c:257-273): the explicit
- * form of the above.  Like the reference CPU backend's plan (src/ggml-backend.c:761-790) it keeps a shallow copy of the cgraph,
- * so the graph has to outlive the plan; the persistent-launch plans of its decode runs are built at the first compute and
- * cached in the backend like any other. */
+/* ggml_backend_graph_plan_create / _free / _compute (src/ggml-backend-impl.h:94-99, src/ggml-backend.c:257-273): the explicit,
+ * static form of the above.  Like the reference CPU backend's plan (src/ggml-backend.c:761-790) it keeps a shallow copy of the cgraph,
+ * so the graph has to outlive the plan.  The first compute runs node by node (it sizes the scratch areas and builds the
+ * persistent-launch plans of the decode runs); the second records the same sequence into a CUDA graph (b200_graph_begin / _end), and from
+ * then on a compute is ONE graph launch -- the launch-bound whole-model decode step (GPT-2 117M: ~170 kernels of 2-5 us) stops
+ * paying the host's per-launch cost.  The recording freezes addresses and scalar arguments, so every compute first fingerprints
+ * what a kernel would read from the nodes (op, op_params, shapes, strides, addresses) and records again when that changed; a
+ * graph that cannot be recorded (MUL_MAT_ID reads its routing back, split tensors drive several devices) stays node by node. */
 struct b200_graph_plan {
     struct ggml_cgraph cgraph;
+    b200_graph *graph;
+    uint64_t fingerprint;
+    int state;                     /* 0: never computed, 1: computed node by node once, 2: recorded, -1: cannot be recorded */
 };
+
+static uint64_t b200_fnv(uint64_t h, const void *p, size_t n) {
+    const unsigned char *c = (const unsigned char *)p;
+    for (size_t i = 0; i < n; i++) h = (h ^ c[i]) * 0x100000001b3ull;
+    return h;
+}
+static uint64_t b200_graph_fingerprint(const struct ggml_cgraph *g, bool *recordable) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    *recordable = true;
+    h = b200_fnv(h, &g->n_nodes, sizeof(g->n_nodes));
+    for (int i = 0; i < g->n_nodes; i++) {
+        const struct ggml_tensor *t = g->nodes[i];
+        if (t->op == GGML_OP_MUL_MAT_ID) *recordable = false;
+        for (int k = -1; k < GGML_MAX_SRC; k++) {
+            const struct ggml_tensor *x = k < 0 ? t : t->src[k];
+            if (!x) continue;
+            if (b200_tensor_is_split(x)) *recordable = false;
+            h = b200_fnv(h, &x->data, sizeof(x->data));
+            h = b200_fnv(h, x->ne, sizeof(x->ne));
+            h = b200_fnv(h, x->nb, sizeof(x->nb));
+            h = b200_fnv(h, &x->type, sizeof(x->type));
+        }
+        h = b200_fnv(h, &t->op, sizeof(t->op));
+        h = b200_fnv(h, t->op_params, sizeof(t->op_params));
+    }
+    return h;
+}
 
 GGML_CALL static ggml_backend_graph_plan_t b200_backend_graph_plan_create(ggml_backend_t backend, const struct ggml_cgraph *cgraph) {
     GGML_UNUSED(backend);
@@ -1380,12 +1439,64 @@ GGML_CALL static ggml_backend_graph_plan_t b200_backend_graph_plan_create(ggml_b
 
 GGML_CALL static void b200_backend_graph_plan_free(ggml_backend_t backend, ggml_backend_graph_plan_t plan) {
     GGML_UNUSED(backend);
+    struct b200_graph_plan *gp = (struct b200_graph_plan *)plan;
+    if (gp) b200_graph_destroy(gp->graph);
     free(plan);
 }
 
 GGML_CALL static enum ggml_status b200_backend_graph_plan_compute(ggml_backend_t backend, ggml_backend_graph_plan_t plan) {
+    struct b200_backend_context *bc = (struct b200_backend_context *)backend->context;
     struct b200_graph_plan *gp = (struct b200_graph_plan *)plan;
-    return b200_backend_graph_compute(backend, &gp->cgraph);
+    if (!bc->opt_graphs || gp->state < 0) return b200_backend_graph_compute(backend, &gp->cgraph);
+    bool recordable = true;
+    const uint64_t fp = b200_graph_fingerprint(&gp->cgraph, &recordable);
+    if (!recordable) {
+        gp->state = -1;
+        return b200_backend_graph_compute(backend, &gp->cgraph);
+    }
+    if (gp->state == 2 && fp != gp->fingerprint) {          /* the caller changed the graph under the plan: record again */
+        b200_graph_destroy(gp->graph);
+        gp->graph = NULL;
+        gp->state = 1;
+    }
+    if (gp->state == 2) {
+        if (bc->failed) {
+            bc->failed = 0;
+            return GGML_STATUS_FAILED;
+        }
+        if (b200_graph_launch(bc->ctx, gp->graph) == B200_OK) return GGML_STATUS_SUCCESS;
+        fprintf(stderr, "ggml-b200: graph launch failed: %s\n", b200_last_error(bc->ctx));
+        return GGML_STATUS_FAILED;
+    }
+    if (gp->state == 0) {                                    /* first compute: as graph_compute would (allocations, decode plans) */
+        gp->state = 1;
+        gp->fingerprint = fp;
+        return b200_backend_graph_compute(backend, &gp->cgraph);
+    }
+    /* record, then launch what was recorded */
+    gp->fingerprint = fp;
+    if (b200_graph_begin(bc->ctx) != B200_OK) {
+        gp->state = -1;
+        return b200_backend_graph_compute(backend, &gp->cgraph);
+    }
+    const enum ggml_status st = b200_backend_graph_compute(backend, &gp->cgraph);
+    b200_graph *g = NULL;
+    const int rc = b200_graph_end(bc->ctx, st == GGML_STATUS_SUCCESS ? &g : NULL);
+    if (st != GGML_STATUS_SUCCESS || rc != B200_OK || !g) {  /* nothing ran: compute it the plain way and stop trying */
+        b200_graph_destroy(g);
+        gp->state = -1;
+        return b200_backend_graph_compute(backend, &gp->cgraph);
+    }
+    gp->graph = g;
+    gp->state = 2;
+    if (b200_graph_launch(bc->ctx, gp->graph) != B200_OK) return GGML_STATUS_FAILED;
+    return GGML_STATUS_SUCCESS;
+}
+
+/* kernel nodes of the CUDA graph a plan replays (0: the plan computes node by node) */
+GGML_CALL int64_t ggml_backend_b200_graph_plan_kernels(ggml_backend_graph_plan_t plan) {
+    const struct b200_graph_plan *gp = (const struct b200_graph_plan *)plan;
+    return gp && gp->state == 2 ? b200_graph_node_count(gp->graph) : 0;
 }
 
 /* nodes [first, last) one after the other; with one_unit_next: only the first unit of work found in that window (a node, a same-input
@@ -1562,6 +1673,7 @@ GGML_CALL ggml_backend_t ggml_backend_b200_init(int device) {
     bc->device = device;
     bc->opt_plans = 1;
     bc->opt_fuse = 1;
+    bc->opt_graphs = 1;
     snprintf(bc->name, sizeof(bc->name), "%s%d", GGML_B200_NAME, device);
     if (b200_ctx_create(device, &bc->ctx) != B200_OK) {
         fprintf(stderr, "ggml-b200: %s\n", b200_last_error(NULL));
@@ -1615,6 +1727,10 @@ GGML_CALL int ggml_backend_b200_set_option(ggml_backend_t backend, const char *k
     GGML_ASSERT(ggml_backend_is_b200(backend));
     if (strcmp(key, "plans") == 0) {
         ((struct b200_backend_context *)backend->context)->opt_plans = value != 0;
+        return B200_OK;
+    }
+    if (strcmp(key, "graphs") == 0) {
+        ((struct b200_backend_context *)backend->context)->opt_graphs = value != 0;
         return B200_OK;
     }
     if (strcmp(key, "fuse") == 0) {

@@ -42,6 +42,8 @@ GGML_API GGML_CALL int64_t                    ggml_backend_b200_launch_count(ggm
 GGML_API GGML_CALL int64_t                    ggml_backend_b200_plan_launch_count(ggml_backend_t backend);
 /* graph nodes that were folded into the kernel of a neighbour (NORM+MUL+ADD, SCALE+DIAG_MASK_INF+SOFT_MAX, ...) */
 GGML_API GGML_CALL int64_t                    ggml_backend_b200_fused_node_count(ggml_backend_t backend);
+/* kernel nodes of the CUDA graph a ggml_backend_graph_plan_t of this backend replays; 0 while (or if) it computes node by node */
+GGML_API GGML_CALL int64_t                    ggml_backend_b200_graph_plan_kernels(ggml_backend_graph_plan_t plan);
 /* "plans" (0/1: compute runs of decode MUL_MATs as one persistent launch), "fuse" (0/1: fold in-place neighbours into one kernel);
  * everything else forwards to
  * b200_ctx_set_option (include/ggml_b200.h) */

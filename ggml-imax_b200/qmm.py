@@ -57,6 +57,13 @@ class Tensor(C.Structure):
                 ("q_total_blocks", C.c_int64), ("q_block_off", C.c_int64)]
 
 
+class RopeParams(C.Structure):
+    """b200_rope_params: the op_params of GGML_OP_ROPE (src/ggml.c:5866-5889)"""
+    _fields_ = [("n_dims", C.c_int32), ("mode", C.c_int32), ("n_ctx", C.c_int32), ("n_orig_ctx", C.c_int32), ("freq_base", C.c_float),
+                ("freq_scale", C.c_float), ("ext_factor", C.c_float), ("attn_factor", C.c_float), ("beta_fast", C.c_float), ("beta_slow", C.c_float),
+                ("xpos_base", C.c_float), ("xpos_down", C.c_int32)]
+
+
 class Epilogue(C.Structure):
     _fields_ = [("bias_dev", C.c_void_p), ("residual_dev", C.c_void_p), ("act", C.c_int32), ("reserved", C.c_int32)]
 
@@ -147,6 +154,9 @@ _SIGNATURES = {
     "b200_op_diag_mask_inf": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.c_int]),
     "b200_op_soft_max": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.c_float, C.c_float, C.c_int]),
     "b200_op_copy": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor)]),
+    "b200_graph_node_count": (C.c_int64, [C.c_void_p]),
+    "b200_op_rope": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(RopeParams)]),
+    "b200_op_repeat": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor)]),
     "b200_op_mul_mat_dense": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor)]),
     "b200_block_dots": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "b200_mul_mat_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -363,6 +373,14 @@ class Context:
 
     def op_copy(self, a, dst):
         self._check(self.lib.b200_op_copy(self.h, self._d(a), self._d(dst)))
+
+    def op_rope(self, a, pos, dst, n_dims: int, mode: int = 0, n_ctx: int = 0, n_orig_ctx: int = 0, freq_base: float = 10000.0, freq_scale: float = 1.0,
+                ext_factor: float = 0.0, attn_factor: float = 1.0, beta_fast: float = 0.0, beta_slow: float = 0.0, xpos_base: float = 0.0, xpos_down: bool = False):
+        rp = RopeParams(n_dims, mode, n_ctx, n_orig_ctx, freq_base, freq_scale, ext_factor, attn_factor, beta_fast, beta_slow, xpos_base, int(xpos_down))
+        self._check(self.lib.b200_op_rope(self.h, self._d(a), self._d(pos), self._d(dst), C.byref(rp)))
+
+    def op_repeat(self, a, dst):
+        self._check(self.lib.b200_op_repeat(self.h, self._d(a), self._d(dst)))
 
     def op_mul_mat_dense(self, a, b, dst):
         self._check(self.lib.b200_op_mul_mat_dense(self.h, self._d(a), self._d(b), self._d(dst)))

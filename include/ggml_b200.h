@@ -121,18 +121,19 @@ B200_API int b200_host_malloc(void **hptr, size_t size);
 B200_API int b200_host_free(void *hptr);
 
 /* ---- launch graphs --------------------------------------------------------------------------
- * Decode runs hundreds of microsecond-sized mul_mats per token, so the launch path matters as much as
- * the kernels.  b200_graph_begin/end bracket any sequence of the asynchronous calls of this header
- * (b200_mul_mat, b200_quantize_q8_0, b200_*_async on pinned memory ...) on the context's stream and
- * turn it into one replayable CUDA graph; b200_graph_launch replays it.  This is what the backend's
- * graph_compute uses for a repeated ggml_cgraph (cf. the reference's opt-in GGML_CUDA_USE_GRAPHS,
- * src/ggml-cuda.cu:2461-2709).  No allocation may happen between begin and end: call
- * b200_reserve_workspace first when the sequence contains prefill-sized mul_mats. */
+ * A launch-bound sequence (the whole-model decode step of a small model: GPT-2 117M issues ~170 kernels of 2-5 us) pays the host's
+ * per-launch cost on every kernel.  b200_graph_begin/end bracket any sequence of the asynchronous calls of this header on the
+ * context's stream and turn it into one replayable CUDA graph; b200_graph_launch replays it.  Between begin and end every call
+ * is recorded instead of executed; a call that has to wait for the device (b200_synchronize, b200_download, a scratch area that
+ * must grow: call b200_reserve_workspace first) makes b200_graph_end return B200_ERR_UNSUPPORTED, and nothing is kept.  The
+ * recorded addresses and scalar arguments are frozen: record again when they change.  The backend's ggml_backend_graph_plan_*
+ * uses this (cf. the reference's opt-in GGML_CUDA_USE_GRAPHS, src/ggml-cuda.cu:2461-2709). */
 typedef struct b200_graph b200_graph;
-B200_API int  b200_graph_begin(b200_ctx *ctx);
-B200_API int  b200_graph_end(b200_ctx *ctx, b200_graph **out);
-B200_API int  b200_graph_launch(b200_ctx *ctx, b200_graph *graph);
-B200_API void b200_graph_destroy(b200_graph *graph);
+B200_API int     b200_graph_begin(b200_ctx *ctx);
+B200_API int     b200_graph_end(b200_ctx *ctx, b200_graph **out);       /* out == NULL: discard what was recorded */
+B200_API int     b200_graph_launch(b200_ctx *ctx, b200_graph *graph);
+B200_API int64_t b200_graph_node_count(const b200_graph *graph);         /* nodes (kernels, copies) one launch replays */
+B200_API void    b200_graph_destroy(b200_graph *graph);
 /* make sure the scratch of a prefill mul_mat (type, k, m, n) exists (no-op if already large enough) */
 B200_API int  b200_reserve_workspace(b200_ctx *ctx, int type, int64_t k, int64_t m, int64_t n);
 
@@ -351,6 +352,16 @@ B200_API int b200_op_soft_max(b200_ctx *ctx, const b200_tensor *src0, const b200
 /* GGML_OP_CPY / DUP / CONT (ggml_compute_forward_dup, src/ggml.c:8535): element i of the flattened src0 to element i of the flattened dst,
  * both arbitrarily strided; F32 <-> F16 conversions, or any same-type pair of 2- / 4-byte elements (F32, F16, I32, I16) */
 B200_API int b200_op_copy(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *dst);
+/* GGML_OP_ROPE, forward (src/ggml.c:13775, :13953; op_params of ggml_rope_custom, src/ggml.c:5866-5889): src0 F32 or F16 [ne0][heads][tokens][b],
+   pos I32 [tokens].  mode bit 1 = NeoX pairing; bit 2 (GLM) is B200_ERR_UNSUPPORTED. */
+typedef struct b200_rope_params {
+    int32_t n_dims, mode, n_ctx, n_orig_ctx;
+    float   freq_base, freq_scale, ext_factor, attn_factor, beta_fast, beta_slow, xpos_base;
+    int32_t xpos_down;
+} b200_rope_params;
+B200_API int b200_op_rope(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *pos, const b200_tensor *dst, const b200_rope_params *params);
+/* GGML_OP_REPEAT (src/ggml.c:10323): dst tiles src0 along every dimension (dst->ne[i] a multiple of src0->ne[i]); F32, F16, I16, I32 */
+B200_API int b200_op_repeat(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *dst);
 /* GGML_OP_MUL_MAT with an F32 / F16 src0 (ggml_compute_forward_mul_mat, src/ggml.c:11808): dst[n][m] = sum_k src0[m][k] * src1[n][k] per
  * (i2, i3) with the broadcast of src0 over src1's batch dims; both operands k-contiguous, any row / batch strides (K*Q and V*softmax(KQ) on
  * permuted views of the KV cache, main-backend.cpp:567, :597); fp32 accumulation */

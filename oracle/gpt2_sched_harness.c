@@ -37,6 +37,7 @@
 /* instrumentation of the B200 backend (ggml-imax_b200/host/ggml-b200.h) */
 extern int64_t ggml_backend_b200_launch_count(ggml_backend_t backend);
 extern int64_t ggml_backend_b200_fused_node_count(ggml_backend_t backend);
+extern int64_t ggml_backend_b200_graph_plan_kernels(ggml_backend_graph_plan_t plan);
 extern int ggml_backend_b200_set_option(ggml_backend_t backend, const char *key, int64_t value);
 
 struct layer {
@@ -265,13 +266,38 @@ int main(int argc, char **argv) {
         launches_c = ggml_backend_b200_launch_count(gpu) - l0;
         nodes_c = Gc.gf->n_nodes;
         ggml_backend_tensor_get(Gc.logits, lc, (size_t)(N - 1) * N_VOCAB * sizeof(float), sizeof(float) * N_VOCAB);
+        /* the same step as a ggml_backend_graph_plan: computed node by node once, recorded once, then replayed (one CUDA graph launch) */
+        double ms_plan = 0.0;
+        long long plan_kernels = 0;
+        int plan_equal = 1;
+        if (N == 1) {
+            ggml_backend_graph_plan_t gplan = ggml_backend_graph_plan_create(gpu, Gc.gf);
+            const int reps = 20;
+            for (int r = 0; r < 3 + reps; r++) {
+                if (r == 3) { ggml_backend_synchronize(gpu); t0 = ggml_time_us(); }
+                ggml_backend_tensor_set(Gc.tokens, tokens + n_past, 0, sizeof(int32_t));
+                ggml_backend_tensor_set(Gc.positions, pos, 0, sizeof(int32_t));
+                if (ggml_backend_graph_plan_compute(gpu, gplan) != GGML_STATUS_SUCCESS) { printf("], \"error\": \"graph_plan_compute failed\"}\n"); return 7; }
+                ggml_backend_synchronize(gpu);
+            }
+            ms_plan = (double)(ggml_time_us() - t0) / 1e3 / reps;
+            plan_kernels = (long long)ggml_backend_b200_graph_plan_kernels(gplan);
+            float *lp = (float *)malloc(sizeof(float) * N_VOCAB);
+            ggml_backend_tensor_get(Gc.logits, lp, 0, sizeof(float) * N_VOCAB);
+            plan_equal = memcmp(lp, lc, sizeof(float) * N_VOCAB) == 0;
+            free(lp);
+            ggml_backend_graph_plan_free(gpu, gplan);
+            if (!plan_equal) ok = 0;
+        }
         const double e = nmse(lb, la, N_VOCAB), ec = nmse(lc, la, N_VOCAB);
         int fin = 1;
         for (int i = 0; i < N_VOCAB; i++) if (!isfinite(lb[i]) || !isfinite(lc[i])) fin = 0;
         if (!(e <= 5e-4) || !(ec <= 5e-4) || !fin) ok = 0;
         printf("%s{\"n_past\": %d, \"n\": %d, \"logits_nmse_vs_cpu\": %.3e, \"b200_whole_graph_logits_nmse_vs_cpu\": %.3e, \"finite\": %s, \"ms_cpu\": %.2f, "
-               "\"ms_sched_b200\": %.2f, \"ms_b200_whole_graph\": %.3f, \"ms_b200_enqueue\": %.3f, \"b200_launches\": %lld, \"graph_nodes\": %lld}", step ? ", " : "", n_past, N, e, ec,
-               fin ? "true" : "false", ms_cpu, ms_sched, ms_b200, ms_b200_enqueue, (long long)launches_c, (long long)nodes_c);
+               "\"ms_sched_b200\": %.2f, \"ms_b200_whole_graph\": %.3f, \"ms_b200_enqueue\": %.3f, \"b200_launches\": %lld, \"graph_nodes\": %lld, "
+               "\"ms_b200_graph_plan\": %.3f, \"graph_plan_kernels\": %lld, \"graph_plan_equals_node_by_node\": %s}", step ? ", " : "", n_past, N, e, ec,
+               fin ? "true" : "false", ms_cpu, ms_sched, ms_b200, ms_b200_enqueue, (long long)launches_c, (long long)nodes_c, ms_plan, plan_kernels,
+               plan_equal ? "true" : "false");
         n_past += N;
         ggml_free(Ga.ctx);
         ggml_free(Gb.ctx);

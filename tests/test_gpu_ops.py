@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import Q4_0, Q8_0, nmse
+from rope_restatement import rope_numpy
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-6
@@ -344,3 +345,99 @@ def test_events_order_two_streams(qmm, gpu_ctx):
         gpu_ctx.lib.b200_event_destroy(ev)
     finally:
         other.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float16])
+@pytest.mark.parametrize("ne0,heads,n_dims,mode,yarn,xpos", [(64, 16, 64, 0, False, False),      # GPT-J: ggml_rope_inplace(.., n_rot = 64, 0, 0), examples/gpt-j/main.cpp:473
+                                                             (128, 5, 128, 0, True, False), (64, 7, 64, 2, False, False), (80, 4, 20, 2, True, False),
+                                                             (128, 3, 128, 0, False, True)])
+def test_rope(qmm, gpu_ctx, dtype, ne0, heads, n_dims, mode, yarn, xpos):
+    """GGML_OP_ROPE forward: normal and NeoX pairing, YaRN mixing (ext_factor != 0) and the xPos factor, F32 and F16, also in place"""
+    rng = np.random.default_rng(ne0 + heads + mode)
+    B, T = 2, 9
+    x = rng.uniform(-1, 1, (B, T, heads, ne0)).astype(dtype)
+    pos = rng.integers(0, 512, T).astype(np.int32)
+    kw = dict(n_dims=n_dims, mode=mode, n_orig_ctx=256 if yarn else 0, freq_base=10000.0, freq_scale=0.5 if yarn else 1.0, ext_factor=0.7 if yarn else 0.0,
+              attn_factor=1.1 if yarn else 1.0, beta_fast=32.0 if yarn else 0.0, beta_slow=1.0 if yarn else 0.0)
+    if xpos:
+        kw.update(xpos_base=512.0, xpos_down=True)
+    want = rope_numpy(x, pos, **kw)
+    ttype = qmm.TYPE_F32 if dtype == np.float32 else qmm.TYPE_F16
+    a, tp = up(qmm, gpu_ctx, x), up(qmm, gpu_ctx, pos)
+    dst = qmm.DTensor(gpu_ctx, ttype, [ne0, heads, T, B])
+    gpu_ctx.op_rope(a, tp, dst, n_ctx=512, **kw)
+    gpu_ctx.op_rope(a, tp, a, n_ctx=512, **kw)                       # ggml_rope_inplace
+    gpu_ctx.synchronize()
+    got, got_inplace = dst.numpy().reshape(x.shape), a.numpy().reshape(x.shape)
+    assert np.array_equal(got, got_inplace)
+    assert nmse(got.astype(np.float64), want.astype(np.float64)) <= (1e-7 if dtype == np.float32 else 1e-6)
+    assert np.abs(got.astype(np.float64) - want.astype(np.float64)).max() <= (2e-5 if dtype == np.float32 else 2e-3)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float16, np.int32, np.int16])
+@pytest.mark.parametrize("nr", [(1, 1, 1, 1), (2, 1, 1, 1), (1, 3, 1, 2), (2, 2, 2, 2)])
+def test_repeat(qmm, gpu_ctx, dtype, nr):
+    """ggml_compute_forward_repeat (src/ggml.c:10323): the tiling np.tile does; GPT-J's old-style bias broadcast (examples/gpt-j/main.cpp:452-456)"""
+    rng = np.random.default_rng(7)
+    shape = (3, 4, 5, 10)                                             # [ne3][ne2][ne1][ne0]
+    a = rng.integers(-1000, 1000, shape).astype(dtype)
+    ttype = {np.dtype(np.float32): qmm.TYPE_F32, np.dtype(np.float16): qmm.TYPE_F16, np.dtype(np.int32): qmm.TYPE_I32, np.dtype(np.int16): qmm.TYPE_I16}[np.dtype(dtype)]
+    want = np.tile(a, nr[::-1])
+    dst = qmm.DTensor(gpu_ctx, ttype, list(want.shape[::-1]))
+    gpu_ctx.op_repeat(up(qmm, gpu_ctx, a), dst)
+    gpu_ctx.synchronize()
+    assert np.array_equal(dst.numpy().reshape(want.shape), want)
+
+
+def test_recorded_sequence_replays_and_refuses_a_wait(qmm, gpu_ctx, oracle):
+    """b200_graph_begin / _end / _launch: a sequence with a decode mul_mat of the path in it is recorded (nothing runs), replayed on new input and equals the
+    same calls issued one by one, bitwise; a call that waits for the device inside the recording makes b200_graph_end report B200_ERR_UNSUPPORTED and
+    leaves the context usable."""
+    rng = np.random.default_rng(5)
+    k, m = 1024, 768
+    w = rng.uniform(-1, 1, (m, k)).astype(np.float32)
+    qt = qmm.QTensor(gpu_ctx, Q4_0, k, m)
+    qt.set(oracle.quantize_weights(Q4_0, w))
+    x = qmm.DTensor(gpu_ctx, qmm.TYPE_F32, [k])
+    h = qmm.DTensor(gpu_ctx, qmm.TYPE_F32, [k])
+    y = qmm.DTensor(gpu_ctx, qmm.TYPE_F32, [m])
+
+    def sequence():
+        gpu_ctx.op_norm(x, h, eps=1e-5)
+        gpu_ctx.op_scale(h, h, 0.5)
+        gpu_ctx.mul_mat_device(qt, h.buf.ptr, 1, y.buf.ptr, 1, 1)
+        gpu_ctx.op_unary("gelu", y, y)
+
+    x0 = rng.uniform(-2, 2, k).astype(np.float32)
+    x.buf.upload(x0)
+    sequence()                                                         # sizes the scratch areas
+    gpu_ctx.synchronize()
+    y.buf.upload(np.zeros(m, np.float32))
+    gpu_ctx.graph_begin()
+    sequence()
+    g = gpu_ctx.graph_end()
+    try:
+        assert gpu_ctx.lib.b200_graph_node_count(g) >= 4
+        gpu_ctx.synchronize()
+        assert not y.numpy().any()                                     # recording executed nothing
+        for rep in range(3):
+            xi = rng.uniform(-2, 2, k).astype(np.float32)
+            x.buf.upload(xi)
+            gpu_ctx.graph_launch(g)
+            gpu_ctx.synchronize()
+            got = y.numpy().copy()
+            sequence()
+            gpu_ctx.synchronize()
+            assert np.array_equal(got, y.numpy())
+    finally:
+        gpu_ctx.graph_destroy(g)
+    gpu_ctx.graph_begin()
+    gpu_ctx.op_scale(x, h, 2.0)
+    with pytest.raises(qmm.B200Error):
+        gpu_ctx.synchronize()                                          # waiting for a stream that is being recorded
+    with pytest.raises(qmm.B200Error) as ei:
+        gpu_ctx.graph_end()
+    assert ei.value.code == qmm.ERR_UNSUPPORTED
+    gpu_ctx.op_scale(x, h, 2.0)                                        # the context works again
+    gpu_ctx.synchronize()
+    assert np.array_equal(h.numpy().reshape(-1), x.numpy().reshape(-1) * 2.0)
