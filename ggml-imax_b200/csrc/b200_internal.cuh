@@ -44,6 +44,7 @@ struct b200_ctx {
     int64_t      trace_capacity;   // in launches
     int64_t      trace_next;       // next launch slot
     int64_t      launches;
+    int64_t      launches_mark;    // value at b200_graph_begin: recording launches nothing
     char         err[512];
 };
 

@@ -290,6 +290,7 @@ int b200_graph_begin(b200_ctx *ctx) {
     B200_CUDA_TRY(ctx, b200_use_device(ctx->device));
     // relaxed: the recording thread may still allocate (a scratch area that has to grow invalidates nothing)
     B200_CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    ctx->launches_mark = ctx->launches;
     return B200_OK;
 }
 
@@ -298,6 +299,7 @@ int b200_graph_end(b200_ctx *ctx, b200_graph **out) {
     if (out) *out = NULL;
     cudaGraph_t graph = NULL;
     const cudaError_t rc = cudaStreamEndCapture(ctx->stream, &graph);
+    ctx->launches = ctx->launches_mark;
     if (rc != cudaSuccess || graph == NULL) {
         b200_set_error(ctx, "the recorded sequence cannot be a CUDA graph: %s", cudaGetErrorString(rc));
         (void)cudaGetLastError();

@@ -496,6 +496,7 @@ struct b200_cached_plan {
     size_t     xin_bytes[B200_MAX_XIN], xin_off[B200_MAX_XIN];
 };
 
+#define B200_MAX_DEFERRED 64
 struct b200_backend_context {
     int       device;
     b200_ctx *ctx;
@@ -507,6 +508,14 @@ struct b200_backend_context {
     int       opt_graphs;  /* 0: graph plans never record a CUDA graph (ggml_backend_b200_set_option "graphs") */
     int64_t   plan_launches;
     int64_t   fused_nodes; /* graph nodes that did not need a launch of their own */
+    /* consumers of every tensor of the graph being computed (b200_uses_*), built on demand for the fusions that skip whole nodes */
+    const struct ggml_tensor **use_keys;
+    int32_t  *use_cnt;
+    size_t    use_size;
+    int       use_valid;
+    /* REPEATs of a row whose only reader comes later in the graph: computed right before that reader unless it folds them in */
+    struct ggml_tensor *deferred[B200_MAX_DEFERRED];
+    int       n_deferred;
     int       failed;      /* an asynchronous error surfaced in synchronize (which cannot return one): the next graph_compute reports it */
 };
 
@@ -561,6 +570,8 @@ GGML_CALL static void b200_backend_free(ggml_backend_t backend) {
     b200_synchronize(bc->ctx);
     for (int i = 0; i < B200_PLAN_CACHE; i++) b200_cached_plan_release(bc, &bc->plans[i]);
     b200_ctx_destroy(bc->ctx);
+    free(bc->use_keys);
+    free(bc->use_cnt);
     free(bc);
     free(backend);
 }
@@ -822,9 +833,243 @@ static bool b200_row_vector(const struct ggml_tensor *v, int64_t ne0) {
     return v && v->type == GGML_TYPE_F32 && v->ne[0] == ne0 && ggml_nrows(v) == 1 && v->nb[0] == sizeof(float) && b200_in_device_buffer(v);
 }
 static bool b200_inplace_child(const struct ggml_tensor *child, const struct ggml_tensor *parent) {
-    return child->src[0] == parent && child->data == parent->data && child->view_src == NULL && ggml_are_same_shape(child, parent) &&
-           !(parent->flags & GGML_TENSOR_FLAG_OUTPUT);
+    if (child->src[0] != parent || child->data != parent->data || !ggml_are_same_shape(child, parent) || (parent->flags & GGML_TENSOR_FLAG_OUTPUT)) return false;
+    for (int i = 0; i < GGML_MAX_DIMS; i++)
+        if (child->nb[i] != parent->nb[i]) return false;
+    if (child->view_src == NULL) return true;               /* the allocator's reuse */
+    /* the explicit form (ggml_scale_inplace, ggml_diag_mask_inf_inplace, ggml_soft_max_inplace: examples/gpt-j/main.cpp:500-509): the child is
+     * ggml_view_tensor(parent) and overwrites it, so whatever reads that memory later sees the child's values with or without the fusion */
+    return child->view_src == (parent->view_src ? parent->view_src : parent) && child->view_offs == parent->view_offs;
 }
+/*
+ * Fusions that SKIP nodes whose result nobody else reads (the old-style graphs of examples/gpt-j/main.cpp, where every gain / bias row is
+ * first broadcast by GGML_OP_REPEAT and nothing is computed in place of its first operand):
+ *   NORM -> REPEAT(gain) -> MUL -> REPEAT(bias) -> ADD                                  one kernel (main.cpp:446-456, :559-567)
+ *   MUL_MAT(decode) -> REPEAT(bias) -> ADD [-> GELU] [-> ADD(residual)]                 the GEMV's epilogue (main.cpp:530-553)
+ * The proof that the skipped results are dead is a count of their readers over the WHOLE graph, so these are only tried when
+ *   - the cgraph is a complete one (ggml_backend_sched hands over ggml_graph_view()s, whose readers may sit in another split: never fused),
+ *   - the group's last node was placed by the graph allocator in the memory of one of the group's own intermediates (a graph whose
+ *     tensors all own their memory may have any of them read back afterwards: never fused),
+ *   - no intermediate carries GGML_TENSOR_FLAG_OUTPUT and every reader of every intermediate (views included) is inside the group,
+ *   - the destination does not overlap an input the kernel still reads (the allocator may have recycled the activation's memory).
+ */
+static size_t b200_use_slot(const struct b200_backend_context *bc, const struct ggml_tensor *t) {
+    size_t h = ((uintptr_t)t >> 4) * 0x9E3779B97F4A7C15ull >> 20;
+    h &= bc->use_size - 1;
+    while (bc->use_keys[h] && bc->use_keys[h] != t) h = (h + 1) & (bc->use_size - 1);
+    return h;
+}
+static void b200_use_add(struct b200_backend_context *bc, const struct ggml_tensor *t) {
+    const size_t h = b200_use_slot(bc, t);
+    bc->use_keys[h] = t;
+    bc->use_cnt[h]++;
+}
+/* readers of one node: its distinct sources, and the tensor it is a view of */
+static int b200_refs_from(const struct ggml_tensor *node, const struct ggml_tensor *t) {
+    int n = 0;
+    for (int k = 0; k < GGML_MAX_SRC; k++) {
+        if (node->src[k] != t) continue;
+        bool seen = false;
+        for (int j = 0; j < k; j++) seen |= node->src[j] == t;
+        n += !seen;
+    }
+    return n + (node->view_src == t);
+}
+static bool b200_uses_build(struct b200_backend_context *bc, const struct ggml_cgraph *g) {
+    if (bc->use_valid) return true;
+    if (g->visited_hash_table.size == 0 || g->visited_hash_table.keys == NULL) return false;      /* a ggml_graph_view: readers may be elsewhere */
+    size_t want = 1024;
+    while (want < (size_t)g->n_nodes * 8) want <<= 1;
+    if (want > bc->use_size) {
+        free(bc->use_keys);
+        free(bc->use_cnt);
+        bc->use_keys = (const struct ggml_tensor **)malloc(want * sizeof(*bc->use_keys));
+        bc->use_cnt = (int32_t *)malloc(want * sizeof(*bc->use_cnt));
+        bc->use_size = bc->use_keys && bc->use_cnt ? want : 0;
+        if (!bc->use_size) return false;
+    }
+    memset(bc->use_keys, 0, bc->use_size * sizeof(*bc->use_keys));
+    memset(bc->use_cnt, 0, bc->use_size * sizeof(*bc->use_cnt));
+    for (int i = 0; i < g->n_nodes; i++) {
+        const struct ggml_tensor *node = g->nodes[i];
+        for (int k = 0; k < GGML_MAX_SRC; k++) {
+            if (!node->src[k]) continue;
+            bool seen = false;
+            for (int j = 0; j < k; j++) seen |= node->src[j] == node->src[k];
+            if (!seen) b200_use_add(bc, node->src[k]);
+        }
+        if (node->view_src) b200_use_add(bc, node->view_src);
+    }
+    bc->use_valid = 1;
+    return true;
+}
+/* every reader of t is one of nodes[i .. i + n) */
+static bool b200_read_only_by_group(struct b200_backend_context *bc, const struct ggml_cgraph *g, const struct ggml_tensor *t, int i, int n) {
+    if (t->flags & GGML_TENSOR_FLAG_OUTPUT) return false;
+    int inside = 0;
+    for (int j = i; j < i + n; j++) inside += b200_refs_from(g->nodes[j], t);
+    return bc->use_cnt[b200_use_slot(bc, t)] == inside;
+}
+static bool b200_ranges_overlap(const struct ggml_tensor *a, const struct ggml_tensor *b) {
+    const char *a0 = (const char *)a->data, *b0 = (const char *)b->data;
+    return a0 < b0 + ggml_nbytes(b) && b0 < a0 + ggml_nbytes(a);
+}
+/* REPEAT of a device-resident F32 row of ne0 elements to the shape of `like` */
+static bool b200_repeat_of_row(const struct ggml_tensor *rep, const struct ggml_tensor *like) {
+    return rep->op == GGML_OP_REPEAT && rep->type == GGML_TYPE_F32 && ggml_are_same_shape(rep, like) && b200_row_vector(rep->src[0], like->ne[0]) &&
+           rep->src[0]->data != NULL;
+}
+static bool b200_binary_of(const struct ggml_tensor *node, enum ggml_op op, const struct ggml_tensor *x, const struct ggml_tensor *y) {
+    return node->op == op && node->type == GGML_TYPE_F32 && ((node->src[0] == x && node->src[1] == y) || (node->src[0] == y && node->src[1] == x));
+}
+
+/* A REPEAT of a row does not reference the tensor whose shape it takes (ggml_repeat, src/ggml.c:4390), so ggml_build_forward_expand may
+ * emit it long before its reader (GPT-J: the bias REPEATs of a block's MLP come out before the previous block's nodes).  Such a node is
+ * DEFERRED when it is met: its memory is reserved from there to its reader, so writing it at any point in between is the same program.
+ * The reader either folds the row into its own kernel (and the REPEAT is never computed) or has it computed right before it runs. */
+static int b200_deferred_index(const struct b200_backend_context *bc, const struct ggml_tensor *t) {
+    for (int k = 0; k < bc->n_deferred; k++)
+        if (bc->deferred[k] == t) return k;
+    return -1;
+}
+static void b200_deferred_drop(struct b200_backend_context *bc, const struct ggml_tensor *t) {
+    const int k = b200_deferred_index(bc, t);
+    if (k >= 0) bc->deferred[k] = bc->deferred[--bc->n_deferred];
+}
+static bool b200_try_defer_repeat(struct b200_backend_context *bc, const struct ggml_cgraph *cgraph, struct ggml_tensor *rep) {
+    if (!bc->opt_fuse || rep->op != GGML_OP_REPEAT || rep->type != GGML_TYPE_F32 || bc->n_deferred >= B200_MAX_DEFERRED) return false;
+    if (!b200_row_vector(rep->src[0], rep->ne[0]) || !ggml_is_contiguous(rep) || rep->view_src != NULL || (rep->flags & GGML_TENSOR_FLAG_OUTPUT)) return false;
+    if (!b200_uses_build(bc, cgraph)) return false;
+    if (bc->use_cnt[b200_use_slot(bc, rep)] != 1) return false;          /* exactly one reader, inside this graph */
+    bc->deferred[bc->n_deferred++] = rep;
+    bc->fused_nodes++;                                                     /* (taken back if it has to be computed after all) */
+    return true;
+}
+static enum ggml_status b200_compute_glue(struct b200_backend_context *bc, struct ggml_tensor *node);
+/* before `node` runs on its own: the deferred REPEATs it reads */
+static enum ggml_status b200_materialize_deferred_for(struct b200_backend_context *bc, const struct ggml_tensor *node) {
+    if (bc->n_deferred == 0) return GGML_STATUS_SUCCESS;
+    for (int k = 0; k <= GGML_MAX_SRC; k++) {
+        struct ggml_tensor *s = k < GGML_MAX_SRC ? node->src[k] : node->view_src;
+        if (!s || b200_deferred_index(bc, s) < 0) continue;
+        b200_deferred_drop(bc, s);
+        bc->fused_nodes--;
+        const enum ggml_status st = b200_compute_glue(bc, s);
+        if (st != GGML_STATUS_SUCCESS) return st;
+    }
+    return GGML_STATUS_SUCCESS;
+}
+/* a REPEAT of a row to the shape of `like` that this group may fold in: deferred earlier, or one of nodes[i .. i + n) */
+static bool b200_foldable_repeat(const struct b200_backend_context *bc, const struct ggml_cgraph *cgraph, const struct ggml_tensor *rep, const struct ggml_tensor *like,
+                                 int i, int n) {
+    if (!rep || !b200_repeat_of_row(rep, like)) return false;
+    if (b200_deferred_index(bc, rep) >= 0) return true;
+    for (int j = i; j < i + n; j++)
+        if (cgraph->nodes[j] == rep) return true;
+    return false;
+}
+
+/* NORM -> MUL(REPEAT(gain)) -> ADD(REPEAT(bias)); REPEATs of this group may sit between its nodes */
+static int b200_try_fuse_norm_repeat(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int i, int last, enum ggml_status *st) {
+    struct ggml_tensor *n0 = cgraph->nodes[i], *m2 = NULL, *a4 = NULL;
+    if (!bc->opt_fuse || (n0->op != GGML_OP_NORM && n0->op != GGML_OP_RMS_NORM) || !b200_glue_supported(n0) || !ggml_is_contiguous(n0)) return 0;
+    int j = i + 1;
+    while (j < last && cgraph->nodes[j]->op == GGML_OP_REPEAT) j++;
+    if (j >= last || cgraph->nodes[j]->op != GGML_OP_MUL) return 0;
+    m2 = cgraph->nodes[j++];
+    while (j < last && cgraph->nodes[j]->op == GGML_OP_REPEAT) j++;
+    if (j >= last || cgraph->nodes[j]->op != GGML_OP_ADD) return 0;
+    a4 = cgraph->nodes[j];
+    const int n = j - i + 1;
+    if (n > 5) return 0;
+    struct ggml_tensor *r1 = m2->src[0] == n0 ? m2->src[1] : m2->src[0], *r3 = a4->src[0] == m2 ? a4->src[1] : a4->src[0];
+    if (!b200_foldable_repeat(bc, cgraph, r1, n0, i, n) || !b200_foldable_repeat(bc, cgraph, r3, n0, i, n) || r1 == r3) return 0;
+    if (!b200_binary_of(m2, GGML_OP_MUL, r1, n0) || !b200_binary_of(a4, GGML_OP_ADD, m2, r3)) return 0;
+    for (int k = i + 1; k < i + n; k++)                          /* no foreign REPEAT inside the window */
+        if (cgraph->nodes[k]->op == GGML_OP_REPEAT && cgraph->nodes[k] != r1 && cgraph->nodes[k] != r3) return 0;
+    if (!ggml_is_contiguous(a4) || !ggml_are_same_shape(a4, n0) || a4->view_src != NULL) return 0;
+    if (a4->data != n0->data && a4->data != r1->data && a4->data != m2->data && a4->data != r3->data) return 0;      /* not an allocator-managed graph */
+    if (!b200_uses_build(bc, cgraph)) return 0;
+    if (!b200_read_only_by_group(bc, cgraph, n0, i, n) || !b200_read_only_by_group(bc, cgraph, r1, i, n) || !b200_read_only_by_group(bc, cgraph, m2, i, n) ||
+        !b200_read_only_by_group(bc, cgraph, r3, i, n))
+        return 0;
+    const struct ggml_tensor *x = n0->src[0];
+    if (b200_ranges_overlap(a4, r1->src[0]) || b200_ranges_overlap(a4, r3->src[0])) return 0;
+    if (b200_ranges_overlap(a4, x) && !(a4->data == x->data && ggml_is_contiguous(x))) return 0;       /* row by row in place is fine, a shifted overlap is not */
+    b200_tensor a, g, b, d;
+    float eps;
+    memcpy(&eps, n0->op_params, sizeof(eps));
+    if (!b200_fill_tensor(x, &a) || !b200_fill_tensor(r1->src[0], &g) || !b200_fill_tensor(r3->src[0], &b) || !b200_fill_tensor(a4, &d)) return 0;
+    b200_deferred_drop(bc, r1);
+    b200_deferred_drop(bc, r3);
+    *st = b200_glue_status(bc, a4, b200_op_norm(bc->ctx, &a, &g, &b, &d, eps, n0->op == GGML_OP_RMS_NORM));
+    return n;
+}
+
+/* MUL_MAT(decode) -> ADD(REPEAT(bias)) [-> GELU] [-> ADD(residual)]; the REPEAT deferred earlier or right after the mul_mat */
+static int b200_try_fuse_mul_mat_repeat(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int i, int last, enum ggml_status *st) {
+    struct ggml_tensor *mm = cgraph->nodes[i];
+    if (!bc->opt_fuse || i + 1 >= last || mm->src[1]->ne[1] > 8 || mm->ne[2] != 1 || mm->ne[3] != 1 || b200_tensor_is_split(mm->src[0])) return 0;
+    int n = 1;
+    if (cgraph->nodes[i + 1]->op == GGML_OP_REPEAT) n = 2;
+    if (i + n >= last) return 0;
+    struct ggml_tensor *add = cgraph->nodes[i + n];
+    if (add->op != GGML_OP_ADD || !ggml_is_contiguous(add)) return 0;
+    struct ggml_tensor *rep = add->src[0] == mm ? add->src[1] : add->src[0];
+    n++;
+    if (!b200_foldable_repeat(bc, cgraph, rep, mm, i, n) || !b200_binary_of(add, GGML_OP_ADD, rep, mm)) return 0;
+    if (n == 3 && cgraph->nodes[i + 1] != rep) return 0;        /* a foreign REPEAT in between */
+    b200_epilogue epi;
+    memset(&epi, 0, sizeof(epi));
+    epi.bias_dev = (const float *)rep->src[0]->data;
+    const struct ggml_tensor *inter[5];
+    int n_inter = 0;
+    inter[n_inter++] = mm;
+    inter[n_inter++] = rep;
+    struct ggml_tensor *cur = add;
+    const struct ggml_tensor *residual = NULL;
+    if (i + n < last) {
+        struct ggml_tensor *nx = cgraph->nodes[i + n];
+        if (nx->op == GGML_OP_UNARY && ggml_get_unary_op(nx) == GGML_UNARY_OP_GELU && nx->src[0] == cur && ggml_is_contiguous(nx) && nx->type == GGML_TYPE_F32) {
+            epi.act = B200_EPI_GELU;
+            inter[n_inter++] = cur;
+            cur = nx;
+            n++;
+        }
+    }
+    if (i + n < last) {
+        struct ggml_tensor *nx = cgraph->nodes[i + n];
+        if (nx->op == GGML_OP_ADD && nx->type == GGML_TYPE_F32 && (nx->src[0] == cur || nx->src[1] == cur) && nx->src[0] != nx->src[1] && ggml_is_contiguous(nx)) {
+            const struct ggml_tensor *r = nx->src[0] == cur ? nx->src[1] : nx->src[0];
+            if (r->type == GGML_TYPE_F32 && ggml_are_same_shape(r, mm) && ggml_is_contiguous(r) && b200_in_device_buffer(r) && r->data != NULL &&
+                b200_deferred_index(bc, r) < 0) {
+                residual = r;
+                epi.residual_dev = (const float *)r->data;
+                inter[n_inter++] = cur;
+                cur = nx;
+                n++;
+            }
+        }
+    }
+    if (cur->view_src != NULL || !ggml_are_same_shape(cur, mm)) return 0;
+    bool managed = false;
+    for (int k = 0; k < n_inter; k++) managed |= cur->data == inter[k]->data;
+    if (!managed) return 0;                                    /* not an allocator-managed graph */
+    if (!b200_uses_build(bc, cgraph)) return 0;
+    for (int k = 0; k < n_inter; k++)
+        if (!b200_read_only_by_group(bc, cgraph, inter[k], i, n)) return 0;
+    if (b200_ranges_overlap(cur, mm->src[1]) || b200_ranges_overlap(cur, rep->src[0])) return 0;
+    if (residual && b200_ranges_overlap(cur, residual) && cur->data != residual->data) return 0;
+    b200_mul_mat_args args;
+    if (!b200_fill_mul_mat_args(mm, &args)) return 0;
+    args.dst_dev = (float *)cur->data;
+    const int rc = b200_mul_mat_fused(bc->ctx, &args, &epi);
+    if (rc == B200_ERR_UNSUPPORTED) return 0;          /* not a single-launch shape: the operators run one by one */
+    b200_deferred_drop(bc, rep);
+    *st = b200_glue_status(bc, mm, rc);
+    return n;
+}
+
 /*   MUL_MAT(quantized, decode shape) -> ADD(bias row) [-> GELU] [-> ADD(residual)]     the GEMV's epilogue (main-backend.cpp:614-625, :659-699)
  * under the same rule: every follower computes in place of its predecessor.  Returns the nodes consumed (0 = no fusion). */
 static int b200_try_fuse_mul_mat(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int i, int last, enum ggml_status *st) {
@@ -1359,15 +1604,23 @@ GGML_CALL static enum ggml_status b200_backend_graph_compute(ggml_backend_t back
         bc->failed = 0;
         return GGML_STATUS_FAILED;
     }
+    bc->use_valid = 0;
+    bc->n_deferred = 0;
     int i = 0;
     while (i < cgraph->n_nodes) {
         struct ggml_tensor *node = cgraph->nodes[i];
-        if (ggml_is_empty(node) || b200_op_is_noop(node->op)) { i++; continue; }
+        if (ggml_is_empty(node) || b200_op_is_noop(node->op)) {
+            if (b200_materialize_deferred_for(bc, node) != GGML_STATUS_SUCCESS) return GGML_STATUS_FAILED;
+            i++;
+            continue;
+        }
         int last = i;
         uint64_t key = 0;
         bool split = false;
         const int n = b200_decode_run(cgraph, i, &last, &key, &split);
         if (n >= 2) {
+            for (int j = i; j < last; j++)
+                if (b200_materialize_deferred_for(bc, cgraph->nodes[j]) != GGML_STATUS_SUCCESS) return GGML_STATUS_FAILED;
             const int as_plan = b200_try_run_as_plan(bc, cgraph, i, last, n, key, split);
             if (as_plan < 0) return GGML_STATUS_FAILED;
             if (as_plan == 0) {
@@ -1383,6 +1636,12 @@ GGML_CALL static enum ggml_status b200_backend_graph_compute(ggml_backend_t back
         const enum ggml_status st = b200_graph_compute_nodes(bc, cgraph, i, cgraph->n_nodes, &next);
         if (st != GGML_STATUS_SUCCESS) return st;
         i = next;
+    }
+    while (bc->n_deferred > 0) {                    /* (every deferred node has a reader in this graph, so nothing is left; kept as a net) */
+        struct ggml_tensor *rep = bc->deferred[--bc->n_deferred];
+        bc->fused_nodes--;
+        const enum ggml_status st = b200_compute_glue(bc, rep);
+        if (st != GGML_STATUS_SUCCESS) return st;
     }
     return GGML_STATUS_SUCCESS;
 }
@@ -1400,6 +1659,7 @@ struct b200_graph_plan {
     b200_graph *graph;
     uint64_t fingerprint;
     int state;                     /* 0: never computed, 1: computed node by node once, 2: recorded, -1: cannot be recorded */
+    int64_t plan_launches, fused_nodes;   /* what one replay adds to the backend's counters */
 };
 
 static uint64_t b200_fnv(uint64_t h, const void *p, size_t n) {
@@ -1464,7 +1724,11 @@ GGML_CALL static enum ggml_status b200_backend_graph_plan_compute(ggml_backend_t
             bc->failed = 0;
             return GGML_STATUS_FAILED;
         }
-        if (b200_graph_launch(bc->ctx, gp->graph) == B200_OK) return GGML_STATUS_SUCCESS;
+        if (b200_graph_launch(bc->ctx, gp->graph) == B200_OK) {
+            bc->plan_launches += gp->plan_launches;
+            bc->fused_nodes += gp->fused_nodes;
+            return GGML_STATUS_SUCCESS;
+        }
         fprintf(stderr, "ggml-b200: graph launch failed: %s\n", b200_last_error(bc->ctx));
         return GGML_STATUS_FAILED;
     }
@@ -1479,7 +1743,12 @@ GGML_CALL static enum ggml_status b200_backend_graph_plan_compute(ggml_backend_t
         gp->state = -1;
         return b200_backend_graph_compute(backend, &gp->cgraph);
     }
+    const int64_t pl0 = bc->plan_launches, fn0 = bc->fused_nodes;
     const enum ggml_status st = b200_backend_graph_compute(backend, &gp->cgraph);
+    gp->plan_launches = bc->plan_launches - pl0;
+    gp->fused_nodes = bc->fused_nodes - fn0;
+    bc->plan_launches = pl0;                                 /* recording launched nothing */
+    bc->fused_nodes = fn0;
     b200_graph *g = NULL;
     const int rc = b200_graph_end(bc->ctx, st == GGML_STATUS_SUCCESS ? &g : NULL);
     if (st != GGML_STATUS_SUCCESS || rc != B200_OK || !g) {  /* nothing ran: compute it the plain way and stop trying */
@@ -1490,6 +1759,8 @@ GGML_CALL static enum ggml_status b200_backend_graph_plan_compute(ggml_backend_t
     gp->graph = g;
     gp->state = 2;
     if (b200_graph_launch(bc->ctx, gp->graph) != B200_OK) return GGML_STATUS_FAILED;
+    bc->plan_launches += gp->plan_launches;
+    bc->fused_nodes += gp->fused_nodes;
     return GGML_STATUS_SUCCESS;
 }
 
@@ -1509,6 +1780,10 @@ static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc
             *one_unit_next = i;
             if (done_one) return GGML_STATUS_SUCCESS;
         }
+        {
+            const enum ggml_status st = b200_materialize_deferred_for(bc, node);
+            if (st != GGML_STATUS_SUCCESS) return st;
+        }
         if (ggml_is_empty(node) || b200_op_is_noop(node->op)) continue;
         done_one = true;
         if (node->op == GGML_OP_MUL_MAT && b200_tensor_is_split(node->src[0])) {
@@ -1519,7 +1794,8 @@ static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc
         if (node->op == GGML_OP_MUL_MAT && b200_type_is_repacked(node->src[0]->type)) {
             {
                 enum ggml_status st = GGML_STATUS_SUCCESS;
-                const int fused = b200_try_fuse_mul_mat(bc, cgraph, i, last, &st);
+                int fused = b200_try_fuse_mul_mat(bc, cgraph, i, last, &st);
+                if (fused == 0) fused = b200_try_fuse_mul_mat_repeat(bc, cgraph, i, last, &st);
                 if (fused > 0) {
                     if (st != GGML_STATUS_SUCCESS) return st;
                     bc->fused_nodes += fused - 1;
@@ -1541,6 +1817,7 @@ static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc
                 for (int j = 0; j < n; j++)
                     if (next->data == run[j]->data) dep = true;
                 if (dep) break;
+                if (b200_materialize_deferred_for(bc, next) != GGML_STATUS_SUCCESS) return GGML_STATUS_FAILED;
                 run[n++] = next;
                 i++;
             }
@@ -1555,7 +1832,9 @@ static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc
         }
         {
             enum ggml_status st = GGML_STATUS_SUCCESS;
-            const int fused = b200_try_fuse(bc, cgraph, i, last, &st);
+            if (node->op == GGML_OP_REPEAT && b200_try_defer_repeat(bc, cgraph, node)) continue;
+            int fused = b200_try_fuse(bc, cgraph, i, last, &st);
+            if (fused == 0) fused = b200_try_fuse_norm_repeat(bc, cgraph, i, last, &st);
             if (fused > 0) {
                 if (st != GGML_STATUS_SUCCESS) return st;
                 bc->fused_nodes += fused - 1;

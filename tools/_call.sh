@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_ops.py tests/test_gpu_backend_ops.py tests/test_gpu_gpt2_sched.py tests/test_gpu_gpt2_backend.py -q > gpurun_out/r02_rope_graph_tests.log 2>&1; tail -15 gpurun_out/r02_rope_graph_tests.log
-cd oracle/_ref && ./test-backend-ops test -b B2000 > ../../gpurun_out/r02_test_backend_ops_all.log 2>&1; tail -3 ../../gpurun_out/r02_test_backend_ops_all.log
+timeout 900 python -m pytest tests/test_gpu_gptj_graph.py tests/test_gpu_gpt2_sched.py tests/test_gpu_gpt2_backend.py tests/test_gpu_dropin_graph.py -x -q > gpurun_out/r02_gptj_tests.log 2>&1; tail -12 gpurun_out/r02_gptj_tests.log
+timeout 600 oracle/_ref/gptj-harness q4_0 28 4096 16 64 50400 2048 8 3 $(nproc) > gpurun_out/r02_gptj_6b.json 2> gpurun_out/r02_gptj_6b.err; cut -c1-2500 gpurun_out/r02_gptj_6b.json; tail -3 gpurun_out/r02_gptj_6b.err
