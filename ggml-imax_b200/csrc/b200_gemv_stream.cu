@@ -659,7 +659,7 @@ bool b200_try_launch_gemv_stream_batch(b200_ctx *ctx, const b200_gemv_params *ps
     if (count < 2 || count > kMaxBatch) return false;
     for (int j = 0; j < count; j++) {
         const b200_gemv_params &p = ps[j];
-        if (p.n != 1 || p.dst_n != 1 || p.dots || p.bias || p.residual || p.act) return false;
+        if (p.n != 1 || p.dst_n != 1 || p.dots || p.bias || p.residual || p.residual2 || p.act) return false;
         if ((p.gather != NULL) != (ps[0].gather != NULL)) return false;
         if (p.gather) {
             // one gather description must fit all: same group, same state, same producer to wait for, and the matrices' LL
@@ -692,7 +692,7 @@ bool b200_try_launch_gemv_stream(b200_ctx *ctx, const b200_gemv_params &p, int *
     if (p.k % 256 != 0 || p.k > 32768 || p.n < 1 || p.n > 8) return false;
     if (((uintptr_t)p.qs & 15) != 0 || ((uintptr_t)p.d & 15) != 0) return false;
     if (p.dots == NULL && p.dst_n != p.n) return false;  // column-chunked dst keeps the generic addressing
-    if (p.gather && (p.n != 1 || p.dots || p.bias || p.residual || p.act)) return false;
+    if (p.gather && (p.n != 1 || p.dots || p.bias || p.residual || p.residual2 || p.act)) return false;
     StreamGeom g;
     if (!stream_geometry(p, &g)) return false;
     const bool dots = p.dots != NULL;

@@ -123,6 +123,7 @@ struct b200_gemv_params {
     // optional epilogue of a plain 2-D launch (b200_mul_mat_fused): dst = act(W x + bias) + residual
     const float   *bias;       // [m] or null
     const float   *residual;   // dense like dst ([n][m]) or null; may be dst itself
+    const float   *residual2;  // a second one, added after the first
     int            act;        // B200_EPI_NONE / B200_EPI_GELU
     // bound of the waits on peers' tagged stores (fused all-gather path); filled in by the launcher from the context
     uint32_t      *abort_dev, *abort_host;
@@ -134,6 +135,7 @@ __device__ __forceinline__ float b200_gemv_epilogue(const b200_gemv_params &p, f
     if (p.bias) v += p.bias[row];
     if (p.act == B200_EPI_GELU) v = 0.5f * v * (1.0f + tanhf(0.79788456080286535587989211986876f * v * (1.0f + 0.044715f * v * v)));   // src/ggml.c:1966
     if (p.residual) v += p.residual[idx];
+    if (p.residual2) v += p.residual2[idx];
     return v;
 }
 int b200_launch_gemv(b200_ctx *ctx, const b200_gemv_params &p);

@@ -45,6 +45,7 @@ static int run_gemv_chunks(b200_ctx *ctx, const b200_mul_mat_args *a, const uint
         if (epi) {
             p.bias = epi->bias_dev;
             p.residual = epi->residual_dev;
+            p.residual2 = epi->residual2_dev;
             p.act = epi->act;
         }
         int rc = b200_launch_gemv(ctx, p);
@@ -147,7 +148,7 @@ int b200_mul_mat(b200_ctx *ctx, const b200_mul_mat_args *a) {
 
 int b200_mul_mat_fused(b200_ctx *ctx, const b200_mul_mat_args *a, const b200_epilogue *epi) {
     B200_REQUIRE(ctx, ctx && a, B200_ERR_INVALID);
-    if (!epi || (!epi->bias_dev && !epi->residual_dev && epi->act == B200_EPI_NONE)) return b200_mul_mat(ctx, a);
+    if (!epi || (!epi->bias_dev && !epi->residual_dev && !epi->residual2_dev && epi->act == B200_EPI_NONE)) return b200_mul_mat(ctx, a);
     B200_REQUIRE(ctx, epi->act == B200_EPI_NONE || epi->act == B200_EPI_GELU, B200_ERR_INVALID);
     B200_REQUIRE(ctx, quant_type_ok(a->type), B200_ERR_UNSUPPORTED);
     B200_REQUIRE(ctx, a->ne00 > 0 && a->ne00 % B200_QK == 0 && a->ne01 > 0 && a->ne11 > 0, B200_ERR_INVALID);

@@ -23,6 +23,29 @@
 
 namespace {
 
+// Every kernel of this file starts with pdl_enter(): it lets the next kernel of the stream begin launching at once (that kernel waits for
+// THIS grid to complete before it touches memory -- a GEMV of the path fills its weight ring first, which depends on nothing) and then waits
+// for the grid in front of it.  launch_k adds the launch attribute that makes the pair of instructions mean something (context option "pdl");
+// without it both are no-ops.  A decode step of a whole model is a chain of ~2-5 us kernels: their launch latencies overlap instead of adding up.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+void launch_k(b200_ctx *ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ctx->opt_pdl ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);      // errors surface in finish() through cudaGetLastError
+}
+
 struct T4 {                      // a 4-D strided tensor as the kernels see it
     char *p;
     int64_t ne0, ne1, ne2, ne3;
@@ -98,6 +121,7 @@ __global__ void __launch_bounds__(256) get_rows_kernel(const char *__restrict__ 
                                                        const char *__restrict__ rows, int64_t nb10, int64_t nb11, int64_t nb12,
                                                        int64_t ne10, int64_t ne11, float *__restrict__ dst, int64_t nb1, int64_t nb2, int64_t nb3,
                                                        int64_t nc, int64_t nr, int *__restrict__ bad) {
+    pdl_enter();
     const int64_t nc4 = nc >> 2;
     const int64_t total = nr * nc4;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -137,6 +161,7 @@ __global__ void __launch_bounds__(256) get_rows_scalar_kernel(const char *__rest
                                                               const char *__restrict__ rows, int64_t nb10, int64_t nb11, int64_t nb12, int64_t ne10,
                                                               int64_t ne11, char *__restrict__ dst, int64_t nb1, int64_t nb2, int64_t nb3, int64_t nc,
                                                               int64_t nr, int *__restrict__ bad) {
+    pdl_enter();
     const int64_t total = nr * nc;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = t / nc, c = t - r * nc;
@@ -160,6 +185,7 @@ template <int OP> __device__ __forceinline__ float bin(float a, float b) { retur
 // rows are dense in all three tensors and src1 covers whole rows (ne10 == ne0): float4 per thread
 template <int OP>
 __global__ void __launch_bounds__(256) binary_rows_kernel(T4 a, T4 b, T4 d) {
+    pdl_enter();
     const int64_t n4 = d.ne0 >> 2;
     const int64_t total = n4 * d.ne1 * d.ne2 * d.ne3;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -177,6 +203,7 @@ __global__ void __launch_bounds__(256) binary_rows_kernel(T4 a, T4 b, T4 d) {
 // anything else: one thread per element, src1 indexed modulo its extent in every dimension (ggml_can_repeat(src1, src0))
 template <int OP>
 __global__ void __launch_bounds__(256) binary_generic_kernel(T4 a, T4 b, T4 d) {
+    pdl_enter();
     const int64_t total = d.ne0 * d.ne1 * d.ne2 * d.ne3;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = t / d.ne0;
@@ -212,6 +239,7 @@ __device__ __forceinline__ float unary_apply(int op, float x) {
 // MODE 0: unary(op), 1: x * s, 2: diag_mask_inf(n_past = op; nc, nr)
 template <int MODE>
 __global__ void __launch_bounds__(256) elementwise_kernel(const float *__restrict__ x, float *__restrict__ y, int64_t n, int op, float s, int64_t nc, int64_t nr) {
+    pdl_enter();
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
         const float v = x[t];
         float o;
@@ -230,6 +258,7 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const float *__restric
 // dst == src is fine.  gain / bias: optional row vectors of ne0 floats (the MUL and ADD that follow NORM in a transformer block).
 template <bool RMS>
 __global__ void __launch_bounds__(256) norm_kernel(T4 a, T4 d, const float *__restrict__ gain, const float *__restrict__ bias, float eps) {
+    pdl_enter();
     __shared__ float red[33];
     int64_t r = blockIdx.x;
     const int64_t i3 = r / (a.ne2 * a.ne1);
@@ -263,6 +292,7 @@ __global__ void __launch_bounds__(256) norm_kernel(T4 a, T4 d, const float *__re
 // bias) is issued before the first reduction, so a decode step pays one memory latency instead of three, and no CTA barrier at all
 template <bool RMS, int VPL>
 __global__ void __launch_bounds__(128) norm_warp_kernel(T4 a, T4 d, const float *__restrict__ gain, const float *__restrict__ bias, float eps, int64_t nrows) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= nrows) return;
@@ -308,6 +338,54 @@ __global__ void __launch_bounds__(128) norm_warp_kernel(T4 a, T4 d, const float 
     }
 }
 
+// rows of 1025 .. 256 * 4 * VPT floats (GPT-J's 4096): one CTA per row, the row in registers, every load issued before the first reduction
+template <bool RMS, int VPT>
+__global__ void __launch_bounds__(256) norm_block_kernel(T4 a, T4 d, const float *__restrict__ gain, const float *__restrict__ bias, float eps) {
+    pdl_enter();
+    __shared__ float red[33];
+    int64_t r = blockIdx.x;
+    const int64_t i3 = r / (a.ne2 * a.ne1);
+    r -= i3 * a.ne2 * a.ne1;
+    const int64_t i2 = r / a.ne1, i1 = r - i2 * a.ne1;
+    const float4 *x = reinterpret_cast<const float4 *>(a.p + i3 * a.nb3 + i2 * a.nb2 + i1 * a.nb1);
+    float4 *y = reinterpret_cast<float4 *>(d.p + i3 * d.nb3 + i2 * d.nb2 + i1 * d.nb1);
+    const int n4 = (int)(a.ne0 >> 2);
+    float4 v[VPT], g[VPT], b[VPT];
+#pragma unroll
+    for (int j = 0; j < VPT; j++) {
+        const int i = threadIdx.x + 256 * j;
+        v[j] = i < n4 ? x[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gain) g[j] = i < n4 ? reinterpret_cast<const float4 *>(gain)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) b[j] = i < n4 ? reinterpret_cast<const float4 *>(bias)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float inv_n = 1.0f / (float)a.ne0;
+    float mean = 0.f;
+    if (!RMS) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; j++) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+        mean = block_reduce<false>(s, red) * inv_n;
+    }
+    float s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPT; j++) {
+        if (threadIdx.x + 256 * j < n4) {
+            v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+            s2 += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+        }
+    }
+    const float scale = 1.0f / sqrtf(block_reduce<false>(s2, red) * inv_n + eps);
+#pragma unroll
+    for (int j = 0; j < VPT; j++) {
+        const int i = threadIdx.x + 256 * j;
+        if (i >= n4) continue;
+        float4 o = make_float4(v[j].x * scale, v[j].y * scale, v[j].z * scale, v[j].w * scale);
+        if (gain) { o.x *= g[j].x; o.y *= g[j].y; o.z *= g[j].z; o.w *= g[j].w; }
+        if (bias) { o.x += b[j].x; o.y += b[j].y; o.z += b[j].z; o.w += b[j].w; }
+        y[i] = o;
+    }
+}
+
 // ---- SOFT_MAX (+ scale, + mask with ALiBi slope, + causal mask) ------------------------------------------------------------------------------
 // one CTA per row: w = x * scale + slope * mask[row % ne1] (and -inf where i > n_past + row % ne1 when the DIAG_MASK_INF in front was
 // folded in), y = exp(w - max) / sum.  Three passes over the row, the last one writes: in-place safe.
@@ -315,6 +393,7 @@ template <typename MASK_T>
 __global__ void __launch_bounds__(256) soft_max_kernel(const float *__restrict__ x, float *__restrict__ y, const MASK_T *__restrict__ mask, int64_t nc,
                                                        int64_t ne1, int64_t ne2, float scale, float max_bias, float m0, float m1, uint32_t n_head_log2,
                                                        int n_past) {
+    pdl_enter();
     __shared__ float red[33];
     const int64_t row = blockIdx.x;
     const int64_t i1 = row % ne1;
@@ -359,6 +438,7 @@ template <> __device__ __forceinline__ uint32_t convert<uint32_t, uint32_t>(uint
 
 template <typename S, typename D>
 __global__ void __launch_bounds__(256) copy_kernel(T4 a, T4 d, int64_t total) {
+    pdl_enter();
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = t / d.ne0;
         const int64_t j0 = t - r * d.ne0;
@@ -376,6 +456,7 @@ __global__ void __launch_bounds__(256) copy_kernel(T4 a, T4 d, int64_t total) {
 }
 // same shape, dense rows on both sides, 16-byte aligned: 128 bits per thread
 __global__ void __launch_bounds__(256) copy_rows16_kernel(T4 a, T4 d, int64_t row_bytes) {
+    pdl_enter();
     const int64_t n16 = row_bytes >> 4;
     const int64_t total = n16 * d.ne1 * d.ne2 * d.ne3;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -412,6 +493,7 @@ __device__ __forceinline__ void rope_yarn_dev(float theta_extrap, const RopeK &r
 }
 template <typename T>
 __global__ void __launch_bounds__(256) rope_kernel(T4 a, T4 d, const int32_t *__restrict__ pos, RopeK r) {
+    pdl_enter();
     const int64_t half = a.ne0 >> 1;
     const int64_t total = half * a.ne1 * a.ne2 * a.ne3;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -448,6 +530,7 @@ __global__ void __launch_bounds__(256) rope_kernel(T4 a, T4 d, const int32_t *__
 // ---- REPEAT (src/ggml.c:10323): dst[i] = src0[i mod src0 shape], 2- and 4-byte elements ------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) repeat_kernel(T4 a, T4 d, int64_t total) {
+    pdl_enter();
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = t / d.ne0;
         const int64_t j0 = t - r * d.ne0;
@@ -465,6 +548,7 @@ __global__ void __launch_bounds__(256) repeat_kernel(T4 a, T4 d, int64_t total) 
 // through shared memory, RM x RN accumulators per thread, fp32 FMA.
 template <typename A, int TM, int TN, int RM, int RN>
 __global__ void __launch_bounds__((TM / RM) * (TN / RN)) mul_mat_dense_kernel(T4 a, T4 b, T4 d, int64_t r2, int64_t r3) {
+    pdl_enter();
     constexpr int KT = 16;
     constexpr int NT = (TM / RM) * (TN / RN);
     __shared__ float As[KT][TM + 1];
@@ -528,6 +612,7 @@ __global__ void __launch_bounds__((TM / RM) * (TN / RN)) mul_mat_dense_kernel(T4
 // read once for all N columns.  K*Q of a decode step is m = n_past + 1 rows of 64 floats per head, V*P is 64 rows of n_past + 1.
 template <typename A, int NC>
 __global__ void __launch_bounds__(256) mul_mat_dense_rows_kernel(T4 a, T4 b, T4 d, int64_t r2, int64_t r3) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m >= a.ne1) return;
@@ -591,10 +676,10 @@ int b200_op_get_rows(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *
         const __half *qd = reinterpret_cast<const __half *>(qs + src0->q_total_blocks * b200_qs_bytes(src0->type));
         const int grid = grid_for(nr * (nc / 4), 256, ctx->sm_count);
         if (src0->type == B200_TYPE_Q4_0)
-            get_rows_kernel<B200_TYPE_Q4_0><<<grid, 256, 0, ctx->stream>>>(nullptr, a.nb1, a.nb2, a.nb3, a.ne1, qs, qd, src0->q_block_off, r.p, r.nb0, r.nb1, r.nb2,
+            launch_k(ctx, get_rows_kernel<B200_TYPE_Q4_0>, grid, 256, nullptr, a.nb1, a.nb2, a.nb3, a.ne1, qs, qd, src0->q_block_off, r.p, r.nb0, r.nb1, r.nb2,
                                                                          r.ne0, r.ne1, reinterpret_cast<float *>(d.p), d.nb1, d.nb2, d.nb3, nc, nr, nullptr);
         else
-            get_rows_kernel<B200_TYPE_Q8_0><<<grid, 256, 0, ctx->stream>>>(nullptr, a.nb1, a.nb2, a.nb3, a.ne1, qs, qd, src0->q_block_off, r.p, r.nb0, r.nb1, r.nb2,
+            launch_k(ctx, get_rows_kernel<B200_TYPE_Q8_0>, grid, 256, nullptr, a.nb1, a.nb2, a.nb3, a.ne1, qs, qd, src0->q_block_off, r.p, r.nb0, r.nb1, r.nb2,
                                                                          r.ne0, r.ne1, reinterpret_cast<float *>(d.p), d.nb1, d.nb2, d.nb3, nc, nr, nullptr);
         return finish(ctx, "get_rows");
     }
@@ -602,16 +687,16 @@ int b200_op_get_rows(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *
     B200_REQUIRE(ctx, src0->nb[0] == elt_size(src0->type), B200_ERR_UNSUPPORTED);
     const bool vec = nc % 4 == 0 && aligned16(dst) && ((uintptr_t)src0->data & 15) == 0;
     if (vec && src0->type == B200_TYPE_F32 && aligned16(src0)) {
-        get_rows_kernel<B200_TYPE_F32><<<grid_for(nr * (nc / 4), 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+        launch_k(ctx, get_rows_kernel<B200_TYPE_F32>, grid_for(nr * (nc / 4), 256, ctx->sm_count), 256, 
             a.p, a.nb1, a.nb2, a.nb3, a.ne1, nullptr, nullptr, 0, r.p, r.nb0, r.nb1, r.nb2, r.ne0, r.ne1, reinterpret_cast<float *>(d.p), d.nb1, d.nb2, d.nb3, nc, nr, nullptr);
     } else if (vec && src0->type == B200_TYPE_F16 && src0->nb[1] % 8 == 0 && src0->nb[2] % 8 == 0 && src0->nb[3] % 8 == 0) {
-        get_rows_kernel<B200_TYPE_F16><<<grid_for(nr * (nc / 4), 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+        launch_k(ctx, get_rows_kernel<B200_TYPE_F16>, grid_for(nr * (nc / 4), 256, ctx->sm_count), 256, 
             a.p, a.nb1, a.nb2, a.nb3, a.ne1, nullptr, nullptr, 0, r.p, r.nb0, r.nb1, r.nb2, r.ne0, r.ne1, reinterpret_cast<float *>(d.p), d.nb1, d.nb2, d.nb3, nc, nr, nullptr);
     } else if (src0->type == B200_TYPE_F32) {
-        get_rows_scalar_kernel<B200_TYPE_F32><<<grid_for(nr * nc, 256, ctx->sm_count), 256, 0, ctx->stream>>>(a.p, a.nb1, a.nb2, a.nb3, a.ne1, r.p, r.nb0, r.nb1, r.nb2,
+        launch_k(ctx, get_rows_scalar_kernel<B200_TYPE_F32>, grid_for(nr * nc, 256, ctx->sm_count), 256, a.p, a.nb1, a.nb2, a.nb3, a.ne1, r.p, r.nb0, r.nb1, r.nb2,
                                                                                                           r.ne0, r.ne1, d.p, d.nb1, d.nb2, d.nb3, nc, nr, nullptr);
     } else {
-        get_rows_scalar_kernel<B200_TYPE_F16><<<grid_for(nr * nc, 256, ctx->sm_count), 256, 0, ctx->stream>>>(a.p, a.nb1, a.nb2, a.nb3, a.ne1, r.p, r.nb0, r.nb1, r.nb2,
+        launch_k(ctx, get_rows_scalar_kernel<B200_TYPE_F16>, grid_for(nr * nc, 256, ctx->sm_count), 256, a.p, a.nb1, a.nb2, a.nb3, a.ne1, r.p, r.nb0, r.nb1, r.nb2,
                                                                                                           r.ne0, r.ne1, d.p, d.nb1, d.nb2, d.nb3, nc, nr, nullptr);
     }
     return finish(ctx, "get_rows");
@@ -631,8 +716,8 @@ int b200_op_binary(b200_ctx *ctx, int op, const b200_tensor *src0, const b200_te
                       aligned16(src1) && aligned16(dst);
     const int grid = grid_for(rows ? n / 4 : n, 256, ctx->sm_count);
 #define B200_BIN(OP)                                                                          \
-    if (rows) binary_rows_kernel<OP><<<grid, 256, 0, ctx->stream>>>(a, b, d);                 \
-    else binary_generic_kernel<OP><<<grid, 256, 0, ctx->stream>>>(a, b, d)
+    if (rows) launch_k(ctx, binary_rows_kernel<OP>, grid, 256, a, b, d);                 \
+    else launch_k(ctx, binary_generic_kernel<OP>, grid, 256, a, b, d)
     if (op == B200_OP_ADD) { B200_BIN(B200_OP_ADD); }
     else if (op == B200_OP_MUL) { B200_BIN(B200_OP_MUL); }
     else { B200_BIN(B200_OP_DIV); }
@@ -650,9 +735,9 @@ static int elementwise(b200_ctx *ctx, int mode, const b200_tensor *src0, const b
     const float *x = static_cast<const float *>(src0->data);
     float *y = static_cast<float *>(dst->data);
     const int grid = grid_for(n, 256, ctx->sm_count);
-    if (mode == 0) elementwise_kernel<0><<<grid, 256, 0, ctx->stream>>>(x, y, n, op, s, src0->ne[0], src0->ne[1]);
-    else if (mode == 1) elementwise_kernel<1><<<grid, 256, 0, ctx->stream>>>(x, y, n, op, s, src0->ne[0], src0->ne[1]);
-    else elementwise_kernel<2><<<grid, 256, 0, ctx->stream>>>(x, y, n, op, s, src0->ne[0], src0->ne[1]);
+    if (mode == 0) launch_k(ctx, elementwise_kernel<0>, grid, 256, x, y, n, op, s, src0->ne[0], src0->ne[1]);
+    else if (mode == 1) launch_k(ctx, elementwise_kernel<1>, grid, 256, x, y, n, op, s, src0->ne[0], src0->ne[1]);
+    else launch_k(ctx, elementwise_kernel<2>, grid, 256, x, y, n, op, s, src0->ne[0], src0->ne[1]);
     return finish(ctx, "elementwise");
 }
 
@@ -688,14 +773,23 @@ int b200_op_norm(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *gain
     if (ne0 % 4 == 0 && ne0 <= 1024 && aligned16(src0) && aligned16(dst) && ((uintptr_t)g & 15) == 0 && ((uintptr_t)b & 15) == 0) {
         const unsigned blocks = (unsigned)((nr + 3) / 4);
         const T4 a = view(src0), d = view(dst);
-#define B200_NORM_WARP(R, V) norm_warp_kernel<R, V><<<blocks, 128, 0, ctx->stream>>>(a, d, g, b, eps, nr)
+#define B200_NORM_WARP(R, V) launch_k(ctx, norm_warp_kernel<R, V>, blocks, 128, a, d, g, b, eps, nr)
         if (ne0 <= 256) { if (rms) B200_NORM_WARP(true, 2); else B200_NORM_WARP(false, 2); }
         else { if (rms) B200_NORM_WARP(true, 8); else B200_NORM_WARP(false, 8); }
 #undef B200_NORM_WARP
         return finish(ctx, "norm");
     }
-    if (rms) norm_kernel<true><<<(unsigned)nr, threads, 0, ctx->stream>>>(view(src0), view(dst), g, b, eps);
-    else norm_kernel<false><<<(unsigned)nr, threads, 0, ctx->stream>>>(view(src0), view(dst), g, b, eps);
+    if (ne0 % 4 == 0 && ne0 <= 8192 && aligned16(src0) && aligned16(dst) && ((uintptr_t)g & 15) == 0 && ((uintptr_t)b & 15) == 0) {
+        const T4 a = view(src0), d = view(dst);
+#define B200_NORM_BLOCK(R, V) launch_k(ctx, norm_block_kernel<R, V>, (unsigned)nr, 256, a, d, g, b, eps)
+        if (ne0 <= 2048) { if (rms) B200_NORM_BLOCK(true, 2); else B200_NORM_BLOCK(false, 2); }
+        else if (ne0 <= 4096) { if (rms) B200_NORM_BLOCK(true, 4); else B200_NORM_BLOCK(false, 4); }
+        else { if (rms) B200_NORM_BLOCK(true, 8); else B200_NORM_BLOCK(false, 8); }
+#undef B200_NORM_BLOCK
+        return finish(ctx, "norm");
+    }
+    if (rms) launch_k(ctx, norm_kernel<true>, (unsigned)nr, threads, view(src0), view(dst), g, b, eps);
+    else launch_k(ctx, norm_kernel<false>, (unsigned)nr, threads, view(src0), view(dst), g, b, eps);
     return finish(ctx, "norm");
 }
 
@@ -719,10 +813,10 @@ int b200_op_soft_max(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *
     const float *x = static_cast<const float *>(src0->data);
     float *y = static_cast<float *>(dst->data);
     if (mask && mask->type == B200_TYPE_F16)
-        soft_max_kernel<__half><<<(unsigned)nr, threads, 0, ctx->stream>>>(x, y, static_cast<const __half *>(mask->data), nc, src0->ne[1], src0->ne[2], scale, max_bias,
+        launch_k(ctx, soft_max_kernel<__half>, (unsigned)nr, threads, x, y, static_cast<const __half *>(mask->data), nc, src0->ne[1], src0->ne[2], scale, max_bias,
                                                                           m0, m1, n_head_log2, n_past);
     else
-        soft_max_kernel<float><<<(unsigned)nr, threads, 0, ctx->stream>>>(x, y, mask ? static_cast<const float *>(mask->data) : nullptr, nc, src0->ne[1], src0->ne[2],
+        launch_k(ctx, soft_max_kernel<float>, (unsigned)nr, threads, x, y, mask ? static_cast<const float *>(mask->data) : nullptr, nc, src0->ne[1], src0->ne[2],
                                                                          scale, max_bias, m0, m1, n_head_log2, n_past);
     return finish(ctx, "soft_max");
 }
@@ -747,15 +841,15 @@ int b200_op_copy(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *dst)
         }
         const int64_t row_bytes = src0->ne[0] * es;
         if (same_shape(src0, dst) && src0->nb[0] == es && dst->nb[0] == es && row_bytes % 16 == 0 && aligned16(src0) && aligned16(dst)) {
-            copy_rows16_kernel<<<grid_for(n * es / 16, 256, ctx->sm_count), 256, 0, ctx->stream>>>(a, d, row_bytes);
+            launch_k(ctx, copy_rows16_kernel, grid_for(n * es / 16, 256, ctx->sm_count), 256, a, d, row_bytes);
             return finish(ctx, "copy");
         }
     }
     const int grid = grid_for(n, 256, ctx->sm_count);
-    if (src0->type == dst->type && es == 4) copy_kernel<uint32_t, uint32_t><<<grid, 256, 0, ctx->stream>>>(a, d, n);
-    else if (src0->type == dst->type) copy_kernel<uint16_t, uint16_t><<<grid, 256, 0, ctx->stream>>>(a, d, n);
-    else if (src0->type == B200_TYPE_F32) copy_kernel<float, __half><<<grid, 256, 0, ctx->stream>>>(a, d, n);
-    else copy_kernel<__half, float><<<grid, 256, 0, ctx->stream>>>(a, d, n);
+    if (src0->type == dst->type && es == 4) launch_k(ctx, copy_kernel<uint32_t, uint32_t>, grid, 256, a, d, n);
+    else if (src0->type == dst->type) launch_k(ctx, copy_kernel<uint16_t, uint16_t>, grid, 256, a, d, n);
+    else if (src0->type == B200_TYPE_F32) launch_k(ctx, copy_kernel<float, __half>, grid, 256, a, d, n);
+    else launch_k(ctx, copy_kernel<__half, float>, grid, 256, a, d, n);
     return finish(ctx, "copy");
 }
 
@@ -783,8 +877,8 @@ int b200_op_rope(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *pos,
     r.xpos_base = rp->xpos_base; r.xpos_down = rp->xpos_down;
     const T4 a = view(src0), d = view(dst);
     const int grid = grid_for(n / 2, 256, ctx->sm_count);
-    if (src0->type == B200_TYPE_F32) rope_kernel<float><<<grid, 256, 0, ctx->stream>>>(a, d, static_cast<const int32_t *>(pos->data), r);
-    else rope_kernel<__half><<<grid, 256, 0, ctx->stream>>>(a, d, static_cast<const int32_t *>(pos->data), r);
+    if (src0->type == B200_TYPE_F32) launch_k(ctx, rope_kernel<float>, grid, 256, a, d, static_cast<const int32_t *>(pos->data), r);
+    else launch_k(ctx, rope_kernel<__half>, grid, 256, a, d, static_cast<const int32_t *>(pos->data), r);
     return finish(ctx, "rope");
 }
 
@@ -798,8 +892,8 @@ int b200_op_repeat(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *ds
     if (n == 0) return B200_OK;
     const T4 a = view(src0), d = view(dst);
     const int grid = grid_for(n, 256, ctx->sm_count);
-    if (es == 4) repeat_kernel<uint32_t><<<grid, 256, 0, ctx->stream>>>(a, d, n);
-    else repeat_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(a, d, n);
+    if (es == 4) launch_k(ctx, repeat_kernel<uint32_t>, grid, 256, a, d, n);
+    else launch_k(ctx, repeat_kernel<uint16_t>, grid, 256, a, d, n);
     return finish(ctx, "repeat");
 }
 
@@ -826,14 +920,14 @@ int b200_op_mul_mat_dense(b200_ctx *ctx, const b200_tensor *src0, const b200_ten
     if (N <= 8) {
         const dim3 grid((unsigned)((M + 7) / 8), (unsigned)batch, 1);
 #define B200_ROWS(NC)                                                                                                           \
-    if (src0->type == B200_TYPE_F32) mul_mat_dense_rows_kernel<float, NC><<<grid, 256, 0, ctx->stream>>>(a, b, d, r2, r3);     \
-    else mul_mat_dense_rows_kernel<__half, NC><<<grid, 256, 0, ctx->stream>>>(a, b, d, r2, r3)
+    if (src0->type == B200_TYPE_F32) launch_k(ctx, mul_mat_dense_rows_kernel<float, NC>, grid, 256, a, b, d, r2, r3);     \
+    else launch_k(ctx, mul_mat_dense_rows_kernel<__half, NC>, grid, 256, a, b, d, r2, r3)
         if (N == 1) { B200_ROWS(1); } else if (N <= 4) { B200_ROWS(4); } else { B200_ROWS(8); }
 #undef B200_ROWS
     } else {
         const dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64), (unsigned)batch);
-        if (src0->type == B200_TYPE_F32) mul_mat_dense_kernel<float, 64, 64, 4, 4><<<grid, 256, 0, ctx->stream>>>(a, b, d, r2, r3);
-        else mul_mat_dense_kernel<__half, 64, 64, 4, 4><<<grid, 256, 0, ctx->stream>>>(a, b, d, r2, r3);
+        if (src0->type == B200_TYPE_F32) launch_k(ctx, mul_mat_dense_kernel<float, 64, 64, 4, 4>, grid, 256, a, b, d, r2, r3);
+        else launch_k(ctx, mul_mat_dense_kernel<__half, 64, 64, 4, 4>, grid, 256, a, b, d, r2, r3);
     }
     return finish(ctx, "mul_mat_dense");
 }

@@ -1006,29 +1006,35 @@ static int b200_try_fuse_norm_repeat(struct b200_backend_context *bc, struct ggm
     return n;
 }
 
-/* MUL_MAT(decode) -> ADD(REPEAT(bias)) [-> GELU] [-> ADD(residual)]; the REPEAT deferred earlier or right after the mul_mat */
+/* MUL_MAT(decode) [-> ADD(REPEAT(bias))] [-> GELU] [-> ADD(residual)] [-> ADD(second residual)]; the REPEAT deferred earlier or right after the
+ * mul_mat.  GPT-J: fc -> bias -> GELU; proj -> bias; attention projection -> + MLP branch -> + residual stream (examples/gpt-j/main.cpp:520-559) */
 static int b200_try_fuse_mul_mat_repeat(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int i, int last, enum ggml_status *st) {
     struct ggml_tensor *mm = cgraph->nodes[i];
     if (!bc->opt_fuse || i + 1 >= last || mm->src[1]->ne[1] > 8 || mm->ne[2] != 1 || mm->ne[3] != 1 || b200_tensor_is_split(mm->src[0])) return 0;
-    int n = 1;
-    if (cgraph->nodes[i + 1]->op == GGML_OP_REPEAT) n = 2;
-    if (i + n >= last) return 0;
-    struct ggml_tensor *add = cgraph->nodes[i + n];
-    if (add->op != GGML_OP_ADD || !ggml_is_contiguous(add)) return 0;
-    struct ggml_tensor *rep = add->src[0] == mm ? add->src[1] : add->src[0];
-    n++;
-    if (!b200_foldable_repeat(bc, cgraph, rep, mm, i, n) || !b200_binary_of(add, GGML_OP_ADD, rep, mm)) return 0;
-    if (n == 3 && cgraph->nodes[i + 1] != rep) return 0;        /* a foreign REPEAT in between */
     b200_epilogue epi;
     memset(&epi, 0, sizeof(epi));
-    epi.bias_dev = (const float *)rep->src[0]->data;
-    const struct ggml_tensor *inter[5];
-    int n_inter = 0;
-    inter[n_inter++] = mm;
-    inter[n_inter++] = rep;
-    struct ggml_tensor *cur = add;
-    const struct ggml_tensor *residual = NULL;
-    if (i + n < last) {
+    const struct ggml_tensor *inter[6], *rep = NULL, *residual[2] = { NULL, NULL };
+    int n_inter = 0, n = 1, n_res = 0;
+    struct ggml_tensor *cur = mm;
+    {   /* bias */
+        int k = n;
+        if (i + k < last && cgraph->nodes[i + k]->op == GGML_OP_REPEAT) k++;
+        if (i + k < last) {
+            struct ggml_tensor *add = cgraph->nodes[i + k];
+            if (add->op == GGML_OP_ADD && ggml_is_contiguous(add)) {
+                struct ggml_tensor *r = add->src[0] == mm ? add->src[1] : add->src[0];
+                if (b200_foldable_repeat(bc, cgraph, r, mm, i, k + 1) && b200_binary_of(add, GGML_OP_ADD, r, mm) && (k == n || cgraph->nodes[i + n] == r)) {
+                    rep = r;
+                    epi.bias_dev = (const float *)r->src[0]->data;
+                    inter[n_inter++] = cur;
+                    inter[n_inter++] = r;
+                    cur = add;
+                    n = k + 1;
+                }
+            }
+        }
+    }
+    if (rep && i + n < last) {
         struct ggml_tensor *nx = cgraph->nodes[i + n];
         if (nx->op == GGML_OP_UNARY && ggml_get_unary_op(nx) == GGML_UNARY_OP_GELU && nx->src[0] == cur && ggml_is_contiguous(nx) && nx->type == GGML_TYPE_F32) {
             epi.act = B200_EPI_GELU;
@@ -1037,20 +1043,21 @@ static int b200_try_fuse_mul_mat_repeat(struct b200_backend_context *bc, struct 
             n++;
         }
     }
-    if (i + n < last) {
+    while (n_res < 2 && i + n < last) {
         struct ggml_tensor *nx = cgraph->nodes[i + n];
-        if (nx->op == GGML_OP_ADD && nx->type == GGML_TYPE_F32 && (nx->src[0] == cur || nx->src[1] == cur) && nx->src[0] != nx->src[1] && ggml_is_contiguous(nx)) {
-            const struct ggml_tensor *r = nx->src[0] == cur ? nx->src[1] : nx->src[0];
-            if (r->type == GGML_TYPE_F32 && ggml_are_same_shape(r, mm) && ggml_is_contiguous(r) && b200_in_device_buffer(r) && r->data != NULL &&
-                b200_deferred_index(bc, r) < 0) {
-                residual = r;
-                epi.residual_dev = (const float *)r->data;
-                inter[n_inter++] = cur;
-                cur = nx;
-                n++;
-            }
-        }
+        if (nx->op != GGML_OP_ADD || nx->type != GGML_TYPE_F32 || (nx->src[0] != cur && nx->src[1] != cur) || nx->src[0] == nx->src[1] || !ggml_is_contiguous(nx)) break;
+        const struct ggml_tensor *r = nx->src[0] == cur ? nx->src[1] : nx->src[0];
+        if (r->type != GGML_TYPE_F32 || !ggml_are_same_shape(r, mm) || !ggml_is_contiguous(r) || !b200_in_device_buffer(r) || r->data == NULL ||
+            b200_deferred_index(bc, r) >= 0)
+            break;
+        residual[n_res++] = r;
+        inter[n_inter++] = cur;
+        cur = nx;
+        n++;
     }
+    if (n == 1) return 0;
+    epi.residual_dev = residual[0] ? (const float *)residual[0]->data : NULL;
+    epi.residual2_dev = residual[1] ? (const float *)residual[1]->data : NULL;
     if (cur->view_src != NULL || !ggml_are_same_shape(cur, mm)) return 0;
     bool managed = false;
     for (int k = 0; k < n_inter; k++) managed |= cur->data == inter[k]->data;
@@ -1058,14 +1065,15 @@ static int b200_try_fuse_mul_mat_repeat(struct b200_backend_context *bc, struct 
     if (!b200_uses_build(bc, cgraph)) return 0;
     for (int k = 0; k < n_inter; k++)
         if (!b200_read_only_by_group(bc, cgraph, inter[k], i, n)) return 0;
-    if (b200_ranges_overlap(cur, mm->src[1]) || b200_ranges_overlap(cur, rep->src[0])) return 0;
-    if (residual && b200_ranges_overlap(cur, residual) && cur->data != residual->data) return 0;
+    if (b200_ranges_overlap(cur, mm->src[1]) || (rep && b200_ranges_overlap(cur, rep->src[0]))) return 0;
+    for (int k = 0; k < n_res; k++)
+        if (b200_ranges_overlap(cur, residual[k]) && cur->data != residual[k]->data) return 0;
     b200_mul_mat_args args;
     if (!b200_fill_mul_mat_args(mm, &args)) return 0;
     args.dst_dev = (float *)cur->data;
     const int rc = b200_mul_mat_fused(bc->ctx, &args, &epi);
     if (rc == B200_ERR_UNSUPPORTED) return 0;          /* not a single-launch shape: the operators run one by one */
-    b200_deferred_drop(bc, rep);
+    if (rep) b200_deferred_drop(bc, rep);
     *st = b200_glue_status(bc, mm, rc);
     return n;
 }

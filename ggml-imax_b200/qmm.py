@@ -65,7 +65,7 @@ class RopeParams(C.Structure):
 
 
 class Epilogue(C.Structure):
-    _fields_ = [("bias_dev", C.c_void_p), ("residual_dev", C.c_void_p), ("act", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("bias_dev", C.c_void_p), ("residual_dev", C.c_void_p), ("act", C.c_int32), ("reserved", C.c_int32), ("residual2_dev", C.c_void_p)]
 
 
 EPI_NONE, EPI_GELU = 0, 1
@@ -525,11 +525,11 @@ class Context:
         a.dst_dev = dst_ptr
         return a
 
-    def mul_mat_fused(self, w: QTensor, x_ptr: int, n: int, dst_ptr: int, bias_ptr: int = 0, residual_ptr: int = 0, act: int = EPI_NONE):
+    def mul_mat_fused(self, w: QTensor, x_ptr: int, n: int, dst_ptr: int, bias_ptr: int = 0, residual_ptr: int = 0, act: int = EPI_NONE, residual2_ptr: int = 0):
         """decode mul_mat with bias / GELU / residual folded into the GEMV epilogue (b200_mul_mat_fused)"""
         a = self.make_args(w, x_ptr, n, dst_ptr)
         e = Epilogue()
-        e.bias_dev, e.residual_dev, e.act = bias_ptr or None, residual_ptr or None, act
+        e.bias_dev, e.residual_dev, e.act, e.residual2_dev = bias_ptr or None, residual_ptr or None, act, residual2_ptr or None
         self._check(self.lib.b200_mul_mat_fused(self.h, C.byref(a), C.byref(e)))
 
     def mul_mat_batch(self, args_list):

@@ -192,8 +192,9 @@ typedef struct b200_mul_mat_args {
 
 B200_API int b200_mul_mat(b200_ctx *ctx, const b200_mul_mat_args *args);
 /* the same with the operators that follow a decode mul_mat in a transformer block folded into its epilogue:
- *     dst = act(src0 x src1 + bias) + residual
- * -- the ADD of a bias row, the GELU and the ADD of the residual stream (examples/gpt-2/main-backend.cpp:614-625, :659-672, :683-699) --
+ *     dst = (act(src0 x src1 + bias) + residual) + residual2
+ * -- the ADD of a bias row, the GELU and the ADD of the residual stream (examples/gpt-2/main-backend.cpp:614-625, :659-672, :683-699); GPT-J sums its
+ * MLP branch and the residual stream onto the attention projection (examples/gpt-j/main.cpp:556-559), hence the second one --
  * for 2-D decode shapes that take the GEMV (ne11 <= 8, no batch dims).  bias_dev [ne01] or NULL, residual_dev dense like dst or NULL (may be
  * dst_dev itself), act = B200_EPI_NONE / B200_EPI_GELU.  Same bits as b200_mul_mat followed by the separate operators.
  * B200_ERR_UNSUPPORTED for any other shape: the caller runs the operators one by one. */
@@ -204,6 +205,7 @@ typedef struct b200_epilogue {
     const float *residual_dev;
     int32_t      act;
     int32_t      reserved;
+    const float *residual2_dev;     /* added after residual_dev, or NULL (may be dst_dev itself, like residual_dev) */
 } b200_epilogue;
 B200_API int b200_mul_mat_fused(b200_ctx *ctx, const b200_mul_mat_args *args, const b200_epilogue *epilogue);
 /* `count` mul_mats with NO data dependencies among them (e.g. the q/k/v/fc_in projections of a GPT-J block, which all

@@ -104,7 +104,7 @@ def test_unary(qmm, gpu_ctx, name):
     assert nmse(got, want) <= 1e-10, nmse(got, want)
 
 
-@pytest.mark.parametrize("ne0", [64, 768, 1000, 5000])
+@pytest.mark.parametrize("ne0", [64, 768, 1000, 1028, 2048, 4096, 5000, 8192, 8196])       # warp kernel <= 1024, row-in-registers CTA <= 8192, loop kernel beyond / unaligned
 @pytest.mark.parametrize("rms", [False, True])
 def test_norm_and_fused_affine(qmm, gpu_ctx, ne0, rms):
     """ggml_compute_forward_norm_f32 (src/ggml.c:11353) / rms_norm; and norm * gain + bias in one kernel"""
@@ -280,7 +280,7 @@ def test_unsupported_combinations_are_refused(qmm, gpu_ctx):
 
 @pytest.mark.parametrize("qtype", [Q4_0, Q8_0])
 @pytest.mark.parametrize("k,m,n", [(768, 2304, 1), (3072, 768, 1), (768, 3072, 3), (4096, 4096, 1), (96, 50, 2), (16384, 4096, 1)])
-@pytest.mark.parametrize("bias,gelu,res", [(True, False, False), (True, True, False), (True, False, True), (False, False, True), (True, True, True)])
+@pytest.mark.parametrize("bias,gelu,res", [(True, False, 0), (True, True, 0), (True, False, 1), (False, False, 1), (True, True, 1), (False, False, 2), (True, False, 2)])
 def test_mul_mat_fused_epilogue_equals_the_separate_operators(qmm, gpu_ctx, oracle, qtype, k, m, n, bias, gelu, res):
     """b200_mul_mat_fused: dst = act(W x + bias) + residual in the GEMV epilogue (streaming kernel for k % 256 == 0, generic kernel
     otherwise; k > 4096 goes through the k-split combine) -- bitwise what b200_mul_mat, ADD, GELU, ADD give one after the other, also with
@@ -291,6 +291,7 @@ def test_mul_mat_fused_epilogue_equals_the_separate_operators(qmm, gpu_ctx, orac
     x = up(qmm, gpu_ctx, rng.uniform(-1, 1, (n, k)).astype(np.float32))
     b = up(qmm, gpu_ctx, rng.uniform(-1, 1, (m,)).astype(np.float32))
     r0 = rng.uniform(-1, 1, (n, m)).astype(np.float32)
+    r2 = up(qmm, gpu_ctx, rng.uniform(-1, 1, (n, m)).astype(np.float32))              # res == 2: the second residual (GPT-J: + MLP branch, + residual stream)
     # separate operators
     d1 = empty(qmm, gpu_ctx, (n, m))
     gpu_ctx.mul_mat_device(w, x.buf.ptr, n, d1.buf.ptr)
@@ -300,11 +301,13 @@ def test_mul_mat_fused_epilogue_equals_the_separate_operators(qmm, gpu_ctx, orac
         gpu_ctx.op_unary("gelu", d1, d1)
     if res:
         gpu_ctx.op_binary(qmm.OP_ADD, d1, up(qmm, gpu_ctx, r0), d1)
+    if res == 2:
+        gpu_ctx.op_binary(qmm.OP_ADD, d1, r2, d1)
     # one launch; the residual IS the destination buffer
     d2 = up(qmm, gpu_ctx, r0)
     l0 = gpu_ctx.launch_count()
     gpu_ctx.mul_mat_fused(w, x.buf.ptr, n, d2.buf.ptr, bias_ptr=b.buf.ptr if bias else 0, residual_ptr=d2.buf.ptr if res else 0,
-                          act=qmm.EPI_GELU if gelu else qmm.EPI_NONE)
+                          act=qmm.EPI_GELU if gelu else qmm.EPI_NONE, residual2_ptr=r2.buf.ptr if res == 2 else 0)
     assert gpu_ctx.launch_count() - l0 == 1
     gpu_ctx.synchronize()
     assert np.array_equal(d1.numpy(), d2.numpy())
