@@ -31,12 +31,14 @@ __device__ __forceinline__ void pdl_enter() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+struct DynSmem { size_t bytes; };
 template <typename... KArgs, typename... Args>
-void launch_k(b200_ctx *ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, Args... args) {
+void launch_ks(b200_ctx *ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, DynSmem smem, Args... args) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;
     cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem.bytes;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -44,6 +46,10 @@ void launch_k(b200_ctx *ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, Args
     cfg.attrs = attr;
     cfg.numAttrs = ctx->opt_pdl ? 1 : 0;
     (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);      // errors surface in finish() through cudaGetLastError
+}
+template <typename... KArgs, typename... Args>
+void launch_k(b200_ctx *ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, Args... args) {
+    launch_ks(ctx, kern, grid, block, DynSmem{0}, args...);
 }
 
 struct T4 {                      // a 4-D strided tensor as the kernels see it
@@ -466,6 +472,74 @@ __global__ void __launch_bounds__(256) copy_rows16_kernel(T4 a, T4 d, int64_t ro
         r -= i3 * d.ne2 * d.ne1;
         const int64_t i2 = r / d.ne1, i1 = r - i2 * d.ne1;
         *reinterpret_cast<uint4 *>(d.p + i3 * d.nb3 + i2 * d.nb2 + i1 * d.nb1 + c) = *reinterpret_cast<const uint4 *>(a.p + i3 * a.nb3 + i2 * a.nb2 + i1 * a.nb1 + c);
+    }
+}
+
+// ---- attention of a decode step as ONE kernel: K*Q -> SCALE -> DIAG_MASK_INF -> SOFT_MAX -> V*P -> merged heads ----------------------------
+// (examples/gpt-j/main.cpp:490-530, examples/gpt-2/main-backend.cpp:567-610: six graph nodes, four launches otherwise).  One CTA per
+// (head, token): scores of the T cached positions into shared memory (a warp per position, lanes over the head dimension), the
+// softmax of soft_max_kernel (same rounding of the scale, same three steps), then a warp per output dimension over V's rows, which
+// the caches keep contiguous along T.  K [hd][T][H] and V [T][hd][H] are F16 or F32 views with any row / head strides; Q is F32
+// [hd][N][H]; the result goes straight to the merged layout dst[hd][H][N] the CPY / CONT behind the PERMUTE would produce.
+template <typename KT, typename VT>
+__global__ void __launch_bounds__(1024) attention_decode_kernel(T4 q, T4 k, T4 v, T4 d, float scale, int n_past) {
+    pdl_enter();
+    extern __shared__ float sc[];                      // T scores, then the probabilities
+    __shared__ float red[33];
+    const int h = blockIdx.x, i = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int hd = (int)q.ne0, T = (int)k.ne1;
+    const int lim = n_past >= 0 ? min(T, n_past + i + 1) : T;              // positions t >= lim are masked out
+    // 32 warps so that the chains of dependent memory latencies stay short: a decode step has T of a few hundred at most per launch here,
+    // and a CTA that walks its positions (or its output rows) eight at a time spends its life waiting for L2
+    const float *qr = reinterpret_cast<const float *>(q.p + (int64_t)i * q.nb1 + (int64_t)h * q.nb2);
+    float qv[8];                                         // hd <= 256: this lane's slice of q stays in registers
+#pragma unroll
+    for (int j = 0; j < 8; j++) qv[j] = lane + 32 * j < hd ? qr[lane + 32 * j] : 0.f;
+    for (int t = warp; t < lim; t += nw) {
+        const KT *kr = reinterpret_cast<const KT *>(k.p + (int64_t)t * k.nb1 + (int64_t)h * k.nb2);
+        float s = 0.f;
+        if (hd <= 256) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (lane + 32 * j < hd) s += convert<KT, float>(kr[lane + 32 * j]) * qv[j];
+        } else {
+            for (int e = lane; e < hd; e += 32) s += convert<KT, float>(kr[e]) * qr[e];
+        }
+        s = warp_sum(s);
+        if (lane == 0) sc[t] = __fmul_rn(s, scale);
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int t = threadIdx.x; t < lim; t += blockDim.x) mx = fmaxf(mx, sc[t]);
+    mx = block_reduce<true>(mx, red);
+    float sum = 0.f;
+    for (int t = threadIdx.x; t < lim; t += blockDim.x) {
+        const float e = expf(sc[t] - mx);
+        sc[t] = e;
+        sum += e;
+    }
+    sum = block_reduce<false>(sum, red);               // (its barriers also publish sc[])
+    const float inv = 1.0f / sum;
+    float *out = reinterpret_cast<float *>(d.p + (int64_t)h * d.nb1 + (int64_t)i * d.nb2);
+    // four output rows per warp at a time: their loads are all in flight before the first multiply
+    for (int e0 = warp * 4; e0 < hd; e0 += nw * 4) {
+        const VT *vr[4];
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 4; r++) vr[r] = reinterpret_cast<const VT *>(v.p + (int64_t)min(e0 + r, hd - 1) * v.nb1 + (int64_t)h * v.nb2);
+        for (int t = lane; t < lim; t += 32) {
+            const float p = sc[t] * inv;
+            float x[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) x[r] = convert<VT, float>(vr[r][t]);
+#pragma unroll
+            for (int r = 0; r < 4; r++) acc[r] += x[r] * p;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const float a = warp_sum(acc[r]);
+            if (lane == 0 && e0 + r < hd) out[e0 + r] = a;
+        }
     }
 }
 
@@ -895,6 +969,33 @@ int b200_op_repeat(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *ds
     if (es == 4) launch_k(ctx, repeat_kernel<uint32_t>, grid, 256, a, d, n);
     else launch_k(ctx, repeat_kernel<uint16_t>, grid, 256, a, d, n);
     return finish(ctx, "repeat");
+}
+
+int b200_op_attention_decode(b200_ctx *ctx, const b200_tensor *q, const b200_tensor *k, const b200_tensor *v, const b200_tensor *dst, float scale, int n_past) {
+    OPS_ENTER(ctx);
+    B200_REQUIRE(ctx, q && k && v && dst, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, q->type == B200_TYPE_F32 && dst->type == B200_TYPE_F32 && (k->type == B200_TYPE_F32 || k->type == B200_TYPE_F16) &&
+                          (v->type == B200_TYPE_F32 || v->type == B200_TYPE_F16), B200_ERR_UNSUPPORTED);
+    const int64_t hd = q->ne[0], N = q->ne[1], H = q->ne[2], T = k->ne[1];
+    B200_REQUIRE(ctx, q->ne[3] == 1 && k->ne[3] == 1 && v->ne[3] == 1 && dst->ne[3] == 1, B200_ERR_UNSUPPORTED);
+    B200_REQUIRE(ctx, k->ne[0] == hd && k->ne[2] == H && v->ne[0] == T && v->ne[1] == hd && v->ne[2] == H, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, dst->ne[0] == hd && dst->ne[1] == H && dst->ne[2] == N, B200_ERR_INVALID);
+    B200_REQUIRE(ctx, q->nb[0] == 4 && dst->nb[0] == 4 && k->nb[0] == elt_size(k->type) && v->nb[0] == elt_size(v->type), B200_ERR_INVALID);
+    if (N > 8 || T > 1024 || H > 65535 || hd > 1024) {
+        b200_set_error(ctx, "b200_op_attention_decode: a decode-sized problem only (N <= 8, T <= 1024)");
+        return B200_ERR_UNSUPPORTED;
+    }
+    if (hd == 0 || N == 0 || H == 0 || T == 0) return B200_OK;
+    const T4 a = view(q), b = view(k), c = view(v), d = view(dst);
+    const dim3 grid((unsigned)H, (unsigned)N);
+    const size_t smem = (size_t)T * sizeof(float);
+    const bool kh = k->type == B200_TYPE_F16, vh = v->type == B200_TYPE_F16;
+    const int threads = hd >= 128 ? 1024 : (hd >= 64 ? 512 : 256);       // about one warp per 4 output rows
+    if (kh && vh) launch_ks(ctx, attention_decode_kernel<__half, __half>, grid, threads, DynSmem{smem}, a, b, c, d, scale, n_past);
+    else if (kh) launch_ks(ctx, attention_decode_kernel<__half, float>, grid, threads, DynSmem{smem}, a, b, c, d, scale, n_past);
+    else if (vh) launch_ks(ctx, attention_decode_kernel<float, __half>, grid, threads, DynSmem{smem}, a, b, c, d, scale, n_past);
+    else launch_ks(ctx, attention_decode_kernel<float, float>, grid, threads, DynSmem{smem}, a, b, c, d, scale, n_past);
+    return finish(ctx, "attention_decode");
 }
 
 int b200_op_mul_mat_dense(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *src1, const b200_tensor *dst) {

@@ -1006,6 +1006,74 @@ static int b200_try_fuse_norm_repeat(struct b200_backend_context *bc, struct ggm
     return n;
 }
 
+/* The attention of a decode step: MUL_MAT(K, Q) -> SCALE -> DIAG_MASK_INF -> SOFT_MAX (each in place of the one before) -> MUL_MAT(V, .) ->
+ * PERMUTE(0, 2, 1, 3) -> CPY / CONT into a contiguous [n_embd][N] (examples/gpt-j/main.cpp:490-530, examples/gpt-2/main-backend.cpp:567-610), views
+ * in between, as ONE launch (b200_op_attention_decode) under the reader-count rule above. */
+static int b200_next_real(const struct ggml_cgraph *cgraph, int j, int last) {
+    while (j < last && (ggml_is_empty(cgraph->nodes[j]) || b200_op_is_noop(cgraph->nodes[j]->op))) j++;
+    return j;
+}
+static int b200_try_fuse_attention(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int i, int last, enum ggml_status *st) {
+    struct ggml_tensor *kq = cgraph->nodes[i];
+    if (!bc->opt_fuse || kq->op != GGML_OP_MUL_MAT || kq->type != GGML_TYPE_F32) return 0;
+    const struct ggml_tensor *K = kq->src[0], *Q = kq->src[1];
+    if (!K || !Q || Q->type != GGML_TYPE_F32 || (K->type != GGML_TYPE_F32 && K->type != GGML_TYPE_F16)) return 0;
+    const int64_t hd = Q->ne[0], N = Q->ne[1], H = Q->ne[2], T = K->ne[1];
+    if (K->ne[0] != hd || K->ne[2] != H || K->ne[3] != 1 || Q->ne[3] != 1 || N > 8 || T > 1024 || hd > 1024) return 0;
+    if (K->nb[0] != ggml_type_size(K->type) || Q->nb[0] != sizeof(float) || !b200_glue_supported_srcs(kq)) return 0;
+    int j = b200_next_real(cgraph, i + 1, last);
+    if (j >= last) return 0;
+    struct ggml_tensor *sc = cgraph->nodes[j];
+    if (sc->op != GGML_OP_SCALE || !b200_inplace_child(sc, kq)) return 0;
+    j = b200_next_real(cgraph, j + 1, last);
+    if (j >= last) return 0;
+    struct ggml_tensor *mk = cgraph->nodes[j];
+    if (mk->op != GGML_OP_DIAG_MASK_INF || !b200_inplace_child(mk, sc)) return 0;
+    j = b200_next_real(cgraph, j + 1, last);
+    if (j >= last) return 0;
+    struct ggml_tensor *sm = cgraph->nodes[j];
+    if (sm->op != GGML_OP_SOFT_MAX || !b200_inplace_child(sm, mk) || sm->src[1] != NULL || sm->src[2] != NULL) return 0;
+    float s, scale, max_bias;
+    memcpy(&s, sc->op_params, sizeof(s));
+    memcpy(&scale, (const float *)sm->op_params + 0, sizeof(scale));
+    memcpy(&max_bias, (const float *)sm->op_params + 1, sizeof(max_bias));
+    if (max_bias != 0.0f) return 0;
+    j = b200_next_real(cgraph, j + 1, last);
+    if (j >= last) return 0;
+    struct ggml_tensor *pv = cgraph->nodes[j];
+    if (pv->op != GGML_OP_MUL_MAT || pv->src[1] != sm || pv->type != GGML_TYPE_F32 || !ggml_is_contiguous(pv)) return 0;
+    const struct ggml_tensor *V = pv->src[0];
+    if (!V || (V->type != GGML_TYPE_F32 && V->type != GGML_TYPE_F16) || V->ne[0] != T || V->ne[1] != hd || V->ne[2] != H || V->ne[3] != 1 ||
+        V->nb[0] != ggml_type_size(V->type) || !b200_in_device_buffer(V) || b200_tensor_is_split(V))
+        return 0;
+    j = b200_next_real(cgraph, j + 1, last);
+    if (j >= last) return 0;
+    struct ggml_tensor *cp = cgraph->nodes[j];
+    if ((cp->op != GGML_OP_CPY && cp->op != GGML_OP_CONT) || cp->type != GGML_TYPE_F32 || !ggml_is_contiguous(cp) || ggml_nelements(cp) != hd * H * N) return 0;
+    const struct ggml_tensor *perm = cp->src[0];
+    if (!perm || perm->op != GGML_OP_PERMUTE || perm->src[0] != pv || perm->ne[0] != hd || perm->ne[1] != H || perm->ne[2] != N || perm->ne[3] != 1 ||
+        perm->nb[0] != sizeof(float) || perm->nb[1] != pv->nb[2] || perm->nb[2] != pv->nb[1] || perm->data != pv->data)
+        return 0;
+    const int n = j - i + 1;
+    if (!b200_uses_build(bc, cgraph)) return 0;
+    const struct ggml_tensor *inter[6] = { kq, sc, mk, sm, pv, perm };
+    for (int k = 0; k < 6; k++)
+        if (!b200_read_only_by_group(bc, cgraph, inter[k], i, n)) return 0;
+    if (b200_ranges_overlap(cp, K) || b200_ranges_overlap(cp, V) || b200_ranges_overlap(cp, Q)) return 0;
+    b200_tensor tq, tk, tv, td;
+    if (!b200_fill_tensor(Q, &tq) || !b200_fill_tensor(K, &tk) || !b200_fill_tensor(V, &tv)) return 0;
+    memset(&td, 0, sizeof(td));
+    td.type = (int32_t)GGML_TYPE_F32;
+    td.data = cp->data;
+    td.ne[0] = hd; td.ne[1] = H; td.ne[2] = N; td.ne[3] = 1;
+    td.nb[0] = (int64_t)sizeof(float); td.nb[1] = td.nb[0] * hd; td.nb[2] = td.nb[1] * H; td.nb[3] = td.nb[2] * N;
+    const int rc = b200_op_attention_decode(bc->ctx, &tq, &tk, &tv, &td, s * scale, ((const int32_t *)mk->op_params)[0]);
+    if (rc == B200_ERR_UNSUPPORTED) return 0;
+    *st = b200_glue_status(bc, cp, rc);
+    /* launches saved: of the six real nodes one remains */
+    return n;
+}
+
 /* MUL_MAT(decode) [-> ADD(REPEAT(bias))] [-> GELU] [-> ADD(residual)] [-> ADD(second residual)]; the REPEAT deferred earlier or right after the
  * mul_mat.  GPT-J: fc -> bias -> GELU; proj -> bias; attention projection -> + MLP branch -> + residual stream (examples/gpt-j/main.cpp:520-559) */
 static int b200_try_fuse_mul_mat_repeat(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int i, int last, enum ggml_status *st) {
@@ -1841,7 +1909,8 @@ static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc
         {
             enum ggml_status st = GGML_STATUS_SUCCESS;
             if (node->op == GGML_OP_REPEAT && b200_try_defer_repeat(bc, cgraph, node)) continue;
-            int fused = b200_try_fuse(bc, cgraph, i, last, &st);
+            int fused = node->op == GGML_OP_MUL_MAT ? b200_try_fuse_attention(bc, cgraph, i, last, &st) : 0;
+            if (fused == 0) fused = b200_try_fuse(bc, cgraph, i, last, &st);
             if (fused == 0) fused = b200_try_fuse_norm_repeat(bc, cgraph, i, last, &st);
             if (fused > 0) {
                 if (st != GGML_STATUS_SUCCESS) return st;

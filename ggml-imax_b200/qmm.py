@@ -157,6 +157,7 @@ _SIGNATURES = {
     "b200_graph_node_count": (C.c_int64, [C.c_void_p]),
     "b200_op_rope": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(RopeParams)]),
     "b200_op_repeat": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor)]),
+    "b200_op_attention_decode": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor), C.c_float, C.c_int]),
     "b200_op_mul_mat_dense": (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.POINTER(Tensor), C.POINTER(Tensor)]),
     "b200_block_dots": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "b200_mul_mat_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -378,6 +379,9 @@ class Context:
                 ext_factor: float = 0.0, attn_factor: float = 1.0, beta_fast: float = 0.0, beta_slow: float = 0.0, xpos_base: float = 0.0, xpos_down: bool = False):
         rp = RopeParams(n_dims, mode, n_ctx, n_orig_ctx, freq_base, freq_scale, ext_factor, attn_factor, beta_fast, beta_slow, xpos_base, int(xpos_down))
         self._check(self.lib.b200_op_rope(self.h, self._d(a), self._d(pos), self._d(dst), C.byref(rp)))
+
+    def op_attention_decode(self, q, k, v, dst, scale: float, n_past: int = -1):
+        self._check(self.lib.b200_op_attention_decode(self.h, self._d(q), self._d(k), self._d(v), self._d(dst), C.c_float(scale), n_past))
 
     def op_repeat(self, a, dst):
         self._check(self.lib.b200_op_repeat(self.h, self._d(a), self._d(dst)))

@@ -364,6 +364,13 @@ typedef struct b200_rope_params {
 B200_API int b200_op_rope(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *pos, const b200_tensor *dst, const b200_rope_params *params);
 /* GGML_OP_REPEAT (src/ggml.c:10323): dst tiles src0 along every dimension (dst->ne[i] a multiple of src0->ne[i]); F32, F16, I16, I32 */
 B200_API int b200_op_repeat(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *dst);
+/* The attention of a decode step in one launch -- what the six graph nodes MUL_MAT(K, Q) -> SCALE -> DIAG_MASK_INF -> SOFT_MAX -> MUL_MAT(V, .) ->
+ * CPY / CONT of the PERMUTEd result compute (examples/gpt-j/main.cpp:490-530, examples/gpt-2/main-backend.cpp:567-610):
+ *   dst[:, h, i] = sum_t V[t, :, h] * softmax_t(scale * K[:, t, h] . Q[:, i, h]  masked for t > n_past + i)
+ * q F32 [hd][N][H], k F16/F32 [hd][T][H], v F16/F32 [T][hd][H] (any row / head strides: views of the KV cache), dst F32 [hd][H][N];
+ * n_past < 0 = no causal mask.  Decode-sized problems only (N <= 8, T <= 1024): B200_ERR_UNSUPPORTED otherwise, the caller runs the nodes. */
+B200_API int b200_op_attention_decode(b200_ctx *ctx, const b200_tensor *q, const b200_tensor *k, const b200_tensor *v, const b200_tensor *dst, float scale,
+                                      int n_past);
 /* GGML_OP_MUL_MAT with an F32 / F16 src0 (ggml_compute_forward_mul_mat, src/ggml.c:11808): dst[n][m] = sum_k src0[m][k] * src1[n][k] per
  * (i2, i3) with the broadcast of src0 over src1's batch dims; both operands k-contiguous, any row / batch strides (K*Q and V*softmax(KQ) on
  * permuted views of the KV cache, main-backend.cpp:567, :597); fp32 accumulation */

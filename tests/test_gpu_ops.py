@@ -444,3 +444,48 @@ def test_recorded_sequence_replays_and_refuses_a_wait(qmm, gpu_ctx, oracle):
     gpu_ctx.op_scale(x, h, 2.0)                                        # the context works again
     gpu_ctx.synchronize()
     assert np.array_equal(h.numpy().reshape(-1), x.numpy().reshape(-1) * 2.0)
+
+
+@pytest.mark.parametrize("kdt,vdt", [(np.float16, np.float16), (np.float32, np.float32), (np.float16, np.float32)])
+@pytest.mark.parametrize("hd,H,N,n_past,n_ctx", [(64, 12, 1, 36, 64), (256, 16, 1, 0, 32), (256, 16, 3, 197, 256), (80, 5, 8, 1016, 1024)])
+def test_attention_decode_one_launch(qmm, gpu_ctx, kdt, vdt, hd, H, N, n_past, n_ctx):
+    """b200_op_attention_decode against the six operators it stands for (K*Q, SCALE, DIAG_MASK_INF, SOFT_MAX, V*P, merge of the heads) in float64, on
+    strided views of a KV cache laid out like GPT-J's (examples/gpt-j/main.cpp:476-512: k rows [n_ctx][n_embd], v transposed [n_embd][n_ctx])"""
+    rng = np.random.default_rng(hd + H + N + n_past)
+    T, E = n_past + N, hd * H
+    kc = rng.uniform(-1, 1, (n_ctx, E)).astype(kdt)                   # cache of k: position-major
+    vc = rng.uniform(-1, 1, (E, n_ctx)).astype(vdt)                   # cache of v: one row per embedding dimension
+    q = rng.uniform(-1, 1, (N, H, hd)).astype(np.float32)             # [hd][H][N] as computed; read through a permuted view [hd][N][H]
+    scale = 1.0 / np.sqrt(hd)
+    tk, tv, tq = up(qmm, gpu_ctx, kc), up(qmm, gpu_ctx, vc), up(qmm, gpu_ctx, q)
+    ek, ev = kc.itemsize, vc.itemsize
+    K = tk.view([hd, T, H, 1], [ek, ek * E, ek * hd, ek * E * n_ctx])
+    V = tv.view([T, hd, H, 1], [ev, ev * n_ctx, ev * n_ctx * hd, ev * n_ctx * E])
+    Q = tq.view([hd, N, H, 1], [4, 4 * E, 4 * hd, 4 * E * N])
+    dst = qmm.DTensor(gpu_ctx, qmm.TYPE_F32, [hd, H, N, 1])
+    l0 = gpu_ctx.launch_count()
+    gpu_ctx.op_attention_decode(Q, K, V, dst, scale, n_past)
+    assert gpu_ctx.launch_count() - l0 == 1
+    gpu_ctx.synchronize()
+    got = dst.numpy().reshape(N, H, hd)
+    k64 = kc[:T].astype(np.float64).reshape(T, H, hd)
+    v64 = vc[:, :T].astype(np.float64).reshape(H, hd, T)
+    want = np.empty((N, H, hd))
+    for i in range(N):
+        for h in range(H):
+            s = (k64[:, h, :] @ q[i, h].astype(np.float64)) * scale
+            s[np.arange(T) > n_past + i] = -np.inf
+            p = np.exp(s - s.max())
+            p /= p.sum()
+            want[i, h] = v64[h] @ p
+    assert nmse(got, want) <= 1e-10, nmse(got, want)
+
+
+def test_attention_decode_declines_long_contexts(qmm, gpu_ctx):
+    q = qmm.DTensor(gpu_ctx, qmm.TYPE_F32, [64, 1, 2, 1])
+    k = qmm.DTensor(gpu_ctx, qmm.TYPE_F32, [64, 1025, 2, 1])
+    v = qmm.DTensor(gpu_ctx, qmm.TYPE_F32, [1025, 64, 2, 1])
+    d = qmm.DTensor(gpu_ctx, qmm.TYPE_F32, [64, 2, 1, 1])
+    with pytest.raises(qmm.B200Error) as e:
+        gpu_ctx.op_attention_decode(q, k, v, d, 1.0, 1024)
+    assert e.value.code == qmm.ERR_UNSUPPORTED
