@@ -565,7 +565,8 @@ __device__ __forceinline__ void rope_yarn_dev(float theta_extrap, const RopeK &r
     *c = cosf(theta) * mscale;
     *s = sinf(theta) * mscale;
 }
-template <typename T>
+// TS -> TD: the CPY that stores a rotated k into an F16 cache folds into the store (same rounding, one conversion)
+template <typename TS, typename TD>
 __global__ void __launch_bounds__(256) rope_kernel(T4 a, T4 d, const int32_t *__restrict__ pos, RopeK r) {
     pdl_enter();
     const int64_t half = a.ne0 >> 1;
@@ -576,13 +577,13 @@ __global__ void __launch_bounds__(256) rope_kernel(T4 a, T4 d, const int32_t *__
         const int64_t i3 = row / (a.ne2 * a.ne1);
         row -= i3 * a.ne2 * a.ne1;
         const int64_t i2 = row / a.ne1, i1 = row - i2 * a.ne1;
-        const T *src = reinterpret_cast<const T *>(a.p + i3 * a.nb3 + i2 * a.nb2 + i1 * a.nb1);
-        T *dst = reinterpret_cast<T *>(d.p + i3 * d.nb3 + i2 * d.nb2 + i1 * d.nb1);
+        const TS *src = reinterpret_cast<const TS *>(a.p + i3 * a.nb3 + i2 * a.nb2 + i1 * a.nb1);
+        TD *dst = reinterpret_cast<TD *>(d.p + i3 * d.nb3 + i2 * d.nb2 + i1 * d.nb1);
         const int p = pos[i2];
         const int ic = 2 * j;
         if (r.neox && ic >= r.n_dims) {                      // beyond the rotated part: plain copy of the pair
-            dst[ic] = src[ic];
-            dst[ic + 1] = src[ic + 1];
+            dst[ic] = convert<float, TD>(convert<TS, float>(src[ic]));
+            dst[ic + 1] = convert<float, TD>(convert<TS, float>(src[ic + 1]));
             continue;
         }
         float theta = r.neox ? (float)p * r.freq_scale : (float)p;
@@ -590,14 +591,14 @@ __global__ void __launch_bounds__(256) rope_kernel(T4 a, T4 d, const int32_t *__
         float c, s;
         rope_yarn_dev(theta, r, r.neox ? 0 : ic, &c, &s);
         const int i0 = r.neox ? j : ic, i1x = r.neox ? j + r.n_dims / 2 : ic + 1;
-        const float x0 = convert<T, float>(src[i0]), x1 = convert<T, float>(src[i1x]);
+        const float x0 = convert<TS, float>(src[i0]), x1 = convert<TS, float>(src[i1x]);
         float zeta = 1.0f;
-        if (sizeof(T) == 4 && !r.neox && r.xpos_base != 0.0f) {
+        if (sizeof(TS) == 4 && !r.neox && r.xpos_base != 0.0f) {
             zeta = powf(((float)ic + 0.4f * (float)a.ne0) / (1.4f * (float)a.ne0), (float)p / r.xpos_base);
             if (r.xpos_down) zeta = 1.0f / zeta;
         }
-        dst[i0] = convert<float, T>(x0 * c * zeta - x1 * s * zeta);
-        dst[i1x] = convert<float, T>(x0 * s * zeta + x1 * c * zeta);
+        dst[i0] = convert<float, TD>(x0 * c * zeta - x1 * s * zeta);
+        dst[i1x] = convert<float, TD>(x0 * s * zeta + x1 * c * zeta);
     }
 }
 
@@ -930,9 +931,10 @@ int b200_op_copy(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *dst)
 int b200_op_rope(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *pos, const b200_tensor *dst, const b200_rope_params *rp) {
     OPS_ENTER(ctx);
     B200_REQUIRE(ctx, src0 && pos && dst && rp, B200_ERR_INVALID);
-    B200_REQUIRE(ctx, (src0->type == B200_TYPE_F32 || src0->type == B200_TYPE_F16) && dst->type == src0->type && pos->type == B200_TYPE_I32, B200_ERR_UNSUPPORTED);
+    B200_REQUIRE(ctx, (src0->type == B200_TYPE_F32 || src0->type == B200_TYPE_F16) && pos->type == B200_TYPE_I32 &&
+                          (dst->type == src0->type || (src0->type == B200_TYPE_F32 && dst->type == B200_TYPE_F16)), B200_ERR_UNSUPPORTED);
     B200_REQUIRE(ctx, (rp->mode & 4) == 0, B200_ERR_UNSUPPORTED);                                  // GLM layout: not built
-    B200_REQUIRE(ctx, same_shape(src0, dst) && src0->nb[0] == elt_size(src0->type) && dst->nb[0] == src0->nb[0], B200_ERR_INVALID);
+    B200_REQUIRE(ctx, same_shape(src0, dst) && src0->nb[0] == elt_size(src0->type) && dst->nb[0] == elt_size(dst->type), B200_ERR_INVALID);
     B200_REQUIRE(ctx, rp->n_dims > 0 && rp->n_dims % 2 == 0 && rp->n_dims <= src0->ne[0] && src0->ne[0] % 2 == 0, B200_ERR_INVALID);
     B200_REQUIRE(ctx, pos->ne[0] >= src0->ne[2] && pos->nb[0] == 4, B200_ERR_INVALID);
     const int64_t n = nelements(src0);
@@ -951,8 +953,9 @@ int b200_op_rope(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *pos,
     r.xpos_base = rp->xpos_base; r.xpos_down = rp->xpos_down;
     const T4 a = view(src0), d = view(dst);
     const int grid = grid_for(n / 2, 256, ctx->sm_count);
-    if (src0->type == B200_TYPE_F32) launch_k(ctx, rope_kernel<float>, grid, 256, a, d, static_cast<const int32_t *>(pos->data), r);
-    else launch_k(ctx, rope_kernel<__half>, grid, 256, a, d, static_cast<const int32_t *>(pos->data), r);
+    if (src0->type == B200_TYPE_F32 && dst->type == B200_TYPE_F16) launch_k(ctx, rope_kernel<float, __half>, grid, 256, a, d, static_cast<const int32_t *>(pos->data), r);
+    else if (src0->type == B200_TYPE_F32) launch_k(ctx, rope_kernel<float, float>, grid, 256, a, d, static_cast<const int32_t *>(pos->data), r);
+    else launch_k(ctx, rope_kernel<__half, __half>, grid, 256, a, d, static_cast<const int32_t *>(pos->data), r);
     return finish(ctx, "rope");
 }
 

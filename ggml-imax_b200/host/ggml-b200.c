@@ -513,6 +513,7 @@ struct b200_backend_context {
     int32_t  *use_cnt;
     size_t    use_size;
     int       use_valid;
+    int       graph_managed;   /* this graph_compute has seen the allocator place a node in a dead intermediate's memory: unflagged intermediates are not the caller's to read */
     /* REPEATs of a row whose only reader comes later in the graph: computed right before that reader unless it folds them in */
     struct ggml_tensor *deferred[B200_MAX_DEFERRED];
     int       n_deferred;
@@ -1002,17 +1003,73 @@ static int b200_try_fuse_norm_repeat(struct b200_backend_context *bc, struct ggm
     if (!b200_fill_tensor(x, &a) || !b200_fill_tensor(r1->src[0], &g) || !b200_fill_tensor(r3->src[0], &b) || !b200_fill_tensor(a4, &d)) return 0;
     b200_deferred_drop(bc, r1);
     b200_deferred_drop(bc, r3);
+    bc->graph_managed = 1;
     *st = b200_glue_status(bc, a4, b200_op_norm(bc->ctx, &a, &g, &b, &d, eps, n0->op == GGML_OP_RMS_NORM));
+    return n;
+}
+
+static int b200_next_real(const struct ggml_cgraph *cgraph, int j, int last) {
+    while (j < last && (ggml_is_empty(cgraph->nodes[j]) || b200_op_is_noop(cgraph->nodes[j]->op))) j++;
+    return j;
+}
+/* ROPE -> CPY into a contiguous F16 / F32 destination (the rotated k of a token into the KV cache, examples/gpt-j/main.cpp:473-484): the rotation
+ * writes the cache directly.  The F32 result is skipped, so nothing else may read it -- nor, when the ROPE is the in-place form, the memory it
+ * shares with the projection's output: every tensor up the chain of views to the producing node has exactly the next one as its reader. */
+static int b200_try_fuse_rope_cpy(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int i, int last, enum ggml_status *st) {
+    struct ggml_tensor *rope = cgraph->nodes[i];
+    if (!bc->opt_fuse || !bc->graph_managed || rope->op != GGML_OP_ROPE || rope->type != GGML_TYPE_F32 || !b200_glue_supported(rope)) return 0;
+    const int j = b200_next_real(cgraph, i + 1, last);
+    if (j >= last) return 0;
+    struct ggml_tensor *cp = cgraph->nodes[j];
+    if (cp->op != GGML_OP_CPY || cp->src[0] != rope || (cp->type != GGML_TYPE_F16 && cp->type != GGML_TYPE_F32) || !ggml_is_contiguous(cp) ||
+        ggml_nelements(cp) != ggml_nelements(rope) || !ggml_is_contiguous(rope) || cp->data == NULL || !b200_in_device_buffer(cp))
+        return 0;
+    const int n = j - i + 1;
+    if (!b200_uses_build(bc, cgraph) || !b200_read_only_by_group(bc, cgraph, rope, i, n)) return 0;
+    if (rope->data == rope->src[0]->data) {                 /* in place: the un-rotated values stay behind in that memory */
+        const struct ggml_tensor *chain[10], *t = rope->src[0];
+        int n_chain = 0;
+        chain[n_chain++] = rope;
+        while (t != NULL) {                                 /* (a view's view_src is the root of the chain, not its immediate parent: count every member) */
+            int refs = 0;
+            for (int k = 0; k < n_chain; k++) refs += b200_refs_from(chain[k], t);
+            if ((t->flags & GGML_TENSOR_FLAG_OUTPUT) || bc->use_cnt[b200_use_slot(bc, t)] != refs) return 0;
+            if (!b200_op_is_noop(t->op) || t->op == GGML_OP_NONE) break;         /* the producing node (or a leaf) */
+            if (n_chain == 10) return 0;
+            chain[n_chain++] = t;
+            t = t->src[0];
+        }
+    }
+    if (b200_ranges_overlap(cp, rope->src[0]) || b200_ranges_overlap(cp, rope->src[1])) return 0;
+    b200_tensor a, pos, d;
+    if (!b200_fill_tensor(rope->src[0], &a) || !b200_fill_tensor(rope->src[1], &pos)) return 0;
+    memset(&d, 0, sizeof(d));
+    d.type = (int32_t)cp->type;
+    d.data = cp->data;
+    const int64_t es = (int64_t)ggml_type_size(cp->type);
+    for (int k = 0; k < 4; k++) d.ne[k] = rope->ne[k];
+    d.nb[0] = es; d.nb[1] = d.nb[0] * d.ne[0]; d.nb[2] = d.nb[1] * d.ne[1]; d.nb[3] = d.nb[2] * d.ne[2];
+    const int32_t *op = (const int32_t *)rope->op_params;
+    b200_rope_params rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.n_dims = op[1]; rp.mode = op[2]; rp.n_ctx = op[3]; rp.n_orig_ctx = op[4];
+    memcpy(&rp.freq_base, op + 5, sizeof(float));
+    memcpy(&rp.freq_scale, op + 6, sizeof(float));
+    memcpy(&rp.ext_factor, op + 7, sizeof(float));
+    memcpy(&rp.attn_factor, op + 8, sizeof(float));
+    memcpy(&rp.beta_fast, op + 9, sizeof(float));
+    memcpy(&rp.beta_slow, op + 10, sizeof(float));
+    memcpy(&rp.xpos_base, op + 11, sizeof(float));
+    { bool down; memcpy(&down, op + 12, sizeof(bool)); rp.xpos_down = down ? 1 : 0; }
+    const int rc = b200_op_rope(bc->ctx, &a, &pos, &d, &rp);
+    if (rc == B200_ERR_UNSUPPORTED) return 0;
+    *st = b200_glue_status(bc, cp, rc);
     return n;
 }
 
 /* The attention of a decode step: MUL_MAT(K, Q) -> SCALE -> DIAG_MASK_INF -> SOFT_MAX (each in place of the one before) -> MUL_MAT(V, .) ->
  * PERMUTE(0, 2, 1, 3) -> CPY / CONT into a contiguous [n_embd][N] (examples/gpt-j/main.cpp:490-530, examples/gpt-2/main-backend.cpp:567-610), views
  * in between, as ONE launch (b200_op_attention_decode) under the reader-count rule above. */
-static int b200_next_real(const struct ggml_cgraph *cgraph, int j, int last) {
-    while (j < last && (ggml_is_empty(cgraph->nodes[j]) || b200_op_is_noop(cgraph->nodes[j]->op))) j++;
-    return j;
-}
 static int b200_try_fuse_attention(struct b200_backend_context *bc, struct ggml_cgraph *cgraph, int i, int last, enum ggml_status *st) {
     struct ggml_tensor *kq = cgraph->nodes[i];
     if (!bc->opt_fuse || kq->op != GGML_OP_MUL_MAT || kq->type != GGML_TYPE_F32) return 0;
@@ -1142,6 +1199,7 @@ static int b200_try_fuse_mul_mat_repeat(struct b200_backend_context *bc, struct 
     const int rc = b200_mul_mat_fused(bc->ctx, &args, &epi);
     if (rc == B200_ERR_UNSUPPORTED) return 0;          /* not a single-launch shape: the operators run one by one */
     if (rep) b200_deferred_drop(bc, rep);
+    bc->graph_managed = 1;
     *st = b200_glue_status(bc, mm, rc);
     return n;
 }
@@ -1681,6 +1739,7 @@ GGML_CALL static enum ggml_status b200_backend_graph_compute(ggml_backend_t back
         return GGML_STATUS_FAILED;
     }
     bc->use_valid = 0;
+    bc->graph_managed = 0;
     bc->n_deferred = 0;
     int i = 0;
     while (i < cgraph->n_nodes) {
@@ -1910,6 +1969,7 @@ static enum ggml_status b200_graph_compute_nodes(struct b200_backend_context *bc
             enum ggml_status st = GGML_STATUS_SUCCESS;
             if (node->op == GGML_OP_REPEAT && b200_try_defer_repeat(bc, cgraph, node)) continue;
             int fused = node->op == GGML_OP_MUL_MAT ? b200_try_fuse_attention(bc, cgraph, i, last, &st) : 0;
+            if (fused == 0 && node->op == GGML_OP_ROPE) fused = b200_try_fuse_rope_cpy(bc, cgraph, i, last, &st);
             if (fused == 0) fused = b200_try_fuse(bc, cgraph, i, last, &st);
             if (fused == 0) fused = b200_try_fuse_norm_repeat(bc, cgraph, i, last, &st);
             if (fused > 0) {

@@ -355,7 +355,8 @@ B200_API int b200_op_soft_max(b200_ctx *ctx, const b200_tensor *src0, const b200
  * both arbitrarily strided; F32 <-> F16 conversions, or any same-type pair of 2- / 4-byte elements (F32, F16, I32, I16) */
 B200_API int b200_op_copy(b200_ctx *ctx, const b200_tensor *src0, const b200_tensor *dst);
 /* GGML_OP_ROPE, forward (src/ggml.c:13775, :13953; op_params of ggml_rope_custom, src/ggml.c:5866-5889): src0 F32 or F16 [ne0][heads][tokens][b],
-   pos I32 [tokens].  mode bit 1 = NeoX pairing; bit 2 (GLM) is B200_ERR_UNSUPPORTED. */
+   pos I32 [tokens].  mode bit 1 = NeoX pairing; bit 2 (GLM) is B200_ERR_UNSUPPORTED.  dst has src0's type, or F16 for an F32 src0 (the CPY that
+   stores the rotated k into an F16 KV cache, examples/gpt-j/main.cpp:473-484, folded into the store: same bits as ROPE then CPY). */
 typedef struct b200_rope_params {
     int32_t n_dims, mode, n_ctx, n_orig_ctx;
     float   freq_base, freq_scale, ext_factor, attn_factor, beta_fast, beta_slow, xpos_base;

@@ -369,6 +369,12 @@ def test_rope(qmm, gpu_ctx, dtype, ne0, heads, n_dims, mode, yarn, xpos):
     a, tp = up(qmm, gpu_ctx, x), up(qmm, gpu_ctx, pos)
     dst = qmm.DTensor(gpu_ctx, ttype, [ne0, heads, T, B])
     gpu_ctx.op_rope(a, tp, dst, n_ctx=512, **kw)
+    if dtype == np.float32:                                          # the rotation stored as F16 == ROPE then CPY(F32 -> F16), bit for bit
+        h1, h2 = qmm.DTensor(gpu_ctx, qmm.TYPE_F16, [ne0, heads, T, B]), qmm.DTensor(gpu_ctx, qmm.TYPE_F16, [ne0, heads, T, B])
+        gpu_ctx.op_rope(a, tp, h1, n_ctx=512, **kw)
+        gpu_ctx.op_copy(dst, h2)
+        gpu_ctx.synchronize()
+        assert np.array_equal(h1.numpy(), h2.numpy())
     gpu_ctx.op_rope(a, tp, a, n_ctx=512, **kw)                       # ggml_rope_inplace
     gpu_ctx.synchronize()
     got, got_inplace = dst.numpy().reshape(x.shape), a.numpy().reshape(x.shape)
