@@ -1,4 +1,4 @@
-// b200_gemm_f16.cu -- the prefill path (n >= 32): dst[n][m] = W[m,k] x X[n,k]^T as ONE dense contraction on the 5th-generation
+// b200_gemm_f16.cu -- the prefill path (every n the GEMV does not take): dst[n][m] = W[m,k] x X[n,k]^T as ONE dense contraction on the 5th-generation
 // tensor cores, fp16 operands, fp32 accumulation in TMEM.
 //
 // Stands in for the COMPUTE phase of ggml_compute_forward_mul_mat (src/ggml.c:12056-12096) for prefill-sized batches, the way the

@@ -11,7 +11,11 @@ static bool use_gemm(const b200_ctx *ctx, const b200_mul_mat_args *a) {
     if (!b200_gemm_available()) return false;
     if (a->flags & B200_MM_FORCE_GEMM) return true;
     if (!ctx->opt_gemm) return false;
-    return a->ne11 > ctx->opt_gemv_max_n;
+    if (a->ne11 > ctx->opt_gemv_max_n) return true;
+    // The streaming GEMV keeps its quantized activation columns in shared memory next to the weight ring; past n * k of 64 KB (Q4_0) /
+    // 32 KB (Q8_0: twice the ring bytes per row) it falls back to the generic kernel, and the tensor-core path -- its columns padded to
+    // one tile -- is as fast or faster from there on (profiles/r02_sweep_n.log: 4096 x 16384 Q4_0, n = 8: 96 us against 48 us).
+    return a->ne11 >= 2 && a->ne11 * a->ne00 >= (a->type == B200_TYPE_Q8_0 ? 32768 : 65536);
 }
 
 static int run_gemv_chunks(b200_ctx *ctx, const b200_mul_mat_args *a, const uint8_t *qs, const __half *d, const b200_epilogue *epi = nullptr) {
@@ -60,9 +64,10 @@ size_t b200_prefill_ws_bytes(int type, int64_t k, int64_t m, int64_t n) {
     return exact > f16 ? exact : f16;
 }
 
-// n at which the fp16 tensor-core contraction takes over from the exact per-block kernel (its 256-column tiles are mostly
-// padding below that)
-static const int64_t kGemmF16MinN = 32;
+// n at which the fp16 tensor-core contraction takes over from the exact per-block kernel.  It was 32 ("the 256-column tiles are mostly
+// padding below that") until the sweep over n showed the exact kernel taking 67 us on 4096 x 4096 at n = 31 where the fp16 one takes
+// 29 us at n = 32 (profiles/r02_sweep_n.log): padding costs nothing next to streaming and dequantizing the weights.
+static const int64_t kGemmF16MinN = 1;
 
 static int run_gemm_f16(b200_ctx *ctx, const b200_mul_mat_args *a, const uint8_t *qs, const __half *d) {
     const int64_t k = a->ne00, m = a->ne01, n = a->ne11, nb = k / 32;

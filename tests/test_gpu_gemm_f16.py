@@ -1,4 +1,4 @@
-"""The default prefill path for n >= 32 (b200_gemm_f16.cu): weights dequantized to fp16 inside the kernel, Q8_0-quantized activations
+"""The default path for every n the GEMV does not take (n > 8, or fewer columns of a long row: b200_gemm_f16.cu): weights dequantized to fp16 inside the kernel, Q8_0-quantized activations
 as fp16, ONE dense contraction with fp32 accumulation on the tensor cores (tcgen05 cta_group::2, a CTA pair per 256 x 256 tile,
 persistent, tail tiles split along k) -- what the reference's CUDA backend does for large batches (ggml_cuda_op_mul_mat_cublas,
 src/ggml-cuda.cu:1208-1306).  Bounds: NMSE <= 5e-4 against the oracle is the reference's bar (tests/test-backend-ops.cpp:921-923);
@@ -19,6 +19,8 @@ SHAPES = [
     (16384, 4096, 512), (4096, 16384, 128),        # GPT-J fc_in / fc_out
     (20000, 512, 700),                             # several full rounds, ragged n, short k (no split possible)
     (2304, 768, 128), (50257 // 8, 768, 128),      # GPT-2 qkv and (a slice of) lm_head at the 128-token prompt
+    (4096, 4096, 9), (300, 256, 17), (4096, 16384, 31), (1000, 96, 12),      # short prompts: a few columns of one padded tile
+    (4096, 16384, 4), (16384, 4096, 8),            # the columns at which the GEMV's activations stop fitting beside its weight ring (Q8_0: also 16384 x 4096 x 8)
 ]
 
 

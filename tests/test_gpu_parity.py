@@ -127,8 +127,8 @@ def test_block_dots_gemm_bit_exact(gpu_ctx, qmm, oracle, qtype, m, k, n):
                                    (257, 736, 129), (50257 // 16, 768, 128)])
 def test_mul_mat_gemm_vs_oracle(gpu_ctx, qmm, oracle, qtype, m, k, n):
     """Prefill shapes through the tensor-core GEMMs (forced, so small n is covered too): the exact kernel (int8 MMA per quant
-    block, fp32 scaling: only the summation order differs from the oracle) and the default, which from n = 32 up is the fp16
-    contraction (operands rounded once to fp16: NMSE ~1e-7, bound 1e-6 here against the reference's 5e-4)."""
+    block, fp32 scaling: only the summation order differs from the oracle) and the default, the fp16 contraction (operands rounded
+    once to fp16: NMSE ~1e-7, bound 1e-6 here against the reference's 5e-4) at every n since profiles/r02_sweep_n.log."""
     t, wire = make_w(oracle, qmm, gpu_ctx, qtype, m, k, seed=m * 3 + k + n)
     rng = np.random.default_rng(m + n + 2)
     x = rng.uniform(-1, 1, (n, k)).astype(np.float32)
@@ -141,7 +141,7 @@ def test_mul_mat_gemm_vs_oracle(gpu_ctx, qmm, oracle, qtype, m, k, n):
         gpu_ctx.set_option("gemm_exact", 0)
         got16 = gpu_ctx.mul_mat(t, x, flags=qmm.MM_FORCE_GEMM)
         err16 = nmse(got16, ref)
-        assert np.all(np.isfinite(got16)) and err16 <= MUL_MAT_NMSE_TOL and err16 <= (F16_GEMM_NMSE if n >= 32 else 1e-9), err16
+        assert np.all(np.isfinite(got16)) and err16 <= MUL_MAT_NMSE_TOL and err16 <= F16_GEMM_NMSE, err16
     finally:
         gpu_ctx.set_option("gemm_exact", 0)
         t.free()
@@ -161,7 +161,7 @@ def test_mul_mat_golden_cases(gpu_ctx, qmm, golden):
         assert np.all(np.isfinite(got))
         err = nmse(got, ref)
         assert err <= MUL_MAT_NMSE_TOL, f"case {ci} {(t, m, n, k, bs0, bs1, nr0, nr1)}: nmse {err}"
-        assert err <= (1e-9 if n < 32 else F16_GEMM_NMSE), f"case {ci}: only fp32 summation order (n < 32) / one fp16 rounding per operand may differ, nmse {err}"
+        assert err <= (1e-9 if n <= 8 and n * k < 32768 else F16_GEMM_NMSE), f"case {ci}: only fp32 summation order (GEMV) / one fp16 rounding per operand (tensor-core path) may differ, nmse {err}"
         w.free()
 
 
@@ -180,10 +180,12 @@ def test_mul_mat_vs_oracle(gpu_ctx, qmm, oracle, qtype, m, k, n):
             for flags in (0, qmm.MM_FORCE_GEMV):
                 got = gpu_ctx.mul_mat(t, x, flags=flags)
                 err = nmse(got, ref)
-                assert err <= MUL_MAT_NMSE_TOL and err <= 1e-9, (stream, flags, err)
+                # the default dispatch leaves the GEMV (fp32 summation order only) for the fp16 tensor-core path past 8 columns
+                bound = 1e-9 if flags == qmm.MM_FORCE_GEMV or (n <= 8 and n * k < 32768) else F16_GEMM_NMSE
+                assert err <= MUL_MAT_NMSE_TOL and err <= bound, (stream, flags, err)
     finally:
         gpu_ctx.set_option("gemv_stream", 1)
-    assert nmse(gpu_ctx.mul_mat_host(t, x), ref) <= 1e-9
+    assert nmse(gpu_ctx.mul_mat_host(t, x), ref) <= (1e-9 if n <= 8 and n * k < 32768 else F16_GEMM_NMSE)
     t.free()
 
 
@@ -295,7 +297,7 @@ def test_full_size_properties(gpu_ctx, qmm, oracle, qtype, m, k, n):
     cols = np.unique(np.concatenate([[0, n - 1], rng.integers(0, n, 6)]))
     ref = oracle.mul_mat(qtype, np.ascontiguousarray(wire[rows]), k, len(rows), 1, 1, np.ascontiguousarray(x[cols])[None, None])[0, 0]
     sub = y1[np.ix_(cols, rows)]
-    assert nmse(sub, ref) <= MUL_MAT_NMSE_TOL and nmse(sub, ref) <= (1e-8 if n < 32 else F16_GEMM_NMSE)
+    assert nmse(sub, ref) <= MUL_MAT_NMSE_TOL and nmse(sub, ref) <= (1e-8 if n <= 8 and n * k < 32768 else F16_GEMM_NMSE)
     back = t.get()
     assert int(back.astype(np.uint64).sum()) == int(wire.astype(np.uint64).sum()) and np.array_equal(back[:4096], wire.ravel()[:4096])
     t.free()
