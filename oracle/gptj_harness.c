@@ -268,9 +268,19 @@ int main(int argc, char **argv) {
         const enum ggml_status stc = ggml_backend_graph_compute_async(gpu, Gc.gf);
         const double ms_enqueue = (double)(ggml_time_us() - t0) / 1e3;
         ggml_backend_synchronize(gpu);
-        const double ms_b200 = (double)(ggml_time_us() - t0) / 1e3;
+        double ms_b200 = (double)(ggml_time_us() - t0) / 1e3;
         if (stc != GGML_STATUS_SUCCESS) { printf("], \"error\": \"B200 graph_compute failed (%d)\"}\n", (int)stc); return 6; }
-        const long long launches = (long long)(ggml_backend_b200_launch_count(gpu) - l0);
+        long long launches = (long long)(ggml_backend_b200_launch_count(gpu) - l0);
+        double ms_b200_first = ms_b200;
+        if (N > 1) {       /* the prompt once more: the first call of a new shape also pays for module loading, scratch growth and kernel attributes */
+            ggml_backend_tensor_set(Gc.tokens, tokens + n_past, 0, sizeof(int32_t) * (size_t)N);
+            ggml_backend_tensor_set(Gc.positions, pos, 0, sizeof(int32_t) * (size_t)N);
+            const int64_t l1 = ggml_backend_b200_launch_count(gpu);
+            t0 = ggml_time_us();
+            if (ggml_backend_graph_compute(gpu, Gc.gf) != GGML_STATUS_SUCCESS) { printf("], \"error\": \"B200 graph_compute (second prompt run) failed\"}\n"); return 6; }
+            ms_b200 = (double)(ggml_time_us() - t0) / 1e3;
+            launches = (long long)(ggml_backend_b200_launch_count(gpu) - l1);
+        }
         ggml_backend_tensor_get(Gc.logits, lc, (size_t)(N - 1) * hp.n_vocab * sizeof(float), sizeof(float) * (size_t)hp.n_vocab);
         /* the same decode step as a graph plan: node by node once, recorded once, then replayed */
         double ms_plan = 0.0;
@@ -309,9 +319,9 @@ int main(int argc, char **argv) {
         int fin = 1;
         for (int i = 0; i < hp.n_vocab; i++) if (!isfinite(lc[i]) || !isfinite(la[i])) fin = 0;
         if (!(e <= 5e-4) || !fin) ok = 0;
-        printf("%s{\"n_past\": %d, \"n\": %d, \"taps_nmse_vs_cpu\": %.3e, \"logits_nmse_vs_cpu\": %.3e, \"finite\": %s, \"ms_cpu\": %.2f, \"ms_b200\": %.3f, \"ms_b200_enqueue\": %.3f, "
+        printf("%s{\"n_past\": %d, \"n\": %d, \"taps_nmse_vs_cpu\": %.3e, \"logits_nmse_vs_cpu\": %.3e, \"finite\": %s, \"ms_cpu\": %.2f, \"ms_b200\": %.3f, \"ms_b200_first_call\": %.3f, \"ms_b200_enqueue\": %.3f, "
                "\"b200_launches\": %lld, \"graph_nodes\": %d, \"ms_b200_graph_plan\": %.3f, \"graph_plan_kernels\": %lld, \"graph_plan_equals_node_by_node\": %s}",
-               step ? ", " : "", n_past, N, e_tap, e, fin ? "true" : "false", ms_cpu, ms_b200, ms_enqueue, launches, Gc.gf->n_nodes, ms_plan, plan_kernels,
+               step ? ", " : "", n_past, N, e_tap, e, fin ? "true" : "false", ms_cpu, ms_b200, ms_b200_first, ms_enqueue, launches, Gc.gf->n_nodes, ms_plan, plan_kernels,
                plan_equal ? "true" : "false");
         fflush(stdout);
         n_past += N;

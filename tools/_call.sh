@@ -1,5 +1,8 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_gemm_f16.py tests/test_gpu_parity.py -q > gpurun_out/r02_smalln_tests.log 2>&1; tail -5 gpurun_out/r02_smalln_tests.log
-for shape in "4096 4096 16" "11008 4096 512"; do echo "== $shape"; timeout 200 python tools/gemm_timeline.py q4_0 $shape 2>&1 | tail -9; done > gpurun_out/r02_gemm_timeline_smalln_after.log
-cat gpurun_out/r02_gemm_timeline_smalln_after.log | cut -c1-200
-timeout 600 python tools/time_gemm.py 2>&1 | tail -3
+for np in 8 32 128; do timeout 600 oracle/_ref/gptj-harness q4_0 28 4096 16 64 50400 2048 $np 2 $(nproc) > gpurun_out/r02_gptj_6b_p$np.json 2> gpurun_out/r02_gptj_6b.err; python - <<PY
+import json
+r=json.load(open('gpurun_out/r02_gptj_6b_p$np.json'))
+for s in r['steps']: print({k:s[k] for k in ('n','logits_nmse_vs_cpu','ms_cpu','ms_b200','ms_b200_first_call','ms_b200_graph_plan','b200_launches')})
+print(r['ok'])
+PY
+done
