@@ -879,8 +879,13 @@ static int b200_refs_from(const struct ggml_tensor *node, const struct ggml_tens
 static bool b200_uses_build(struct b200_backend_context *bc, const struct ggml_cgraph *g) {
     if (bc->use_valid) return true;
     if (g->visited_hash_table.size == 0 || g->visited_hash_table.keys == NULL) return false;      /* a ggml_graph_view: readers may be elsewhere */
+    size_t refs = 0;                                      /* an upper bound of the distinct tensors that get an entry */
+    for (int i = 0; i < g->n_nodes; i++) {
+        for (int k = 0; k < GGML_MAX_SRC; k++) refs += g->nodes[i]->src[k] != NULL;
+        refs += g->nodes[i]->view_src != NULL;
+    }
     size_t want = 1024;
-    while (want < (size_t)g->n_nodes * 8) want <<= 1;
+    while (want < refs * 2 + 16) want <<= 1;              /* open addressing: never more than half full */
     if (want > bc->use_size) {
         free(bc->use_keys);
         free(bc->use_cnt);
