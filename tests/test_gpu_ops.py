@@ -495,3 +495,21 @@ def test_attention_decode_declines_long_contexts(qmm, gpu_ctx):
     with pytest.raises(qmm.B200Error) as e:
         gpu_ctx.op_attention_decode(q, k, v, d, 1.0, 1024)
     assert e.value.code == qmm.ERR_UNSUPPORTED
+
+
+def test_rope_on_strided_rows(qmm, gpu_ctx):
+    """ROPE reads and writes through the tensors' strides: q of a fused qkv projection is a column slice (row pitch 3 * n_embd), the result goes to a dense tensor"""
+    rng = np.random.default_rng(3)
+    hd, H, T = 64, 6, 5
+    E = hd * H
+    qkv = rng.uniform(-1, 1, (T, 3 * E)).astype(np.float32)
+    pos = np.arange(7, 7 + T, dtype=np.int32)
+    t = up(qmm, gpu_ctx, qkv)
+    k_view = t.view([hd, H, T, 1], [4, 4 * hd, 4 * 3 * E, 4 * 3 * E * T], offset=4 * E)           # the k third of every row
+    dst = qmm.DTensor(gpu_ctx, qmm.TYPE_F32, [hd, H, T, 1])
+    gpu_ctx.op_rope(k_view, up(qmm, gpu_ctx, pos), dst, n_dims=hd, mode=2, n_ctx=64)
+    gpu_ctx.synchronize()
+    x = qkv[:, E:2 * E].reshape(1, T, H, hd)
+    want = rope_numpy(np.ascontiguousarray(x), pos, n_dims=hd, mode=2, n_orig_ctx=0, freq_base=10000.0, freq_scale=1.0, ext_factor=0.0, attn_factor=1.0,
+                      beta_fast=0.0, beta_slow=0.0)
+    assert nmse(dst.numpy().reshape(1, T, H, hd).astype(np.float64), want.astype(np.float64)) <= 1e-10
