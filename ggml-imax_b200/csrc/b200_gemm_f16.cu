@@ -555,8 +555,13 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
 // F32 activations -> X'[n][k] fp16 = fp16_rn(q * d) of their Q8_0 quantization (quantize_row_q8_0, src/ggml-quants.c:535-618,
 // same explicitly rounded arithmetic as b200_quantize.cu), written in the k-order of the operand tiles: within every aligned
 // group of four the order is (0, 2, 1, 3).  8 lanes per block, one 128-bit load and one 64-bit store per lane.
-__global__ void __launch_bounds__(256) quantize_to_f16_kernel(const float *__restrict__ x, int64_t k, int64_t nrows, size_t row_stride, __half *__restrict__ out) {
+__global__ void __launch_bounds__(256) quantize_to_f16_kernel(const float *__restrict__ x, int64_t k, int64_t nrows, size_t row_stride, __half *__restrict__ out,
+                                                              uint32_t *__restrict__ counters, int n_counters) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // the GEMM may take the SMs as they free up (it waits for X' itself)
+    // the split-k arrival counters of the GEMM behind: zeroed here rather than by a memset between the two kernels, which would make the
+    // GEMM the programmatic dependent of a copy-engine node instead of this grid (the GEMM touches them only after its griddepcontrol.wait)
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < n_counters; i += blockDim.x) counters[i] = 0u;
     const int64_t nb = k / 32;
     const int64_t total = nrows * nb * 8;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)b200_align_up((size_t)total, 32); t += (int64_t)gridDim.x * blockDim.x) {
@@ -658,11 +663,10 @@ int b200_launch_gemm_f16(b200_ctx *ctx, int type, const uint8_t *qs, const __hal
         int64_t grid = (total + 255) / 256;
         const int64_t cap = (int64_t)ctx->sm_count * 16;
         if (grid > cap) grid = cap;
-        quantize_to_f16_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(x, k, n, x_row_stride, xp);
+        quantize_to_f16_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(x, k, n, x_row_stride, xp, counters, sc.rem);
         ctx->launches++;
         B200_CUDA_TRY(ctx, cudaGetLastError());
     }
-    if (sc.rem > 0) B200_CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, (size_t)sc.rem * 4, ctx->stream));
     CUtensorMap map_raw, map_b, map_raw_pf, map_dw_pf;
     B200_REQUIRE(ctx, ((uintptr_t)qs & 15) == 0 && ((uintptr_t)d & 1) == 0, B200_ERR_UNSUPPORTED);
     const bool dw_pf = (nb * 2) % 16 == 0 && nb >= 16 && ((uintptr_t)d & 15) == 0;

@@ -1,9 +1,13 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_ops.py -q -x > gpurun_out/r02_gemv_ncols_tests.log 2>&1; tail -4 gpurun_out/r02_gemv_ncols_tests.log
-ncu --metrics gpu__time_duration.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum --clock-control none -k regex:gemv_stream --csv --log-file gpurun_out/r02_gemv_ncols_after.csv python tools/_gemv8_once.py > gpurun_out/ncu_gemv8.log 2>&1
-python - <<'PY'
-import csv,re
-lines=[l for l in open('gpurun_out/r02_gemv_ncols_after.csv') if l.startswith('"')]
-for x in csv.DictReader(lines):
-    print(re.sub(r'\(.*','',x['Kernel Name'])[-40:], x['Metric Name'], x['Metric Value'])
+timeout 1500 python -m pytest tests/test_gpu_gemm_f16.py tests/test_gpu_parity.py -q -x > gpurun_out/r02_gemm_counters_tests.log 2>&1; tail -3 gpurun_out/r02_gemm_counters_tests.log
+timeout 600 python tools/time_gemm.py 2>&1 | tail -2
+timeout 600 python tools/stress_gemm.py 2>&1 | tail -3
+timeout 900 python tools/sweep_n.py 2>&1 | head -1 | cut -c1-700
+python bench.py --no-cpu-baseline > gpurun_out/r02_bench_counters.json 2> gpurun_out/r02_bench_counters.err; python - <<'PY'
+import json
+r=json.loads(open('gpurun_out/r02_bench_counters.json').read().strip().splitlines()[-1])
+x=r['extra']
+print(r['value'], r['roofline']['frac'])
+for k in ('c2_gemm_q4_0_m11008_k4096_n512','c2_gemm_q8_0_m11008_k4096_n512','gptj6b_q4_0_prefill_512_tokens'):
+    print(k, {kk:vv for kk,vv in x[k].items() if kk in ('us_per_mul_mat','TFLOP/s','ms','prompt_tokens/s')})
 PY
