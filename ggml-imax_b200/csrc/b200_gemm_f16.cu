@@ -558,6 +558,7 @@ gemm_f16_pair_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_c
 __global__ void __launch_bounds__(256) quantize_to_f16_kernel(const float *__restrict__ x, int64_t k, int64_t nrows, size_t row_stride, __half *__restrict__ out,
                                                               uint32_t *__restrict__ counters, int n_counters) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // the GEMM may take the SMs as they free up (it waits for X' itself)
+    asm volatile("griddepcontrol.wait;" ::: "memory");                  // this grid's own launch overlaps the kernel in front; x, X' and the counters are that kernel's until here
     // the split-k arrival counters of the GEMM behind: zeroed here rather than by a memset between the two kernels, which would make the
     // GEMM the programmatic dependent of a copy-engine node instead of this grid (the GEMM touches them only after its griddepcontrol.wait)
     if (blockIdx.x == 0)
@@ -663,7 +664,17 @@ int b200_launch_gemm_f16(b200_ctx *ctx, int type, const uint8_t *qs, const __hal
         int64_t grid = (total + 255) / 256;
         const int64_t cap = (int64_t)ctx->sm_count * 16;
         if (grid > cap) grid = cap;
-        quantize_to_f16_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(x, k, n, x_row_stride, xp, counters, sc.rem);
+        cudaLaunchConfig_t qcfg;
+        memset(&qcfg, 0, sizeof(qcfg));
+        qcfg.gridDim = dim3((unsigned)grid, 1, 1);
+        qcfg.blockDim = dim3(256, 1, 1);
+        qcfg.stream = ctx->stream;
+        cudaLaunchAttribute qattr[1];
+        qattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        qattr[0].val.programmaticStreamSerializationAllowed = 1;
+        qcfg.attrs = qattr;
+        qcfg.numAttrs = ctx->opt_pdl ? 1 : 0;
+        B200_CUDA_TRY(ctx, cudaLaunchKernelEx(&qcfg, quantize_to_f16_kernel, x, k, n, x_row_stride, xp, counters, (int)sc.rem));
         ctx->launches++;
         B200_CUDA_TRY(ctx, cudaGetLastError());
     }

@@ -1,11 +1,10 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_gemm_f16.py tests/test_gpu_parity.py -q -x > gpurun_out/r02_gemm_counters_tests.log 2>&1; tail -3 gpurun_out/r02_gemm_counters_tests.log
+timeout 1500 python -m pytest tests/test_gpu_gemm_f16.py -q -x > gpurun_out/r02_gemm_counters_tests.log 2>&1; tail -3 gpurun_out/r02_gemm_counters_tests.log
 timeout 600 python tools/time_gemm.py 2>&1 | tail -2
-timeout 600 python tools/stress_gemm.py 2>&1 | tail -3
-timeout 900 python tools/sweep_n.py 2>&1 | head -1 | cut -c1-700
-python bench.py --no-cpu-baseline > gpurun_out/r02_bench_counters.json 2> gpurun_out/r02_bench_counters.err; python - <<'PY'
+for t in q4_0; do for shape in "11008 4096 512" "4096 4096 16"; do timeout 300 python tools/stress_gemm.py $t $shape 100 2>&1 | tail -1; done; done
+python bench.py --no-cpu-baseline > gpurun_out/r02_bench_counters2.json 2> gpurun_out/r02_bench_counters2.err; python - <<'PY'
 import json
-r=json.loads(open('gpurun_out/r02_bench_counters.json').read().strip().splitlines()[-1])
+r=json.loads(open('gpurun_out/r02_bench_counters2.json').read().strip().splitlines()[-1])
 x=r['extra']
 print(r['value'], r['roofline']['frac'])
 for k in ('c2_gemm_q4_0_m11008_k4096_n512','c2_gemm_q8_0_m11008_k4096_n512','gptj6b_q4_0_prefill_512_tokens'):
