@@ -1,13 +1,3 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_gptj_graph.py tests/test_gpu_gpt2_sched.py tests/test_gpu_parity.py tests/test_gpu_dropin_graph.py -q -x > gpurun_out/r02_hint_tests.log 2>&1; tail -3 gpurun_out/r02_hint_tests.log
-for f in 1 0; do timeout 600 oracle/_ref/gptj-harness q4_0 28 4096 16 64 50400 2048 8 3 $(nproc) $f > gpurun_out/r02_gptj_hint_$f.json 2> gpurun_out/r02_gptj_6b.err; python - <<PY
-import json
-r=json.load(open('gpurun_out/r02_gptj_hint_$f.json'))
-print('fuse=$f', [(s['n'], s['ms_b200'], s['ms_b200_graph_plan'], s['b200_launches']) for s in r['steps']], r['ok'])
-PY
-done
-timeout 300 oracle/_ref/gpt2-sched-harness q4_0 128 3 8 1 0 > gpurun_out/r02_gpt2_plan.json; python - <<'PY'
-import json
-r=json.load(open('gpurun_out/r02_gpt2_plan.json'))
-print([(s['n'], s['ms_b200_whole_graph'], s['ms_b200_graph_plan']) for s in r['steps']])
-PY
+for shape in "4096 4096 512" "16384 4096 512" "4096 16384 512"; do echo "== $shape"; timeout 200 python tools/gemm_timeline.py q4_0 $shape 2>&1 | tail -9; done > gpurun_out/r02_gemm_timeline_gptj_shapes.log
+cat gpurun_out/r02_gemm_timeline_gptj_shapes.log | cut -c1-160
