@@ -275,8 +275,8 @@ int main(int argc, char **argv) {
             const int reps = 20;
             for (int r = 0; r < 3 + reps; r++) {
                 if (r == 3) { ggml_backend_synchronize(gpu); t0 = ggml_time_us(); }
-                ggml_backend_tensor_set(Gc.tokens, tokens + n_past, 0, sizeof(int32_t));
-                ggml_backend_tensor_set(Gc.positions, pos, 0, sizeof(int32_t));
+                ggml_backend_tensor_set_async(gpu, Gc.tokens, tokens + n_past, 0, sizeof(int32_t));       /* on the backend's stream, in front of the replay */
+                ggml_backend_tensor_set_async(gpu, Gc.positions, pos, 0, sizeof(int32_t));
                 if (ggml_backend_graph_plan_compute(gpu, gplan) != GGML_STATUS_SUCCESS) { printf("], \"error\": \"graph_plan_compute failed\"}\n"); return 7; }
                 ggml_backend_synchronize(gpu);
             }
