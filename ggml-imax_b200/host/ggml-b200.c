@@ -1106,7 +1106,7 @@ static int b200_try_fuse_attention(struct b200_backend_context *bc, struct ggml_
     if (pv->op != GGML_OP_MUL_MAT || pv->src[1] != sm || pv->type != GGML_TYPE_F32 || !ggml_is_contiguous(pv)) return 0;
     const struct ggml_tensor *V = pv->src[0];
     if (!V || (V->type != GGML_TYPE_F32 && V->type != GGML_TYPE_F16) || V->ne[0] != T || V->ne[1] != hd || V->ne[2] != H || V->ne[3] != 1 ||
-        V->nb[0] != ggml_type_size(V->type) || !b200_in_device_buffer(V) || b200_tensor_is_split(V))
+        V->nb[0] != ggml_type_size(V->type) || !b200_in_device_buffer(V) || b200_tensor_is_split(V) || b200_deferred_index(bc, V) >= 0)
         return 0;
     j = b200_next_real(cgraph, j + 1, last);
     if (j >= last) return 0;
