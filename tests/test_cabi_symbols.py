@@ -62,6 +62,19 @@ def test_backend_library_exports():
         assert s in exp, s
 
 
+def test_backend_library_exports_every_symbol_of_its_header():
+    """host/ggml-b200.h (what an application includes next to ggml-backend.h): every declared entry point is exported"""
+    lib = PKG / "lib" / "libggml-b200-backend.so"
+    if not lib.exists():
+        pytest.skip("backend library needs the reference headers at build time")
+    text = re.sub(r"/\*.*?\*/", "", (PKG / "host" / "ggml-b200.h").read_text(), flags=re.S)
+    declared = sorted(set(re.findall(r"\b(ggml_backend_b200_\w+)\s*\(", text)))
+    assert len(declared) >= 12 and "ggml_backend_b200_graph_plan_kernels" in declared and "ggml_backend_b200_split_buffer_type" in declared
+    exp = exported(lib)
+    missing = [d for d in declared if d not in exp]
+    assert not missing, missing
+
+
 def test_product_does_not_reference_oracle():
     """No file of the product tree may include, link or call anything under oracle/."""
     for p in list((PKG / "csrc").glob("*")) + list((PKG / "host").glob("*")) + [PKG / "qmm.py", PKG / "Makefile", HEADER]:
